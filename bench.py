@@ -1,0 +1,270 @@
+#!/usr/bin/env python
+"""Headline benchmark of the TransformerCVN hot path (BASELINE.json: events/s).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--events B] [--precision bf16|fp32]
+
+A "step" = one pass of the hot path over one synthetic batch: COO hits -> densify (/255 fused) ->
+DenseNet(event maps) + DenseNet(prong maps) -> tokens -> 6-layer encoder -> event/prong logits.
+N=1 workload = BASELINE.json configs[1]: eval-mode inference over 256 events (P ~ U[1,10] prongs each,
+3x400x280 maps at 1 % / 0.2 % occupancy).  N>1: every rank runs its own 256-event shard
+(events are independent in inference: no data-path collective, weak scaling).
+
+  value  events/s with the COO hit lists already resident in HBM (CUDA events, max over ranks)
+  e2e    the same step driven from pinned HOST buffers: H2D of the hit lists and D2H of the logits inside
+         the timed region
+  roofline      dominant kernel (the 3x3 bottleneck convolution of dense block 1) timed alone with CUDA events
+  cpu_baseline  the oracle port of the reference's PyTorch CPU path on a bounded sample of the same workload
+--impl reference times that CPU path alone (rank 0 only), with all host threads.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "events/sec (event + prong 3x400x280 maps), inference"
+UNIT = "events/s"
+H, W = 400, 280
+GFLOP_PER_IMAGE_FWD = 4.971  # SURVEY.md §8(d), forward hooks on the reference DenseNet
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+                "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def make_inputs(events: int, seed: int):
+    from dune_transformercvn_b200 import synth
+    return synth.make_batch(events, seed=seed, max_prongs=10)
+
+
+def oracle_state_and_opts():
+    from dune_transformercvn_b200 import synth
+    from dune_transformercvn_b200.config import NUM_EVENT_CLASSES, NUM_PRONG_CLASSES, PathOptions
+    from dune_transformercvn_b200.params import network_specs
+    opts = PathOptions.tutorial()
+    specs = network_specs(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES)
+    return synth.init_state(specs, seed=0, perturb=False), opts
+
+
+def time_cpu_reference(sample_events: int, steps: int, warmup: int, seed: int):
+    """The reference's CPU path (oracle port: the reference tree itself is absent on the GPU box)."""
+    from oracle import restate
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    state, opts = oracle_state_and_opts()
+    batch = make_inputs(sample_events, seed)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            restate.sparse_forward(state, opts, batch)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    mean = sum(times) / len(times)
+    sample = (f"{sample_events} events / {sample_events + batch.num_prongs} images per step, eval forward incl. densify, "
+              f"fp32 torch CPU, {steps} timed steps")
+    return sample_events / mean, mean * 1e3, cores, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_events = 8
+    steps = max(1, min(args.steps, 5))
+    warmup = 1 if args.warmup > 0 else 0
+    value, ms, cores, sample = time_cpu_reference(sample_events, steps, warmup, 1234)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"BASELINE configs[1]: eval inference, {args.events} events/GPU, P~U[1,10], 3x400x280",
+                       "note": "CPU arm runs a bounded sample per step"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from dune_transformercvn_b200 import lib as tl
+    from dune_transformercvn_b200 import synth
+    from dune_transformercvn_b200.config import NUM_EVENT_CLASSES, NUM_PRONG_CLASSES, PathOptions
+    from dune_transformercvn_b200.ingest import densify
+    from dune_transformercvn_b200.network import NeutrinoDenseNetwork
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (ours) needs a CUDA device: there is no CPU path"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    tl.load()
+
+    opts = PathOptions.tutorial()
+    net = NeutrinoDenseNetwork(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES, precision=args.precision)
+    net = net.to(dev).eval()
+    batch = make_inputs(args.events, 1234 + rank)
+    images = batch.num_events + batch.num_prongs
+    host = batch.pin()
+    resident = batch.to(dev)
+    ev_buf = torch.empty((batch.num_events, 3, H, W), dtype=torch.float32, device=dev)
+    pr_buf = torch.empty((batch.num_prongs, 3, H, W), dtype=torch.float32, device=dev)
+    out_host = (torch.empty((batch.num_events, NUM_EVENT_CLASSES)).pin_memory(),
+                torch.empty((batch.num_events, batch.prong_mask.shape[1], NUM_PRONG_CLASSES)).pin_memory())
+
+    def step(b):
+        ev = densify(b.event_values, b.event_coords, (H, W), batch.num_events, 255.0, out=ev_buf)
+        pr = densify(b.prong_values, b.prong_coords, (H, W), batch.num_prongs, 255.0, out=pr_buf)
+        return net(b.features, b.extra, ev, b.event_mask, pr, b.prong_mask)
+
+    def step_e2e():
+        b = host.to(dev, non_blocking=True)
+        ev, pr = step(b)
+        out_host[0].copy_(ev, non_blocking=True)
+        out_host[1].copy_(pr, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    with torch.no_grad():
+        net.freeze_packed(False)
+        for _ in range(max(args.warmup, 3)):
+            step(resident)
+        net.freeze_packed(True)
+        sampler = ClockSampler(local)
+        sampler.start()
+        ms = timed(lambda: step(resident), args.steps)
+        sampler.stop_flag.set()
+        for _ in range(2):
+            step_e2e()
+        ms_e2e = timed(step_e2e, args.steps)
+    sampler.join(timeout=2)
+    value = world * args.events * args.steps / (ms / 1e3)
+    e2e_value = world * args.events * args.steps / (ms_e2e / 1e3)
+    h2d = host.nbytes()
+    d2h = sum(t.numel() * t.element_size() for t in out_host)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    total_images = images  # per rank; every rank has the same expected count
+    tflops = total_images * GFLOP_PER_IMAGE_FWD * 1e9 * args.steps / (ms / 1e3) / 1e12
+    roofline = {"bound": "tensor", "achieved": tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                "frac": tflops / pk["bf16_sustained"], "traffic": None,
+                "kernel": "whole DenseNet forward (per-kernel figure: see profiles/)", "peak_source": pk["source"] + " sustained"}
+    cpu = None
+    if not args.no_cpu_baseline:
+        v, cms, cores, sample = time_cpu_reference(4, 2, 1, 1234)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    # launches per step: densify x2 + per CNN chunk (stem 2 + 30 layers x 2 + 4 transitions x 2 + tail 2) + seq 2
+    chunk = 32
+    per_chunk = 2 + 30 * 2 + 4 * 2 + 2
+    n_chunks = -(-batch.num_events // chunk) + -(-batch.num_prongs // chunk)
+    launches = (2 + n_chunks * per_chunk + 2) * args.steps
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[1]: eval inference, {args.events} events/GPU "
+                                   f"({images} images of 3x400x280 on rank 0), P~U[1,10], occupancy 1%/0.2%",
+                       "precision": args.precision, "parallelism": f"event-sharded x{world}, no collective",
+                       "l2": "dense maps per step (%.1f GB) exceed the 126 MB L2" % (images * 3 * H * W * 4 / 1e9)},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "images_per_s": value * images / args.events,
+            "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary()}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--events", type=int, default=256)
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,130 @@
+// DenseNet pixel-map embedding, eval-mode forward: the layer walk.
+// Follows transformercvn/network/layers/dense_net.py:111-167 (DenseNet.features / condense /
+// output_block) with the dataflow re-designed for in-place concat buffers (no torch.cat, dense_net.py:45):
+//   stem -> pool -> blk[0][:, 0:64]
+//   layer i of block b:  mid = PReLU2(BN2(conv1(PReLU1(BN1(blk[b][:, :k_i])))))      (one fused GEMM)
+//                        blk[b][:, k_i : k_i+32] = conv2_3x3(mid)                     (one shifted GEMM)
+//   transition b:        blk[b+1][:, 0:c/2] = conv1x1(avgpool2(PReLU(BN(blk[b]))))    (pool first: 4x fewer FLOPs)
+//   tail:                embedding = PReLU(BN1d(Linear(mean_hw(PReLU(BN(blk[last]))))))
+// Images are processed in chunks so a chunk's block buffer stays L2-resident between its layers.
+#include "kernels.h"
+#include "plan.h"
+#include "umma.h"
+
+using namespace tcvn;
+
+
+
+namespace {
+
+inline const float* pf(const char* packed, size_t off) { return reinterpret_cast<const float*>(packed + off); }
+
+int forward_chunk(const CnnPlan& P, const char* pk, const float* pixels, int n, float* embedding, char* ws,
+                  cudaStream_t st) {
+  const tcvn_cnn_desc& d = P.d;
+  const bool f32 = P.prec == TCVN_FP32;
+  void* stem = ws + P.ws_stem;
+  void* mid = ws + P.ws_mid;
+  void* pool = ws + P.ws_pool;
+  float* gap = reinterpret_cast<float*>(ws + P.ws_gap);
+  TCVN_TRY(launch_stem_conv(pixels, n, d.in_channels, d.height, d.width, pf(pk, P.p_w0), pf(pk, P.p_s_scale),
+                            pf(pk, P.p_s_shift), pf(pk, P.p_s_alpha), d.init_features, stem, f32, st));
+  const BlockPlan& B0 = P.blocks[0];
+  TCVN_TRY(launch_stem_pool(stem, n, P.Hs, P.Ws, d.init_features, ws + B0.ws_blk, B0.ctot, B0.H, B0.W, f32, st));
+  for (size_t b = 0; b < P.blocks.size(); ++b) {
+    const BlockPlan& B = P.blocks[b];
+    void* blk = ws + B.ws_blk;
+    const long long rows = (long long)n * B.R;
+    for (const LayerPlan& L : B.layers) {
+      if (f32) {
+        GemmArgs g{};
+        g.A = blk; g.lda = B.ctot; g.m_total = rows; g.K = L.kphys; g.taps = 1; g.tap_off[0] = 0;
+        g.W = pf(pk, L.p_w1); g.N = P.mid;
+        g.a_scale = pf(pk, L.p_a_scale); g.a_shift = pf(pk, L.p_a_shift); g.a_alpha = pf(pk, L.p_a_alpha);
+        g.o_scale = pf(pk, L.p_o_scale); g.o_shift = pf(pk, L.p_o_shift); g.o_alpha = pf(pk, L.p_o_alpha);
+        g.out = mid; g.ldo = P.mid; g.out_col0 = 0; g.ring_Hp = B.Hp; g.ring_Wp = B.Wp;
+        g.a_is_f32 = true; g.out_is_f32 = true;
+        TCVN_TRY(launch_simt_gemm(g, st));
+        GemmArgs c{};
+        c.A = mid; c.lda = P.mid; c.m_total = rows; c.K = P.mid; c.taps = 9;
+        for (int t = 0; t < 9; ++t) c.tap_off[t] = (t / 3 - 1) * B.Wp + (t % 3 - 1);
+        c.W = pf(pk, L.p_w2); c.N = d.growth;
+        c.o_shift = pf(pk, L.p_b2);
+        c.out = blk; c.ldo = B.ctot; c.out_col0 = L.kphys; c.ring_Hp = B.Hp; c.ring_Wp = B.Wp;
+        c.a_is_f32 = true; c.out_is_f32 = true;
+        TCVN_TRY(launch_simt_gemm(c, st));
+      } else {
+        TCVN_TRY(umma_dense_layer(P, B, L, pk, blk, mid, rows, st));
+      }
+    }
+    if (B.has_transition) {
+      const BlockPlan& Nx = P.blocks[b + 1];
+      TCVN_TRY(launch_act_pool2(blk, n, B.H, B.W, B.ctot, B.ctot, pf(pk, B.p_t_scale), pf(pk, B.p_t_shift),
+                                pf(pk, B.p_t_alpha), pool, Nx.H, Nx.W, f32, st));
+      const long long nrows = (long long)n * Nx.R;
+      if (f32) {
+        GemmArgs g{};
+        g.A = pool; g.lda = B.ctot; g.m_total = nrows; g.K = B.ctot; g.taps = 1; g.tap_off[0] = 0;
+        g.W = pf(pk, B.p_tw); g.N = B.toutp;
+        g.o_shift = pf(pk, B.p_tb);
+        g.out = ws + Nx.ws_blk; g.ldo = Nx.ctot; g.out_col0 = 0; g.ring_Hp = Nx.Hp; g.ring_Wp = Nx.Wp;
+        g.a_is_f32 = true; g.out_is_f32 = true;
+        TCVN_TRY(launch_simt_gemm(g, st));
+      } else {
+        TCVN_TRY(umma_transition(P, B, Nx, pk, pool, ws + Nx.ws_blk, nrows, st));
+      }
+    }
+  }
+  const BlockPlan& last = P.blocks.back();
+  TCVN_TRY(launch_act_gap(ws + last.ws_blk, n, last.H, last.W, last.ctot, last.ctot, pf(pk, P.p_f_scale),
+                          pf(pk, P.p_f_shift), pf(pk, P.p_f_alpha), gap, f32, st));
+  GemmArgs g{};
+  g.A = gap; g.lda = last.ctot; g.m_total = n; g.K = last.ctot; g.taps = 1; g.tap_off[0] = 0;
+  g.W = pf(pk, P.p_lw); g.N = d.out_features;
+  g.o_scale = pf(pk, P.p_lo_scale); g.o_shift = pf(pk, P.p_lo_shift); g.o_alpha = pf(pk, P.p_lo_alpha);
+  g.out = embedding; g.ldo = d.out_features; g.out_col0 = 0;
+  g.a_is_f32 = true; g.out_is_f32 = true;
+  TCVN_TRY(launch_simt_gemm(g, st));
+  return TCVN_OK;
+}
+
+}  // namespace
+
+extern "C" int tcvn_cnn_forward(const tcvn_cnn_desc* d, tcvn_precision prec, const void* packed, const float* pixels,
+                                int n_images, float* embedding, void* workspace, size_t workspace_bytes,
+                                tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(d && packed && workspace, "cnn_forward: null pointer");
+  TCVN_CHECK_ARG(prec == TCVN_FP32 || prec == TCVN_BF16, "cnn_forward: unknown precision");
+  TCVN_CHECK_ARG(n_images >= 0, "cnn_forward: negative image count");
+  if (n_images == 0) return TCVN_OK;
+  TCVN_CHECK_ARG(pixels && embedding, "cnn_forward: null pointer");
+  CnnPlan P;
+  TCVN_CHECK_ARG(CnnPlan::build(*d, prec, n_images, &P), "cnn_forward: bad descriptor");
+  if (workspace_bytes < P.ws_bytes)
+    return fail(TCVN_ERR_WORKSPACE, "cnn_forward: workspace %zu < %zu bytes", workspace_bytes, P.ws_bytes);
+  const size_t img_floats = (size_t)d->in_channels * d->height * d->width;
+  for (int i0 = 0; i0 < n_images; i0 += P.chunk) {
+    const int n = n_images - i0 < P.chunk ? n_images - i0 : P.chunk;
+    TCVN_TRY(forward_chunk(P, static_cast<const char*>(packed), pixels + (size_t)i0 * img_floats, n,
+                           embedding + (size_t)i0 * d->out_features, static_cast<char*>(workspace), stream));
+  }
+  return TCVN_OK;
+}
+
+extern "C" int tcvn_cnn_read_stage(const tcvn_cnn_desc* d, tcvn_precision prec, const void* workspace, int n_images,
+                                   int stage, float* out, int32_t* channels, int32_t* h, int32_t* w,
+                                   tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(d && workspace && channels && h && w, "cnn_read_stage: null pointer");
+  CnnPlan P;
+  TCVN_CHECK_ARG(CnnPlan::build(*d, prec, n_images, &P), "cnn_read_stage: bad descriptor");
+  TCVN_CHECK_ARG(n_images <= P.chunk, "cnn_read_stage: only the last chunk (%d images) is still in the workspace", P.chunk);
+  TCVN_CHECK_ARG(stage >= 0 && stage <= 2 * (int)P.blocks.size() - 1, "cnn_read_stage: no stage %d", stage);
+  const int b = stage == 0 ? 0 : (stage % 2 == 1 ? (stage - 1) / 2 : stage / 2);
+  const BlockPlan& B = P.blocks[b];
+  // stage 0 and transition outputs are the first c0 channels of a block buffer; block outputs are all of it
+  const int c = (stage % 2 == 1) ? B.clog : B.c0;
+  *channels = c; *h = B.H; *w = B.W;
+  if (out == nullptr) return TCVN_OK;
+  return launch_ring_to_nchw(static_cast<const char*>(workspace) + B.ws_blk, n_images, B.H, B.W, B.ctot, c, B.c0,
+                             B.c0p - B.c0, out, prec == TCVN_FP32, stream);
+}

@@ -1,0 +1,27 @@
+// Thread-local error text behind tcvn_last_error(); ABI version.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include "../../include/tcvn.h"
+
+namespace tcvn {
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+  return code;
+}
+}  // namespace tcvn
+
+extern "C" int tcvn_abi_version(void) { return TCVN_ABI_VERSION; }
+extern "C" const char* tcvn_last_error(void) { return tcvn::g_error; }

@@ -1,0 +1,52 @@
+// Internal launch wrappers shared by the CNN walker (cnn.cu).  Not part of the C ABI.
+#pragma once
+#include "common.cuh"
+#include "plan.h"
+
+namespace tcvn {
+
+// out[m, col0 + n] = epi( sum_t sum_k act(A[m + tap_off[t], k]) * W[t][k][n] )   (fp32 CUDA-core path)
+//   act(x)  = prelu(x * a_scale[k] + a_shift[k], a_alpha[k])   when a_scale != nullptr, else x
+//   epi(v)  = prelu(v * o_scale[n] + o_shift[n], o_alpha[n])   when o_scale != nullptr, else v + o_shift[n]
+//   rows of the zero ring (ring_R > 0) are written as zeros; rows outside [0, m_total) read as zeros.
+struct GemmArgs {
+  const void* A; int lda; long long m_total; int K; int taps; int tap_off[9];
+  const float* W; int N;
+  const float* a_scale; const float* a_shift; const float* a_alpha;
+  const float* o_scale; const float* o_shift; const float* o_alpha;
+  void* out; int ldo; int out_col0;
+  int ring_Hp, ring_Wp;  // 0 = no ring masking
+  bool a_is_f32; bool out_is_f32;  // element types of A / out (false = bf16)
+};
+int launch_simt_gemm(const GemmArgs& g, cudaStream_t stream);
+
+// conv0 7x7 s2 p3 + bias + BN0 + PReLU0 on NCHW fp32 pixels -> [n, Hs, Ws, C0] (no ring)
+int launch_stem_conv(const float* pixels, int n, int cin, int H, int W, const float* w0, const float* s_scale,
+                     const float* s_shift, const float* s_alpha, int c0, void* out, bool out_f32, cudaStream_t stream);
+// AvgPool2d(3, 2) of the stem output into channels [0, c) of block 0's ringed buffer
+int launch_stem_pool(const void* in, int n, int Hs, int Ws, int c, void* blk, int ldo, int H, int W, bool f32,
+                     cudaStream_t stream);
+// transition front half: BN + PReLU + AvgPool2d(2,2) of a ringed block buffer into a ringed buffer of the next geometry
+int launch_act_pool2(const void* blk, int n, int H, int W, int ld, int c, const float* scale, const float* shift,
+                     const float* alpha, void* out, int H2, int W2, bool f32, cudaStream_t stream);
+// tail front half: BN + PReLU + global average over the interior -> gap [n, c] fp32
+int launch_act_gap(const void* blk, int n, int H, int W, int ld, int c, const float* scale, const float* shift,
+                   const float* alpha, float* gap, bool f32, cudaStream_t stream);
+// ringed channels-last -> NCHW fp32 (test hook)
+int launch_ring_to_nchw(const void* blk, int n, int H, int W, int ld, int c, int c_skip_from, int c_skip, float* out,
+                        bool f32, cudaStream_t stream);
+
+// pack.cu helpers (also used by seq.cu)
+int fold(const float* arena, const BnArena& bn, const float* conv_bias, int c0, int c0p, int n_out, float eps,
+         char* packed, size_t o_scale, size_t o_shift, size_t o_alpha, cudaStream_t st);
+int repack(const float* src, int n_log, int k_log, int taps, int c0, int c0p, int K_out, int N_out, bool k_major,
+           bool bf16, void* dst, cudaStream_t st);
+int pad_copy(const float* src, int n_log, float* dst, int n_out, cudaStream_t st);
+
+#define TCVN_TRY(expr)                \
+  do {                                \
+    int rc__ = (expr);                \
+    if (rc__ != TCVN_OK) return rc__; \
+  } while (0)
+
+}  // namespace tcvn

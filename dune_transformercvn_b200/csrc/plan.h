@@ -1,0 +1,211 @@
+// Host-side plan of one DenseNet pixel-map CNN: geometry of the padded channels-last feature
+// maps, offsets into the reference-ordered fp32 arena, offsets into the packed parameter block
+// and into the caller's workspace.  Pure arithmetic, no CUDA.
+//
+// Reference topology: transformercvn/network/layers/dense_net.py:97-162 (walk mirrored from
+// dune_transformercvn_b200/params.py::densenet_specs, which is pinned against the reference's
+// state_dict by tests/test_params.py).
+#pragma once
+#include <stdint.h>
+
+#include <vector>
+
+#include "../../include/tcvn.h"
+
+namespace tcvn {
+
+constexpr int kChanAlign = 8;      // concat-buffer channel slices start on 16-byte (bf16) boundaries
+constexpr int kKChunk = 64;        // bf16 K tile = one 128-byte swizzle row
+constexpr int kDefaultChunk = 32;  // images per pass through the CNN
+
+inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+struct BnArena {  // float offsets of one BatchNorm + PReLU pair in the arena
+  int64_t w, b, rm, rv, alpha;
+  int c;
+};
+
+struct LayerPlan {
+  int cin;       // logical input channels (C0 + growth*i)
+  int kphys;     // physical input channels in the block buffer (C0p + growth*i)
+  int kpad;      // kphys rounded up to kKChunk (bf16 weights are zero beyond kphys)
+  BnArena norm1, norm2;
+  int64_t conv1_w, conv1_b, conv2_w, conv2_b;  // arena offsets
+  // packed offsets (bytes)
+  size_t p_a_scale, p_a_shift, p_a_alpha;  // [kpad] fp32: BN1+PReLU1 fold over physical channels
+  size_t p_w1;                             // fp32: [kphys][mid] ; bf16: [mid][kpad]
+  size_t p_o_scale, p_o_shift, p_o_alpha;  // [mid] fp32: conv1 bias + BN2 + PReLU2 fold
+  size_t p_w2;                             // fp32: [9][mid][growth] ; bf16: [9][growth][mid]
+  size_t p_b2;                             // [growth] fp32
+};
+
+struct BlockPlan {
+  int H, W, Hp, Wp, R;  // interior size, padded size, rows per image (Hp*Wp)
+  int c0, c0p, ctot;    // logical / padded input channels, physical channels of the block buffer
+  int clog;             // logical output channels (c0 + growth*layers)
+  std::vector<LayerPlan> layers;
+  // transition after this block (absent after the last one)
+  bool has_transition;
+  BnArena tnorm;
+  int64_t tconv_w, tconv_b;
+  int tout, toutp;  // logical / padded output channels (= next block's c0 / c0p)
+  int tkpad;        // ctot rounded up to kKChunk
+  size_t p_t_scale, p_t_shift, p_t_alpha;  // [ctot] fp32
+  size_t p_tw;                             // fp32: [ctot][toutp] ; bf16: [toutp][tkpad]
+  size_t p_tb;                             // [toutp] fp32
+  // workspace offsets (bytes)
+  size_t ws_blk;
+};
+
+struct CnnPlan {
+  tcvn_cnn_desc d;
+  tcvn_precision prec;
+  int esize;  // bytes per activation element
+  int mid;    // bottleneck width
+  int Hs, Ws;  // stem conv output (200 x 140)
+  // arena
+  int64_t conv0_w, conv0_b;
+  BnArena norm0;
+  BnArena final_norm;
+  int64_t lin_w;
+  BnArena out_norm;
+  int64_t arena_floats;
+  // packed
+  size_t p_w0;                             // [in*49][init] fp32
+  size_t p_s_scale, p_s_shift, p_s_alpha;  // [init] fp32: conv0 bias + BN0 + PReLU0
+  size_t p_f_scale, p_f_shift, p_f_alpha;  // [ctot_last] fp32
+  size_t p_lw;                             // [ctot_last][out] fp32
+  size_t p_lo_scale, p_lo_shift, p_lo_alpha;  // [out] fp32
+  size_t packed_bytes;
+  std::vector<BlockPlan> blocks;
+  // workspace (sized for `chunk` images)
+  int chunk;
+  size_t ws_stem, ws_mid, ws_pool, ws_gap, ws_bytes;
+
+  static bool build(const tcvn_cnn_desc& d, tcvn_precision prec, int n_images, CnnPlan* out);
+  // physical channel of logical channel c inside block b's buffer
+  int phys(int b, int c) const {
+    const BlockPlan& B = blocks[b];
+    return c < B.c0 ? c : c + (B.c0p - B.c0);
+  }
+};
+
+inline bool CnnPlan::build(const tcvn_cnn_desc& d, tcvn_precision prec, int n_images, CnnPlan* out) {
+  if (d.num_blocks < 1 || d.num_blocks > TCVN_MAX_BLOCKS) return false;
+  if (d.in_channels < 1 || d.init_features < 1 || d.growth < 1 || d.bn_size < 1 || d.out_features < 1) return false;
+  CnnPlan& P = *out;
+  P.d = d;
+  P.prec = prec;
+  P.esize = prec == TCVN_BF16 ? 2 : 4;
+  P.mid = d.bn_size * d.growth;
+  P.Hs = (d.height + 6 - 7) / 2 + 1;
+  P.Ws = (d.width + 6 - 7) / 2 + 1;
+  int64_t a = 0;
+  size_t p = 0;
+  auto take = [&](int64_t n) { int64_t o = a; a += n; return o; };
+  auto ptake = [&](size_t bytes) { size_t o = p; p += (bytes + 255) / 256 * 256; return o; };
+  auto bn = [&](int c) {
+    BnArena r;
+    r.c = c;
+    r.w = take(c); r.b = take(c); r.rm = take(c); r.rv = take(c);
+    r.alpha = take(c);  // the PReLU weight follows its BatchNorm in state_dict order
+    return r;
+  };
+  const size_t wsz = prec == TCVN_BF16 ? 2 : 4;
+  P.conv0_w = take((int64_t)d.init_features * d.in_channels * 49);
+  P.conv0_b = take(d.init_features);
+  P.norm0 = bn(d.init_features);
+  P.p_w0 = ptake((size_t)d.in_channels * 49 * d.init_features * 4);
+  P.p_s_scale = ptake(d.init_features * 4);
+  P.p_s_shift = ptake(d.init_features * 4);
+  P.p_s_alpha = ptake(d.init_features * 4);
+  int H = (P.Hs - 3) / 2 + 1, W = (P.Ws - 3) / 2 + 1;  // AvgPool2d(3, stride 2, no padding)
+  int c = d.init_features;
+  P.blocks.clear();
+  for (int b = 0; b < d.num_blocks; ++b) {
+    BlockPlan B;
+    B.H = H; B.W = W; B.Hp = H + 2; B.Wp = W + 2; B.R = B.Hp * B.Wp;
+    B.c0 = c;
+    B.c0p = round_up(c, kChanAlign);
+    const int nl = d.block_layers[b];
+    if (nl < 0) return false;
+    B.ctot = B.c0p + nl * d.growth;
+    B.clog = c + nl * d.growth;
+    for (int i = 0; i < nl; ++i) {
+      LayerPlan L;
+      L.cin = c + i * d.growth;
+      L.kphys = B.c0p + i * d.growth;
+      L.kpad = round_up(L.kphys, kKChunk);
+      L.norm1 = bn(L.cin);
+      L.conv1_w = take((int64_t)P.mid * L.cin);
+      L.conv1_b = take(P.mid);
+      L.norm2 = bn(P.mid);
+      L.conv2_w = take((int64_t)d.growth * P.mid * 9);
+      L.conv2_b = take(d.growth);
+      L.p_a_scale = ptake(L.kpad * 4);
+      L.p_a_shift = ptake(L.kpad * 4);
+      L.p_a_alpha = ptake(L.kpad * 4);
+      L.p_w1 = ptake(prec == TCVN_BF16 ? (size_t)P.mid * L.kpad * wsz : (size_t)L.kphys * P.mid * wsz);
+      L.p_o_scale = ptake(P.mid * 4);
+      L.p_o_shift = ptake(P.mid * 4);
+      L.p_o_alpha = ptake(P.mid * 4);
+      L.p_w2 = ptake((size_t)9 * P.mid * d.growth * wsz);
+      L.p_b2 = ptake(d.growth * 4);
+      B.layers.push_back(L);
+    }
+    c = B.clog;
+    B.has_transition = b != d.num_blocks - 1;
+    if (B.has_transition) {
+      B.tnorm = bn(c);
+      B.tout = c / 2;
+      B.toutp = round_up(B.tout, kChanAlign);
+      B.tkpad = round_up(B.ctot, kKChunk);
+      B.tconv_w = take((int64_t)B.tout * c);
+      B.tconv_b = take(B.tout);
+      B.p_t_scale = ptake(B.tkpad * 4);
+      B.p_t_shift = ptake(B.tkpad * 4);
+      B.p_t_alpha = ptake(B.tkpad * 4);
+      B.p_tw = ptake(prec == TCVN_BF16 ? (size_t)B.toutp * B.tkpad * wsz : (size_t)B.ctot * B.toutp * wsz);
+      B.p_tb = ptake(B.toutp * 4);
+      c = B.tout;
+      H /= 2; W /= 2;  // AvgPool2d(2, 2) floors
+      if (H < 1 || W < 1) return false;
+    }
+    P.blocks.push_back(B);
+  }
+  const BlockPlan& last = P.blocks.back();
+  P.final_norm = bn(c);
+  P.lin_w = take((int64_t)d.out_features * c);
+  P.out_norm = bn(d.out_features);
+  P.arena_floats = a;
+  P.p_f_scale = ptake(last.ctot * 4);
+  P.p_f_shift = ptake(last.ctot * 4);
+  P.p_f_alpha = ptake(last.ctot * 4);
+  P.p_lw = ptake((size_t)last.ctot * d.out_features * 4);
+  P.p_lo_scale = ptake(d.out_features * 4);
+  P.p_lo_shift = ptake(d.out_features * 4);
+  P.p_lo_alpha = ptake(d.out_features * 4);
+  P.packed_bytes = p;
+  // workspace
+  P.chunk = n_images < kDefaultChunk ? (n_images < 1 ? 1 : n_images) : kDefaultChunk;
+  size_t w = 0;
+  auto wtake = [&](size_t bytes) { size_t o = w; w += (bytes + 1023) / 1024 * 1024; return o; };
+  const size_t n = P.chunk;
+  P.ws_stem = wtake(n * P.Hs * P.Ws * d.init_features * P.esize);
+  size_t mid_rows = 0, pool_elems = 0;
+  for (auto& B : P.blocks) {
+    B.ws_blk = wtake(n * B.R * (size_t)B.ctot * P.esize);
+    if ((size_t)B.R > mid_rows) mid_rows = B.R;
+  }
+  for (size_t b = 0; b + 1 < P.blocks.size(); ++b) {
+    size_t e = (size_t)P.blocks[b + 1].R * P.blocks[b].ctot;
+    if (e > pool_elems) pool_elems = e;
+  }
+  P.ws_mid = wtake(n * mid_rows * P.mid * P.esize);
+  P.ws_pool = wtake(n * pool_elems * P.esize + 1024);
+  P.ws_gap = wtake(n * (size_t)last.ctot * 4);
+  P.ws_bytes = w;
+  return true;
+}
+
+}  // namespace tcvn

@@ -1,0 +1,358 @@
+"""Drop-in for ``transformercvn.network``'s dense network, running on libtcvn's CUDA kernels.
+
+``NeutrinoDenseNetwork`` keeps the reference's constructor, ``forward`` signature, sub-module
+surface and ``state_dict`` names/shapes/order
+(transformercvn/network/networks/neutrino_full_dense_network.py:19-21,
+neutrino_full_base_network.py:128-188), so ``load_state_dict`` of a reference checkpoint, the
+weight-decay grouping by parameter name (trainers/neutrino_base.py:116-128) and
+``Evaluate.ipynb`` work unchanged.  The fp32 master parameters are ordinary ``nn.Parameter``s;
+the kernel-ready (BN-folded, re-laid, bf16) copies are a cache rebuilt when a parameter changes.
+
+All arithmetic happens in libtcvn.so; without it, or on a CPU tensor, every call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+
+from . import lib as _lib
+from . import synth
+from .config import PIXEL_H, PIXEL_W
+from .params import TensorSpec, embedding_dims, network_specs, prong_decoder_widths
+
+_PRECISIONS = {"fp32": _lib.TCVN_FP32, "bf16": _lib.TCVN_BF16}
+
+
+class _Node(nn.Module):
+    """Name-only container: the reference's module tree is reproduced for its parameter names."""
+
+
+def _attach(root: nn.Module, spec: TensorSpec, value: torch.Tensor) -> None:
+    parts = spec.name.split(".")
+    mod = root
+    for p in parts[:-1]:
+        child = mod._modules.get(p)
+        if child is None:
+            child = _Node()
+            mod.add_module(p, child)
+        mod = child
+    if spec.is_param:
+        mod.register_parameter(parts[-1], nn.Parameter(value))
+    else:
+        mod.register_buffer(parts[-1], value)
+
+
+class _Engine:
+    """Packed-parameter cache, workspaces and the calls into the C ABI for one network."""
+
+    def __init__(self, owner: "NeutrinoDenseNetwork"):
+        self.owner = (owner,)  # tuple: keeps nn.Module.__setattr__ from registering a cycle
+        self.key = None
+        self.packed: Dict[str, torch.Tensor] = {}
+        self.ws: Dict[Tuple, torch.Tensor] = {}
+        self.frozen = False
+
+    # ---- descriptors ------------------------------------------------------------------------
+    def cnn_desc(self, out_features: int) -> _lib.CnnDesc:
+        o = self.owner[0].options
+        d = _lib.CnnDesc()
+        d.in_channels = self.owner[0].pixel_dim
+        d.init_features = o.initial_pixel_dim
+        d.growth = o.densenet_growth_rate
+        d.bn_size = o.densenet_batch_norm_size
+        blocks = list(o.densenet_structure)
+        d.num_blocks = len(blocks)
+        for i, n in enumerate(blocks):
+            d.block_layers[i] = n
+        d.out_features = out_features
+        d.height, d.width = self.owner[0].image_size
+        d.bn_eps = 1e-5
+        return d
+
+    def seq_desc(self) -> _lib.SeqDesc:
+        net = self.owner[0]
+        o = net.options
+        pix, feat, pos = embedding_dims(o)
+        d = _lib.SeqDesc()
+        d.hidden, d.heads, d.layers, d.ffn = o.hidden_dim, o.num_attention_heads, o.num_encoder_layers, o.hidden_dim
+        d.pixel_dim, d.feature_dim, d.position_dim = pix, feat, pos
+        d.num_event_classes, d.num_prong_classes = net.num_event_classes, net.num_prong_classes
+        widths = prong_decoder_widths(o)
+        d.num_decoder_layers = len(widths)
+        for i, w in enumerate(widths):
+            d.decoder_widths[i] = w
+        d.bn_eps = 1e-5
+        d.ln_eps = 1e-5
+        return d
+
+    # ---- packing -----------------------------------------------------------------------------
+    def _arena(self, tensors: Dict[str, torch.Tensor], prefix: str) -> torch.Tensor:
+        specs = [s for s in self.owner[0].specs if s.name.startswith(prefix) and s.in_arena]
+        return torch.cat([tensors[s.name].detach().reshape(-1).float() for s in specs])
+
+    def _state_key(self, tensors: Dict[str, torch.Tensor], prec: int):
+        v = 0
+        p = 0
+        for t in tensors.values():
+            v += t._version
+            p ^= t.data_ptr()
+        first = next(iter(tensors.values()))
+        return (str(first.device), prec, v, p)
+
+    def ensure_packed(self, prec: int) -> None:
+        net = self.owner[0]
+        if self.frozen and self.key is not None and self.key[1] == prec:
+            return
+        tensors = dict(net.named_parameters())
+        tensors.update(dict(net.named_buffers()))
+        key = self._state_key(tensors, prec)
+        if key == self.key:
+            return
+        L = _lib.load()
+        dev = next(iter(tensors.values())).device
+        if dev.type != "cuda":
+            raise _lib.TcvnError("NeutrinoDenseNetwork: parameters are on the CPU; move the module to a CUDA device "
+                                 "(this path has no CPU implementation)")
+        st = _lib.stream_ptr(dev)
+        pix, feat, pos = embedding_dims(net.options)
+        pe = "prong_embedding."
+        for tag, prefix, width in (("prong", pe + "prong_pixel_embedding.", pix),
+                                   ("event", pe + "event_pixel_embedding.", pix + feat)):
+            d = self.cnn_desc(width)
+            arena = self._arena(tensors, prefix)
+            expect = L.tcvn_cnn_arena_floats(C.byref(d))
+            if arena.numel() != expect:
+                raise _lib.TcvnError(f"{tag} CNN arena has {arena.numel()} floats, library expects {expect}")
+            nbytes = L.tcvn_cnn_packed_bytes(C.byref(d), prec)
+            buf = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+            _lib.check(L.tcvn_cnn_pack(C.byref(d), prec, _lib.ptr(arena), _lib.ptr(buf), nbytes, st), "tcvn_cnn_pack")
+            self.packed[tag] = buf
+        sd = self.seq_desc()
+        nbytes = L.tcvn_seq_packed_bytes(C.byref(sd))
+        if nbytes == 0:
+            raise _lib.TcvnError("sequence descriptor rejected: " + L.tcvn_last_error().decode())
+        buf = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        position = tensors[pe + "event_position_embedding"].detach().reshape(-1).float().contiguous()
+        arenas = [self._arena(tensors, p) for p in (pe + "combined_embedding.", "encoder.", "event_decoder.",
+                                                    "prong_decoder.")]
+        _lib.check(L.tcvn_seq_pack(C.byref(sd), _lib.ptr(position), *[_lib.ptr(a) for a in arenas], _lib.ptr(buf),
+                                   nbytes, st), "tcvn_seq_pack")
+        self.packed["seq"] = buf
+        self.key = key
+
+    # ---- workspaces --------------------------------------------------------------------------
+    def workspace(self, kind: str, nbytes: int, dev) -> torch.Tensor:
+        k = (kind, str(dev))
+        buf = self.ws.get(k)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.zeros(nbytes, dtype=torch.uint8, device=dev)  # zero-filled once: ring rows stay finite
+            self.ws[k] = buf
+        return buf
+
+    # ---- kernels -----------------------------------------------------------------------------
+    def cnn(self, tag: str, pixels: torch.Tensor, prec: int) -> torch.Tensor:
+        L = _lib.load()
+        net = self.owner[0]
+        pix, feat, _ = embedding_dims(net.options)
+        width = pix if tag == "prong" else pix + feat
+        d = self.cnn_desc(width)
+        n = pixels.shape[0]
+        out = torch.empty((n, width), dtype=torch.float32, device=pixels.device)
+        if n == 0:
+            return out
+        if tuple(pixels.shape[1:]) != (d.in_channels, d.height, d.width):
+            raise _lib.TcvnError(f"{tag} pixels have shape {tuple(pixels.shape)}, expected (N,{d.in_channels},{d.height},{d.width})")
+        pixels = pixels.contiguous().float()
+        nbytes = L.tcvn_cnn_workspace_bytes(C.byref(d), prec, n)
+        ws = self.workspace("cnn", nbytes, pixels.device)
+        _lib.check(L.tcvn_cnn_forward(C.byref(d), prec, _lib.ptr(self.packed[tag]), _lib.ptr(pixels), n, _lib.ptr(out),
+                                      _lib.ptr(ws), ws.numel(), _lib.stream_ptr(pixels.device)), "tcvn_cnn_forward")
+        return out
+
+    def read_stage(self, tag: str, n: int, stage: int, prec: int, dev) -> torch.Tensor:
+        """Test hook: a feature map of the last ``cnn`` call as (n,C,H,W) fp32."""
+        L = _lib.load()
+        net = self.owner[0]
+        pix, feat, _ = embedding_dims(net.options)
+        d = self.cnn_desc(pix if tag == "prong" else pix + feat)
+        ws = self.ws[("cnn", str(dev))]
+        c, h, w = C.c_int32(), C.c_int32(), C.c_int32()
+        st = _lib.stream_ptr(dev)
+        _lib.check(L.tcvn_cnn_read_stage(C.byref(d), prec, _lib.ptr(ws), n, stage, None, C.byref(c), C.byref(h),
+                                         C.byref(w), st), "tcvn_cnn_read_stage")
+        out = torch.empty((n, c.value, h.value, w.value), dtype=torch.float32, device=dev)
+        _lib.check(L.tcvn_cnn_read_stage(C.byref(d), prec, _lib.ptr(ws), n, stage, _lib.ptr(out), C.byref(c),
+                                         C.byref(h), C.byref(w), st), "tcvn_cnn_read_stage")
+        return out
+
+    def seq(self, stages: int, event_emb, prong_emb, event_mask, prong_mask, tokens=None, hidden=None):
+        L = _lib.load()
+        net = self.owner[0]
+        sd = self.seq_desc()
+        b, l = prong_mask.shape
+        dev = prong_mask.device
+        s = 1 + l
+        pm = prong_mask.contiguous().to(torch.uint8)
+        em = None if event_mask is None else event_mask.contiguous().to(torch.uint8)
+        f32 = dict(dtype=torch.float32, device=dev)
+        if stages & _lib.SEQ_TOKENS and tokens is None:
+            tokens = torch.empty((b, s, sd.hidden), **f32)
+        if stages & _lib.SEQ_ENCODER and hidden is None:
+            hidden = torch.empty((s, b, sd.hidden), **f32)
+        ev_logits = pr_logits = None
+        if stages & _lib.SEQ_HEADS:
+            ev_logits = torch.empty((b, sd.num_event_classes), **f32)
+            pr_logits = torch.empty((b, l, sd.num_prong_classes), **f32)
+        nbytes = L.tcvn_seq_workspace_bytes(C.byref(sd), b, l)
+        ws = self.workspace("seq", nbytes, dev)
+        _lib.check(L.tcvn_seq_forward(C.byref(sd), _lib.ptr(self.packed["seq"]), stages, _lib.ptr(event_emb),
+                                      _lib.ptr(prong_emb), _lib.ptr(em), _lib.ptr(pm), b, l, _lib.ptr(tokens),
+                                      _lib.ptr(hidden), _lib.ptr(ev_logits), _lib.ptr(pr_logits), _lib.ptr(ws),
+                                      ws.numel(), _lib.stream_ptr(dev)), "tcvn_seq_forward")
+        return tokens, hidden, ev_logits, pr_logits
+
+
+def _check_eval(mod: nn.Module) -> None:
+    if mod.training:
+        raise NotImplementedError(
+            "dune_transformercvn_b200: the CUDA path currently implements eval-mode (running-statistics) forward only; "
+            "call .eval() — training kernels (batch-stat BN, dropout, backward) are not built yet and there is "
+            "deliberately no PyTorch fallback")
+
+
+class ProngEmbedding(_Node):
+    """``BaseProngEmbedding`` surface (neutrino_full_base_network.py:87-125): pixels -> tokens, mask."""
+
+    def forward(self, features, extra, event_pixels, event_mask, prong_pixels, prong_mask):
+        eng: _Engine = self._engine[0]
+        net = eng.owner[0]
+        _check_eval(net)
+        prec = _PRECISIONS[net.precision]
+        _lib.require_cuda(event_pixels, "event_pixels")
+        eng.ensure_packed(prec)
+        ev = eng.cnn("event", event_pixels, prec)
+        pr = eng.cnn("prong", prong_pixels, prec)
+        tokens, _, _, _ = eng.seq(_lib.SEQ_TOKENS, ev, pr, event_mask, prong_mask)
+        return tokens, torch.cat((event_mask, prong_mask), dim=1)
+
+
+class ProngEncoder(_Node):
+    """``ProngCustomBertEncoder`` surface (prong_custom_bert_encoder.py:57-75)."""
+
+    def forward(self, hidden, sequence_mask):
+        eng: _Engine = self._engine[0]
+        net = eng.owner[0]
+        _check_eval(net)
+        _lib.require_cuda(hidden, "hidden")
+        eng.ensure_packed(_PRECISIONS[net.precision])
+        _, out, _, _ = eng.seq(_lib.SEQ_ENCODER, None, None, sequence_mask[:, :1], sequence_mask[:, 1:],
+                               tokens=hidden.contiguous().float())
+        return out, ~sequence_mask, sequence_mask
+
+
+class _HeadBase(_Node):
+    def _run(self, x_event: Optional[torch.Tensor], x_prong: Optional[torch.Tensor]):
+        """Heads over explicit hidden vectors: builds the (S,B,D) layout the fused kernel reads."""
+        eng: _Engine = self._engine[0]
+        net = eng.owner[0]
+        _check_eval(net)
+        eng.ensure_packed(_PRECISIONS[net.precision])
+        d = net.options.hidden_dim
+        if x_prong is None:
+            b, l = x_event.shape[0], 0
+            dev = x_event.device
+        else:
+            l, b = x_prong.shape[0], x_prong.shape[1]
+            dev = x_prong.device
+        hidden = torch.zeros((1 + l, b, d), dtype=torch.float32, device=dev)
+        if x_event is not None:
+            hidden[0] = x_event
+        if x_prong is not None:
+            hidden[1:] = x_prong
+        mask = torch.ones((b, max(l, 0)), dtype=torch.bool, device=dev)
+        _, _, ev, pr = eng.seq(_lib.SEQ_HEADS, None, None, None, mask, hidden=hidden)
+        return ev, pr
+
+
+class EventDecoder(_HeadBase):
+    """``ProngDecoder`` surface (prong_decoder.py:13-16): (B,128) -> (B,num_event_classes)."""
+
+    def forward(self, x):
+        _lib.require_cuda(x, "event_decoder input")
+        return self._run(x.float(), None)[0]
+
+
+class ProngDecoder(_HeadBase):
+    """``ProngTargetDecoder`` surface (prong_target_decoder.py:35-41): (L,B,128) -> (L,B,num_prong_classes)."""
+
+    def forward(self, x):
+        _lib.require_cuda(x, "prong_decoder input")
+        return self._run(None, x.float())[1].transpose(0, 1)
+
+
+class NeutrinoDenseNetwork(nn.Module):
+    """Same constructor and forward as the reference class of this name."""
+
+    def __init__(self, options, features_dim: int, extra_dim: int, pixel_dim: int, num_prong_classes: int,
+                 num_event_classes: int, image_size=(PIXEL_H, PIXEL_W), precision: str = "fp32", seed: int = 0):
+        super().__init__()
+        if not (bool(options.linear_batch_norm) and bool(options.linear_prelu_activation)):
+            raise _lib.TcvnError("only linear_batch_norm=True, linear_prelu_activation=True (both shipped configs) are built")
+        if not bool(options.disable_smart_features):
+            raise _lib.TcvnError("disable_smart_features=False is not built (both shipped configs disable it)")
+        if bool(options.one_hot_pixels) or bool(getattr(options, "transformer_norm_first", False)):
+            raise _lib.TcvnError("one_hot_pixels / transformer_norm_first are not built (off in both shipped configs)")
+        if precision not in _PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
+        self.options = options
+        self.features_dim, self.extra_dim, self.pixel_dim = features_dim, extra_dim, pixel_dim
+        self.num_prong_classes, self.num_event_classes = num_prong_classes, num_event_classes
+        self.image_size = (int(image_size[0]), int(image_size[1]))
+        self.precision = precision
+        self.specs: List[TensorSpec] = network_specs(options, features_dim, extra_dim, pixel_dim, num_prong_classes,
+                                                     num_event_classes)
+        engine = _Engine(self)
+        self._engine = (engine,)
+        for name, cls in (("prong_embedding", ProngEmbedding), ("encoder", ProngEncoder),
+                          ("event_decoder", EventDecoder), ("prong_decoder", ProngDecoder)):
+            m = cls()
+            m._engine = (engine,)
+            self.add_module(name, m)
+        state = synth.init_state(self.specs, seed=seed, perturb=False)
+        for s in self.specs:
+            _attach(self, s, state[s.name])
+
+    @property
+    def engine(self) -> _Engine:
+        return self._engine[0]
+
+    def freeze_packed(self, frozen: bool = True) -> None:
+        """Serving mode: skip the per-call check for changed parameters."""
+        self.engine.frozen = frozen
+
+    def forward(self, features, extra, event_pixels, event_mask, prong_pixels, prong_mask):
+        """(B,L,F), (B,E), (B,3,H,W), (B,1) bool, (T,3,H,W), (B,L) bool -> (B,E_cls), (B,L,P_cls).
+
+        neutrino_full_base_network.py:166-188.  ``features``/``extra`` only feed the smart-feature
+        embedding, which the shipped configs disable (it contributes zeros)."""
+        _check_eval(self)
+        eng = self.engine
+        prec = _PRECISIONS[self.precision]
+        _lib.require_cuda(event_pixels, "event_pixels")
+        _lib.require_cuda(prong_pixels, "prong_pixels")
+        eng.ensure_packed(prec)
+        ev = eng.cnn("event", event_pixels, prec)
+        pr = eng.cnn("prong", prong_pixels, prec)
+        _, _, ev_logits, pr_logits = eng.seq(_lib.SEQ_TOKENS | _lib.SEQ_ENCODER | _lib.SEQ_HEADS, ev, pr, event_mask,
+                                             prong_mask)
+        return ev_logits, pr_logits
+
+    def forward_sparse(self, batch: "synth.SparseBatch"):
+        """Trainer-level path (neutrino_full_base_trainer.py:113-116): /255 + densify + network, no host sync."""
+        from .ingest import densify
+        ev = densify(batch.event_values, batch.event_coords, self.image_size, batch.num_events, 255.0)
+        pr = densify(batch.prong_values, batch.prong_coords, self.image_size, batch.num_prongs, 255.0)
+        return self.forward(batch.features, batch.extra, ev, batch.event_mask, pr, batch.prong_mask)

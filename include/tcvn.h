@@ -1,0 +1,161 @@
+/* tcvn.h — C ABI of the B200-native TransformerCVN hot path (libtcvn.so, sm_100a only).
+ *
+ * The reference (ayankele/dune-transformercvn) has no FFI: its "plugin API" for this path is
+ * Python attribute lookup.  Each entry point below names the reference
+ * interface it stands in for (paths relative to the reference tree).  The Python host side
+ * (dune_transformercvn_b200/) binds these with ctypes; INTEGRATION.md shows the binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative tcvn_status; tcvn_last_error() gives
+ *     a thread-local message.  Nothing throws, nothing allocates device memory, nothing
+ *     synchronises the stream: the caller owns every buffer and the stream.
+ *   - all pointers except descriptors are DEVICE pointers unless the name ends in _host.
+ *   - workspace sizes are queried with the matching *_bytes function.
+ *   - "arena" = the fp32 tensors of a reference sub-module's state_dict, concatenated in
+ *     state_dict order, int64 num_batches_tracked counters omitted
+ *     (dune_transformercvn_b200/params.py pins that order against the reference).
+ *   - activations are channels-last with a one-pixel zero ring: a feature map of N images,
+ *     H x W pixels and C channels is a row-major matrix [N*(H+2)*(W+2), C]; a 3x3 tap is then
+ *     a constant row offset, and the DenseNet concat is a column slice written in place.
+ */
+#ifndef TCVN_H_
+#define TCVN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCVN_ABI_VERSION 1
+#define TCVN_MAX_BLOCKS 8
+#define TCVN_MAX_DECODER_LAYERS 8
+
+typedef struct CUstream_st* tcvn_stream_t;
+
+typedef enum tcvn_status {
+  TCVN_OK = 0,
+  TCVN_ERR_ARG = -1,        /* bad descriptor / null pointer / size mismatch            */
+  TCVN_ERR_WORKSPACE = -2,  /* caller's workspace or packed buffer is too small         */
+  TCVN_ERR_CUDA = -3,       /* a CUDA runtime / driver call failed (launch, tensor map) */
+  TCVN_ERR_UNSUPPORTED = -4 /* configuration outside what the kernels were written for  */
+} tcvn_status;
+
+typedef enum tcvn_precision {
+  TCVN_FP32 = 0, /* fp32 storage, fp32 FMA accumulation (CUDA cores): the 1e-4 parity path   */
+  TCVN_BF16 = 1  /* bf16 storage, tcgen05 MMA with fp32 TMEM accumulators: the throughput path */
+} tcvn_precision;
+
+typedef enum tcvn_value_dtype { TCVN_VAL_F32 = 0, TCVN_VAL_U8 = 1 } tcvn_value_dtype;
+
+typedef enum tcvn_dense_layout {
+  TCVN_NCHW_F32 = 0 /* what transformercvn's sparse_to_dense returns */
+} tcvn_dense_layout;
+
+int tcvn_abi_version(void);
+const char* tcvn_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * K1  ingest: Minkowski-format COO hits -> dense pixel maps, value / divisor fused.
+ * Replaces: sparse_to_dense(features, coordinates, image_size)
+ *           transformercvn/network/trainers/neutrino_full_dense_trainer.py:15-24
+ *           and the "/ 255.0" of preprocess_pixels, same file :59-60.
+ * coords (nnz,3) int32 rows [image, y, x] sorted by image; values (nnz,channels) f32 or u8;
+ * out (n_images, channels, height, width) fp32, fully written (zeros + hits) in one pass.
+ * divisor == 0 means "no scaling".  Bit-exact against the reference (IEEE fp32 division).   */
+int tcvn_densify(const int32_t* coords, const void* values, tcvn_value_dtype value_dtype, int64_t nnz,
+                 int channels, int n_images, int height, int width, float divisor, float* out,
+                 tcvn_dense_layout layout, tcvn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * DenseNet pixel-map embedding.
+ * Replaces: transformercvn/network/layers/dense_net.py:97-167 (DenseNet), :8-45 (Bottleneck),
+ *           :78-94 (Transition), constructed by
+ *           transformercvn/network/networks/neutrino_full_dense_network.py:6-16.            */
+typedef struct tcvn_cnn_desc {
+  int32_t in_channels;   /* 3                      dense_net.py:112                      */
+  int32_t init_features; /* 64  initial_pixel_dim  dense_net.py:112-118                  */
+  int32_t growth;        /* 32  densenet_growth_rate                                     */
+  int32_t bn_size;       /* 4   bottleneck width = bn_size * growth                      */
+  int32_t num_blocks;    /* 5                                                            */
+  int32_t block_layers[TCVN_MAX_BLOCKS]; /* 3,6,12,6,3                                  */
+  int32_t out_features;  /* 256 (prong CNN) / 288 (event CNN)                            */
+  int32_t height, width; /* 400, 280                                                     */
+  float bn_eps;          /* 1e-5 (torch default)                                         */
+} tcvn_cnn_desc;
+
+/* number of fp32 values in the CNN's arena (state_dict order, counters omitted) */
+int64_t tcvn_cnn_arena_floats(const tcvn_cnn_desc* d);
+/* device bytes of the packed (kernel-ready) parameter block for inference */
+size_t tcvn_cnn_packed_bytes(const tcvn_cnn_desc* d, tcvn_precision prec);
+/* arena -> packed: folds eval-mode BatchNorm (running stats) into per-channel scale/shift,
+ * re-lays conv weights K-major with the channel padding of the in-place concat buffers,
+ * converts to bf16 for TCVN_BF16.  Runs on the stream; call again after the weights change. */
+int tcvn_cnn_pack(const tcvn_cnn_desc* d, tcvn_precision prec, const float* arena, void* packed,
+                  size_t packed_bytes, tcvn_stream_t stream);
+/* workspace for a forward pass over n_images images */
+size_t tcvn_cnn_workspace_bytes(const tcvn_cnn_desc* d, tcvn_precision prec, int n_images);
+/* eval-mode forward: pixels (n_images, in_channels, height, width) fp32 NCHW  ->
+ * embedding (n_images, out_features) fp32.  The workspace must have been zero-filled once
+ * after allocation (its padding rings are never written).                                  */
+int tcvn_cnn_forward(const tcvn_cnn_desc* d, tcvn_precision prec, const void* packed, const float* pixels,
+                     int n_images, float* embedding, void* workspace, size_t workspace_bytes,
+                     tcvn_stream_t stream);
+/* test hook: copies one internal feature map of the last forward (still in the workspace) to
+ * out as (n_images, channels, h, w) fp32 NCHW.  stage: 0 = stem after pool, 2b+1 = dense block
+ * b output, 2b+2 = transition b output (b from 0).  Returns the channel count in *channels.   */
+int tcvn_cnn_read_stage(const tcvn_cnn_desc* d, tcvn_precision prec, const void* workspace, int n_images,
+                        int stage, float* out, int32_t* channels, int32_t* h, int32_t* w,
+                        tcvn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Token assembly + transformer encoder + classification heads (eval mode).
+ * Replaces: BaseProngEmbedding.forward  networks/neutrino_full_base_network.py:87-125
+ *           (with layers/packed_data.py:59-76 and layers/prong_feature_embedding.py:7-33),
+ *           ProngCustomBertEncoder.forward  layers/prong_custom_bert_encoder.py:57-75,
+ *           ProngDecoder  layers/prong_decoder.py:13-16,
+ *           ProngTargetDecoder  layers/prong_target_decoder.py:35-41.                      */
+typedef struct tcvn_seq_desc {
+  int32_t hidden;        /* 128 */
+  int32_t heads;         /* 8   */
+  int32_t layers;        /* 6   */
+  int32_t ffn;           /* 128 (dim_feedforward = hidden_dim, prong_custom_bert_encoder.py:45-52) */
+  int32_t pixel_dim;     /* 256 */
+  int32_t feature_dim;   /* 32  (zeros when disable_smart_features) */
+  int32_t position_dim;  /* 32  */
+  int32_t num_event_classes; /* 4 */
+  int32_t num_prong_classes; /* 8 */
+  int32_t num_decoder_layers;                    /* 4  */
+  int32_t decoder_widths[TCVN_MAX_DECODER_LAYERS]; /* 64,32,16,8 */
+  float bn_eps;          /* 1e-5 */
+  float ln_eps;          /* 1e-5 */
+} tcvn_seq_desc;
+
+size_t tcvn_seq_packed_bytes(const tcvn_seq_desc* d);
+/* Arenas (fp32, state_dict order): position = prong_embedding.event_position_embedding (1,P)
+ * — the reference uses the EVENT vector for prong rows too (neutrino_full_base_network.py:107);
+ * combined = prong_embedding.combined_embedding.*; encoder = encoder.encoder.layers.*;
+ * event_decoder = event_decoder.hidden_layer.*; prong_decoder = prong_decoder.*             */
+int tcvn_seq_pack(const tcvn_seq_desc* d, const float* position, const float* combined, const float* encoder,
+                  const float* event_decoder, const float* prong_decoder, void* packed, size_t packed_bytes,
+                  tcvn_stream_t stream);
+
+#define TCVN_SEQ_TOKENS 1  /* embeddings -> tokens (B,S,hidden)                      */
+#define TCVN_SEQ_ENCODER 2 /* tokens -> hidden (S,B,hidden), masked                  */
+#define TCVN_SEQ_HEADS 4   /* hidden -> event_logits (B,E), prong_logits (B,L,C)     */
+/* stages: OR of the flags above; a skipped earlier stage reads its output buffer as input.
+ * event_embedding (B, pixel_dim+feature_dim), prong_embedding (T, pixel_dim) packed in
+ * (event, slot) order of the set bits of prong_mask (B,L) (uint8/bool); event_mask (B,1) may be
+ * NULL (= all true).  S = 1 + L <= 32.  tokens / hidden may be NULL when all three stages run. */
+size_t tcvn_seq_workspace_bytes(const tcvn_seq_desc* d, int n_events, int max_prongs);
+int tcvn_seq_forward(const tcvn_seq_desc* d, const void* packed, int stages, const float* event_embedding,
+                     const float* prong_embedding, const uint8_t* event_mask, const uint8_t* prong_mask,
+                     int n_events, int max_prongs, float* tokens, float* hidden, float* event_logits,
+                     float* prong_logits, void* workspace, size_t workspace_bytes, tcvn_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCVN_H_ */

@@ -1,0 +1,154 @@
+"""GPU parity (run on the B200 box: pytest -m gpu): CUDA path through the C ABI vs the CPU oracle.
+
+Tolerances: densify is bit-exact; the fp32 path must match the oracle's logits within 1e-4
+relative (max|d|/max|ref|, BASELINE.json north_star); the bf16 path within 2e-2.
+"""
+import os
+
+import pytest
+import torch
+
+from conftest import rel_err
+from dune_transformercvn_b200 import lib as tl
+from dune_transformercvn_b200 import synth
+from dune_transformercvn_b200.config import NUM_EVENT_CLASSES, NUM_PRONG_CLASSES, PathOptions
+from dune_transformercvn_b200.ingest import densify, sparse_to_dense
+from dune_transformercvn_b200.network import NeutrinoDenseNetwork
+from oracle import restate
+
+pytestmark = pytest.mark.gpu
+H, W = 400, 280
+FP32_TOL = 1e-4
+BF16_TOL = 2e-2
+
+
+@pytest.fixture(scope="module")
+def dev():
+    assert torch.cuda.is_available(), "these tests need the B200"
+    return torch.device("cuda:0")
+
+
+def _net(state_seed, perturb, dev, precision="fp32"):
+    opts = PathOptions.tutorial()
+    net = NeutrinoDenseNetwork(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES, precision=precision)
+    state = synth.init_state(net.specs, seed=state_seed, perturb=perturb)
+    net.load_state_dict(state, strict=True)
+    return net.to(dev).eval(), state, opts
+
+
+# ------------------------------------------------------------------------------------------ ingest
+def test_densify_matches_golden_bit_exact(golden_dir, dev):
+    cases = torch.load(os.path.join(golden_dir, "densify.pt"))
+    for tag, c in cases.items():
+        dense = densify(c["values"].to(dev), c["coords"].to(dev), (H, W), divisor=255.0).cpu()
+        assert list(dense.shape) == c["shape"]
+        nz = dense.nonzero()
+        assert torch.equal(nz.to(torch.int32), c["nz_index"])
+        assert torch.equal(dense[tuple(nz.t())], c["nz_value"])
+        # the drop-in signature (caller already divided, as preprocess_pixels does)
+        d2 = sparse_to_dense((c["values"] / 255.0).to(dev), c["coords"].to(dev), (H, W)).cpu()
+        assert torch.equal(d2, dense)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "u8"])
+def test_densify_matches_oracle_bit_exact(dev, dtype):
+    import numpy as np
+    b = synth.make_batch(5, seed=77, value_dtype=np.uint8 if dtype == "u8" else np.float32)
+    for vals, coords, n in ((b.event_values, b.event_coords, b.num_events), (b.prong_values, b.prong_coords, b.num_prongs)):
+        want = restate.densify(restate.preprocess_values(vals.float()), coords, H, W)
+        got = densify(vals.to(dev), coords.to(dev), (H, W), num_images=n, divisor=255.0).cpu()
+        assert torch.equal(got, want)
+
+
+def test_densify_edge_cases(dev):
+    # empty hit list with a known image count -> all zeros; single hit in the last pixel; trailing empty images
+    z = densify(torch.zeros(0, 3, device=dev), torch.zeros(0, 3, dtype=torch.int32, device=dev), (H, W), num_images=2)
+    assert z.shape == (2, 3, H, W) and float(z.abs().sum()) == 0.0
+    coords = torch.tensor([[0, 0, 0], [1, H - 1, W - 1]], dtype=torch.int32, device=dev)
+    vals = torch.tensor([[255.0, 1.0, 2.0], [3.0, 4.0, 5.0]], device=dev)
+    d = densify(vals, coords, (H, W), num_images=4, divisor=255.0).cpu()
+    assert d.shape == (4, 3, H, W) and int((d != 0).sum()) == 6
+    assert d[0, 0, 0, 0] == 1.0 and d[1, 2, H - 1, W - 1] == torch.tensor(5.0) / 255.0
+    assert float(d[2:].abs().sum()) == 0.0
+    # round trip at full size: sum of the dense map == sum of the scaled hit values, in fp64
+    b = synth.make_batch(64, seed=5)
+    dd = densify(b.prong_values.to(dev), b.prong_coords.to(dev), (H, W), num_images=b.num_prongs, divisor=255.0)
+    assert dd.shape[0] == b.num_prongs
+    assert float(dd.double().sum()) == pytest.approx(float((b.prong_values / 255.0).double().sum()), rel=1e-12)
+    assert int((dd != 0).sum()) == b.prong_values.numel()
+
+
+# ------------------------------------------------------------------------------------------ forward
+@pytest.mark.parametrize("tag", ["default", "perturbed"])
+def test_fp32_forward_matches_golden_and_oracle(golden_dir, dev, tag):
+    g = torch.load(os.path.join(golden_dir, "forward_eval.pt"))[tag]
+    net, state, opts = _net(g["seed"], g["perturb"], dev)
+    assert synth.state_checksum(state) == pytest.approx(g["state_checksum"], rel=1e-12)
+    batch = synth.make_batch(2, seed=g["batch_seed"], prongs_per_event=g["prongs"])
+    gb = batch.to(dev)
+    with torch.no_grad():
+        ev_logits, pr_logits = net.forward_sparse(gb)
+    assert rel_err(ev_logits.cpu(), g["event_logits"]) < FP32_TOL
+    assert rel_err(pr_logits.cpu(), g["prong_logits"]) < FP32_TOL
+    # per-stage: CNN feature maps, embeddings, tokens, encoder output
+    ev = densify(gb.event_values, gb.event_coords, (H, W), batch.num_events, 255.0)
+    pr = densify(gb.prong_values, gb.prong_coords, (H, W), batch.num_prongs, 255.0)
+    eng = net.engine
+    pr_emb = eng.cnn("prong", pr, tl.TCVN_FP32)
+    taps = {}
+    with torch.no_grad():
+        restate.sparse_forward(state, opts, batch, taps=taps)
+    names = ["stem_pool"]
+    for b in range(5):
+        names.append(f"dense{b + 1}")
+        if b < 4:
+            names.append(f"transition{b + 1}")
+    for stage, name in enumerate(names):
+        got = eng.read_stage("prong", batch.num_prongs, stage, tl.TCVN_FP32, dev).cpu()
+        want = taps["prong_cnn"][name]
+        assert got.shape == want.shape, name
+        assert rel_err(got, want) < FP32_TOL, name
+    assert rel_err(pr_emb.cpu(), g["prong_embedding"]) < FP32_TOL
+    ev_emb = eng.cnn("event", ev, tl.TCVN_FP32)
+    assert rel_err(ev_emb.cpu(), g["event_embedding"]) < FP32_TOL
+    with torch.no_grad():
+        tokens, mask = net.prong_embedding(gb.features, gb.extra, ev, gb.event_mask, pr, gb.prong_mask)
+        hidden = net.encoder(tokens, mask)[0]
+        ev2 = net.event_decoder(hidden[0])
+        pr2 = net.prong_decoder(hidden[1:])
+    assert rel_err(tokens.cpu(), g["tokens"]) < FP32_TOL
+    assert torch.equal(mask.cpu(), torch.cat((batch.event_mask, batch.prong_mask), 1))
+    assert rel_err(hidden.cpu(), g["hidden"]) < FP32_TOL
+    assert rel_err(ev2.cpu(), g["event_logits"]) < FP32_TOL
+    assert rel_err(pr2.cpu(), g["prong_logits"]) < FP32_TOL
+
+
+def test_fp32_forward_ragged_batch_vs_oracle(dev):
+    """Ragged prong counts incl. L=1 events and a chunk boundary (> 32 prong images), padded slots constant."""
+    net, state, opts = _net(3, True, dev)
+    batch = synth.make_batch(6, seed=99, prongs_per_event=[10, 1, 7, 9, 3, 8])
+    with torch.no_grad():
+        ev, pr = net.forward_sparse(batch.to(dev))
+        want_ev, want_pr = restate.sparse_forward(state, opts, batch)
+    assert rel_err(ev.cpu(), want_ev) < FP32_TOL
+    assert rel_err(pr.cpu(), want_pr) < FP32_TOL
+    assert (ev.argmax(-1).cpu() == want_ev.argmax(-1)).all()
+    # padded slots all carry the head's response to a zero vector (Evaluate.ipynb cell 19 behaviour)
+    pad = pr.cpu()[~batch.prong_mask]
+    assert pad.shape[0] > 1 and float((pad - pad[0]).abs().max()) == 0.0
+
+
+def test_general_mask_and_single_event(dev):
+    """Non-prefix masks pack in (event, slot) order like masked_pack_1d (packed_data.py:59-66)."""
+    net, state, opts = _net(4, True, dev)
+    batch = synth.make_batch(2, seed=5, prongs_per_event=[2, 2])
+    mask = torch.tensor([[True, False, True], [False, True, True]])
+    feats = torch.zeros(2, 3, 1)
+    ev = restate.densify(restate.preprocess_values(batch.event_values), batch.event_coords, H, W)
+    pr = restate.densify(restate.preprocess_values(batch.prong_values), batch.prong_coords, H, W)
+    with torch.no_grad():
+        want_ev, want_pr = restate.network_forward(state, opts, ev, batch.event_mask, pr, mask)
+        got_ev, got_pr = net(feats.to(dev), batch.extra.to(dev), ev.to(dev), batch.event_mask.to(dev), pr.to(dev),
+                             mask.to(dev))
+    assert rel_err(got_ev.cpu(), want_ev) < FP32_TOL
+    assert rel_err(got_pr.cpu(), want_pr) < FP32_TOL

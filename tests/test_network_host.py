@@ -1,0 +1,58 @@
+"""Host-side logic of the drop-in network (CPU): names, load_state_dict, loud failure without CUDA."""
+import json
+import os
+
+import pytest
+import torch
+
+from dune_transformercvn_b200 import lib as tl
+from dune_transformercvn_b200 import synth
+from dune_transformercvn_b200.config import NUM_EVENT_CLASSES, NUM_PRONG_CLASSES
+from dune_transformercvn_b200.network import NeutrinoDenseNetwork
+
+
+@pytest.fixture(scope="module")
+def net(tutorial_options):
+    return NeutrinoDenseNetwork(tutorial_options, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES)
+
+
+def test_state_dict_is_the_references(net, golden_dir):
+    inv = json.load(open(os.path.join(golden_dir, "state_dict_keys.json")))
+    sd = net.state_dict()
+    assert list(sd.keys()) == [k for k, _, _ in inv["keys"]]
+    assert [list(v.shape) for v in sd.values()] == [s for _, s, _ in inv["keys"]]
+    assert [str(v.dtype) for v in sd.values()] == [d for _, _, d in inv["keys"]]
+    assert [n for n, _ in net.named_parameters()] == inv["params"]
+
+
+def test_weight_decay_grouping_matches_reference_rule(net):
+    """trainers/neutrino_base.py:116-128 splits on 'bias' / 'LayerNorm.weight' substrings of the names."""
+    no_decay = ["bias", "LayerNorm.weight"]
+    b = [n for n, _ in net.named_parameters() if any(nd in n for nd in no_decay)]
+    a = [n for n, _ in net.named_parameters() if not any(nd in n for nd in no_decay)]
+    assert len(b) == 314 and len(a) == 464        # counts probed on the reference
+
+
+def test_load_state_dict_strict_roundtrip(net):
+    state = synth.init_state(net.specs, seed=5, perturb=True)
+    res = net.load_state_dict(state, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    k = "prong_embedding.event_pixel_embedding.features.dense3.layers.7.output_block.conv2.weight"
+    assert torch.equal(net.state_dict()[k], state[k])
+
+
+def test_submodule_surface(net):
+    for name in ("prong_embedding", "encoder", "event_decoder", "prong_decoder"):
+        assert callable(getattr(net, name))
+
+
+def test_cpu_call_fails_loudly(net):
+    net.eval()
+    b = synth.make_batch(1, seed=3, prongs_per_event=[1])
+    ev = torch.zeros(1, 3, 400, 280)
+    with pytest.raises(tl.TcvnError):
+        net(b.features, b.extra, ev, b.event_mask, ev, b.prong_mask)
+    net.train()
+    with pytest.raises(NotImplementedError):
+        net(b.features, b.extra, ev, b.event_mask, ev, b.prong_mask)
+    net.eval()
