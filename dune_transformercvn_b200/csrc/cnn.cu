@@ -62,16 +62,15 @@ int forward_chunk(const CnnPlan& P, const char* pk, const float* pixels, int n, 
       TCVN_TRY(launch_act_pool2(blk, n, B.H, B.W, B.ctot, B.ctot, pf(pk, B.p_t_scale), pf(pk, B.p_t_shift),
                                 pf(pk, B.p_t_alpha), pool, Nx.H, Nx.W, f32, st));
       const long long nrows = (long long)n * Nx.R;
-      if (f32) {
+      {
+        // after pool-first the transition GEMMs are 2 % of the FLOPs: CUDA-core GEMM in both precisions
         GemmArgs g{};
         g.A = pool; g.lda = B.ctot; g.m_total = nrows; g.K = B.ctot; g.taps = 1; g.tap_off[0] = 0;
         g.W = pf(pk, B.p_tw); g.N = B.toutp;
         g.o_shift = pf(pk, B.p_tb);
         g.out = ws + Nx.ws_blk; g.ldo = Nx.ctot; g.out_col0 = 0; g.ring_Hp = Nx.Hp; g.ring_Wp = Nx.Wp;
-        g.a_is_f32 = true; g.out_is_f32 = true;
+        g.a_is_f32 = f32; g.out_is_f32 = f32;
         TCVN_TRY(launch_simt_gemm(g, st));
-      } else {
-        TCVN_TRY(umma_transition(P, B, Nx, pk, pool, ws + Nx.ws_blk, nrows, st));
       }
     }
   }

@@ -159,8 +159,7 @@ extern "C" int tcvn_cnn_pack(const tcvn_cnn_desc* d, tcvn_precision prec, const 
     }
     if (B.has_transition) {
       TCVN_TRY(fold(arena, B.tnorm, nullptr, B.c0, B.c0p, B.tkpad, eps, pk, B.p_t_scale, B.p_t_shift, B.p_t_alpha, st));
-      if (bf) TCVN_TRY(repack(arena + B.tconv_w, B.tout, B.clog, 1, B.c0, B.c0p, B.tkpad, B.toutp, true, true, pk + B.p_tw, st));
-      else TCVN_TRY(repack(arena + B.tconv_w, B.tout, B.clog, 1, B.c0, B.c0p, B.ctot, B.toutp, false, false, pk + B.p_tw, st));
+      TCVN_TRY(repack(arena + B.tconv_w, B.tout, B.clog, 1, B.c0, B.c0p, B.ctot, B.toutp, false, false, pk + B.p_tw, st));
       TCVN_TRY(pad_copy(arena + B.tconv_b, B.tout, reinterpret_cast<float*>(pk + B.p_tb), B.toutp, st));
     }
   }

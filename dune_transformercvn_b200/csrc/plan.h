@@ -51,7 +51,7 @@ struct BlockPlan {
   int tout, toutp;  // logical / padded output channels (= next block's c0 / c0p)
   int tkpad;        // ctot rounded up to kKChunk
   size_t p_t_scale, p_t_shift, p_t_alpha;  // [ctot] fp32
-  size_t p_tw;                             // fp32: [ctot][toutp] ; bf16: [toutp][tkpad]
+  size_t p_tw;                             // [ctot][toutp] fp32 (CUDA-core GEMM in both precisions)
   size_t p_tb;                             // [toutp] fp32
   // workspace offsets (bytes)
   size_t ws_blk;
@@ -165,7 +165,7 @@ inline bool CnnPlan::build(const tcvn_cnn_desc& d, tcvn_precision prec, int n_im
       B.p_t_scale = ptake(B.tkpad * 4);
       B.p_t_shift = ptake(B.tkpad * 4);
       B.p_t_alpha = ptake(B.tkpad * 4);
-      B.p_tw = ptake(prec == TCVN_BF16 ? (size_t)B.toutp * B.tkpad * wsz : (size_t)B.ctot * B.toutp * wsz);
+      B.p_tw = ptake((size_t)B.ctot * B.toutp * 4);
       B.p_tb = ptake(B.toutp * 4);
       c = B.tout;
       H /= 2; W /= 2;  // AvgPool2d(2, 2) floors

@@ -416,7 +416,7 @@ extern "C" int tcvn_seq_forward(const tcvn_seq_desc* d, const void* packed, int 
                                 const float* prong_embedding, const uint8_t* event_mask, const uint8_t* prong_mask,
                                 int n_events, int max_prongs, float* tokens, float* hidden, float* event_logits,
                                 float* prong_logits, void* workspace, size_t workspace_bytes, tcvn_stream_t stream) {
-  TCVN_CHECK_ARG(d && packed && prong_mask && workspace, "seq_forward: null pointer");
+  TCVN_CHECK_ARG(d && packed && workspace && (prong_mask || max_prongs == 0), "seq_forward: null pointer");
   TCVN_CHECK_ARG(stages > 0 && stages < 8, "seq_forward: bad stage mask %d", stages);
   TCVN_CHECK_ARG(stages != (TCVN_SEQ_TOKENS | TCVN_SEQ_HEADS), "seq_forward: stages must be contiguous");
   TCVN_CHECK_ARG(n_events >= 0 && max_prongs >= 0, "seq_forward: negative size");
@@ -433,7 +433,7 @@ extern "C" int tcvn_seq_forward(const tcvn_seq_desc* d, const void* packed, int 
   if (enc && !tok) TCVN_CHECK_ARG(tokens, "seq_forward: tokens input missing");
   if (enc && !hd) TCVN_CHECK_ARG(hidden, "seq_forward: hidden output missing");
   if (hd && !enc) TCVN_CHECK_ARG(hidden, "seq_forward: hidden input missing");
-  if (hd) TCVN_CHECK_ARG(event_logits && prong_logits, "seq_forward: logits output missing");
+  if (hd) TCVN_CHECK_ARG(event_logits && (prong_logits || max_prongs == 0), "seq_forward: logits output missing");
   int* offsets = static_cast<int*>(workspace);
   cudaStream_t st = stream;
   prong_offsets_kernel<<<1, 256, 0, st>>>(prong_mask, n_events, max_prongs, offsets);

@@ -1,9 +1,470 @@
+// bf16 tcgen05 path of the DenseNet bottleneck layer (dense_net.py:8-45), sm_100a.
+//
+//   conv1 kernel   mid = PReLU2(BN2(conv1x1(PReLU1(BN1(blk[:, :k]))) + b1))
+//       GEMM  M = pixels (128-row tiles of the ringed channels-last buffer), N = 128, K = k (64-wide chunks).
+//       TMA loads the RAW concat tile and the weight chunk; 4 transform warps apply BN1+PReLU1 in place in
+//       the 128B-swizzled tile (each layer has its own BN over the same concat channels, so the activation
+//       cannot be stored once); one thread issues tcgen05.mma into a double-buffered TMEM accumulator;
+//       4 epilogue warps read TMEM, apply bias+BN2+PReLU2, zero the ring rows and store bf16.
+//   conv2 kernel   blk[:, k:k+32] = conv3x3(mid) + b2      (zero padding == the ring of `mid`)
+//       shifted GEMM: a 3x3 tap is a constant row offset in the ringed layout, so ONE haloed tile
+//       (128 + 2*(Wp+1) rows x 128 ch) is loaded per output tile and the 9 taps are 9 MMA groups whose A
+//       descriptors start at different rows of that tile; the 9x32x128 weights stay resident in SMEM.
+// Both kernels are persistent (one CTA per SM, static round-robin over tiles) and warp-specialised.
+#include <mutex>
+#include <map>
+#include <tuple>
+#include <stdlib.h>
+
+#include "ptx.cuh"
 #include "umma.h"
+
 namespace tcvn {
-int umma_dense_layer(const CnnPlan&, const BlockPlan&, const LayerPlan&, const char*, void*, void*, long long, cudaStream_t) {
-  return fail(TCVN_ERR_UNSUPPORTED, "bf16 tcgen05 path not built yet");
+
+using bf16 = __nv_bfloat16;
+
+// ------------------------------------------------------------------------------------------------
+// host: tensor maps
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
 }
-int umma_transition(const CnnPlan&, const BlockPlan&, const BlockPlan&, const char*, const void*, void*, long long, cudaStream_t) {
-  return fail(TCVN_ERR_UNSUPPORTED, "bf16 tcgen05 path not built yet");
+
+// bf16 row-major matrix [rows][cols] with `pitch` elements per row; box = box_cols x box_rows, 128B swizzle,
+// out-of-bounds elements (negative rows included) read as zero.
+static int make_map(const void* base, long long rows, int cols, int pitch, int box_cols, int box_rows,
+                    CUtensorMap* out) {
+  typedef std::tuple<const void*, long long, int, int, int, int> Key;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  Key key(base, rows, cols, pitch, box_cols, box_rows);
+  {
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return TCVN_OK; }
+  }
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(TCVN_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)pitch * sizeof(bf16)};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(TCVN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%d pitch=%d box=%dx%d", (int)r, rows,
+                cols, pitch, box_cols, box_rows);
+  std::lock_guard<std::mutex> g(mu);
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = *out;
+  return TCVN_OK;
 }
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv1: fused BN1+PReLU1 -> 1x1 conv -> bias+BN2+PReLU2
+// ------------------------------------------------------------------------------------------------
+constexpr int kC1Stages = 4;
+constexpr int kC1Threads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 transform, warps 6-9 epilogue
+constexpr int kTileM = 128;
+constexpr int kMid = 128;        // bottleneck width the kernels are specialised for
+constexpr int kStageA = kTileM * 128;  // 16 KB: 128 rows x 64 bf16
+constexpr int kStageW = kMid * 128;    // 16 KB: 128 out-channels x 64 bf16
+
+struct Conv1Params {
+  long long m_total;
+  int kchunks, kphys;
+  const float *a_scale, *a_shift, *a_alpha, *o_scale, *o_shift, *o_alpha;
+  bf16* out;
+  int ldo, Hp, Wp, num_tiles;
+};
+
+__device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kC1Threads, 1) umma_conv1_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                   const __grid_constant__ CUtensorMap tmW,
+                                                                   const Conv1Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;                                   // [stages][16 KB]
+  uint8_t* sW = smem + kC1Stages * kStageA;             // [stages][16 KB]
+  float* s_epi = reinterpret_cast<float*>(sW + kC1Stages * kStageW);  // o_scale | o_shift | o_alpha  [3][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + 3 * kMid);
+  uint64_t* full = bars;                    // TMA -> transform
+  uint64_t* ready = bars + kC1Stages;       // transform -> MMA
+  uint64_t* empty = bars + 2 * kC1Stages;   // MMA -> TMA
+  uint64_t* tfull = bars + 3 * kC1Stages;   // MMA -> epilogue   [2]
+  uint64_t* tempty = tfull + 2;             // epilogue -> MMA   [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kC1Stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&ready[s], 128); ptx::mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 128); }
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW);
+  }
+  for (int i = threadIdx.x; i < kMid; i += blockDim.x) {
+    s_epi[i] = p.o_scale[i];
+    s_epi[kMid + i] = p.o_shift[i];
+    s_epi[2 * kMid + i] = p.o_alpha[i];
+  }
+  if (warp == 0) ptx::tmem_alloc(tmem_slot, 256);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[stage], kStageA + kStageW);
+          ptx::tma_load_2d(sA + stage * kStageA, &tmA, &full[stage], kc * 64, tile * kTileM);
+          ptx::tma_load_2d(sW + stage * kStageW, &tmW, &full[stage], kc * 64, 0);
+          if (++stage == kC1Stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(kTileM, kMid);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kMid;
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          ptx::mbar_wait(&ready[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(sA + stage * kStageA);
+          const uint32_t w_addr = ptx::smem_u32(sW + stage * kStageW);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            ptx::umma_bf16(d_tmem, ptx::umma_desc_sw128(a_addr + k * 32, 0), ptx::umma_desc_sw128(w_addr + k * 32, 0),
+                           idesc, (kc | k) != 0);
+          ptx::umma_commit(&empty[stage]);
+          if (++stage == kC1Stages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tfull[acc]);
+        if ((acc ^= 1) == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp < 6) {
+    // transform: thread owns 16-byte chunk `pc` of rows rb, rb+16, ... ; with the 128B swizzle the chunk at
+    // physical position pc of row r holds channels 8*(pc ^ (r & 7)); (rb + 16 i) & 7 == rb & 7, so one
+    // thread always sees the same 8 channels of a K chunk and keeps their BN/PReLU constants in registers.
+    const int t = threadIdx.x - 64;
+    const int pc = t & 7, rb = t >> 3;
+    const int cg = pc ^ (rb & 7);
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      for (int kc = 0; kc < p.kchunks; ++kc) {
+        const int ch = kc * 64 + cg * 8;
+        const bool live = ch < p.kphys;  // kphys is a multiple of 8: a group is all-live or all-dead
+        float sc[8], sh[8], al[8];
+        {
+          const float4* s4 = reinterpret_cast<const float4*>(p.a_scale + ch);
+          const float4* h4 = reinterpret_cast<const float4*>(p.a_shift + ch);
+          const float4* a4 = reinterpret_cast<const float4*>(p.a_alpha + ch);
+          float4 x0 = __ldg(s4), x1 = __ldg(s4 + 1), y0 = __ldg(h4), y1 = __ldg(h4 + 1), z0 = __ldg(a4), z1 = __ldg(a4 + 1);
+          sc[0] = x0.x; sc[1] = x0.y; sc[2] = x0.z; sc[3] = x0.w; sc[4] = x1.x; sc[5] = x1.y; sc[6] = x1.z; sc[7] = x1.w;
+          sh[0] = y0.x; sh[1] = y0.y; sh[2] = y0.z; sh[3] = y0.w; sh[4] = y1.x; sh[5] = y1.y; sh[6] = y1.z; sh[7] = y1.w;
+          al[0] = z0.x; al[1] = z0.y; al[2] = z0.z; al[3] = z0.w; al[4] = z1.x; al[5] = z1.y; al[6] = z1.z; al[7] = z1.w;
+        }
+        ptx::mbar_wait(&full[stage], phase);
+        uint8_t* base = sA + stage * kStageA + rb * 128 + pc * 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint4* q = reinterpret_cast<uint4*>(base + i * 16 * 128);
+          uint4 v = *q;
+          uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float lo = prelu(fmaf(bf_lo(w[j]), sc[2 * j], sh[2 * j]), al[2 * j]);
+            float hi = prelu(fmaf(bf_hi(w[j]), sc[2 * j + 1], sh[2 * j + 1]), al[2 * j + 1]);
+            w[j] = live ? pack_bf16(lo, hi) : 0u;
+          }
+          *q = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&ready[stage]);
+        if (++stage == kC1Stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    const int g = warp & 3;             // TMEM lane group this warp may read
+    const int row = g * 32 + lane;
+    const int R = p.Hp * p.Wp;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const long long m = (long long)tile * kTileM + row;
+      bool ring = false;
+      {
+        const int rr = (int)(m % R);
+        const int y = rr / p.Wp, x = rr - y * p.Wp;
+        ring = y == 0 || y == p.Hp - 1 || x == 0 || x == p.Wp - 1;
+      }
+      const bool store = m < p.m_total;
+      ptx::mbar_wait(&tfull[acc], acc_phase);
+      ptx::tc_fence_after();
+      bf16* orow = p.out + m * p.ldo;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(g * 32) << 16) + acc * kMid + c * 32, r);
+        ptx::tmem_ld_wait();
+        uint32_t o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = c * 32 + 2 * j;
+          float v0 = prelu(fmaf(__uint_as_float(r[2 * j]), s_epi[n], s_epi[kMid + n]), s_epi[2 * kMid + n]);
+          float v1 = prelu(fmaf(__uint_as_float(r[2 * j + 1]), s_epi[n + 1], s_epi[kMid + n + 1]), s_epi[2 * kMid + n + 1]);
+          o[j] = ring ? 0u : pack_bf16(v0, v1);
+        }
+        if (store) {
+          uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tempty[acc]);
+      if ((acc ^= 1) == 0) acc_phase ^= 1;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, 256);
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv2: 3x3 convolution as a shifted GEMM over one haloed tile
+// ------------------------------------------------------------------------------------------------
+constexpr int kC2Stages = 2;
+constexpr int kC2Threads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kGrowth = 32;
+constexpr int kBoxRows = 32;
+constexpr int kW2Bytes = 9 * 2 * kGrowth * 128;  // 72 KB: [tap][half][32 rows x 128 B]
+
+struct Conv2Params {
+  long long m_total;
+  int Hp, Wp, halo_rows, nbox;  // halo_rows = nbox * kBoxRows >= 128 + 2*(Wp+1)
+  const float* bias;
+  bf16* out;
+  int ldo, col0, num_tiles, base_offset_mode;
+};
+
+__global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                   const __grid_constant__ CUtensorMap tmW,
+                                                                   const Conv2Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int half_bytes = p.halo_rows * 128;
+  const int stage_bytes = 2 * half_bytes;
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + kW2Bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + kC2Stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kC2Stages;
+  uint64_t* tfull = bars + 2 * kC2Stages;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* wfull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kC2Stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 128); }
+    ptx::mbar_init(wfull, 1);
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW);
+  }
+  if (threadIdx.x < kGrowth) s_bias[threadIdx.x] = p.bias[threadIdx.x];
+  if (warp == 0) ptx::tmem_alloc(tmem_slot, 64);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int halo = p.Wp + 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(wfull, kW2Bytes);
+      for (int t = 0; t < 9; ++t)
+        for (int h = 0; h < 2; ++h)
+          ptx::tma_load_2d(sW + (t * 2 + h) * 4096, &tmW, wfull, h * 64, t * kGrowth);
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        ptx::mbar_arrive_expect_tx(&full[stage], stage_bytes);
+        const int row0 = tile * kTileM - halo;
+        for (int h = 0; h < 2; ++h)
+          for (int b = 0; b < p.nbox; ++b)
+            ptx::tma_load_2d(sA + stage * stage_bytes + h * half_bytes + b * kBoxRows * 128, &tmA, &full[stage], h * 64,
+                             row0 + b * kBoxRows);
+        if (++stage == kC2Stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(kTileM, kGrowth);
+      ptx::mbar_wait(wfull, 0);
+      const uint32_t w_addr = ptx::smem_u32(sW);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+        ptx::mbar_wait(&full[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kGrowth;
+        const uint32_t a_stage = ptx::smem_u32(sA + stage * stage_bytes);
+        for (int t = 0; t < 9; ++t) {
+          const int rowstart = halo + (t / 3 - 1) * p.Wp + (t % 3 - 1);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t a_addr = a_stage + (kk >> 2) * half_bytes + rowstart * 128 + (kk & 3) * 32;
+            const uint32_t b_addr = w_addr + (t * 2 + (kk >> 2)) * 4096 + (kk & 3) * 32;
+            const uint32_t bo = p.base_offset_mode ? ((a_addr >> 7) & 7u) : 0u;
+            ptx::umma_bf16(d_tmem, ptx::umma_desc_sw128(a_addr, bo), ptx::umma_desc_sw128(b_addr, 0), idesc, (t | kk) != 0);
+          }
+        }
+        ptx::umma_commit(&empty[stage]);
+        ptx::umma_commit(&tfull[acc]);
+        if (++stage == kC2Stages) { stage = 0; phase ^= 1; }
+        if ((acc ^= 1) == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int g = warp & 3;
+    const int row = g * 32 + lane;
+    const int R = p.Hp * p.Wp;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const long long m = (long long)tile * kTileM + row;
+      bool ring = false;
+      {
+        const int rr = (int)(m % R);
+        const int y = rr / p.Wp, x = rr - y * p.Wp;
+        ring = y == 0 || y == p.Hp - 1 || x == 0 || x == p.Wp - 1;
+      }
+      ptx::mbar_wait(&tfull[acc], acc_phase);
+      ptx::tc_fence_after();
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(g * 32) << 16) + acc * kGrowth, r);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tempty[acc]);
+      if (m < p.m_total) {
+        uint32_t o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          o[j] = ring ? 0u : pack_bf16(__uint_as_float(r[2 * j]) + s_bias[2 * j], __uint_as_float(r[2 * j + 1]) + s_bias[2 * j + 1]);
+        uint4* dst = reinterpret_cast<uint4*>(p.out + m * p.ldo + p.col0);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+      }
+      if ((acc ^= 1) == 0) acc_phase ^= 1;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, 64);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------------------
+static inline const float* pf(const char* packed, size_t off) { return reinterpret_cast<const float*>(packed + off); }
+
+int umma_dense_layer(const CnnPlan& P, const BlockPlan& B, const LayerPlan& L, const char* pk, void* blk, void* mid,
+                     long long rows, cudaStream_t st) {
+  if (P.mid != kMid || P.d.growth != kGrowth)
+    return fail(TCVN_ERR_UNSUPPORTED, "tcgen05 path is specialised for bottleneck width 128 / growth 32 (got %d / %d)",
+                P.mid, P.d.growth);
+  if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one chunk");
+  const int tiles = (int)ceil_div_ll(rows, kTileM);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  static bool attr_done = false;
+  const size_t smem1 = 1024 + kC1Stages * (kStageA + kStageW) + 3 * kMid * 4 + (3 * kC1Stages + 4) * 8 + 16;
+  const int halo_rows_max = 288;
+  if (!attr_done) {
+    TCVN_CUDA(cudaFuncSetAttribute(umma_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    TCVN_CUDA(cudaFuncSetAttribute(umma_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   1024 + kW2Bytes + kC2Stages * 2 * halo_rows_max * 128 + 256));
+    attr_done = true;
+  }
+  // ---- conv1
+  CUtensorMap tmA, tmW;
+  TCVN_TRY(make_map(blk, rows, B.ctot, B.ctot, 64, kTileM, &tmA));
+  TCVN_TRY(make_map(pk + L.p_w1, kMid, L.kpad, L.kpad, 64, kMid, &tmW));
+  Conv1Params c1;
+  c1.m_total = rows; c1.kchunks = L.kpad / kKChunk; c1.kphys = L.kphys;
+  c1.a_scale = pf(pk, L.p_a_scale); c1.a_shift = pf(pk, L.p_a_shift); c1.a_alpha = pf(pk, L.p_a_alpha);
+  c1.o_scale = pf(pk, L.p_o_scale); c1.o_shift = pf(pk, L.p_o_shift); c1.o_alpha = pf(pk, L.p_o_alpha);
+  c1.out = static_cast<bf16*>(mid); c1.ldo = kMid; c1.Hp = B.Hp; c1.Wp = B.Wp; c1.num_tiles = tiles;
+  umma_conv1_kernel<<<grid, kC1Threads, smem1, st>>>(tmA, tmW, c1);
+  TCVN_LAUNCH_CHECK();
+  // ---- conv2
+  Conv2Params c2;
+  c2.m_total = rows; c2.Hp = B.Hp; c2.Wp = B.Wp;
+  c2.nbox = ceil_div(kTileM + 2 * (B.Wp + 1), kBoxRows);
+  c2.halo_rows = c2.nbox * kBoxRows;
+  if (c2.halo_rows > halo_rows_max)
+    return fail(TCVN_ERR_UNSUPPORTED, "feature map width %d needs a %d-row halo tile (max %d)", B.W, c2.halo_rows, halo_rows_max);
+  c2.bias = pf(pk, L.p_b2);
+  c2.out = static_cast<bf16*>(blk); c2.ldo = B.ctot; c2.col0 = L.kphys; c2.num_tiles = tiles;
+  // Measured on B200: the 128B swizzle of a UMMA operand is a function of the absolute shared-memory address
+  // (bits [4,7) ^= bits [7,10)), exactly as TMA wrote it, so a descriptor may start at ANY row of the haloed
+  // tile with matrix-base-offset 0 (setting it to (addr >> 7) & 7 gives wrong results).
+  c2.base_offset_mode = 0;
+  CUtensorMap tmM, tmW2;
+  TCVN_TRY(make_map(mid, rows, kMid, kMid, 64, kBoxRows, &tmM));
+  TCVN_TRY(make_map(pk + L.p_w2, 9 * kGrowth, kMid, kMid, 64, kGrowth, &tmW2));
+  const size_t smem2 = 1024 + kW2Bytes + (size_t)kC2Stages * 2 * c2.halo_rows * 128 + 256;
+  umma_conv2_kernel<<<grid, kC2Threads, smem2, st>>>(tmM, tmW2, c2);
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+int umma_transition(const CnnPlan&, const BlockPlan&, const BlockPlan&, const char*, const void*, void*, long long,
+                    cudaStream_t) {
+  return fail(TCVN_ERR_UNSUPPORTED, "transition runs on the CUDA-core GEMM in this build");
+}
+
 }  // namespace tcvn

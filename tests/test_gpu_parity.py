@@ -152,3 +152,69 @@ def test_general_mask_and_single_event(dev):
                              mask.to(dev))
     assert rel_err(got_ev.cpu(), want_ev) < FP32_TOL
     assert rel_err(got_pr.cpu(), want_pr) < FP32_TOL
+
+
+# ------------------------------------------------------------------------------------------ bf16 tcgen05 path
+def test_bf16_forward_vs_oracle_and_fp32_path(dev):
+    """bf16 storage + tcgen05 MMA (fp32 accumulate): logits within 2e-2 of the fp32 oracle, same top-1."""
+    net, state, opts = _net(1, True, dev, precision="bf16")
+    batch = synth.make_batch(6, seed=42, prongs_per_event=[10, 1, 7, 9, 3, 8])
+    gb = batch.to(dev)
+    with torch.no_grad():
+        ev, pr = net.forward_sparse(gb)
+        want_ev, want_pr = restate.sparse_forward(state, opts, batch)
+    assert not torch.isnan(ev).any() and not torch.isnan(pr).any()
+    assert rel_err(ev.cpu(), want_ev) < BF16_TOL
+    assert rel_err(pr.cpu(), want_pr) < BF16_TOL
+    assert (ev.argmax(-1).cpu() == want_ev.argmax(-1)).all()
+    valid = batch.prong_mask
+    assert (pr.argmax(-1).cpu()[valid] == want_pr.argmax(-1)[valid]).float().mean() >= 0.999
+    # run-to-run determinism of the tensor-core path
+    with torch.no_grad():
+        ev2, pr2 = net.forward_sparse(gb)
+    assert torch.equal(ev, ev2) and torch.equal(pr, pr2)
+
+
+def test_bf16_feature_maps_stage_by_stage(dev):
+    """Every dense block / transition output of the tcgen05 path against the oracle (bf16 rounding level)."""
+    net, state, opts = _net(1, True, dev, precision="bf16")
+    batch = synth.make_batch(2, seed=21, prongs_per_event=[3, 1])
+    gb = batch.to(dev)
+    taps = {}
+    with torch.no_grad():
+        restate.sparse_forward(state, opts, batch, taps=taps)
+    pr = densify(gb.prong_values, gb.prong_coords, (H, W), batch.num_prongs, 255.0)
+    eng = net.engine
+    eng.ensure_packed(tl.TCVN_BF16)
+    emb = eng.cnn("prong", pr, tl.TCVN_BF16)
+    names = ["stem_pool"]
+    for b in range(5):
+        names.append(f"dense{b + 1}")
+        if b < 4:
+            names.append(f"transition{b + 1}")
+    for stage, name in enumerate(names):
+        got = eng.read_stage("prong", batch.num_prongs, stage, tl.TCVN_BF16, dev).cpu()
+        assert rel_err(got, taps["prong_cnn"][name]) < BF16_TOL, name
+    assert rel_err(emb.cpu(), taps["prong_embedding"]) < BF16_TOL
+
+
+def test_bf16_linearity_of_conv_tiles_at_full_size(dev):
+    """Size-independent property at BASELINE size (256 events): permuting the events permutes the logits
+    exactly (tiles, chunks and the haloed 3x3 loads never mix images)."""
+    net, state, opts = _net(0, False, dev, precision="bf16")
+    batch = synth.make_batch(256, seed=1234)
+    gb = batch.to(dev)
+    with torch.no_grad():
+        ev, pr = net.forward_sparse(gb)
+        # same events, reversed order
+        ev_px = densify(gb.event_values, gb.event_coords, (H, W), batch.num_events, 255.0)
+        pr_px = densify(gb.prong_values, gb.prong_coords, (H, W), batch.num_prongs, 255.0)
+        counts = torch.tensor(batch.prongs_per_event)
+        starts = torch.cumsum(counts, 0) - counts
+        order = torch.arange(255, -1, -1)
+        pr_idx = torch.cat([torch.arange(int(starts[i]), int(starts[i] + counts[i])) for i in order]).to(dev)
+        ev2, pr2 = net(gb.features[order.to(dev)], gb.extra[order.to(dev)], ev_px[order.to(dev)],
+                       gb.event_mask[order.to(dev)], pr_px[pr_idx], gb.prong_mask[order.to(dev)])
+    assert torch.isfinite(ev).all() and torch.isfinite(pr).all()
+    assert torch.equal(ev2.flip(0), ev)
+    assert torch.equal(pr2.flip(0), pr)
