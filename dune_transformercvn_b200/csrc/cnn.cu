@@ -6,7 +6,8 @@
 //                        blk[b][:, k_i : k_i+32] = conv2_3x3(mid)                     (one shifted GEMM)
 //   transition b:        blk[b+1][:, 0:c/2] = conv1x1(avgpool2(PReLU(BN(blk[b]))))    (pool first: 4x fewer FLOPs)
 //   tail:                embedding = PReLU(BN1d(Linear(mean_hw(PReLU(BN(blk[last]))))))
-// Images are processed in chunks so a chunk's block buffer stays L2-resident between its layers.
+// Images are processed in per-block chunks (plan.h) so a block's concat buffer stays L2-resident between its
+// layers while the small late blocks still get enough rows per launch to fill the machine.
 #include "kernels.h"
 #include "plan.h"
 #include "umma.h"
@@ -19,21 +20,27 @@ namespace {
 
 inline const float* pf(const char* packed, size_t off) { return reinterpret_cast<const float*>(packed + off); }
 
-int forward_chunk(const CnnPlan& P, const char* pk, const float* pixels, int n, float* embedding, char* ws,
-                  cudaStream_t st) {
-  const tcvn_cnn_desc& d = P.d;
-  const bool f32 = P.prec == TCVN_FP32;
-  void* stem = ws + P.ws_stem;
-  void* mid = ws + P.ws_mid;
-  void* pool = ws + P.ws_pool;
-  float* gap = reinterpret_cast<float*>(ws + P.ws_gap);
-  TCVN_TRY(launch_stem_conv(pixels, n, d.in_channels, d.height, d.width, pf(pk, P.p_w0), pf(pk, P.p_s_scale),
-                            pf(pk, P.p_s_shift), pf(pk, P.p_s_alpha), d.init_features, stem, f32, st));
-  const BlockPlan& B0 = P.blocks[0];
-  TCVN_TRY(launch_stem_pool(stem, n, P.Hs, P.Ws, d.init_features, ws + B0.ws_blk, B0.ctot, B0.H, B0.W, f32, st));
-  for (size_t b = 0; b < P.blocks.size(); ++b) {
-    const BlockPlan& B = P.blocks[b];
+struct Walk {
+  const CnnPlan& P;
+  const char* pk;
+  const float* pixels;  // whole batch
+  char* ws;
+  cudaStream_t st;
+  bool f32;
+
+  int stem(int i0, int n) {
+    const tcvn_cnn_desc& d = P.d;
+    const size_t img_floats = (size_t)d.in_channels * d.height * d.width;
+    const BlockPlan& B0 = P.blocks[0];
+    return launch_stem(pixels + (size_t)i0 * img_floats, n, d.in_channels, d.height, d.width, pf(pk, P.p_w0),
+                       pf(pk, P.p_s_scale), pf(pk, P.p_s_shift), pf(pk, P.p_s_alpha), d.init_features, ws + B0.ws_blk,
+                       B0.ctot, B0.H, B0.W, f32, st);
+  }
+
+  int dense_block(const BlockPlan& B, int n) {
+    const tcvn_cnn_desc& d = P.d;
     void* blk = ws + B.ws_blk;
+    void* mid = ws + P.ws_mid;
     const long long rows = (long long)n * B.R;
     for (const LayerPlan& L : B.layers) {
       if (f32) {
@@ -57,35 +64,57 @@ int forward_chunk(const CnnPlan& P, const char* pk, const float* pixels, int n, 
         TCVN_TRY(umma_dense_layer(P, B, L, pk, blk, mid, rows, st));
       }
     }
-    if (B.has_transition) {
-      const BlockPlan& Nx = P.blocks[b + 1];
-      TCVN_TRY(launch_act_pool2(blk, n, B.H, B.W, B.ctot, B.ctot, pf(pk, B.p_t_scale), pf(pk, B.p_t_shift),
-                                pf(pk, B.p_t_alpha), pool, Nx.H, Nx.W, f32, st));
-      const long long nrows = (long long)n * Nx.R;
-      {
-        // after pool-first the transition GEMMs are 2 % of the FLOPs: CUDA-core GEMM in both precisions
-        GemmArgs g{};
-        g.A = pool; g.lda = B.ctot; g.m_total = nrows; g.K = B.ctot; g.taps = 1; g.tap_off[0] = 0;
-        g.W = pf(pk, B.p_tw); g.N = B.toutp;
-        g.o_shift = pf(pk, B.p_tb);
-        g.out = ws + Nx.ws_blk; g.ldo = Nx.ctot; g.out_col0 = 0; g.ring_Hp = Nx.Hp; g.ring_Wp = Nx.Wp;
-        g.a_is_f32 = f32; g.out_is_f32 = f32;
-        TCVN_TRY(launch_simt_gemm(g, st));
+    return TCVN_OK;
+  }
+
+  // transition after block b over n images -> images [j, j+n) of block b+1's buffer
+  int transition(int b, int n, int j) {
+    const BlockPlan& B = P.blocks[b];
+    const BlockPlan& Nx = P.blocks[b + 1];
+    void* pool = ws + P.ws_pool;
+    TCVN_TRY(launch_act_pool2(ws + B.ws_blk, n, B.H, B.W, B.ctot, B.ctot, pf(pk, B.p_t_scale), pf(pk, B.p_t_shift),
+                              pf(pk, B.p_t_alpha), pool, Nx.H, Nx.W, f32, st));
+    // after pool-first the transition GEMMs are 2 % of the FLOPs: CUDA-core GEMM in both precisions
+    GemmArgs g{};
+    g.A = pool; g.lda = B.ctot; g.m_total = (long long)n * Nx.R; g.K = B.ctot; g.taps = 1; g.tap_off[0] = 0;
+    g.W = pf(pk, B.p_tw); g.N = B.toutp;
+    g.o_shift = pf(pk, B.p_tb);
+    g.out = ws + Nx.ws_blk + (size_t)j * Nx.R * Nx.ctot * P.esize; g.ldo = Nx.ctot; g.out_col0 = 0;
+    g.ring_Hp = Nx.Hp; g.ring_Wp = Nx.Wp;
+    g.a_is_f32 = f32; g.out_is_f32 = f32;
+    return launch_simt_gemm(g, st);
+  }
+
+  // fills block b's buffer for images [i0, i0+n) of the batch and runs its dense layers
+  int process(int b, int i0, int n) {
+    if (b == 0) {
+      TCVN_TRY(stem(i0, n));
+    } else {
+      const int sub = P.blocks[b - 1].chunk;
+      for (int j = 0; j < n; j += sub) {
+        const int m = n - j < sub ? n - j : sub;
+        TCVN_TRY(process(b - 1, i0 + j, m));
+        TCVN_TRY(transition(b - 1, m, j));
       }
     }
+    return dense_block(P.blocks[b], n);
   }
-  const BlockPlan& last = P.blocks.back();
-  TCVN_TRY(launch_act_gap(ws + last.ws_blk, n, last.H, last.W, last.ctot, last.ctot, pf(pk, P.p_f_scale),
-                          pf(pk, P.p_f_shift), pf(pk, P.p_f_alpha), gap, f32, st));
-  GemmArgs g{};
-  g.A = gap; g.lda = last.ctot; g.m_total = n; g.K = last.ctot; g.taps = 1; g.tap_off[0] = 0;
-  g.W = pf(pk, P.p_lw); g.N = d.out_features;
-  g.o_scale = pf(pk, P.p_lo_scale); g.o_shift = pf(pk, P.p_lo_shift); g.o_alpha = pf(pk, P.p_lo_alpha);
-  g.out = embedding; g.ldo = d.out_features; g.out_col0 = 0;
-  g.a_is_f32 = true; g.out_is_f32 = true;
-  TCVN_TRY(launch_simt_gemm(g, st));
-  return TCVN_OK;
-}
+
+  int tail(int n, float* embedding) {
+    const tcvn_cnn_desc& d = P.d;
+    const BlockPlan& last = P.blocks.back();
+    float* gap = reinterpret_cast<float*>(ws + P.ws_gap);
+    TCVN_TRY(launch_act_gap(ws + last.ws_blk, n, last.H, last.W, last.ctot, last.ctot, pf(pk, P.p_f_scale),
+                            pf(pk, P.p_f_shift), pf(pk, P.p_f_alpha), gap, f32, st));
+    GemmArgs g{};
+    g.A = gap; g.lda = last.ctot; g.m_total = n; g.K = last.ctot; g.taps = 1; g.tap_off[0] = 0;
+    g.W = pf(pk, P.p_lw); g.N = d.out_features;
+    g.o_scale = pf(pk, P.p_lo_scale); g.o_shift = pf(pk, P.p_lo_shift); g.o_alpha = pf(pk, P.p_lo_alpha);
+    g.out = embedding; g.ldo = d.out_features; g.out_col0 = 0;
+    g.a_is_f32 = true; g.out_is_f32 = true;
+    return launch_simt_gemm(g, st);
+  }
+};
 
 }  // namespace
 
@@ -101,11 +130,13 @@ extern "C" int tcvn_cnn_forward(const tcvn_cnn_desc* d, tcvn_precision prec, con
   TCVN_CHECK_ARG(CnnPlan::build(*d, prec, n_images, &P), "cnn_forward: bad descriptor");
   if (workspace_bytes < P.ws_bytes)
     return fail(TCVN_ERR_WORKSPACE, "cnn_forward: workspace %zu < %zu bytes", workspace_bytes, P.ws_bytes);
-  const size_t img_floats = (size_t)d->in_channels * d->height * d->width;
-  for (int i0 = 0; i0 < n_images; i0 += P.chunk) {
-    const int n = n_images - i0 < P.chunk ? n_images - i0 : P.chunk;
-    TCVN_TRY(forward_chunk(P, static_cast<const char*>(packed), pixels + (size_t)i0 * img_floats, n,
-                           embedding + (size_t)i0 * d->out_features, static_cast<char*>(workspace), stream));
+  Walk w{P, static_cast<const char*>(packed), pixels, static_cast<char*>(workspace), stream, prec == TCVN_FP32};
+  const int last = (int)P.blocks.size() - 1;
+  const int top = P.blocks[last].chunk;
+  for (int i0 = 0; i0 < n_images; i0 += top) {
+    const int n = n_images - i0 < top ? n_images - i0 : top;
+    TCVN_TRY(w.process(last, i0, n));
+    TCVN_TRY(w.tail(n, embedding + (size_t)i0 * d->out_features));
   }
   return TCVN_OK;
 }

@@ -20,12 +20,11 @@ struct GemmArgs {
 };
 int launch_simt_gemm(const GemmArgs& g, cudaStream_t stream);
 
-// conv0 7x7 s2 p3 + bias + BN0 + PReLU0 on NCHW fp32 pixels -> [n, Hs, Ws, C0] (no ring)
-int launch_stem_conv(const float* pixels, int n, int cin, int H, int W, const float* w0, const float* s_scale,
-                     const float* s_shift, const float* s_alpha, int c0, void* out, bool out_f32, cudaStream_t stream);
-// AvgPool2d(3, 2) of the stem output into channels [0, c) of block 0's ringed buffer
-int launch_stem_pool(const void* in, int n, int Hs, int Ws, int c, void* blk, int ldo, int H, int W, bool f32,
-                     cudaStream_t stream);
+// stem, fused: conv0 7x7 s2 p3 + bias + BN0 + PReLU0 + AvgPool2d(3,2) on NCHW fp32 pixels -> channels [0, c0) of
+// block 0's ringed buffer [n, Hb+2, Wb+2, ldo]
+int launch_stem(const float* pixels, int n, int cin, int H, int W, const float* w0, const float* s_scale,
+                const float* s_shift, const float* s_alpha, int c0, void* blk, int ldo, int Hb, int Wb, bool f32,
+                cudaStream_t stream);
 // transition front half: BN + PReLU + AvgPool2d(2,2) of a ringed block buffer into a ringed buffer of the next geometry
 int launch_act_pool2(const void* blk, int n, int H, int W, int ld, int c, const float* scale, const float* shift,
                      const float* alpha, void* out, int H2, int W2, bool f32, cudaStream_t stream);

@@ -16,7 +16,6 @@ namespace tcvn {
 
 constexpr int kChanAlign = 8;      // concat-buffer channel slices start on 16-byte (bf16) boundaries
 constexpr int kKChunk = 64;        // bf16 K tile = one 128-byte swizzle row
-constexpr int kDefaultChunk = 32;  // images per pass through the CNN
 
 inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
 
@@ -53,8 +52,9 @@ struct BlockPlan {
   size_t p_t_scale, p_t_shift, p_t_alpha;  // [ctot] fp32
   size_t p_tw;                             // [ctot][toutp] fp32 (CUDA-core GEMM in both precisions)
   size_t p_tb;                             // [toutp] fp32
-  // workspace offsets (bytes)
-  size_t ws_blk;
+  // workspace
+  int chunk;      // images of this block processed per pass
+  size_t ws_blk;  // byte offset
 };
 
 struct CnnPlan {
@@ -186,24 +186,39 @@ inline bool CnnPlan::build(const tcvn_cnn_desc& d, tcvn_precision prec, int n_im
   P.p_lo_shift = ptake(d.out_features * 4);
   P.p_lo_alpha = ptake(d.out_features * 4);
   P.packed_bytes = p;
-  // workspace
-  P.chunk = n_images < kDefaultChunk ? (n_images < 1 ? 1 : n_images) : kDefaultChunk;
+  // workspace: block b is processed `chunk` images at a time, sized so that its concat buffer plus the
+  // bottleneck intermediate stay L2-resident between layers (126 MB L2); later blocks have smaller maps and
+  // take whole multiples of the previous block's chunk so that their launches still fill the 148 SMs.
+  const size_t l2_budget = (size_t)80 << 20;
+  int prev = 0;
+  for (auto& B : P.blocks) {
+    const size_t per_image = (size_t)B.R * (B.ctot + P.mid) * P.esize;
+    int c = (int)(l2_budget / per_image);
+    if (c < 1) c = 1;
+    if (prev) c = c / prev * prev;
+    if (c < prev) c = prev;
+    if (c > 1024) c = prev ? 1024 / prev * prev : 1024;
+    if (prev == 0 && c > n_images) c = n_images < 1 ? 1 : n_images;
+    if (prev && c > n_images) c = (n_images + prev - 1) / prev * prev;  // never larger than the batch needs
+    B.chunk = c;
+    prev = c;
+  }
+  P.chunk = P.blocks[0].chunk;
   size_t w = 0;
   auto wtake = [&](size_t bytes) { size_t o = w; w += (bytes + 1023) / 1024 * 1024; return o; };
-  const size_t n = P.chunk;
-  P.ws_stem = wtake(n * P.Hs * P.Ws * d.init_features * P.esize);
+  P.ws_stem = 0;  // the stem is fused with its pooling: no pre-pool map in memory
   size_t mid_rows = 0, pool_elems = 0;
   for (auto& B : P.blocks) {
-    B.ws_blk = wtake(n * B.R * (size_t)B.ctot * P.esize);
-    if ((size_t)B.R > mid_rows) mid_rows = B.R;
+    B.ws_blk = wtake((size_t)B.chunk * B.R * (size_t)B.ctot * P.esize);
+    if ((size_t)B.chunk * B.R > mid_rows) mid_rows = (size_t)B.chunk * B.R;
   }
   for (size_t b = 0; b + 1 < P.blocks.size(); ++b) {
-    size_t e = (size_t)P.blocks[b + 1].R * P.blocks[b].ctot;
+    size_t e = (size_t)P.blocks[b].chunk * P.blocks[b + 1].R * P.blocks[b].ctot;
     if (e > pool_elems) pool_elems = e;
   }
-  P.ws_mid = wtake(n * mid_rows * P.mid * P.esize);
-  P.ws_pool = wtake(n * pool_elems * P.esize + 1024);
-  P.ws_gap = wtake(n * (size_t)last.ctot * 4);
+  P.ws_mid = wtake(mid_rows * P.mid * P.esize);
+  P.ws_pool = wtake(pool_elems * P.esize + 1024);
+  P.ws_gap = wtake((size_t)P.blocks.back().chunk * (size_t)last.ctot * 4);
   P.ws_bytes = w;
   return true;
 }

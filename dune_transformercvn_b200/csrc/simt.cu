@@ -138,122 +138,130 @@ int launch_simt_gemm(const GemmArgs& a, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Stem: direct 7x7 stride-2 convolution on NCHW fp32 pixels, fused bias + BN0 + PReLU0.
-// One thread per output pixel, 64 output channels in registers; the pixel maps are ~99 % zeros, so a
-// warp skips a tap when none of its 32 input values is non-zero (adding 0*w is exact, so skipping
-// it is bit-identical).
+// Stem, fused: 7x7 stride-2 convolution on NCHW fp32 pixels + bias + BN0 + PReLU0 + AvgPool2d(3, 2),
+// written straight into channels [0, 64) of block 0's ringed buffer (dense_net.py:111-122).  The
+// 64 x 200 x 140 pre-pool map (3.6 MB/image in bf16 - the largest tensor of the network) never
+// reaches memory.  Persistent CTAs keep the 147 x 64 filter bank in shared memory and loop over
+// 8 x 8 tiles of pooled pixels (17 x 17 conv outputs, 39 x 39 x 3 input window).  One thread per
+// conv output, 64 channels in registers; the pixel maps are ~99 % zeros, so a warp skips a tap when
+// none of its 32 input values is non-zero (adding 0*w is exact: skipping is bit-identical).
 // ------------------------------------------------------------------------------------------------
-constexpr int kStemTile = 16;
-constexpr int kStemIn = 2 * kStemTile + 5;  // 37 input rows/cols per tile
+constexpr int kStemTP = 8;                   // pooled tile edge
+constexpr int kStemTC = 2 * kStemTP + 1;     // 17 conv outputs per edge
+constexpr int kStemIn = 2 * kStemTC + 5;     // 39 input pixels per edge
+constexpr int kStemThreads = 320;            // 289 conv outputs -> 10 warps
 
 template <typename TO, int C0>
-__global__ void __launch_bounds__(256) stem_conv_kernel(const float* __restrict__ pixels, int cin, int H, int W, int Hs,
-                                                        int Ws, const float* __restrict__ w0,
-                                                        const float* __restrict__ s_scale,
-                                                        const float* __restrict__ s_shift,
-                                                        const float* __restrict__ s_alpha, TO* __restrict__ out) {
+__global__ void __launch_bounds__(kStemThreads) stem_fused_kernel(const float* __restrict__ pixels, int n_images, int cin,
+                                                                  int H, int W, int Hs, int Ws,
+                                                                  const float* __restrict__ w0,
+                                                                  const float* __restrict__ s_scale,
+                                                                  const float* __restrict__ s_shift,
+                                                                  const float* __restrict__ s_alpha,
+                                                                  TO* __restrict__ blk, int ldo, int Hb, int Wb) {
   extern __shared__ __align__(16) float smem[];
-  float* wsm = smem;                          // [cin*49][C0]
-  float* ism = smem + cin * 49 * C0;          // [cin][37][37+1]
-  const int n = blockIdx.z;
-  const int oy0 = blockIdx.y * kStemTile, ox0 = blockIdx.x * kStemTile;
-  const int iy0 = 2 * oy0 - 3, ix0 = 2 * ox0 - 3;
+  float* wsm = smem;                                        // [cin*49][C0]
+  float* ism = wsm + cin * 49 * C0;                         // [cin][39][40]
+  TO* csm = reinterpret_cast<TO*>(ism + cin * kStemIn * (kStemIn + 1));  // [289][C0] activated conv outputs
   for (int i = threadIdx.x; i < cin * 49 * C0; i += blockDim.x) wsm[i] = __ldg(w0 + i);
-  const float* img = pixels + (size_t)n * cin * H * W;
-  for (int i = threadIdx.x; i < cin * kStemIn * kStemIn; i += blockDim.x) {
-    const int c = i / (kStemIn * kStemIn);
-    const int r = i - c * kStemIn * kStemIn;
-    const int yy = r / kStemIn, xx = r - yy * kStemIn;
-    const int y = iy0 + yy, x = ix0 + xx;
-    float v = 0.f;
-    if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(img + ((size_t)c * H + y) * W + x);
-    ism[(c * kStemIn + yy) * (kStemIn + 1) + xx] = v;
-  }
-  __syncthreads();
-  const int ty = threadIdx.x / kStemTile, tx = threadIdx.x % kStemTile;
-  float acc[C0];
+  const int tiles_x = (Wb + kStemTP - 1) / kStemTP, tiles_y = (Hb + kStemTP - 1) / kStemTP;
+  const int per_image = tiles_x * tiles_y;
+  const long long total = (long long)n_images * per_image;
+  const int t = threadIdx.x;
+  const bool active = t < kStemTC * kStemTC;
+  const int cy = active ? t / kStemTC : 0, cx = active ? t % kStemTC : 0;
+  for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int n = (int)(tile / per_image);
+    const int rem = (int)(tile - (long long)n * per_image);
+    const int py0 = (rem / tiles_x) * kStemTP, px0 = (rem % tiles_x) * kStemTP;
+    const int iy0 = 4 * py0 - 3, ix0 = 4 * px0 - 3;
+    const float* img = pixels + (size_t)n * cin * H * W;
+    __syncthreads();  // previous tile's pooling reads of csm / conv reads of ism are done
+    for (int i = t; i < cin * kStemIn * kStemIn; i += blockDim.x) {
+      const int c = i / (kStemIn * kStemIn);
+      const int r = i - c * kStemIn * kStemIn;
+      const int yy = r / kStemIn, xx = r - yy * kStemIn;
+      const int y = iy0 + yy, x = ix0 + xx;
+      float v = 0.f;
+      if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(img + ((size_t)c * H + y) * W + x);
+      ism[(c * kStemIn + yy) * (kStemIn + 1) + xx] = v;
+    }
+    __syncthreads();
+    float acc[C0];
 #pragma unroll
-  for (int j = 0; j < C0; ++j) acc[j] = 0.f;
-  for (int c = 0; c < cin; ++c)
-    for (int ky = 0; ky < 7; ++ky) {
-      const float* irow = ism + (c * kStemIn + 2 * ty + ky) * (kStemIn + 1) + 2 * tx;
+    for (int j = 0; j < C0; ++j) acc[j] = 0.f;
+    for (int c = 0; c < cin; ++c)
+      for (int ky = 0; ky < 7; ++ky) {
+        const float* irow = ism + (c * kStemIn + 2 * cy + ky) * (kStemIn + 1) + 2 * cx;
 #pragma unroll
-      for (int kx = 0; kx < 7; ++kx) {
-        const float v = irow[kx];
-        if (__any_sync(0xffffffffu, v != 0.f)) {
-          const float4* w4 = reinterpret_cast<const float4*>(wsm + ((c * 7 + ky) * 7 + kx) * C0);
+        for (int kx = 0; kx < 7; ++kx) {
+          const float v = active ? irow[kx] : 0.f;
+          if (__any_sync(0xffffffffu, v != 0.f)) {
+            const float4* w4 = reinterpret_cast<const float4*>(wsm + ((c * 7 + ky) * 7 + kx) * C0);
 #pragma unroll
-          for (int j = 0; j < C0 / 4; ++j) {
-            const float4 w = w4[j];
-            acc[4 * j + 0] = fmaf(v, w.x, acc[4 * j + 0]);
-            acc[4 * j + 1] = fmaf(v, w.y, acc[4 * j + 1]);
-            acc[4 * j + 2] = fmaf(v, w.z, acc[4 * j + 2]);
-            acc[4 * j + 3] = fmaf(v, w.w, acc[4 * j + 3]);
+            for (int j = 0; j < C0 / 4; ++j) {
+              const float4 w = w4[j];
+              acc[4 * j + 0] = fmaf(v, w.x, acc[4 * j + 0]);
+              acc[4 * j + 1] = fmaf(v, w.y, acc[4 * j + 1]);
+              acc[4 * j + 2] = fmaf(v, w.z, acc[4 * j + 2]);
+              acc[4 * j + 3] = fmaf(v, w.w, acc[4 * j + 3]);
+            }
           }
         }
       }
+    if (active) {
+      TO* o = csm + (size_t)t * C0;
+#pragma unroll
+      for (int j = 0; j < C0; ++j)
+        o[j] = from_f32<TO>(prelu(fmaf(acc[j], __ldg(s_scale + j), __ldg(s_shift + j)), __ldg(s_alpha + j)));
     }
-  const int oy = oy0 + ty, ox = ox0 + tx;
-  if (oy < Hs && ox < Ws) {
-    TO* o = out + (((size_t)n * Hs + oy) * Ws + ox) * C0;
+    __syncthreads();
+    for (int i = t; i < kStemTP * kStemTP * C0; i += blockDim.x) {
+      const int ch = i % C0;
+      const int p = i / C0;
+      const int pyl = p / kStemTP, pxl = p % kStemTP;
+      const int py = py0 + pyl, px = px0 + pxl;
+      if (py >= Hb || px >= Wb) continue;
+      float s = 0.f;
 #pragma unroll
-    for (int j = 0; j < C0; ++j)
-      o[j] = from_f32<TO>(prelu(fmaf(acc[j], __ldg(s_scale + j), __ldg(s_shift + j)), __ldg(s_alpha + j)));
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) s += to_f32<TO>(csm[((2 * pyl + dy) * kStemTC + 2 * pxl + dx) * C0 + ch]);
+      const size_t row = (size_t)n * (Hb + 2) * (Wb + 2) + (size_t)(py + 1) * (Wb + 2) + (px + 1);
+      blk[row * ldo + ch] = from_f32<TO>(s / 9.0f);
+    }
   }
 }
 
-int launch_stem_conv(const float* pixels, int n, int cin, int H, int W, const float* w0, const float* s_scale,
-                     const float* s_shift, const float* s_alpha, int c0, void* out, bool out_f32,
-                     cudaStream_t stream) {
+int launch_stem(const float* pixels, int n, int cin, int H, int W, const float* w0, const float* s_scale,
+                const float* s_shift, const float* s_alpha, int c0, void* blk, int ldo, int Hb, int Wb, bool f32,
+                cudaStream_t stream) {
   if (c0 != 64) return fail(TCVN_ERR_UNSUPPORTED, "stem: init_features %d (kernel is specialised for 64)", c0);
+  if (n == 0) return TCVN_OK;
   const int Hs = (H + 6 - 7) / 2 + 1, Ws = (W + 6 - 7) / 2 + 1;
-  const size_t smem = ((size_t)cin * 49 * c0 + (size_t)cin * kStemIn * (kStemIn + 1)) * sizeof(float);
-  if (smem > 200 * 1024) return fail(TCVN_ERR_UNSUPPORTED, "stem: %d input channels do not fit shared memory", cin);
-  dim3 grid(ceil_div(Ws, kStemTile), ceil_div(Hs, kStemTile), n);
-  if (out_f32) {
-    TCVN_CUDA(cudaFuncSetAttribute(stem_conv_kernel<float, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stem_conv_kernel<float, 64><<<grid, 256, smem, stream>>>(pixels, cin, H, W, Hs, Ws, w0, s_scale, s_shift, s_alpha,
-                                                             static_cast<float*>(out));
-  } else {
-    TCVN_CUDA(cudaFuncSetAttribute(stem_conv_kernel<__nv_bfloat16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem));
-    stem_conv_kernel<__nv_bfloat16, 64><<<grid, 256, smem, stream>>>(pixels, cin, H, W, Hs, Ws, w0, s_scale, s_shift,
-                                                                     s_alpha, static_cast<__nv_bfloat16*>(out));
+  if ((Hs - 3) / 2 + 1 != Hb || (Ws - 3) / 2 + 1 != Wb) return fail(TCVN_ERR_ARG, "stem: geometry mismatch");
+  const size_t smem = ((size_t)cin * 49 * c0 + (size_t)cin * kStemIn * (kStemIn + 1)) * sizeof(float) +
+                      (size_t)kStemTC * kStemTC * c0 * (f32 ? 4 : 2);
+  if (smem > 220 * 1024) return fail(TCVN_ERR_UNSUPPORTED, "stem: %d input channels do not fit shared memory", cin);
+  int sms = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  TCVN_LAUNCH_CHECK();
-  return TCVN_OK;
-}
-
-// AvgPool2d(kernel 3, stride 2, no padding): [n,Hs,Ws,c] -> ringed block buffer channels [0,c)
-template <typename T>
-__global__ void stem_pool_kernel(const T* __restrict__ in, int Hs, int Ws, int c, T* __restrict__ blk, int ldo, int H,
-                                 int W, long long total) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int ch = (int)(idx % c);
-  long long r = idx / c;
-  const int x = (int)(r % W); r /= W;
-  const int y = (int)(r % H);
-  const int n = (int)(r / H);
-  const T* src = in + (((size_t)n * Hs + 2 * y) * Ws + 2 * x) * c + ch;
-  float s = 0.f;
-#pragma unroll
-  for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-    for (int dx = 0; dx < 3; ++dx) s += to_f32<T>(src[((size_t)dy * Ws + dx) * c]);
-  const size_t row = (size_t)n * (H + 2) * (W + 2) + (size_t)(y + 1) * (W + 2) + (x + 1);
-  blk[row * ldo + ch] = from_f32<T>(s / 9.0f);
-}
-
-int launch_stem_pool(const void* in, int n, int Hs, int Ws, int c, void* blk, int ldo, int H, int W, bool f32,
-                     cudaStream_t stream) {
-  const long long total = (long long)n * H * W * c;
-  if (total == 0) return TCVN_OK;
-  const unsigned grid = (unsigned)ceil_div_ll(total, 256);
-  if (f32) stem_pool_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(in), Hs, Ws, c,
-                                                             static_cast<float*>(blk), ldo, H, W, total);
-  else stem_pool_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), Hs, Ws, c,
-                                                                 static_cast<__nv_bfloat16*>(blk), ldo, H, W, total);
+  const long long tiles = (long long)n * ((Wb + kStemTP - 1) / kStemTP) * ((Hb + kStemTP - 1) / kStemTP);
+  const int per_sm = f32 ? 1 : 2;
+  const int grid = (int)(tiles < (long long)sms * per_sm ? tiles : (long long)sms * per_sm);
+  if (f32) {
+    TCVN_CUDA(cudaFuncSetAttribute(stem_fused_kernel<float, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stem_fused_kernel<float, 64><<<grid, kStemThreads, smem, stream>>>(pixels, n, cin, H, W, Hs, Ws, w0, s_scale, s_shift,
+                                                                        s_alpha, static_cast<float*>(blk), ldo, Hb, Wb);
+  } else {
+    TCVN_CUDA(cudaFuncSetAttribute(stem_fused_kernel<__nv_bfloat16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+    stem_fused_kernel<__nv_bfloat16, 64><<<grid, kStemThreads, smem, stream>>>(
+        pixels, n, cin, H, W, Hs, Ws, w0, s_scale, s_shift, s_alpha, static_cast<__nv_bfloat16*>(blk), ldo, Hb, Wb);
+  }
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
 }

@@ -112,12 +112,14 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 
 __global__ void __launch_bounds__(kC1Threads, 1) umma_conv1_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmW,
+                                                                   const __grid_constant__ CUtensorMap tmO,
                                                                    const Conv1Params p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                   // [stages][16 KB]
   uint8_t* sW = smem + kC1Stages * kStageA;             // [stages][16 KB]
-  float* s_epi = reinterpret_cast<float*>(sW + kC1Stages * kStageW);  // o_scale | o_shift | o_alpha  [3][128]
+  uint8_t* sOut = sW + kC1Stages * kStageW;             // 32 KB output staging: 2 halves x [128 rows x 128 B], swizzled
+  float* s_epi = reinterpret_cast<float*>(sOut + 2 * kStageA);  // o_scale | o_shift | o_alpha  [3][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + 3 * kMid);
   uint64_t* full = bars;                    // TMA -> transform
   uint64_t* ready = bars + kC1Stages;       // transform -> MMA
@@ -133,6 +135,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_conv1_kernel(const __grid_
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmW);
+    ptx::prefetch_tmap(&tmO);
   }
   for (int i = threadIdx.x; i < kMid; i += blockDim.x) {
     s_epi[i] = p.o_scale[i];
@@ -226,9 +229,12 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_conv1_kernel(const __grid_
       }
     }
   } else {
+    // epilogue: TMEM -> registers -> bias+BN2+PReLU2 -> bf16 -> swizzled SMEM tile -> TMA store (coalesced,
+    // asynchronous; rows past the end of the buffer are clipped by the tensor map)
     const int g = warp & 3;             // TMEM lane group this warp may read
     const int row = g * 32 + lane;
     const int R = p.Hp * p.Wp;
+    const bool issuer = threadIdx.x == 6 * 32;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const long long m = (long long)tile * kTileM + row;
@@ -238,33 +244,49 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_conv1_kernel(const __grid_
         const int y = rr / p.Wp, x = rr - y * p.Wp;
         ring = y == 0 || y == p.Hp - 1 || x == 0 || x == p.Wp - 1;
       }
-      const bool store = m < p.m_total;
       ptx::mbar_wait(&tfull[acc], acc_phase);
       ptx::tc_fence_after();
-      bf16* orow = p.out + m * p.ldo;
+      if (issuer) ptx::tma_store_wait_read();  // the previous tile's store has drained the staging tile
+      ptx::named_bar_sync(1, 128);
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(g * 32) << 16) + acc * kMid + c * 32, r);
         ptx::tmem_ld_wait();
-        uint32_t o[16];
+        uint8_t* orow = sOut + (c >> 1) * kStageA + row * 128;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int n = c * 32 + 2 * j;
-          float v0 = prelu(fmaf(__uint_as_float(r[2 * j]), s_epi[n], s_epi[kMid + n]), s_epi[2 * kMid + n]);
-          float v1 = prelu(fmaf(__uint_as_float(r[2 * j + 1]), s_epi[n + 1], s_epi[kMid + n + 1]), s_epi[2 * kMid + n + 1]);
-          o[j] = ring ? 0u : pack_bf16(v0, v1);
-        }
-        if (store) {
-          uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+        for (int q = 0; q < 4; ++q) {
+          uint32_t o[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+          for (int h = 0; h < 2; ++h) {
+            const int n = c * 32 + q * 8 + h * 4;
+            const float4 sc = *reinterpret_cast<const float4*>(s_epi + n);
+            const float4 sh = *reinterpret_cast<const float4*>(s_epi + kMid + n);
+            const float4 al = *reinterpret_cast<const float4*>(s_epi + 2 * kMid + n);
+            const int j = q * 8 + h * 4;
+            const float v0 = prelu(fmaf(__uint_as_float(r[j + 0]), sc.x, sh.x), al.x);
+            const float v1 = prelu(fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y), al.y);
+            const float v2 = prelu(fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z), al.z);
+            const float v3 = prelu(fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w), al.w);
+            o[2 * h] = ring ? 0u : pack_bf16(v0, v1);
+            o[2 * h + 1] = ring ? 0u : pack_bf16(v2, v3);
+          }
+          const int chunk = (c & 1) * 4 + q;  // 16-byte chunk within the 128-byte half-row
+          *reinterpret_cast<uint4*>(orow + ((chunk ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty[acc]);
+      ptx::fence_proxy_async_smem();
+      ptx::named_bar_sync(1, 128);
+      if (issuer) {
+        ptx::tma_store_2d(&tmO, sOut, 0, tile * kTileM);
+        ptx::tma_store_2d(&tmO, sOut + kStageA, 64, tile * kTileM);
+        ptx::tma_store_commit();
+      }
       if ((acc ^= 1) == 0) acc_phase ^= 1;
     }
+    if (issuer) ptx::tma_store_wait_all();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -345,7 +367,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
     if (lane == 0) {
       const uint32_t idesc = ptx::umma_idesc_bf16(kTileM, kGrowth);
       ptx::mbar_wait(wfull, 0);
-      const uint32_t w_addr = ptx::smem_u32(sW);
+      const uint32_t w_lo = ptx::umma_desc_lo(ptx::smem_u32(sW));
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -354,14 +376,22 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kGrowth;
         const uint32_t a_stage = ptx::smem_u32(sA + stage * stage_bytes);
-        for (int t = 0; t < 9; ++t) {
-          const int rowstart = halo + (t / 3 - 1) * p.Wp + (t % 3 - 1);
+        // 72 MMAs, straight-line: descriptors differ only in their 14-bit start-address field, which moves in
+        // 16-byte units: +8 per row, +2 per K step of 16 channels (all offsets below are in those units)
+        const uint32_t a_lo = ptx::umma_desc_lo(a_stage);
+        const uint32_t half16 = (uint32_t)half_bytes >> 4;
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint32_t a_addr = a_stage + (kk >> 2) * half_bytes + rowstart * 128 + (kk & 3) * 32;
-            const uint32_t b_addr = w_addr + (t * 2 + (kk >> 2)) * 4096 + (kk & 3) * 32;
-            const uint32_t bo = p.base_offset_mode ? ((a_addr >> 7) & 7u) : 0u;
-            ptx::umma_bf16(d_tmem, ptx::umma_desc_sw128(a_addr, bo), ptx::umma_desc_sw128(b_addr, 0), idesc, (t | kk) != 0);
+        for (int dy = 0; dy < 3; ++dy) {
+          const uint32_t row_lo = a_lo + (uint32_t)(halo + (dy - 1) * p.Wp - 1) * 8u;
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+            for (int kk = 0; kk < 8; ++kk) {
+              const uint32_t al = row_lo + dx * 8u + (kk >> 2) * half16 + (kk & 3) * 2u;
+              const uint32_t bl = w_lo + ((dy * 3 + dx) * 2 + (kk >> 2)) * 256u + (kk & 3) * 2u;
+              ptx::umma_bf16(d_tmem, ptx::umma_desc_join(ptx::kUmmaDescHiSw128, al),
+                             ptx::umma_desc_join(ptx::kUmmaDescHiSw128, bl), idesc, (dy | dx | kk) != 0);
+            }
           }
         }
         ptx::umma_commit(&empty[stage]);
@@ -421,7 +451,7 @@ int umma_dense_layer(const CnnPlan& P, const BlockPlan& B, const LayerPlan& L, c
   const int tiles = (int)ceil_div_ll(rows, kTileM);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   static bool attr_done = false;
-  const size_t smem1 = 1024 + kC1Stages * (kStageA + kStageW) + 3 * kMid * 4 + (3 * kC1Stages + 4) * 8 + 16;
+  const size_t smem1 = 1024 + kC1Stages * (kStageA + kStageW) + 2 * kStageA + 3 * kMid * 4 + (3 * kC1Stages + 4) * 8 + 16;
   const int halo_rows_max = 288;
   if (!attr_done) {
     TCVN_CUDA(cudaFuncSetAttribute(umma_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
@@ -430,15 +460,16 @@ int umma_dense_layer(const CnnPlan& P, const BlockPlan& B, const LayerPlan& L, c
     attr_done = true;
   }
   // ---- conv1
-  CUtensorMap tmA, tmW;
+  CUtensorMap tmA, tmW, tmO;
   TCVN_TRY(make_map(blk, rows, B.ctot, B.ctot, 64, kTileM, &tmA));
   TCVN_TRY(make_map(pk + L.p_w1, kMid, L.kpad, L.kpad, 64, kMid, &tmW));
+  TCVN_TRY(make_map(mid, rows, kMid, kMid, 64, kTileM, &tmO));
   Conv1Params c1;
   c1.m_total = rows; c1.kchunks = L.kpad / kKChunk; c1.kphys = L.kphys;
   c1.a_scale = pf(pk, L.p_a_scale); c1.a_shift = pf(pk, L.p_a_shift); c1.a_alpha = pf(pk, L.p_a_alpha);
   c1.o_scale = pf(pk, L.p_o_scale); c1.o_shift = pf(pk, L.p_o_shift); c1.o_alpha = pf(pk, L.p_o_alpha);
   c1.out = static_cast<bf16*>(mid); c1.ldo = kMid; c1.Hp = B.Hp; c1.Wp = B.Wp; c1.num_tiles = tiles;
-  umma_conv1_kernel<<<grid, kC1Threads, smem1, st>>>(tmA, tmW, c1);
+  umma_conv1_kernel<<<grid, kC1Threads, smem1, st>>>(tmA, tmW, tmO, c1);
   TCVN_LAUNCH_CHECK();
   // ---- conv2
   Conv2Params c2;
