@@ -74,7 +74,9 @@ struct Walk {
     void* pool = ws + P.ws_pool;
     TCVN_TRY(launch_act_pool2(ws + B.ws_blk, n, B.H, B.W, B.ctot, B.ctot, pf(pk, B.p_t_scale), pf(pk, B.p_t_shift),
                               pf(pk, B.p_t_alpha), pool, Nx.H, Nx.W, f32, st));
-    // after pool-first the transition GEMMs are 2 % of the FLOPs: CUDA-core GEMM in both precisions
+    if (!f32)
+      return umma_transition(P, B, Nx, pk, pool, ws + Nx.ws_blk + (size_t)j * Nx.R * Nx.ctot * P.esize,
+                             (long long)n * Nx.R, st);
     GemmArgs g{};
     g.A = pool; g.lda = B.ctot; g.m_total = (long long)n * Nx.R; g.K = B.ctot; g.taps = 1; g.tap_off[0] = 0;
     g.W = pf(pk, B.p_tw); g.N = B.toutp;

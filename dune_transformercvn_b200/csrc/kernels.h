@@ -39,7 +39,8 @@ int launch_ring_to_nchw(const void* blk, int n, int H, int W, int ld, int c, int
 int fold(const float* arena, const BnArena& bn, const float* conv_bias, int c0, int c0p, int n_out, float eps,
          char* packed, size_t o_scale, size_t o_shift, size_t o_alpha, cudaStream_t st);
 int repack(const float* src, int n_log, int k_log, int taps, int c0, int c0p, int K_out, int N_out, bool k_major,
-           bool bf16, void* dst, cudaStream_t st);
+           bool bf16, void* dst, cudaStream_t st, const float* row_bn_w = nullptr, const float* row_bn_rv = nullptr,
+           float eps = 0.f);
 int pad_copy(const float* src, int n_log, float* dst, int n_out, cudaStream_t st);
 
 #define TCVN_TRY(expr)                \

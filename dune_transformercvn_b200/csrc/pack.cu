@@ -45,6 +45,8 @@ struct RepackArgs {
   int k_major;       // 1: dst[tap][n][k]  (K contiguous) ; 0: dst[tap][k][n]
   int bf16;
   void* dst;
+  // optional per-output-row scale = bn_w[n] / sqrt(bn_rv[n] + eps): folds the BatchNorm that FOLLOWS this conv
+  const float* row_bn_w; const float* row_bn_rv; float eps;
 };
 
 __global__ void repack_kernel(const RepackArgs a) {
@@ -65,7 +67,10 @@ __global__ void repack_kernel(const RepackArgs a) {
   if (kp < a.c0) k = kp;
   else if (kp >= a.c0p) k = kp - (a.c0p - a.c0);
   float v = 0.f;
-  if (k >= 0 && k < a.k_log && n < a.n_log) v = a.src[((size_t)n * a.k_log + k) * a.taps + tap];
+  if (k >= 0 && k < a.k_log && n < a.n_log) {
+    v = a.src[((size_t)n * a.k_log + k) * a.taps + tap];
+    if (a.row_bn_w) v *= a.row_bn_w[n] / sqrtf(a.row_bn_rv[n] + a.eps);
+  }
   if (a.bf16) static_cast<__nv_bfloat16*>(a.dst)[idx] = __float2bfloat16_rn(v);
   else static_cast<float*>(a.dst)[idx] = v;
 }
@@ -73,6 +78,11 @@ __global__ void repack_kernel(const RepackArgs a) {
 __global__ void pad_copy_kernel(const float* src, int n_log, float* dst, int n_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_out) dst[i] = i < n_log ? src[i] : 0.f;
+}
+
+__global__ void fill_kernel(float* dst, int n, float v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = v;
 }
 
 int pad_copy(const float* src, int n_log, float* dst, int n_out, cudaStream_t st) {
@@ -95,8 +105,9 @@ int fold(const float* arena, const BnArena& bn, const float* conv_bias, int c0, 
 }
 
 int repack(const float* src, int n_log, int k_log, int taps, int c0, int c0p, int K_out, int N_out, bool k_major,
-                  bool bf16, void* dst, cudaStream_t st) {
+           bool bf16, void* dst, cudaStream_t st, const float* row_bn_w, const float* row_bn_rv, float eps) {
   RepackArgs r;
+  r.row_bn_w = row_bn_w; r.row_bn_rv = row_bn_rv; r.eps = eps;
   r.src = src; r.n_log = n_log; r.k_log = k_log; r.taps = taps; r.c0 = c0; r.c0p = c0p; r.K_out = K_out; r.N_out = N_out;
   r.k_major = k_major; r.bf16 = bf16; r.dst = dst;
   const long long total = (long long)taps * K_out * N_out;
@@ -150,7 +161,8 @@ extern "C" int tcvn_cnn_pack(const tcvn_cnn_desc* d, tcvn_precision prec, const 
   for (auto& B : P.blocks) {
     for (auto& L : B.layers) {
       TCVN_TRY(fold(arena, L.norm1, nullptr, B.c0, B.c0p, L.kpad, eps, pk, L.p_a_scale, L.p_a_shift, L.p_a_alpha, st));
-      if (bf) TCVN_TRY(repack(arena + L.conv1_w, P.mid, L.cin, 1, B.c0, B.c0p, L.kpad, P.mid, true, true, pk + L.p_w1, st));
+      if (bf) TCVN_TRY(repack(arena + L.conv1_w, P.mid, L.cin, 1, B.c0, B.c0p, L.kpad, P.mid, true, true, pk + L.p_w1, st,
+                              arena + L.norm2.w, arena + L.norm2.rv, eps));
       else TCVN_TRY(repack(arena + L.conv1_w, P.mid, L.cin, 1, B.c0, B.c0p, L.kphys, P.mid, false, false, pk + L.p_w1, st));
       TCVN_TRY(fold(arena, L.norm2, arena + L.conv1_b, NOGAP, NOGAP, P.mid, eps, pk, L.p_o_scale, L.p_o_shift,
                     L.p_o_alpha, st));
@@ -161,6 +173,13 @@ extern "C" int tcvn_cnn_pack(const tcvn_cnn_desc* d, tcvn_precision prec, const 
       TCVN_TRY(fold(arena, B.tnorm, nullptr, B.c0, B.c0p, B.tkpad, eps, pk, B.p_t_scale, B.p_t_shift, B.p_t_alpha, st));
       TCVN_TRY(repack(arena + B.tconv_w, B.tout, B.clog, 1, B.c0, B.c0p, B.ctot, B.toutp, false, false, pk + B.p_tw, st));
       TCVN_TRY(pad_copy(arena + B.tconv_b, B.tout, reinterpret_cast<float*>(pk + B.p_tb), B.toutp, st));
+      if (bf) {
+        const int n16 = B.tn_tiles * 128;
+        TCVN_TRY(repack(arena + B.tconv_w, B.tout, B.clog, 1, B.c0, B.c0p, B.tkpad, n16, true, true, pk + B.p_tw16, st));
+        TCVN_TRY(pad_copy(arena + B.tconv_b, B.tout, reinterpret_cast<float*>(pk + B.p_tb16), n16, st));
+        fill_kernel<<<ceil_div(n16, 128), 128, 0, st>>>(reinterpret_cast<float*>(pk + B.p_ta16), n16, 1.0f);
+        TCVN_LAUNCH_CHECK();
+      }
     }
   }
   const BlockPlan& last = P.blocks.back();

@@ -52,6 +52,9 @@ struct BlockPlan {
   size_t p_t_scale, p_t_shift, p_t_alpha;  // [ctot] fp32
   size_t p_tw;                             // [ctot][toutp] fp32 (CUDA-core GEMM in both precisions)
   size_t p_tb;                             // [toutp] fp32
+  int tn_tiles;                            // bf16 path: N tiles of 128 output channels
+  size_t p_tw16;                           // bf16 [tn_tiles*128][tkpad], K-major, zero rows beyond tout
+  size_t p_tb16, p_ta16;                   // [tn_tiles*128] fp32: bias (0-padded), PReLU slope 1 (identity)
   // workspace
   int chunk;      // images of this block processed per pass
   size_t ws_blk;  // byte offset
@@ -167,6 +170,10 @@ inline bool CnnPlan::build(const tcvn_cnn_desc& d, tcvn_precision prec, int n_im
       B.p_t_alpha = ptake(B.tkpad * 4);
       B.p_tw = ptake((size_t)B.ctot * B.toutp * 4);
       B.p_tb = ptake(B.toutp * 4);
+      B.tn_tiles = (B.toutp + 127) / 128;
+      B.p_tw16 = ptake(prec == TCVN_BF16 ? (size_t)B.tn_tiles * 128 * B.tkpad * 2 : 0);
+      B.p_tb16 = ptake(prec == TCVN_BF16 ? (size_t)B.tn_tiles * 128 * 4 : 0);
+      B.p_ta16 = ptake(prec == TCVN_BF16 ? (size_t)B.tn_tiles * 128 * 4 : 0);
       c = B.tout;
       H /= 2; W /= 2;  // AvgPool2d(2, 2) floors
       if (H < 1 || W < 1) return false;

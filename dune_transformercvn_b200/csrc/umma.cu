@@ -86,21 +86,32 @@ static int sm_count() {
 }
 
 // ------------------------------------------------------------------------------------------------
-// conv1: fused BN1+PReLU1 -> 1x1 conv -> bias+BN2+PReLU2
+// GEMM with fused operand activation:  out[m, n] = PReLU_n( sum_k act_k(A[m, k]) * W[n, k] + shift[n] )
+//   conv1 of a bottleneck: act = BN1+PReLU1 per input channel, W = BN2-scaled conv1 weights, shift = folded
+//                          bias/BN2, PReLU2 slopes;  N = 128
+//   transition conv:       act = identity (input already activated + pooled), shift = bias, slope 1; N tiles of 128
+// Warp roles (576 threads, 1 CTA/SM, persistent over tiles):
+//   warp 0      TMA producer: raw A tile [128 rows x 64 ch] + W chunk [128 n x 64 k] per stage
+//   warp 1      MMA issuer (one thread): 4 x tcgen05.mma (M128 N128 K16) per stage into TMEM accumulator acc
+//   warps 2-9   operand transform in place in the 128B-swizzled A tile (generic proxy -> fence -> async proxy)
+//   warps 10-17 two epilogue groups, one per TMEM accumulator: TMEM -> regs -> +shift, PReLU, ring rows -> 0,
+//               bf16 -> swizzled staging tile -> TMA store
 // ------------------------------------------------------------------------------------------------
 constexpr int kC1Stages = 4;
-constexpr int kC1Threads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 transform, warps 6-9 epilogue
+constexpr int kC1Threads = 576;
 constexpr int kTileM = 128;
-constexpr int kMid = 128;        // bottleneck width the kernels are specialised for
+constexpr int kMid = 128;              // N tile = bottleneck width the kernels are specialised for
 constexpr int kStageA = kTileM * 128;  // 16 KB: 128 rows x 64 bf16
 constexpr int kStageW = kMid * 128;    // 16 KB: 128 out-channels x 64 bf16
+constexpr int kXformThreads = 256;
 
-struct Conv1Params {
+struct GemmParams {
   long long m_total;
-  int kchunks, kphys;
-  const float *a_scale, *a_shift, *a_alpha, *o_scale, *o_shift, *o_alpha;
-  bf16* out;
-  int ldo, Hp, Wp, num_tiles;
+  int kchunks, kphys;      // K chunks of 64; channels >= kphys are forced to zero by the transform
+  int n_tiles_n;           // N tiles of 128 (1 for conv1)
+  const float *a_scale, *a_shift, *a_alpha;  // [kchunks*64] (TRANSFORM only)
+  const float *o_shift, *o_alpha;            // [n_tiles_n*128]
+  int Hp, Wp, num_tiles;   // num_tiles = m tiles * n_tiles_n
 };
 
 __device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
@@ -109,19 +120,20 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ float prelu_fast(float v, float a) { return fmaf(a, fminf(v, 0.f), fmaxf(v, 0.f)); }
 
-__global__ void __launch_bounds__(kC1Threads, 1) umma_conv1_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                                   const __grid_constant__ CUtensorMap tmW,
-                                                                   const __grid_constant__ CUtensorMap tmO,
-                                                                   const Conv1Params p) {
+template <bool TRANSFORM>
+__global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                  const __grid_constant__ CUtensorMap tmW,
+                                                                  const __grid_constant__ CUtensorMap tmO,
+                                                                  const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                   // [stages][16 KB]
   uint8_t* sW = smem + kC1Stages * kStageA;             // [stages][16 KB]
-  uint8_t* sOut = sW + kC1Stages * kStageW;             // 32 KB output staging: 2 halves x [128 rows x 128 B], swizzled
-  float* s_epi = reinterpret_cast<float*>(sOut + 2 * kStageA);  // o_scale | o_shift | o_alpha  [3][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + 3 * kMid);
-  uint64_t* full = bars;                    // TMA -> transform
+  uint8_t* sOut = sW + kC1Stages * kStageW;             // [2 groups][2 halves][128 rows x 128 B], swizzled
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + 4 * kStageA);
+  uint64_t* full = bars;                    // TMA -> transform (or MMA)
   uint64_t* ready = bars + kC1Stages;       // transform -> MMA
   uint64_t* empty = bars + 2 * kC1Stages;   // MMA -> TMA
   uint64_t* tfull = bars + 3 * kC1Stages;   // MMA -> epilogue   [2]
@@ -130,17 +142,16 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_conv1_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kC1Stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&ready[s], 128); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kC1Stages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&ready[s], kXformThreads);
+      ptx::mbar_init(&empty[s], 1);
+    }
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 128); }
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmW);
     ptx::prefetch_tmap(&tmO);
-  }
-  for (int i = threadIdx.x; i < kMid; i += blockDim.x) {
-    s_epi[i] = p.o_scale[i];
-    s_epi[kMid + i] = p.o_shift[i];
-    s_epi[2 * kMid + i] = p.o_alpha[i];
   }
   if (warp == 0) ptx::tmem_alloc(tmem_slot, 256);
   ptx::tc_fence_before();
@@ -152,11 +163,12 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_conv1_kernel(const __grid_
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&full[stage], kStageA + kStageW);
-          ptx::tma_load_2d(sA + stage * kStageA, &tmA, &full[stage], kc * 64, tile * kTileM);
-          ptx::tma_load_2d(sW + stage * kStageW, &tmW, &full[stage], kc * 64, 0);
+          ptx::tma_load_2d(sA + stage * kStageA, &tmA, &full[stage], kc * 64, mt * kTileM);
+          ptx::tma_load_2d(sW + stage * kStageW, &tmW, &full[stage], kc * 64, nt * kMid);
           if (++stage == kC1Stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -171,14 +183,14 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_conv1_kernel(const __grid_
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kMid;
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          ptx::mbar_wait(&ready[stage], phase);
+          ptx::mbar_wait(TRANSFORM ? &ready[stage] : &full[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(sA + stage * kStageA);
-          const uint32_t w_addr = ptx::smem_u32(sW + stage * kStageW);
+          const uint32_t a_lo = ptx::umma_desc_lo(ptx::smem_u32(sA + stage * kStageA));
+          const uint32_t w_lo = ptx::umma_desc_lo(ptx::smem_u32(sW + stage * kStageW));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            ptx::umma_bf16(d_tmem, ptx::umma_desc_sw128(a_addr + k * 32, 0), ptx::umma_desc_sw128(w_addr + k * 32, 0),
-                           idesc, (kc | k) != 0);
+            ptx::umma_bf16(d_tmem, ptx::umma_desc_join(ptx::kUmmaDescHiSw128, a_lo + 2 * k),
+                           ptx::umma_desc_join(ptx::kUmmaDescHiSw128, w_lo + 2 * k), idesc, (kc | k) != 0);
           ptx::umma_commit(&empty[stage]);
           if (++stage == kC1Stages) { stage = 0; phase ^= 1; }
         }
@@ -186,105 +198,117 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_conv1_kernel(const __grid_
         if ((acc ^= 1) == 0) acc_phase ^= 1;
       }
     }
-  } else if (warp < 6) {
-    // transform: thread owns 16-byte chunk `pc` of rows rb, rb+16, ... ; with the 128B swizzle the chunk at
-    // physical position pc of row r holds channels 8*(pc ^ (r & 7)); (rb + 16 i) & 7 == rb & 7, so one
-    // thread always sees the same 8 channels of a K chunk and keeps their BN/PReLU constants in registers.
-    const int t = threadIdx.x - 64;
-    const int pc = t & 7, rb = t >> 3;
-    const int cg = pc ^ (rb & 7);
-    int stage = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      for (int kc = 0; kc < p.kchunks; ++kc) {
-        const int ch = kc * 64 + cg * 8;
-        const bool live = ch < p.kphys;  // kphys is a multiple of 8: a group is all-live or all-dead
-        float sc[8], sh[8], al[8];
-        {
-          const float4* s4 = reinterpret_cast<const float4*>(p.a_scale + ch);
-          const float4* h4 = reinterpret_cast<const float4*>(p.a_shift + ch);
-          const float4* a4 = reinterpret_cast<const float4*>(p.a_alpha + ch);
-          float4 x0 = __ldg(s4), x1 = __ldg(s4 + 1), y0 = __ldg(h4), y1 = __ldg(h4 + 1), z0 = __ldg(a4), z1 = __ldg(a4 + 1);
-          sc[0] = x0.x; sc[1] = x0.y; sc[2] = x0.z; sc[3] = x0.w; sc[4] = x1.x; sc[5] = x1.y; sc[6] = x1.z; sc[7] = x1.w;
-          sh[0] = y0.x; sh[1] = y0.y; sh[2] = y0.z; sh[3] = y0.w; sh[4] = y1.x; sh[5] = y1.y; sh[6] = y1.z; sh[7] = y1.w;
-          al[0] = z0.x; al[1] = z0.y; al[2] = z0.z; al[3] = z0.w; al[4] = z1.x; al[5] = z1.y; al[6] = z1.z; al[7] = z1.w;
-        }
-        ptx::mbar_wait(&full[stage], phase);
-        uint8_t* base = sA + stage * kStageA + rb * 128 + pc * 16;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          uint4* q = reinterpret_cast<uint4*>(base + i * 16 * 128);
-          uint4 v = *q;
-          uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            float lo = prelu(fmaf(bf_lo(w[j]), sc[2 * j], sh[2 * j]), al[2 * j]);
-            float hi = prelu(fmaf(bf_hi(w[j]), sc[2 * j + 1], sh[2 * j + 1]), al[2 * j + 1]);
-            w[j] = live ? pack_bf16(lo, hi) : 0u;
+  } else if (warp < 10) {
+    if (TRANSFORM) {
+      // thread owns 16-byte chunk `pc` of rows rb, rb+32, ... ; with the 128B swizzle the chunk at physical
+      // position pc of row r holds channels 8*(pc ^ (r & 7)); (rb + 32 i) & 7 == rb & 7, so a thread always
+      // sees the same 8 channels of a K chunk and keeps their BN/PReLU constants in registers.
+      const int t = threadIdx.x - 64;
+      const int pc = t & 7, rb = t >> 3;
+      const int cg = pc ^ (rb & 7);
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          const int ch = kc * 64 + cg * 8;
+          const bool live = ch < p.kphys;  // kphys is a multiple of 8: a group is all-live or all-dead
+          float sc[8], sh[8], al[8];
+          {
+            const float4* s4 = reinterpret_cast<const float4*>(p.a_scale + ch);
+            const float4* h4 = reinterpret_cast<const float4*>(p.a_shift + ch);
+            const float4* a4 = reinterpret_cast<const float4*>(p.a_alpha + ch);
+            const float4 x0 = __ldg(s4), x1 = __ldg(s4 + 1), y0 = __ldg(h4), y1 = __ldg(h4 + 1), z0 = __ldg(a4), z1 = __ldg(a4 + 1);
+            sc[0] = x0.x; sc[1] = x0.y; sc[2] = x0.z; sc[3] = x0.w; sc[4] = x1.x; sc[5] = x1.y; sc[6] = x1.z; sc[7] = x1.w;
+            sh[0] = y0.x; sh[1] = y0.y; sh[2] = y0.z; sh[3] = y0.w; sh[4] = y1.x; sh[5] = y1.y; sh[6] = y1.z; sh[7] = y1.w;
+            al[0] = z0.x; al[1] = z0.y; al[2] = z0.z; al[3] = z0.w; al[4] = z1.x; al[5] = z1.y; al[6] = z1.z; al[7] = z1.w;
           }
-          *q = make_uint4(w[0], w[1], w[2], w[3]);
+          ptx::mbar_wait(&full[stage], phase);
+          uint8_t* base = sA + stage * kStageA + rb * 128 + pc * 16;
+          uint4 v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const uint4*>(base + i * 32 * 128);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float lo = prelu_fast(fmaf(bf_lo(w[q]), sc[2 * q], sh[2 * q]), al[2 * q]);
+              const float hi = prelu_fast(fmaf(bf_hi(w[q]), sc[2 * q + 1], sh[2 * q + 1]), al[2 * q + 1]);
+              w[q] = live ? pack_bf16(lo, hi) : 0u;
+            }
+            *reinterpret_cast<uint4*>(base + i * 32 * 128) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(&ready[stage]);
+          if (++stage == kC1Stages) { stage = 0; phase ^= 1; }
         }
-        ptx::fence_proxy_async_smem();
-        ptx::mbar_arrive(&ready[stage]);
-        if (++stage == kC1Stages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
-    // epilogue: TMEM -> registers -> bias+BN2+PReLU2 -> bf16 -> swizzled SMEM tile -> TMA store (coalesced,
-    // asynchronous; rows past the end of the buffer are clipped by the tensor map)
+    const int grp = (warp - 10) >> 2;   // epilogue group == TMEM accumulator it drains
     const int g = warp & 3;             // TMEM lane group this warp may read
     const int row = g * 32 + lane;
     const int R = p.Hp * p.Wp;
-    const bool issuer = threadIdx.x == 6 * 32;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const long long m = (long long)tile * kTileM + row;
+    const bool issuer = threadIdx.x == (10 + 4 * grp) * 32;
+    uint8_t* stg = sOut + grp * 2 * kStageA;
+    uint32_t acc_phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != grp) continue;
+      const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
+      const long long m = (long long)mt * kTileM + row;
       bool ring = false;
       {
         const int rr = (int)(m % R);
         const int y = rr / p.Wp, x = rr - y * p.Wp;
         ring = y == 0 || y == p.Hp - 1 || x == 0 || x == p.Wp - 1;
       }
-      ptx::mbar_wait(&tfull[acc], acc_phase);
+      const float* shift = p.o_shift + nt * kMid;
+      const float* alpha = p.o_alpha + nt * kMid;
+      ptx::mbar_wait(&tfull[grp], acc_phase);
       ptx::tc_fence_after();
-      if (issuer) ptx::tma_store_wait_read();  // the previous tile's store has drained the staging tile
-      ptx::named_bar_sync(1, 128);
+      if (issuer) ptx::tma_store_wait_read();  // this group's previous store has drained the staging tile
+      ptx::named_bar_sync(1 + grp, 128);
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(g * 32) << 16) + acc * kMid + c * 32, r);
+      for (int c = 0; c < 4; c += 2) {
+        uint32_t r0[32], r1[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(g * 32) << 16) + grp * kMid + c * 32, r0);
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(g * 32) << 16) + grp * kMid + c * 32 + 32, r1);
         ptx::tmem_ld_wait();
-        uint8_t* orow = sOut + (c >> 1) * kStageA + row * 128;
+        uint8_t* orow = stg + (c >> 1) * kStageA + row * 128;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t o[4];
+        for (int hh = 0; hh < 2; ++hh) {
+          const uint32_t* r = hh ? r1 : r0;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int n = c * 32 + q * 8 + h * 4;
-            const float4 sc = *reinterpret_cast<const float4*>(s_epi + n);
-            const float4 sh = *reinterpret_cast<const float4*>(s_epi + kMid + n);
-            const float4 al = *reinterpret_cast<const float4*>(s_epi + 2 * kMid + n);
-            const int j = q * 8 + h * 4;
-            const float v0 = prelu(fmaf(__uint_as_float(r[j + 0]), sc.x, sh.x), al.x);
-            const float v1 = prelu(fmaf(__uint_as_float(r[j + 1]), sc.y, sh.y), al.y);
-            const float v2 = prelu(fmaf(__uint_as_float(r[j + 2]), sc.z, sh.z), al.z);
-            const float v3 = prelu(fmaf(__uint_as_float(r[j + 3]), sc.w, sh.w), al.w);
-            o[2 * h] = ring ? 0u : pack_bf16(v0, v1);
-            o[2 * h + 1] = ring ? 0u : pack_bf16(v2, v3);
+          for (int q = 0; q < 4; ++q) {
+            uint32_t o[4];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              const int n = (c + hh) * 32 + q * 8 + h * 4;
+              const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + n));
+              const float4 al = __ldg(reinterpret_cast<const float4*>(alpha + n));
+              const int j = q * 8 + h * 4;
+              const float v0 = prelu_fast(__uint_as_float(r[j + 0]) + sh.x, al.x);
+              const float v1 = prelu_fast(__uint_as_float(r[j + 1]) + sh.y, al.y);
+              const float v2 = prelu_fast(__uint_as_float(r[j + 2]) + sh.z, al.z);
+              const float v3 = prelu_fast(__uint_as_float(r[j + 3]) + sh.w, al.w);
+              o[2 * h] = ring ? 0u : pack_bf16(v0, v1);
+              o[2 * h + 1] = ring ? 0u : pack_bf16(v2, v3);
+            }
+            const int chunk = hh * 4 + q;  // 16-byte chunk within the 128-byte half-row
+            *reinterpret_cast<uint4*>(orow + ((chunk ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
           }
-          const int chunk = (c & 1) * 4 + q;  // 16-byte chunk within the 128-byte half-row
-          *reinterpret_cast<uint4*>(orow + ((chunk ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&tempty[acc]);
+      ptx::mbar_arrive(&tempty[grp]);
       ptx::fence_proxy_async_smem();
-      ptx::named_bar_sync(1, 128);
+      ptx::named_bar_sync(1 + grp, 128);
       if (issuer) {
-        ptx::tma_store_2d(&tmO, sOut, 0, tile * kTileM);
-        ptx::tma_store_2d(&tmO, sOut + kStageA, 64, tile * kTileM);
+        ptx::tma_store_2d(&tmO, stg, nt * kMid, mt * kTileM);
+        ptx::tma_store_2d(&tmO, stg + kStageA, nt * kMid + 64, mt * kTileM);
         ptx::tma_store_commit();
       }
-      if ((acc ^= 1) == 0) acc_phase ^= 1;
+      acc_phase ^= 1;
     }
     if (issuer) ptx::tma_store_wait_all();
   }
@@ -442,36 +466,54 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
 // ------------------------------------------------------------------------------------------------
 static inline const float* pf(const char* packed, size_t off) { return reinterpret_cast<const float*>(packed + off); }
 
+static int launch_gemm(bool transform, const void* A, long long rows, int a_cols, int a_pitch, const void* W, int w_rows,
+                       int kpad, int kphys, const float* a_scale, const float* a_shift, const float* a_alpha,
+                       const float* o_shift, const float* o_alpha, void* out, int out_cols, int out_pitch, int n_tiles_n,
+                       int Hp, int Wp, cudaStream_t st) {
+  if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one chunk");
+  const size_t smem = 1024 + kC1Stages * (kStageA + kStageW) + 4 * kStageA + (3 * kC1Stages + 4) * 8 + 16;
+  static bool attr_done = false;
+  if (!attr_done) {
+    TCVN_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TCVN_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  CUtensorMap tmA, tmW, tmO;
+  TCVN_TRY(make_map(A, rows, a_cols, a_pitch, 64, kTileM, &tmA));
+  TCVN_TRY(make_map(W, w_rows, kpad, kpad, 64, kMid, &tmW));
+  TCVN_TRY(make_map(out, rows, out_cols, out_pitch, 64, kTileM, &tmO));
+  GemmParams g;
+  g.m_total = rows; g.kchunks = kpad / kKChunk; g.kphys = kphys; g.n_tiles_n = n_tiles_n;
+  g.a_scale = a_scale; g.a_shift = a_shift; g.a_alpha = a_alpha; g.o_shift = o_shift; g.o_alpha = o_alpha;
+  g.Hp = Hp; g.Wp = Wp;
+  g.num_tiles = (int)ceil_div_ll(rows, kTileM) * n_tiles_n;
+  const int grid = g.num_tiles < sm_count() ? g.num_tiles : sm_count();
+  if (transform) umma_gemm_kernel<true><<<grid, kC1Threads, smem, st>>>(tmA, tmW, tmO, g);
+  else umma_gemm_kernel<false><<<grid, kC1Threads, smem, st>>>(tmA, tmW, tmO, g);
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
 int umma_dense_layer(const CnnPlan& P, const BlockPlan& B, const LayerPlan& L, const char* pk, void* blk, void* mid,
                      long long rows, cudaStream_t st) {
   if (P.mid != kMid || P.d.growth != kGrowth)
     return fail(TCVN_ERR_UNSUPPORTED, "tcgen05 path is specialised for bottleneck width 128 / growth 32 (got %d / %d)",
                 P.mid, P.d.growth);
   if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one chunk");
+  // ---- conv1 (BN2 scale is folded into the bf16 weights by pack.cu; the epilogue adds the folded shift)
+  TCVN_TRY(launch_gemm(true, blk, rows, B.ctot, B.ctot, pk + L.p_w1, kMid, L.kpad, L.kphys, pf(pk, L.p_a_scale),
+                       pf(pk, L.p_a_shift), pf(pk, L.p_a_alpha), pf(pk, L.p_o_shift), pf(pk, L.p_o_alpha), mid, kMid, kMid,
+                       1, B.Hp, B.Wp, st));
+  // ---- conv2
   const int tiles = (int)ceil_div_ll(rows, kTileM);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  static bool attr_done = false;
-  const size_t smem1 = 1024 + kC1Stages * (kStageA + kStageW) + 2 * kStageA + 3 * kMid * 4 + (3 * kC1Stages + 4) * 8 + 16;
   const int halo_rows_max = 288;
+  static bool attr_done = false;
   if (!attr_done) {
-    TCVN_CUDA(cudaFuncSetAttribute(umma_conv1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
     TCVN_CUDA(cudaFuncSetAttribute(umma_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    1024 + kW2Bytes + kC2Stages * 2 * halo_rows_max * 128 + 256));
     attr_done = true;
   }
-  // ---- conv1
-  CUtensorMap tmA, tmW, tmO;
-  TCVN_TRY(make_map(blk, rows, B.ctot, B.ctot, 64, kTileM, &tmA));
-  TCVN_TRY(make_map(pk + L.p_w1, kMid, L.kpad, L.kpad, 64, kMid, &tmW));
-  TCVN_TRY(make_map(mid, rows, kMid, kMid, 64, kTileM, &tmO));
-  Conv1Params c1;
-  c1.m_total = rows; c1.kchunks = L.kpad / kKChunk; c1.kphys = L.kphys;
-  c1.a_scale = pf(pk, L.p_a_scale); c1.a_shift = pf(pk, L.p_a_shift); c1.a_alpha = pf(pk, L.p_a_alpha);
-  c1.o_scale = pf(pk, L.p_o_scale); c1.o_shift = pf(pk, L.p_o_shift); c1.o_alpha = pf(pk, L.p_o_alpha);
-  c1.out = static_cast<bf16*>(mid); c1.ldo = kMid; c1.Hp = B.Hp; c1.Wp = B.Wp; c1.num_tiles = tiles;
-  umma_conv1_kernel<<<grid, kC1Threads, smem1, st>>>(tmA, tmW, tmO, c1);
-  TCVN_LAUNCH_CHECK();
-  // ---- conv2
   Conv2Params c2;
   c2.m_total = rows; c2.Hp = B.Hp; c2.Wp = B.Wp;
   c2.nbox = ceil_div(kTileM + 2 * (B.Wp + 1), kBoxRows);
@@ -493,9 +535,14 @@ int umma_dense_layer(const CnnPlan& P, const BlockPlan& B, const LayerPlan& L, c
   return TCVN_OK;
 }
 
-int umma_transition(const CnnPlan&, const BlockPlan&, const BlockPlan&, const char*, const void*, void*, long long,
-                    cudaStream_t) {
-  return fail(TCVN_ERR_UNSUPPORTED, "transition runs on the CUDA-core GEMM in this build");
+// transition 1x1 convolution on the pooled, activated map: N tiles of 128 output channels.  Columns beyond
+// the real output width receive zeros (zero weight rows); in the next block's buffer those columns belong to
+// dense layers that overwrite them before anything reads them, and the tensor map clips at the buffer width.
+int umma_transition(const CnnPlan& P, const BlockPlan& B, const BlockPlan& Nx, const char* pk, const void* pool,
+                    void* next_blk, long long rows, cudaStream_t st) {
+  return launch_gemm(false, pool, rows, B.ctot, B.ctot, pk + B.p_tw16, B.tn_tiles * kMid, B.tkpad, B.ctot, nullptr,
+                     nullptr, nullptr, pf(pk, B.p_tb16), pf(pk, B.p_ta16), next_blk, Nx.ctot, Nx.ctot, B.tn_tiles, Nx.Hp,
+                     Nx.Wp, st);
 }
 
 }  // namespace tcvn
