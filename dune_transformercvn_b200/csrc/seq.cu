@@ -150,10 +150,13 @@ __global__ void __launch_bounds__(kSeqThreads) seq_forward_kernel(const SeqDev P
   const int b = blockIdx.x;
   const int S = 1 + L;
   const int D = P.D;
-  float* x = sm;                          // [kSeqMax][D]     current hidden state
-  float* big = x + kSeqMax * D;           // [kSeqMax][3D]    token inputs / qkv / ffn hidden
-  float* ctx = big + kSeqMax * 3 * D;     // [kSeqMax][D]     attention context / sub-layer output
-  float* xin = ctx + kSeqMax * D;         // [kSeqMax][in_dim] token-assembly inputs
+  // buffers are sized by the batch's sequence length (rows rounded up to 8, plus 8 rows of slack the
+  // 8-row register tiles of linear_rows may read), so several events fit one SM
+  const int SR = ((S + 7) & ~7) + 8;
+  float* x = sm;                          // [SR][D]     current hidden state
+  float* big = x + SR * D;                // [SR][3D]    token inputs / qkv / ffn hidden
+  float* ctx = big + SR * 3 * D;          // [SR][D]     attention context / sub-layer output
+  float* xin = ctx + SR * D;              // [SR][in_dim] token-assembly inputs
   __shared__ int valid[kSeqMax];
   __shared__ int prow[kSeqMax];
   if (threadIdx.x < kSeqMax) {
@@ -438,7 +441,8 @@ extern "C" int tcvn_seq_forward(const tcvn_seq_desc* d, const void* packed, int 
   cudaStream_t st = stream;
   prong_offsets_kernel<<<1, 256, 0, st>>>(prong_mask, n_events, max_prongs, offsets);
   TCVN_LAUNCH_CHECK();
-  const size_t smem = ((size_t)kSeqMax * d->hidden * 5 + (size_t)kSeqMax * P.in_dim) * sizeof(float);
+  const int SR = ((1 + max_prongs + 7) & ~7) + 8;
+  const size_t smem = ((size_t)SR * d->hidden * 5 + (size_t)SR * P.in_dim) * sizeof(float);
   TCVN_CUDA(cudaFuncSetAttribute(seq_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   seq_forward_kernel<<<n_events, kSeqThreads, smem, st>>>(make_dev(P, static_cast<const char*>(packed)), stages,
                                                           event_embedding, prong_embedding, event_mask, prong_mask,

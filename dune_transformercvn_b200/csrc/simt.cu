@@ -138,97 +138,183 @@ int launch_simt_gemm(const GemmArgs& a, cudaStream_t stream) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Stem, fused: 7x7 stride-2 convolution on NCHW fp32 pixels + bias + BN0 + PReLU0 + AvgPool2d(3, 2),
-// written straight into channels [0, 64) of block 0's ringed buffer (dense_net.py:111-122).  The
-// 64 x 200 x 140 pre-pool map (3.6 MB/image in bf16 - the largest tensor of the network) never
-// reaches memory.  Persistent CTAs keep the 147 x 64 filter bank in shared memory and loop over
-// 8 x 8 tiles of pooled pixels (17 x 17 conv outputs, 39 x 39 x 3 input window).  One thread per
-// conv output, 64 channels in registers; the pixel maps are ~99 % zeros, so a warp skips a tap when
-// none of its 32 input values is non-zero (adding 0*w is exact: skipping is bit-identical).
+// Stem, fused and hit-driven: 7x7 stride-2 convolution on NCHW fp32 pixels + bias + BN0 + PReLU0 +
+// AvgPool2d(3, 2), written straight into channels [0, 64) of block 0's ringed buffer
+// (dense_net.py:111-122).  The 64 x 200 x 140 pre-pool map never reaches memory.
+//
+// The pixel maps are ~99 % zeros, so the convolution is evaluated from the hits: a persistent CTA keeps
+// the 147 x 64 filter bank in shared memory and loops over 8 x 8 tiles of pooled pixels
+// (17 x 17 conv outputs <- 39 x 39 x 3 input window).  Per tile it (1) compacts the non-zero pixels
+// of the window into a list in a fixed order (ballot + prefix sums: deterministic), (2) lets every hit
+// add v * w[tap] to the <= 4 x 4 conv outputs it reaches - thread (cy mod 4, cx mod 2, channel) owns
+// its accumulators, so there are no atomics and no barriers between hits, and the summation order is
+// fixed, (3) applies bias/BN/PReLU in place and (4) average-pools 3x3/2 into the output rows.  For a
+// dense input this degrades gracefully to the full convolution (the list holds the whole window).
 // ------------------------------------------------------------------------------------------------
 constexpr int kStemTP = 8;                   // pooled tile edge
 constexpr int kStemTC = 2 * kStemTP + 1;     // 17 conv outputs per edge
 constexpr int kStemIn = 2 * kStemTC + 5;     // 39 input pixels per edge
-constexpr int kStemThreads = 320;            // 289 conv outputs -> 10 warps
+constexpr int kStemThreads = 512;            // (cy mod 4) x (cx mod 2) x 64 channels
+constexpr int kStemRows = kStemIn;           // window rows (pixels, all channels together)
 
 template <typename TO, int C0>
 __global__ void __launch_bounds__(kStemThreads) stem_fused_kernel(const float* __restrict__ pixels, int n_images, int cin,
-                                                                  int H, int W, int Hs, int Ws,
-                                                                  const float* __restrict__ w0,
+                                                                  int H, int W, const float* __restrict__ w0,
                                                                   const float* __restrict__ s_scale,
                                                                   const float* __restrict__ s_shift,
                                                                   const float* __restrict__ s_alpha,
                                                                   TO* __restrict__ blk, int ldo, int Hb, int Wb) {
   extern __shared__ __align__(16) float smem[];
-  float* wsm = smem;                                        // [cin*49][C0]
-  float* ism = wsm + cin * 49 * C0;                         // [cin][39][40]
-  TO* csm = reinterpret_cast<TO*>(ism + cin * kStemIn * (kStemIn + 1));  // [289][C0] activated conv outputs
+  float* wsm = smem;                                  // [cin*49][C0]
+  float* acc = wsm + cin * 49 * C0;                   // [289][C0]
+  float4* hits = reinterpret_cast<float4*>(acc + kStemTC * kStemTC * C0);  // [39*39] (packed yx, v0, v1, v2)
+  __shared__ int row_count[kStemRows];
+  __shared__ int row_start[kStemRows + 1];
+  __shared__ int touched[kStemTC * kStemTC];  // conv outputs reached by at least one hit of this tile
   for (int i = threadIdx.x; i < cin * 49 * C0; i += blockDim.x) wsm[i] = __ldg(w0 + i);
   const int tiles_x = (Wb + kStemTP - 1) / kStemTP, tiles_y = (Hb + kStemTP - 1) / kStemTP;
   const int per_image = tiles_x * tiles_y;
   const long long total = (long long)n_images * per_image;
-  const int t = threadIdx.x;
-  const bool active = t < kStemTC * kStemTC;
-  const int cy = active ? t / kStemTC : 0, cx = active ? t % kStemTC : 0;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int ch = t & (C0 - 1);
+  const int own_px = (t >> 6) & 1, own_py = t >> 7;   // owns conv outputs with cx % 2 == own_px, cy % 4 == own_py
+  const float sc = __ldg(s_scale + ch), sh = __ldg(s_shift + ch), al = __ldg(s_alpha + ch);
+  const size_t plane = (size_t)H * W;
+  // window values of the tile being compacted: [row slot][column slot][channel]; warp w scans window rows
+  // w, w+16, w+32, lane covers columns lane and lane+32.  Loaded one tile AHEAD (pure loads, no votes in
+  // between) so the global-memory latency hides behind the previous tile's scatter / pooling.
+  float v[3][2][3];
+  auto load_window = [&](long long tile_id) {
+    const int n = (int)(tile_id / per_image);
+    const int rem = (int)(tile_id - (long long)n * per_image);
+    const int iy0 = 4 * (rem / tiles_x) * kStemTP - 3, ix0 = 4 * (rem % tiles_x) * kStemTP - 3;
+    const float* img = pixels + (size_t)n * cin * plane;
+#pragma unroll
+    for (int rs = 0; rs < 3; ++rs) {
+      const int yy = warp + 16 * rs, y = iy0 + yy;
+#pragma unroll
+      for (int cs = 0; cs < 2; ++cs) {
+        const int xx = lane + 32 * cs, x = ix0 + xx;
+        const bool ok = yy < kStemIn && xx < kStemIn && y >= 0 && y < H && x >= 0 && x < W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[rs][cs][c] = (ok && c < cin) ? __ldg(img + c * plane + (size_t)y * W + x) : 0.f;
+      }
+    }
+  };
+  if ((long long)blockIdx.x < total) load_window(blockIdx.x);
   for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
     const int n = (int)(tile / per_image);
     const int rem = (int)(tile - (long long)n * per_image);
     const int py0 = (rem / tiles_x) * kStemTP, px0 = (rem % tiles_x) * kStemTP;
-    const int iy0 = 4 * py0 - 3, ix0 = 4 * px0 - 3;
-    const float* img = pixels + (size_t)n * cin * H * W;
-    __syncthreads();  // previous tile's pooling reads of csm / conv reads of ism are done
-    for (int i = t; i < cin * kStemIn * kStemIn; i += blockDim.x) {
-      const int c = i / (kStemIn * kStemIn);
-      const int r = i - c * kStemIn * kStemIn;
-      const int yy = r / kStemIn, xx = r - yy * kStemIn;
-      const int y = iy0 + yy, x = ix0 + xx;
-      float v = 0.f;
-      if (y >= 0 && y < H && x >= 0 && x < W) v = __ldg(img + ((size_t)c * H + y) * W + x);
-      ism[(c * kStemIn + yy) * (kStemIn + 1) + xx] = v;
+    __syncthreads();  // previous tile fully consumed
+    // ---- (1) compact the non-zero pixels of the window, rows in order, columns in order
+    unsigned m0[3], m1[3];
+#pragma unroll
+    for (int rs = 0; rs < 3; ++rs) {
+      const int yy = warp + 16 * rs;
+      m0[rs] = __ballot_sync(0xffffffffu, v[rs][0][0] != 0.f || v[rs][0][1] != 0.f || v[rs][0][2] != 0.f);
+      m1[rs] = __ballot_sync(0xffffffffu, v[rs][1][0] != 0.f || v[rs][1][1] != 0.f || v[rs][1][2] != 0.f);
+      if (lane == 0 && yy < kStemIn) row_count[yy] = __popc(m0[rs]) + __popc(m1[rs]);
+    }
+    // zero the accumulators while the counts settle
+    {
+      float4* a4 = reinterpret_cast<float4*>(acc);
+      for (int i = t; i < kStemTC * kStemTC * C0 / 4; i += blockDim.x) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < kStemTC * kStemTC) touched[t] = 0;
     }
     __syncthreads();
-    float acc[C0];
+    if (warp == 0) {
+      int run = 0;
+      for (int base = 0; base < kStemRows; base += 32) {
+        const int r = base + lane;
+        const int c = r < kStemRows ? row_count[r] : 0;
+        int incl = c;
 #pragma unroll
-    for (int j = 0; j < C0; ++j) acc[j] = 0.f;
-    for (int c = 0; c < cin; ++c)
-      for (int ky = 0; ky < 7; ++ky) {
-        const float* irow = ism + (c * kStemIn + 2 * cy + ky) * (kStemIn + 1) + 2 * cx;
+        for (int o = 1; o < 32; o <<= 1) {
+          const int up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += up;
+        }
+        if (r < kStemRows) row_start[r] = run + incl - c;
+        run += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (lane == 0) row_start[kStemRows] = run;
+    }
+    __syncthreads();
 #pragma unroll
-        for (int kx = 0; kx < 7; ++kx) {
-          const float v = active ? irow[kx] : 0.f;
-          if (__any_sync(0xffffffffu, v != 0.f)) {
-            const float4* w4 = reinterpret_cast<const float4*>(wsm + ((c * 7 + ky) * 7 + kx) * C0);
+    for (int rs = 0; rs < 3; ++rs) {
+      const int yy = warp + 16 * rs;
+      if (yy < kStemIn) {
+        const int base = row_start[yy];
+        const unsigned below = (1u << lane) - 1u;
+        if (m0[rs] >> lane & 1u)
+          hits[base + __popc(m0[rs] & below)] =
+              make_float4(__int_as_float(yy * 64 + lane), v[rs][0][0], v[rs][0][1], v[rs][0][2]);
+        if (m1[rs] >> lane & 1u)
+          hits[base + __popc(m0[rs]) + __popc(m1[rs] & below)] =
+              make_float4(__int_as_float(yy * 64 + lane + 32), v[rs][1][0], v[rs][1][1], v[rs][1][2]);
+      }
+    }
+    if (tile + gridDim.x < total) load_window(tile + gridDim.x);  // in flight during the rest of this tile
+    __syncthreads();
+    // ---- (2) scatter every hit into the conv outputs it reaches (input yy = 2*cy + ky)
+    const int nhits = row_start[kStemRows];
+    for (int h = 0; h < nhits; ++h) {
+      const float4 hit = hits[h];
+      const int code = __float_as_int(hit.x);
+      const int yy = code >> 6, xx = code & 63;
+      // the unique cy in [cy_lo, cy_lo + 4) with cy % 4 == own_py, cy_lo = max(0, ceil((yy - 6) / 2))
+      const int cy_lo = yy > 6 ? (yy - 5) >> 1 : 0;
+      const int cy = cy_lo + ((own_py - cy_lo) & 3);
+      const int ky = yy - 2 * cy;
+      if (cy > kStemTC - 1 || ky < 0) continue;   // ky <= 6 by construction
+      const int cx_lo = xx > 6 ? (xx - 5) >> 1 : 0;
+      const int cx_a = cx_lo + ((own_px - cx_lo) & 1);
 #pragma unroll
-            for (int j = 0; j < C0 / 4; ++j) {
-              const float4 w = w4[j];
-              acc[4 * j + 0] = fmaf(v, w.x, acc[4 * j + 0]);
-              acc[4 * j + 1] = fmaf(v, w.y, acc[4 * j + 1]);
-              acc[4 * j + 2] = fmaf(v, w.z, acc[4 * j + 2]);
-              acc[4 * j + 3] = fmaf(v, w.w, acc[4 * j + 3]);
-            }
-          }
+      for (int k = 0; k < 2; ++k) {
+        const int cx = cx_a + 2 * k;
+        const int kx = xx - 2 * cx;
+        if (cx <= kStemTC - 1 && kx >= 0) {
+          const float* wp = wsm + (ky * 7 + kx) * C0 + ch;
+          float a = acc[(cy * kStemTC + cx) * C0 + ch];
+          a = fmaf(hit.y, wp[0], a);
+          if (cin > 1) a = fmaf(hit.z, wp[49 * C0], a);
+          if (cin > 2) a = fmaf(hit.w, wp[2 * 49 * C0], a);
+          acc[(cy * kStemTC + cx) * C0 + ch] = a;
+          if (ch == 0) touched[cy * kStemTC + cx] = 1;
         }
       }
-    if (active) {
-      TO* o = csm + (size_t)t * C0;
-#pragma unroll
-      for (int j = 0; j < C0; ++j)
-        o[j] = from_f32<TO>(prelu(fmaf(acc[j], __ldg(s_scale + j), __ldg(s_shift + j)), __ldg(s_alpha + j)));
     }
     __syncthreads();
+    // ---- (3)+(4) bias + BN0 + PReLU0, AvgPool2d(3, 2) -> ringed block buffer.  A conv output no hit reached is
+    // the per-channel constant PReLU(shift); a pooling window of nine such outputs is evaluated once per thread
+    // (same additions and division as the general case, so the shortcut is bit-identical).
+    const float c_act = prelu(fmaf(0.f, sc, sh), al);
+    float c_pool = 0.f;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) c_pool += c_act;
+    c_pool /= 9.0f;
     for (int i = t; i < kStemTP * kStemTP * C0; i += blockDim.x) {
-      const int ch = i % C0;
       const int p = i / C0;
       const int pyl = p / kStemTP, pxl = p % kStemTP;
       const int py = py0 + pyl, px = px0 + pxl;
       if (py >= Hb || px >= Wb) continue;
-      float s = 0.f;
+      const int base = (2 * pyl) * kStemTC + 2 * pxl;
+      int any = 0;
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) s += to_f32<TO>(csm[((2 * pyl + dy) * kStemTC + 2 * pxl + dx) * C0 + ch]);
+        for (int dx = 0; dx < 3; ++dx) any |= touched[base + dy * kStemTC + dx];
+      float r = c_pool;
+      if (any) {
+        float s2 = 0.f;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) s2 += prelu(fmaf(acc[(base + dy * kStemTC + dx) * C0 + ch], sc, sh), al);
+        r = s2 / 9.0f;
+      }
       const size_t row = (size_t)n * (Hb + 2) * (Wb + 2) + (size_t)(py + 1) * (Wb + 2) + (px + 1);
-      blk[row * ldo + ch] = from_f32<TO>(s / 9.0f);
+      blk[row * ldo + ch] = from_f32<TO>(r);
     }
   }
 }
@@ -240,9 +326,9 @@ int launch_stem(const float* pixels, int n, int cin, int H, int W, const float* 
   if (n == 0) return TCVN_OK;
   const int Hs = (H + 6 - 7) / 2 + 1, Ws = (W + 6 - 7) / 2 + 1;
   if ((Hs - 3) / 2 + 1 != Hb || (Ws - 3) / 2 + 1 != Wb) return fail(TCVN_ERR_ARG, "stem: geometry mismatch");
-  const size_t smem = ((size_t)cin * 49 * c0 + (size_t)cin * kStemIn * (kStemIn + 1)) * sizeof(float) +
-                      (size_t)kStemTC * kStemTC * c0 * (f32 ? 4 : 2);
-  if (smem > 220 * 1024) return fail(TCVN_ERR_UNSUPPORTED, "stem: %d input channels do not fit shared memory", cin);
+  if (cin > 3) return fail(TCVN_ERR_UNSUPPORTED, "stem: %d input channels (kernel handles up to 3)", cin);
+  const size_t smem = ((size_t)cin * 49 * c0 + (size_t)kStemTC * kStemTC * c0) * sizeof(float) +
+                      (size_t)kStemIn * kStemIn * sizeof(float4);
   int sms = 148;
   {
     int dev = 0;
@@ -250,17 +336,16 @@ int launch_stem(const float* pixels, int n, int cin, int H, int W, const float* 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const long long tiles = (long long)n * ((Wb + kStemTP - 1) / kStemTP) * ((Hb + kStemTP - 1) / kStemTP);
-  const int per_sm = f32 ? 1 : 2;
-  const int grid = (int)(tiles < (long long)sms * per_sm ? tiles : (long long)sms * per_sm);
+  const int grid = (int)(tiles < (long long)sms ? tiles : (long long)sms);
   if (f32) {
     TCVN_CUDA(cudaFuncSetAttribute(stem_fused_kernel<float, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    stem_fused_kernel<float, 64><<<grid, kStemThreads, smem, stream>>>(pixels, n, cin, H, W, Hs, Ws, w0, s_scale, s_shift,
-                                                                        s_alpha, static_cast<float*>(blk), ldo, Hb, Wb);
+    stem_fused_kernel<float, 64><<<grid, kStemThreads, smem, stream>>>(pixels, n, cin, H, W, w0, s_scale, s_shift, s_alpha,
+                                                                        static_cast<float*>(blk), ldo, Hb, Wb);
   } else {
     TCVN_CUDA(cudaFuncSetAttribute(stem_fused_kernel<__nv_bfloat16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smem));
     stem_fused_kernel<__nv_bfloat16, 64><<<grid, kStemThreads, smem, stream>>>(
-        pixels, n, cin, H, W, Hs, Ws, w0, s_scale, s_shift, s_alpha, static_cast<__nv_bfloat16*>(blk), ldo, Hb, Wb);
+        pixels, n, cin, H, W, w0, s_scale, s_shift, s_alpha, static_cast<__nv_bfloat16*>(blk), ldo, Hb, Wb);
   }
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
@@ -268,34 +353,87 @@ int launch_stem(const float* pixels, int n, int cin, int H, int W, const float* 
 
 // Transition front half.  AvgPool2d(2,2) is linear and the 1x1 convolution is per-pixel, so
 // pool(conv(a)) == conv(pool(a)) (bias included): pooling the activated map first makes the GEMM 4x smaller.
+// one thread = one output pixel x 8 (bf16) / 4 (fp32) channels: 16-byte loads and stores
+template <typename T> struct Vec16;
+template <> struct Vec16<float> { static constexpr int N = 4; };
+template <> struct Vec16<__nv_bfloat16> { static constexpr int N = 8; };
+
+template <typename T>
+__device__ __forceinline__ void load_vec(const T* p, float (&f)[Vec16<T>::N]);
+template <>
+__device__ __forceinline__ void load_vec<float>(const float* p, float (&f)[4]) {
+  const float4 v = *reinterpret_cast<const float4*>(p);
+  f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+}
+template <>
+__device__ __forceinline__ void load_vec<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store_vec(T* p, const float (&f)[Vec16<T>::N]);
+template <>
+__device__ __forceinline__ void store_vec<float>(float* p, const float (&f)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+}
+template <>
+__device__ __forceinline__ void store_vec<__nv_bfloat16>(__nv_bfloat16* p, const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 template <typename T>
 __global__ void act_pool2_kernel(const T* __restrict__ blk, int H, int W, int ld, int c,
                                  const float* __restrict__ scale, const float* __restrict__ shift,
                                  const float* __restrict__ alpha, T* __restrict__ out, int H2, int W2,
                                  long long total) {
+  constexpr int V = Vec16<T>::N;
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int ch = (int)(idx % c);
-  long long r = idx / c;
+  const int cv = c / V;
+  const int ch = (int)(idx % cv) * V;
+  long long r = idx / cv;
   const int x = (int)(r % W2); r /= W2;
   const int y = (int)(r % H2);
   const int n = (int)(r / H2);
   const int Wp = W + 2;
   const size_t row0 = (size_t)n * (H + 2) * Wp + (size_t)(2 * y + 1) * Wp + (2 * x + 1);
-  const float sc = __ldg(scale + ch), sh = __ldg(shift + ch), al = __ldg(alpha + ch);
-  float s = 0.f;
+  float sc[V], sh[V], al[V], s[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    sc[i] = __ldg(scale + ch + i); sh[i] = __ldg(shift + ch + i); al[i] = __ldg(alpha + ch + i);
+    s[i] = 0.f;
+  }
 #pragma unroll
   for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-    for (int dx = 0; dx < 2; ++dx)
-      s += prelu(fmaf(to_f32<T>(blk[(row0 + (size_t)dy * Wp + dx) * ld + ch]), sc, sh), al);
+    for (int dx = 0; dx < 2; ++dx) {
+      float f[V];
+      load_vec<T>(blk + (row0 + (size_t)dy * Wp + dx) * ld + ch, f);
+#pragma unroll
+      for (int i = 0; i < V; ++i) s[i] += prelu(fmaf(f[i], sc[i], sh[i]), al[i]);
+    }
+#pragma unroll
+  for (int i = 0; i < V; ++i) s[i] *= 0.25f;
   const size_t orow = (size_t)n * (H2 + 2) * (W2 + 2) + (size_t)(y + 1) * (W2 + 2) + (x + 1);
-  out[orow * c + ch] = from_f32<T>(s * 0.25f);
+  store_vec<T>(out + orow * c + ch, s);
 }
 
 int launch_act_pool2(const void* blk, int n, int H, int W, int ld, int c, const float* scale, const float* shift,
                      const float* alpha, void* out, int H2, int W2, bool f32, cudaStream_t stream) {
-  const long long total = (long long)n * H2 * W2 * c;
+  const int V = f32 ? 4 : 8;
+  if (c % V || ld % V) return fail(TCVN_ERR_UNSUPPORTED, "act_pool2: channel count %d / pitch %d not a multiple of %d", c, ld, V);
+  const long long total = (long long)n * H2 * W2 * (c / V);
   if (total == 0) return TCVN_OK;
   const unsigned grid = (unsigned)ceil_div_ll(total, 256);
   if (f32) act_pool2_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(blk), H, W, ld, c, scale, shift,

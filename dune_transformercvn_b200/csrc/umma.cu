@@ -132,7 +132,8 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
   uint8_t* sA = smem;                                   // [stages][16 KB]
   uint8_t* sW = smem + kC1Stages * kStageA;             // [stages][16 KB]
   uint8_t* sOut = sW + kC1Stages * kStageW;             // [2 groups][2 halves][128 rows x 128 B], swizzled
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + 4 * kStageA);
+  float* s_epi = reinterpret_cast<float*>(sOut + 4 * kStageA);  // [2 groups][128 shift + 64 packed slopes]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + 2 * 192);
   uint64_t* full = bars;                    // TMA -> transform (or MMA)
   uint64_t* ready = bars + kC1Stages;       // transform -> MMA
   uint64_t* empty = bars + 2 * kC1Stages;   // MMA -> TMA
@@ -221,21 +222,32 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
             sh[0] = y0.x; sh[1] = y0.y; sh[2] = y0.z; sh[3] = y0.w; sh[4] = y1.x; sh[5] = y1.y; sh[6] = y1.z; sh[7] = y1.w;
             al[0] = z0.x; al[1] = z0.y; al[2] = z0.z; al[3] = z0.w; al[4] = z1.x; al[5] = z1.y; al[6] = z1.z; al[7] = z1.w;
           }
+          // BN in fp32, PReLU on packed bf16 pairs (max/min are exact; one rounding of slope * negative part)
+          __nv_bfloat162 al2[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) al2[q] = __floats2bfloat162_rn(al[2 * q], al[2 * q + 1]);
+          const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
           ptx::mbar_wait(&full[stage], phase);
           uint8_t* base = sA + stage * kStageA + rb * 128 + pc * 16;
-          uint4 v[4];
+          if (live) {
+            uint4 v[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const uint4*>(base + i * 32 * 128);
+            for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const uint4*>(base + i * 32 * 128);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+            for (int i = 0; i < 4; ++i) {
+              uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float lo = prelu_fast(fmaf(bf_lo(w[q]), sc[2 * q], sh[2 * q]), al[2 * q]);
-              const float hi = prelu_fast(fmaf(bf_hi(w[q]), sc[2 * q + 1], sh[2 * q + 1]), al[2 * q + 1]);
-              w[q] = live ? pack_bf16(lo, hi) : 0u;
+              for (int q = 0; q < 4; ++q) {
+                const __nv_bfloat162 y = __floats2bfloat162_rn(fmaf(bf_lo(w[q]), sc[2 * q], sh[2 * q]),
+                                                               fmaf(bf_hi(w[q]), sc[2 * q + 1], sh[2 * q + 1]));
+                const __nv_bfloat162 r = __hfma2(al2[q], __hmin2(y, zero2), __hmax2(y, zero2));
+                w[q] = *reinterpret_cast<const uint32_t*>(&r);
+              }
+              *reinterpret_cast<uint4*>(base + i * 32 * 128) = make_uint4(w[0], w[1], w[2], w[3]);
             }
-            *reinterpret_cast<uint4*>(base + i * 32 * 128) = make_uint4(w[0], w[1], w[2], w[3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(base + i * 32 * 128) = make_uint4(0u, 0u, 0u, 0u);
           }
           ptx::fence_proxy_async_smem();
           ptx::mbar_arrive(&ready[stage]);
@@ -250,6 +262,8 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
     const int R = p.Hp * p.Wp;
     const bool issuer = threadIdx.x == (10 + 4 * grp) * 32;
     uint8_t* stg = sOut + grp * 2 * kStageA;
+    float* s_shift = s_epi + grp * 192;                                   // [128] fp32
+    uint32_t* s_alpha2 = reinterpret_cast<uint32_t*>(s_shift + kMid);     // [64] bf16x2
     uint32_t acc_phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -262,8 +276,16 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
         const int y = rr / p.Wp, x = rr - y * p.Wp;
         ring = y == 0 || y == p.Hp - 1 || x == 0 || x == p.Wp - 1;
       }
-      const float* shift = p.o_shift + nt * kMid;
-      const float* alpha = p.o_alpha + nt * kMid;
+      // this tile's epilogue constants -> shared memory (shift fp32, PReLU slopes as packed bf16 pairs)
+      {
+        const int e = threadIdx.x - (10 + 4 * grp) * 32;  // 0..127
+        s_shift[e] = __ldg(p.o_shift + nt * kMid + e);
+        if (e < kMid / 2) {
+          const float2 a = __ldg(reinterpret_cast<const float2*>(p.o_alpha + nt * kMid) + e);
+          const __nv_bfloat162 a2 = __floats2bfloat162_rn(a.x, a.y);
+          s_alpha2[e] = *reinterpret_cast<const uint32_t*>(&a2);
+        }
+      }
       ptx::mbar_wait(&tfull[grp], acc_phase);
       ptx::tc_fence_after();
       if (issuer) ptx::tma_store_wait_read();  // this group's previous store has drained the staging tile
@@ -275,6 +297,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(g * 32) << 16) + grp * kMid + c * 32 + 32, r1);
         ptx::tmem_ld_wait();
         uint8_t* orow = stg + (c >> 1) * kStageA + row * 128;
+        const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
 #pragma unroll
         for (int hh = 0; hh < 2; ++hh) {
           const uint32_t* r = hh ? r1 : r0;
@@ -284,18 +307,19 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int n = (c + hh) * 32 + q * 8 + h * 4;
-              const float4 sh = __ldg(reinterpret_cast<const float4*>(shift + n));
-              const float4 al = __ldg(reinterpret_cast<const float4*>(alpha + n));
+              const float4 sh = *reinterpret_cast<const float4*>(s_shift + n);
+              const uint2 a2 = *reinterpret_cast<const uint2*>(s_alpha2 + (n >> 1));
               const int j = q * 8 + h * 4;
-              const float v0 = prelu_fast(__uint_as_float(r[j + 0]) + sh.x, al.x);
-              const float v1 = prelu_fast(__uint_as_float(r[j + 1]) + sh.y, al.y);
-              const float v2 = prelu_fast(__uint_as_float(r[j + 2]) + sh.z, al.z);
-              const float v3 = prelu_fast(__uint_as_float(r[j + 3]) + sh.w, al.w);
-              o[2 * h] = ring ? 0u : pack_bf16(v0, v1);
-              o[2 * h + 1] = ring ? 0u : pack_bf16(v2, v3);
+              const __nv_bfloat162 y0 = __floats2bfloat162_rn(__uint_as_float(r[j + 0]) + sh.x, __uint_as_float(r[j + 1]) + sh.y);
+              const __nv_bfloat162 y1 = __floats2bfloat162_rn(__uint_as_float(r[j + 2]) + sh.z, __uint_as_float(r[j + 3]) + sh.w);
+              const __nv_bfloat162 p0 = __hfma2(*reinterpret_cast<const __nv_bfloat162*>(&a2.x), __hmin2(y0, zero2), __hmax2(y0, zero2));
+              const __nv_bfloat162 p1 = __hfma2(*reinterpret_cast<const __nv_bfloat162*>(&a2.y), __hmin2(y1, zero2), __hmax2(y1, zero2));
+              o[2 * h] = *reinterpret_cast<const uint32_t*>(&p0);
+              o[2 * h + 1] = *reinterpret_cast<const uint32_t*>(&p1);
             }
             const int chunk = hh * 4 + q;  // 16-byte chunk within the 128-byte half-row
-            *reinterpret_cast<uint4*>(orow + ((chunk ^ (row & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(orow + ((chunk ^ (row & 7)) << 4)) =
+                ring ? make_uint4(0u, 0u, 0u, 0u) : make_uint4(o[0], o[1], o[2], o[3]);
           }
         }
       }
@@ -318,20 +342,30 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
 }
 
 // ------------------------------------------------------------------------------------------------
-// conv2: 3x3 convolution as a shifted GEMM over one haloed tile
+// conv2: 3x3 convolution as a shifted GEMM over one haloed tile, vertical taps in the MMA, horizontal
+// taps in the epilogue.
+//   Y[q][(dx, n)] = sum_dy sum_c mid[q + (dy-1)*Wp][c] * W[dy][dx][n][c]      3 x 8 MMAs of M128 N96 K16
+//   out[p][n]     = Y[p-1][(0,n)] + Y[p][(1,n)] + Y[p+1][(2,n)] + b[n]        lane shuffles after tcgen05.ld
+// An MMA with N = 32 spends its time re-reading the 4 KB A slab from shared memory (measured: tensor pipe
+// 74 % busy at 28 % of peak); widening N to the three horizontal taps reads A a third as often.  Row p+-1
+// is the neighbouring TMEM lane, so each tile produces 126 output rows from 128 Y rows; the two lanes at
+// every warp boundary are exchanged through shared memory.
 // ------------------------------------------------------------------------------------------------
 constexpr int kC2Stages = 2;
 constexpr int kC2Threads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
 constexpr int kGrowth = 32;
 constexpr int kBoxRows = 32;
-constexpr int kW2Bytes = 9 * 2 * kGrowth * 128;  // 72 KB: [tap][half][32 rows x 128 B]
+constexpr int kC2N = 3 * kGrowth;               // 96 accumulator columns: (dx, n)
+constexpr int kC2Out = kTileM - 2;              // 126 output rows per tile
+constexpr int kW2Slab = kC2N * 128;             // 12 KB: [96 rows x 128 B] per (dy, half)
+constexpr int kW2Bytes = 3 * 2 * kW2Slab;       // 72 KB
 
 struct Conv2Params {
   long long m_total;
-  int Hp, Wp, halo_rows, nbox;  // halo_rows = nbox * kBoxRows >= 128 + 2*(Wp+1)
+  int Hp, Wp, halo_rows, nbox;  // halo_rows = nbox * kBoxRows >= 128 + 2*Wp
   const float* bias;
   bf16* out;
-  int ldo, col0, num_tiles, base_offset_mode;
+  int ldo, col0, num_tiles;
 };
 
 __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -351,6 +385,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
   uint64_t* wfull = tempty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
+  float* s_exch = s_bias + kGrowth;  // [4 warps][2][32]: lane 31's dx=0 block, lane 0's dx=2 block
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -362,24 +397,23 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
     ptx::prefetch_tmap(&tmW);
   }
   if (threadIdx.x < kGrowth) s_bias[threadIdx.x] = p.bias[threadIdx.x];
-  if (warp == 0) ptx::tmem_alloc(tmem_slot, 64);
+  if (warp == 0) ptx::tmem_alloc(tmem_slot, 256);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const int halo = p.Wp + 1;
 
   if (warp == 0) {
     if (lane == 0) {
       ptx::mbar_arrive_expect_tx(wfull, kW2Bytes);
-      for (int t = 0; t < 9; ++t)
+      for (int dy = 0; dy < 3; ++dy)
         for (int h = 0; h < 2; ++h)
-          ptx::tma_load_2d(sW + (t * 2 + h) * 4096, &tmW, wfull, h * 64, t * kGrowth);
+          ptx::tma_load_2d(sW + (dy * 2 + h) * kW2Slab, &tmW, wfull, h * 64, dy * kC2N);
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         ptx::mbar_wait(&empty[stage], phase ^ 1);
         ptx::mbar_arrive_expect_tx(&full[stage], stage_bytes);
-        const int row0 = tile * kTileM - halo;
+        const int row0 = tile * kC2Out - 1 - p.Wp;  // Y row 0 of the tile is output row tile*126 - 1
         for (int h = 0; h < 2; ++h)
           for (int b = 0; b < p.nbox; ++b)
             ptx::tma_load_2d(sA + stage * stage_bytes + h * half_bytes + b * kBoxRows * 128, &tmA, &full[stage], h * 64,
@@ -389,33 +423,30 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_bf16(kTileM, kGrowth);
+      const uint32_t idesc = ptx::umma_idesc_bf16(kTileM, kC2N);
       ptx::mbar_wait(wfull, 0);
       const uint32_t w_lo = ptx::umma_desc_lo(ptx::smem_u32(sW));
+      const uint32_t half16 = (uint32_t)half_bytes >> 4;
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
         ptx::mbar_wait(&full[stage], phase);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kGrowth;
-        const uint32_t a_stage = ptx::smem_u32(sA + stage * stage_bytes);
-        // 72 MMAs, straight-line: descriptors differ only in their 14-bit start-address field, which moves in
-        // 16-byte units: +8 per row, +2 per K step of 16 channels (all offsets below are in those units)
-        const uint32_t a_lo = ptx::umma_desc_lo(a_stage);
-        const uint32_t half16 = (uint32_t)half_bytes >> 4;
+        const uint32_t d_tmem = tmem_base + acc * 128;
+        // descriptors differ only in their 14-bit start-address field, in 16-byte units: +8 per row of the
+        // haloed tile (any row is a legal start: the 128B swizzle is a function of the absolute address),
+        // +2 per K step of 16 channels
+        const uint32_t a_lo = ptx::umma_desc_lo(ptx::smem_u32(sA + stage * stage_bytes));
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy) {
-          const uint32_t row_lo = a_lo + (uint32_t)(halo + (dy - 1) * p.Wp - 1) * 8u;
+          const uint32_t row_lo = a_lo + (uint32_t)(dy * p.Wp) * 8u;
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-#pragma unroll
-            for (int kk = 0; kk < 8; ++kk) {
-              const uint32_t al = row_lo + dx * 8u + (kk >> 2) * half16 + (kk & 3) * 2u;
-              const uint32_t bl = w_lo + ((dy * 3 + dx) * 2 + (kk >> 2)) * 256u + (kk & 3) * 2u;
-              ptx::umma_bf16(d_tmem, ptx::umma_desc_join(ptx::kUmmaDescHiSw128, al),
-                             ptx::umma_desc_join(ptx::kUmmaDescHiSw128, bl), idesc, (dy | dx | kk) != 0);
-            }
+          for (int kk = 0; kk < 8; ++kk) {
+            const uint32_t al = row_lo + (kk >> 2) * half16 + (kk & 3) * 2u;
+            const uint32_t bl = w_lo + (dy * 2 + (kk >> 2)) * (kW2Slab >> 4) + (kk & 3) * 2u;
+            ptx::umma_bf16(d_tmem, ptx::umma_desc_join(ptx::kUmmaDescHiSw128, al),
+                           ptx::umma_desc_join(ptx::kUmmaDescHiSw128, bl), idesc, (dy | kk) != 0);
           }
         }
         ptx::umma_commit(&empty[stage]);
@@ -428,37 +459,60 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
     const int g = warp & 3;
     const int row = g * 32 + lane;
     const int R = p.Hp * p.Wp;
+    float* ex_mine = s_exch + g * 64;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const long long m = (long long)tile * kTileM + row;
+      const long long m = (long long)tile * kC2Out + row - 1;  // output row of this lane
       bool ring = false;
       {
-        const int rr = (int)(m % R);
+        const int rr = (int)((m + R) % R);
         const int y = rr / p.Wp, x = rr - y * p.Wp;
         ring = y == 0 || y == p.Hp - 1 || x == 0 || x == p.Wp - 1;
       }
       ptx::mbar_wait(&tfull[acc], acc_phase);
       ptx::tc_fence_after();
-      uint32_t r[32];
-      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(g * 32) << 16) + acc * kGrowth, r);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(g * 32) << 16) + acc * 128;
+      uint32_t left[32], mid[32], right[32];
+      ptx::tmem_ld_32x32(t_addr, left);
+      ptx::tmem_ld_32x32(t_addr + 32, mid);
+      ptx::tmem_ld_32x32(t_addr + 64, right);
       ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty[acc]);
-      if (m < p.m_total) {
-        uint32_t o[16];
+      // publish the boundary lanes, then pull the neighbours' values: Y[p-1] block 0, Y[p+1] block 2
+      ptx::named_bar_sync(3, 128);  // previous tile's exchange fully consumed
+      if (lane == 31) {
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          o[j] = ring ? 0u : pack_bf16(__uint_as_float(r[2 * j]) + s_bias[2 * j], __uint_as_float(r[2 * j + 1]) + s_bias[2 * j + 1]);
+        for (int j = 0; j < 32; ++j) ex_mine[j] = __uint_as_float(left[j]);
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ex_mine[32 + j] = __uint_as_float(right[j]);
+      }
+      ptx::named_bar_sync(3, 128);
+      float o[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float l = __shfl_up_sync(0xffffffffu, __uint_as_float(left[j]), 1);
+        float r = __shfl_down_sync(0xffffffffu, __uint_as_float(right[j]), 1);
+        if (lane == 0 && g > 0) l = s_exch[(g - 1) * 64 + j];
+        if (lane == 31 && g < 3) r = s_exch[(g + 1) * 64 + 32 + j];
+        o[j] = l + __uint_as_float(mid[j]) + r + s_bias[j];
+      }
+      if (row >= 1 && row <= kC2Out && m < p.m_total) {
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) w[j] = ring ? 0u : pack_bf16(o[2 * j], o[2 * j + 1]);
         uint4* dst = reinterpret_cast<uint4*>(p.out + m * p.ldo + p.col0);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+        for (int j = 0; j < 4; ++j) dst[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
       }
       if ((acc ^= 1) == 0) acc_phase ^= 1;
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 0) ptx::tmem_dealloc(tmem_base, 64);
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, 256);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -471,7 +525,7 @@ static int launch_gemm(bool transform, const void* A, long long rows, int a_cols
                        const float* o_shift, const float* o_alpha, void* out, int out_cols, int out_pitch, int n_tiles_n,
                        int Hp, int Wp, cudaStream_t st) {
   if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one chunk");
-  const size_t smem = 1024 + kC1Stages * (kStageA + kStageW) + 4 * kStageA + (3 * kC1Stages + 4) * 8 + 16;
+  const size_t smem = 1024 + kC1Stages * (kStageA + kStageW) + 4 * kStageA + 2 * 192 * 4 + (3 * kC1Stages + 4) * 8 + 16;
   static bool attr_done = false;
   if (!attr_done) {
     TCVN_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -505,18 +559,18 @@ int umma_dense_layer(const CnnPlan& P, const BlockPlan& B, const LayerPlan& L, c
                        pf(pk, L.p_a_shift), pf(pk, L.p_a_alpha), pf(pk, L.p_o_shift), pf(pk, L.p_o_alpha), mid, kMid, kMid,
                        1, B.Hp, B.Wp, st));
   // ---- conv2
-  const int tiles = (int)ceil_div_ll(rows, kTileM);
+  const int tiles = (int)ceil_div_ll(rows, kC2Out);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   const int halo_rows_max = 288;
   static bool attr_done = false;
   if (!attr_done) {
     TCVN_CUDA(cudaFuncSetAttribute(umma_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   1024 + kW2Bytes + kC2Stages * 2 * halo_rows_max * 128 + 256));
+                                   1024 + kW2Bytes + kC2Stages * 2 * halo_rows_max * 128 + 1536));
     attr_done = true;
   }
   Conv2Params c2;
   c2.m_total = rows; c2.Hp = B.Hp; c2.Wp = B.Wp;
-  c2.nbox = ceil_div(kTileM + 2 * (B.Wp + 1), kBoxRows);
+  c2.nbox = ceil_div(kTileM + 2 * B.Wp, kBoxRows);
   c2.halo_rows = c2.nbox * kBoxRows;
   if (c2.halo_rows > halo_rows_max)
     return fail(TCVN_ERR_UNSUPPORTED, "feature map width %d needs a %d-row halo tile (max %d)", B.W, c2.halo_rows, halo_rows_max);
@@ -525,11 +579,10 @@ int umma_dense_layer(const CnnPlan& P, const BlockPlan& B, const LayerPlan& L, c
   // Measured on B200: the 128B swizzle of a UMMA operand is a function of the absolute shared-memory address
   // (bits [4,7) ^= bits [7,10)), exactly as TMA wrote it, so a descriptor may start at ANY row of the haloed
   // tile with matrix-base-offset 0 (setting it to (addr >> 7) & 7 gives wrong results).
-  c2.base_offset_mode = 0;
   CUtensorMap tmM, tmW2;
   TCVN_TRY(make_map(mid, rows, kMid, kMid, 64, kBoxRows, &tmM));
-  TCVN_TRY(make_map(pk + L.p_w2, 9 * kGrowth, kMid, kMid, 64, kGrowth, &tmW2));
-  const size_t smem2 = 1024 + kW2Bytes + (size_t)kC2Stages * 2 * c2.halo_rows * 128 + 256;
+  TCVN_TRY(make_map(pk + L.p_w2, 9 * kGrowth, kMid, kMid, 64, kC2N, &tmW2));
+  const size_t smem2 = 1024 + kW2Bytes + (size_t)kC2Stages * 2 * c2.halo_rows * 128 + 1536;
   umma_conv2_kernel<<<grid, kC2Threads, smem2, st>>>(tmM, tmW2, c2);
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
