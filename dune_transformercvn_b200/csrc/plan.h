@@ -7,6 +7,7 @@
 // state_dict by tests/test_params.py).
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -193,10 +194,22 @@ inline bool CnnPlan::build(const tcvn_cnn_desc& d, tcvn_precision prec, int n_im
   P.p_lo_shift = ptake(d.out_features * 4);
   P.p_lo_alpha = ptake(d.out_features * 4);
   P.packed_bytes = p;
-  // workspace: block b is processed `chunk` images at a time, sized so that its concat buffer plus the
-  // bottleneck intermediate stay L2-resident between layers (126 MB L2); later blocks have smaller maps and
-  // take whole multiples of the previous block's chunk so that their launches still fill the 148 SMs.
-  const size_t l2_budget = (size_t)80 << 20;
+  // workspace: block b is processed `chunk` images at a time; later blocks have smaller maps and take whole
+  // multiples of the previous block's chunk so that their launches still fill the 148 SMs.  The chunk is sized
+  // by a working-set budget (concat buffer + bottleneck intermediate).  Measured on B200 (scripts/sweep_budget.sh,
+  // 256-event batch): 48 MB 5.3k, 80 MB 6.6k, 160 MB 7.7k, 320 MB 8.7k, 768 MB 9.3k, 1024 MB 9.3k events/s - the
+  // layer kernels are issue/latency-bound, not HBM-bound, so keeping a chunk inside the 126 MB L2 buys nothing
+  // yet and long persistent launches win; revisit when the kernels approach the memory roofline.
+  size_t l2_budget = (size_t)768 << 20;
+  if (const char* e = getenv("TCVN_L2_BUDGET_MB")) { const int mb = atoi(e); if (mb > 0) l2_budget = (size_t)mb << 20; }
+  // tiles of the two persistent kernels of a dense layer (128 / 126 rows) over `c` images: fraction of the
+  // last wave of 148 CTAs that does useful work
+  auto wave_eff = [&](const BlockPlan& B, int c) {
+    const long long rows = (long long)c * B.R;
+    const long long t1 = (rows + 127) / 128, t2 = (rows + 125) / 126;
+    const double e1 = (double)t1 / (double)((t1 + 147) / 148 * 148), e2 = (double)t2 / (double)((t2 + 147) / 148 * 148);
+    return e1 < e2 ? e1 : e2;
+  };
   int prev = 0;
   for (auto& B : P.blocks) {
     const size_t per_image = (size_t)B.R * (B.ctot + P.mid) * P.esize;
@@ -204,8 +217,20 @@ inline bool CnnPlan::build(const tcvn_cnn_desc& d, tcvn_precision prec, int n_im
     if (c < 1) c = 1;
     if (prev) c = c / prev * prev;
     if (c < prev) c = prev;
-    if (c > 1024) c = prev ? 1024 / prev * prev : 1024;
-    if (prev == 0 && c > n_images) c = n_images < 1 ? 1 : n_images;
+    if (c > 4096) c = prev ? 4096 / prev * prev : 4096;
+    if (prev == 0) {
+      if (c > n_images) c = n_images < 1 ? 1 : n_images;
+      else {
+        // first block: among chunk sizes within 25 % of the budget pick the one that fills its last wave best
+        int best = c;
+        double best_eff = wave_eff(B, c);
+        for (int k = c - 1; k >= c - c / 4 && k >= 1; --k) {
+          const double e = wave_eff(B, k);
+          if (e > best_eff + 0.02) { best = k; best_eff = e; }
+        }
+        c = best;
+      }
+    }
     if (prev && c > n_images) c = (n_images + prev - 1) / prev * prev;  // never larger than the batch needs
     B.chunk = c;
     prev = c;
