@@ -27,11 +27,21 @@ struct Walk {
   char* ws;
   cudaStream_t st;
   bool f32;
+  // COO-direct ingest (pixels == nullptr): the stem reads the hit list itself
+  const int32_t* coords = nullptr;
+  const void* values = nullptr;
+  bool values_u8 = false;
+  float divisor = 0.f;
 
   int stem(int i0, int n) {
     const tcvn_cnn_desc& d = P.d;
     const size_t img_floats = (size_t)d.in_channels * d.height * d.width;
     const BlockPlan& B0 = P.blocks[0];
+    if (pixels == nullptr)
+      return launch_stem_coo(coords, values, values_u8, reinterpret_cast<const long long*>(ws + P.ws_hitofs), i0, divisor,
+                             n, d.in_channels, d.height, d.width, pf(pk, P.p_w0), pf(pk, P.p_s_scale),
+                             pf(pk, P.p_s_shift), pf(pk, P.p_s_alpha), d.init_features, ws + B0.ws_blk, B0.ctot, B0.H,
+                             B0.W, f32, st);
     return launch_stem(pixels + (size_t)i0 * img_floats, n, d.in_channels, d.height, d.width, pf(pk, P.p_w0),
                        pf(pk, P.p_s_scale), pf(pk, P.p_s_shift), pf(pk, P.p_s_alpha), d.init_features, ws + B0.ws_blk,
                        B0.ctot, B0.H, B0.W, f32, st);
@@ -133,6 +143,33 @@ extern "C" int tcvn_cnn_forward(const tcvn_cnn_desc* d, tcvn_precision prec, con
   if (workspace_bytes < P.ws_bytes)
     return fail(TCVN_ERR_WORKSPACE, "cnn_forward: workspace %zu < %zu bytes", workspace_bytes, P.ws_bytes);
   Walk w{P, static_cast<const char*>(packed), pixels, static_cast<char*>(workspace), stream, prec == TCVN_FP32};
+  const int last = (int)P.blocks.size() - 1;
+  const int top = P.blocks[last].chunk;
+  for (int i0 = 0; i0 < n_images; i0 += top) {
+    const int n = n_images - i0 < top ? n_images - i0 : top;
+    TCVN_TRY(w.process(last, i0, n));
+    TCVN_TRY(w.tail(n, embedding + (size_t)i0 * d->out_features));
+  }
+  return TCVN_OK;
+}
+
+extern "C" int tcvn_cnn_forward_sparse(const tcvn_cnn_desc* d, tcvn_precision prec, const void* packed,
+                                       const int32_t* coords, const void* values, tcvn_value_dtype value_dtype,
+                                       int64_t nnz, float divisor, int n_images, float* embedding, void* workspace,
+                                       size_t workspace_bytes, tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(d && packed && workspace, "cnn_forward_sparse: null pointer");
+  TCVN_CHECK_ARG(prec == TCVN_FP32 || prec == TCVN_BF16, "cnn_forward_sparse: unknown precision");
+  TCVN_CHECK_ARG(value_dtype == TCVN_VAL_F32 || value_dtype == TCVN_VAL_U8, "cnn_forward_sparse: unknown value dtype");
+  TCVN_CHECK_ARG(n_images >= 0 && nnz >= 0, "cnn_forward_sparse: negative size");
+  if (n_images == 0) return TCVN_OK;
+  TCVN_CHECK_ARG(embedding && (nnz == 0 || (coords && values)), "cnn_forward_sparse: null pointer");
+  CnnPlan P;
+  TCVN_CHECK_ARG(CnnPlan::build(*d, prec, n_images, &P), "cnn_forward_sparse: bad descriptor");
+  if (workspace_bytes < P.ws_bytes)
+    return fail(TCVN_ERR_WORKSPACE, "cnn_forward_sparse: workspace %zu < %zu bytes", workspace_bytes, P.ws_bytes);
+  Walk w{P, static_cast<const char*>(packed), nullptr, static_cast<char*>(workspace), stream, prec == TCVN_FP32};
+  w.coords = coords; w.values = values; w.values_u8 = value_dtype == TCVN_VAL_U8; w.divisor = divisor;
+  TCVN_TRY(launch_hit_offsets(coords, nnz, n_images, reinterpret_cast<long long*>(w.ws + P.ws_hitofs), stream));
   const int last = (int)P.blocks.size() - 1;
   const int top = P.blocks[last].chunk;
   for (int i0 = 0; i0 < n_images; i0 += top) {

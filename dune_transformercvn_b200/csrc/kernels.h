@@ -25,6 +25,12 @@ int launch_simt_gemm(const GemmArgs& g, cudaStream_t stream);
 int launch_stem(const float* pixels, int n, int cin, int H, int W, const float* w0, const float* s_scale,
                 const float* s_shift, const float* s_alpha, int c0, void* blk, int ldo, int Hb, int Wb, bool f32,
                 cudaStream_t stream);
+// stem straight from the COO hit list (no dense map): image_offsets[i] = first hit of image i
+int launch_hit_offsets(const int32_t* coords, long long nnz, int n_images, long long* offsets, cudaStream_t stream);
+int launch_stem_coo(const int32_t* coords, const void* values, bool values_u8, const long long* image_offsets, int image0,
+                    float divisor, int n, int cin, int H, int W, const float* w0, const float* s_scale,
+                    const float* s_shift, const float* s_alpha, int c0, void* blk, int ldo, int Hb, int Wb, bool f32,
+                    cudaStream_t stream);
 // transition front half: BN + PReLU + AvgPool2d(2,2) of a ringed block buffer into a ringed buffer of the next geometry
 int launch_act_pool2(const void* blk, int n, int H, int W, int ld, int c, const float* scale, const float* shift,
                      const float* alpha, void* out, int H2, int W2, bool f32, cudaStream_t stream);

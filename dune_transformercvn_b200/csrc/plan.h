@@ -84,7 +84,7 @@ struct CnnPlan {
   std::vector<BlockPlan> blocks;
   // workspace (sized for `chunk` images)
   int chunk;
-  size_t ws_stem, ws_mid, ws_pool, ws_gap, ws_bytes;
+  size_t ws_stem, ws_mid, ws_pool, ws_gap, ws_hitofs, ws_bytes;
 
   static bool build(const tcvn_cnn_desc& d, tcvn_precision prec, int n_images, CnnPlan* out);
   // physical channel of logical channel c inside block b's buffer
@@ -230,6 +230,7 @@ inline bool CnnPlan::build(const tcvn_cnn_desc& d, tcvn_precision prec, int n_im
         }
         c = best;
       }
+      if (const char* e = getenv("TCVN_CHUNK0")) { const int f = atoi(e); if (f > 0 && f <= n_images) c = f; }
     }
     if (prev && c > n_images) c = (n_images + prev - 1) / prev * prev;  // never larger than the batch needs
     B.chunk = c;
@@ -251,6 +252,7 @@ inline bool CnnPlan::build(const tcvn_cnn_desc& d, tcvn_precision prec, int n_im
   P.ws_mid = wtake(mid_rows * P.mid * P.esize);
   P.ws_pool = wtake(pool_elems * P.esize + 1024);
   P.ws_gap = wtake((size_t)P.blocks.back().chunk * (size_t)last.ctot * 4);
+  P.ws_hitofs = wtake(((size_t)(n_images < 1 ? 1 : n_images) + 1) * sizeof(long long));
   P.ws_bytes = w;
   return true;
 }

@@ -157,6 +157,74 @@ constexpr int kStemIn = 2 * kStemTC + 5;     // 39 input pixels per edge
 constexpr int kStemThreads = 512;            // (cy mod 4) x (cx mod 2) x 64 channels
 constexpr int kStemRows = kStemIn;           // window rows (pixels, all channels together)
 
+// Phases (2)-(4) of the stem for one tile, shared by the dense-window and the COO-direct kernels: scatter the
+// compacted hits, then bias+BN0+PReLU0 and AvgPool2d(3, 2) into the ringed block buffer.
+template <typename TO, int C0>
+__device__ __forceinline__ void stem_scatter_pool(const float* wsm, float* acc, const float4* hits, int nhits,
+                                                  int* touched, int cin, float sc, float sh, float al, int ch, int own_py,
+                                                  int own_px, int t, int n, int py0, int px0, TO* __restrict__ blk,
+                                                  int ldo, int Hb, int Wb) {
+  // ---- (2) scatter every hit into the conv outputs it reaches (input yy = 2*cy + ky)
+  for (int h = 0; h < nhits; ++h) {
+    const float4 hit = hits[h];
+    const int code = __float_as_int(hit.x);
+    const int yy = code >> 6, xx = code & 63;
+    // the unique cy in [cy_lo, cy_lo + 4) with cy % 4 == own_py, cy_lo = max(0, ceil((yy - 6) / 2))
+    const int cy_lo = yy > 6 ? (yy - 5) >> 1 : 0;
+    const int cy = cy_lo + ((own_py - cy_lo) & 3);
+    const int ky = yy - 2 * cy;
+    if (cy > kStemTC - 1 || ky < 0) continue;   // ky <= 6 by construction
+    const int cx_lo = xx > 6 ? (xx - 5) >> 1 : 0;
+    const int cx_a = cx_lo + ((own_px - cx_lo) & 1);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int cx = cx_a + 2 * k;
+      const int kx = xx - 2 * cx;
+      if (cx <= kStemTC - 1 && kx >= 0) {
+        const float* wp = wsm + (ky * 7 + kx) * C0 + ch;
+        float a = acc[(cy * kStemTC + cx) * C0 + ch];
+        a = fmaf(hit.y, wp[0], a);
+        if (cin > 1) a = fmaf(hit.z, wp[49 * C0], a);
+        if (cin > 2) a = fmaf(hit.w, wp[2 * 49 * C0], a);
+        acc[(cy * kStemTC + cx) * C0 + ch] = a;
+        if (ch == 0) touched[cy * kStemTC + cx] = 1;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- (3)+(4) bias + BN0 + PReLU0, AvgPool2d(3, 2) -> ringed block buffer.  A conv output no hit reached is
+  // the per-channel constant PReLU(shift); a pooling window of nine such outputs is evaluated once per thread
+  // (same additions and division as the general case, so the shortcut is bit-identical).
+  const float c_act = prelu(fmaf(0.f, sc, sh), al);
+  float c_pool = 0.f;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) c_pool += c_act;
+  c_pool /= 9.0f;
+  for (int i = t; i < kStemTP * kStemTP * C0; i += blockDim.x) {
+    const int p = i / C0;
+    const int pyl = p / kStemTP, pxl = p % kStemTP;
+    const int py = py0 + pyl, px = px0 + pxl;
+    if (py >= Hb || px >= Wb) continue;
+    const int base = (2 * pyl) * kStemTC + 2 * pxl;
+    int any = 0;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) any |= touched[base + dy * kStemTC + dx];
+    float r = c_pool;
+    if (any) {
+      float s2 = 0.f;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) s2 += prelu(fmaf(acc[(base + dy * kStemTC + dx) * C0 + ch], sc, sh), al);
+      r = s2 / 9.0f;
+    }
+    const size_t row = (size_t)n * (Hb + 2) * (Wb + 2) + (size_t)(py + 1) * (Wb + 2) + (px + 1);
+    blk[row * ldo + ch] = from_f32<TO>(r);
+  }
+}
+
 template <typename TO, int C0>
 __global__ void __launch_bounds__(kStemThreads) stem_fused_kernel(const float* __restrict__ pixels, int n_images, int cin,
                                                                   int H, int W, const float* __restrict__ w0,
@@ -256,67 +324,147 @@ __global__ void __launch_bounds__(kStemThreads) stem_fused_kernel(const float* _
     }
     if (tile + gridDim.x < total) load_window(tile + gridDim.x);  // in flight during the rest of this tile
     __syncthreads();
-    // ---- (2) scatter every hit into the conv outputs it reaches (input yy = 2*cy + ky)
-    const int nhits = row_start[kStemRows];
-    for (int h = 0; h < nhits; ++h) {
-      const float4 hit = hits[h];
-      const int code = __float_as_int(hit.x);
-      const int yy = code >> 6, xx = code & 63;
-      // the unique cy in [cy_lo, cy_lo + 4) with cy % 4 == own_py, cy_lo = max(0, ceil((yy - 6) / 2))
-      const int cy_lo = yy > 6 ? (yy - 5) >> 1 : 0;
-      const int cy = cy_lo + ((own_py - cy_lo) & 3);
-      const int ky = yy - 2 * cy;
-      if (cy > kStemTC - 1 || ky < 0) continue;   // ky <= 6 by construction
-      const int cx_lo = xx > 6 ? (xx - 5) >> 1 : 0;
-      const int cx_a = cx_lo + ((own_px - cx_lo) & 1);
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const int cx = cx_a + 2 * k;
-        const int kx = xx - 2 * cx;
-        if (cx <= kStemTC - 1 && kx >= 0) {
-          const float* wp = wsm + (ky * 7 + kx) * C0 + ch;
-          float a = acc[(cy * kStemTC + cx) * C0 + ch];
-          a = fmaf(hit.y, wp[0], a);
-          if (cin > 1) a = fmaf(hit.z, wp[49 * C0], a);
-          if (cin > 2) a = fmaf(hit.w, wp[2 * 49 * C0], a);
-          acc[(cy * kStemTC + cx) * C0 + ch] = a;
-          if (ch == 0) touched[cy * kStemTC + cx] = 1;
-        }
+    stem_scatter_pool<TO, C0>(wsm, acc, hits, row_start[kStemRows], touched, cin, sc, sh, al, ch, own_py, own_px, t, n, py0,
+                              px0, blk, ldo, Hb, Wb);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Stem straight from the Minkowski-format hit list: the dense 3 x 400 x 280 map is never built.
+// Fuses sparse_to_dense + "/255" (neutrino_full_dense_trainer.py:15-24,59-60) into the stem: each tile CTA
+// walks its image's slice of the (image-sorted) hit list in order, keeps the hits that fall into its input
+// window (ballot compaction: deterministic order) and hands them to the same scatter / pool code.
+// image_offsets[i] = first hit of image i (built by hit_offsets_kernel), so no binary search per tile.
+// ------------------------------------------------------------------------------------------------
+__global__ void hit_offsets_kernel(const int32_t* __restrict__ coords, long long nnz, int n_images,
+                                   long long* __restrict__ offsets) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n_images) return;
+  long long lo = 0, hi = nnz;
+  while (lo < hi) {
+    const long long mid = (lo + hi) >> 1;
+    if (__ldg(coords + 3 * mid) < i) lo = mid + 1; else hi = mid;
+  }
+  offsets[i] = lo;
+}
+
+template <typename TO, int C0, typename V>
+__global__ void __launch_bounds__(kStemThreads) stem_coo_kernel(const int32_t* __restrict__ coords,
+                                                                const V* __restrict__ values,
+                                                                const long long* __restrict__ image_offsets, int image0,
+                                                                float divisor, int n_images, int cin, int H, int W,
+                                                                const float* __restrict__ w0,
+                                                                const float* __restrict__ s_scale,
+                                                                const float* __restrict__ s_shift,
+                                                                const float* __restrict__ s_alpha, TO* __restrict__ blk,
+                                                                int ldo, int Hb, int Wb) {
+  extern __shared__ __align__(16) float smem[];
+  float* wsm = smem;                                  // [cin*49][C0]
+  float* acc = wsm + cin * 49 * C0;                   // [289][C0]
+  float4* hits = reinterpret_cast<float4*>(acc + kStemTC * kStemTC * C0);  // [39*39] (packed yx, v0, v1, v2)
+  __shared__ int wcount[kStemThreads / 32];
+  __shared__ int touched[kStemTC * kStemTC];
+  for (int i = threadIdx.x; i < cin * 49 * C0; i += blockDim.x) wsm[i] = __ldg(w0 + i);
+  const int tiles_x = (Wb + kStemTP - 1) / kStemTP, tiles_y = (Hb + kStemTP - 1) / kStemTP;
+  const int per_image = tiles_x * tiles_y;
+  const long long total = (long long)n_images * per_image;
+  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+  const int ch = t & (C0 - 1);
+  const int own_px = (t >> 6) & 1, own_py = t >> 7;
+  const float sc = __ldg(s_scale + ch), sh = __ldg(s_shift + ch), al = __ldg(s_alpha + ch);
+  constexpr int kCap = kStemIn * kStemIn;
+  for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int n = (int)(tile / per_image);
+    const int rem = (int)(tile - (long long)n * per_image);
+    const int py0 = (rem / tiles_x) * kStemTP, px0 = (rem % tiles_x) * kStemTP;
+    const int iy0 = 4 * py0 - 3, ix0 = 4 * px0 - 3;
+    const long long lo = __ldg(image_offsets + image0 + n), hi = __ldg(image_offsets + image0 + n + 1);
+    __syncthreads();  // previous tile fully consumed
+    {
+      float4* a4 = reinterpret_cast<float4*>(acc);
+      for (int i = t; i < kStemTC * kStemTC * C0 / 4; i += blockDim.x) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t < kStemTC * kStemTC) touched[t] = 0;
+    }
+    int base = 0;
+    for (long long h0 = lo; h0 < hi; h0 += kStemThreads) {
+      const long long h = h0 + t;
+      bool in = false;
+      int yy = 0, xx = 0;
+      if (h < hi) {
+        const int y = __ldg(coords + 3 * h + 1), x = __ldg(coords + 3 * h + 2);
+        yy = y - iy0; xx = x - ix0;
+        in = y >= 0 && y < H && x >= 0 && x < W && yy >= 0 && yy < kStemIn && xx >= 0 && xx < kStemIn;
       }
+      const unsigned b = __ballot_sync(0xffffffffu, in);
+      if (lane == 0) wcount[warp] = __popc(b);
+      __syncthreads();
+      int before = 0, all = 0;
+#pragma unroll
+      for (int w = 0; w < kStemThreads / 32; ++w) {
+        const int c = wcount[w];
+        before += w < warp ? c : 0;
+        all += c;
+      }
+      if (in) {
+        const int slot = base + before + __popc(b & ((1u << lane) - 1u));
+        float v[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          if (c < cin) {
+            float val = static_cast<float>(values[h * cin + c]);
+            if (divisor != 0.f) val = __fdiv_rn(val, divisor);  // same bits as the reference's v / 255.0
+            v[c] = val;
+          }
+        if (slot < kCap) hits[slot] = make_float4(__int_as_float(yy * 64 + xx), v[0], v[1], v[2]);
+      }
+      base += all;
+      __syncthreads();
     }
     __syncthreads();
-    // ---- (3)+(4) bias + BN0 + PReLU0, AvgPool2d(3, 2) -> ringed block buffer.  A conv output no hit reached is
-    // the per-channel constant PReLU(shift); a pooling window of nine such outputs is evaluated once per thread
-    // (same additions and division as the general case, so the shortcut is bit-identical).
-    const float c_act = prelu(fmaf(0.f, sc, sh), al);
-    float c_pool = 0.f;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) c_pool += c_act;
-    c_pool /= 9.0f;
-    for (int i = t; i < kStemTP * kStemTP * C0; i += blockDim.x) {
-      const int p = i / C0;
-      const int pyl = p / kStemTP, pxl = p % kStemTP;
-      const int py = py0 + pyl, px = px0 + pxl;
-      if (py >= Hb || px >= Wb) continue;
-      const int base = (2 * pyl) * kStemTC + 2 * pxl;
-      int any = 0;
-#pragma unroll
-      for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) any |= touched[base + dy * kStemTC + dx];
-      float r = c_pool;
-      if (any) {
-        float s2 = 0.f;
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-          for (int dx = 0; dx < 3; ++dx) s2 += prelu(fmaf(acc[(base + dy * kStemTC + dx) * C0 + ch], sc, sh), al);
-        r = s2 / 9.0f;
-      }
-      const size_t row = (size_t)n * (Hb + 2) * (Wb + 2) + (size_t)(py + 1) * (Wb + 2) + (px + 1);
-      blk[row * ldo + ch] = from_f32<TO>(r);
-    }
+    stem_scatter_pool<TO, C0>(wsm, acc, hits, base < kCap ? base : kCap, touched, cin, sc, sh, al, ch, own_py, own_px, t, n,
+                              py0, px0, blk, ldo, Hb, Wb);
   }
+}
+
+int launch_hit_offsets(const int32_t* coords, long long nnz, int n_images, long long* offsets, cudaStream_t stream) {
+  hit_offsets_kernel<<<ceil_div(n_images + 1, 128), 128, 0, stream>>>(coords, nnz, n_images, offsets);
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+int launch_stem_coo(const int32_t* coords, const void* values, bool values_u8, const long long* image_offsets, int image0,
+                    float divisor, int n, int cin, int H, int W, const float* w0, const float* s_scale,
+                    const float* s_shift, const float* s_alpha, int c0, void* blk, int ldo, int Hb, int Wb, bool f32,
+                    cudaStream_t stream) {
+  if (c0 != 64) return fail(TCVN_ERR_UNSUPPORTED, "stem: init_features %d (kernel is specialised for 64)", c0);
+  if (n == 0) return TCVN_OK;
+  const int Hs = (H + 6 - 7) / 2 + 1, Ws = (W + 6 - 7) / 2 + 1;
+  if ((Hs - 3) / 2 + 1 != Hb || (Ws - 3) / 2 + 1 != Wb) return fail(TCVN_ERR_ARG, "stem: geometry mismatch");
+  if (cin > 3) return fail(TCVN_ERR_UNSUPPORTED, "stem: %d input channels (kernel handles up to 3)", cin);
+  const size_t smem = ((size_t)cin * 49 * c0 + (size_t)kStemTC * kStemTC * c0) * sizeof(float) +
+                      (size_t)kStemIn * kStemIn * sizeof(float4);
+  int sms = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const long long tiles = (long long)n * ((Wb + kStemTP - 1) / kStemTP) * ((Hb + kStemTP - 1) / kStemTP);
+  const int grid = (int)(tiles < (long long)sms ? tiles : (long long)sms);
+#define TCVN_STEM_COO(TO, V)                                                                                          \
+  do {                                                                                                                \
+    TCVN_CUDA(cudaFuncSetAttribute(stem_coo_kernel<TO, 64, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    stem_coo_kernel<TO, 64, V><<<grid, kStemThreads, smem, stream>>>(coords, static_cast<const V*>(values), image_offsets, \
+                                                                     image0, divisor, n, cin, H, W, w0, s_scale, s_shift, \
+                                                                     s_alpha, static_cast<TO*>(blk), ldo, Hb, Wb);     \
+  } while (0)
+  if (f32 && !values_u8) TCVN_STEM_COO(float, float);
+  else if (f32 && values_u8) TCVN_STEM_COO(float, uint8_t);
+  else if (!f32 && !values_u8) TCVN_STEM_COO(__nv_bfloat16, float);
+  else TCVN_STEM_COO(__nv_bfloat16, uint8_t);
+#undef TCVN_STEM_COO
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
 }
 
 int launch_stem(const float* pixels, int n, int cin, int H, int W, const float* w0, const float* s_scale,

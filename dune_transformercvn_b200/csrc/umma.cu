@@ -97,7 +97,7 @@ static int sm_count() {
 //   warps 10-17 two epilogue groups, one per TMEM accumulator: TMEM -> regs -> +shift, PReLU, ring rows -> 0,
 //               bf16 -> swizzled staging tile -> TMA store
 // ------------------------------------------------------------------------------------------------
-constexpr int kC1Stages = 4;
+constexpr int kC1Stages = 5;
 constexpr int kC1Threads = 576;
 constexpr int kTileM = 128;
 constexpr int kMid = 128;              // N tile = bottleneck width the kernels are specialised for

@@ -24,7 +24,7 @@ MAX_BLOCKS, MAX_DECODER_LAYERS = 8, 8
 EXPORTS = (
     "tcvn_abi_version", "tcvn_last_error", "tcvn_densify",
     "tcvn_cnn_arena_floats", "tcvn_cnn_packed_bytes", "tcvn_cnn_pack", "tcvn_cnn_workspace_bytes",
-    "tcvn_cnn_forward", "tcvn_cnn_read_stage",
+    "tcvn_cnn_forward", "tcvn_cnn_forward_sparse", "tcvn_cnn_read_stage",
     "tcvn_seq_packed_bytes", "tcvn_seq_pack", "tcvn_seq_workspace_bytes", "tcvn_seq_forward",
 )
 
@@ -70,6 +70,7 @@ def load() -> C.CDLL:
     lib.tcvn_cnn_workspace_bytes.argtypes = [C.POINTER(CnnDesc), i32, i32]
     lib.tcvn_cnn_workspace_bytes.restype = sz
     lib.tcvn_cnn_forward.argtypes = [C.POINTER(CnnDesc), i32, vp, vp, i32, vp, vp, sz, vp]
+    lib.tcvn_cnn_forward_sparse.argtypes = [C.POINTER(CnnDesc), i32, vp, vp, vp, i32, i64, f32, i32, vp, vp, sz, vp]
     lib.tcvn_cnn_read_stage.argtypes = [C.POINTER(CnnDesc), i32, vp, i32, i32, vp, C.POINTER(C.c_int32),
                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp]
     lib.tcvn_seq_packed_bytes.argtypes = [C.POINTER(SeqDesc)]

@@ -172,6 +172,36 @@ class _Engine:
                                       _lib.ptr(ws), ws.numel(), _lib.stream_ptr(pixels.device)), "tcvn_cnn_forward")
         return out
 
+    def cnn_sparse(self, tag: str, values: torch.Tensor, coords: torch.Tensor, n: int, prec: int,
+                   divisor: float = 255.0) -> torch.Tensor:
+        """Pixel-map embedding straight from the COO hit list (the dense map is never built)."""
+        L = _lib.load()
+        net = self.owner[0]
+        pix, feat, _ = embedding_dims(net.options)
+        width = pix if tag == "prong" else pix + feat
+        d = self.cnn_desc(width)
+        out = torch.empty((n, width), dtype=torch.float32, device=values.device)
+        if n == 0:
+            return out
+        if coords.dtype != torch.int32:
+            coords = coords.to(torch.int32)
+        coords = coords.contiguous()
+        if values.dtype == torch.uint8:
+            vd = _lib.TCVN_VAL_U8
+        else:
+            vd = _lib.TCVN_VAL_F32
+            values = values.float()
+        values = values.contiguous()
+        if values.dim() != 2 or values.shape[1] != d.in_channels:
+            raise _lib.TcvnError(f"{tag} hit values have shape {tuple(values.shape)}, expected (nnz,{d.in_channels})")
+        nbytes = L.tcvn_cnn_workspace_bytes(C.byref(d), prec, n)
+        ws = self.workspace("cnn", nbytes, values.device)
+        _lib.check(L.tcvn_cnn_forward_sparse(C.byref(d), prec, _lib.ptr(self.packed[tag]), _lib.ptr(coords),
+                                             _lib.ptr(values), vd, coords.shape[0], float(divisor), n, _lib.ptr(out),
+                                             _lib.ptr(ws), ws.numel(), _lib.stream_ptr(values.device)),
+                   "tcvn_cnn_forward_sparse")
+        return out
+
     def read_stage(self, tag: str, n: int, stage: int, prec: int, dev) -> torch.Tensor:
         """Test hook: a feature map of the last ``cnn`` call as (n,C,H,W) fp32."""
         L = _lib.load()
@@ -350,9 +380,23 @@ class NeutrinoDenseNetwork(nn.Module):
                                              prong_mask)
         return ev_logits, pr_logits
 
-    def forward_sparse(self, batch: "synth.SparseBatch"):
-        """Trainer-level path (neutrino_full_base_trainer.py:113-116): /255 + densify + network, no host sync."""
-        from .ingest import densify
-        ev = densify(batch.event_values, batch.event_coords, self.image_size, batch.num_events, 255.0)
-        pr = densify(batch.prong_values, batch.prong_coords, self.image_size, batch.num_prongs, 255.0)
-        return self.forward(batch.features, batch.extra, ev, batch.event_mask, pr, batch.prong_mask)
+    def forward_sparse(self, batch: "synth.SparseBatch", materialize: bool = False):
+        """Trainer-level path (neutrino_full_base_trainer.py:113-116): /255 + sparse_to_dense + network.
+
+        By default the stem consumes the hit lists directly (no dense map, no host sync);
+        ``materialize=True`` runs the literal sequence densify kernel -> dense forward instead."""
+        if materialize:
+            from .ingest import densify
+            ev = densify(batch.event_values, batch.event_coords, self.image_size, batch.num_events, 255.0)
+            pr = densify(batch.prong_values, batch.prong_coords, self.image_size, batch.num_prongs, 255.0)
+            return self.forward(batch.features, batch.extra, ev, batch.event_mask, pr, batch.prong_mask)
+        _check_eval(self)
+        eng = self.engine
+        prec = _PRECISIONS[self.precision]
+        _lib.require_cuda(batch.event_values, "event hit values")
+        eng.ensure_packed(prec)
+        ev = eng.cnn_sparse("event", batch.event_values, batch.event_coords, batch.num_events, prec)
+        pr = eng.cnn_sparse("prong", batch.prong_values, batch.prong_coords, batch.num_prongs, prec)
+        _, _, ev_logits, pr_logits = eng.seq(_lib.SEQ_TOKENS | _lib.SEQ_ENCODER | _lib.SEQ_HEADS, ev, pr,
+                                             batch.event_mask, batch.prong_mask)
+        return ev_logits, pr_logits

@@ -103,6 +103,14 @@ size_t tcvn_cnn_workspace_bytes(const tcvn_cnn_desc* d, tcvn_precision prec, int
 int tcvn_cnn_forward(const tcvn_cnn_desc* d, tcvn_precision prec, const void* packed, const float* pixels,
                      int n_images, float* embedding, void* workspace, size_t workspace_bytes,
                      tcvn_stream_t stream);
+/* Same forward fed straight from the Minkowski-format hit list: fuses sparse_to_dense and the
+ * "/ divisor" of preprocess_pixels (trainers/neutrino_full_dense_trainer.py:15-24,59-60) into the stem,
+ * so the dense 3 x H x W map is never built.  coords (nnz,3) int32 [image, y, x] sorted by image,
+ * values (nnz, in_channels) f32 or u8, coordinates unique per image (as the dataset guarantees).     */
+int tcvn_cnn_forward_sparse(const tcvn_cnn_desc* d, tcvn_precision prec, const void* packed,
+                            const int32_t* coords, const void* values, tcvn_value_dtype value_dtype, int64_t nnz,
+                            float divisor, int n_images, float* embedding, void* workspace,
+                            size_t workspace_bytes, tcvn_stream_t stream);
 /* test hook: copies one internal feature map of the last forward (still in the workspace) to
  * out as (n_images, channels, h, w) fp32 NCHW.  stage: 0 = stem after pool, 2b+1 = dense block
  * b output, 2b+2 = transition b output (b from 0).  Returns the channel count in *channels.   */

@@ -218,3 +218,33 @@ def test_bf16_linearity_of_conv_tiles_at_full_size(dev):
     assert torch.isfinite(ev).all() and torch.isfinite(pr).all()
     assert torch.equal(ev2.flip(0), ev)
     assert torch.equal(pr2.flip(0), pr)
+
+
+# ------------------------------------------------------------------------------------------ COO-direct stem
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sparse_direct_stem_equals_densify_then_forward(dev, precision):
+    """The stem fed from the hit list must give what densify -> dense forward gives (same arithmetic, same
+    summation order for (y,x)-sorted hits: bit-identical), for f32 and u8 hit values, incl. an image whose
+    only hit is the dummy (0,0) hit of an empty prong (fully_sparse_dataset.py:148-153)."""
+    import numpy as np
+    net, state, opts = _net(2, True, dev, precision=precision)
+    for vdt in (np.float32, np.uint8):
+        batch = synth.make_batch(5, seed=8, prongs_per_event=[4, 1, 6, 2, 3], value_dtype=vdt)
+        # make prong image 2 "empty": a single zero-valued dummy hit at (0,0)
+        pc, pv = batch.prong_coords.clone(), batch.prong_values.clone()
+        keep = pc[:, 0] != 2
+        dummy_c = torch.tensor([[2, 0, 0]], dtype=torch.int32)
+        dummy_v = torch.zeros(1, 3, dtype=pv.dtype)
+        first = int((pc[:, 0] < 2).sum())
+        pc = torch.cat((pc[keep][:first], dummy_c, pc[keep][first:]))
+        pv = torch.cat((pv[keep][:first], dummy_v, pv[keep][first:]))
+        batch.prong_coords, batch.prong_values = pc, pv
+        gb = batch.to(dev)
+        with torch.no_grad():
+            ev_a, pr_a = net.forward_sparse(gb)
+            ev_b, pr_b = net.forward_sparse(gb, materialize=True)
+        assert torch.equal(ev_a, ev_b) and torch.equal(pr_a, pr_b)
+        if precision == "fp32" and vdt is np.float32:
+            with torch.no_grad():
+                want_ev, want_pr = restate.sparse_forward(state, opts, batch)
+            assert rel_err(ev_a.cpu(), want_ev) < FP32_TOL and rel_err(pr_a.cpu(), want_pr) < FP32_TOL
