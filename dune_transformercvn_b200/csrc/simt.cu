@@ -193,35 +193,67 @@ __device__ __forceinline__ void stem_scatter_pool(const float* wsm, float* acc, 
   }
   __syncthreads();
   // ---- (3)+(4) bias + BN0 + PReLU0, AvgPool2d(3, 2) -> ringed block buffer.  A conv output no hit reached is
-  // the per-channel constant PReLU(shift); a pooling window of nine such outputs is evaluated once per thread
-  // (same additions and division as the general case, so the shortcut is bit-identical).
+  // the per-channel constant PReLU(shift), so a pooling window of nine such outputs is a per-channel constant
+  // too (evaluated with the same additions and division as the general case: the shortcut is bit-identical).
+  // Pixels whose window was reached are listed and evaluated 8 at a time (64 channels x 8 pixels = 512 threads);
+  // all other pixels get the constant vector with 16-byte stores.
+  __shared__ int pool_list[kStemTP * kStemTP];
+  __shared__ unsigned char pool_kind[kStemTP * kStemTP];  // 0 constant, 1 reached (listed), 2 outside the map
+  __shared__ int pool_count;
+  __shared__ __align__(16) TO pool_const[C0];
   const float c_act = prelu(fmaf(0.f, sc, sh), al);
   float c_pool = 0.f;
 #pragma unroll
   for (int k = 0; k < 9; ++k) c_pool += c_act;
   c_pool /= 9.0f;
-  for (int i = t; i < kStemTP * kStemTP * C0; i += blockDim.x) {
-    const int p = i / C0;
-    const int pyl = p / kStemTP, pxl = p % kStemTP;
-    const int py = py0 + pyl, px = px0 + pxl;
-    if (py >= Hb || px >= Wb) continue;
-    const int base = (2 * pyl) * kStemTC + 2 * pxl;
-    int any = 0;
+  if (t < C0) pool_const[t] = from_f32<TO>(c_pool);
+  if (t < 32) {  // one warp classifies the 64 pooled pixels (2 per lane) and compacts the reached ones in order
+    int cnt = 0;
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-      for (int dx = 0; dx < 3; ++dx) any |= touched[base + dy * kStemTC + dx];
-    float r = c_pool;
-    if (any) {
-      float s2 = 0.f;
+    for (int half = 0; half < 2; ++half) {
+      const int p = half * 32 + t;
+      const int pyl = p / kStemTP, pxl = p % kStemTP;
+      const int base = (2 * pyl) * kStemTC + 2 * pxl;
+      int any = 0;
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) s2 += prelu(fmaf(acc[(base + dy * kStemTC + dx) * C0 + ch], sc, sh), al);
-      r = s2 / 9.0f;
+        for (int dx = 0; dx < 3; ++dx) any |= touched[base + dy * kStemTC + dx];
+      const bool inside = py0 + pyl < Hb && px0 + pxl < Wb;
+      const unsigned b = __ballot_sync(0xffffffffu, any && inside);
+      if (any && inside) pool_list[cnt + __popc(b & ((1u << t) - 1u))] = p;
+      pool_kind[p] = inside ? (any ? 1 : 0) : 2;
+      cnt += __popc(b);
     }
-    const size_t row = (size_t)n * (Hb + 2) * (Wb + 2) + (size_t)(py + 1) * (Wb + 2) + (px + 1);
-    blk[row * ldo + ch] = from_f32<TO>(r);
+    if (t == 0) pool_count = cnt;
+  }
+  __syncthreads();
+  // constant pixels: 64 pixels x 8 sixteen-byte chunks
+  {
+    constexpr int VEC = 16 / sizeof(TO);           // channels per 16-byte store
+    constexpr int CHUNKS = C0 / VEC;               // stores per pixel
+    for (int i = t; i < kStemTP * kStemTP * CHUNKS; i += blockDim.x) {
+      const int p = i / CHUNKS, q = i % CHUNKS;
+      const int pyl = p / kStemTP, pxl = p % kStemTP;
+      const int py = py0 + pyl, px = px0 + pxl;
+      if (pool_kind[p] != 0) continue;
+      const size_t row = (size_t)n * (Hb + 2) * (Wb + 2) + (size_t)(py + 1) * (Wb + 2) + (px + 1);
+      *reinterpret_cast<uint4*>(blk + row * ldo + q * VEC) = *reinterpret_cast<const uint4*>(pool_const + q * VEC);
+    }
+  }
+  // reached pixels: full evaluation, one pixel per group of C0 threads
+  const int npool = pool_count;
+  for (int idx = t / C0; idx < npool; idx += blockDim.x / C0) {
+    const int p = pool_list[idx];
+    const int pyl = p / kStemTP, pxl = p % kStemTP;
+    const int base = (2 * pyl) * kStemTC + 2 * pxl;
+    float s2 = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) s2 += prelu(fmaf(acc[(base + dy * kStemTC + dx) * C0 + ch], sc, sh), al);
+    const size_t row = (size_t)n * (Hb + 2) * (Wb + 2) + (size_t)(py0 + pyl + 1) * (Wb + 2) + (px0 + pxl + 1);
+    blk[row * ldo + ch] = from_f32<TO>(s2 / 9.0f);
   }
 }
 
@@ -374,8 +406,8 @@ __global__ void __launch_bounds__(kStemThreads) stem_coo_kernel(const int32_t* _
   const float sc = __ldg(s_scale + ch), sh = __ldg(s_shift + ch), al = __ldg(s_alpha + ch);
   constexpr int kCap = kStemIn * kStemIn;
   for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-    const int n = (int)(tile / per_image);
-    const int rem = (int)(tile - (long long)n * per_image);
+    const int n = (int)tile / per_image;   // launch_stem_coo keeps the tile count below 2^31
+    const int rem = (int)tile - n * per_image;
     const int py0 = (rem / tiles_x) * kStemTP, px0 = (rem % tiles_x) * kStemTP;
     const int iy0 = 4 * py0 - 3, ix0 = 4 * px0 - 3;
     const long long lo = __ldg(image_offsets + image0 + n), hi = __ldg(image_offsets + image0 + n + 1);
@@ -450,6 +482,7 @@ int launch_stem_coo(const int32_t* coords, const void* values, bool values_u8, c
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const long long tiles = (long long)n * ((Wb + kStemTP - 1) / kStemTP) * ((Hb + kStemTP - 1) / kStemTP);
+  if (tiles >= (1ll << 31)) return fail(TCVN_ERR_UNSUPPORTED, "stem: too many tiles in one chunk");
   const int grid = (int)(tiles < (long long)sms ? tiles : (long long)sms);
 #define TCVN_STEM_COO(TO, V)                                                                                          \
   do {                                                                                                                \

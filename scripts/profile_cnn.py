@@ -22,8 +22,12 @@ def main():
     px = densify(batch.prong_values, batch.prong_coords, (400, 280), n, 255.0)
     eng = net.engine
     eng.ensure_packed(tl.TCVN_BF16)
+    sparse = "--sparse" in sys.argv
     for _ in range(reps):
-        emb = eng.cnn("prong", px, tl.TCVN_BF16)
+        if sparse:
+            emb = eng.cnn_sparse("prong", batch.prong_values, batch.prong_coords, n, tl.TCVN_BF16)
+        else:
+            emb = eng.cnn("prong", px, tl.TCVN_BF16)
     torch.cuda.synchronize()
     print("ok", float(emb.float().abs().mean()))
 
