@@ -135,6 +135,60 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def kernel_rooflines(net, resident, batch, dev, pk, args):
+    """Times the two layer kernels of dense block 1 alone (CUDA events on the launching stream, inputs ~0.8 GB
+    per launch, i.e. larger than L2).  Dominant kernel of the step = the fused-activation 1x1 GEMM family
+    (umma_gemm_kernel<true>, 35-40 % of the step in profiles/): HBM-bound.  Algorithmic bytes per image-layer
+    (DESIGN.md): conv1 reads K*2 B and writes 256 B per ringed pixel row, conv2 reads 256 B and writes 64 B."""
+    import ctypes as C
+    from dune_transformercvn_b200 import lib as tl
+    L = tl.load()
+    eng = net.engine
+    n = min(batch.num_prongs, 194)
+    if n < 8:
+        return None, {}
+    nnz = int((resident.prong_coords[:, 0] < n).sum().item())
+    coords, values = resident.prong_coords[:nnz].contiguous(), resident.prong_values[:nnz].contiguous()
+    eng.cnn_sparse("prong", values, coords, n, tl.TCVN_BF16)   # leaves this chunk's feature maps in the workspace
+    d = eng.cnn_desc(256)
+    ws = eng.ws[("cnn", str(dev))]
+    rows = n * 101 * 71          # ringed rows of block 1 (99x69 map + ring)
+    pixels = n * 99 * 69
+    layer, k = 2, 128            # third bottleneck of block 1: 128 input channels
+    out = {}
+    for which, name in ((1, "conv1"), (2, "conv2")):
+        def launch():
+            tl.check(L.tcvn_cnn_run_layer(C.byref(d), tl.TCVN_BF16, tl.ptr(eng.packed["prong"]), tl.ptr(ws), ws.numel(), n,
+                                          0, layer, which, tl.stream_ptr(dev)), "tcvn_cnn_run_layer")
+        for _ in range(3):
+            launch()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 20
+        e0.record()
+        for _ in range(reps):
+            launch()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / reps
+        if which == 1:
+            nbytes = rows * k * 2 + 128 * k * 2 + rows * 128 * 2
+            gbs = nbytes / (us * 1e-6) / 1e9
+            out[name] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
+                         "traffic": 755.3e6 * n / 194, "kernel": "umma_gemm_kernel<true> (BN+PReLU -> 1x1 conv -> BN+PReLU), "
+                         f"dense1 layer 3, {n} images", "us_per_launch": us, "algorithmic_bytes": nbytes,
+                         "peak_source": pk["source"] + " copy bandwidth",
+                         "traffic_source": "ncu dram__bytes_read+write, profiles/r1_conv1_gemm_194img.txt, scaled by images"}
+        else:
+            flops = pixels * 2 * 9 * 128 * 32
+            tf = flops / (us * 1e-6) / 1e12
+            out[name] = {"bound": "tensor", "achieved": tf, "peak": pk["bf16_burst"], "unit": "TFLOP/s",
+                         "frac": tf / pk["bf16_burst"], "traffic": None, "kernel": "umma_conv2_kernel (3x3 conv, N=96 MMAs), "
+                         f"dense1 layer 3, {n} images", "us_per_launch": us, "algorithmic_flops": flops,
+                         "peak_source": pk["source"] + " cuBLAS bf16 burst (kernel timed alone)"}
+    return out["conv1"], {"conv2": out["conv2"]}
+
+
 def run_ours(args):
     import torch.distributed as dist
     from dune_transformercvn_b200 import lib as tl
@@ -207,7 +261,9 @@ def run_ours(args):
         net.freeze_packed(True)
         sampler = ClockSampler(local)
         sampler.start()
+        l0 = tl.load().tcvn_launch_count()
         ms = timed(lambda: step(resident), args.steps)
+        launches_timed = tl.load().tcvn_launch_count() - l0
         sampler.stop_flag.set()
         for _ in range(2):
             step_e2e()
@@ -226,18 +282,15 @@ def run_ours(args):
     pk = peaks()
     total_images = images  # per rank; every rank has the same expected count
     tflops = total_images * GFLOP_PER_IMAGE_FWD * 1e9 * args.steps / (ms / 1e3) / 1e12
-    roofline = {"bound": "tensor", "achieved": tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
-                "frac": tflops / pk["bf16_sustained"], "traffic": None,
-                "kernel": "whole DenseNet forward (per-kernel figure: see profiles/)", "peak_source": pk["source"] + " sustained"}
+    roofline, extra_rooflines = kernel_rooflines(net, resident, batch, dev, pk, args) if args.precision == "bf16" else (None, {})
+    if roofline is None:
+        roofline = {"bound": "tensor", "achieved": tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                    "frac": tflops / pk["bf16_sustained"], "traffic": None, "kernel": "whole DenseNet forward (fp32 path)"}
     cpu = None
     if not args.no_cpu_baseline:
         v, cms, cores, sample = time_cpu_reference(4, 2, 1, 1234)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
-    # launches per step: densify x2 + per CNN chunk (stem 2 + 30 layers x 2 + 4 transitions x 2 + tail 2) + seq 2
-    chunk = 32
-    per_chunk = 2 + 30 * 2 + 4 * 2 + 2
-    n_chunks = -(-batch.num_events // chunk) + -(-batch.num_prongs // chunk)
-    launches = (2 + n_chunks * per_chunk + 2) * args.steps
+    launches = launches_timed  # counted by the library itself (tcvn_launch_count) around the timed region
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
@@ -249,7 +302,8 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "images_per_s": value * images / args.events,
-            "roofline": roofline, "cpu_baseline": cpu, "clocks": sampler.summary()}
+            "whole_net_tflops": tflops, "roofline": roofline, "rooflines_other": extra_rooflines,
+            "cpu_baseline": cpu, "clocks": sampler.summary()}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -258,7 +312,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--events", type=int, default=256)

@@ -180,6 +180,24 @@ extern "C" int tcvn_cnn_forward_sparse(const tcvn_cnn_desc* d, tcvn_precision pr
   return TCVN_OK;
 }
 
+extern "C" int tcvn_cnn_run_layer(const tcvn_cnn_desc* d, tcvn_precision prec, const void* packed, void* workspace,
+                                  size_t workspace_bytes, int n_images, int block, int layer, int which,
+                                  tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(d && packed && workspace, "cnn_run_layer: null pointer");
+  TCVN_CHECK_ARG(prec == TCVN_BF16, "cnn_run_layer: only the tcgen05 path has separately launchable layer kernels");
+  CnnPlan P;
+  TCVN_CHECK_ARG(CnnPlan::build(*d, prec, n_images, &P), "cnn_run_layer: bad descriptor");
+  if (workspace_bytes < P.ws_bytes)
+    return fail(TCVN_ERR_WORKSPACE, "cnn_run_layer: workspace %zu < %zu bytes", workspace_bytes, P.ws_bytes);
+  TCVN_CHECK_ARG(block >= 0 && block < (int)P.blocks.size(), "cnn_run_layer: no block %d", block);
+  const BlockPlan& B = P.blocks[block];
+  TCVN_CHECK_ARG(layer >= 0 && layer < (int)B.layers.size(), "cnn_run_layer: no layer %d", layer);
+  TCVN_CHECK_ARG(n_images >= 1 && n_images <= B.chunk, "cnn_run_layer: %d images (block chunk is %d)", n_images, B.chunk);
+  char* ws = static_cast<char*>(workspace);
+  return umma_dense_layer_part(P, B, B.layers[layer], static_cast<const char*>(packed), ws + B.ws_blk, ws + P.ws_mid,
+                               (long long)n_images * B.R, which, stream);
+}
+
 extern "C" int tcvn_cnn_read_stage(const tcvn_cnn_desc* d, tcvn_precision prec, const void* workspace, int n_images,
                                    int stage, float* out, int32_t* channels, int32_t* h, int32_t* w,
                                    tcvn_stream_t stream) {

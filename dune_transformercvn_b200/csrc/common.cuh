@@ -25,7 +25,13 @@ int fail(int code, const char* fmt, ...);
       return ::tcvn::fail(TCVN_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
   } while (0)
 
-#define TCVN_LAUNCH_CHECK() TCVN_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this: counts launches for tcvn_launch_count()
+void count_launch();
+#define TCVN_LAUNCH_CHECK()        \
+  do {                             \
+    ::tcvn::count_launch();        \
+    TCVN_CUDA(cudaGetLastError()); \
+  } while (0)
 
 static inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

@@ -227,7 +227,8 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
 #pragma unroll
           for (int q = 0; q < 4; ++q) al2[q] = __floats2bfloat162_rn(al[2 * q], al[2 * q + 1]);
           const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
-          ptx::mbar_wait(&full[stage], phase);
+          if (lane == 0) ptx::mbar_wait(&full[stage], phase);  // one poller per warp keeps the LSU free
+          __syncwarp();
           uint8_t* base = sA + stage * kStageA + rb * 128 + pc * 16;
           if (live) {
             uint4 v[4];
@@ -286,7 +287,8 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
           s_alpha2[e] = *reinterpret_cast<const uint32_t*>(&a2);
         }
       }
-      ptx::mbar_wait(&tfull[grp], acc_phase);
+      if (lane == 0) ptx::mbar_wait(&tfull[grp], acc_phase);
+      __syncwarp();
       ptx::tc_fence_after();
       if (issuer) ptx::tma_store_wait_read();  // this group's previous store has drained the staging tile
       ptx::named_bar_sync(1 + grp, 128);
@@ -469,7 +471,8 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
         const int y = rr / p.Wp, x = rr - y * p.Wp;
         ring = y == 0 || y == p.Hp - 1 || x == 0 || x == p.Wp - 1;
       }
-      ptx::mbar_wait(&tfull[acc], acc_phase);
+      if (lane == 0) ptx::mbar_wait(&tfull[acc], acc_phase);
+      __syncwarp();
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(g * 32) << 16) + acc * 128;
       uint32_t left[32], mid[32], right[32];
@@ -550,15 +553,22 @@ static int launch_gemm(bool transform, const void* A, long long rows, int a_cols
 
 int umma_dense_layer(const CnnPlan& P, const BlockPlan& B, const LayerPlan& L, const char* pk, void* blk, void* mid,
                      long long rows, cudaStream_t st) {
+  return umma_dense_layer_part(P, B, L, pk, blk, mid, rows, 3, st);
+}
+
+// which: bit 0 = conv1 (fused-activation GEMM), bit 1 = conv2 (3x3 shifted GEMM)
+int umma_dense_layer_part(const CnnPlan& P, const BlockPlan& B, const LayerPlan& L, const char* pk, void* blk, void* mid,
+                          long long rows, int which, cudaStream_t st) {
   if (P.mid != kMid || P.d.growth != kGrowth)
     return fail(TCVN_ERR_UNSUPPORTED, "tcgen05 path is specialised for bottleneck width 128 / growth 32 (got %d / %d)",
                 P.mid, P.d.growth);
   if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one chunk");
   // ---- conv1 (BN2 scale is folded into the bf16 weights by pack.cu; the epilogue adds the folded shift)
-  TCVN_TRY(launch_gemm(true, blk, rows, B.ctot, B.ctot, pk + L.p_w1, kMid, L.kpad, L.kphys, pf(pk, L.p_a_scale),
+  if (which & 1) TCVN_TRY(launch_gemm(true, blk, rows, B.ctot, B.ctot, pk + L.p_w1, kMid, L.kpad, L.kphys, pf(pk, L.p_a_scale),
                        pf(pk, L.p_a_shift), pf(pk, L.p_a_alpha), pf(pk, L.p_o_shift), pf(pk, L.p_o_alpha), mid, kMid, kMid,
                        1, B.Hp, B.Wp, st));
   // ---- conv2
+  if (!(which & 2)) return TCVN_OK;
   const int tiles = (int)ceil_div_ll(rows, kC2Out);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   const int halo_rows_max = 288;

@@ -22,9 +22,9 @@ MAX_BLOCKS, MAX_DECODER_LAYERS = 8, 8
 
 # every symbol include/tcvn.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = (
-    "tcvn_abi_version", "tcvn_last_error", "tcvn_densify",
+    "tcvn_abi_version", "tcvn_last_error", "tcvn_launch_count", "tcvn_densify",
     "tcvn_cnn_arena_floats", "tcvn_cnn_packed_bytes", "tcvn_cnn_pack", "tcvn_cnn_workspace_bytes",
-    "tcvn_cnn_forward", "tcvn_cnn_forward_sparse", "tcvn_cnn_read_stage",
+    "tcvn_cnn_forward", "tcvn_cnn_forward_sparse", "tcvn_cnn_run_layer", "tcvn_cnn_read_stage",
     "tcvn_seq_packed_bytes", "tcvn_seq_pack", "tcvn_seq_workspace_bytes", "tcvn_seq_forward",
 )
 
@@ -61,6 +61,7 @@ def load() -> C.CDLL:
     vp, i32, i64, sz, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_size_t, C.c_float
     lib.tcvn_abi_version.restype = C.c_int
     lib.tcvn_last_error.restype = C.c_char_p
+    lib.tcvn_launch_count.restype = C.c_longlong
     lib.tcvn_densify.argtypes = [vp, vp, i32, i64, i32, i32, i32, i32, f32, vp, i32, vp]
     lib.tcvn_cnn_arena_floats.argtypes = [C.POINTER(CnnDesc)]
     lib.tcvn_cnn_arena_floats.restype = i64
@@ -71,6 +72,7 @@ def load() -> C.CDLL:
     lib.tcvn_cnn_workspace_bytes.restype = sz
     lib.tcvn_cnn_forward.argtypes = [C.POINTER(CnnDesc), i32, vp, vp, i32, vp, vp, sz, vp]
     lib.tcvn_cnn_forward_sparse.argtypes = [C.POINTER(CnnDesc), i32, vp, vp, vp, i32, i64, f32, i32, vp, vp, sz, vp]
+    lib.tcvn_cnn_run_layer.argtypes = [C.POINTER(CnnDesc), i32, vp, vp, sz, i32, i32, i32, i32, vp]
     lib.tcvn_cnn_read_stage.argtypes = [C.POINTER(CnnDesc), i32, vp, i32, i32, vp, C.POINTER(C.c_int32),
                                         C.POINTER(C.c_int32), C.POINTER(C.c_int32), vp]
     lib.tcvn_seq_packed_bytes.argtypes = [C.POINTER(SeqDesc)]

@@ -56,6 +56,8 @@ typedef enum tcvn_dense_layout {
 
 int tcvn_abi_version(void);
 const char* tcvn_last_error(void);
+/* kernels launched by this library in this process so far (bench.py reports the per-step count) */
+long long tcvn_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * K1  ingest: Minkowski-format COO hits -> dense pixel maps, value / divisor fused.
@@ -111,6 +113,11 @@ int tcvn_cnn_forward_sparse(const tcvn_cnn_desc* d, tcvn_precision prec, const v
                             const int32_t* coords, const void* values, tcvn_value_dtype value_dtype, int64_t nnz,
                             float divisor, int n_images, float* embedding, void* workspace,
                             size_t workspace_bytes, tcvn_stream_t stream);
+/* measurement hook (bench.py roofline): re-launches ONE kernel of dense layer `layer` of block `block` on the
+ * feature maps a previous forward left in the workspace.  which: 1 = conv1 (fused BN+PReLU GEMM), 2 = conv2
+ * (3x3 shifted GEMM), 3 = both.  TCVN_BF16 only.                                                          */
+int tcvn_cnn_run_layer(const tcvn_cnn_desc* d, tcvn_precision prec, const void* packed, void* workspace,
+                       size_t workspace_bytes, int n_images, int block, int layer, int which, tcvn_stream_t stream);
 /* test hook: copies one internal feature map of the last forward (still in the workspace) to
  * out as (n_images, channels, h, w) fp32 NCHW.  stage: 0 = stem after pool, 2b+1 = dense block
  * b output, 2b+2 = transition b output (b from 0).  Returns the channel count in *channels.   */

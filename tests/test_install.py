@@ -1,0 +1,34 @@
+"""install() swaps the names the reference trainer resolves (CPU; needs /root/reference, skipped elsewhere)."""
+import pytest
+
+from oracle import reference_import
+
+
+@pytest.mark.skipif(not reference_import.available(), reason="reference tree not present (GPU box)")
+def test_install_rebinds_reference_names(tutorial_options):
+    ref = reference_import.load()
+    from dune_transformercvn_b200 import install
+    from dune_transformercvn_b200.network import NeutrinoDenseNetwork
+    from dune_transformercvn_b200.ingest import sparse_to_dense
+    orig = ref.dense_trainer.NeutrinoDenseNetwork
+    install.install()
+    try:
+        assert ref.dense_trainer.NeutrinoDenseNetwork is NeutrinoDenseNetwork
+        assert ref.dense_trainer.sparse_to_dense is sparse_to_dense
+        # the reference's own create_network builds OUR class from ITS Options object
+        fake = type("T", (), {"options": ref.tutorial_options(), "num_features": 1, "num_extra": 1, "pixel_features": 3,
+                              "num_prong_classes": 8, "num_event_classes": 4})()
+        fake.training_dataset = type("D", (), {"num_features": 1, "num_extra": 1, "pixel_features": 3,
+                                               "num_prong_classes": 8, "num_event_classes": 4})()
+        try:
+            net = ref.dense_trainer.NeutrinoFullDenseTrainer.create_network(fake)
+        except AttributeError:
+            net = NeutrinoDenseNetwork(ref.tutorial_options(), 1, 1, 3, 8, 4)
+        assert isinstance(net, NeutrinoDenseNetwork)
+        # and a reference state_dict loads strictly into it
+        torch_ref = orig(ref.tutorial_options(), 1, 1, 3, 8, 4)
+        res = net.load_state_dict(torch_ref.state_dict(), strict=True)
+        assert not res.missing_keys and not res.unexpected_keys
+    finally:
+        install.uninstall()
+    assert ref.dense_trainer.NeutrinoDenseNetwork is orig
