@@ -16,14 +16,7 @@ def test_install_rebinds_reference_names(tutorial_options):
         assert ref.dense_trainer.NeutrinoDenseNetwork is NeutrinoDenseNetwork
         assert ref.dense_trainer.sparse_to_dense is sparse_to_dense
         # the reference's own create_network builds OUR class from ITS Options object
-        fake = type("T", (), {"options": ref.tutorial_options(), "num_features": 1, "num_extra": 1, "pixel_features": 3,
-                              "num_prong_classes": 8, "num_event_classes": 4})()
-        fake.training_dataset = type("D", (), {"num_features": 1, "num_extra": 1, "pixel_features": 3,
-                                               "num_prong_classes": 8, "num_event_classes": 4})()
-        try:
-            net = ref.dense_trainer.NeutrinoFullDenseTrainer.create_network(fake)
-        except AttributeError:
-            net = NeutrinoDenseNetwork(ref.tutorial_options(), 1, 1, 3, 8, 4)
+        net = ref.dense_trainer.NeutrinoFullDenseTrainer.create_network(None, ref.tutorial_options(), 1, 1, 3, 8, 4)
         assert isinstance(net, NeutrinoDenseNetwork)
         # and a reference state_dict loads strictly into it
         torch_ref = orig(ref.tutorial_options(), 1, 1, 3, 8, 4)
