@@ -17,6 +17,8 @@ struct GemmArgs {
   void* out; int ldo; int out_col0;
   int ring_Hp, ring_Wp;  // 0 = no ring masking
   bool a_is_f32; bool out_is_f32;  // element types of A / out (false = bf16)
+  int a_ring_Hp = 0, a_ring_Wp = 0;  // > 0: activated A rows on the zero ring read as 0
+  bool accumulate = false;           // out += result
 };
 int launch_simt_gemm(const GemmArgs& g, cudaStream_t stream);
 

@@ -23,6 +23,8 @@ struct GemmDev {
   const float* o_scale; const float* o_shift; const float* o_alpha;
   void* out; int ldo; int out_col0;
   int ring_Hp, ring_Wp;
+  int a_ring_Hp, a_ring_Wp;  // > 0: activated A rows that fall on the zero ring read as 0 (conv zero padding)
+  int accumulate;            // out += result
 };
 
 template <typename TA, typename TO, int TN>
@@ -48,7 +50,12 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const GemmDev g) {
 
   for (int t = 0; t < g.taps; ++t) {
     const long long gm = m0 + ar + g.tap_off[t];
-    const bool row_ok = gm >= 0 && gm < g.m_total;
+    bool row_ok = gm >= 0 && gm < g.m_total;
+    if (row_ok && g.a_ring_Hp > 0) {
+      const int rr = (int)(gm % (g.a_ring_Hp * g.a_ring_Wp));
+      const int y = rr / g.a_ring_Wp, x = rr - y * g.a_ring_Wp;
+      row_ok = !(y == 0 || y == g.a_ring_Hp - 1 || x == 0 || x == g.a_ring_Wp - 1);
+    }
     const TA* arow = A + (row_ok ? gm : 0) * (long long)g.lda;
     const float* Wt = g.W + (size_t)t * g.K * g.N;
     for (int k0 = 0; k0 < g.K; k0 += kBK) {
@@ -103,15 +110,17 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const GemmDev g) {
       if (n >= g.N) continue;
       float v = acc[i][j];
       if (g.o_scale != nullptr) v = prelu(fmaf(v, __ldg(g.o_scale + n), __ldg(g.o_shift + n)), __ldg(g.o_alpha + n));
-      else v += __ldg(g.o_shift + n);
+      else if (g.o_shift != nullptr) v += __ldg(g.o_shift + n);
       if (ring) v = 0.f;
-      out[m * (long long)g.ldo + g.out_col0 + n] = from_f32<TO>(v);
+      TO* dst = out + m * (long long)g.ldo + g.out_col0 + n;
+      if (g.accumulate) v += to_f32<TO>(*dst);
+      *dst = from_f32<TO>(v);
     }
   }
 }
 
 int launch_simt_gemm(const GemmArgs& a, cudaStream_t stream) {
-  TCVN_CHECK_ARG(a.N % 4 == 0 && a.taps >= 1 && a.taps <= 9 && a.o_shift != nullptr, "simt_gemm: bad arguments");
+  TCVN_CHECK_ARG(a.N % 4 == 0 && a.taps >= 1 && a.taps <= 9, "simt_gemm: bad arguments");
   if (a.m_total <= 0) return TCVN_OK;
   GemmDev g;
   g.A = a.A; g.lda = a.lda; g.m_total = a.m_total; g.K = a.K; g.taps = a.taps;
@@ -120,6 +129,7 @@ int launch_simt_gemm(const GemmArgs& a, cudaStream_t stream) {
   g.a_scale = a.a_scale; g.a_shift = a.a_shift; g.a_alpha = a.a_alpha;
   g.o_scale = a.o_scale; g.o_shift = a.o_shift; g.o_alpha = a.o_alpha;
   g.out = a.out; g.ldo = a.ldo; g.out_col0 = a.out_col0; g.ring_Hp = a.ring_Hp; g.ring_Wp = a.ring_Wp;
+  g.a_ring_Hp = a.a_ring_Hp; g.a_ring_Wp = a.a_ring_Wp; g.accumulate = a.accumulate ? 1 : 0;
   const bool narrow = a.N <= 32;
   const int BN = narrow ? 32 : 64;
   dim3 grid((unsigned)ceil_div_ll(a.m_total, kBM), (unsigned)ceil_div(a.N, BN));

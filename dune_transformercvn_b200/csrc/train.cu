@@ -1,0 +1,655 @@
+// Training primitives (fp32, CUDA cores): the building blocks of the train-mode forward and the hand-written
+// backward of the hot path.  Everything works on row matrices: a feature map is the ringed channels-last
+// matrix [N*(H+2)*(W+2), C] of the inference path (ring rows carry no data and no gradient), token / image
+// level tensors are plain [rows, C] matrices (ring_hp == 0).
+//
+// Reference semantics being reproduced (torch defaults):
+//   BatchNorm (dense_net.py:19,30,85,119,147,159; prong_feature_embedding.py:17; encoder.py:14) in train mode:
+//     normalise with the batch mean and the BIASED batch variance, update running_mean / running_var (the
+//     latter with the UNBIASED variance) with momentum 0.1;
+//   PReLU with one slope per channel; backward d(alpha) = sum(dy * min(x, 0)).
+#include "kernels.h"
+
+namespace tcvn {
+
+__device__ __forceinline__ bool is_ring(long long m, int Hp, int Wp) {
+  if (Hp <= 0) return false;
+  const int rr = (int)(m % ((long long)Hp * Wp));
+  const int y = rr / Wp, x = rr - y * Wp;
+  return y == 0 || y == Hp - 1 || x == 0 || x == Wp - 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight gradient of the (shifted) GEMM:  dW[t][k][n] += sum_m act(A[m + off_t, k]) * G[m, n]
+// ------------------------------------------------------------------------------------------------
+struct WgradDev {
+  const float* A; int lda; long long m_total; int K; int taps; int tap_off[9];
+  const float *a_scale, *a_shift, *a_alpha;
+  int a_ring_Hp, a_ring_Wp;
+  const float* G; int ldg; int g_col0; int N;
+  int g_ring_Hp, g_ring_Wp;
+  float* dW;  // [taps][K][N], accumulated with atomics
+  int rows_per_slab;
+};
+
+constexpr int kWgK = 64, kWgN = 32, kWgR = 32;
+
+__global__ void __launch_bounds__(256) wgrad_kernel(const WgradDev g) {
+  __shared__ float As[kWgR][kWgK + 1];
+  __shared__ float Gs[kWgR][kWgN + 1];
+  const int tid = threadIdx.x;
+  const int k0 = blockIdx.x * kWgK;
+  const int n0 = (blockIdx.y % ((g.N + kWgN - 1) / kWgN)) * kWgN;
+  const int tap = blockIdx.y / ((g.N + kWgN - 1) / kWgN);
+  const long long r_begin = (long long)blockIdx.z * g.rows_per_slab;
+  const long long r_end = min(g.m_total, r_begin + g.rows_per_slab);
+  const int tk = (tid >> 4) * 4, tn = (tid & 15) * 2;  // 16 k-groups x 16 n-groups
+  float acc[4][2] = {};
+  const bool transform = g.a_scale != nullptr;
+  for (long long r0 = r_begin; r0 < r_end; r0 += kWgR) {
+    // A tile: 32 rows x 64 k, 8 elements per thread (row = tid / 8, k = (tid % 8) * 8 ..)
+    {
+      const int r = tid >> 3, kq = (tid & 7) * 8;
+      const long long m = r0 + r;
+      const long long gm = m + g.tap_off[tap];
+      const bool ok = m < r_end && gm >= 0 && gm < g.m_total && !is_ring(gm, g.a_ring_Hp, g.a_ring_Wp);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int k = k0 + kq + i;
+        float v = 0.f;
+        if (ok && k < g.K) {
+          v = g.A[gm * (long long)g.lda + k];
+          if (transform) v = prelu(fmaf(v, __ldg(g.a_scale + k), __ldg(g.a_shift + k)), __ldg(g.a_alpha + k));
+        }
+        As[r][kq + i] = v;
+      }
+    }
+    {
+      const int r = tid >> 3, nq = (tid & 7) * 4;
+      const long long m = r0 + r;
+      const bool ok = m < r_end && !is_ring(m, g.g_ring_Hp, g.g_ring_Wp);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = n0 + nq + i;
+        Gs[r][nq + i] = (ok && n < g.N) ? g.G[m * (long long)g.ldg + g.g_col0 + n] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < kWgR; ++r) {
+      const float g0 = Gs[r][tn], g1 = Gs[r][tn + 1];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float a = As[r][tk + i];
+        acc[i][0] = fmaf(a, g0, acc[i][0]);
+        acc[i][1] = fmaf(a, g1, acc[i][1]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int k = k0 + tk + i, n = n0 + tn + j;
+      if (k < g.K && n < g.N) atomicAdd(g.dW + ((size_t)tap * g.K + k) * g.N + n, acc[i][j]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-column sums over the interior rows:  out[j][c] += sum_m f_j(...)
+//   MODE 0  X                       -> sum x, sum x^2                    (BatchNorm batch statistics)
+//   MODE 1  dA, X, fold             -> sum g, sum g*xhat, sum dA*min(y,0) (BN + PReLU backward reductions)
+//   MODE 2  X                       -> sum x                             (bias gradients)
+// fold = [scale | shift | alpha | mean | rstd] (5 x C), y = scale*x + shift, g = dA * (y >= 0 ? 1 : alpha)
+// ------------------------------------------------------------------------------------------------
+struct ColDev {
+  const float* X; int ldx; int xcol0;
+  const float* D; int ldd; int dcol0;
+  const float* fold; int C;
+  long long m_total; int Hp, Wp; int rows_per_slab;
+  double* out;  // [nsums][C]
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) colsum_kernel(const ColDev p) {
+  constexpr int NS = MODE == 0 ? 2 : (MODE == 1 ? 3 : 1);
+  __shared__ double red[8][32][NS];
+  const int lane_c = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane_c;
+  const long long r_begin = (long long)blockIdx.y * p.rows_per_slab;
+  const long long r_end = min(p.m_total, r_begin + p.rows_per_slab);
+  double acc[NS];
+#pragma unroll
+  for (int j = 0; j < NS; ++j) acc[j] = 0.0;
+  if (c < p.C) {
+    float sc = 0.f, sh = 0.f, al = 0.f, mean = 0.f, rstd = 0.f;
+    if (MODE == 1) {
+      sc = p.fold[c]; sh = p.fold[p.C + c]; al = p.fold[2 * p.C + c]; mean = p.fold[3 * p.C + c]; rstd = p.fold[4 * p.C + c];
+    }
+    float part[NS];
+#pragma unroll
+    for (int j = 0; j < NS; ++j) part[j] = 0.f;
+    int cnt = 0;
+    for (long long m = r_begin + rl; m < r_end; m += 8) {
+      if (!is_ring(m, p.Hp, p.Wp)) {
+        if (MODE == 0) {
+          const float x = p.X[m * (long long)p.ldx + p.xcol0 + c];
+          part[0] += x;
+          part[1] = fmaf(x, x, part[1]);
+        } else if (MODE == 1) {
+          const float x = p.X[m * (long long)p.ldx + p.xcol0 + c];
+          const float d = p.D[m * (long long)p.ldd + p.dcol0 + c];
+          const float y = fmaf(x, sc, sh);
+          const float g = y >= 0.f ? d : d * al;
+          part[0] += g;
+          part[1] = fmaf(g, (x - mean) * rstd, part[1]);
+          part[2] = fmaf(d, fminf(y, 0.f), part[2]);
+        } else {
+          part[0] += p.X[m * (long long)p.ldx + p.xcol0 + c];
+        }
+      }
+      if (++cnt == 64) {  // flush the fp32 partials into doubles every 64 rows
+#pragma unroll
+        for (int j = 0; j < NS; ++j) { acc[j] += (double)part[j]; part[j] = 0.f; }
+        cnt = 0;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NS; ++j) acc[j] += (double)part[j];
+  }
+#pragma unroll
+  for (int j = 0; j < NS; ++j) red[rl][lane_c][j] = acc[j];
+  __syncthreads();
+  if (rl == 0 && c < p.C) {
+#pragma unroll
+    for (int j = 0; j < NS; ++j) {
+      double s = 0.0;
+      for (int r = 0; r < 8; ++r) s += red[r][lane_c][j];
+      atomicAdd(p.out + (size_t)j * p.C + c, s);
+    }
+  }
+}
+
+// batch statistics -> fold [scale | shift | alpha | mean | rstd], running-stat update (momentum, unbiased var)
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, double count, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, const float* __restrict__ alpha, float eps,
+                                   float momentum, float* running_mean, float* running_var, float* __restrict__ fold) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = sums[c] / count;
+  double var = sums[C + c] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float sc = gamma[c] * rstd;
+  fold[c] = sc;
+  fold[C + c] = beta[c] - (float)mean * sc;
+  fold[2 * C + c] = alpha ? alpha[c] : 1.f;
+  fold[3 * C + c] = (float)mean;
+  fold[4 * C + c] = rstd;
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// BN + PReLU backward, elementwise half:  dX (+)= scale * (g - sum_g/M - xhat * sum_gxhat/M)
+struct BnBwdDev {
+  const float* D; int ldd; int dcol0;
+  const float* X; int ldx; int xcol0;
+  const float* fold; const double* sums; int C; double count;
+  float* dX; int lddx; int dxcol0; int accumulate;
+  long long m_total; int Hp, Wp;
+};
+
+__global__ void bnact_bwd_apply_kernel(const BnBwdDev p) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= p.m_total * p.C) return;
+  const int c = (int)(idx % p.C);
+  const long long m = idx / p.C;
+  float* dst = p.dX + m * (long long)p.lddx + p.dxcol0 + c;
+  if (is_ring(m, p.Hp, p.Wp)) {
+    if (!p.accumulate) *dst = 0.f;
+    return;
+  }
+  const float sc = p.fold[c], sh = p.fold[p.C + c], al = p.fold[2 * p.C + c], mean = p.fold[3 * p.C + c],
+              rstd = p.fold[4 * p.C + c];
+  const float x = p.X[m * (long long)p.ldx + p.xcol0 + c];
+  const float d = p.D[m * (long long)p.ldd + p.dcol0 + c];
+  const float y = fmaf(x, sc, sh);
+  const float g = y >= 0.f ? d : d * al;
+  const float mg = (float)(p.sums[c] / p.count), mgx = (float)(p.sums[p.C + c] / p.count);
+  const float v = sc * (g - mg - (x - mean) * rstd * mgx);
+  *dst = p.accumulate ? *dst + v : v;
+}
+
+// parameter gradients of a BN + PReLU pair from the reductions: dgamma = sum g*xhat, dbeta = sum g, dalpha
+__global__ void bnact_param_grads_kernel(const double* __restrict__ sums, int C, float* dgamma, float* dbeta, float* dalpha) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (dgamma) dgamma[c] += (float)sums[C + c];
+  if (dbeta) dbeta[c] += (float)sums[c];
+  if (dalpha) dalpha[c] += (float)sums[2 * C + c];
+}
+
+__global__ void add_cols_kernel(const double* __restrict__ sums, int C, float* dst) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < C) dst[c] += (float)sums[c];
+}
+
+// out[m, c] = PReLU(BN(x[m, c])) (ring rows -> 0): materialised activation for the few places that need it
+__global__ void bnact_fwd_kernel(const float* __restrict__ X, int ldx, int xcol0, const float* __restrict__ fold, int C,
+                                 long long m_total, int Hp, int Wp, float* __restrict__ out, int ldo, int ocol0) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= m_total * C) return;
+  const int c = (int)(idx % C);
+  const long long m = idx / C;
+  float v = 0.f;
+  if (!is_ring(m, Hp, Wp)) v = prelu(fmaf(X[m * (long long)ldx + xcol0 + c], fold[c], fold[C + c]), fold[2 * C + c]);
+  out[m * (long long)ldo + ocol0 + c] = v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pooling forward / backward on ringed maps
+// ------------------------------------------------------------------------------------------------
+// AvgPool2d(3,2) of the un-ringed stem map act(z0) [n,Hs,Ws,C] -> ringed [n,H+2,W+2,ld] channels [0,C)
+__global__ void stem_pool_fwd_kernel(const float* __restrict__ z, const float* __restrict__ fold, int Hs, int Ws, int C,
+                                     float* __restrict__ blk, int ld, int H, int W, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  long long r = idx / C;
+  const int x = (int)(r % W); r /= W;
+  const int y = (int)(r % H);
+  const int n = (int)(r / H);
+  const float sc = fold[c], sh = fold[C + c], al = fold[2 * C + c];
+  float s = 0.f;
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx)
+      s += prelu(fmaf(z[(((size_t)n * Hs + 2 * y + dy) * Ws + 2 * x + dx) * C + c], sc, sh), al);
+  blk[((size_t)n * (H + 2) * (W + 2) + (size_t)(y + 1) * (W + 2) + x + 1) * ld + c] = s / 9.0f;
+}
+
+// gradient of the above w.r.t. the activated stem map: dA[n,oy,ox,c] = (1/9) sum of dP over the windows holding (oy,ox)
+__global__ void stem_pool_bwd_kernel(const float* __restrict__ dblk, int ld, int H, int W, int C, float* __restrict__ dA,
+                                     int Hs, int Ws, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  long long r = idx / C;
+  const int ox = (int)(r % Ws); r /= Ws;
+  const int oy = (int)(r % Hs);
+  const int n = (int)(r / Hs);
+  float s = 0.f;
+  for (int py = max(0, (oy - 1) / 2); py <= min(H - 1, oy / 2); ++py) {
+    if (2 * py > oy || oy > 2 * py + 2) continue;
+    for (int px = max(0, (ox - 1) / 2); px <= min(W - 1, ox / 2); ++px) {
+      if (2 * px > ox || ox > 2 * px + 2) continue;
+      s += dblk[((size_t)n * (H + 2) * (W + 2) + (size_t)(py + 1) * (W + 2) + px + 1) * ld + c];
+    }
+  }
+  dA[idx] = s / 9.0f;
+}
+
+// AvgPool2d(2,2) backward: dA[ringed H x W rows, C] = 0.25 * dP[ringed H2 x W2 parent] (0 where the floor cropped)
+__global__ void pool2_bwd_kernel(const float* __restrict__ dP, int H2, int W2, int C, float* __restrict__ dA, int H, int W,
+                                 long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  long long r = idx / C;
+  const int Wp = W + 2, Hp = H + 2;
+  const int xx = (int)(r % Wp); r /= Wp;
+  const int yy = (int)(r % Hp);
+  const int n = (int)(r / Hp);
+  float v = 0.f;
+  const int y = yy - 1, x = xx - 1;
+  if (y >= 0 && y < 2 * H2 && x >= 0 && x < 2 * W2)
+    v = 0.25f * dP[((size_t)n * (H2 + 2) * (W2 + 2) + (size_t)(y / 2 + 1) * (W2 + 2) + x / 2 + 1) * C + c];
+  dA[idx] = v;
+}
+
+// global average pool backward: dA[ringed rows, C] = dGap[n, c] / (H*W) on interior rows
+__global__ void gap_bwd_kernel(const float* __restrict__ dGap, int C, float* __restrict__ dA, int H, int W, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int c = (int)(idx % C);
+  const long long m = idx / C;
+  const int R = (H + 2) * (W + 2);
+  const int n = (int)(m / R);
+  dA[idx] = is_ring(m, H + 2, W + 2) ? 0.f : dGap[(size_t)n * C + c] / (float)(H * W);
+}
+
+// ------------------------------------------------------------------------------------------------
+// dropout: x *= mask / (1 - p), mask from a counter-based generator keyed by (seed, stream, element)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t mix32(uint64_t z) {  // splitmix64 finaliser
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return (uint32_t)((z ^ (z >> 31)) >> 32);
+}
+
+__global__ void dropout_kernel(float* X, int ld, int col0, int C, long long m_total, unsigned long long seed,
+                               unsigned long long stream_id, float p) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= m_total * C) return;
+  const int c = (int)(idx % C);
+  const long long m = idx / C;
+  const uint32_t r = mix32(seed * 0x100000001b3ull + stream_id * 0x9e3779b97f4a7c15ull + (unsigned long long)idx);
+  const bool keep = (r >> 8) * (1.0f / 16777216.0f) >= p;
+  float* v = X + m * (long long)ld + col0 + c;
+  *v = keep ? *v / (1.f - p) : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// stem convolution for training: raw conv0 output (no bias fold) and its weight gradient, both hit-driven
+// ------------------------------------------------------------------------------------------------
+// z[n,oy,ox,c] = b[c] + sum over hits: one thread per (hit, output position) pair walks the 64 channels
+__global__ void stem_fill_bias_kernel(float* z, const float* __restrict__ bias, int C, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < total) z[idx] = bias[idx % C];
+}
+
+// pixels NCHW fp32; for every non-zero input value scatter v*w into the <=16 outputs it reaches (atomic: training path)
+__global__ void stem_conv_scatter_kernel(const float* __restrict__ pixels, int cin, int H, int W, int Hs, int Ws,
+                                         const float* __restrict__ w /*[cin*49][C]*/, int C, float* __restrict__ z,
+                                         const float* __restrict__ dz, float* __restrict__ dw, long long total) {
+  // total = n * cin * H * W input values; one warp per 32 consecutive values, lanes then share the channel loop
+  const long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll;
+  const int lane = threadIdx.x & 31;
+  const long long idx = base + lane;
+  float v = 0.f;
+  if (idx < total) v = __ldg(pixels + idx);
+  unsigned nz = __ballot_sync(0xffffffffu, v != 0.f);
+  while (nz) {
+    const int src = __ffs(nz) - 1;
+    nz &= nz - 1;
+    const float val = __shfl_sync(0xffffffffu, v, src);
+    const long long e = base + src;
+    const int x = (int)(e % W);
+    long long r = e / W;
+    const int y = (int)(r % H); r /= H;
+    const int c = (int)(r % cin);
+    const int n = (int)(r / cin);
+    // outputs (oy, ox) with 2*oy - 3 + ky == y, ky in [0,7)
+    for (int ky = (y + 3) & 1; ky < 7; ky += 2) {
+      const int oy = (y + 3 - ky) >> 1;
+      if (oy < 0 || oy >= Hs) continue;
+      for (int kx = (x + 3) & 1; kx < 7; kx += 2) {
+        const int ox = (x + 3 - kx) >> 1;
+        if (ox < 0 || ox >= Ws) continue;
+        const size_t o = (((size_t)n * Hs + oy) * Ws + ox) * C;
+        const size_t wi = ((size_t)(c * 7 + ky) * 7 + kx) * C;
+        for (int ch = lane; ch < C; ch += 32) {
+          if (dz == nullptr) atomicAdd(z + o + ch, val * __ldg(w + wi + ch));
+          else atomicAdd(dw + wi + ch, val * __ldg(dz + o + ch));
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host wrappers
+// ------------------------------------------------------------------------------------------------
+static int slabs_for(long long rows, int* rows_per_slab) {
+  int slabs = (int)ceil_div_ll(rows, 2048);
+  if (slabs > 296) slabs = 296;
+  if (slabs < 1) slabs = 1;
+  *rows_per_slab = (int)ceil_div_ll(rows, slabs);
+  return (int)ceil_div_ll(rows, *rows_per_slab);
+}
+
+}  // namespace tcvn
+
+using namespace tcvn;
+
+extern "C" int tcvn_t_gemm(const float* A, int lda, int64_t m_total, int K, int taps, const int32_t* tap_off,
+                           const float* W, int N, const float* a_fold, int a_ring_hp, int a_ring_wp, const float* bias,
+                           float* out, int ldo, int out_col0, int out_ring_hp, int out_ring_wp, int accumulate,
+                           tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(A && W && out && taps >= 1 && taps <= 9 && (taps == 1 || tap_off), "t_gemm: bad arguments");
+  GemmArgs g{};
+  g.A = A; g.lda = lda; g.m_total = m_total; g.K = K; g.taps = taps;
+  for (int t = 0; t < taps; ++t) g.tap_off[t] = tap_off ? tap_off[t] : 0;
+  g.W = W; g.N = N;
+  if (a_fold) { g.a_scale = a_fold; g.a_shift = a_fold + K; g.a_alpha = a_fold + 2 * K; }
+  g.o_shift = bias;
+  g.out = out; g.ldo = ldo; g.out_col0 = out_col0; g.ring_Hp = out_ring_hp; g.ring_Wp = out_ring_wp;
+  g.a_is_f32 = true; g.out_is_f32 = true; g.a_ring_Hp = a_ring_hp; g.a_ring_Wp = a_ring_wp; g.accumulate = accumulate != 0;
+  return launch_simt_gemm(g, stream);
+}
+
+extern "C" int tcvn_t_wgrad(const float* A, int lda, int64_t m_total, int K, int taps, const int32_t* tap_off,
+                            const float* a_fold, int a_ring_hp, int a_ring_wp, const float* G, int ldg, int g_col0, int N,
+                            int g_ring_hp, int g_ring_wp, float* dW, tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(A && G && dW && taps >= 1 && taps <= 9 && (taps == 1 || tap_off), "t_wgrad: bad arguments");
+  if (m_total <= 0) return TCVN_OK;
+  WgradDev g{};
+  g.A = A; g.lda = lda; g.m_total = m_total; g.K = K; g.taps = taps;
+  for (int t = 0; t < taps; ++t) g.tap_off[t] = tap_off ? tap_off[t] : 0;
+  if (a_fold) { g.a_scale = a_fold; g.a_shift = a_fold + K; g.a_alpha = a_fold + 2 * K; }
+  g.a_ring_Hp = a_ring_hp; g.a_ring_Wp = a_ring_wp;
+  g.G = G; g.ldg = ldg; g.g_col0 = g_col0; g.N = N; g.g_ring_Hp = g_ring_hp; g.g_ring_Wp = g_ring_wp;
+  g.dW = dW;
+  const int slabs = slabs_for(m_total, &g.rows_per_slab);
+  dim3 grid(ceil_div(K, kWgK), ceil_div(N, kWgN) * taps, slabs);
+  wgrad_kernel<<<grid, 256, 0, stream>>>(g);
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+// mode 0: sums[2][C] = (sum x, sum x^2); mode 1: sums[3][C] BN+PReLU backward reductions; mode 2: sums[1][C] = sum x.
+// sums is zeroed first.
+extern "C" int tcvn_t_colsums(int mode, const float* X, int ldx, int xcol0, const float* D, int ldd, int dcol0,
+                              const float* fold, int C, int64_t m_total, int ring_hp, int ring_wp, double* sums,
+                              tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(X && sums && mode >= 0 && mode <= 2 && (mode != 1 || (D && fold)), "t_colsums: bad arguments");
+  const int ns = mode == 0 ? 2 : (mode == 1 ? 3 : 1);
+  TCVN_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * ns * C, stream));
+  if (m_total <= 0) return TCVN_OK;
+  ColDev p{};
+  p.X = X; p.ldx = ldx; p.xcol0 = xcol0; p.D = D; p.ldd = ldd; p.dcol0 = dcol0; p.fold = fold; p.C = C;
+  p.m_total = m_total; p.Hp = ring_hp; p.Wp = ring_wp; p.out = sums;
+  const int slabs = slabs_for(m_total, &p.rows_per_slab);
+  dim3 grid(ceil_div(C, 32), slabs);
+  if (mode == 0) colsum_kernel<0><<<grid, 256, 0, stream>>>(p);
+  else if (mode == 1) colsum_kernel<1><<<grid, 256, 0, stream>>>(p);
+  else colsum_kernel<2><<<grid, 256, 0, stream>>>(p);
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+extern "C" int tcvn_t_bn_finalize(const double* sums, int C, double count, const float* gamma, const float* beta,
+                                  const float* alpha, float eps, float momentum, float* running_mean, float* running_var,
+                                  float* fold, tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(sums && gamma && beta && fold && count > 0, "t_bn_finalize: bad arguments");
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(sums, C, count, gamma, beta, alpha, eps, momentum, running_mean,
+                                                           running_var, fold);
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+extern "C" int tcvn_t_bnact_bwd_apply(const float* D, int ldd, int dcol0, const float* X, int ldx, int xcol0,
+                                      const float* fold, const double* sums, int C, double count, float* dX, int lddx,
+                                      int dxcol0, int accumulate, int64_t m_total, int ring_hp, int ring_wp, float* dgamma,
+                                      float* dbeta, float* dalpha, tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(D && X && fold && sums && count > 0, "t_bnact_bwd_apply: bad arguments");
+  if (dX && m_total > 0) {
+    BnBwdDev p{};
+    p.D = D; p.ldd = ldd; p.dcol0 = dcol0; p.X = X; p.ldx = ldx; p.xcol0 = xcol0; p.fold = fold; p.sums = sums; p.C = C;
+    p.count = count; p.dX = dX; p.lddx = lddx; p.dxcol0 = dxcol0; p.accumulate = accumulate; p.m_total = m_total;
+    p.Hp = ring_hp; p.Wp = ring_wp;
+    bnact_bwd_apply_kernel<<<(unsigned)ceil_div_ll(m_total * C, 256), 256, 0, stream>>>(p);
+    TCVN_LAUNCH_CHECK();
+  }
+  if (dgamma || dbeta || dalpha) {
+    bnact_param_grads_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(sums, C, dgamma, dbeta, dalpha);
+    TCVN_LAUNCH_CHECK();
+  }
+  return TCVN_OK;
+}
+
+extern "C" int tcvn_t_add_colsums(const double* sums, int C, float* dst, tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(sums && dst, "t_add_colsums: null pointer");
+  add_cols_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(sums, C, dst);
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+extern "C" int tcvn_t_bnact_fwd(const float* X, int ldx, int xcol0, const float* fold, int C, int64_t m_total, int ring_hp,
+                                int ring_wp, float* out, int ldo, int ocol0, tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(X && fold && out, "t_bnact_fwd: null pointer");
+  if (m_total <= 0) return TCVN_OK;
+  bnact_fwd_kernel<<<(unsigned)ceil_div_ll(m_total * C, 256), 256, 0, stream>>>(X, ldx, xcol0, fold, C, m_total, ring_hp,
+                                                                                ring_wp, out, ldo, ocol0);
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+// kind 0: stem pool fwd (src = z0 [n,Hs,Ws,C], fold; dst = ringed blk, ld);  kind 1: stem pool bwd (src = d blk, ld; dst = dA
+// [n,Hs,Ws,C]);  kind 2: pool2 bwd (src = dP ringed [n,H2+2,W2+2,C]; dst = dA ringed [n,H+2,W+2,C]);
+// kind 3: gap bwd (src = dGap [n,C]; dst = dA ringed [n,H+2,W+2,C])
+extern "C" int tcvn_t_pool(int kind, const float* src, const float* fold, float* dst, int n, int C, int H, int W, int H2,
+                           int W2, int ld, tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(src && dst && kind >= 0 && kind <= 3, "t_pool: bad arguments");
+  if (n <= 0) return TCVN_OK;
+  long long total;
+  switch (kind) {
+    case 0:  // H,W = pooled size; H2,W2 = stem conv size
+      total = (long long)n * H * W * C;
+      stem_pool_fwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(src, fold, H2, W2, C, dst, ld, H, W, total);
+      break;
+    case 1:
+      total = (long long)n * H2 * W2 * C;
+      stem_pool_bwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(src, ld, H, W, C, dst, H2, W2, total);
+      break;
+    case 2:
+      total = (long long)n * (H + 2) * (W + 2) * C;
+      pool2_bwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(src, H2, W2, C, dst, H, W, total);
+      break;
+    default:
+      total = (long long)n * (H + 2) * (W + 2) * C;
+      gap_bwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(src, C, dst, H, W, total);
+      break;
+  }
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+extern "C" int tcvn_t_dropout(float* X, int ld, int col0, int C, int64_t m_total, uint64_t seed, uint64_t stream_id, float p,
+                              tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(X && p >= 0.f && p < 1.f, "t_dropout: bad arguments");
+  if (p == 0.f || m_total <= 0) return TCVN_OK;
+  dropout_kernel<<<(unsigned)ceil_div_ll(m_total * C, 256), 256, 0, stream>>>(X, ld, col0, C, m_total, seed, stream_id, p);
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+// forward (dz == NULL): z[n,Hs,Ws,C] = bias + conv7x7s2p3(pixels);  backward (dz != NULL): dw[cin*49][C] += x (*) dz
+extern "C" int tcvn_t_stem_conv(const float* pixels, int n, int cin, int H, int W, const float* w, const float* bias, int C,
+                                float* z, const float* dz, float* dw, tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(pixels && w && ((dz == nullptr && z && bias) || (dz && dw)), "t_stem_conv: bad arguments");
+  if (n <= 0) return TCVN_OK;
+  const int Hs = (H + 6 - 7) / 2 + 1, Ws = (W + 6 - 7) / 2 + 1;
+  if (dz == nullptr) {
+    const long long outs = (long long)n * Hs * Ws * C;
+    stem_fill_bias_kernel<<<(unsigned)ceil_div_ll(outs, 256), 256, 0, stream>>>(z, bias, C, outs);
+    TCVN_LAUNCH_CHECK();
+  }
+  const long long total = (long long)n * cin * H * W;
+  stem_conv_scatter_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(pixels, cin, H, W, Hs, Ws, w, C, z, dz, dw,
+                                                                                   total);
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused AdamW over a flat fp32 buffer (torch.optim.AdamW semantics, trainers/neutrino_base.py:109-130), with the
+// global-norm clip factor of Lightning's gradient_clip_val (train.py:140) read from device memory: no host sync.
+// ------------------------------------------------------------------------------------------------
+namespace tcvn {
+
+__global__ void sumsq_kernel(const float* __restrict__ x, long long n, double* __restrict__ out) {
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const double v = x[i];
+    acc += v * v;
+  }
+  __shared__ double red[256];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) atomicAdd(out, red[0]);
+}
+
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                             long long n, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1,
+                             float bc2_sqrt, const double* __restrict__ gnorm_sq, float max_norm, float grad_mul) {
+  float clip = grad_mul;
+  if (gnorm_sq != nullptr && max_norm > 0.f) {
+    const float norm = (float)sqrt(*gnorm_sq) * grad_mul;
+    const float coef = max_norm / (norm + 1e-6f);
+    if (coef < 1.f) clip *= coef;
+  }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float grad = g[i] * clip;
+    float w = p[i] * (1.f - lr * weight_decay);
+    const float mi = beta1 * m[i] + (1.f - beta1) * grad;
+    const float vi = beta2 * v[i] + (1.f - beta2) * grad * grad;
+    m[i] = mi;
+    v[i] = vi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    w -= (lr / bc1) * (mi / denom);
+    p[i] = w;
+  }
+}
+
+}  // namespace tcvn
+
+extern "C" int tcvn_sumsq(const float* x, int64_t n, double* out, int zero_first, tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(x && out && n >= 0, "sumsq: bad arguments");
+  if (zero_first) TCVN_CUDA(cudaMemsetAsync(out, 0, sizeof(double), stream));
+  if (n == 0) return TCVN_OK;
+  int blocks = (int)tcvn::ceil_div_ll(n, 256 * 8);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  tcvn::sumsq_kernel<<<blocks, 256, 0, stream>>>(x, n, out);
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+extern "C" int tcvn_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                               float beta1, float beta2, float eps, float weight_decay, int64_t step, const double* gnorm_sq,
+                               float max_norm, float grad_mul, tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "adamw_step: bad arguments");
+  if (n == 0) return TCVN_OK;
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  int blocks = (int)tcvn::ceil_div_ll(n, 256 * 4);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  tcvn::adamw_kernel<<<blocks, 256, 0, stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+                                                  bc1, bc2_sqrt, gnorm_sq, max_norm, grad_mul);
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+// fused BN + PReLU + AvgPool2d(2,2) (transition front half) and BN + PReLU + global average (tail), fp32, with a
+// batch-statistics fold: the same kernels the inference path uses
+extern "C" int tcvn_t_act_pool2(const float* blk, int n, int H, int W, int ld, int C, const float* fold, float* out, int H2,
+                                int W2, tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(blk && fold && out, "t_act_pool2: null pointer");
+  return tcvn::launch_act_pool2(blk, n, H, W, ld, C, fold, fold + C, fold + 2 * C, out, H2, W2, true, stream);
+}
+
+extern "C" int tcvn_t_act_gap(const float* blk, int n, int H, int W, int ld, int C, const float* fold, float* gap,
+                              tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(blk && fold && gap, "t_act_gap: null pointer");
+  return tcvn::launch_act_gap(blk, n, H, W, ld, C, fold, fold + C, fold + 2 * C, gap, true, stream);
+}

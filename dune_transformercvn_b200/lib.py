@@ -26,6 +26,9 @@ EXPORTS = (
     "tcvn_cnn_arena_floats", "tcvn_cnn_packed_bytes", "tcvn_cnn_pack", "tcvn_cnn_workspace_bytes",
     "tcvn_cnn_forward", "tcvn_cnn_forward_sparse", "tcvn_cnn_run_layer", "tcvn_cnn_read_stage",
     "tcvn_seq_packed_bytes", "tcvn_seq_pack", "tcvn_seq_workspace_bytes", "tcvn_seq_forward",
+    "tcvn_t_gemm", "tcvn_t_wgrad", "tcvn_t_colsums", "tcvn_t_bn_finalize", "tcvn_t_bnact_bwd_apply", "tcvn_t_add_colsums",
+    "tcvn_t_bnact_fwd", "tcvn_t_pool", "tcvn_t_dropout", "tcvn_t_stem_conv", "tcvn_t_layernorm", "tcvn_t_attention",
+    "tcvn_t_eltwise", "tcvn_t_tokens", "tcvn_t_act_pool2", "tcvn_t_act_gap", "tcvn_sumsq", "tcvn_adamw_step",
 )
 
 
@@ -81,6 +84,26 @@ def load() -> C.CDLL:
     lib.tcvn_seq_workspace_bytes.argtypes = [C.POINTER(SeqDesc), i32, i32]
     lib.tcvn_seq_workspace_bytes.restype = sz
     lib.tcvn_seq_forward.argtypes = [C.POINTER(SeqDesc), vp, i32, vp, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, sz, vp]
+    u64, f64 = C.c_uint64, C.c_double
+    lib.tcvn_t_gemm.argtypes = [vp, i32, i64, i32, i32, vp, vp, i32, vp, i32, i32, vp, vp, i32, i32, i32, i32, i32, vp]
+    lib.tcvn_t_wgrad.argtypes = [vp, i32, i64, i32, i32, vp, vp, i32, i32, vp, i32, i32, i32, i32, i32, vp, vp]
+    lib.tcvn_t_colsums.argtypes = [i32, vp, i32, i32, vp, i32, i32, vp, i32, i64, i32, i32, vp, vp]
+    lib.tcvn_t_bn_finalize.argtypes = [vp, i32, f64, vp, vp, vp, f32, f32, vp, vp, vp, vp]
+    lib.tcvn_t_bnact_bwd_apply.argtypes = [vp, i32, i32, vp, i32, i32, vp, vp, i32, f64, vp, i32, i32, i32, i64, i32, i32,
+                                           vp, vp, vp, vp]
+    lib.tcvn_t_add_colsums.argtypes = [vp, i32, vp, vp]
+    lib.tcvn_t_bnact_fwd.argtypes = [vp, i32, i32, vp, i32, i64, i32, i32, vp, i32, i32, vp]
+    lib.tcvn_t_pool.argtypes = [i32, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp]
+    lib.tcvn_t_dropout.argtypes = [vp, i32, i32, i32, i64, u64, u64, f32, vp]
+    lib.tcvn_t_stem_conv.argtypes = [vp, i32, i32, i32, i32, vp, vp, i32, vp, vp, vp, vp]
+    lib.tcvn_t_layernorm.argtypes = [i32, vp, vp, i32, i32, vp, vp, f32, vp, vp, vp, vp, vp, vp]
+    lib.tcvn_t_attention.argtypes = [i32, vp, vp, i32, i32, i32, i32, vp, vp, vp, f32, u64, u64, vp]
+    lib.tcvn_t_eltwise.argtypes = [i32, vp, vp, vp, i32, i64, vp, vp]
+    lib.tcvn_t_tokens.argtypes = [i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]
+    lib.tcvn_t_act_pool2.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp]
+    lib.tcvn_t_act_gap.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp]
+    lib.tcvn_sumsq.argtypes = [vp, i64, vp, i32, vp]
+    lib.tcvn_adamw_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, vp, f32, f32, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("tcvn_abi_version",):

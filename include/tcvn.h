@@ -170,6 +170,70 @@ int tcvn_seq_forward(const tcvn_seq_desc* d, const void* packed, int stages, con
                      int n_events, int max_prongs, float* tokens, float* hidden, float* event_logits,
                      float* prong_logits, void* workspace, size_t workspace_bytes, tcvn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training primitives (fp32): the kernels behind the train-mode forward and the hand-written backward.
+ * Row-matrix convention: a feature map is the ringed channels-last matrix (ring_hp = H+2, ring_wp = W+2; ring
+ * rows carry neither data nor gradient), token / image level tensors are plain [rows, C] (ring_hp = 0).
+ * fold = [scale | shift | alpha | mean | rstd] (5 x C) of one BatchNorm+PReLU pair for the current batch.
+ * Replaces autograd of: nn.Conv2d / nn.Linear (dense_net.py:21-38,87-92,158), nn.BatchNorm2d/1d in train mode,
+ * nn.PReLU, nn.AvgPool2d, nn.Dropout, nn.TransformerEncoderLayer (prong_custom_bert_encoder.py:45-54).       */
+/* out[m, col0+n] (+)= bias[n] + sum_t sum_k act(A[m+tap_off[t], k]) * W[t][k][n];  act = PReLU(BN) from a_fold or identity */
+int tcvn_t_gemm(const float* A, int lda, int64_t m_total, int K, int taps, const int32_t* tap_off, const float* W, int N,
+                const float* a_fold, int a_ring_hp, int a_ring_wp, const float* bias, float* out, int ldo, int out_col0,
+                int out_ring_hp, int out_ring_wp, int accumulate, tcvn_stream_t stream);
+/* dW[t][k][n] += sum_m act(A[m+tap_off[t], k]) * G[m, g_col0+n]   (atomic accumulation; caller zeroes dW) */
+int tcvn_t_wgrad(const float* A, int lda, int64_t m_total, int K, int taps, const int32_t* tap_off, const float* a_fold,
+                 int a_ring_hp, int a_ring_wp, const float* G, int ldg, int g_col0, int N, int g_ring_hp, int g_ring_wp,
+                 float* dW, tcvn_stream_t stream);
+/* column sums over interior rows into doubles: mode 0 (sum x, sum x^2), mode 1 BN+PReLU backward reductions
+ * (sum g, sum g*xhat, sum dA*min(y,0)), mode 2 (sum x) */
+int tcvn_t_colsums(int mode, const float* X, int ldx, int xcol0, const float* D, int ldd, int dcol0, const float* fold, int C,
+                   int64_t m_total, int ring_hp, int ring_wp, double* sums, tcvn_stream_t stream);
+/* batch statistics -> fold; updates running_mean / running_var in place (momentum, unbiased variance) when given */
+int tcvn_t_bn_finalize(const double* sums, int C, double count, const float* gamma, const float* beta, const float* alpha,
+                       float eps, float momentum, float* running_mean, float* running_var, float* fold, tcvn_stream_t stream);
+/* dX (+)= BN+PReLU backward of D at X; dgamma/dbeta/dalpha += the reductions (each nullable) */
+int tcvn_t_bnact_bwd_apply(const float* D, int ldd, int dcol0, const float* X, int ldx, int xcol0, const float* fold,
+                           const double* sums, int C, double count, float* dX, int lddx, int dxcol0, int accumulate,
+                           int64_t m_total, int ring_hp, int ring_wp, float* dgamma, float* dbeta, float* dalpha,
+                           tcvn_stream_t stream);
+int tcvn_t_add_colsums(const double* sums, int C, float* dst, tcvn_stream_t stream);
+int tcvn_t_bnact_fwd(const float* X, int ldx, int xcol0, const float* fold, int C, int64_t m_total, int ring_hp, int ring_wp,
+                     float* out, int ldo, int ocol0, tcvn_stream_t stream);
+/* kind 0 stem BN+PReLU+AvgPool(3,2) fwd, 1 its backward to the activated stem map, 2 AvgPool(2,2) backward, 3 global
+ * average pool backward (see csrc/train.cu) */
+int tcvn_t_pool(int kind, const float* src, const float* fold, float* dst, int n, int C, int H, int W, int H2, int W2, int ld,
+                tcvn_stream_t stream);
+int tcvn_t_dropout(float* X, int ld, int col0, int C, int64_t m_total, uint64_t seed, uint64_t stream_id, float p,
+                   tcvn_stream_t stream);
+/* raw conv0 (7x7 s2 p3) from NCHW pixels, hit-driven: forward (dz NULL) z = bias + conv; backward dw += x (*) dz */
+int tcvn_t_stem_conv(const float* pixels, int n, int cin, int H, int W, const float* w, const float* bias, int C, float* z,
+                     const float* dz, float* dw, tcvn_stream_t stream);
+/* dir 0: out = LayerNorm(a + b), saves pre-norm sum and (mean, rstd); dir 1: a = dOut -> out = d(pre), dgamma/dbeta += */
+int tcvn_t_layernorm(int dir, const float* a, const float* b, int D, int R, const float* gamma, const float* beta, float eps,
+                     float* pre, float* stats, float* out, float* dgamma, float* dbeta, tcvn_stream_t stream);
+/* dir 0: P = softmax(mask(QK^T/sqrt(dh))), ctx = dropout(P) V; dir 1: dqkv from dctx */
+int tcvn_t_attention(int dir, const float* qkv, const uint8_t* mask, int B, int S, int heads, int D, float* P,
+                     float* ctx_or_dctx, float* dqkv, float p_drop, uint64_t seed, uint64_t stream_id, tcvn_stream_t stream);
+/* kind 0 gelu, 1 gelu backward (a = pre-activation, b = dOut), 2 a + b, 3 rows of a times mask */
+int tcvn_t_eltwise(int kind, const float* a, const float* b, const uint8_t* mask, int C, int64_t total, float* out,
+                   tcvn_stream_t stream);
+/* token plumbing: op 0 offsets from mask, 1 token-input gather (dir 1: gradient back), 2 rows <-> padded sequence,
+ * 3 prong-head rows */
+int tcvn_t_tokens(int op, int dir, float* a, float* b, const float* pos, const uint8_t* prong_mask, int* offsets, int B, int T,
+                  int L, int D, int pixel_dim, int feature_dim, int position_dim, float* x, tcvn_stream_t stream);
+/* BN+PReLU+AvgPool(2,2) and BN+PReLU+global-average with a batch-statistics fold (fp32) */
+int tcvn_t_act_pool2(const float* blk, int n, int H, int W, int ld, int C, const float* fold, float* out, int H2, int W2,
+                     tcvn_stream_t stream);
+int tcvn_t_act_gap(const float* blk, int n, int H, int W, int ld, int C, const float* fold, float* gap, tcvn_stream_t stream);
+/* sum of squares into a device double (global gradient norm, no host sync) */
+int tcvn_sumsq(const float* x, int64_t n, double* out, int zero_first, tcvn_stream_t stream);
+/* fused AdamW over a flat buffer; replaces torch.optim.AdamW.step (trainers/neutrino_base.py:109-130) and Lightning's
+ * clip_grad_norm_ (train.py:140): grads are multiplied by grad_mul * min(1, max_norm / (sqrt(*gnorm_sq)*grad_mul + 1e-6)) */
+int tcvn_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                    float beta2, float eps, float weight_decay, int64_t step, const double* gnorm_sq, float max_norm,
+                    float grad_mul, tcvn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
