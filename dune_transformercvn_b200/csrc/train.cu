@@ -108,7 +108,8 @@ struct ColDev {
   const float* D; int ldd; int dcol0;
   const float* fold; int C;
   long long m_total; int Hp, Wp; int rows_per_slab;
-  double* out;  // [nsums][C]
+  double* out;  // [nsums][out_stride]
+  int out_stride;
 };
 
 template <int MODE>
@@ -166,7 +167,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const ColDev p) {
     for (int j = 0; j < NS; ++j) {
       double s = 0.0;
       for (int r = 0; r < 8; ++r) s += red[r][lane_c][j];
-      atomicAdd(p.out + (size_t)j * p.C + c, s);
+      atomicAdd(p.out + (size_t)j * p.out_stride + c, s);
     }
   }
 }
@@ -404,6 +405,23 @@ static int slabs_for(long long rows, int* rows_per_slab) {
   return (int)ceil_div_ll(rows, *rows_per_slab);
 }
 
+// column sums ACCUMULATED into out[j * out_stride + c] (the caller zeroes it): the walker keeps one (sum, sum^2)
+// table per concat buffer and adds each layer's 32 new channels to it
+int colsums_into(int mode, const float* X, int ldx, int xcol0, const float* D, int ldd, int dcol0, const float* fold, int C,
+                 long long m_total, int ring_hp, int ring_wp, double* out, int out_stride, cudaStream_t stream) {
+  if (m_total <= 0 || C <= 0) return TCVN_OK;
+  ColDev p{};
+  p.X = X; p.ldx = ldx; p.xcol0 = xcol0; p.D = D; p.ldd = ldd; p.dcol0 = dcol0; p.fold = fold; p.C = C;
+  p.m_total = m_total; p.Hp = ring_hp; p.Wp = ring_wp; p.out = out; p.out_stride = out_stride;
+  const int slabs = slabs_for(m_total, &p.rows_per_slab);
+  dim3 grid(ceil_div(C, 32), slabs);
+  if (mode == 0) colsum_kernel<0><<<grid, 256, 0, stream>>>(p);
+  else if (mode == 1) colsum_kernel<1><<<grid, 256, 0, stream>>>(p);
+  else colsum_kernel<2><<<grid, 256, 0, stream>>>(p);
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
 }  // namespace tcvn
 
 using namespace tcvn;
@@ -451,17 +469,7 @@ extern "C" int tcvn_t_colsums(int mode, const float* X, int ldx, int xcol0, cons
   TCVN_CHECK_ARG(X && sums && mode >= 0 && mode <= 2 && (mode != 1 || (D && fold)), "t_colsums: bad arguments");
   const int ns = mode == 0 ? 2 : (mode == 1 ? 3 : 1);
   TCVN_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * ns * C, stream));
-  if (m_total <= 0) return TCVN_OK;
-  ColDev p{};
-  p.X = X; p.ldx = ldx; p.xcol0 = xcol0; p.D = D; p.ldd = ldd; p.dcol0 = dcol0; p.fold = fold; p.C = C;
-  p.m_total = m_total; p.Hp = ring_hp; p.Wp = ring_wp; p.out = sums;
-  const int slabs = slabs_for(m_total, &p.rows_per_slab);
-  dim3 grid(ceil_div(C, 32), slabs);
-  if (mode == 0) colsum_kernel<0><<<grid, 256, 0, stream>>>(p);
-  else if (mode == 1) colsum_kernel<1><<<grid, 256, 0, stream>>>(p);
-  else colsum_kernel<2><<<grid, 256, 0, stream>>>(p);
-  TCVN_LAUNCH_CHECK();
-  return TCVN_OK;
+  return colsums_into(mode, X, ldx, xcol0, D, ldd, dcol0, fold, C, m_total, ring_hp, ring_wp, sums, C, stream);
 }
 
 extern "C" int tcvn_t_bn_finalize(const double* sums, int C, double count, const float* gamma, const float* beta,
@@ -592,7 +600,8 @@ __global__ void sumsq_kernel(const float* __restrict__ x, long long n, double* _
 
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                              long long n, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1,
-                             float bc2_sqrt, const double* __restrict__ gnorm_sq, float max_norm, float grad_mul) {
+                             float bc2_sqrt, const double* __restrict__ gnorm_sq, float max_norm, float grad_mul,
+                             const uint8_t* __restrict__ select, int select_id) {
   float clip = grad_mul;
   if (gnorm_sq != nullptr && max_norm > 0.f) {
     const float norm = (float)sqrt(*gnorm_sq) * grad_mul;
@@ -600,6 +609,7 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     if (coef < 1.f) clip *= coef;
   }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (select != nullptr && select[i] != select_id) continue;
     const float grad = g[i] * clip;
     float w = p[i] * (1.f - lr * weight_decay);
     const float mi = beta1 * m[i] + (1.f - beta1) * grad;
@@ -625,17 +635,20 @@ extern "C" int tcvn_sumsq(const float* x, int64_t n, double* out, int zero_first
   return TCVN_OK;
 }
 
-extern "C" int tcvn_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
-                               float beta1, float beta2, float eps, float weight_decay, int64_t step, const double* gnorm_sq,
-                               float max_norm, float grad_mul, tcvn_stream_t stream) {
+extern "C" int tcvn_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
+                               double beta1, double beta2, double eps, double weight_decay, int64_t step,
+                               const double* gnorm_sq, float max_norm, float grad_mul, const uint8_t* select, int select_id,
+                               tcvn_stream_t stream) {
   TCVN_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "adamw_step: bad arguments");
   if (n == 0) return TCVN_OK;
-  const float bc1 = 1.f - powf(beta1, (float)step);
-  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  // bias corrections in double on the host, like torch.optim.AdamW's Python scalars
+  const float bc1 = (float)(1.0 - pow(beta1, (double)step));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
   int blocks = (int)tcvn::ceil_div_ll(n, 256 * 4);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  tcvn::adamw_kernel<<<blocks, 256, 0, stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
-                                                  bc1, bc2_sqrt, gnorm_sq, max_norm, grad_mul);
+  tcvn::adamw_kernel<<<blocks, 256, 0, stream>>>(params, grads, exp_avg, exp_avg_sq, n, (float)lr, (float)beta1, (float)beta2,
+                                                  (float)eps, (float)weight_decay, bc1, bc2_sqrt, gnorm_sq, max_norm, grad_mul,
+                                                  select, select_id);
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
 }

@@ -1,0 +1,457 @@
+// DenseNet pixel-map embedding, TRAIN mode: forward with batch-statistics BatchNorm + dropout, and the
+// hand-written backward.  fp32 on the CUDA-core primitives of train.cu (the parity path of training).
+//
+// Reference being reproduced: transformercvn/network/layers/dense_net.py:8-167 under autograd in .train():
+//   every BatchNorm normalises with the statistics of the current batch (biased variance) and updates its
+//   running buffers (momentum 0.1, unbiased variance); Dropout(p) follows conv2 of every bottleneck (:38) and
+//   the output block (:161).
+// Dataflow (same in-place concat buffers as the inference walk, cnn.cu):
+//   * the per-channel (sum, sum^2) of a concat buffer are accumulated ONCE per channel when it is produced;
+//     the BN1 of every later layer of the block (each with its own gamma/beta/running buffers) reuses them;
+//   * a layer keeps its raw conv1 output `mid` (pre-BN2) for the backward; BN+PReLU are applied by the consumer
+//     GEMM on operand load, never materialised;
+//   * the gradient of a concat buffer is one buffer per block; layer i adds its input gradient to channels
+//     [0, k_i) after reading its own output gradient from channels [k_i, k_i+32).
+// Parameter gradients are ACCUMULATED into `grad_arena`, which has the arena's layout (reference state_dict
+// order); slots of the running buffers are left untouched.
+#include "kernels.h"
+#include "plan.h"
+
+namespace tcvn {
+
+int colsums_into(int mode, const float* X, int ldx, int xcol0, const float* D, int ldd, int dcol0, const float* fold, int C,
+                 long long m_total, int ring_hp, int ring_wp, double* out, int out_stride, cudaStream_t stream);
+
+namespace {
+
+constexpr int NOGAP = 1 << 30;
+
+struct TLayer { size_t w1, w1t, w2, w2t, fold1, fold2, mid; };
+struct TBlock {
+  size_t blk, gblk, sums, fold_t, pooled, wt, wtt, tb;
+  std::vector<TLayer> layers;
+};
+
+struct TrainPlan {
+  CnnPlan P;
+  int n;
+  size_t w0, z0, fold0, fold_f, gap, dgap, lin, fold_o, lw, lwt;
+  std::vector<TBlock> blocks;
+  size_t sA, sB, dmid, sums_scr, dwp;
+  size_t bytes;
+
+  static bool build(const tcvn_cnn_desc& d, int n, TrainPlan* T) {
+    if (!CnnPlan::build(d, TCVN_FP32, n, &T->P)) return false;
+    const CnnPlan& P = T->P;
+    T->n = n;
+    size_t w = 0;
+    auto take = [&](size_t floats) { size_t o = w; w += (floats * 4 + 255) / 256 * 256; return o; };
+    const size_t N = (size_t)(n < 1 ? 1 : n);
+    const int C0 = d.init_features, mid = P.mid, g = d.growth;
+    T->w0 = take((size_t)d.in_channels * 49 * C0);
+    T->z0 = take(N * P.Hs * P.Ws * C0);
+    T->fold0 = take(5 * C0);
+    size_t max_rows_c = N * P.Hs * P.Ws * C0, max_rows_mid = 0, max_dw = (size_t)d.in_channels * 49 * C0;
+    int max_c = C0 > d.out_features ? C0 : d.out_features;
+    if (mid > max_c) max_c = mid;
+    T->blocks.clear();
+    for (size_t b = 0; b < P.blocks.size(); ++b) {
+      const BlockPlan& B = P.blocks[b];
+      TBlock X;
+      const size_t rows = N * B.R;
+      X.blk = take(rows * B.ctot);
+      X.gblk = take(rows * B.ctot);
+      X.sums = take(2 * 2 * (size_t)B.ctot);  // doubles
+      if (rows * B.ctot > max_rows_c) max_rows_c = rows * B.ctot;
+      if (rows * mid > max_rows_mid) max_rows_mid = rows * mid;
+      if (B.ctot > max_c) max_c = B.ctot;
+      for (const LayerPlan& L : B.layers) {
+        TLayer Y;
+        Y.w1 = take((size_t)L.kphys * mid);
+        Y.w1t = take((size_t)L.kphys * mid);
+        Y.w2 = take((size_t)9 * mid * g);
+        Y.w2t = take((size_t)9 * mid * g);
+        Y.fold1 = take(5 * (size_t)L.kphys);
+        Y.fold2 = take(5 * (size_t)mid);
+        Y.mid = take(rows * mid);
+        if ((size_t)L.kphys * mid > max_dw) max_dw = (size_t)L.kphys * mid;
+        if ((size_t)9 * mid * g > max_dw) max_dw = (size_t)9 * mid * g;
+        X.layers.push_back(Y);
+      }
+      X.fold_t = X.pooled = X.wt = X.wtt = X.tb = 0;
+      if (B.has_transition) {
+        const BlockPlan& Nx = P.blocks[b + 1];
+        X.fold_t = take(5 * (size_t)B.ctot);
+        X.pooled = take(N * Nx.R * B.ctot);
+        X.wt = take((size_t)B.ctot * B.toutp);
+        X.wtt = take((size_t)B.ctot * B.toutp);
+        X.tb = take(B.toutp);
+        if ((size_t)B.ctot * B.toutp > max_dw) max_dw = (size_t)B.ctot * B.toutp;
+      }
+      T->blocks.push_back(X);
+    }
+    const BlockPlan& last = P.blocks.back();
+    T->fold_f = take(5 * (size_t)last.ctot);
+    T->gap = take(N * last.ctot);
+    T->dgap = take(N * last.ctot);
+    T->lin = take(N * d.out_features);
+    T->fold_o = take(5 * (size_t)d.out_features);
+    T->lw = take((size_t)last.ctot * d.out_features);
+    T->lwt = take((size_t)last.ctot * d.out_features);
+    if ((size_t)last.ctot * d.out_features > max_dw) max_dw = (size_t)last.ctot * d.out_features;
+    T->sA = take(max_rows_c);
+    T->sB = take(max_rows_c);
+    T->dmid = take(max_rows_mid);
+    T->sums_scr = take(2 * 3 * (size_t)max_c);  // doubles
+    T->dwp = take(max_dw);
+    T->bytes = w;
+    return true;
+  }
+};
+
+// ---- small kernels of the walk -------------------------------------------------------------------------------
+// batch statistics -> fold [scale | shift | alpha | mean | rstd] over n_out PHYSICAL channels (alignment-padding
+// channels get an all-zero fold), running-buffer update over the logical channels
+struct FinArgs {
+  const double* s1; const double* s2;  // sum x, sum x^2 by physical channel
+  int n_out, c_log, c0, c0p;
+  double count;
+  const float *gamma, *beta, *alpha;
+  float eps, momentum;
+  float *rm, *rv;
+  float* fold;
+};
+
+__global__ void bn_finalize_map_kernel(const FinArgs a) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.n_out) return;
+  int c = -1;
+  if (p < a.c0) c = p;
+  else if (p >= a.c0p) c = p - (a.c0p - a.c0);
+  float sc = 0.f, sh = 0.f, al = 0.f, mu = 0.f, rs = 0.f;
+  if (c >= 0 && c < a.c_log) {
+    const double mean = a.s1[p] / a.count;
+    double var = a.s2[p] / a.count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    rs = (float)(1.0 / sqrt(var + (double)a.eps));
+    sc = a.gamma[c] * rs;
+    sh = a.beta[c] - (float)mean * sc;
+    al = a.alpha[c];
+    mu = (float)mean;
+    if (a.rm) {
+      const double unbiased = a.count > 1.0 ? var * a.count / (a.count - 1.0) : var;
+      a.rm[c] = (1.f - a.momentum) * a.rm[c] + a.momentum * (float)mean;
+      a.rv[c] = (1.f - a.momentum) * a.rv[c] + a.momentum * (float)unbiased;
+    }
+  }
+  a.fold[p] = sc;
+  a.fold[a.n_out + p] = sh;
+  a.fold[2 * a.n_out + p] = al;
+  a.fold[3 * a.n_out + p] = mu;
+  a.fold[4 * a.n_out + p] = rs;
+}
+
+// BN + PReLU parameter gradients from the backward reductions sums[3][stride] (physical channels)
+__global__ void bn_param_grads_map_kernel(const double* __restrict__ sums, int stride, int c_log, int c0, int c0p,
+                                          float* dgamma, float* dbeta, float* dalpha) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= c_log) return;
+  const int p = c < c0 ? c : c + (c0p - c0);
+  dbeta[c] += (float)sums[p];
+  dgamma[c] += (float)sums[stride + p];
+  dalpha[c] += (float)sums[2 * stride + p];
+}
+
+// weight gradient in kernel layout [taps][K_phys][N_phys] -> += reference layout [n_log][k_log][taps]
+__global__ void unpack_grad_kernel(const float* __restrict__ src, int taps, int K_phys, int N_phys, int n_log, int k_log,
+                                   int c0, int c0p, float* __restrict__ dst) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)n_log * k_log * taps) return;
+  const int t = (int)(idx % taps);
+  const int k = (int)((idx / taps) % k_log);
+  const int n = (int)(idx / ((long long)taps * k_log));
+  const int kp = k < c0 ? k : k + (c0p - c0);
+  dst[idx] += src[((size_t)t * K_phys + kp) * N_phys + n];
+}
+
+__global__ void add_sums_kernel(const double* __restrict__ sums, int c, float* dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < c) dst[i] += (float)sums[i];
+}
+
+struct TWalk {
+  const TrainPlan& T;
+  float* arena;
+  float* garena;
+  char* ws;
+  cudaStream_t st;
+  float p_drop, momentum;
+  uint64_t seed, site;
+
+  float* f(size_t off) const { return reinterpret_cast<float*>(ws + off); }
+  double* dbl(size_t off) const { return reinterpret_cast<double*>(ws + off); }
+
+  int finalize(const double* s1, const double* s2, int n_out, const BnArena& bn, int c0, int c0p, double count, float* fold,
+               bool update) {
+    FinArgs a;
+    a.s1 = s1; a.s2 = s2; a.n_out = n_out; a.c_log = bn.c; a.c0 = c0; a.c0p = c0p; a.count = count;
+    a.gamma = arena + bn.w; a.beta = arena + bn.b; a.alpha = arena + bn.alpha;
+    a.eps = T.P.d.bn_eps; a.momentum = momentum;
+    a.rm = update ? arena + bn.rm : nullptr; a.rv = update ? arena + bn.rv : nullptr;
+    a.fold = fold;
+    bn_finalize_map_kernel<<<ceil_div(n_out, 128), 128, 0, st>>>(a);
+    TCVN_LAUNCH_CHECK();
+    return TCVN_OK;
+  }
+
+  int gemm(const float* A, int lda, long long rows, int K, int taps, const int* tap_off, const float* W, int N,
+           const float* a_fold, int a_hp, int a_wp, const float* bias, float* out, int ldo, int col0, int o_hp, int o_wp,
+           bool accumulate = false) {
+    return tcvn_t_gemm(A, lda, rows, K, taps, tap_off, W, N, a_fold, a_hp, a_wp, bias, out, ldo, col0, o_hp, o_wp,
+                       accumulate ? 1 : 0, st);
+  }
+
+  int stats_scratch(const float* X, int ldx, int col0, int C, long long rows, int hp, int wp) {
+    TCVN_CUDA(cudaMemsetAsync(dbl(T.sums_scr), 0, sizeof(double) * 2 * C, st));
+    return colsums_into(0, X, ldx, col0, nullptr, 0, 0, nullptr, C, rows, hp, wp, dbl(T.sums_scr), C, st);
+  }
+
+  int bias_grad(const float* G, int ldg, int col0, int C, long long rows, int hp, int wp, float* dst) {
+    TCVN_CUDA(cudaMemsetAsync(dbl(T.sums_scr), 0, sizeof(double) * C, st));
+    TCVN_TRY(colsums_into(2, G, ldg, col0, nullptr, 0, 0, nullptr, C, rows, hp, wp, dbl(T.sums_scr), C, st));
+    add_sums_kernel<<<ceil_div(C, 128), 128, 0, st>>>(dbl(T.sums_scr), C, dst);
+    TCVN_LAUNCH_CHECK();
+    return TCVN_OK;
+  }
+
+  // dX (+)= backward of PReLU(BN(X)) given D = gradient of the activated value; parameter gradients of `bn`
+  int bn_bwd(const float* X, int ldx, const float* D, int ldd, const float* fold, int C, double count, long long rows, int hp,
+             int wp, float* dX, int lddx, bool accumulate, const BnArena& bn, int c0, int c0p) {
+    double* s = dbl(T.sums_scr);
+    TCVN_CUDA(cudaMemsetAsync(s, 0, sizeof(double) * 3 * C, st));
+    TCVN_TRY(colsums_into(1, X, ldx, 0, D, ldd, 0, fold, C, rows, hp, wp, s, C, st));
+    TCVN_TRY(tcvn_t_bnact_bwd_apply(D, ldd, 0, X, ldx, 0, fold, s, C, count, dX, lddx, 0, accumulate ? 1 : 0, rows, hp, wp,
+                                    nullptr, nullptr, nullptr, st));
+    bn_param_grads_map_kernel<<<ceil_div(bn.c, 128), 128, 0, st>>>(s, C, bn.c, c0, c0p, garena + bn.w, garena + bn.b,
+                                                                   garena + bn.alpha);
+    TCVN_LAUNCH_CHECK();
+    return TCVN_OK;
+  }
+
+  // dW (reference layout, in garena) += A^T G computed in kernel layout through the scratch buffer
+  int wgrad(const float* A, int lda, long long rows, int K_phys, int taps, const int* tap_off, const float* a_fold, int a_hp,
+            int a_wp, const float* G, int ldg, int gcol0, int N_phys, int g_hp, int g_wp, int n_log, int k_log, int c0,
+            int c0p, float* dst) {
+    float* dwp = f(T.dwp);
+    TCVN_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)taps * K_phys * N_phys, st));
+    TCVN_TRY(tcvn_t_wgrad(A, lda, rows, K_phys, taps, tap_off, a_fold, a_hp, a_wp, G, ldg, gcol0, N_phys, g_hp, g_wp, dwp, st));
+    const long long total = (long long)n_log * k_log * taps;
+    unpack_grad_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(dwp, taps, K_phys, N_phys, n_log, k_log, c0, c0p, dst);
+    TCVN_LAUNCH_CHECK();
+    return TCVN_OK;
+  }
+
+  int pack() {
+    const CnnPlan& P = T.P;
+    const tcvn_cnn_desc& d = P.d;
+    const int mid = P.mid, g = d.growth;
+    TCVN_TRY(repack(arena + P.conv0_w, d.init_features, d.in_channels * 49, 1, NOGAP, NOGAP, d.in_channels * 49,
+                    d.init_features, false, false, f(T.w0), st));
+    for (size_t b = 0; b < P.blocks.size(); ++b) {
+      const BlockPlan& B = P.blocks[b];
+      const TBlock& X = T.blocks[b];
+      for (size_t i = 0; i < B.layers.size(); ++i) {
+        const LayerPlan& L = B.layers[i];
+        const TLayer& Y = X.layers[i];
+        TCVN_TRY(repack(arena + L.conv1_w, mid, L.cin, 1, B.c0, B.c0p, L.kphys, mid, false, false, f(Y.w1), st));
+        TCVN_TRY(repack(arena + L.conv1_w, mid, L.cin, 1, B.c0, B.c0p, L.kphys, mid, true, false, f(Y.w1t), st));
+        TCVN_TRY(repack(arena + L.conv2_w, g, mid, 9, NOGAP, NOGAP, mid, g, false, false, f(Y.w2), st));
+        TCVN_TRY(repack(arena + L.conv2_w, g, mid, 9, NOGAP, NOGAP, mid, g, true, false, f(Y.w2t), st));
+      }
+      if (B.has_transition) {
+        TCVN_TRY(repack(arena + B.tconv_w, B.tout, B.clog, 1, B.c0, B.c0p, B.ctot, B.toutp, false, false, f(X.wt), st));
+        TCVN_TRY(repack(arena + B.tconv_w, B.tout, B.clog, 1, B.c0, B.c0p, B.ctot, B.toutp, true, false, f(X.wtt), st));
+        TCVN_TRY(pad_copy(arena + B.tconv_b, B.tout, f(X.tb), B.toutp, st));
+      }
+    }
+    const BlockPlan& last = P.blocks.back();
+    TCVN_TRY(repack(arena + P.lin_w, d.out_features, last.clog, 1, last.c0, last.c0p, last.ctot, d.out_features, false,
+                    false, f(T.lw), st));
+    TCVN_TRY(repack(arena + P.lin_w, d.out_features, last.clog, 1, last.c0, last.c0p, last.ctot, d.out_features, true,
+                    false, f(T.lwt), st));
+    return TCVN_OK;
+  }
+
+  int forward(const float* pixels, float* emb) {
+    const CnnPlan& P = T.P;
+    const tcvn_cnn_desc& d = P.d;
+    const int n = T.n, C0 = d.init_features, mid = P.mid, g = d.growth;
+    TCVN_TRY(pack());
+    // ---- stem: raw conv0 -> batch statistics -> BN0 + PReLU0 + AvgPool(3,2) into block 0
+    const BlockPlan& B0 = P.blocks[0];
+    const long long stem_rows = (long long)n * P.Hs * P.Ws;
+    TCVN_TRY(tcvn_t_stem_conv(pixels, n, d.in_channels, d.height, d.width, f(T.w0), arena + P.conv0_b, C0, f(T.z0), nullptr,
+                              nullptr, st));
+    TCVN_TRY(stats_scratch(f(T.z0), C0, 0, C0, stem_rows, 0, 0));
+    TCVN_TRY(finalize(dbl(T.sums_scr), dbl(T.sums_scr) + C0, C0, P.norm0, NOGAP, NOGAP, (double)stem_rows, f(T.fold0), true));
+    TCVN_TRY(tcvn_t_pool(0, f(T.z0), f(T.fold0), f(T.blocks[0].blk), n, C0, B0.H, B0.W, P.Hs, P.Ws, B0.ctot, st));
+    for (size_t b = 0; b < P.blocks.size(); ++b) {
+      const BlockPlan& B = P.blocks[b];
+      const TBlock& X = T.blocks[b];
+      const long long rows = (long long)n * B.R;
+      const double count = (double)n * B.H * B.W;
+      float* blk = f(X.blk);
+      double* s1 = dbl(X.sums);
+      double* s2 = s1 + B.ctot;
+      TCVN_CUDA(cudaMemsetAsync(s1, 0, sizeof(double) * 2 * B.ctot, st));
+      TCVN_TRY(colsums_into(0, blk, B.ctot, 0, nullptr, 0, 0, nullptr, B.c0p, rows, B.Hp, B.Wp, s1, B.ctot, st));
+      int tap_off[9];
+      for (int t = 0; t < 9; ++t) tap_off[t] = (t / 3 - 1) * B.Wp + (t % 3 - 1);
+      for (size_t i = 0; i < B.layers.size(); ++i) {
+        const LayerPlan& L = B.layers[i];
+        const TLayer& Y = X.layers[i];
+        TCVN_TRY(finalize(s1, s2, L.kphys, L.norm1, B.c0, B.c0p, count, f(Y.fold1), true));
+        TCVN_TRY(gemm(blk, B.ctot, rows, L.kphys, 1, nullptr, f(Y.w1), mid, f(Y.fold1), 0, 0, arena + L.conv1_b, f(Y.mid), mid,
+                      0, B.Hp, B.Wp));
+        TCVN_TRY(stats_scratch(f(Y.mid), mid, 0, mid, rows, B.Hp, B.Wp));
+        TCVN_TRY(finalize(dbl(T.sums_scr), dbl(T.sums_scr) + mid, mid, L.norm2, NOGAP, NOGAP, count, f(Y.fold2), true));
+        TCVN_TRY(gemm(f(Y.mid), mid, rows, mid, 9, tap_off, f(Y.w2), g, f(Y.fold2), B.Hp, B.Wp, arena + L.conv2_b, blk, B.ctot,
+                      L.kphys, B.Hp, B.Wp));
+        TCVN_TRY(tcvn_t_dropout(blk, B.ctot, L.kphys, g, rows, seed, site * 4096 + b * 64 + i, p_drop, st));
+        TCVN_TRY(colsums_into(0, blk, B.ctot, L.kphys, nullptr, 0, 0, nullptr, g, rows, B.Hp, B.Wp, s1 + L.kphys, B.ctot, st));
+      }
+      if (B.has_transition) {
+        const BlockPlan& Nx = P.blocks[b + 1];
+        TCVN_TRY(finalize(s1, s2, B.ctot, B.tnorm, B.c0, B.c0p, count, f(X.fold_t), true));
+        TCVN_TRY(tcvn_t_act_pool2(blk, n, B.H, B.W, B.ctot, B.ctot, f(X.fold_t), f(X.pooled), Nx.H, Nx.W, st));
+        TCVN_TRY(gemm(f(X.pooled), B.ctot, (long long)n * Nx.R, B.ctot, 1, nullptr, f(X.wt), B.toutp, nullptr, 0, 0, f(X.tb),
+                      f(T.blocks[b + 1].blk), Nx.ctot, 0, Nx.Hp, Nx.Wp));
+      } else {
+        TCVN_TRY(finalize(s1, s2, B.ctot, P.final_norm, B.c0, B.c0p, count, f(T.fold_f), true));
+        TCVN_TRY(tcvn_t_act_gap(blk, n, B.H, B.W, B.ctot, B.ctot, f(T.fold_f), f(T.gap), st));
+      }
+    }
+    // ---- tail: Linear (no bias) -> BatchNorm1d (batch statistics over the n images) -> PReLU -> Dropout
+    const BlockPlan& last = P.blocks.back();
+    const int out = d.out_features;
+    TCVN_TRY(gemm(f(T.gap), last.ctot, n, last.ctot, 1, nullptr, f(T.lw), out, nullptr, 0, 0, nullptr, f(T.lin), out, 0, 0, 0));
+    TCVN_TRY(stats_scratch(f(T.lin), out, 0, out, n, 0, 0));
+    TCVN_TRY(finalize(dbl(T.sums_scr), dbl(T.sums_scr) + out, out, P.out_norm, NOGAP, NOGAP, (double)n, f(T.fold_o), true));
+    TCVN_TRY(tcvn_t_bnact_fwd(f(T.lin), out, 0, f(T.fold_o), out, n, 0, 0, emb, out, 0, st));
+    TCVN_TRY(tcvn_t_dropout(emb, out, 0, out, n, seed, site * 4096 + 4095, p_drop, st));
+    return TCVN_OK;
+  }
+
+  int backward(const float* pixels, float* d_emb) {
+    const CnnPlan& P = T.P;
+    const tcvn_cnn_desc& d = P.d;
+    const int n = T.n, C0 = d.init_features, mid = P.mid, g = d.growth, out = d.out_features;
+    const BlockPlan& last = P.blocks.back();
+    const int nb = (int)P.blocks.size();
+    // ---- tail
+    TCVN_TRY(tcvn_t_dropout(d_emb, out, 0, out, n, seed, site * 4096 + 4095, p_drop, st));
+    TCVN_TRY(bn_bwd(f(T.lin), out, d_emb, out, f(T.fold_o), out, (double)n, n, 0, 0, d_emb, out, false, P.out_norm, NOGAP, NOGAP));
+    TCVN_TRY(wgrad(f(T.gap), last.ctot, n, last.ctot, 1, nullptr, nullptr, 0, 0, d_emb, out, 0, out, 0, 0, out, last.clog,
+                   last.c0, last.c0p, garena + P.lin_w));
+    TCVN_TRY(gemm(d_emb, out, n, out, 1, nullptr, f(T.lwt), last.ctot, nullptr, 0, 0, nullptr, f(T.dgap), last.ctot, 0, 0, 0));
+    TCVN_TRY(tcvn_t_pool(3, f(T.dgap), nullptr, f(T.sA), n, last.ctot, last.H, last.W, 0, 0, last.ctot, st));
+    TCVN_TRY(bn_bwd(f(T.blocks[nb - 1].blk), last.ctot, f(T.sA), last.ctot, f(T.fold_f), last.ctot,
+                    (double)n * last.H * last.W, (long long)n * last.R, last.Hp, last.Wp, f(T.blocks[nb - 1].gblk), last.ctot,
+                    false, P.final_norm, last.c0, last.c0p));
+    for (int b = nb - 1; b >= 0; --b) {
+      const BlockPlan& B = P.blocks[b];
+      const TBlock& X = T.blocks[b];
+      const long long rows = (long long)n * B.R;
+      const double count = (double)n * B.H * B.W;
+      float* blk = f(X.blk);
+      float* gblk = f(X.gblk);
+      float* dmid = f(T.dmid);
+      int tap_off[9], tap_neg[9];
+      for (int t = 0; t < 9; ++t) { tap_off[t] = (t / 3 - 1) * B.Wp + (t % 3 - 1); tap_neg[t] = -tap_off[t]; }
+      for (int i = (int)B.layers.size() - 1; i >= 0; --i) {
+        const LayerPlan& L = B.layers[i];
+        const TLayer& Y = X.layers[i];
+        // gradient of this layer's 32 output channels is complete: every later consumer has added to it
+        TCVN_TRY(tcvn_t_dropout(gblk, B.ctot, L.kphys, g, rows, seed, site * 4096 + b * 64 + i, p_drop, st));
+        TCVN_TRY(bias_grad(gblk, B.ctot, L.kphys, g, rows, B.Hp, B.Wp, garena + L.conv2_b));
+        TCVN_TRY(wgrad(f(Y.mid), mid, rows, mid, 9, tap_off, f(Y.fold2), B.Hp, B.Wp, gblk, B.ctot, L.kphys, g, B.Hp, B.Wp, g, mid,
+                       NOGAP, NOGAP, garena + L.conv2_w));
+        TCVN_TRY(gemm(gblk + L.kphys, B.ctot, rows, g, 9, tap_neg, f(Y.w2t), mid, nullptr, B.Hp, B.Wp, nullptr, dmid, mid, 0, B.Hp,
+                      B.Wp));
+        TCVN_TRY(bn_bwd(f(Y.mid), mid, dmid, mid, f(Y.fold2), mid, count, rows, B.Hp, B.Wp, dmid, mid, false, L.norm2, NOGAP,
+                        NOGAP));
+        TCVN_TRY(bias_grad(dmid, mid, 0, mid, rows, B.Hp, B.Wp, garena + L.conv1_b));
+        TCVN_TRY(wgrad(blk, B.ctot, rows, L.kphys, 1, nullptr, f(Y.fold1), 0, 0, dmid, mid, 0, mid, B.Hp, B.Wp, mid, L.cin, B.c0,
+                       B.c0p, garena + L.conv1_w));
+        TCVN_TRY(gemm(dmid, mid, rows, mid, 1, nullptr, f(Y.w1t), L.kphys, nullptr, 0, 0, nullptr, f(T.sA), L.kphys, 0, B.Hp, B.Wp));
+        TCVN_TRY(bn_bwd(blk, B.ctot, f(T.sA), L.kphys, f(Y.fold1), L.kphys, count, rows, B.Hp, B.Wp, gblk, B.ctot, true, L.norm1,
+                        B.c0, B.c0p));
+      }
+      if (b > 0) {
+        // ---- transition b-1: gblk[:, :toutp] is the gradient of its 1x1 convolution output
+        const BlockPlan& Pv = P.blocks[b - 1];
+        const TBlock& Xp = T.blocks[b - 1];
+        TCVN_TRY(bias_grad(gblk, B.ctot, 0, Pv.tout, rows, B.Hp, B.Wp, garena + Pv.tconv_b));
+        TCVN_TRY(wgrad(f(Xp.pooled), Pv.ctot, rows, Pv.ctot, 1, nullptr, nullptr, 0, 0, gblk, B.ctot, 0, Pv.toutp, B.Hp, B.Wp,
+                       Pv.tout, Pv.clog, Pv.c0, Pv.c0p, garena + Pv.tconv_w));
+        TCVN_TRY(gemm(gblk, B.ctot, rows, Pv.toutp, 1, nullptr, f(Xp.wtt), Pv.ctot, nullptr, B.Hp, B.Wp, nullptr, f(T.sA), Pv.ctot,
+                      0, B.Hp, B.Wp));
+        TCVN_TRY(tcvn_t_pool(2, f(T.sA), nullptr, f(T.sB), n, Pv.ctot, Pv.H, Pv.W, B.H, B.W, Pv.ctot, st));
+        TCVN_TRY(bn_bwd(f(Xp.blk), Pv.ctot, f(T.sB), Pv.ctot, f(Xp.fold_t), Pv.ctot, (double)n * Pv.H * Pv.W,
+                        (long long)n * Pv.R, Pv.Hp, Pv.Wp, f(Xp.gblk), Pv.ctot, false, Pv.tnorm, Pv.c0, Pv.c0p));
+      } else {
+        // ---- stem: AvgPool(3,2) backward -> BN0 + PReLU0 backward -> conv0 bias / weight gradients (hit-driven)
+        const long long stem_rows = (long long)n * P.Hs * P.Ws;
+        TCVN_TRY(tcvn_t_pool(1, gblk, nullptr, f(T.sA), n, C0, B.H, B.W, P.Hs, P.Ws, B.ctot, st));
+        TCVN_TRY(bn_bwd(f(T.z0), C0, f(T.sA), C0, f(T.fold0), C0, (double)stem_rows, stem_rows, 0, 0, f(T.sA), C0, false, P.norm0,
+                        NOGAP, NOGAP));
+        TCVN_TRY(bias_grad(f(T.sA), C0, 0, C0, stem_rows, 0, 0, garena + P.conv0_b));
+        float* dwp = f(T.dwp);
+        const int k0 = d.in_channels * 49;
+        TCVN_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)k0 * C0, st));
+        TCVN_TRY(tcvn_t_stem_conv(pixels, n, d.in_channels, d.height, d.width, f(T.w0), nullptr, C0, nullptr, f(T.sA), dwp, st));
+        unpack_grad_kernel<<<ceil_div(k0 * C0, 256), 256, 0, st>>>(dwp, 1, k0, C0, C0, k0, NOGAP, NOGAP, garena + P.conv0_w);
+        TCVN_LAUNCH_CHECK();
+      }
+    }
+    return TCVN_OK;
+  }
+};
+
+}  // namespace
+}  // namespace tcvn
+
+using namespace tcvn;
+
+extern "C" size_t tcvn_cnn_train_workspace_bytes(const tcvn_cnn_desc* d, int n_images) {
+  TrainPlan T;
+  if (!d || n_images < 0 || !TrainPlan::build(*d, n_images, &T)) { set_error("cnn_train: bad descriptor"); return 0; }
+  return T.bytes;
+}
+
+extern "C" int tcvn_cnn_train_forward(const tcvn_cnn_desc* d, float* arena, const float* pixels, int n_images, float p_drop,
+                                      float momentum, uint64_t seed, uint64_t site, float* embedding, void* workspace,
+                                      size_t workspace_bytes, tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(d && arena && pixels && embedding && workspace, "cnn_train_forward: null pointer");
+  TCVN_CHECK_ARG(n_images >= 2, "cnn_train_forward: BatchNorm in train mode needs at least 2 images (got %d)", n_images);
+  TCVN_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "cnn_train_forward: dropout probability out of range");
+  TrainPlan T;
+  TCVN_CHECK_ARG(TrainPlan::build(*d, n_images, &T), "cnn_train_forward: bad descriptor");
+  if (workspace_bytes < T.bytes)
+    return fail(TCVN_ERR_WORKSPACE, "cnn_train_forward: workspace %zu < %zu bytes", workspace_bytes, T.bytes);
+  TWalk w{T, arena, nullptr, static_cast<char*>(workspace), stream, p_drop, momentum, seed, site};
+  return w.forward(pixels, embedding);
+}
+
+extern "C" int tcvn_cnn_train_backward(const tcvn_cnn_desc* d, const float* arena, float* grad_arena, const float* pixels,
+                                       int n_images, float p_drop, uint64_t seed, uint64_t site, float* d_embedding,
+                                       void* workspace, size_t workspace_bytes, tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(d && arena && grad_arena && pixels && d_embedding && workspace, "cnn_train_backward: null pointer");
+  TCVN_CHECK_ARG(n_images >= 2, "cnn_train_backward: needs the state of a train-mode forward over >= 2 images");
+  TrainPlan T;
+  TCVN_CHECK_ARG(TrainPlan::build(*d, n_images, &T), "cnn_train_backward: bad descriptor");
+  if (workspace_bytes < T.bytes)
+    return fail(TCVN_ERR_WORKSPACE, "cnn_train_backward: workspace %zu < %zu bytes", workspace_bytes, T.bytes);
+  TWalk w{T, const_cast<float*>(arena), grad_arena, static_cast<char*>(workspace), stream, p_drop, 0.f, seed, site};
+  return w.backward(pixels, d_embedding);
+}

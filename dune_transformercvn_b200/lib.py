@@ -29,6 +29,8 @@ EXPORTS = (
     "tcvn_t_gemm", "tcvn_t_wgrad", "tcvn_t_colsums", "tcvn_t_bn_finalize", "tcvn_t_bnact_bwd_apply", "tcvn_t_add_colsums",
     "tcvn_t_bnact_fwd", "tcvn_t_pool", "tcvn_t_dropout", "tcvn_t_stem_conv", "tcvn_t_layernorm", "tcvn_t_attention",
     "tcvn_t_eltwise", "tcvn_t_tokens", "tcvn_t_act_pool2", "tcvn_t_act_gap", "tcvn_sumsq", "tcvn_adamw_step",
+    "tcvn_cnn_train_workspace_bytes", "tcvn_cnn_train_forward", "tcvn_cnn_train_backward",
+    "tcvn_seq_train_workspace_bytes", "tcvn_seq_train_forward", "tcvn_seq_train_backward",
 )
 
 
@@ -103,7 +105,17 @@ def load() -> C.CDLL:
     lib.tcvn_t_act_pool2.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp]
     lib.tcvn_t_act_gap.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.tcvn_sumsq.argtypes = [vp, i64, vp, i32, vp]
-    lib.tcvn_adamw_step.argtypes = [vp, vp, vp, vp, i64, f32, f32, f32, f32, f32, i64, vp, f32, f32, vp]
+    lib.tcvn_adamw_step.argtypes = [vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i64, vp, f32, f32, vp, i32, vp]
+    lib.tcvn_cnn_train_workspace_bytes.argtypes = [C.POINTER(CnnDesc), i32]
+    lib.tcvn_cnn_train_workspace_bytes.restype = sz
+    lib.tcvn_cnn_train_forward.argtypes = [C.POINTER(CnnDesc), vp, vp, i32, f32, f32, u64, u64, vp, vp, sz, vp]
+    lib.tcvn_cnn_train_backward.argtypes = [C.POINTER(CnnDesc), vp, vp, vp, i32, f32, u64, u64, vp, vp, sz, vp]
+    lib.tcvn_seq_train_workspace_bytes.argtypes = [C.POINTER(SeqDesc), i32, i32, i32]
+    lib.tcvn_seq_train_workspace_bytes.restype = sz
+    lib.tcvn_seq_train_forward.argtypes = [C.POINTER(SeqDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, u64,
+                                           vp, vp, vp, sz, vp]
+    lib.tcvn_seq_train_backward.argtypes = [C.POINTER(SeqDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32,
+                                            u64, vp, vp, vp, vp, vp, sz, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("tcvn_abi_version",):

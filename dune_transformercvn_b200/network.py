@@ -248,8 +248,9 @@ class _Engine:
 def _check_eval(mod: nn.Module) -> None:
     if mod.training:
         raise NotImplementedError(
-            "dune_transformercvn_b200: the CUDA path currently implements eval-mode (running-statistics) forward only; "
-            "call .eval() — training kernels (batch-stat BN, dropout, backward) are not built yet and there is "
+            "dune_transformercvn_b200: in train mode only the whole-network forward (NeutrinoDenseNetwork.forward / "
+            "forward_sparse, what the reference's training_step calls) is built; the sub-module surface "
+            "(prong_embedding / encoder / decoders called on their own) is eval-only — call .eval(). There is "
             "deliberately no PyTorch fallback")
 
 
@@ -354,10 +355,18 @@ class NeutrinoDenseNetwork(nn.Module):
         state = synth.init_state(self.specs, seed=seed, perturb=False)
         for s in self.specs:
             _attach(self, s, state[s.name])
+        from .training import TrainEngine
+        self._train_engine = (TrainEngine(self),)
+        for p in self.parameters():
+            p._tcvn_engine = self._train_engine
 
     @property
     def engine(self) -> _Engine:
         return self._engine[0]
+
+    @property
+    def train_engine(self):
+        return self._train_engine[0]
 
     def freeze_packed(self, frozen: bool = True) -> None:
         """Serving mode: skip the per-call check for changed parameters."""
@@ -367,8 +376,14 @@ class NeutrinoDenseNetwork(nn.Module):
         """(B,L,F), (B,E), (B,3,H,W), (B,1) bool, (T,3,H,W), (B,L) bool -> (B,E_cls), (B,L,P_cls).
 
         neutrino_full_base_network.py:166-188.  ``features``/``extra`` only feed the smart-feature
-        embedding, which the shipped configs disable (it contributes zeros)."""
-        _check_eval(self)
+        embedding, which the shipped configs disable (it contributes zeros).
+
+        In ``.train()`` mode this is the train-mode forward (batch-statistics BatchNorm with running-buffer
+        updates, dropout) recorded as ONE autograd node whose backward is the hand-written CUDA backward
+        (fp32; training.py)."""
+        if self.training:
+            from .training import train_forward
+            return train_forward(self.train_engine, event_pixels, event_mask, prong_pixels, prong_mask)
         eng = self.engine
         prec = _PRECISIONS[self.precision]
         _lib.require_cuda(event_pixels, "event_pixels")
@@ -390,7 +405,8 @@ class NeutrinoDenseNetwork(nn.Module):
             ev = densify(batch.event_values, batch.event_coords, self.image_size, batch.num_events, 255.0)
             pr = densify(batch.prong_values, batch.prong_coords, self.image_size, batch.num_prongs, 255.0)
             return self.forward(batch.features, batch.extra, ev, batch.event_mask, pr, batch.prong_mask)
-        _check_eval(self)
+        if self.training:
+            return self.forward_sparse(batch, materialize=True)
         eng = self.engine
         prec = _PRECISIONS[self.precision]
         _lib.require_cuda(batch.event_values, "event hit values")

@@ -1,0 +1,449 @@
+"""Training side of the drop-in network: flat parameter / gradient arenas, the autograd bridge to the
+hand-written forward+backward in libtcvn, a fused AdamW, and the data-parallel gradient exchange.
+
+What it replaces in the reference (paths relative to /root/reference/transformercvn):
+  * autograd over ``NeutrinoDenseNetwork.forward`` in ``training_step``
+    (network/trainers/neutrino_full_base_trainer.py:162-192) -> ``tcvn_cnn_train_*`` / ``tcvn_seq_train_*``;
+  * ``torch.optim.AdamW`` built by ``configure_optimizers`` (network/trainers/neutrino_base.py:109-130) and
+    Lightning's global-norm clip (train.py:140) -> :class:`TcvnAdamW` (``tcvn_sumsq`` + ``tcvn_adamw_step``);
+  * DDP's gradient averaging (train.py:123-127) -> :class:`GradientExchange`: NCCL all-reduce over slices of the
+    flat gradient arena, issued from inside backward so the exchange of one sub-network overlaps the backward
+    of the next.
+The loss itself (focal loss, 0.9/0.1 mix) stays in the caller, as in the reference.
+
+Every float tensor of the network (parameters and BatchNorm running buffers, reference state_dict order) lives
+in ONE fp32 arena; the ``nn.Parameter``s are views into it, their ``.grad``s views into a second arena of the
+same layout.  There is no CPU path: everything here raises on CPU tensors.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, List, Optional, Tuple
+
+import torch
+
+from . import lib as _lib
+from .params import embedding_dims
+
+BN_MOMENTUM = 0.1  # torch.nn.BatchNorm default, used by every BatchNorm of the reference
+
+_PREFIX = {
+    "prong": "prong_embedding.prong_pixel_embedding.",
+    "event": "prong_embedding.event_pixel_embedding.",
+    "position": "prong_embedding.event_position_embedding",
+    "combined": "prong_embedding.combined_embedding.",
+    "encoder": "encoder.",
+    "event_decoder": "event_decoder.",
+    "prong_decoder": "prong_decoder.",
+}
+# parameters the reference never reaches in forward (disable_smart_features=True; neutrino_full_base_network.py:107
+# reads the EVENT position vector for prongs too): they keep grad None, exactly like under torch autograd
+_NO_GRAD_PREFIXES = ("prong_embedding.feature_embedding.", "prong_embedding.prong_position_embedding")
+
+
+def _tensors_of(net) -> Dict[str, torch.Tensor]:
+    out = dict(net.named_parameters())
+    out.update(dict(net.named_buffers()))
+    return out
+
+
+class FlatArena:
+    """One fp32 buffer holding every float tensor of the network + a gradient buffer of the same layout."""
+
+    def __init__(self, net):
+        self.net = (net,)
+        self.specs = [s for s in net.specs if s.in_arena]
+        self.offset: Dict[str, int] = {}
+        cur = 0
+        for s in self.specs:
+            self.offset[s.name] = cur
+            cur += s.numel
+        self.total = cur
+        self.flat: Optional[torch.Tensor] = None
+        self.gflat: Optional[torch.Tensor] = None
+        self.gviews: Dict[str, torch.Tensor] = {}
+        self.select: Optional[torch.Tensor] = None   # per-element optimizer group id (0 = not optimised)
+        self.select_key = None
+        self.seg: Dict[str, Tuple[int, int]] = {}
+        for tag, prefix in _PREFIX.items():
+            names = [s for s in self.specs if s.name.startswith(prefix)]
+            lo = self.offset[names[0].name]
+            self.seg[tag] = (lo, self.offset[names[-1].name] + names[-1].numel)
+
+    # ---- layout ---------------------------------------------------------------------------------
+    def has_grad(self, name: str) -> bool:
+        return not name.startswith(_NO_GRAD_PREFIXES)
+
+    def bound(self) -> bool:
+        if self.flat is None:
+            return False
+        base = self.flat.data_ptr()
+        tensors = _tensors_of(self.net[0])
+        for s in self.specs:
+            t = tensors[s.name]
+            if t.data_ptr() != base + 4 * self.offset[s.name] or t.dtype != torch.float32:
+                return False
+        return True
+
+    def bind(self) -> None:
+        """Move every float tensor into the arena (values preserved) and make the module's tensors views."""
+        net = self.net[0]
+        tensors = _tensors_of(net)
+        dev = tensors[self.specs[0].name].device
+        if dev.type != "cuda":
+            raise _lib.TcvnError("training needs the module on a CUDA device (there is no CPU implementation)")
+        flat = torch.empty(self.total, dtype=torch.float32, device=dev)
+        for s in self.specs:
+            o = self.offset[s.name]
+            flat[o:o + s.numel].copy_(tensors[s.name].detach().reshape(-1).float())
+        for s in self.specs:
+            o = self.offset[s.name]
+            tensors[s.name].data = flat[o:o + s.numel].view(s.shape)
+        self.flat = flat
+        self.gflat = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.gviews = {s.name: self.gflat[self.offset[s.name]:self.offset[s.name] + s.numel].view(s.shape)
+                       for s in self.specs if s.is_param and self.has_grad(s.name)}
+        self.select = None
+
+    def ensure(self) -> None:
+        if not self.bound():
+            self.bind()
+
+    def attach_grads(self) -> None:
+        """Make every parameter's .grad the view into the gradient arena; zero what was reset to None."""
+        params = dict(self.net[0].named_parameters())
+        missing = [n for n, v in self.gviews.items() if params[n].grad is not v]
+        if not missing:
+            return
+        if len(missing) == len(self.gviews):
+            self.gflat.zero_()
+        else:
+            for n in missing:
+                self.gviews[n].zero_()
+        for n in missing:
+            params[n].grad = self.gviews[n]
+
+    def ptr(self, tag: str, grad: bool = False) -> C.c_void_p:
+        buf = self.gflat if grad else self.flat
+        return C.c_void_p(buf.data_ptr() + 4 * self.seg[tag][0])
+
+    def grad_slice(self, tag: str) -> torch.Tensor:
+        lo, hi = self.seg[tag]
+        return self.gflat[lo:hi]
+
+
+class GradientExchange:
+    """Data-parallel gradient averaging over NCCL (the reference's plain DDP, train.py:123-127: rank-local
+    BatchNorm statistics, one averaged gradient).  ``reduce(slice)`` is called from inside backward as soon as
+    a sub-network's gradients are final; ``wait()`` joins the collectives before the optimizer reads them."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.pending: List = []
+        self.bytes = 0
+
+    def reduce(self, grad_slice: torch.Tensor) -> None:
+        if self.world == 1:
+            return
+        op = self.dist.ReduceOp.AVG if grad_slice.is_cuda else self.dist.ReduceOp.SUM
+        work = self.dist.all_reduce(grad_slice, op=op, group=self.group, async_op=True)
+        self.pending.append((work, grad_slice, op))
+        self.bytes += grad_slice.numel() * grad_slice.element_size()
+
+    def wait(self) -> None:
+        for work, sl, op in self.pending:
+            work.wait()
+            if op == self.dist.ReduceOp.SUM:   # gloo (CPU tests) has no AVG
+                sl.div_(self.world)
+        self.pending.clear()
+
+
+class TrainEngine:
+    """Train-mode forward and backward of the whole network through the C ABI."""
+
+    def __init__(self, net):
+        self.net = (net,)
+        self.arena = FlatArena(net)
+        self.ws: Dict[str, torch.Tensor] = {}
+        self.step_index = 0
+        self.exchange: Optional[GradientExchange] = None
+        self.saved = None
+        self._nbt: Optional[List[torch.Tensor]] = None
+
+    def workspace(self, kind: str, nbytes: int, dev) -> torch.Tensor:
+        buf = self.ws.get(kind)
+        if buf is None or buf.numel() < nbytes or buf.device != dev:
+            self.ws.pop(kind, None)
+            buf = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+            self.ws[kind] = buf
+        return buf
+
+    def _cnn_desc(self, tag: str) -> _lib.CnnDesc:
+        net = self.net[0]
+        pix, feat, _ = embedding_dims(net.options)
+        return net.engine.cnn_desc(pix if tag == "prong" else pix + feat)
+
+    def forward(self, event_pixels, event_mask, prong_pixels, prong_mask):
+        net = self.net[0]
+        L = _lib.load()
+        for t, what in ((event_pixels, "event_pixels"), (prong_pixels, "prong_pixels"), (prong_mask, "prong_mask")):
+            _lib.require_cuda(t, what)
+        dev = event_pixels.device
+        self.arena.ensure()
+        net.engine.key = None  # running buffers (and soon the weights) change under the eval-path cache
+        st = _lib.stream_ptr(dev)
+        p_drop = float(net.options.dropout)
+        self.step_index += 1
+        seed = (torch.initial_seed() * 1000003 + self.step_index) & 0xFFFFFFFFFFFF
+        b, l = prong_mask.shape
+        t = prong_pixels.shape[0]
+        pix, feat, _ = embedding_dims(net.options)
+        ev_px = event_pixels.contiguous().float()
+        pr_px = prong_pixels.contiguous().float()
+        f32 = dict(dtype=torch.float32, device=dev)
+        emb = {"event": torch.empty((b, pix + feat), **f32), "prong": torch.empty((t, pix), **f32)}
+        for site, (tag, px, n) in enumerate((("event", ev_px, b), ("prong", pr_px, t)), start=1):
+            d = self._cnn_desc(tag)
+            if tuple(px.shape[1:]) != (d.in_channels, d.height, d.width):
+                raise _lib.TcvnError(f"{tag} pixels have shape {tuple(px.shape)}, expected (N,{d.in_channels},{d.height},{d.width})")
+            nbytes = L.tcvn_cnn_train_workspace_bytes(C.byref(d), n)
+            ws = self.workspace("cnn_" + tag, nbytes, dev)
+            _lib.check(L.tcvn_cnn_train_forward(C.byref(d), self.arena.ptr(tag), _lib.ptr(px), n, p_drop, BN_MOMENTUM, seed, site,
+                                                _lib.ptr(emb[tag]), _lib.ptr(ws), ws.numel(), st), f"tcvn_cnn_train_forward({tag})")
+        sd = net.engine.seq_desc()
+        pm = prong_mask.contiguous().to(torch.uint8)
+        em = None if event_mask is None else event_mask.contiguous().to(torch.uint8)
+        nbytes = L.tcvn_seq_train_workspace_bytes(C.byref(sd), b, l, t)
+        if nbytes == 0:
+            raise _lib.TcvnError("tcvn_seq_train_workspace_bytes: " + L.tcvn_last_error().decode())
+        ws = self.workspace("seq", nbytes, dev)
+        ev_logits = torch.empty((b, sd.num_event_classes), **f32)
+        pr_logits = torch.empty((l * b, sd.num_prong_classes), **f32)
+        a = self.arena
+        _lib.check(L.tcvn_seq_train_forward(C.byref(sd), a.ptr("position"), a.ptr("combined"), a.ptr("encoder"),
+                                            a.ptr("event_decoder"), a.ptr("prong_decoder"), _lib.ptr(emb["event"]),
+                                            _lib.ptr(emb["prong"]), _lib.ptr(em), _lib.ptr(pm), b, l, t, p_drop, BN_MOMENTUM,
+                                            seed, _lib.ptr(ev_logits), _lib.ptr(pr_logits), _lib.ptr(ws), ws.numel(), st),
+                   "tcvn_seq_train_forward")
+        if self._nbt is None:
+            self._nbt = [buf for name, buf in net.named_buffers()
+                         if name.endswith("num_batches_tracked") and not name.startswith(_NO_GRAD_PREFIXES)]
+        if self._nbt:
+            torch._foreach_add_(self._nbt, 1)
+        self.saved = dict(ev_px=ev_px, pr_px=pr_px, pm=pm, b=b, l=l, t=t, seed=seed, p_drop=p_drop, dev=dev)
+        return ev_logits, pr_logits
+
+    def backward(self, d_ev_logits: Optional[torch.Tensor], d_pr_logits: Optional[torch.Tensor]) -> None:
+        if self.saved is None:
+            raise _lib.TcvnError("backward without a train-mode forward (or called twice)")
+        s, self.saved = self.saved, None
+        net = self.net[0]
+        L = _lib.load()
+        dev = s["dev"]
+        st = _lib.stream_ptr(dev)
+        a = self.arena
+        a.attach_grads()
+        sd = net.engine.seq_desc()
+        b, l, t = s["b"], s["l"], s["t"]
+        f32 = dict(dtype=torch.float32, device=dev)
+        pix, feat, _ = embedding_dims(net.options)
+        d_ev = torch.zeros((b, sd.num_event_classes), **f32) if d_ev_logits is None else d_ev_logits.contiguous().float().clone()
+        d_pr = torch.zeros((l * b, sd.num_prong_classes), **f32) if d_pr_logits is None else d_pr_logits.contiguous().float().clone()
+        d_emb = {"event": torch.empty((b, pix + feat), **f32), "prong": torch.empty((t, pix), **f32)}
+        ws = self.ws["seq"]
+        _lib.check(L.tcvn_seq_train_backward(C.byref(sd), a.ptr("position"), a.ptr("combined"), a.ptr("encoder"),
+                                             a.ptr("event_decoder"), a.ptr("prong_decoder"), a.ptr("position", True),
+                                             a.ptr("combined", True), a.ptr("encoder", True), a.ptr("event_decoder", True),
+                                             a.ptr("prong_decoder", True), _lib.ptr(s["pm"]), b, l, t, s["p_drop"], s["seed"],
+                                             _lib.ptr(d_ev), _lib.ptr(d_pr), _lib.ptr(d_emb["event"]), _lib.ptr(d_emb["prong"]),
+                                             _lib.ptr(ws), ws.numel(), st), "tcvn_seq_train_backward")
+        ex = self.exchange
+        if ex is not None:
+            lo = a.seg["combined"][0]
+            ex.reduce(a.gflat[lo:])                       # combined embedding, encoder, both heads
+            ex.reduce(a.grad_slice("position"))
+        # event CNN first: its (small) exchange then overlaps the long prong-CNN backward
+        for site, tag, px, n in ((1, "event", s["ev_px"], b), (2, "prong", s["pr_px"], t)):
+            d = self._cnn_desc(tag)
+            ws = self.ws["cnn_" + tag]
+            _lib.check(L.tcvn_cnn_train_backward(C.byref(d), a.ptr(tag), a.ptr(tag, True), _lib.ptr(px), n, s["p_drop"], s["seed"],
+                                                 site, _lib.ptr(d_emb[tag]), _lib.ptr(ws), ws.numel(), st),
+                       f"tcvn_cnn_train_backward({tag})")
+            if ex is not None:
+                ex.reduce(a.grad_slice(tag))
+
+
+class _TrainFn(torch.autograd.Function):
+    """Autograd node of the whole network: the hand-written backward writes parameter gradients straight into the
+    gradient arena (the parameters' .grad views), so no per-parameter tensors cross the autograd boundary."""
+
+    @staticmethod
+    def forward(ctx, anchor, engine, event_pixels, event_mask, prong_pixels, prong_mask):
+        ctx.engine = engine
+        ev, pr = engine.forward(event_pixels, event_mask, prong_pixels, prong_mask)
+        return ev, pr
+
+    @staticmethod
+    def backward(ctx, d_ev, d_pr):
+        ctx.engine.backward(d_ev, d_pr)
+        return None, None, None, None, None, None
+
+
+def train_forward(engine: TrainEngine, event_pixels, event_mask, prong_pixels, prong_mask):
+    """(B,E) event logits and (B,L,C) prong logits, differentiable w.r.t. the network's parameters."""
+    dev = event_pixels.device
+    anchor = torch.zeros((), device=dev, requires_grad=True)
+    ev, pr = _TrainFn.apply(anchor, engine, event_pixels, event_mask, prong_pixels, prong_mask)
+    b, l = prong_mask.shape
+    return ev, pr.view(l, b, -1).transpose(0, 1)
+
+
+class TcvnAdamW(torch.optim.Optimizer):
+    """Fused AdamW over the flat arenas of a dune_transformercvn_b200 network (torch.optim.AdamW semantics).
+
+    Selected the way the reference selects its optimizer — ``getattr(torch.optim, options.optimizer)``
+    (network/trainers/neutrino_base.py:109) — after ``register()`` publishes it as ``torch.optim.TcvnAdamW``;
+    instantiated as ``cls(param_groups, lr=...)`` with the reference's decay / no-decay groups (:116-130).
+    ``max_grad_norm`` fuses Lightning's ``gradient_clip_val`` (train.py:140) into the step (no host sync)."""
+
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, max_grad_norm: float = 0.0):
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        super().__init__(params, defaults)
+        self.max_grad_norm = float(max_grad_norm)
+        self._arena: Optional[FlatArena] = None
+        self._m = self._v = self._gnorm = None
+        self._steps = [0 for _ in self.param_groups]
+
+    def attach(self, net) -> "TcvnAdamW":
+        """Bind to the network whose parameters this optimizer was given."""
+        eng = net.train_engine
+        eng.arena.ensure()
+        self._arena = eng.arena
+        self._engine = eng
+        dev = self._arena.flat.device
+        self._m = torch.zeros_like(self._arena.flat)
+        self._v = torch.zeros_like(self._arena.flat)
+        self._gnorm = torch.zeros(1, dtype=torch.float64, device=dev)
+        return self
+
+    def _find_arena(self) -> None:
+        for g in self.param_groups:
+            for p in g["params"]:
+                eng = getattr(p, "_tcvn_engine", None)
+                if eng is not None:
+                    self.attach(eng[0].net[0])
+                    return
+        raise _lib.TcvnError("TcvnAdamW drives only the parameters of a dune_transformercvn_b200 network "
+                             "(no generic / CPU fallback): none of the given parameters belongs to one")
+
+    def _selector(self) -> torch.Tensor:
+        a = self._arena
+        by_ptr = {}
+        for gi, g in enumerate(self.param_groups):
+            for p in g["params"]:
+                by_ptr[p.data_ptr()] = (gi + 1, p)
+        key = tuple(sorted((ptr, gi, p.grad is not None) for ptr, (gi, p) in by_ptr.items()))
+        if a.select is not None and a.select_key == key:
+            return a.select
+        sel = torch.zeros(a.total, dtype=torch.uint8)
+        base = a.flat.data_ptr()
+        for s in a.specs:
+            if not s.is_param:
+                continue
+            hit = by_ptr.get(base + 4 * a.offset[s.name])
+            if hit is None or hit[1].grad is None:
+                continue
+            sel[a.offset[s.name]:a.offset[s.name] + s.numel] = hit[0]
+        a.select = sel.to(a.flat.device)
+        a.select_key = key
+        return a.select
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        if self._arena is None or not self._arena.bound():
+            self._find_arena()
+        a = self._arena
+        if self._engine.exchange is not None:
+            self._engine.exchange.wait()
+        L = _lib.load()
+        st = _lib.stream_ptr(a.flat.device)
+        sel = self._selector()
+        gn = None
+        if self.max_grad_norm > 0.0:
+            _lib.check(L.tcvn_sumsq(_lib.ptr(a.gflat), a.total, _lib.ptr(self._gnorm), 1, st), "tcvn_sumsq")
+            gn = _lib.ptr(self._gnorm)
+        for gi, g in enumerate(self.param_groups):
+            self._steps[gi] += 1
+            b1, b2 = g["betas"]
+            _lib.check(L.tcvn_adamw_step(_lib.ptr(a.flat), _lib.ptr(a.gflat), _lib.ptr(self._m), _lib.ptr(self._v), a.total,
+                                         float(g["lr"]), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]),
+                                         self._steps[gi], gn, self.max_grad_norm, 1.0, _lib.ptr(sel), gi + 1, st),
+                       "tcvn_adamw_step")
+        self._engine.net[0].engine.key = None
+        return loss
+
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        """One memset of the gradient arena; the .grad views stay attached (set_to_none would only force the next
+        backward to re-attach them)."""
+        if self._arena is not None and self._arena.gflat is not None:
+            self._arena.gflat.zero_()
+        else:
+            super().zero_grad(set_to_none)
+
+    # checkpointing: moments are exposed per parameter like torch.optim.AdamW's state
+    def state_dict(self):
+        if self._arena is not None:
+            a = self._arena
+            base = a.flat.data_ptr()
+            off = {base + 4 * a.offset[s.name]: (a.offset[s.name], s) for s in a.specs if s.is_param}
+            for gi, g in enumerate(self.param_groups):
+                for p in g["params"]:
+                    hit = off.get(p.data_ptr())
+                    if hit is None:
+                        continue
+                    o, s = hit
+                    self.state[p] = {"step": torch.tensor(float(self._steps[gi])),
+                                     "exp_avg": self._m[o:o + s.numel].view(s.shape),
+                                     "exp_avg_sq": self._v[o:o + s.numel].view(s.shape)}
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict) -> None:
+        super().load_state_dict(state_dict)
+        if self._arena is None:
+            self._find_arena()
+        a = self._arena
+        base = a.flat.data_ptr()
+        off = {base + 4 * a.offset[s.name]: (a.offset[s.name], s) for s in a.specs if s.is_param}
+        for gi, g in enumerate(self.param_groups):
+            for p in g["params"]:
+                hit, stt = off.get(p.data_ptr()), self.state.get(p)
+                if hit is None or not stt:
+                    continue
+                o, s = hit
+                self._m[o:o + s.numel].copy_(stt["exp_avg"].reshape(-1))
+                self._v[o:o + s.numel].copy_(stt["exp_avg_sq"].reshape(-1))
+                self._steps[gi] = int(stt["step"])
+
+
+def register() -> None:
+    """Publish the optimizer under ``torch.optim.TcvnAdamW`` so ``"optimizer": "TcvnAdamW"`` in an options JSON
+    selects it through the reference's own lookup (network/trainers/neutrino_base.py:109)."""
+    torch.optim.TcvnAdamW = TcvnAdamW
+
+
+def reference_param_groups(net, weight_decay: float) -> List[dict]:
+    """The reference's two groups (network/trainers/neutrino_base.py:116-128): names containing neither "bias" nor
+    "LayerNorm.weight" are decayed."""
+    no_decay = ("bias", "LayerNorm.weight")
+    named = list(net.named_parameters())
+    return [
+        {"params": [p for n, p in named if not any(nd in n for nd in no_decay)], "weight_decay": weight_decay},
+        {"params": [p for n, p in named if any(nd in n for nd in no_decay)], "weight_decay": 0.0},
+    ]

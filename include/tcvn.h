@@ -229,10 +229,44 @@ int tcvn_t_act_gap(const float* blk, int n, int H, int W, int ld, int C, const f
 /* sum of squares into a device double (global gradient norm, no host sync) */
 int tcvn_sumsq(const float* x, int64_t n, double* out, int zero_first, tcvn_stream_t stream);
 /* fused AdamW over a flat buffer; replaces torch.optim.AdamW.step (trainers/neutrino_base.py:109-130) and Lightning's
- * clip_grad_norm_ (train.py:140): grads are multiplied by grad_mul * min(1, max_norm / (sqrt(*gnorm_sq)*grad_mul + 1e-6)) */
-int tcvn_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
-                    float beta2, float eps, float weight_decay, int64_t step, const double* gnorm_sq, float max_norm,
-                    float grad_mul, tcvn_stream_t stream);
+ * clip_grad_norm_ (train.py:140): grads are multiplied by grad_mul * min(1, max_norm / (sqrt(*gnorm_sq)*grad_mul + 1e-6)).
+ * select (nullable, one byte per element): only elements with select[i] == select_id are updated - one call per
+ * parameter group (the reference's decay / no-decay split, neutrino_base.py:116-128); 0 marks buffers and parameters
+ * that receive no gradient */
+int tcvn_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
+                    double beta2, double eps, double weight_decay, int64_t step, const double* gnorm_sq, float max_norm,
+                    float grad_mul, const uint8_t* select, int select_id, tcvn_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Training walks: train-mode forward (batch-statistics BatchNorm with running-buffer update, dropout) and the
+ * hand-written backward of the two halves of the network.  Replaces torch autograd over
+ * layers/dense_net.py:8-167 and networks/neutrino_full_base_network.py:99-188 in the reference's training_step
+ * (trainers/neutrino_full_base_trainer.py:162-192).  `arena` / `grad_arena` hold the fp32 tensors of the
+ * sub-module in state_dict order (running buffers included; their gradient slots are never touched); parameter
+ * gradients are ACCUMULATED.  The workspace carries the saved activations from forward to backward and must not
+ * be reused in between.  Dropout masks derive from (seed, site, element): pass the same values to both calls. */
+size_t tcvn_cnn_train_workspace_bytes(const tcvn_cnn_desc* d, int n_images);
+int tcvn_cnn_train_forward(const tcvn_cnn_desc* d, float* arena, const float* pixels, int n_images, float p_drop,
+                           float momentum, uint64_t seed, uint64_t site, float* embedding, void* workspace,
+                           size_t workspace_bytes, tcvn_stream_t stream);
+/* d_embedding (n_images, out_features) is overwritten */
+int tcvn_cnn_train_backward(const tcvn_cnn_desc* d, const float* arena, float* grad_arena, const float* pixels,
+                            int n_images, float p_drop, uint64_t seed, uint64_t site, float* d_embedding, void* workspace,
+                            size_t workspace_bytes, tcvn_stream_t stream);
+size_t tcvn_seq_train_workspace_bytes(const tcvn_seq_desc* d, int n_events, int max_prongs, int n_prongs);
+/* prong_logits: (max_prongs * n_events, classes) in (slot, event) order */
+int tcvn_seq_train_forward(const tcvn_seq_desc* d, const float* position, float* combined, const float* encoder,
+                           const float* event_decoder, float* prong_decoder, const float* event_embedding,
+                           const float* prong_embedding, const uint8_t* event_mask, const uint8_t* prong_mask, int n_events,
+                           int max_prongs, int n_prongs, float p_drop, float momentum, uint64_t seed, float* event_logits,
+                           float* prong_logits, void* workspace, size_t workspace_bytes, tcvn_stream_t stream);
+/* d_event_logits / d_prong_logits are overwritten; d_event_embedding (B, pixel+feature), d_prong_embedding (T, pixel) */
+int tcvn_seq_train_backward(const tcvn_seq_desc* d, const float* position, const float* combined, const float* encoder,
+                            const float* event_decoder, const float* prong_decoder, float* g_position, float* g_combined,
+                            float* g_encoder, float* g_event_decoder, float* g_prong_decoder, const uint8_t* prong_mask,
+                            int n_events, int max_prongs, int n_prongs, float p_drop, uint64_t seed, float* d_event_logits,
+                            float* d_prong_logits, float* d_event_embedding, float* d_prong_embedding, void* workspace,
+                            size_t workspace_bytes, tcvn_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -53,6 +53,8 @@ def test_cpu_call_fails_loudly(net):
     with pytest.raises(tl.TcvnError):
         net(b.features, b.extra, ev, b.event_mask, ev, b.prong_mask)
     net.train()
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(tl.TcvnError):          # train mode: CUDA kernels only as well
         net(b.features, b.extra, ev, b.event_mask, ev, b.prong_mask)
+    with pytest.raises(NotImplementedError):   # sub-modules on their own are eval-only
+        net.prong_embedding(b.features, b.extra, ev, b.event_mask, ev, b.prong_mask)
     net.eval()
