@@ -135,6 +135,113 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def focal_loss_mix(ev_logits, pr_logits, ev_t, pr_t, opts):
+    """The reference's loss (neutrino_full_base_trainer.py:148-177), which stays caller-side code: focal loss with
+    gamma, 0.9 event + 0.1 prong over slots with target >= 0."""
+    def focal(logits, t):
+        logp = torch.log_softmax(logits, dim=-1).gather(1, t.view(-1, 1)).squeeze(1)
+        return (-logp * (1 - logp.exp()) ** opts.loss_gamma).mean()
+    sel = pr_t >= 0
+    a = opts.event_prong_loss_proportion
+    return a * focal(ev_logits, ev_t) + (1 - a) * focal(pr_logits[sel], pr_t[sel])
+
+
+def time_cpu_train(sample_events: int, steps: int, seed: int):
+    """Reference CPU training step (oracle port, fp32 torch autograd): forward + loss + backward."""
+    from oracle import restate
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    state, opts = oracle_state_and_opts()
+    batch = make_inputs(sample_events, seed)
+    g = torch.Generator().manual_seed(seed)
+    ev_t = torch.randint(0, 4, (sample_events,), generator=g)
+    pr_t = torch.randint(0, 8, tuple(batch.prong_mask.shape), generator=g)
+    pr_t[~batch.prong_mask] = -1
+    st = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in state.items()}
+    times = []
+    for i in range(steps + 1):
+        t0 = time.perf_counter()
+        ev, pr = restate.sparse_forward(st, opts, batch, train=True)
+        restate.training_loss(ev, pr, ev_t, pr_t, opts).backward()
+        if i:
+            times.append(time.perf_counter() - t0)
+    mean = sum(times) / len(times)
+    return {"value": sample_events / mean, "unit": "events/s", "cores": cores, "kind": "port",
+            "sample": f"{sample_events} events / {sample_events + batch.num_prongs} images per step, train forward + loss + "
+                      f"backward (dropout = identity), fp32 torch CPU autograd, {steps} timed steps"}
+
+
+def run_train_leg(args, dev, rank, world, timed, sampler_index):
+    """BASELINE configs[2]: DenseNet TransformerCVN training, event-sharded data parallel, NCCL gradient all-reduce.
+    One step = densify -> train-mode forward -> focal loss -> hand-written backward (gradient exchange issued from
+    inside it) -> fused clip + AdamW.  Every rank holds `--train-events` events (weak scaling)."""
+    import torch.distributed as dist
+    from dune_transformercvn_b200 import lib as tl
+    from dune_transformercvn_b200 import training
+    from dune_transformercvn_b200.config import NUM_EVENT_CLASSES, NUM_PRONG_CLASSES, PathOptions
+    from dune_transformercvn_b200.network import NeutrinoDenseNetwork
+    opts = PathOptions.tutorial()
+    net = NeutrinoDenseNetwork(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES, precision=args.precision).to(dev).train()
+    if world > 1:   # same initial weights everywhere (the constructor is seeded, this is DDP's broadcast)
+        net.train_engine.arena.ensure()
+        dist.broadcast(net.train_engine.arena.flat, src=0)
+        net.train_engine.exchange = training.GradientExchange()
+    opt = training.TcvnAdamW(training.reference_param_groups(net, opts.l2_penalty), lr=opts.learning_rate,
+                             max_grad_norm=opts.gradient_clip)
+    batch = make_inputs(args.train_events, 4321 + rank)
+    g = torch.Generator().manual_seed(99 + rank)
+    ev_t = torch.randint(0, NUM_EVENT_CLASSES, (args.train_events,), generator=g)
+    pr_t = torch.randint(0, NUM_PRONG_CLASSES, tuple(batch.prong_mask.shape), generator=g)
+    pr_t[~batch.prong_mask] = -1
+    host = batch.pin()
+    host_t = (ev_t.pin_memory(), pr_t.pin_memory())
+    resident = batch.to(dev)
+    res_t = (ev_t.to(dev), pr_t.to(dev))
+    loss_host = torch.empty(1).pin_memory()
+
+    def step(b, t):
+        opt.zero_grad()
+        ev, pr = net.forward_sparse(b)
+        loss = focal_loss_mix(ev, pr, t[0], t[1], opts)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def step_e2e():
+        b = host.to(dev, non_blocking=True)
+        t = (host_t[0].to(dev, non_blocking=True), host_t[1].to(dev, non_blocking=True))
+        loss_host.copy_(step(b, t).detach().reshape(1), non_blocking=True)
+
+    for _ in range(max(args.warmup, 3)):
+        step(resident, res_t)
+    l0 = tl.load().tcvn_launch_count()
+    ms = timed(lambda: step(resident, res_t), args.train_steps)
+    launches = tl.load().tcvn_launch_count() - l0
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.train_steps)
+    loss_val = float(loss_host[0])
+    images = batch.num_events + batch.num_prongs
+    ex = net.train_engine.exchange
+    out = {"metric": "events/sec, training step (forward + loss + backward + gradient all-reduce + AdamW)",
+           "value": world * args.train_events * args.train_steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+           "ms_per_step": ms / args.train_steps, "steps": args.train_steps, "scaling": "weak",
+           "dtype": "f32" if args.train_precision == "fp32" else "bf16",
+           "config": {"workload": f"BASELINE configs[2]: tutorial DenseNet TransformerCVN, {args.train_events} events/GPU "
+                                  f"({images} images on rank 0), dropout {opts.dropout}, AdamW + clip {opts.gradient_clip}",
+                      "parallelism": f"event-sharded x{world}, rank-local BatchNorm, NCCL all-reduce of the flat fp32 gradient "
+                                     f"arena in 4 slices issued from inside backward"},
+           "e2e": {"value": world * args.train_events * args.train_steps / (ms_e2e / 1e3), "unit": UNIT,
+                   "h2d_bytes_per_step": host.nbytes() + sum(t.numel() * t.element_size() for t in host_t),
+                   "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.train_steps},
+           "allreduce_bytes_per_step": 0 if ex is None else ex.bytes // max(1, (max(args.warmup, 3) + 2 * args.train_steps + 1)),
+           "gpu_launches": launches, "images_per_s": world * images * args.train_steps / (ms / 1e3),
+           "train_gflop_per_image": 14.39, "whole_net_tflops": images * 14.39e9 * args.train_steps / (ms / 1e3) / 1e12,
+           "final_loss": loss_val}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = time_cpu_train(2, 1, 4321)
+    return out
+
+
 def kernel_rooflines(net, resident, batch, dev, pk, args):
     """Times the two layer kernels of dense block 1 alone (CUDA events on the launching stream, inputs ~0.8 GB
     per launch, i.e. larger than L2).  Dominant kernel of the step = the fused-activation 1x1 GEMM family
@@ -271,6 +378,9 @@ def run_ours(args):
     sampler.join(timeout=2)
     value = world * args.events * args.steps / (ms / 1e3)
     e2e_value = world * args.events * args.steps / (ms_e2e / 1e3)
+    train = None
+    if not args.no_train:
+        train = run_train_leg(args, dev, rank, world, timed, local)
     h2d = host.nbytes()
     d2h = sum(t.numel() * t.element_size() for t in out_host)
 
@@ -303,7 +413,7 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "images_per_s": value * images / args.events,
             "whole_net_tflops": tflops, "roofline": roofline, "rooflines_other": extra_rooflines,
-            "cpu_baseline": cpu, "clocks": sampler.summary()}
+            "cpu_baseline": cpu, "clocks": sampler.summary(), "train": train}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -318,6 +428,10 @@ def main():
     ap.add_argument("--events", type=int, default=256)
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training leg (BASELINE configs[2]) reported under \"train\"")
+    ap.add_argument("--train-events", type=int, default=16, help="events per GPU per training step (2023_08_07 JSON batch_size)")
+    ap.add_argument("--train-steps", type=int, default=5)
+    ap.add_argument("--train-precision", default="fp32", choices=["fp32"])
     ap.add_argument("--materialize", action="store_true", help="build the dense pixel maps (densify kernel) instead "
                     "of feeding the stem from the hit lists")
     args = ap.parse_args()

@@ -81,9 +81,14 @@ def main():
         if n not in o_grads:
             print("EXTRA grad", n, float(p.grad.abs().max()))
             continue
-        worst.append((rel(p.grad, o_grads[n]), n, float(o_grads[n].abs().max())))
+        worst.append((float((p.grad.double().cpu() - o_grads[n]).abs().max()), n, float(o_grads[n].abs().max())))
         tot += float((p.grad.double() ** 2).sum())
+    gmax = max(w[2] for w in worst)
+    # error of a tensor relative to max(its own scale, 1e-4 of the largest gradient entry of the network): gradients
+    # that are mathematically zero (conv biases in front of a train-mode BatchNorm) are pure rounding noise
+    worst = [(w[0] / max(w[2], 1e-4 * gmax), w[1], w[2]) for w in worst]
     worst.sort(reverse=True)
+    print("largest gradient entry", gmax)
     print("grad norm", tot ** 0.5, "oracle", float(sum((v.double() ** 2).sum() for v in o_grads.values())) ** 0.5)
     print("worst 25 parameter gradients (rel err, name, max|ref|):")
     for w in worst[:25]:
@@ -111,6 +116,7 @@ def main():
     for k, v in ref_params.items():
         if k in o_grads:
             v.grad = o_grads[k].float()
+            named[k].grad.copy_(v.grad.to(dev))     # same gradients on both sides: this checks the optimizer alone
     no_decay = ("bias", "LayerNorm.weight")
     groups_ref = [{"params": [p for n, p in ref_params.items() if not any(nd in n for nd in no_decay)], "weight_decay": 2.13e-5},
                   {"params": [p for n, p in ref_params.items() if any(nd in n for nd in no_decay)], "weight_decay": 0.0}]
@@ -129,7 +135,7 @@ def main():
     # ---- dropout: forward/backward mask consistency by a directional finite difference
     opts2 = PathOptions.tutorial()
     net2 = NeutrinoDenseNetwork(opts2, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES)
-    net2.load_state_dict(state)
+    net2.load_state_dict(synth.init_state(net2.specs, seed=2, perturb=True))
     net2 = net2.to(dev).train()
     eng = net2.train_engine
 
@@ -151,7 +157,7 @@ def main():
         sel[o:o + v.numel()] = 1.0
     d = gflat * sel
     d = d / d.norm()
-    for eps in (1e-2, 3e-3, 1e-3):
+    for eps in (1e-4, 3e-5, 1e-5):
         eng.arena.flat.copy_(flat0 + eps * d)
         lp = float(run(100))
         eng.arena.flat.copy_(flat0 - eps * d)
