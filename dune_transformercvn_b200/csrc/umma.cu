@@ -45,8 +45,7 @@ static EncodeTiledFn encode_fn() {
 
 // bf16 row-major matrix [rows][cols] with `pitch` elements per row; box = box_cols x box_rows, 128B swizzle,
 // out-of-bounds elements (negative rows included) read as zero.
-static int make_map(const void* base, long long rows, int cols, int pitch, int box_cols, int box_rows,
-                    CUtensorMap* out) {
+int make_map(const void* base, long long rows, int cols, int pitch, int box_cols, int box_rows, CUtensorMap* out) {
   typedef std::tuple<const void*, long long, int, int, int, int> Key;
   static std::map<Key, CUtensorMap> cache;
   static std::mutex mu;
@@ -74,7 +73,7 @@ static int make_map(const void* base, long long rows, int cols, int pitch, int b
   return TCVN_OK;
 }
 
-static int sm_count() {
+int sm_count() {
   static int n = 0;
   if (n == 0) {
     int dev = 0;
@@ -523,7 +522,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
 // ------------------------------------------------------------------------------------------------
 static inline const float* pf(const char* packed, size_t off) { return reinterpret_cast<const float*>(packed + off); }
 
-static int launch_gemm(bool transform, const void* A, long long rows, int a_cols, int a_pitch, const void* W, int w_rows,
+int launch_gemm(bool transform, const void* A, long long rows, int a_cols, int a_pitch, const void* W, int w_rows,
                        int kpad, int kphys, const float* a_scale, const float* a_shift, const float* a_alpha,
                        const float* o_shift, const float* o_alpha, void* out, int out_cols, int out_pitch, int n_tiles_n,
                        int Hp, int Wp, cudaStream_t st) {

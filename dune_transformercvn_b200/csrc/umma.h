@@ -1,5 +1,7 @@
 // bf16 tcgen05 path: launch wrappers used by the CNN walker.
 #pragma once
+#include <cuda.h>
+
 #include "kernels.h"
 
 namespace tcvn {
@@ -9,4 +11,16 @@ int umma_dense_layer_part(const CnnPlan& P, const BlockPlan& B, const LayerPlan&
                           void* mid, long long rows, int which, cudaStream_t st);
 int umma_transition(const CnnPlan& P, const BlockPlan& B, const BlockPlan& Nx, const char* packed, const void* pool,
                     void* next_blk, long long rows, cudaStream_t st);
+
+// shared with the training kernels (umma_train.cu)
+int make_map(const void* base, long long rows, int cols, int pitch, int box_cols, int box_rows, CUtensorMap* out);
+int sm_count();
+// out[m, n] = PReLU_n( sum_k act_k(A[m, k]) * W[n, k] + shift[n] ), bf16 in / bf16 out, N tiles of 128 (see umma.cu)
+int launch_gemm(bool transform, const void* A, long long rows, int a_cols, int a_pitch, const void* W, int w_rows, int kpad,
+                int kphys, const float* a_scale, const float* a_shift, const float* a_alpha, const float* o_shift,
+                const float* o_alpha, void* out, int out_cols, int out_pitch, int n_tiles_n, int Hp, int Wp, cudaStream_t st);
+int umma_wgrad(const void* A, long long rows, int a_cols, int a_pitch, int n_items, const int* item_col, const int* item_shift,
+               const int* item_valid, const float* a_scale, const float* a_shift, const float* a_alpha, int a_fold_cols,
+               const void* G, int g_cols, int g_pitch, int g_col0, float* dw, cudaStream_t st);
+int umma_conv2_dgrad(const void* g2x, const void* wd, long long rows, int Hp, int Wp, void* out, cudaStream_t st);
 }  // namespace tcvn

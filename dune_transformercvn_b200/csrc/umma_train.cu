@@ -1,0 +1,428 @@
+// tcgen05 kernels of the TRAINING path (bf16 operands, fp32 accumulation in TMEM), sm_100a.
+//
+//   umma_wgrad_kernel      weight gradients: dW[item][k][n] = sum_m act(A[m + shift_item, col_item + k]) * G[m, n]
+//       The reduction runs over PIXEL ROWS, which are the slow dimension of both row-major operands, so both
+//       MMA operands are MN-major: TMA drops a [64 rows x 64 channels] box (128-byte rows, 128B swizzle) and the
+//       instruction descriptor's a_major/b_major bits make the tensor core read it transposed - no transposed copy
+//       of an activation ever exists.  M = 128 channels of A (two 64-channel boxes, LBO apart), N = 128 channels
+//       of G, K = 16 rows per instruction.  Up to four "items" (column blocks of A, or row-shifted views of A)
+//       accumulate into four 128-column TMEM accumulators that live for the whole kernel; each persistent CTA owns a
+//       strided set of 64-row tiles and adds its partial sums to the fp32 result with red.global at the end.
+//         conv1:  items = 128-channel column blocks of the concat buffer, act = BN1 + PReLU1 applied in place in
+//                 the swizzled SMEM tile (same trick as the forward conv1 kernel), G = d(mid)
+//         conv2:  items = the three vertical taps (row shifts -Wp, 0, +Wp) of the activated bottleneck map,
+//                 G = the gradient of the 32 output channels in its three horizontal shifts (G2x, 96 + 32 zero
+//                 columns) so that one N=128 MMA covers a whole filter row
+//   umma_conv2_dgrad_kernel   d(act mid)[p][c] = sum_dy sum_k G2x[p + (1-dy) Wp][k] * Wd[dy][c][k]
+//       3x3 input gradient as a 3-tap shifted GEMM over one haloed tile (K-major, like the forward conv2 kernel), the
+//       horizontal taps being the K blocks of G2x.  N = 128.
+#include "ptx.cuh"
+#include "umma.h"
+
+namespace tcvn {
+
+using bf16 = __nv_bfloat16;
+
+namespace {
+
+constexpr int kWgRows = 64;                 // pixel rows per stage
+constexpr int kWgBox = kWgRows * 128;       // 8 KB: one [64 rows x 64 channels] box
+constexpr int kWgThreads = 448;             // warp 0 TMA, warp 1 MMA, warps 2-9 transform, warps 10-13 epilogue
+constexpr int kWgXform = 256;
+
+struct WgradParams {
+  long long rows;
+  int n_items;            // 1..4
+  int item_col[4];        // first A column of the item (elements)
+  int item_shift[4];      // row shift of the item's A view
+  int item_valid[4];      // A columns of the item that are real (<= 128): rows of the result to write
+  int a_cols;             // columns of A covered by the transform constants (channels >= a_cols are forced to 0)
+  const float *a_scale, *a_shift, *a_alpha;
+  int g_col0;
+  float* dw;              // [n_items][128][128] fp32, accumulated
+  int num_tiles, stages;
+};
+
+__device__ __forceinline__ float bfl(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bfh(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+constexpr uint32_t kIdescMN = (1u << 15) | (1u << 16);   // a_major = b_major = MN
+
+template <bool TRANSFORM>
+__global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                   const __grid_constant__ CUtensorMap tmG,
+                                                                   const WgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int stage_bytes = (2 * p.n_items + 2) * kWgBox;   // A boxes of every item, then the two G boxes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* ready = bars + 8;
+  uint64_t* empty = bars + 16;
+  uint64_t* done = bars + 24;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      ptx::mbar_init(&full[s], 1);
+      ptx::mbar_init(&ready[s], kWgXform);
+      ptx::mbar_init(&empty[s], 1);
+    }
+    ptx::mbar_init(done, 1);
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmG);
+  }
+  if (warp == 0) ptx::tmem_alloc(tmem_slot, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int row0 = tile * kWgRows;
+        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        ptx::mbar_arrive_expect_tx(&full[stage], stage_bytes);
+        uint8_t* s = smem + stage * stage_bytes;
+        for (int it = 0; it < p.n_items; ++it)
+          for (int h = 0; h < 2; ++h)
+            ptx::tma_load_2d(s + (2 * it + h) * kWgBox, &tmA, &full[stage], p.item_col[it] + h * 64, row0 + p.item_shift[it]);
+        for (int h = 0; h < 2; ++h)
+          ptx::tma_load_2d(s + (2 * p.n_items + h) * kWgBox, &tmG, &full[stage], p.g_col0 + h * 64, row0);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(128, 128) | kIdescMN;
+      // MN-major, 128B swizzle: 64 channels contiguous (128 B), the next 64 channels LBO = one box further, 8-row
+      // groups SBO = 1024 B apart; one instruction consumes 16 rows = 2048 B
+      const uint32_t lbo = ((uint32_t)kWgBox >> 4) << 16;
+      int stage = 0; uint32_t phase = 0;
+      bool first = true;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(TRANSFORM ? &ready[stage] : &full[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t s_addr = ptx::smem_u32(smem + stage * stage_bytes);
+        const uint32_t g_lo = (((s_addr + 2 * p.n_items * kWgBox) & 0x3FFFFu) >> 4) | lbo;
+#pragma unroll 1
+        for (int it = 0; it < p.n_items; ++it) {
+          const uint32_t a_lo = (((s_addr + 2 * it * kWgBox) & 0x3FFFFu) >> 4) | lbo;
+#pragma unroll
+          for (int ks = 0; ks < kWgRows / 16; ++ks)
+            ptx::umma_bf16(tmem_base + it * 128, ptx::umma_desc_join(ptx::kUmmaDescHiSw128, a_lo + ks * 128),
+                           ptx::umma_desc_join(ptx::kUmmaDescHiSw128, g_lo + ks * 128), idesc, !(first && ks == 0));
+        }
+        first = false;
+        ptx::umma_commit(&empty[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      ptx::umma_commit(done);
+    }
+  } else if (warp < 10) {
+    if (TRANSFORM) {
+      // thread owns 16-byte chunk `pc` of rows rb and rb + 32 of every box: channels 8 * (pc ^ (rb & 7)) of the box
+      const int t = threadIdx.x - 64;
+      const int pc = t & 7, rb = t >> 3;
+      const int cg = pc ^ (rb & 7);
+      const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        if (lane == 0) ptx::mbar_wait(&full[stage], phase);
+        __syncwarp();
+        uint8_t* s = smem + stage * stage_bytes;
+        for (int bx = 0; bx < 2 * p.n_items; ++bx) {
+          const int ch = p.item_col[bx >> 1] + (bx & 1) * 64 + cg * 8;
+          uint8_t* base = s + bx * kWgBox + rb * 128 + pc * 16;
+          if (ch < p.a_cols) {
+            const float4 x0 = __ldg(reinterpret_cast<const float4*>(p.a_scale + ch)), x1 = __ldg(reinterpret_cast<const float4*>(p.a_scale + ch) + 1);
+            const float4 y0 = __ldg(reinterpret_cast<const float4*>(p.a_shift + ch)), y1 = __ldg(reinterpret_cast<const float4*>(p.a_shift + ch) + 1);
+            const float4 z0 = __ldg(reinterpret_cast<const float4*>(p.a_alpha + ch)), z1 = __ldg(reinterpret_cast<const float4*>(p.a_alpha + ch) + 1);
+            const float sc[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            const float sh[8] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w};
+            const float al[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              uint4 v = *reinterpret_cast<const uint4*>(base + i * 32 * 128);
+              uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const __nv_bfloat162 y = __floats2bfloat162_rn(fmaf(bfl(w[q]), sc[2 * q], sh[2 * q]),
+                                                               fmaf(bfh(w[q]), sc[2 * q + 1], sh[2 * q + 1]));
+                const __nv_bfloat162 a2 = __floats2bfloat162_rn(al[2 * q], al[2 * q + 1]);
+                const __nv_bfloat162 r = __hfma2(a2, __hmin2(y, zero2), __hmax2(y, zero2));
+                w[q] = *reinterpret_cast<const uint32_t*>(&r);
+              }
+              *reinterpret_cast<uint4*>(base + i * 32 * 128) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) *reinterpret_cast<uint4*>(base + i * 32 * 128) = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&ready[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // epilogue: after the CTA's last tile, add its partial sums to the global result
+    const int g = warp & 3;          // TMEM lane group this warp may read (warps 10..13 -> 2,3,0,1)
+    const int row = g * 32 + lane;   // channel of A within the item
+    if (blockIdx.x < p.num_tiles) {
+      if (lane == 0) ptx::mbar_wait(done, 0);
+      __syncwarp();
+      ptx::tc_fence_after();
+      for (int it = 0; it < p.n_items; ++it) {
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(g * 32) << 16) + it * 128 + c * 32, r);
+          ptx::tmem_ld_wait();
+          if (row < p.item_valid[it]) {
+            float* dst = p.dw + ((size_t)it * 128 + row) * 128 + c * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv2 input gradient.  One stage = one 64-column half of the haloed G2x tile.
+// ------------------------------------------------------------------------------------------------
+constexpr int kDgThreads = 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kDgStages = 3;
+constexpr int kDgBoxRows = 32;
+constexpr int kDgWSlab = 128 * 128;            // [128 out channels x 64 k] bf16
+constexpr int kDgWBytes = 3 * 2 * kDgWSlab;    // 96 KB: [dy][half]
+
+struct DgradParams {
+  long long m_total;
+  int Hp, Wp, halo_rows, nbox;
+  bf16* out; int ldo;
+  int num_tiles;
+};
+
+__global__ void __launch_bounds__(kDgThreads, 1) umma_conv2_dgrad_kernel(const __grid_constant__ CUtensorMap tmG,
+                                                                         const __grid_constant__ CUtensorMap tmW,
+                                                                         const DgradParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int half_bytes = p.halo_rows * 128;
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + kDgWBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + kDgStages * half_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kDgStages;
+  uint64_t* tfull = bars + 2 * kDgStages;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* wfull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kDgStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 128); }
+    ptx::mbar_init(wfull, 1);
+    ptx::fence_mbar_init();
+    ptx::prefetch_tmap(&tmG);
+    ptx::prefetch_tmap(&tmW);
+  }
+  if (warp == 0) ptx::tmem_alloc(tmem_slot, 256);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_arrive_expect_tx(wfull, kDgWBytes);
+      for (int dy = 0; dy < 3; ++dy)
+        for (int h = 0; h < 2; ++h)
+          ptx::tma_load_2d(sW + (dy * 2 + h) * kDgWSlab, &tmW, wfull, h * 64, dy * 128);
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int row0 = tile * 128 - p.Wp;   // first row of the haloed tile
+        for (int h = 0; h < 2; ++h) {
+          ptx::mbar_wait(&empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[stage], half_bytes);
+          for (int b = 0; b < p.nbox; ++b)
+            ptx::tma_load_2d(sA + stage * half_bytes + b * kDgBoxRows * 128, &tmG, &full[stage], h * 64, row0 + b * kDgBoxRows);
+          if (++stage == kDgStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = ptx::umma_idesc_bf16(128, 128);
+      ptx::mbar_wait(wfull, 0);
+      const uint32_t w_lo = ptx::umma_desc_lo(ptx::smem_u32(sW));
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * 128;
+        for (int h = 0; h < 2; ++h) {
+          ptx::mbar_wait(&full[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_lo = ptx::umma_desc_lo(ptx::smem_u32(sA + stage * half_bytes));
+          const int ksteps = h == 0 ? 4 : 2;   // columns 96..127 of G2x are zero padding
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy) {
+            // out row p reads G2x row p + (1 - dy) * Wp = tile row (p - m0) + (2 - dy) * Wp
+            const uint32_t row_lo = a_lo + (uint32_t)((2 - dy) * p.Wp) * 8u;
+            for (int kk = 0; kk < ksteps; ++kk)
+              ptx::umma_bf16(d_tmem, ptx::umma_desc_join(ptx::kUmmaDescHiSw128, row_lo + kk * 2u),
+                             ptx::umma_desc_join(ptx::kUmmaDescHiSw128, w_lo + (dy * 2 + h) * (kDgWSlab >> 4) + kk * 2u), idesc,
+                             (h | dy | kk) != 0);
+          }
+          ptx::umma_commit(&empty[stage]);
+          if (++stage == kDgStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tfull[acc]);
+        if ((acc ^= 1) == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    const int g = warp & 3;
+    const int row = g * 32 + lane;
+    const int R = p.Hp * p.Wp;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const long long m = (long long)tile * 128 + row;
+      bool ring = false;
+      {
+        const int rr = (int)(m % R);
+        const int y = rr / p.Wp, x = rr - y * p.Wp;
+        ring = y == 0 || y == p.Hp - 1 || x == 0 || x == p.Wp - 1;
+      }
+      if (lane == 0) ptx::mbar_wait(&tfull[acc], acc_phase);
+      __syncwarp();
+      ptx::tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(g * 32) << 16) + acc * 128;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(t_addr + c * 32, r);
+        ptx::tmem_ld_wait();
+        if (m < p.m_total) {
+          uint32_t w[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+            w[j] = ring ? 0u : *reinterpret_cast<const uint32_t*>(&h2);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(p.out + m * p.ldo + c * 32);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tempty[acc]);
+      if ((acc ^= 1) == 0) acc_phase ^= 1;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, 256);
+}
+
+}  // namespace
+
+// dw[item][k][n] (fp32, ACCUMULATED; the caller zeroes it) += sum_m act(A[m + shift_item, col_item + k]) * G[m, g_col0 + n]
+int umma_wgrad(const void* A, long long rows, int a_cols, int a_pitch, int n_items, const int* item_col, const int* item_shift,
+               const int* item_valid, const float* a_scale, const float* a_shift, const float* a_alpha, int a_fold_cols,
+               const void* G, int g_cols, int g_pitch, int g_col0, float* dw, cudaStream_t st) {
+  if (n_items < 1 || n_items > 4) return fail(TCVN_ERR_ARG, "umma_wgrad: %d items (1..4)", n_items);
+  if (rows <= 0) return TCVN_OK;
+  if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one launch");
+  WgradParams p{};
+  p.rows = rows; p.n_items = n_items;
+  for (int i = 0; i < n_items; ++i) { p.item_col[i] = item_col[i]; p.item_shift[i] = item_shift[i]; p.item_valid[i] = item_valid[i]; }
+  p.a_cols = a_fold_cols; p.a_scale = a_scale; p.a_shift = a_shift; p.a_alpha = a_alpha;
+  p.g_col0 = g_col0; p.dw = dw;
+  p.num_tiles = (int)ceil_div_ll(rows, kWgRows);
+  const int stage_bytes = (2 * n_items + 2) * kWgBox;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages < 2) return fail(TCVN_ERR_UNSUPPORTED, "umma_wgrad: stage of %d bytes leaves no room to pipeline", stage_bytes);
+  p.stages = stages;
+  const size_t smem = 1024 + (size_t)stages * stage_bytes + 26 * 8 + 16;
+  static bool attr_done = false;
+  if (!attr_done) {
+    TCVN_CUDA(cudaFuncSetAttribute(umma_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    TCVN_CUDA(cudaFuncSetAttribute(umma_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_done = true;
+  }
+  CUtensorMap tmA, tmG;
+  TCVN_TRY(make_map(A, rows, a_cols, a_pitch, 64, kWgRows, &tmA));
+  TCVN_TRY(make_map(G, rows, g_cols, g_pitch, 64, kWgRows, &tmG));
+  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  if (a_scale) umma_wgrad_kernel<true><<<grid, kWgThreads, smem, st>>>(tmA, tmG, p);
+  else umma_wgrad_kernel<false><<<grid, kWgThreads, smem, st>>>(tmA, tmG, p);
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+// out[p][c] (bf16 [rows, 128], ring rows zero) = sum_dy sum_k G2x[p + (1 - dy) * Wp][k] * Wd[dy][c][k]
+//   G2x  bf16 [rows, 128]: columns dx*32 + n = G[p + 1 - dx][n], columns 96.. zero
+//   Wd   bf16 [3][128][128]: Wd[dy][c][dx*32 + n] = w2[n][c][dy][dx], columns 96.. zero
+int umma_conv2_dgrad(const void* g2x, const void* wd, long long rows, int Hp, int Wp, void* out, cudaStream_t st) {
+  if (rows <= 0) return TCVN_OK;
+  if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one launch");
+  DgradParams p{};
+  p.m_total = rows; p.Hp = Hp; p.Wp = Wp;
+  p.nbox = ceil_div(128 + 2 * Wp, kDgBoxRows);
+  p.halo_rows = p.nbox * kDgBoxRows;
+  const int halo_rows_max = 288;
+  if (p.halo_rows > halo_rows_max)
+    return fail(TCVN_ERR_UNSUPPORTED, "feature map width %d needs a %d-row halo tile (max %d)", Wp - 2, p.halo_rows, halo_rows_max);
+  p.out = static_cast<bf16*>(out); p.ldo = 128;
+  p.num_tiles = (int)ceil_div_ll(rows, 128);
+  static bool attr_done = false;
+  const size_t smem_max = 1024 + kDgWBytes + (size_t)kDgStages * halo_rows_max * 128 + 256;
+  if (!attr_done) {
+    TCVN_CUDA(cudaFuncSetAttribute(umma_conv2_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));
+    attr_done = true;
+  }
+  CUtensorMap tmG, tmW;
+  TCVN_TRY(make_map(g2x, rows, 128, 128, 64, kDgBoxRows, &tmG));
+  TCVN_TRY(make_map(wd, 3 * 128, 128, 128, 64, 128, &tmW));
+  const size_t smem = 1024 + kDgWBytes + (size_t)kDgStages * p.halo_rows * 128 + 256;
+  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  umma_conv2_dgrad_kernel<<<grid, kDgThreads, smem, st>>>(tmG, tmW, p);
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+}  // namespace tcvn
+
+// ---- C ABI: the two kernels on caller-provided matrices (unit-tested against plain matrix products) ----------
+extern "C" int tcvn_t_umma_wgrad(const void* a_bf16, int64_t rows, int a_cols, int a_pitch, int n_items,
+                                 const int32_t* item_col, const int32_t* item_shift, const int32_t* item_valid,
+                                 const float* a_fold, int a_fold_cols, const void* g_bf16, int g_cols, int g_pitch, int g_col0,
+                                 float* dw, tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(a_bf16 && g_bf16 && dw && item_col && item_shift && item_valid, "t_umma_wgrad: null pointer");
+  TCVN_CHECK_ARG(a_pitch % 8 == 0 && g_pitch % 8 == 0, "t_umma_wgrad: row pitches must be multiples of 8 elements (TMA)");
+  TCVN_CHECK_ARG(a_fold == nullptr || a_fold_cols % 8 == 0, "t_umma_wgrad: fold width must be a multiple of 8");
+  return tcvn::umma_wgrad(a_bf16, rows, a_cols, a_pitch, n_items, item_col, item_shift, item_valid, a_fold,
+                          a_fold ? a_fold + a_fold_cols : nullptr, a_fold ? a_fold + 2 * a_fold_cols : nullptr, a_fold_cols,
+                          g_bf16, g_cols, g_pitch, g_col0, dw, stream);
+}
+
+extern "C" int tcvn_t_umma_conv2_dgrad(const void* g2x_bf16, const void* wd_bf16, int64_t rows, int ring_hp, int ring_wp,
+                                       void* out_bf16, tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(g2x_bf16 && wd_bf16 && out_bf16 && ring_hp >= 3 && ring_wp >= 3, "t_umma_conv2_dgrad: bad arguments");
+  return tcvn::umma_conv2_dgrad(g2x_bf16, wd_bf16, rows, ring_hp, ring_wp, out_bf16, stream);
+}

@@ -86,9 +86,16 @@ def test_train_step_matches_reference(golden_dir, dev, prongs):
         assert rel_err(pr.detach().cpu(), gold["prong_logits"]) < 1e-4
         assert abs(float(loss.detach()) - gold["loss"]) < 1e-4 * gold["loss"]
         assert sorted(n for n, p in named.items() if p.grad is None) == sorted(gold["no_grad"])
-        for n, g in gold["grads"].items():
-            if "full" in g and not n.endswith(("conv1.bias", "conv2.bias", "conv.bias", "conv0.bias")):
-                assert rel_err(named[n].grad.cpu(), g["full"]) < 3e-2, n
+        gmax0 = max(float(v.abs().max()) for v in o_grads.values())
+        for n, g in gold["grads"].items():   # gradients frozen from the unmodified reference (fp64)
+            if "full" in g:
+                d = float((named[n].grad.double().cpu() - g["full"]).abs().max())
+                assert d / max(float(g["full"].abs().max()), 1e-4 * gmax0) < 3e-2, n
+            else:
+                got = named[n].grad.double().cpu().reshape(-1)
+                assert abs(float(got.sum()) - g["sum"]) < 2e-2 * g["abs_sum"], n
+                assert abs(float(got.abs().sum()) - g["abs_sum"]) < 2e-2 * g["abs_sum"], n
+                assert float((got[g["idx"]] - g["vals"]).abs().max()) < 3e-2 * max(float(g["vals"].abs().max()), 1e-4 * gmax0), n
         sd = net.state_dict()
         for k, v in gold["running"].items():
             if not k.startswith("prong_embedding.feature_embedding."):
