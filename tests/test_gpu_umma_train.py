@@ -112,8 +112,9 @@ def test_conv2_dgrad_matches_conv_transpose(dev, n, h, w):
         for dx in range(3):
             wd[dy, :, dx * 32:(dx + 1) * 32] = w2[:, :, dy, dx].t()
     out = torch.empty(rows, 128, dtype=torch.bfloat16, device=dev)
-    tl.check(L.tcvn_t_umma_conv2_dgrad(tl.ptr(g2x.to(dev).bfloat16()), tl.ptr(wd.to(dev).bfloat16()), rows, hp, wp, tl.ptr(out),
-                                       tl.stream_ptr(dev)), "tcvn_t_umma_conv2_dgrad")
+    g2x_d, wd_d = g2x.to(dev).bfloat16(), wd.to(dev).bfloat16()   # keep alive: the C ABI only sees raw pointers
+    tl.check(L.tcvn_t_umma_conv2_dgrad(tl.ptr(g2x_d), tl.ptr(wd_d), rows, hp, wp, tl.ptr(out), tl.stream_ptr(dev)),
+             "tcvn_t_umma_conv2_dgrad")
     got = out.float().cpu().reshape(n, hp, wp, 128)
     ring = torch.cat([got[:, 0].reshape(-1), got[:, -1].reshape(-1), got[:, :, 0].reshape(-1), got[:, :, -1].reshape(-1)])
     assert float(ring.abs().max()) == 0.0
