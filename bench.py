@@ -181,7 +181,7 @@ def run_train_leg(args, dev, rank, world, timed, sampler_index):
     from dune_transformercvn_b200.config import NUM_EVENT_CLASSES, NUM_PRONG_CLASSES, PathOptions
     from dune_transformercvn_b200.network import NeutrinoDenseNetwork
     opts = PathOptions.tutorial()
-    net = NeutrinoDenseNetwork(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES, precision=args.precision).to(dev).train()
+    net = NeutrinoDenseNetwork(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES, precision=args.train_precision).to(dev).train()
     if world > 1:   # same initial weights everywhere (the constructor is seeded, this is DDP's broadcast)
         net.train_engine.arena.ensure()
         dist.broadcast(net.train_engine.arena.flat, src=0)
@@ -431,7 +431,7 @@ def main():
     ap.add_argument("--no-train", action="store_true", help="skip the training leg (BASELINE configs[2]) reported under \"train\"")
     ap.add_argument("--train-events", type=int, default=16, help="events per GPU per training step (2023_08_07 JSON batch_size)")
     ap.add_argument("--train-steps", type=int, default=5)
-    ap.add_argument("--train-precision", default="fp32", choices=["fp32"])
+    ap.add_argument("--train-precision", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--materialize", action="store_true", help="build the dense pixel maps (densify kernel) instead "
                     "of feeding the stem from the hit lists")
     args = ap.parse_args()

@@ -51,6 +51,26 @@ int repack(const float* src, int n_log, int k_log, int taps, int c0, int c0p, in
            float eps = 0.f);
 int pad_copy(const float* src, int n_log, float* dst, int n_out, cudaStream_t st);
 
+// train.cu: typed cores of the training primitives (bool *_bf16 = element type of that operand; false = fp32)
+int colsums_typed(int mode, const void* X, bool x_bf16, int ldx, int xcol0, const void* D, bool d_bf16, int ldd, int dcol0,
+                  const float* fold, int fold_stride, int C, long long m_total, int ring_hp, int ring_wp, double* out,
+                  int out_stride, cudaStream_t stream);
+int colsums_into(int mode, const float* X, int ldx, int xcol0, const float* D, int ldd, int dcol0, const float* fold, int C,
+                 long long m_total, int ring_hp, int ring_wp, double* out, int out_stride, cudaStream_t stream);
+int bnact_bwd_apply_typed(const void* D, bool d_bf16, int ldd, int dcol0, const void* X, bool x_bf16, int ldx, int xcol0,
+                          const float* fold, int fold_stride, const double* sums, int C, double count, void* dX, bool o_bf16,
+                          int lddx, int dxcol0, bool accumulate, long long m_total, int ring_hp, int ring_wp,
+                          cudaStream_t stream);
+int bnact_fwd_typed(const void* X, bool x_bf16, int ldx, int xcol0, const float* fold, int fold_stride, int C, long long m_total,
+                    int ring_hp, int ring_wp, void* out, bool o_bf16, int ldo, int ocol0, cudaStream_t stream);
+int pool_typed(int kind, const void* src, const float* fold, void* dst, bool bf16, int n, int C, int H, int W, int H2, int W2,
+               int ld, cudaStream_t stream);
+int dropout_typed(void* X, bool bf16, int ld, int col0, int C, long long m_total, uint64_t seed, uint64_t stream_id, float p,
+                  cudaStream_t stream);
+int wgrad_typed(const void* A, bool a_bf16, int lda, long long m_total, int K, int taps, const int* tap_off, const float* a_scale,
+                const float* a_shift, const float* a_alpha, int a_ring_hp, int a_ring_wp, const void* G, bool g_bf16, int ldg,
+                int g_col0, int N, int g_ring_hp, int g_ring_wp, float* dW, cudaStream_t stream);
+
 #define TCVN_TRY(expr)                \
   do {                                \
     int rc__ = (expr);                \

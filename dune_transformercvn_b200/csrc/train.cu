@@ -23,10 +23,10 @@ __device__ __forceinline__ bool is_ring(long long m, int Hp, int Wp) {
 // weight gradient of the (shifted) GEMM:  dW[t][k][n] += sum_m act(A[m + off_t, k]) * G[m, n]
 // ------------------------------------------------------------------------------------------------
 struct WgradDev {
-  const float* A; int lda; long long m_total; int K; int taps; int tap_off[9];
+  const void* A; int lda; long long m_total; int K; int taps; int tap_off[9];
   const float *a_scale, *a_shift, *a_alpha;
   int a_ring_Hp, a_ring_Wp;
-  const float* G; int ldg; int g_col0; int N;
+  const void* G; int ldg; int g_col0; int N;
   int g_ring_Hp, g_ring_Wp;
   float* dW;  // [taps][K][N], accumulated with atomics
   int rows_per_slab;
@@ -34,7 +34,10 @@ struct WgradDev {
 
 constexpr int kWgK = 64, kWgN = 32, kWgR = 32;
 
+template <typename TA, typename TG>
 __global__ void __launch_bounds__(256) wgrad_kernel(const WgradDev g) {
+  const TA* gA = static_cast<const TA*>(g.A);
+  const TG* gG = static_cast<const TG*>(g.G);
   __shared__ float As[kWgR][kWgK + 1];
   __shared__ float Gs[kWgR][kWgN + 1];
   const int tid = threadIdx.x;
@@ -58,7 +61,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradDev g) {
         const int k = k0 + kq + i;
         float v = 0.f;
         if (ok && k < g.K) {
-          v = g.A[gm * (long long)g.lda + k];
+          v = to_f32<TA>(gA[gm * (long long)g.lda + k]);
           if (transform) v = prelu(fmaf(v, __ldg(g.a_scale + k), __ldg(g.a_shift + k)), __ldg(g.a_alpha + k));
         }
         As[r][kq + i] = v;
@@ -71,7 +74,7 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradDev g) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int n = n0 + nq + i;
-        Gs[r][nq + i] = (ok && n < g.N) ? g.G[m * (long long)g.ldg + g.g_col0 + n] : 0.f;
+        Gs[r][nq + i] = (ok && n < g.N) ? to_f32<TG>(gG[m * (long long)g.ldg + g.g_col0 + n]) : 0.f;
       }
     }
     __syncthreads();
@@ -104,18 +107,20 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradDev g) {
 // fold = [scale | shift | alpha | mean | rstd] (5 x C), y = scale*x + shift, g = dA * (y >= 0 ? 1 : alpha)
 // ------------------------------------------------------------------------------------------------
 struct ColDev {
-  const float* X; int ldx; int xcol0;
-  const float* D; int ldd; int dcol0;
-  const float* fold; int C;
+  const void* X; int ldx; int xcol0;
+  const void* D; int ldd; int dcol0;
+  const float* fold; int fold_stride; int C;
   long long m_total; int Hp, Wp; int rows_per_slab;
   double* out;  // [nsums][out_stride]
   int out_stride;
 };
 
-template <int MODE>
+template <int MODE, typename TX, typename TD>
 __global__ void __launch_bounds__(256) colsum_kernel(const ColDev p) {
   constexpr int NS = MODE == 0 ? 2 : (MODE == 1 ? 3 : 1);
   __shared__ double red[8][32][NS];
+  const TX* X = static_cast<const TX*>(p.X);
+  const TD* D = static_cast<const TD*>(p.D);
   const int lane_c = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane_c;
   const long long r_begin = (long long)blockIdx.y * p.rows_per_slab;
@@ -126,7 +131,8 @@ __global__ void __launch_bounds__(256) colsum_kernel(const ColDev p) {
   if (c < p.C) {
     float sc = 0.f, sh = 0.f, al = 0.f, mean = 0.f, rstd = 0.f;
     if (MODE == 1) {
-      sc = p.fold[c]; sh = p.fold[p.C + c]; al = p.fold[2 * p.C + c]; mean = p.fold[3 * p.C + c]; rstd = p.fold[4 * p.C + c];
+      const int fs = p.fold_stride;
+      sc = p.fold[c]; sh = p.fold[fs + c]; al = p.fold[2 * fs + c]; mean = p.fold[3 * fs + c]; rstd = p.fold[4 * fs + c];
     }
     float part[NS];
 #pragma unroll
@@ -135,19 +141,19 @@ __global__ void __launch_bounds__(256) colsum_kernel(const ColDev p) {
     for (long long m = r_begin + rl; m < r_end; m += 8) {
       if (!is_ring(m, p.Hp, p.Wp)) {
         if (MODE == 0) {
-          const float x = p.X[m * (long long)p.ldx + p.xcol0 + c];
+          const float x = to_f32<TX>(X[m * (long long)p.ldx + p.xcol0 + c]);
           part[0] += x;
           part[1] = fmaf(x, x, part[1]);
         } else if (MODE == 1) {
-          const float x = p.X[m * (long long)p.ldx + p.xcol0 + c];
-          const float d = p.D[m * (long long)p.ldd + p.dcol0 + c];
+          const float x = to_f32<TX>(X[m * (long long)p.ldx + p.xcol0 + c]);
+          const float d = to_f32<TD>(D[m * (long long)p.ldd + p.dcol0 + c]);
           const float y = fmaf(x, sc, sh);
           const float g = y >= 0.f ? d : d * al;
           part[0] += g;
           part[1] = fmaf(g, (x - mean) * rstd, part[1]);
           part[2] = fmaf(d, fminf(y, 0.f), part[2]);
         } else {
-          part[0] += p.X[m * (long long)p.ldx + p.xcol0 + c];
+          part[0] += to_f32<TX>(X[m * (long long)p.ldx + p.xcol0 + c]);
         }
       }
       if (++cnt == 64) {  // flush the fp32 partials into doubles every 64 rows
@@ -197,32 +203,33 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, doubl
 
 // BN + PReLU backward, elementwise half:  dX (+)= scale * (g - sum_g/M - xhat * sum_gxhat/M)
 struct BnBwdDev {
-  const float* D; int ldd; int dcol0;
-  const float* X; int ldx; int xcol0;
-  const float* fold; const double* sums; int C; double count;
-  float* dX; int lddx; int dxcol0; int accumulate;
+  const void* D; int ldd; int dcol0;
+  const void* X; int ldx; int xcol0;
+  const float* fold; int fold_stride; const double* sums; int C; double count;
+  void* dX; int lddx; int dxcol0; int accumulate;
   long long m_total; int Hp, Wp;
 };
 
+template <typename TX, typename TD, typename TO>
 __global__ void bnact_bwd_apply_kernel(const BnBwdDev p) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= p.m_total * p.C) return;
   const int c = (int)(idx % p.C);
   const long long m = idx / p.C;
-  float* dst = p.dX + m * (long long)p.lddx + p.dxcol0 + c;
+  TO* dst = static_cast<TO*>(p.dX) + m * (long long)p.lddx + p.dxcol0 + c;
   if (is_ring(m, p.Hp, p.Wp)) {
-    if (!p.accumulate) *dst = 0.f;
+    if (!p.accumulate) *dst = from_f32<TO>(0.f);
     return;
   }
-  const float sc = p.fold[c], sh = p.fold[p.C + c], al = p.fold[2 * p.C + c], mean = p.fold[3 * p.C + c],
-              rstd = p.fold[4 * p.C + c];
-  const float x = p.X[m * (long long)p.ldx + p.xcol0 + c];
-  const float d = p.D[m * (long long)p.ldd + p.dcol0 + c];
+  const int fs = p.fold_stride;
+  const float sc = p.fold[c], sh = p.fold[fs + c], al = p.fold[2 * fs + c], mean = p.fold[3 * fs + c], rstd = p.fold[4 * fs + c];
+  const float x = to_f32<TX>(static_cast<const TX*>(p.X)[m * (long long)p.ldx + p.xcol0 + c]);
+  const float d = to_f32<TD>(static_cast<const TD*>(p.D)[m * (long long)p.ldd + p.dcol0 + c]);
   const float y = fmaf(x, sc, sh);
   const float g = y >= 0.f ? d : d * al;
   const float mg = (float)(p.sums[c] / p.count), mgx = (float)(p.sums[p.C + c] / p.count);
   const float v = sc * (g - mg - (x - mean) * rstd * mgx);
-  *dst = p.accumulate ? *dst + v : v;
+  *dst = from_f32<TO>(p.accumulate ? to_f32<TO>(*dst) + v : v);
 }
 
 // parameter gradients of a BN + PReLU pair from the reductions: dgamma = sum g*xhat, dbeta = sum g, dalpha
@@ -240,23 +247,26 @@ __global__ void add_cols_kernel(const double* __restrict__ sums, int C, float* d
 }
 
 // out[m, c] = PReLU(BN(x[m, c])) (ring rows -> 0): materialised activation for the few places that need it
-__global__ void bnact_fwd_kernel(const float* __restrict__ X, int ldx, int xcol0, const float* __restrict__ fold, int C,
-                                 long long m_total, int Hp, int Wp, float* __restrict__ out, int ldo, int ocol0) {
+template <typename TX, typename TO>
+__global__ void bnact_fwd_kernel(const TX* __restrict__ X, int ldx, int xcol0, const float* __restrict__ fold, int fold_stride,
+                                 int C, long long m_total, int Hp, int Wp, TO* __restrict__ out, int ldo, int ocol0) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= m_total * C) return;
   const int c = (int)(idx % C);
   const long long m = idx / C;
   float v = 0.f;
-  if (!is_ring(m, Hp, Wp)) v = prelu(fmaf(X[m * (long long)ldx + xcol0 + c], fold[c], fold[C + c]), fold[2 * C + c]);
-  out[m * (long long)ldo + ocol0 + c] = v;
+  if (!is_ring(m, Hp, Wp))
+    v = prelu(fmaf(to_f32<TX>(X[m * (long long)ldx + xcol0 + c]), fold[c], fold[fold_stride + c]), fold[2 * fold_stride + c]);
+  out[m * (long long)ldo + ocol0 + c] = from_f32<TO>(v);
 }
 
 // ------------------------------------------------------------------------------------------------
 // pooling forward / backward on ringed maps
 // ------------------------------------------------------------------------------------------------
 // AvgPool2d(3,2) of the un-ringed stem map act(z0) [n,Hs,Ws,C] -> ringed [n,H+2,W+2,ld] channels [0,C)
+template <typename TO>
 __global__ void stem_pool_fwd_kernel(const float* __restrict__ z, const float* __restrict__ fold, int Hs, int Ws, int C,
-                                     float* __restrict__ blk, int ld, int H, int W, long long total) {
+                                     TO* __restrict__ blk, int ld, int H, int W, long long total) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int c = (int)(idx % C);
@@ -271,7 +281,7 @@ __global__ void stem_pool_fwd_kernel(const float* __restrict__ z, const float* _
 #pragma unroll
     for (int dx = 0; dx < 3; ++dx)
       s += prelu(fmaf(z[(((size_t)n * Hs + 2 * y + dy) * Ws + 2 * x + dx) * C + c], sc, sh), al);
-  blk[((size_t)n * (H + 2) * (W + 2) + (size_t)(y + 1) * (W + 2) + x + 1) * ld + c] = s / 9.0f;
+  blk[((size_t)n * (H + 2) * (W + 2) + (size_t)(y + 1) * (W + 2) + x + 1) * ld + c] = from_f32<TO>(s / 9.0f);
 }
 
 // gradient of the above w.r.t. the activated stem map: dA[n,oy,ox,c] = (1/9) sum of dP over the windows holding (oy,ox)
@@ -296,7 +306,8 @@ __global__ void stem_pool_bwd_kernel(const float* __restrict__ dblk, int ld, int
 }
 
 // AvgPool2d(2,2) backward: dA[ringed H x W rows, C] = 0.25 * dP[ringed H2 x W2 parent] (0 where the floor cropped)
-__global__ void pool2_bwd_kernel(const float* __restrict__ dP, int H2, int W2, int C, float* __restrict__ dA, int H, int W,
+template <typename T>
+__global__ void pool2_bwd_kernel(const T* __restrict__ dP, int H2, int W2, int C, T* __restrict__ dA, int H, int W,
                                  long long total) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -309,19 +320,20 @@ __global__ void pool2_bwd_kernel(const float* __restrict__ dP, int H2, int W2, i
   float v = 0.f;
   const int y = yy - 1, x = xx - 1;
   if (y >= 0 && y < 2 * H2 && x >= 0 && x < 2 * W2)
-    v = 0.25f * dP[((size_t)n * (H2 + 2) * (W2 + 2) + (size_t)(y / 2 + 1) * (W2 + 2) + x / 2 + 1) * C + c];
-  dA[idx] = v;
+    v = 0.25f * to_f32<T>(dP[((size_t)n * (H2 + 2) * (W2 + 2) + (size_t)(y / 2 + 1) * (W2 + 2) + x / 2 + 1) * C + c]);
+  dA[idx] = from_f32<T>(v);
 }
 
 // global average pool backward: dA[ringed rows, C] = dGap[n, c] / (H*W) on interior rows
-__global__ void gap_bwd_kernel(const float* __restrict__ dGap, int C, float* __restrict__ dA, int H, int W, long long total) {
+template <typename TO>
+__global__ void gap_bwd_kernel(const float* __restrict__ dGap, int C, TO* __restrict__ dA, int H, int W, long long total) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const int c = (int)(idx % C);
   const long long m = idx / C;
   const int R = (H + 2) * (W + 2);
   const int n = (int)(m / R);
-  dA[idx] = is_ring(m, H + 2, W + 2) ? 0.f : dGap[(size_t)n * C + c] / (float)(H * W);
+  dA[idx] = from_f32<TO>(is_ring(m, H + 2, W + 2) ? 0.f : dGap[(size_t)n * C + c] / (float)(H * W));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -334,7 +346,8 @@ __device__ __forceinline__ uint32_t mix32(uint64_t z) {  // splitmix64 finaliser
   return (uint32_t)((z ^ (z >> 31)) >> 32);
 }
 
-__global__ void dropout_kernel(float* X, int ld, int col0, int C, long long m_total, unsigned long long seed,
+template <typename T>
+__global__ void dropout_kernel(T* X, int ld, int col0, int C, long long m_total, unsigned long long seed,
                                unsigned long long stream_id, float p) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= m_total * C) return;
@@ -342,8 +355,8 @@ __global__ void dropout_kernel(float* X, int ld, int col0, int C, long long m_to
   const long long m = idx / C;
   const uint32_t r = mix32(seed * 0x100000001b3ull + stream_id * 0x9e3779b97f4a7c15ull + (unsigned long long)idx);
   const bool keep = (r >> 8) * (1.0f / 16777216.0f) >= p;
-  float* v = X + m * (long long)ld + col0 + c;
-  *v = keep ? *v / (1.f - p) : 0.f;
+  T* v = X + m * (long long)ld + col0 + c;
+  *v = from_f32<T>(keep ? to_f32<T>(*v) / (1.f - p) : 0.f);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -406,18 +419,111 @@ static int slabs_for(long long rows, int* rows_per_slab) {
 }
 
 // column sums ACCUMULATED into out[j * out_stride + c] (the caller zeroes it): the walker keeps one (sum, sum^2)
-// table per concat buffer and adds each layer's 32 new channels to it
-int colsums_into(int mode, const float* X, int ldx, int xcol0, const float* D, int ldd, int dcol0, const float* fold, int C,
-                 long long m_total, int ring_hp, int ring_wp, double* out, int out_stride, cudaStream_t stream) {
+// table per concat buffer and adds each layer's 32 new channels to it.  x_bf16 / d_bf16: element types of X / D.
+int colsums_typed(int mode, const void* X, bool x_bf16, int ldx, int xcol0, const void* D, bool d_bf16, int ldd, int dcol0,
+                  const float* fold, int fold_stride, int C, long long m_total, int ring_hp, int ring_wp, double* out,
+                  int out_stride, cudaStream_t stream) {
   if (m_total <= 0 || C <= 0) return TCVN_OK;
   ColDev p{};
-  p.X = X; p.ldx = ldx; p.xcol0 = xcol0; p.D = D; p.ldd = ldd; p.dcol0 = dcol0; p.fold = fold; p.C = C;
-  p.m_total = m_total; p.Hp = ring_hp; p.Wp = ring_wp; p.out = out; p.out_stride = out_stride;
+  p.X = X; p.ldx = ldx; p.xcol0 = xcol0; p.D = D; p.ldd = ldd; p.dcol0 = dcol0; p.fold = fold; p.fold_stride = fold_stride;
+  p.C = C; p.m_total = m_total; p.Hp = ring_hp; p.Wp = ring_wp; p.out = out; p.out_stride = out_stride;
   const int slabs = slabs_for(m_total, &p.rows_per_slab);
   dim3 grid(ceil_div(C, 32), slabs);
-  if (mode == 0) colsum_kernel<0><<<grid, 256, 0, stream>>>(p);
-  else if (mode == 1) colsum_kernel<1><<<grid, 256, 0, stream>>>(p);
-  else colsum_kernel<2><<<grid, 256, 0, stream>>>(p);
+  typedef __nv_bfloat16 bf;
+#define TCVN_COLSUM(MODE)                                                                          \
+  do {                                                                                             \
+    if (!x_bf16 && !d_bf16) colsum_kernel<MODE, float, float><<<grid, 256, 0, stream>>>(p);         \
+    else if (x_bf16 && d_bf16) colsum_kernel<MODE, bf, bf><<<grid, 256, 0, stream>>>(p);            \
+    else if (x_bf16) colsum_kernel<MODE, bf, float><<<grid, 256, 0, stream>>>(p);                   \
+    else colsum_kernel<MODE, float, bf><<<grid, 256, 0, stream>>>(p);                               \
+  } while (0)
+  if (mode == 0) TCVN_COLSUM(0);
+  else if (mode == 1) TCVN_COLSUM(1);
+  else TCVN_COLSUM(2);
+#undef TCVN_COLSUM
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+int colsums_into(int mode, const float* X, int ldx, int xcol0, const float* D, int ldd, int dcol0, const float* fold, int C,
+                 long long m_total, int ring_hp, int ring_wp, double* out, int out_stride, cudaStream_t stream) {
+  return colsums_typed(mode, X, false, ldx, xcol0, D, false, ldd, dcol0, fold, C, C, m_total, ring_hp, ring_wp, out, out_stride,
+                       stream);
+}
+
+// dX (+)= BN + PReLU backward of D at X (elementwise half); types: 0 = fp32, 1 = bf16
+int bnact_bwd_apply_typed(const void* D, bool d_bf16, int ldd, int dcol0, const void* X, bool x_bf16, int ldx, int xcol0,
+                          const float* fold, int fold_stride, const double* sums, int C, double count, void* dX, bool o_bf16,
+                          int lddx, int dxcol0, bool accumulate, long long m_total, int ring_hp, int ring_wp,
+                          cudaStream_t stream) {
+  if (m_total <= 0 || C <= 0) return TCVN_OK;
+  BnBwdDev p{};
+  p.D = D; p.ldd = ldd; p.dcol0 = dcol0; p.X = X; p.ldx = ldx; p.xcol0 = xcol0; p.fold = fold; p.fold_stride = fold_stride;
+  p.sums = sums; p.C = C; p.count = count; p.dX = dX; p.lddx = lddx; p.dxcol0 = dxcol0; p.accumulate = accumulate ? 1 : 0;
+  p.m_total = m_total; p.Hp = ring_hp; p.Wp = ring_wp;
+  const unsigned grid = (unsigned)ceil_div_ll(m_total * C, 256);
+  typedef __nv_bfloat16 bf;
+  if (!x_bf16 && !d_bf16 && !o_bf16) bnact_bwd_apply_kernel<float, float, float><<<grid, 256, 0, stream>>>(p);
+  else if (x_bf16 && d_bf16 && o_bf16) bnact_bwd_apply_kernel<bf, bf, bf><<<grid, 256, 0, stream>>>(p);
+  else if (x_bf16 && d_bf16 && !o_bf16) bnact_bwd_apply_kernel<bf, bf, float><<<grid, 256, 0, stream>>>(p);
+  else return fail(TCVN_ERR_UNSUPPORTED, "bnact_bwd_apply: type combination not instantiated");
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+int bnact_fwd_typed(const void* X, bool x_bf16, int ldx, int xcol0, const float* fold, int fold_stride, int C, long long m_total,
+                    int ring_hp, int ring_wp, void* out, bool o_bf16, int ldo, int ocol0, cudaStream_t stream) {
+  if (m_total <= 0 || C <= 0) return TCVN_OK;
+  const unsigned grid = (unsigned)ceil_div_ll(m_total * C, 256);
+  typedef __nv_bfloat16 bf;
+  if (!x_bf16 && !o_bf16)
+    bnact_fwd_kernel<float, float><<<grid, 256, 0, stream>>>(static_cast<const float*>(X), ldx, xcol0, fold, fold_stride, C, m_total,
+                                                             ring_hp, ring_wp, static_cast<float*>(out), ldo, ocol0);
+  else if (x_bf16 && o_bf16)
+    bnact_fwd_kernel<bf, bf><<<grid, 256, 0, stream>>>(static_cast<const bf*>(X), ldx, xcol0, fold, fold_stride, C, m_total, ring_hp,
+                                                       ring_wp, static_cast<bf*>(out), ldo, ocol0);
+  else return fail(TCVN_ERR_UNSUPPORTED, "bnact_fwd: type combination not instantiated");
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+// kinds as tcvn_t_pool; bf16 = element type of the ringed block-side buffers (the stem map z0 and dGap stay fp32)
+int pool_typed(int kind, const void* src, const float* fold, void* dst, bool bf16, int n, int C, int H, int W, int H2, int W2,
+               int ld, cudaStream_t stream) {
+  if (n <= 0) return TCVN_OK;
+  typedef __nv_bfloat16 bf;
+  long long total;
+  switch (kind) {
+    case 0:
+      total = (long long)n * H * W * C;
+      if (bf16) stem_pool_fwd_kernel<bf><<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const float*>(src), fold, H2, W2, C, static_cast<bf*>(dst), ld, H, W, total);
+      else stem_pool_fwd_kernel<float><<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const float*>(src), fold, H2, W2, C, static_cast<float*>(dst), ld, H, W, total);
+      break;
+    case 1:   // gradient buffers of a block are fp32 in both precisions
+      total = (long long)n * H2 * W2 * C;
+      stem_pool_bwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const float*>(src), ld, H, W, C, static_cast<float*>(dst), H2, W2, total);
+      break;
+    case 2:
+      total = (long long)n * (H + 2) * (W + 2) * C;
+      if (bf16) pool2_bwd_kernel<bf><<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const bf*>(src), H2, W2, C, static_cast<bf*>(dst), H, W, total);
+      else pool2_bwd_kernel<float><<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const float*>(src), H2, W2, C, static_cast<float*>(dst), H, W, total);
+      break;
+    default:
+      total = (long long)n * (H + 2) * (W + 2) * C;
+      if (bf16) gap_bwd_kernel<bf><<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const float*>(src), C, static_cast<bf*>(dst), H, W, total);
+      else gap_bwd_kernel<float><<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const float*>(src), C, static_cast<float*>(dst), H, W, total);
+      break;
+  }
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+int dropout_typed(void* X, bool bf16, int ld, int col0, int C, long long m_total, uint64_t seed, uint64_t stream_id, float p,
+                  cudaStream_t stream) {
+  if (p == 0.f || m_total <= 0) return TCVN_OK;
+  const unsigned grid = (unsigned)ceil_div_ll(m_total * C, 256);
+  if (bf16) dropout_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<__nv_bfloat16*>(X), ld, col0, C, m_total, seed, stream_id, p);
+  else dropout_kernel<float><<<grid, 256, 0, stream>>>(static_cast<float*>(X), ld, col0, C, m_total, seed, stream_id, p);
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
 }
@@ -442,23 +548,37 @@ extern "C" int tcvn_t_gemm(const float* A, int lda, int64_t m_total, int K, int 
   return launch_simt_gemm(g, stream);
 }
 
-extern "C" int tcvn_t_wgrad(const float* A, int lda, int64_t m_total, int K, int taps, const int32_t* tap_off,
-                            const float* a_fold, int a_ring_hp, int a_ring_wp, const float* G, int ldg, int g_col0, int N,
-                            int g_ring_hp, int g_ring_wp, float* dW, tcvn_stream_t stream) {
-  TCVN_CHECK_ARG(A && G && dW && taps >= 1 && taps <= 9 && (taps == 1 || tap_off), "t_wgrad: bad arguments");
+namespace tcvn {
+int wgrad_typed(const void* A, bool a_bf16, int lda, long long m_total, int K, int taps, const int* tap_off, const float* a_scale,
+                const float* a_shift, const float* a_alpha, int a_ring_hp, int a_ring_wp, const void* G, bool g_bf16, int ldg,
+                int g_col0, int N, int g_ring_hp, int g_ring_wp, float* dW, cudaStream_t stream) {
   if (m_total <= 0) return TCVN_OK;
   WgradDev g{};
   g.A = A; g.lda = lda; g.m_total = m_total; g.K = K; g.taps = taps;
   for (int t = 0; t < taps; ++t) g.tap_off[t] = tap_off ? tap_off[t] : 0;
-  if (a_fold) { g.a_scale = a_fold; g.a_shift = a_fold + K; g.a_alpha = a_fold + 2 * K; }
+  g.a_scale = a_scale; g.a_shift = a_shift; g.a_alpha = a_alpha;
   g.a_ring_Hp = a_ring_hp; g.a_ring_Wp = a_ring_wp;
   g.G = G; g.ldg = ldg; g.g_col0 = g_col0; g.N = N; g.g_ring_Hp = g_ring_hp; g.g_ring_Wp = g_ring_wp;
   g.dW = dW;
   const int slabs = slabs_for(m_total, &g.rows_per_slab);
   dim3 grid(ceil_div(K, kWgK), ceil_div(N, kWgN) * taps, slabs);
-  wgrad_kernel<<<grid, 256, 0, stream>>>(g);
+  typedef __nv_bfloat16 bf;
+  if (!a_bf16 && !g_bf16) wgrad_kernel<float, float><<<grid, 256, 0, stream>>>(g);
+  else if (a_bf16 && g_bf16) wgrad_kernel<bf, bf><<<grid, 256, 0, stream>>>(g);
+  else if (a_bf16) wgrad_kernel<bf, float><<<grid, 256, 0, stream>>>(g);
+  else wgrad_kernel<float, bf><<<grid, 256, 0, stream>>>(g);
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
+}
+}  // namespace tcvn
+
+extern "C" int tcvn_t_wgrad(const float* A, int lda, int64_t m_total, int K, int taps, const int32_t* tap_off,
+                            const float* a_fold, int a_ring_hp, int a_ring_wp, const float* G, int ldg, int g_col0, int N,
+                            int g_ring_hp, int g_ring_wp, float* dW, tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(A && G && dW && taps >= 1 && taps <= 9 && (taps == 1 || tap_off), "t_wgrad: bad arguments");
+  return wgrad_typed(A, false, lda, m_total, K, taps, tap_off, a_fold, a_fold ? a_fold + K : nullptr,
+                     a_fold ? a_fold + 2 * K : nullptr, a_ring_hp, a_ring_wp, G, false, ldg, g_col0, N, g_ring_hp, g_ring_wp, dW,
+                     stream);
 }
 
 // mode 0: sums[2][C] = (sum x, sum x^2); mode 1: sums[3][C] BN+PReLU backward reductions; mode 2: sums[1][C] = sum x.
@@ -487,14 +607,8 @@ extern "C" int tcvn_t_bnact_bwd_apply(const float* D, int ldd, int dcol0, const 
                                       int dxcol0, int accumulate, int64_t m_total, int ring_hp, int ring_wp, float* dgamma,
                                       float* dbeta, float* dalpha, tcvn_stream_t stream) {
   TCVN_CHECK_ARG(D && X && fold && sums && count > 0, "t_bnact_bwd_apply: bad arguments");
-  if (dX && m_total > 0) {
-    BnBwdDev p{};
-    p.D = D; p.ldd = ldd; p.dcol0 = dcol0; p.X = X; p.ldx = ldx; p.xcol0 = xcol0; p.fold = fold; p.sums = sums; p.C = C;
-    p.count = count; p.dX = dX; p.lddx = lddx; p.dxcol0 = dxcol0; p.accumulate = accumulate; p.m_total = m_total;
-    p.Hp = ring_hp; p.Wp = ring_wp;
-    bnact_bwd_apply_kernel<<<(unsigned)ceil_div_ll(m_total * C, 256), 256, 0, stream>>>(p);
-    TCVN_LAUNCH_CHECK();
-  }
+  if (dX) TCVN_TRY(bnact_bwd_apply_typed(D, false, ldd, dcol0, X, false, ldx, xcol0, fold, C, sums, C, count, dX, false, lddx, dxcol0,
+                                         accumulate != 0, m_total, ring_hp, ring_wp, stream));
   if (dgamma || dbeta || dalpha) {
     bnact_param_grads_kernel<<<ceil_div(C, 128), 128, 0, stream>>>(sums, C, dgamma, dbeta, dalpha);
     TCVN_LAUNCH_CHECK();
@@ -512,11 +626,7 @@ extern "C" int tcvn_t_add_colsums(const double* sums, int C, float* dst, tcvn_st
 extern "C" int tcvn_t_bnact_fwd(const float* X, int ldx, int xcol0, const float* fold, int C, int64_t m_total, int ring_hp,
                                 int ring_wp, float* out, int ldo, int ocol0, tcvn_stream_t stream) {
   TCVN_CHECK_ARG(X && fold && out, "t_bnact_fwd: null pointer");
-  if (m_total <= 0) return TCVN_OK;
-  bnact_fwd_kernel<<<(unsigned)ceil_div_ll(m_total * C, 256), 256, 0, stream>>>(X, ldx, xcol0, fold, C, m_total, ring_hp,
-                                                                                ring_wp, out, ldo, ocol0);
-  TCVN_LAUNCH_CHECK();
-  return TCVN_OK;
+  return bnact_fwd_typed(X, false, ldx, xcol0, fold, C, C, m_total, ring_hp, ring_wp, out, false, ldo, ocol0, stream);
 }
 
 // kind 0: stem pool fwd (src = z0 [n,Hs,Ws,C], fold; dst = ringed blk, ld);  kind 1: stem pool bwd (src = d blk, ld; dst = dA
@@ -525,37 +635,13 @@ extern "C" int tcvn_t_bnact_fwd(const float* X, int ldx, int xcol0, const float*
 extern "C" int tcvn_t_pool(int kind, const float* src, const float* fold, float* dst, int n, int C, int H, int W, int H2,
                            int W2, int ld, tcvn_stream_t stream) {
   TCVN_CHECK_ARG(src && dst && kind >= 0 && kind <= 3, "t_pool: bad arguments");
-  if (n <= 0) return TCVN_OK;
-  long long total;
-  switch (kind) {
-    case 0:  // H,W = pooled size; H2,W2 = stem conv size
-      total = (long long)n * H * W * C;
-      stem_pool_fwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(src, fold, H2, W2, C, dst, ld, H, W, total);
-      break;
-    case 1:
-      total = (long long)n * H2 * W2 * C;
-      stem_pool_bwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(src, ld, H, W, C, dst, H2, W2, total);
-      break;
-    case 2:
-      total = (long long)n * (H + 2) * (W + 2) * C;
-      pool2_bwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(src, H2, W2, C, dst, H, W, total);
-      break;
-    default:
-      total = (long long)n * (H + 2) * (W + 2) * C;
-      gap_bwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(src, C, dst, H, W, total);
-      break;
-  }
-  TCVN_LAUNCH_CHECK();
-  return TCVN_OK;
+  return pool_typed(kind, src, fold, dst, false, n, C, H, W, H2, W2, ld, stream);
 }
 
 extern "C" int tcvn_t_dropout(float* X, int ld, int col0, int C, int64_t m_total, uint64_t seed, uint64_t stream_id, float p,
                               tcvn_stream_t stream) {
   TCVN_CHECK_ARG(X && p >= 0.f && p < 1.f, "t_dropout: bad arguments");
-  if (p == 0.f || m_total <= 0) return TCVN_OK;
-  dropout_kernel<<<(unsigned)ceil_div_ll(m_total * C, 256), 256, 0, stream>>>(X, ld, col0, C, m_total, seed, stream_id, p);
-  TCVN_LAUNCH_CHECK();
-  return TCVN_OK;
+  return dropout_typed(X, false, ld, col0, C, m_total, seed, stream_id, p, stream);
 }
 
 // forward (dz == NULL): z[n,Hs,Ws,C] = bias + conv7x7s2p3(pixels);  backward (dz != NULL): dw[cin*49][C] += x (*) dz

@@ -16,11 +16,9 @@
 // order); slots of the running buffers are left untouched.
 #include "kernels.h"
 #include "plan.h"
+#include "umma.h"
 
 namespace tcvn {
-
-int colsums_into(int mode, const float* X, int ldx, int xcol0, const float* D, int ldd, int dcol0, const float* fold, int C,
-                 long long m_total, int ring_hp, int ring_wp, double* out, int out_stride, cudaStream_t stream);
 
 namespace {
 
@@ -418,23 +416,475 @@ struct TWalk {
   }
 };
 
+
+// =================================================================================================
+// bf16 training walk: activations (concat buffers, bottleneck maps) in bf16, every convolution of the dense
+// blocks and transitions on tcgen05 (forward: umma.cu kernels with batch-statistics folds; backward: conv2 input
+// gradient + MN-major weight-gradient kernels of umma_train.cu, conv1 / transition input gradients through the
+// plain K-major GEMM).  Gradients of the concat buffers stay fp32 (they are accumulated across up to 12 layers);
+// statistics, folds and all parameter gradients are fp32/fp64 as in the fp32 walk.  The stem and the tail (<3 % of
+// the FLOPs) run the fp32 kernels.
+// =================================================================================================
+typedef __nv_bfloat16 bf;
+
+struct T16Layer { size_t w1b, w1d, w2b, wd, fold1, fold2, mid_raw, mid_act; };
+struct T16Block {
+  size_t blk, gblk, sums, fold_t, pooled, wtb, wtd, tb16;
+  int gt_pitch;
+  std::vector<T16Layer> layers;
+};
+
+struct TrainPlan16 {
+  CnnPlan P;
+  int n;
+  size_t w0, z0, fold0, fold_f, gap, dgap, lin, fold_o, lw, lwt;
+  std::vector<T16Block> blocks;
+  size_t sA, sB, dmid, g2x, gt, dz0, sums_scr, dwp, zeros, ones;
+  size_t bytes;
+
+  static bool build(const tcvn_cnn_desc& d, int n, TrainPlan16* T) {
+    if (!CnnPlan::build(d, TCVN_BF16, n, &T->P)) return false;
+    const CnnPlan& P = T->P;
+    if (P.mid != 128 || d.growth != 32) return false;   // the tcgen05 kernels are specialised for 128 / 32
+    T->n = n;
+    size_t w = 0;
+    auto take = [&](size_t bytes) { size_t o = w; w += (bytes + 1023) / 1024 * 1024; return o; };
+    const size_t N = (size_t)(n < 1 ? 1 : n);
+    const int C0 = d.init_features, mid = P.mid, g = d.growth;
+    T->w0 = take((size_t)d.in_channels * 49 * C0 * 4);
+    T->z0 = take(N * P.Hs * P.Ws * C0 * 4);
+    T->fold0 = take(5 * C0 * 4);
+    size_t max_rc = 0, max_rows = 0, max_gt = 0, max_dw = (size_t)d.in_channels * 49 * C0;
+    int max_c = C0 > d.out_features ? C0 : d.out_features;
+    if (mid > max_c) max_c = mid;
+    T->blocks.clear();
+    for (size_t b = 0; b < P.blocks.size(); ++b) {
+      const BlockPlan& B = P.blocks[b];
+      T16Block X;
+      const size_t rows = N * B.R;
+      X.blk = take(rows * B.ctot * 2);
+      X.gblk = take(rows * B.ctot * 4);
+      X.sums = take(2 * (size_t)B.ctot * 8);
+      if (rows * B.ctot > max_rc) max_rc = rows * B.ctot;
+      if (rows > max_rows) max_rows = rows;
+      if (B.ctot > max_c) max_c = B.ctot;
+      for (const LayerPlan& L : B.layers) {
+        T16Layer Y;
+        Y.w1b = take((size_t)mid * L.kpad * 2);
+        Y.w1d = take((size_t)L.kphys * mid * 2);
+        Y.w2b = take((size_t)9 * g * mid * 2);
+        Y.wd = take((size_t)3 * 128 * 128 * 2);
+        Y.fold1 = take(5 * (size_t)L.kpad * 4);
+        Y.fold2 = take(5 * (size_t)mid * 4);
+        Y.mid_raw = take(rows * mid * 2);
+        Y.mid_act = take(rows * mid * 2);
+        X.layers.push_back(Y);
+      }
+      X.fold_t = X.pooled = X.wtb = X.wtd = X.tb16 = 0;
+      X.gt_pitch = 0;
+      if (B.has_transition) {
+        const BlockPlan& Nx = P.blocks[b + 1];
+        X.gt_pitch = round_up(B.toutp, 64);
+        X.fold_t = take(5 * (size_t)B.ctot * 4);
+        X.pooled = take(N * Nx.R * B.ctot * 2);
+        X.wtb = take((size_t)B.tn_tiles * 128 * B.tkpad * 2);
+        X.wtd = take((size_t)B.ctot * X.gt_pitch * 2);
+        X.tb16 = take((size_t)B.tn_tiles * 128 * 4);
+        if ((size_t)B.ctot * B.toutp > max_dw) max_dw = (size_t)B.ctot * B.toutp;
+        if (N * Nx.R * X.gt_pitch > max_gt) max_gt = N * Nx.R * X.gt_pitch;
+        if (N * Nx.R * B.ctot > max_rc) max_rc = N * Nx.R * B.ctot;
+      }
+      T->blocks.push_back(X);
+    }
+    const BlockPlan& last = P.blocks.back();
+    T->fold_f = take(5 * (size_t)last.ctot * 4);
+    T->gap = take(N * last.ctot * 4);
+    T->dgap = take(N * last.ctot * 4);
+    T->lin = take(N * d.out_features * 4);
+    T->fold_o = take(5 * (size_t)d.out_features * 4);
+    T->lw = take((size_t)last.ctot * d.out_features * 4);
+    T->lwt = take((size_t)last.ctot * d.out_features * 4);
+    if ((size_t)last.ctot * d.out_features > max_dw) max_dw = (size_t)last.ctot * d.out_features;
+    if ((size_t)4 * 128 * 128 > max_dw) max_dw = (size_t)4 * 128 * 128;
+    T->sA = take(max_rc * 2);
+    T->sB = take(max_rc * 2);
+    T->dmid = take(max_rows * mid * 2);
+    T->g2x = take(max_rows * 128 * 2);
+    T->gt = take((max_gt ? max_gt : 1) * 2);
+    T->dz0 = take(N * P.Hs * P.Ws * C0 * 4);
+    T->sums_scr = take(3 * (size_t)max_c * 8);
+    T->dwp = take(max_dw * 4);
+    T->zeros = take(1024 * 4);
+    T->ones = take(1024 * 4);
+    T->bytes = w;
+    return true;
+  }
+};
+
+__device__ __forceinline__ bool drop_keep16(unsigned long long seed, unsigned long long stream_id, unsigned long long idx,
+                                            float p) {
+  unsigned long long z = seed * 0x100000001b3ull + stream_id * 0x9e3779b97f4a7c15ull + idx;
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  const uint32_t r = (uint32_t)((z ^ (z >> 31)) >> 32);
+  return (r >> 8) * (1.0f / 16777216.0f) >= p;
+}
+
+// G2x[m] = [ G[m+1] | G[m] | G[m-1] | 0 ] (4 x 32 bf16) from the fp32 gradient slice of a layer's 32 output channels,
+// with the layer's dropout mask applied (same (seed, site, element) hash as the forward pass)
+__global__ void g2x_kernel(const float* __restrict__ gblk, int ld, int col0, long long rows, int Hp, int Wp,
+                           unsigned long long seed, unsigned long long stream_id, float p, bf* __restrict__ g2x) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * 32) return;
+  const int c = (int)(idx & 31);
+  const long long m = idx >> 5;
+  const int rr = (int)(m % ((long long)Hp * Wp));
+  const int y = rr / Wp, x = rr - y * Wp;
+  float v = 0.f;
+  if (!(y == 0 || y == Hp - 1 || x == 0 || x == Wp - 1)) {
+    v = gblk[m * (long long)ld + col0 + c];
+    if (p > 0.f) v = drop_keep16(seed, stream_id, (unsigned long long)idx, p) ? v / (1.f - p) : 0.f;
+  }
+  const bf h = __float2bfloat16_rn(v);
+  const bf z = __float2bfloat16_rn(0.f);
+  g2x[m * 128 + 32 + c] = h;
+  g2x[m * 128 + 96 + c] = z;
+  if (m > 0) g2x[(m - 1) * 128 + c] = h;
+  else g2x[64 + c] = z;
+  if (m + 1 < rows) g2x[(m + 1) * 128 + 64 + c] = h;
+  else g2x[m * 128 + c] = z;
+}
+
+// fp32 gradient columns [0, cols) -> bf16 [rows][pitch], zero padded
+__global__ void to_bf16_pad_kernel(const float* __restrict__ src, int ld, int cols, long long rows, int pitch, bf* __restrict__ dst) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * pitch) return;
+  const int c = (int)(idx % pitch);
+  const long long m = idx / pitch;
+  dst[idx] = __float2bfloat16_rn(c < cols ? src[m * (long long)ld + c] : 0.f);
+}
+
+// conv2 weight [32][128][3][3] -> Wd[dy][c][dx*32 + n] bf16 (columns 96.. zero): the operand of the input-gradient GEMM
+__global__ void pack_wd_kernel(const float* __restrict__ w2, bf* __restrict__ wd) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 3 * 128 * 128) return;
+  const int col = idx & 127, c = (idx >> 7) & 127, dy = idx >> 14;
+  float v = 0.f;
+  if (col < 96) {
+    const int dx = col >> 5, n = col & 31;
+    v = w2[((n * 128 + c) * 3 + dy) * 3 + dx];
+  }
+  wd[idx] = __float2bfloat16_rn(v);
+}
+
+// conv2 weight gradient from the tensor-core layout dw[dy][k][dx*32 + n] -> += reference layout [n][k][dy][dx]
+__global__ void unpack_conv2_grad_kernel(const float* __restrict__ dw, float* __restrict__ dst) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 32 * 128 * 9) return;
+  const int t = idx % 9, k = (idx / 9) & 127, n = idx / (9 * 128);
+  const int dy = t / 3, dx = t - dy * 3;
+  dst[idx] += dw[(dy * 128 + k) * 128 + dx * 32 + n];
+}
+
+__global__ void fill_f32_kernel(float* dst, int n, float v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = v;
+}
+
+struct TWalk16 {
+  const TrainPlan16& T;
+  float* arena;
+  float* garena;
+  char* ws;
+  cudaStream_t st;
+  float p_drop, momentum;
+  uint64_t seed, site;
+
+  float* f(size_t off) const { return reinterpret_cast<float*>(ws + off); }
+  bf* h(size_t off) const { return reinterpret_cast<bf*>(ws + off); }
+  double* dbl(size_t off) const { return reinterpret_cast<double*>(ws + off); }
+
+  int finalize(const double* s1, const double* s2, int n_out, const BnArena& bn, int c0, int c0p, double count, float* fold) {
+    FinArgs a;
+    a.s1 = s1; a.s2 = s2; a.n_out = n_out; a.c_log = bn.c; a.c0 = c0; a.c0p = c0p; a.count = count;
+    a.gamma = arena + bn.w; a.beta = arena + bn.b; a.alpha = arena + bn.alpha;
+    a.eps = T.P.d.bn_eps; a.momentum = momentum;
+    a.rm = arena + bn.rm; a.rv = arena + bn.rv;
+    a.fold = fold;
+    bn_finalize_map_kernel<<<ceil_div(n_out, 128), 128, 0, st>>>(a);
+    TCVN_LAUNCH_CHECK();
+    return TCVN_OK;
+  }
+
+  int stats_scratch(const void* X, bool x_bf16, int ldx, int col0, int C, long long rows, int hp, int wp) {
+    TCVN_CUDA(cudaMemsetAsync(dbl(T.sums_scr), 0, sizeof(double) * 2 * C, st));
+    return colsums_typed(0, X, x_bf16, ldx, col0, nullptr, false, 0, 0, nullptr, 0, C, rows, hp, wp, dbl(T.sums_scr), C, st);
+  }
+
+  int bias_grad(const void* G, bool g_bf16, int ldg, int col0, int C, long long rows, int hp, int wp, float* dst) {
+    TCVN_CUDA(cudaMemsetAsync(dbl(T.sums_scr), 0, sizeof(double) * C, st));
+    TCVN_TRY(colsums_typed(2, G, g_bf16, ldg, col0, nullptr, false, 0, 0, nullptr, 0, C, rows, hp, wp, dbl(T.sums_scr), C, st));
+    add_sums_kernel<<<ceil_div(C, 128), 128, 0, st>>>(dbl(T.sums_scr), C, dst);
+    TCVN_LAUNCH_CHECK();
+    return TCVN_OK;
+  }
+
+  int bn_bwd(const void* X, bool x_bf16, int ldx, const void* D, bool d_bf16, int ldd, const float* fold, int fold_stride, int C,
+             double count, long long rows, int hp, int wp, void* dX, bool o_bf16, int lddx, bool accumulate, const BnArena& bn,
+             int c0, int c0p) {
+    double* s = dbl(T.sums_scr);
+    TCVN_CUDA(cudaMemsetAsync(s, 0, sizeof(double) * 3 * C, st));
+    TCVN_TRY(colsums_typed(1, X, x_bf16, ldx, 0, D, d_bf16, ldd, 0, fold, fold_stride, C, rows, hp, wp, s, C, st));
+    TCVN_TRY(bnact_bwd_apply_typed(D, d_bf16, ldd, 0, X, x_bf16, ldx, 0, fold, fold_stride, s, C, count, dX, o_bf16, lddx, 0,
+                                   accumulate, rows, hp, wp, st));
+    bn_param_grads_map_kernel<<<ceil_div(bn.c, 128), 128, 0, st>>>(s, C, bn.c, c0, c0p, garena + bn.w, garena + bn.b,
+                                                                   garena + bn.alpha);
+    TCVN_LAUNCH_CHECK();
+    return TCVN_OK;
+  }
+
+  int gemm32(const float* A, int lda, long long rows, int K, const float* W, int N, const float* bias, float* out, int ldo) {
+    return tcvn_t_gemm(A, lda, rows, K, 1, nullptr, W, N, nullptr, 0, 0, bias, out, ldo, 0, 0, 0, 0, st);
+  }
+
+  int pack() {
+    const CnnPlan& P = T.P;
+    const tcvn_cnn_desc& d = P.d;
+    const int mid = P.mid, g = d.growth;
+    TCVN_TRY(repack(arena + P.conv0_w, d.init_features, d.in_channels * 49, 1, NOGAP, NOGAP, d.in_channels * 49,
+                    d.init_features, false, false, f(T.w0), st));
+    for (size_t b = 0; b < P.blocks.size(); ++b) {
+      const BlockPlan& B = P.blocks[b];
+      const T16Block& X = T.blocks[b];
+      for (size_t i = 0; i < B.layers.size(); ++i) {
+        const LayerPlan& L = B.layers[i];
+        const T16Layer& Y = X.layers[i];
+        TCVN_TRY(repack(arena + L.conv1_w, mid, L.cin, 1, B.c0, B.c0p, L.kpad, mid, true, true, h(Y.w1b), st));
+        TCVN_TRY(repack(arena + L.conv1_w, mid, L.cin, 1, B.c0, B.c0p, L.kphys, mid, false, true, h(Y.w1d), st));
+        TCVN_TRY(repack(arena + L.conv2_w, g, mid, 9, NOGAP, NOGAP, mid, g, true, true, h(Y.w2b), st));
+        pack_wd_kernel<<<ceil_div(3 * 128 * 128, 256), 256, 0, st>>>(arena + L.conv2_w, h(Y.wd));
+        TCVN_LAUNCH_CHECK();
+      }
+      if (B.has_transition) {
+        const int n16 = B.tn_tiles * 128;
+        TCVN_TRY(repack(arena + B.tconv_w, B.tout, B.clog, 1, B.c0, B.c0p, B.tkpad, n16, true, true, h(X.wtb), st));
+        TCVN_TRY(repack(arena + B.tconv_w, B.tout, B.clog, 1, B.c0, B.c0p, B.ctot, X.gt_pitch, false, true, h(X.wtd), st));
+        TCVN_TRY(pad_copy(arena + B.tconv_b, B.tout, f(X.tb16), n16, st));
+      }
+    }
+    const BlockPlan& last = P.blocks.back();
+    TCVN_TRY(repack(arena + P.lin_w, d.out_features, last.clog, 1, last.c0, last.c0p, last.ctot, d.out_features, false,
+                    false, f(T.lw), st));
+    TCVN_TRY(repack(arena + P.lin_w, d.out_features, last.clog, 1, last.c0, last.c0p, last.ctot, d.out_features, true,
+                    false, f(T.lwt), st));
+    fill_f32_kernel<<<4, 256, 0, st>>>(f(T.zeros), 1024, 0.f);
+    TCVN_LAUNCH_CHECK();
+    fill_f32_kernel<<<4, 256, 0, st>>>(f(T.ones), 1024, 1.f);
+    TCVN_LAUNCH_CHECK();
+    return TCVN_OK;
+  }
+
+  int forward(const float* pixels, float* emb) {
+    const CnnPlan& P = T.P;
+    const tcvn_cnn_desc& d = P.d;
+    const int n = T.n, C0 = d.init_features, mid = P.mid, g = d.growth;
+    TCVN_TRY(pack());
+    const BlockPlan& B0 = P.blocks[0];
+    const long long stem_rows = (long long)n * P.Hs * P.Ws;
+    TCVN_TRY(tcvn_t_stem_conv(pixels, n, d.in_channels, d.height, d.width, f(T.w0), arena + P.conv0_b, C0, f(T.z0), nullptr,
+                              nullptr, st));
+    TCVN_TRY(stats_scratch(f(T.z0), false, C0, 0, C0, stem_rows, 0, 0));
+    TCVN_TRY(finalize(dbl(T.sums_scr), dbl(T.sums_scr) + C0, C0, P.norm0, NOGAP, NOGAP, (double)stem_rows, f(T.fold0)));
+    TCVN_TRY(pool_typed(0, f(T.z0), f(T.fold0), h(T.blocks[0].blk), true, n, C0, B0.H, B0.W, P.Hs, P.Ws, B0.ctot, st));
+    for (size_t b = 0; b < P.blocks.size(); ++b) {
+      const BlockPlan& B = P.blocks[b];
+      const T16Block& X = T.blocks[b];
+      const long long rows = (long long)n * B.R;
+      const double count = (double)n * B.H * B.W;
+      bf* blk = h(X.blk);
+      double* s1 = dbl(X.sums);
+      double* s2 = s1 + B.ctot;
+      TCVN_CUDA(cudaMemsetAsync(s1, 0, sizeof(double) * 2 * B.ctot, st));
+      TCVN_TRY(colsums_typed(0, blk, true, B.ctot, 0, nullptr, false, 0, 0, nullptr, 0, B.c0p, rows, B.Hp, B.Wp, s1, B.ctot, st));
+      for (size_t i = 0; i < B.layers.size(); ++i) {
+        const LayerPlan& L = B.layers[i];
+        const T16Layer& Y = X.layers[i];
+        float* f1 = f(Y.fold1);
+        TCVN_TRY(finalize(s1, s2, L.kpad, L.norm1, B.c0, B.c0p, count, f1));
+        // raw conv1 output (+ bias): the BN2 statistics are taken from exactly the bf16 values conv2 will read
+        TCVN_TRY(launch_gemm(true, blk, rows, B.ctot, B.ctot, h(Y.w1b), mid, L.kpad, L.kphys, f1, f1 + L.kpad, f1 + 2 * L.kpad,
+                             arena + L.conv1_b, f(T.ones), h(Y.mid_raw), mid, mid, 1, B.Hp, B.Wp, st));
+        TCVN_TRY(stats_scratch(h(Y.mid_raw), true, mid, 0, mid, rows, B.Hp, B.Wp));
+        TCVN_TRY(finalize(dbl(T.sums_scr), dbl(T.sums_scr) + mid, mid, L.norm2, NOGAP, NOGAP, count, f(Y.fold2)));
+        TCVN_TRY(bnact_fwd_typed(h(Y.mid_raw), true, mid, 0, f(Y.fold2), mid, mid, rows, B.Hp, B.Wp, h(Y.mid_act), true, mid, 0, st));
+        TCVN_TRY(umma_conv2_fwd(h(Y.mid_act), rows, h(Y.w2b), arena + L.conv2_b, blk, B.ctot, L.kphys, B.Hp, B.Wp, B.W, st));
+        TCVN_TRY(dropout_typed(blk, true, B.ctot, L.kphys, g, rows, seed, site * 4096 + b * 64 + i, p_drop, st));
+        TCVN_TRY(colsums_typed(0, blk, true, B.ctot, L.kphys, nullptr, false, 0, 0, nullptr, 0, g, rows, B.Hp, B.Wp, s1 + L.kphys,
+                               B.ctot, st));
+      }
+      if (B.has_transition) {
+        const BlockPlan& Nx = P.blocks[b + 1];
+        float* ft = f(X.fold_t);
+        TCVN_TRY(finalize(s1, s2, B.ctot, B.tnorm, B.c0, B.c0p, count, ft));
+        TCVN_TRY(launch_act_pool2(blk, n, B.H, B.W, B.ctot, B.ctot, ft, ft + B.ctot, ft + 2 * B.ctot, h(X.pooled), Nx.H, Nx.W,
+                                  false, st));
+        TCVN_TRY(launch_gemm(false, h(X.pooled), (long long)n * Nx.R, B.ctot, B.ctot, h(X.wtb), B.tn_tiles * 128, B.tkpad, B.ctot,
+                             nullptr, nullptr, nullptr, f(X.tb16), f(T.ones), h(T.blocks[b + 1].blk), Nx.ctot, Nx.ctot,
+                             B.tn_tiles, Nx.Hp, Nx.Wp, st));
+      } else {
+        float* ff = f(T.fold_f);
+        TCVN_TRY(finalize(s1, s2, B.ctot, P.final_norm, B.c0, B.c0p, count, ff));
+        TCVN_TRY(launch_act_gap(blk, n, B.H, B.W, B.ctot, B.ctot, ff, ff + B.ctot, ff + 2 * B.ctot, f(T.gap), false, st));
+      }
+    }
+    const BlockPlan& last = P.blocks.back();
+    const int out = d.out_features;
+    TCVN_TRY(gemm32(f(T.gap), last.ctot, n, last.ctot, f(T.lw), out, nullptr, f(T.lin), out));
+    TCVN_TRY(stats_scratch(f(T.lin), false, out, 0, out, n, 0, 0));
+    TCVN_TRY(finalize(dbl(T.sums_scr), dbl(T.sums_scr) + out, out, P.out_norm, NOGAP, NOGAP, (double)n, f(T.fold_o)));
+    TCVN_TRY(tcvn_t_bnact_fwd(f(T.lin), out, 0, f(T.fold_o), out, n, 0, 0, emb, out, 0, st));
+    TCVN_TRY(tcvn_t_dropout(emb, out, 0, out, n, seed, site * 4096 + 4095, p_drop, st));
+    return TCVN_OK;
+  }
+
+  int unpack(const float* dwp, int taps, int K_phys, int N_phys, int n_log, int k_log, int c0, int c0p, float* dst) {
+    const long long total = (long long)n_log * k_log * taps;
+    unpack_grad_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(dwp, taps, K_phys, N_phys, n_log, k_log, c0, c0p, dst);
+    TCVN_LAUNCH_CHECK();
+    return TCVN_OK;
+  }
+
+  int backward(const float* pixels, float* d_emb) {
+    const CnnPlan& P = T.P;
+    const tcvn_cnn_desc& d = P.d;
+    const int n = T.n, C0 = d.init_features, mid = P.mid, g = d.growth, out = d.out_features;
+    const BlockPlan& last = P.blocks.back();
+    const int nb = (int)P.blocks.size();
+    float* dwp = f(T.dwp);
+    // ---- tail (fp32)
+    TCVN_TRY(tcvn_t_dropout(d_emb, out, 0, out, n, seed, site * 4096 + 4095, p_drop, st));
+    TCVN_TRY(bn_bwd(f(T.lin), false, out, d_emb, false, out, f(T.fold_o), out, out, (double)n, n, 0, 0, d_emb, false, out, false,
+                    P.out_norm, NOGAP, NOGAP));
+    TCVN_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)last.ctot * out, st));
+    TCVN_TRY(tcvn_t_wgrad(f(T.gap), last.ctot, n, last.ctot, 1, nullptr, nullptr, 0, 0, d_emb, out, 0, out, 0, 0, dwp, st));
+    TCVN_TRY(unpack(dwp, 1, last.ctot, out, out, last.clog, last.c0, last.c0p, garena + P.lin_w));
+    TCVN_TRY(gemm32(d_emb, out, n, out, f(T.lwt), last.ctot, nullptr, f(T.dgap), last.ctot));
+    TCVN_TRY(pool_typed(3, f(T.dgap), nullptr, h(T.sA), true, n, last.ctot, last.H, last.W, 0, 0, last.ctot, st));
+    TCVN_TRY(bn_bwd(h(T.blocks[nb - 1].blk), true, last.ctot, h(T.sA), true, last.ctot, f(T.fold_f), last.ctot, last.ctot,
+                    (double)n * last.H * last.W, (long long)n * last.R, last.Hp, last.Wp, f(T.blocks[nb - 1].gblk), false,
+                    last.ctot, false, P.final_norm, last.c0, last.c0p));
+    for (int b = nb - 1; b >= 0; --b) {
+      const BlockPlan& B = P.blocks[b];
+      const T16Block& X = T.blocks[b];
+      const long long rows = (long long)n * B.R;
+      const double count = (double)n * B.H * B.W;
+      bf* blk = h(X.blk);
+      float* gblk = f(X.gblk);
+      bf* dmid = h(T.dmid);
+      bf* g2x = h(T.g2x);
+      for (int i = (int)B.layers.size() - 1; i >= 0; --i) {
+        const LayerPlan& L = B.layers[i];
+        const T16Layer& Y = X.layers[i];
+        float* f1 = f(Y.fold1);
+        // gradient of the layer's 32 output channels (complete by now) -> bf16, dropout mask applied, 3 horizontal shifts
+        g2x_kernel<<<(unsigned)ceil_div_ll(rows * 32, 256), 256, 0, st>>>(gblk, B.ctot, L.kphys, rows, B.Hp, B.Wp, seed,
+                                                                         site * 4096 + b * 64 + i, p_drop, g2x);
+        TCVN_LAUNCH_CHECK();
+        TCVN_TRY(bias_grad(g2x, true, 128, 32, g, rows, 0, 0, garena + L.conv2_b));
+        // conv2 weight gradient: three vertical taps of the activated bottleneck map against G2x
+        {
+          const int cols[3] = {0, 0, 0}, shifts[3] = {-B.Wp, 0, B.Wp}, valid[3] = {128, 128, 128};
+          TCVN_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * 3 * 128 * 128, st));
+          TCVN_TRY(umma_wgrad(h(Y.mid_act), rows, mid, mid, 3, cols, shifts, valid, nullptr, nullptr, nullptr, 0, g2x, 128, 128, 0,
+                              dwp, st));
+          unpack_conv2_grad_kernel<<<ceil_div(32 * 128 * 9, 256), 256, 0, st>>>(dwp, garena + L.conv2_w);
+          TCVN_LAUNCH_CHECK();
+        }
+        TCVN_TRY(umma_conv2_dgrad(g2x, h(Y.wd), rows, B.Hp, B.Wp, dmid, st));
+        TCVN_TRY(bn_bwd(h(Y.mid_raw), true, mid, dmid, true, mid, f(Y.fold2), mid, mid, count, rows, B.Hp, B.Wp, dmid, true, mid,
+                        false, L.norm2, NOGAP, NOGAP));
+        TCVN_TRY(bias_grad(dmid, true, mid, 0, mid, rows, B.Hp, B.Wp, garena + L.conv1_b));
+        // conv1 weight gradient: 128-channel column blocks of the concat buffer, BN1 + PReLU1 applied in SMEM
+        {
+          const int n_items = ceil_div(L.kphys, 128);
+          int cols[4], shifts[4], valid[4];
+          for (int j = 0; j < n_items; ++j) { cols[j] = 128 * j; shifts[j] = 0; valid[j] = L.kphys - 128 * j < 128 ? L.kphys - 128 * j : 128; }
+          TCVN_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)n_items * 128 * 128, st));
+          TCVN_TRY(umma_wgrad(blk, rows, B.ctot, B.ctot, n_items, cols, shifts, valid, f1, f1 + L.kpad, f1 + 2 * L.kpad, L.kphys,
+                              dmid, mid, mid, 0, dwp, st));
+          TCVN_TRY(unpack(dwp, 1, n_items * 128, 128, mid, L.cin, B.c0, B.c0p, garena + L.conv1_w));
+        }
+        TCVN_TRY(launch_gemm(false, dmid, rows, mid, mid, h(Y.w1d), L.kphys, 128, 128, nullptr, nullptr, nullptr, f(T.zeros),
+                             f(T.ones), h(T.sA), L.kphys, L.kphys, ceil_div(L.kphys, 128), B.Hp, B.Wp, st));
+        TCVN_TRY(bn_bwd(blk, true, B.ctot, h(T.sA), true, L.kphys, f1, L.kpad, L.kphys, count, rows, B.Hp, B.Wp, gblk, false, B.ctot,
+                        true, L.norm1, B.c0, B.c0p));
+      }
+      if (b > 0) {
+        const BlockPlan& Pv = P.blocks[b - 1];
+        const T16Block& Xp = T.blocks[b - 1];
+        bf* gt = h(T.gt);
+        to_bf16_pad_kernel<<<(unsigned)ceil_div_ll(rows * Xp.gt_pitch, 256), 256, 0, st>>>(gblk, B.ctot, Pv.toutp, rows, Xp.gt_pitch, gt);
+        TCVN_LAUNCH_CHECK();
+        TCVN_TRY(bias_grad(gblk, false, B.ctot, 0, Pv.tout, rows, B.Hp, B.Wp, garena + Pv.tconv_b));
+        TCVN_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)Pv.ctot * Pv.toutp, st));
+        TCVN_TRY(wgrad_typed(h(Xp.pooled), true, Pv.ctot, rows, Pv.ctot, 1, nullptr, nullptr, nullptr, nullptr, B.Hp, B.Wp, gt, true,
+                             Xp.gt_pitch, 0, Pv.toutp, B.Hp, B.Wp, dwp, st));
+        TCVN_TRY(unpack(dwp, 1, Pv.ctot, Pv.toutp, Pv.tout, Pv.clog, Pv.c0, Pv.c0p, garena + Pv.tconv_w));
+        TCVN_TRY(launch_gemm(false, gt, rows, Xp.gt_pitch, Xp.gt_pitch, h(Xp.wtd), Pv.ctot, Xp.gt_pitch, Xp.gt_pitch, nullptr, nullptr,
+                             nullptr, f(T.zeros), f(T.ones), h(T.sA), Pv.ctot, Pv.ctot, ceil_div(Pv.ctot, 128), B.Hp, B.Wp, st));
+        TCVN_TRY(pool_typed(2, h(T.sA), nullptr, h(T.sB), true, n, Pv.ctot, Pv.H, Pv.W, B.H, B.W, Pv.ctot, st));
+        TCVN_TRY(bn_bwd(h(Xp.blk), true, Pv.ctot, h(T.sB), true, Pv.ctot, f(Xp.fold_t), Pv.ctot, Pv.ctot, (double)n * Pv.H * Pv.W,
+                        (long long)n * Pv.R, Pv.Hp, Pv.Wp, f(Xp.gblk), false, Pv.ctot, false, Pv.tnorm, Pv.c0, Pv.c0p));
+      } else {
+        const long long stem_rows = (long long)n * P.Hs * P.Ws;
+        float* dz0 = f(T.dz0);
+        TCVN_TRY(pool_typed(1, gblk, nullptr, dz0, false, n, C0, B.H, B.W, P.Hs, P.Ws, B.ctot, st));
+        TCVN_TRY(bn_bwd(f(T.z0), false, C0, dz0, false, C0, f(T.fold0), C0, C0, (double)stem_rows, stem_rows, 0, 0, dz0, false, C0,
+                        false, P.norm0, NOGAP, NOGAP));
+        TCVN_TRY(bias_grad(dz0, false, C0, 0, C0, stem_rows, 0, 0, garena + P.conv0_b));
+        const int k0 = d.in_channels * 49;
+        TCVN_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)k0 * C0, st));
+        TCVN_TRY(tcvn_t_stem_conv(pixels, n, d.in_channels, d.height, d.width, f(T.w0), nullptr, C0, nullptr, dz0, dwp, st));
+        TCVN_TRY(unpack(dwp, 1, k0, C0, C0, k0, NOGAP, NOGAP, garena + P.conv0_w));
+      }
+    }
+    return TCVN_OK;
+  }
+};
+
 }  // namespace
 }  // namespace tcvn
 
 using namespace tcvn;
 
-extern "C" size_t tcvn_cnn_train_workspace_bytes(const tcvn_cnn_desc* d, int n_images) {
+extern "C" size_t tcvn_cnn_train_workspace_bytes(const tcvn_cnn_desc* d, tcvn_precision prec, int n_images) {
+  if (!d || n_images < 0) { set_error("cnn_train: bad descriptor"); return 0; }
+  if (prec == TCVN_BF16) {
+    TrainPlan16 T;
+    if (!TrainPlan16::build(*d, n_images, &T)) { set_error("cnn_train: descriptor not supported by the bf16 training path"); return 0; }
+    return T.bytes;
+  }
   TrainPlan T;
-  if (!d || n_images < 0 || !TrainPlan::build(*d, n_images, &T)) { set_error("cnn_train: bad descriptor"); return 0; }
+  if (prec != TCVN_FP32 || !TrainPlan::build(*d, n_images, &T)) { set_error("cnn_train: bad descriptor"); return 0; }
   return T.bytes;
 }
 
-extern "C" int tcvn_cnn_train_forward(const tcvn_cnn_desc* d, float* arena, const float* pixels, int n_images, float p_drop,
-                                      float momentum, uint64_t seed, uint64_t site, float* embedding, void* workspace,
-                                      size_t workspace_bytes, tcvn_stream_t stream) {
+extern "C" int tcvn_cnn_train_forward(const tcvn_cnn_desc* d, tcvn_precision prec, float* arena, const float* pixels,
+                                      int n_images, float p_drop, float momentum, uint64_t seed, uint64_t site,
+                                      float* embedding, void* workspace, size_t workspace_bytes, tcvn_stream_t stream) {
   TCVN_CHECK_ARG(d && arena && pixels && embedding && workspace, "cnn_train_forward: null pointer");
+  TCVN_CHECK_ARG(prec == TCVN_FP32 || prec == TCVN_BF16, "cnn_train_forward: unknown precision");
   TCVN_CHECK_ARG(n_images >= 2, "cnn_train_forward: BatchNorm in train mode needs at least 2 images (got %d)", n_images);
   TCVN_CHECK_ARG(p_drop >= 0.f && p_drop < 1.f, "cnn_train_forward: dropout probability out of range");
+  if (prec == TCVN_BF16) {
+    TrainPlan16 T;
+    TCVN_CHECK_ARG(TrainPlan16::build(*d, n_images, &T), "cnn_train_forward: descriptor not supported by the bf16 path");
+    if (workspace_bytes < T.bytes)
+      return fail(TCVN_ERR_WORKSPACE, "cnn_train_forward: workspace %zu < %zu bytes", workspace_bytes, T.bytes);
+    TWalk16 w{T, arena, nullptr, static_cast<char*>(workspace), stream, p_drop, momentum, seed, site};
+    return w.forward(pixels, embedding);
+  }
   TrainPlan T;
   TCVN_CHECK_ARG(TrainPlan::build(*d, n_images, &T), "cnn_train_forward: bad descriptor");
   if (workspace_bytes < T.bytes)
@@ -443,11 +893,20 @@ extern "C" int tcvn_cnn_train_forward(const tcvn_cnn_desc* d, float* arena, cons
   return w.forward(pixels, embedding);
 }
 
-extern "C" int tcvn_cnn_train_backward(const tcvn_cnn_desc* d, const float* arena, float* grad_arena, const float* pixels,
-                                       int n_images, float p_drop, uint64_t seed, uint64_t site, float* d_embedding,
-                                       void* workspace, size_t workspace_bytes, tcvn_stream_t stream) {
+extern "C" int tcvn_cnn_train_backward(const tcvn_cnn_desc* d, tcvn_precision prec, const float* arena, float* grad_arena,
+                                       const float* pixels, int n_images, float p_drop, uint64_t seed, uint64_t site,
+                                       float* d_embedding, void* workspace, size_t workspace_bytes, tcvn_stream_t stream) {
   TCVN_CHECK_ARG(d && arena && grad_arena && pixels && d_embedding && workspace, "cnn_train_backward: null pointer");
+  TCVN_CHECK_ARG(prec == TCVN_FP32 || prec == TCVN_BF16, "cnn_train_backward: unknown precision");
   TCVN_CHECK_ARG(n_images >= 2, "cnn_train_backward: needs the state of a train-mode forward over >= 2 images");
+  if (prec == TCVN_BF16) {
+    TrainPlan16 T;
+    TCVN_CHECK_ARG(TrainPlan16::build(*d, n_images, &T), "cnn_train_backward: descriptor not supported by the bf16 path");
+    if (workspace_bytes < T.bytes)
+      return fail(TCVN_ERR_WORKSPACE, "cnn_train_backward: workspace %zu < %zu bytes", workspace_bytes, T.bytes);
+    TWalk16 w{T, const_cast<float*>(arena), grad_arena, static_cast<char*>(workspace), stream, p_drop, 0.f, seed, site};
+    return w.backward(pixels, d_embedding);
+  }
   TrainPlan T;
   TCVN_CHECK_ARG(TrainPlan::build(*d, n_images, &T), "cnn_train_backward: bad descriptor");
   if (workspace_bytes < T.bytes)

@@ -18,9 +18,6 @@
 
 namespace tcvn {
 
-int colsums_into(int mode, const float* X, int ldx, int xcol0, const float* D, int ldd, int dcol0, const float* fold, int C,
-                 long long m_total, int ring_hp, int ring_wp, double* out, int out_stride, cudaStream_t stream);
-
 namespace {
 
 constexpr int NOGAP = 1 << 30;

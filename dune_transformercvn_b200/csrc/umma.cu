@@ -568,6 +568,14 @@ int umma_dense_layer_part(const CnnPlan& P, const BlockPlan& B, const LayerPlan&
                        1, B.Hp, B.Wp, st));
   // ---- conv2
   if (!(which & 2)) return TCVN_OK;
+  return umma_conv2_fwd(mid, rows, pk + L.p_w2, pf(pk, L.p_b2), blk, B.ctot, L.kphys, B.Hp, B.Wp, B.W, st);
+}
+
+// out[:, col0 : col0+32] = conv3x3(mid) + bias over the ringed layout; mid bf16 [rows][128] activated with a zero ring,
+// w2 bf16 [9*32][128] (tap-major, K contiguous), out bf16 with pitch ldo
+int umma_conv2_fwd(const void* mid, long long rows, const void* w2, const float* bias, void* out, int ldo, int col0, int Hp,
+                   int Wp, int W, cudaStream_t st) {
+  if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one chunk");
   const int tiles = (int)ceil_div_ll(rows, kC2Out);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   const int halo_rows_max = 288;
@@ -578,19 +586,19 @@ int umma_dense_layer_part(const CnnPlan& P, const BlockPlan& B, const LayerPlan&
     attr_done = true;
   }
   Conv2Params c2;
-  c2.m_total = rows; c2.Hp = B.Hp; c2.Wp = B.Wp;
-  c2.nbox = ceil_div(kTileM + 2 * B.Wp, kBoxRows);
+  c2.m_total = rows; c2.Hp = Hp; c2.Wp = Wp;
+  c2.nbox = ceil_div(kTileM + 2 * Wp, kBoxRows);
   c2.halo_rows = c2.nbox * kBoxRows;
   if (c2.halo_rows > halo_rows_max)
-    return fail(TCVN_ERR_UNSUPPORTED, "feature map width %d needs a %d-row halo tile (max %d)", B.W, c2.halo_rows, halo_rows_max);
-  c2.bias = pf(pk, L.p_b2);
-  c2.out = static_cast<bf16*>(blk); c2.ldo = B.ctot; c2.col0 = L.kphys; c2.num_tiles = tiles;
+    return fail(TCVN_ERR_UNSUPPORTED, "feature map width %d needs a %d-row halo tile (max %d)", W, c2.halo_rows, halo_rows_max);
+  c2.bias = bias;
+  c2.out = static_cast<bf16*>(out); c2.ldo = ldo; c2.col0 = col0; c2.num_tiles = tiles;
   // Measured on B200: the 128B swizzle of a UMMA operand is a function of the absolute shared-memory address
   // (bits [4,7) ^= bits [7,10)), exactly as TMA wrote it, so a descriptor may start at ANY row of the haloed
   // tile with matrix-base-offset 0 (setting it to (addr >> 7) & 7 gives wrong results).
   CUtensorMap tmM, tmW2;
   TCVN_TRY(make_map(mid, rows, kMid, kMid, 64, kBoxRows, &tmM));
-  TCVN_TRY(make_map(pk + L.p_w2, 9 * kGrowth, kMid, kMid, 64, kC2N, &tmW2));
+  TCVN_TRY(make_map(w2, 9 * kGrowth, kMid, kMid, 64, kC2N, &tmW2));
   const size_t smem2 = 1024 + kW2Bytes + (size_t)kC2Stages * 2 * c2.halo_rows * 128 + 1536;
   umma_conv2_kernel<<<grid, kC2Threads, smem2, st>>>(tmM, tmW2, c2);
   TCVN_LAUNCH_CHECK();

@@ -109,10 +109,10 @@ def load() -> C.CDLL:
     lib.tcvn_adamw_step.argtypes = [vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i64, vp, f32, f32, vp, i32, vp]
     lib.tcvn_t_umma_wgrad.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp, vp]
     lib.tcvn_t_umma_conv2_dgrad.argtypes = [vp, vp, i64, i32, i32, vp, vp]
-    lib.tcvn_cnn_train_workspace_bytes.argtypes = [C.POINTER(CnnDesc), i32]
+    lib.tcvn_cnn_train_workspace_bytes.argtypes = [C.POINTER(CnnDesc), i32, i32]
     lib.tcvn_cnn_train_workspace_bytes.restype = sz
-    lib.tcvn_cnn_train_forward.argtypes = [C.POINTER(CnnDesc), vp, vp, i32, f32, f32, u64, u64, vp, vp, sz, vp]
-    lib.tcvn_cnn_train_backward.argtypes = [C.POINTER(CnnDesc), vp, vp, vp, i32, f32, u64, u64, vp, vp, sz, vp]
+    lib.tcvn_cnn_train_forward.argtypes = [C.POINTER(CnnDesc), i32, vp, vp, i32, f32, f32, u64, u64, vp, vp, sz, vp]
+    lib.tcvn_cnn_train_backward.argtypes = [C.POINTER(CnnDesc), i32, vp, vp, vp, i32, f32, u64, u64, vp, vp, sz, vp]
     lib.tcvn_seq_train_workspace_bytes.argtypes = [C.POINTER(SeqDesc), i32, i32, i32]
     lib.tcvn_seq_train_workspace_bytes.restype = sz
     lib.tcvn_seq_train_forward.argtypes = [C.POINTER(SeqDesc), vp, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, f32, f32, u64,

@@ -196,6 +196,7 @@ class TrainEngine:
         net.engine.key = None  # running buffers (and soon the weights) change under the eval-path cache
         st = _lib.stream_ptr(dev)
         p_drop = float(net.options.dropout)
+        prec = _lib.TCVN_BF16 if net.precision == "bf16" else _lib.TCVN_FP32
         self.step_index += 1
         seed = (torch.initial_seed() * 1000003 + self.step_index) & 0xFFFFFFFFFFFF
         b, l = prong_mask.shape
@@ -209,9 +210,11 @@ class TrainEngine:
             d = self._cnn_desc(tag)
             if tuple(px.shape[1:]) != (d.in_channels, d.height, d.width):
                 raise _lib.TcvnError(f"{tag} pixels have shape {tuple(px.shape)}, expected (N,{d.in_channels},{d.height},{d.width})")
-            nbytes = L.tcvn_cnn_train_workspace_bytes(C.byref(d), n)
+            nbytes = L.tcvn_cnn_train_workspace_bytes(C.byref(d), prec, n)
+            if nbytes == 0:
+                raise _lib.TcvnError("tcvn_cnn_train_workspace_bytes: " + L.tcvn_last_error().decode())
             ws = self.workspace("cnn_" + tag, nbytes, dev)
-            _lib.check(L.tcvn_cnn_train_forward(C.byref(d), self.arena.ptr(tag), _lib.ptr(px), n, p_drop, BN_MOMENTUM, seed, site,
+            _lib.check(L.tcvn_cnn_train_forward(C.byref(d), prec, self.arena.ptr(tag), _lib.ptr(px), n, p_drop, BN_MOMENTUM, seed, site,
                                                 _lib.ptr(emb[tag]), _lib.ptr(ws), ws.numel(), st), f"tcvn_cnn_train_forward({tag})")
         sd = net.engine.seq_desc()
         pm = prong_mask.contiguous().to(torch.uint8)
@@ -233,7 +236,7 @@ class TrainEngine:
                          if name.endswith("num_batches_tracked") and not name.startswith(_NO_GRAD_PREFIXES)]
         if self._nbt:
             torch._foreach_add_(self._nbt, 1)
-        self.saved = dict(ev_px=ev_px, pr_px=pr_px, pm=pm, b=b, l=l, t=t, seed=seed, p_drop=p_drop, dev=dev)
+        self.saved = dict(ev_px=ev_px, pr_px=pr_px, pm=pm, b=b, l=l, t=t, seed=seed, p_drop=p_drop, dev=dev, prec=prec)
         return ev_logits, pr_logits
 
     def backward(self, d_ev_logits: Optional[torch.Tensor], d_pr_logits: Optional[torch.Tensor]) -> None:
@@ -269,7 +272,7 @@ class TrainEngine:
         for site, tag, px, n in ((1, "event", s["ev_px"], b), (2, "prong", s["pr_px"], t)):
             d = self._cnn_desc(tag)
             ws = self.ws["cnn_" + tag]
-            _lib.check(L.tcvn_cnn_train_backward(C.byref(d), a.ptr(tag), a.ptr(tag, True), _lib.ptr(px), n, s["p_drop"], s["seed"],
+            _lib.check(L.tcvn_cnn_train_backward(C.byref(d), s["prec"], a.ptr(tag), a.ptr(tag, True), _lib.ptr(px), n, s["p_drop"], s["seed"],
                                                  site, _lib.ptr(d_emb[tag]), _lib.ptr(ws), ws.numel(), st),
                        f"tcvn_cnn_train_backward({tag})")
             if ex is not None:

@@ -261,14 +261,16 @@ int tcvn_t_umma_conv2_dgrad(const void* g2x_bf16, const void* wd_bf16, int64_t r
  * sub-module in state_dict order (running buffers included; their gradient slots are never touched); parameter
  * gradients are ACCUMULATED.  The workspace carries the saved activations from forward to backward and must not
  * be reused in between.  Dropout masks derive from (seed, site, element): pass the same values to both calls. */
-size_t tcvn_cnn_train_workspace_bytes(const tcvn_cnn_desc* d, int n_images);
-int tcvn_cnn_train_forward(const tcvn_cnn_desc* d, float* arena, const float* pixels, int n_images, float p_drop,
-                           float momentum, uint64_t seed, uint64_t site, float* embedding, void* workspace,
+/* prec: TCVN_FP32 = CUDA-core parity path; TCVN_BF16 = bf16 activations, every dense-block / transition convolution
+ * (forward, input gradient, weight gradient) on tcgen05, fp32 parameters / statistics / parameter gradients */
+size_t tcvn_cnn_train_workspace_bytes(const tcvn_cnn_desc* d, tcvn_precision prec, int n_images);
+int tcvn_cnn_train_forward(const tcvn_cnn_desc* d, tcvn_precision prec, float* arena, const float* pixels, int n_images,
+                           float p_drop, float momentum, uint64_t seed, uint64_t site, float* embedding, void* workspace,
                            size_t workspace_bytes, tcvn_stream_t stream);
 /* d_embedding (n_images, out_features) is overwritten */
-int tcvn_cnn_train_backward(const tcvn_cnn_desc* d, const float* arena, float* grad_arena, const float* pixels,
-                            int n_images, float p_drop, uint64_t seed, uint64_t site, float* d_embedding, void* workspace,
-                            size_t workspace_bytes, tcvn_stream_t stream);
+int tcvn_cnn_train_backward(const tcvn_cnn_desc* d, tcvn_precision prec, const float* arena, float* grad_arena,
+                            const float* pixels, int n_images, float p_drop, uint64_t seed, uint64_t site, float* d_embedding,
+                            void* workspace, size_t workspace_bytes, tcvn_stream_t stream);
 size_t tcvn_seq_train_workspace_bytes(const tcvn_seq_desc* d, int n_events, int max_prongs, int n_prongs);
 /* prong_logits: (max_prongs * n_events, classes) in (slot, event) order */
 int tcvn_seq_train_forward(const tcvn_seq_desc* d, const float* position, float* combined, const float* encoder,

@@ -40,7 +40,8 @@ def main():
     opts.dropout = 0.0
     prongs = [2, 3] if "--big" not in sys.argv else [3, 1, 4, 2]
     batch = synth.make_batch(len(prongs), seed=31, prongs_per_event=prongs)
-    net = NeutrinoDenseNetwork(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES)
+    precision = "bf16" if "--bf16" in sys.argv else "fp32"
+    net = NeutrinoDenseNetwork(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES, precision=precision)
     state = synth.init_state(net.specs, seed=2, perturb=True)
     net.load_state_dict(state)
     net = net.to(dev).train()
@@ -134,7 +135,7 @@ def main():
 
     # ---- dropout: forward/backward mask consistency by a directional finite difference
     opts2 = PathOptions.tutorial()
-    net2 = NeutrinoDenseNetwork(opts2, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES)
+    net2 = NeutrinoDenseNetwork(opts2, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES, precision=precision)
     net2.load_state_dict(synth.init_state(net2.specs, seed=2, perturb=True))
     net2 = net2.to(dev).train()
     eng = net2.train_engine
@@ -174,7 +175,7 @@ def main():
         l = run(200)
         l.backward()
     torch.cuda.synchronize()
-    print(f"fp32 train fwd+bwd, {len(prongs)} events / {sum(prongs)} prongs: {(time.time() - t0) / 3 * 1e3:.1f} ms/step")
+    print(f"{precision} train fwd+bwd, {len(prongs)} events / {sum(prongs)} prongs: {(time.time() - t0) / 3 * 1e3:.1f} ms/step")
 
 
 if __name__ == "__main__":

@@ -34,7 +34,8 @@ def test_arena_layout_follows_the_state_dict(net):
     for tag, width in (("prong", 256), ("event", 288)):
         d = net.engine.cnn_desc(width)
         assert L.tcvn_cnn_arena_floats(C.byref(d)) == a.seg[tag][1] - a.seg[tag][0]
-        assert L.tcvn_cnn_train_workspace_bytes(C.byref(d), 8) > 8 * 64 * 200 * 140 * 4
+        for prec in (tl.TCVN_FP32, tl.TCVN_BF16):
+            assert L.tcvn_cnn_train_workspace_bytes(C.byref(d), prec, 8) > 8 * 64 * 200 * 140 * 4
     sd = net.engine.seq_desc()
     assert L.tcvn_seq_train_workspace_bytes(C.byref(sd), 4, 10, 22) > 0
     assert L.tcvn_seq_train_workspace_bytes(C.byref(sd), 4, 40, 22) == 0      # more slots than the kernels hold
