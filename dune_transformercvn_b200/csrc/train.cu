@@ -115,6 +115,14 @@ struct ColDev {
   int out_stride;
 };
 
+struct BnBwdDev {
+  const void* D; int ldd; int dcol0;
+  const void* X; int ldx; int xcol0;
+  const float* fold; int fold_stride; const double* sums; int C; double count;
+  void* dX; int lddx; int dxcol0; int accumulate;
+  long long m_total; int Hp, Wp;
+};
+
 template <int MODE, typename TX, typename TD>
 __global__ void __launch_bounds__(256) colsum_kernel(const ColDev p) {
   constexpr int NS = MODE == 0 ? 2 : (MODE == 1 ? 3 : 1);
@@ -178,6 +186,206 @@ __global__ void __launch_bounds__(256) colsum_kernel(const ColDev p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// vectorised variants (8 channels = one 16-byte bf16 / two 16-byte fp32 loads per thread, several rows in flight):
+// used whenever C, the pitches and the column offsets are multiples of 8.  A block is tv vector-columns x
+// (256 / tv) rows and walks its row slab; per-channel constants are loaded once per thread.
+// ------------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ void ld8(const T* p, float (&f)[8]);
+template <> __device__ __forceinline__ void ld8<float>(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <> __device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+template <typename T> __device__ __forceinline__ void st8(T* p, const float (&f)[8]);
+template <> __device__ __forceinline__ void st8<float>(float* p, const float (&f)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+}
+template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p, const float (&f)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    w[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+constexpr int kVecU = 4;  // rows in flight per thread
+
+template <int MODE, typename TX, typename TD>
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const ColDev p, int tv) {
+  constexpr int NS = MODE == 0 ? 2 : (MODE == 1 ? 3 : 1);
+  __shared__ double red[256][8];
+  const TX* X = static_cast<const TX*>(p.X);
+  const TD* D = static_cast<const TD*>(p.D);
+  const int rpi = 256 / tv;
+  const int vx = threadIdx.x % tv, ry = threadIdx.x / tv;
+  const int c = (blockIdx.x * tv + vx) * 8;
+  const bool active = c < p.C && ry < rpi;
+  const long long r_begin = (long long)blockIdx.y * p.rows_per_slab;
+  const long long r_end = min(p.m_total, r_begin + p.rows_per_slab);
+  double acc[NS][8];
+  float part[NS][8];
+#pragma unroll
+  for (int j = 0; j < NS; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[j][i] = 0.0; part[j][i] = 0.f; }
+  if (active) {
+    float sc[8], sh[8], al[8], mean[8], rstd[8];
+    if (MODE == 1) {
+      const int fs = p.fold_stride;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sc[i] = p.fold[c + i]; sh[i] = p.fold[fs + c + i]; al[i] = p.fold[2 * fs + c + i];
+        mean[i] = p.fold[3 * fs + c + i]; rstd[i] = p.fold[4 * fs + c + i];
+      }
+    }
+    int cnt = 0;
+    for (long long m0 = r_begin + ry; m0 < r_end; m0 += (long long)rpi * kVecU) {
+      float x[kVecU][8], d[kVecU][8];
+      bool ok[kVecU];
+#pragma unroll
+      for (int u = 0; u < kVecU; ++u) {
+        const long long m = m0 + (long long)u * rpi;
+        ok[u] = m < r_end && !is_ring(m, p.Hp, p.Wp);
+        if (ok[u]) {
+          ld8<TX>(X + m * (long long)p.ldx + p.xcol0 + c, x[u]);
+          if (MODE == 1) ld8<TD>(D + m * (long long)p.ldd + p.dcol0 + c, d[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kVecU; ++u) {
+        if (!ok[u]) continue;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (MODE == 0) {
+            part[0][i] += x[u][i];
+            part[1][i] = fmaf(x[u][i], x[u][i], part[1][i]);
+          } else if (MODE == 1) {
+            const float y = fmaf(x[u][i], sc[i], sh[i]);
+            const float g = y >= 0.f ? d[u][i] : d[u][i] * al[i];
+            part[0][i] += g;
+            part[1][i] = fmaf(g, (x[u][i] - mean[i]) * rstd[i], part[1][i]);
+            part[2][i] = fmaf(d[u][i], fminf(y, 0.f), part[2][i]);
+          } else {
+            part[0][i] += x[u][i];
+          }
+        }
+      }
+      if (++cnt == 16) {  // flush the fp32 partials (<= 64 rows) into doubles
+#pragma unroll
+        for (int j = 0; j < NS; ++j)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { acc[j][i] += (double)part[j][i]; part[j][i] = 0.f; }
+        cnt = 0;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NS; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[j][i] += (double)part[j][i];
+  }
+#pragma unroll
+  for (int j = 0; j < NS; ++j) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = acc[j][i];
+    __syncthreads();
+    if (active && ry == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        double s = 0.0;
+        for (int r = 0; r < rpi; ++r) s += red[r * tv + vx][i];
+        atomicAdd(p.out + (size_t)j * p.out_stride + c + i, s);
+      }
+    }
+  }
+}
+
+template <typename TX, typename TD, typename TO>
+__global__ void __launch_bounds__(256) bnact_bwd_apply_vec_kernel(const BnBwdDev p, int tv, int rows_per_slab) {
+  const int rpi = 256 / tv;
+  const int vx = threadIdx.x % tv, ry = threadIdx.x / tv;
+  const int c = (blockIdx.x * tv + vx) * 8;
+  if (c >= p.C || ry >= rpi) return;
+  const TX* X = static_cast<const TX*>(p.X);
+  const TD* D = static_cast<const TD*>(p.D);
+  TO* O = static_cast<TO*>(p.dX);
+  const long long r_begin = (long long)blockIdx.y * rows_per_slab;
+  const long long r_end = min(p.m_total, r_begin + rows_per_slab);
+  const int fs = p.fold_stride;
+  float sc[8], sh[8], al[8], mean[8], rstd[8], mg[8], mgx[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    sc[i] = p.fold[c + i]; sh[i] = p.fold[fs + c + i]; al[i] = p.fold[2 * fs + c + i];
+    mean[i] = p.fold[3 * fs + c + i]; rstd[i] = p.fold[4 * fs + c + i];
+    mg[i] = (float)(p.sums[c + i] / p.count); mgx[i] = (float)(p.sums[p.C + c + i] / p.count);
+  }
+  for (long long m0 = r_begin + ry; m0 < r_end; m0 += (long long)rpi * kVecU) {
+    float x[kVecU][8], d[kVecU][8], o[kVecU][8];
+    int kind[kVecU];  // 0 skip, 1 ring, 2 interior
+#pragma unroll
+    for (int u = 0; u < kVecU; ++u) {
+      const long long m = m0 + (long long)u * rpi;
+      kind[u] = m >= r_end ? 0 : (is_ring(m, p.Hp, p.Wp) ? 1 : 2);
+      if (kind[u] == 2) {
+        ld8<TX>(X + m * (long long)p.ldx + p.xcol0 + c, x[u]);
+        ld8<TD>(D + m * (long long)p.ldd + p.dcol0 + c, d[u]);
+        if (p.accumulate) ld8<TO>(O + m * (long long)p.lddx + p.dxcol0 + c, o[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kVecU; ++u) {
+      const long long m = m0 + (long long)u * rpi;
+      if (kind[u] == 0) continue;
+      float v[8];
+      if (kind[u] == 1) {
+        if (p.accumulate) continue;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float y = fmaf(x[u][i], sc[i], sh[i]);
+          const float g = y >= 0.f ? d[u][i] : d[u][i] * al[i];
+          v[i] = sc[i] * (g - mg[i] - (x[u][i] - mean[i]) * rstd[i] * mgx[i]);
+          if (p.accumulate) v[i] += o[u][i];
+        }
+      }
+      st8<TO>(O + m * (long long)p.lddx + p.dxcol0 + c, v);
+    }
+  }
+}
+
+template <typename TX, typename TO>
+__global__ void __launch_bounds__(256) bnact_fwd_vec_kernel(const TX* __restrict__ X, int ldx, int xcol0,
+                                                            const float* __restrict__ fold, int fold_stride, int C,
+                                                            long long m_total, int Hp, int Wp, TO* __restrict__ out, int ldo,
+                                                            int ocol0) {
+  const int cv = C / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= m_total * cv) return;
+  const int c = (int)(idx % cv) * 8;
+  const long long m = idx / cv;
+  float v[8];
+  if (is_ring(m, Hp, Wp)) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+  } else {
+    ld8<TX>(X + m * (long long)ldx + xcol0 + c, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = prelu(fmaf(v[i], fold[c + i], fold[fold_stride + c + i]), fold[2 * fold_stride + c + i]);
+  }
+  st8<TO>(out + m * (long long)ldo + ocol0 + c, v);
+}
+
 // batch statistics -> fold [scale | shift | alpha | mean | rstd], running-stat update (momentum, unbiased var)
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, double count, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, const float* __restrict__ alpha, float eps,
@@ -202,14 +410,6 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, doubl
 }
 
 // BN + PReLU backward, elementwise half:  dX (+)= scale * (g - sum_g/M - xhat * sum_gxhat/M)
-struct BnBwdDev {
-  const void* D; int ldd; int dcol0;
-  const void* X; int ldx; int xcol0;
-  const float* fold; int fold_stride; const double* sums; int C; double count;
-  void* dX; int lddx; int dxcol0; int accumulate;
-  long long m_total; int Hp, Wp;
-};
-
 template <typename TX, typename TD, typename TO>
 __global__ void bnact_bwd_apply_kernel(const BnBwdDev p) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -428,8 +628,28 @@ int colsums_typed(int mode, const void* X, bool x_bf16, int ldx, int xcol0, cons
   p.X = X; p.ldx = ldx; p.xcol0 = xcol0; p.D = D; p.ldd = ldd; p.dcol0 = dcol0; p.fold = fold; p.fold_stride = fold_stride;
   p.C = C; p.m_total = m_total; p.Hp = ring_hp; p.Wp = ring_wp; p.out = out; p.out_stride = out_stride;
   const int slabs = slabs_for(m_total, &p.rows_per_slab);
-  dim3 grid(ceil_div(C, 32), slabs);
   typedef __nv_bfloat16 bf;
+  const bool vec = C % 8 == 0 && ldx % 8 == 0 && xcol0 % 8 == 0 && (mode != 1 || (ldd % 8 == 0 && dcol0 % 8 == 0)) &&
+                   reinterpret_cast<uintptr_t>(X) % 32 == 0 && (mode != 1 || reinterpret_cast<uintptr_t>(D) % 32 == 0);
+  if (vec) {
+    const int cv = C / 8;
+    const int tv = cv < 32 ? cv : 32;
+    dim3 vgrid(ceil_div(cv, tv), slabs);
+#define TCVN_COLSUM_V(MODE)                                                                              \
+  do {                                                                                                   \
+    if (!x_bf16 && !d_bf16) colsum_vec_kernel<MODE, float, float><<<vgrid, 256, 0, stream>>>(p, tv);      \
+    else if (x_bf16 && d_bf16) colsum_vec_kernel<MODE, bf, bf><<<vgrid, 256, 0, stream>>>(p, tv);         \
+    else if (x_bf16) colsum_vec_kernel<MODE, bf, float><<<vgrid, 256, 0, stream>>>(p, tv);                \
+    else colsum_vec_kernel<MODE, float, bf><<<vgrid, 256, 0, stream>>>(p, tv);                            \
+  } while (0)
+    if (mode == 0) TCVN_COLSUM_V(0);
+    else if (mode == 1) TCVN_COLSUM_V(1);
+    else TCVN_COLSUM_V(2);
+#undef TCVN_COLSUM_V
+    TCVN_LAUNCH_CHECK();
+    return TCVN_OK;
+  }
+  dim3 grid(ceil_div(C, 32), slabs);
 #define TCVN_COLSUM(MODE)                                                                          \
   do {                                                                                             \
     if (!x_bf16 && !d_bf16) colsum_kernel<MODE, float, float><<<grid, 256, 0, stream>>>(p);         \
@@ -461,8 +681,27 @@ int bnact_bwd_apply_typed(const void* D, bool d_bf16, int ldd, int dcol0, const 
   p.D = D; p.ldd = ldd; p.dcol0 = dcol0; p.X = X; p.ldx = ldx; p.xcol0 = xcol0; p.fold = fold; p.fold_stride = fold_stride;
   p.sums = sums; p.C = C; p.count = count; p.dX = dX; p.lddx = lddx; p.dxcol0 = dxcol0; p.accumulate = accumulate ? 1 : 0;
   p.m_total = m_total; p.Hp = ring_hp; p.Wp = ring_wp;
-  const unsigned grid = (unsigned)ceil_div_ll(m_total * C, 256);
   typedef __nv_bfloat16 bf;
+  const bool vec = C % 8 == 0 && ldx % 8 == 0 && xcol0 % 8 == 0 && ldd % 8 == 0 && dcol0 % 8 == 0 && lddx % 8 == 0 &&
+                   dxcol0 % 8 == 0 && reinterpret_cast<uintptr_t>(X) % 32 == 0 && reinterpret_cast<uintptr_t>(D) % 32 == 0 &&
+                   reinterpret_cast<uintptr_t>(dX) % 32 == 0;
+  if (vec) {
+    const int cv = C / 8;
+    const int tv = cv < 32 ? cv : 32;
+    int rows_per_slab;
+    int slabs = (int)ceil_div_ll(m_total, 512);
+    if (slabs > 1184) slabs = 1184;
+    rows_per_slab = (int)ceil_div_ll(m_total, slabs);
+    slabs = (int)ceil_div_ll(m_total, rows_per_slab);
+    dim3 vgrid(ceil_div(cv, tv), slabs);
+    if (!x_bf16 && !d_bf16 && !o_bf16) bnact_bwd_apply_vec_kernel<float, float, float><<<vgrid, 256, 0, stream>>>(p, tv, rows_per_slab);
+    else if (x_bf16 && d_bf16 && o_bf16) bnact_bwd_apply_vec_kernel<bf, bf, bf><<<vgrid, 256, 0, stream>>>(p, tv, rows_per_slab);
+    else if (x_bf16 && d_bf16 && !o_bf16) bnact_bwd_apply_vec_kernel<bf, bf, float><<<vgrid, 256, 0, stream>>>(p, tv, rows_per_slab);
+    else return fail(TCVN_ERR_UNSUPPORTED, "bnact_bwd_apply: type combination not instantiated");
+    TCVN_LAUNCH_CHECK();
+    return TCVN_OK;
+  }
+  const unsigned grid = (unsigned)ceil_div_ll(m_total * C, 256);
   if (!x_bf16 && !d_bf16 && !o_bf16) bnact_bwd_apply_kernel<float, float, float><<<grid, 256, 0, stream>>>(p);
   else if (x_bf16 && d_bf16 && o_bf16) bnact_bwd_apply_kernel<bf, bf, bf><<<grid, 256, 0, stream>>>(p);
   else if (x_bf16 && d_bf16 && !o_bf16) bnact_bwd_apply_kernel<bf, bf, float><<<grid, 256, 0, stream>>>(p);
@@ -474,8 +713,16 @@ int bnact_bwd_apply_typed(const void* D, bool d_bf16, int ldd, int dcol0, const 
 int bnact_fwd_typed(const void* X, bool x_bf16, int ldx, int xcol0, const float* fold, int fold_stride, int C, long long m_total,
                     int ring_hp, int ring_wp, void* out, bool o_bf16, int ldo, int ocol0, cudaStream_t stream) {
   if (m_total <= 0 || C <= 0) return TCVN_OK;
-  const unsigned grid = (unsigned)ceil_div_ll(m_total * C, 256);
   typedef __nv_bfloat16 bf;
+  if (x_bf16 && o_bf16 && C % 8 == 0 && ldx % 8 == 0 && xcol0 % 8 == 0 && ldo % 8 == 0 && ocol0 % 8 == 0 &&
+      reinterpret_cast<uintptr_t>(X) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0) {
+    const unsigned vgrid = (unsigned)ceil_div_ll(m_total * (C / 8), 256);
+    bnact_fwd_vec_kernel<bf, bf><<<vgrid, 256, 0, stream>>>(static_cast<const bf*>(X), ldx, xcol0, fold, fold_stride, C, m_total,
+                                                            ring_hp, ring_wp, static_cast<bf*>(out), ldo, ocol0);
+    TCVN_LAUNCH_CHECK();
+    return TCVN_OK;
+  }
+  const unsigned grid = (unsigned)ceil_div_ll(m_total * C, 256);
   if (!x_bf16 && !o_bf16)
     bnact_fwd_kernel<float, float><<<grid, 256, 0, stream>>>(static_cast<const float*>(X), ldx, xcol0, fold, fold_stride, C, m_total,
                                                              ring_hp, ring_wp, static_cast<float*>(out), ldo, ocol0);
