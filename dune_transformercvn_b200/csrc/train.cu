@@ -220,8 +220,10 @@ template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p,
 constexpr int kVecU = 4;  // rows in flight per thread
 
 template <int MODE, typename TX, typename TD>
-__global__ void __launch_bounds__(256) colsum_vec_kernel(const ColDev p, int tv) {
+__global__ void __launch_bounds__(256, 2) colsum_vec_kernel(const ColDev p, int tv) {
+  // slabs are short (<= 64 rows per thread): fp32 partials per thread, doubles only across threads / CTAs
   constexpr int NS = MODE == 0 ? 2 : (MODE == 1 ? 3 : 1);
+  constexpr int U = MODE == 1 ? 2 : kVecU;
   __shared__ double red[256][8];
   const TX* X = static_cast<const TX*>(p.X);
   const TD* D = static_cast<const TD*>(p.D);
@@ -231,12 +233,11 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const ColDev p, int tv)
   const bool active = c < p.C && ry < rpi;
   const long long r_begin = (long long)blockIdx.y * p.rows_per_slab;
   const long long r_end = min(p.m_total, r_begin + p.rows_per_slab);
-  double acc[NS][8];
   float part[NS][8];
 #pragma unroll
   for (int j = 0; j < NS; ++j)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { acc[j][i] = 0.0; part[j][i] = 0.f; }
+    for (int i = 0; i < 8; ++i) part[j][i] = 0.f;
   if (active) {
     float sc[8], sh[8], al[8], mean[8], rstd[8];
     if (MODE == 1) {
@@ -247,12 +248,11 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const ColDev p, int tv)
         mean[i] = p.fold[3 * fs + c + i]; rstd[i] = p.fold[4 * fs + c + i];
       }
     }
-    int cnt = 0;
-    for (long long m0 = r_begin + ry; m0 < r_end; m0 += (long long)rpi * kVecU) {
-      float x[kVecU][8], d[kVecU][8];
-      bool ok[kVecU];
+    for (long long m0 = r_begin + ry; m0 < r_end; m0 += (long long)rpi * U) {
+      float x[U][8], d[U][8];
+      bool ok[U];
 #pragma unroll
-      for (int u = 0; u < kVecU; ++u) {
+      for (int u = 0; u < U; ++u) {
         const long long m = m0 + (long long)u * rpi;
         ok[u] = m < r_end && !is_ring(m, p.Hp, p.Wp);
         if (ok[u]) {
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const ColDev p, int tv)
         }
       }
 #pragma unroll
-      for (int u = 0; u < kVecU; ++u) {
+      for (int u = 0; u < U; ++u) {
         if (!ok[u]) continue;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -279,24 +279,13 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const ColDev p, int tv)
           }
         }
       }
-      if (++cnt == 16) {  // flush the fp32 partials (<= 64 rows) into doubles
-#pragma unroll
-        for (int j = 0; j < NS; ++j)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) { acc[j][i] += (double)part[j][i]; part[j][i] = 0.f; }
-        cnt = 0;
-      }
     }
-#pragma unroll
-    for (int j = 0; j < NS; ++j)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[j][i] += (double)part[j][i];
   }
 #pragma unroll
   for (int j = 0; j < NS; ++j) {
     __syncthreads();
 #pragma unroll
-    for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = acc[j][i];
+    for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = (double)part[j][i];
     __syncthreads();
     if (active && ry == 0) {
 #pragma unroll
@@ -310,7 +299,7 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const ColDev p, int tv)
 }
 
 template <typename TX, typename TD, typename TO>
-__global__ void __launch_bounds__(256) bnact_bwd_apply_vec_kernel(const BnBwdDev p, int tv, int rows_per_slab) {
+__global__ void __launch_bounds__(256, 2) bnact_bwd_apply_vec_kernel(const BnBwdDev p, int tv, int rows_per_slab) {
   const int rpi = 256 / tv;
   const int vx = threadIdx.x % tv, ry = threadIdx.x / tv;
   const int c = (blockIdx.x * tv + vx) * 8;
@@ -328,11 +317,11 @@ __global__ void __launch_bounds__(256) bnact_bwd_apply_vec_kernel(const BnBwdDev
     mean[i] = p.fold[3 * fs + c + i]; rstd[i] = p.fold[4 * fs + c + i];
     mg[i] = (float)(p.sums[c + i] / p.count); mgx[i] = (float)(p.sums[p.C + c + i] / p.count);
   }
-  for (long long m0 = r_begin + ry; m0 < r_end; m0 += (long long)rpi * kVecU) {
-    float x[kVecU][8], d[kVecU][8], o[kVecU][8];
-    int kind[kVecU];  // 0 skip, 1 ring, 2 interior
+  for (long long m0 = r_begin + ry; m0 < r_end; m0 += (long long)rpi * 2) {
+    float x[2][8], d[2][8], o[2][8];
+    int kind[2];  // 0 skip, 1 ring, 2 interior
 #pragma unroll
-    for (int u = 0; u < kVecU; ++u) {
+    for (int u = 0; u < 2; ++u) {
       const long long m = m0 + (long long)u * rpi;
       kind[u] = m >= r_end ? 0 : (is_ring(m, p.Hp, p.Wp) ? 1 : 2);
       if (kind[u] == 2) {
@@ -342,7 +331,7 @@ __global__ void __launch_bounds__(256) bnact_bwd_apply_vec_kernel(const BnBwdDev
       }
     }
 #pragma unroll
-    for (int u = 0; u < kVecU; ++u) {
+    for (int u = 0; u < 2; ++u) {
       const long long m = m0 + (long long)u * rpi;
       if (kind[u] == 0) continue;
       float v[8];
@@ -634,7 +623,15 @@ int colsums_typed(int mode, const void* X, bool x_bf16, int ldx, int xcol0, cons
   if (vec) {
     const int cv = C / 8;
     const int tv = cv < 32 ? cv : 32;
-    dim3 vgrid(ceil_div(cv, tv), slabs);
+    const int rpi = 256 / tv;
+    const int gx = ceil_div(cv, tv);
+    // short slabs: one slab = 16 row-steps of a CTA (<= 64 rows per thread), at most ~16 CTAs per SM in total
+    long long vslabs = ceil_div_ll(m_total, (long long)rpi * kVecU * 4);
+    const long long cap = (long long)(148 * 16 / gx > 1 ? 148 * 16 / gx : 1);
+    if (vslabs > cap) vslabs = cap;
+    p.rows_per_slab = (int)ceil_div_ll(m_total, vslabs);
+    vslabs = ceil_div_ll(m_total, p.rows_per_slab);
+    dim3 vgrid(gx, (unsigned)vslabs);
 #define TCVN_COLSUM_V(MODE)                                                                              \
   do {                                                                                                   \
     if (!x_bf16 && !d_bf16) colsum_vec_kernel<MODE, float, float><<<vgrid, 256, 0, stream>>>(p, tv);      \
@@ -688,12 +685,14 @@ int bnact_bwd_apply_typed(const void* D, bool d_bf16, int ldd, int dcol0, const 
   if (vec) {
     const int cv = C / 8;
     const int tv = cv < 32 ? cv : 32;
-    int rows_per_slab;
-    int slabs = (int)ceil_div_ll(m_total, 512);
-    if (slabs > 1184) slabs = 1184;
-    rows_per_slab = (int)ceil_div_ll(m_total, slabs);
-    slabs = (int)ceil_div_ll(m_total, rows_per_slab);
-    dim3 vgrid(ceil_div(cv, tv), slabs);
+    const int rpi = 256 / tv;
+    const int gx = ceil_div(cv, tv);
+    long long vslabs = ceil_div_ll(m_total, (long long)rpi * 2 * 4);
+    const long long cap = (long long)(148 * 16 / gx > 1 ? 148 * 16 / gx : 1);
+    if (vslabs > cap) vslabs = cap;
+    const int rows_per_slab = (int)ceil_div_ll(m_total, vslabs);
+    const int slabs = (int)ceil_div_ll(m_total, rows_per_slab);
+    dim3 vgrid(gx, slabs);
     if (!x_bf16 && !d_bf16 && !o_bf16) bnact_bwd_apply_vec_kernel<float, float, float><<<vgrid, 256, 0, stream>>>(p, tv, rows_per_slab);
     else if (x_bf16 && d_bf16 && o_bf16) bnact_bwd_apply_vec_kernel<bf, bf, bf><<<vgrid, 256, 0, stream>>>(p, tv, rows_per_slab);
     else if (x_bf16 && d_bf16 && !o_bf16) bnact_bwd_apply_vec_kernel<bf, bf, float><<<vgrid, 256, 0, stream>>>(p, tv, rows_per_slab);

@@ -439,7 +439,7 @@ struct TrainPlan16 {
   int n;
   size_t w0, z0, fold0, fold_f, gap, dgap, lin, fold_o, lw, lwt;
   std::vector<T16Block> blocks;
-  size_t sA, sB, dmid, g2x, gt, dz0, sums_scr, dwp, zeros, ones;
+  size_t sA, sB, dmid, g2x, gt, dz0, sums_scr, dwp, parts, zeros, ones;
   size_t bytes;
 
   static bool build(const tcvn_cnn_desc& d, int n, TrainPlan16* T) {
@@ -514,6 +514,7 @@ struct TrainPlan16 {
     T->dz0 = take(N * P.Hs * P.Ws * C0 * 4);
     T->sums_scr = take(3 * (size_t)max_c * 8);
     T->dwp = take(max_dw * 4);
+    T->parts = take((size_t)148 * 4 * 128 * 128 * 4 + 4 * 128 * 128 * 4 * 8);   // per-CTA partial sums of the wgrad kernel
     T->zeros = take(1024 * 4);
     T->ones = take(1024 * 4);
     T->bytes = w;
@@ -795,9 +796,8 @@ struct TWalk16 {
         // conv2 weight gradient: three vertical taps of the activated bottleneck map against G2x
         {
           const int cols[3] = {0, 0, 0}, shifts[3] = {-B.Wp, 0, B.Wp}, valid[3] = {128, 128, 128};
-          TCVN_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * 3 * 128 * 128, st));
           TCVN_TRY(umma_wgrad(h(Y.mid_act), rows, mid, mid, 3, cols, shifts, valid, nullptr, nullptr, nullptr, 0, g2x, 128, 128, 0,
-                              dwp, st));
+                              f(T.parts), dwp, false, st));
           unpack_conv2_grad_kernel<<<ceil_div(32 * 128 * 9, 256), 256, 0, st>>>(dwp, garena + L.conv2_w);
           TCVN_LAUNCH_CHECK();
         }
@@ -810,9 +810,8 @@ struct TWalk16 {
           const int n_items = ceil_div(L.kphys, 128);
           int cols[4], shifts[4], valid[4];
           for (int j = 0; j < n_items; ++j) { cols[j] = 128 * j; shifts[j] = 0; valid[j] = L.kphys - 128 * j < 128 ? L.kphys - 128 * j : 128; }
-          TCVN_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)n_items * 128 * 128, st));
           TCVN_TRY(umma_wgrad(blk, rows, B.ctot, B.ctot, n_items, cols, shifts, valid, f1, f1 + L.kpad, f1 + 2 * L.kpad, L.kphys,
-                              dmid, mid, mid, 0, dwp, st));
+                              dmid, mid, mid, 0, f(T.parts), dwp, false, st));
           TCVN_TRY(unpack(dwp, 1, n_items * 128, 128, mid, L.cin, B.c0, B.c0p, garena + L.conv1_w));
         }
         TCVN_TRY(launch_gemm(false, dmid, rows, mid, mid, h(Y.w1d), L.kphys, 128, 128, nullptr, nullptr, nullptr, f(T.zeros),

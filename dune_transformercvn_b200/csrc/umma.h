@@ -21,8 +21,9 @@ int launch_gemm(bool transform, const void* A, long long rows, int a_cols, int a
                 const float* o_alpha, void* out, int out_cols, int out_pitch, int n_tiles_n, int Hp, int Wp, cudaStream_t st);
 int umma_conv2_fwd(const void* mid, long long rows, const void* w2, const float* bias, void* out, int ldo, int col0, int Hp,
                    int Wp, int W, cudaStream_t st);
+size_t umma_wgrad_parts_bytes(int n_items);
 int umma_wgrad(const void* A, long long rows, int a_cols, int a_pitch, int n_items, const int* item_col, const int* item_shift,
                const int* item_valid, const float* a_scale, const float* a_shift, const float* a_alpha, int a_fold_cols,
-               const void* G, int g_cols, int g_pitch, int g_col0, float* dw, cudaStream_t st);
+               const void* G, int g_cols, int g_pitch, int g_col0, float* parts, float* dw, bool accumulate, cudaStream_t st);
 int umma_conv2_dgrad(const void* g2x, const void* wd, long long rows, int Hp, int Wp, void* out, cudaStream_t st);
 }  // namespace tcvn

@@ -39,7 +39,7 @@ struct WgradParams {
   int a_cols;             // columns of A covered by the transform constants (channels >= a_cols are forced to 0)
   const float *a_scale, *a_shift, *a_alpha;
   int g_col0;
-  float* dw;              // [n_items][128][128] fp32, accumulated
+  float* dw;              // [gridDim.x][n_items][128][128] fp32: one partial sum per CTA (plain stores)
   int num_tiles, stages;
 };
 
@@ -170,24 +170,26 @@ __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_kernel(const __grid_
       }
     }
   } else {
-    // epilogue: after the CTA's last tile, add its partial sums to the global result
+    // epilogue: after the CTA's last tile, store its partial sums (rows beyond the item's valid channels as zeros);
+    // a reduction kernel adds the per-CTA partials - 148 x 64 K atomics per item cost more than the main loop
     const int g = warp & 3;          // TMEM lane group this warp may read (warps 10..13 -> 2,3,0,1)
     const int row = g * 32 + lane;   // channel of A within the item
     if (blockIdx.x < p.num_tiles) {
       if (lane == 0) ptx::mbar_wait(done, 0);
       __syncwarp();
       ptx::tc_fence_after();
+      float* part = p.dw + (size_t)blockIdx.x * p.n_items * 128 * 128;
       for (int it = 0; it < p.n_items; ++it) {
+        const bool valid = row < p.item_valid[it];
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t r[32];
           ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(g * 32) << 16) + it * 128 + c * 32, r);
           ptx::tmem_ld_wait();
-          if (row < p.item_valid[it]) {
-            float* dst = p.dw + ((size_t)it * 128 + row) * 128 + c * 32;
+          uint4* dst = reinterpret_cast<uint4*>(part + ((size_t)it * 128 + row) * 128 + c * 32);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(dst + j, __uint_as_float(r[j]));
-          }
+          for (int j = 0; j < 8; ++j)
+            dst[j] = valid ? make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]) : make_uint4(0u, 0u, 0u, 0u);
         }
       }
     }
@@ -338,20 +340,39 @@ __global__ void __launch_bounds__(kDgThreads, 1) umma_conv2_dgrad_kernel(const _
   if (warp == 0) ptx::tmem_dealloc(tmem_base, 256);
 }
 
+__global__ void reduce_parts_kernel(const float4* __restrict__ parts, int n_parts, long long n4, float4* __restrict__ out,
+                                    int accumulate) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 s = accumulate ? out[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int q = 0; q < n_parts; ++q) {
+    const float4 v = parts[(size_t)q * n4 + i];
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  out[i] = s;
+}
+
 }  // namespace
 
-// dw[item][k][n] (fp32, ACCUMULATED; the caller zeroes it) += sum_m act(A[m + shift_item, col_item + k]) * G[m, g_col0 + n]
+constexpr int kWgMaxCtas = 148;  // per-CTA partial sums: the scratch is sized for this many
+size_t umma_wgrad_parts_bytes(int n_items) { return (size_t)kWgMaxCtas * n_items * 128 * 128 * sizeof(float); }
+
+// dw[item][k][n] (fp32 [n_items][128][128]) (+)= sum_m act(A[m + shift_item, col_item + k]) * G[m, g_col0 + n]
+// parts: scratch of umma_wgrad_parts_bytes(n_items) for the per-CTA partial sums
 int umma_wgrad(const void* A, long long rows, int a_cols, int a_pitch, int n_items, const int* item_col, const int* item_shift,
                const int* item_valid, const float* a_scale, const float* a_shift, const float* a_alpha, int a_fold_cols,
-               const void* G, int g_cols, int g_pitch, int g_col0, float* dw, cudaStream_t st) {
+               const void* G, int g_cols, int g_pitch, int g_col0, float* parts, float* dw, bool accumulate, cudaStream_t st) {
   if (n_items < 1 || n_items > 4) return fail(TCVN_ERR_ARG, "umma_wgrad: %d items (1..4)", n_items);
-  if (rows <= 0) return TCVN_OK;
+  if (rows <= 0) {
+    if (!accumulate) TCVN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)n_items * 128 * 128, st));
+    return TCVN_OK;
+  }
   if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one launch");
   WgradParams p{};
   p.rows = rows; p.n_items = n_items;
   for (int i = 0; i < n_items; ++i) { p.item_col[i] = item_col[i]; p.item_shift[i] = item_shift[i]; p.item_valid[i] = item_valid[i]; }
   p.a_cols = a_fold_cols; p.a_scale = a_scale; p.a_shift = a_shift; p.a_alpha = a_alpha;
-  p.g_col0 = g_col0; p.dw = dw;
+  p.g_col0 = g_col0; p.dw = parts;
   p.num_tiles = (int)ceil_div_ll(rows, kWgRows);
   const int stage_bytes = (2 * n_items + 2) * kWgBox;
   int stages = (200 * 1024) / stage_bytes;
@@ -368,9 +389,17 @@ int umma_wgrad(const void* A, long long rows, int a_cols, int a_pitch, int n_ite
   CUtensorMap tmA, tmG;
   TCVN_TRY(make_map(A, rows, a_cols, a_pitch, 64, kWgRows, &tmA));
   TCVN_TRY(make_map(G, rows, g_cols, g_pitch, 64, kWgRows, &tmG));
-  const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  // few tiles: fewer CTAs (each partial costs a 64 KB store + read per item); many tiles: one CTA per SM
+  int grid = ceil_div(p.num_tiles, 4);
+  if (grid > sm_count()) grid = sm_count();
+  if (grid > kWgMaxCtas) grid = kWgMaxCtas;
+  if (grid < 1) grid = 1;
   if (a_scale) umma_wgrad_kernel<true><<<grid, kWgThreads, smem, st>>>(tmA, tmG, p);
   else umma_wgrad_kernel<false><<<grid, kWgThreads, smem, st>>>(tmA, tmG, p);
+  TCVN_LAUNCH_CHECK();
+  const long long n4 = (long long)n_items * 128 * 128 / 4;
+  reduce_parts_kernel<<<(unsigned)ceil_div_ll(n4, 256), 256, 0, st>>>(reinterpret_cast<const float4*>(parts), grid, n4,
+                                                                     reinterpret_cast<float4*>(dw), accumulate ? 1 : 0);
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
 }
@@ -409,16 +438,21 @@ int umma_conv2_dgrad(const void* g2x, const void* wd, long long rows, int Hp, in
 }  // namespace tcvn
 
 // ---- C ABI: the two kernels on caller-provided matrices (unit-tested against plain matrix products) ----------
+extern "C" size_t tcvn_t_umma_wgrad_workspace_bytes(int n_items) { return tcvn::umma_wgrad_parts_bytes(n_items); }
+
 extern "C" int tcvn_t_umma_wgrad(const void* a_bf16, int64_t rows, int a_cols, int a_pitch, int n_items,
                                  const int32_t* item_col, const int32_t* item_shift, const int32_t* item_valid,
                                  const float* a_fold, int a_fold_cols, const void* g_bf16, int g_cols, int g_pitch, int g_col0,
-                                 float* dw, tcvn_stream_t stream) {
-  TCVN_CHECK_ARG(a_bf16 && g_bf16 && dw && item_col && item_shift && item_valid, "t_umma_wgrad: null pointer");
+                                 float* dw, void* workspace, size_t workspace_bytes, tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(a_bf16 && g_bf16 && dw && item_col && item_shift && item_valid && workspace, "t_umma_wgrad: null pointer");
+  TCVN_CHECK_ARG(n_items >= 1 && n_items <= 4, "t_umma_wgrad: 1..4 items");
+  if (workspace_bytes < tcvn::umma_wgrad_parts_bytes(n_items))
+    return tcvn::fail(TCVN_ERR_WORKSPACE, "t_umma_wgrad: workspace %zu < %zu bytes", workspace_bytes, tcvn::umma_wgrad_parts_bytes(n_items));
   TCVN_CHECK_ARG(a_pitch % 8 == 0 && g_pitch % 8 == 0, "t_umma_wgrad: row pitches must be multiples of 8 elements (TMA)");
   TCVN_CHECK_ARG(a_fold == nullptr || a_fold_cols % 8 == 0, "t_umma_wgrad: fold width must be a multiple of 8");
   return tcvn::umma_wgrad(a_bf16, rows, a_cols, a_pitch, n_items, item_col, item_shift, item_valid, a_fold,
                           a_fold ? a_fold + a_fold_cols : nullptr, a_fold ? a_fold + 2 * a_fold_cols : nullptr, a_fold_cols,
-                          g_bf16, g_cols, g_pitch, g_col0, dw, stream);
+                          g_bf16, g_cols, g_pitch, g_col0, static_cast<float*>(workspace), dw, true, stream);
 }
 
 extern "C" int tcvn_t_umma_conv2_dgrad(const void* g2x_bf16, const void* wd_bf16, int64_t rows, int ring_hp, int ring_wp,

@@ -31,7 +31,7 @@ EXPORTS = (
     "tcvn_t_eltwise", "tcvn_t_tokens", "tcvn_t_act_pool2", "tcvn_t_act_gap", "tcvn_sumsq", "tcvn_adamw_step",
     "tcvn_cnn_train_workspace_bytes", "tcvn_cnn_train_forward", "tcvn_cnn_train_backward",
     "tcvn_seq_train_workspace_bytes", "tcvn_seq_train_forward", "tcvn_seq_train_backward",
-    "tcvn_t_umma_wgrad", "tcvn_t_umma_conv2_dgrad",
+    "tcvn_t_umma_wgrad", "tcvn_t_umma_wgrad_workspace_bytes", "tcvn_t_umma_conv2_dgrad",
 )
 
 
@@ -107,7 +107,9 @@ def load() -> C.CDLL:
     lib.tcvn_t_act_gap.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.tcvn_sumsq.argtypes = [vp, i64, vp, i32, vp]
     lib.tcvn_adamw_step.argtypes = [vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i64, vp, f32, f32, vp, i32, vp]
-    lib.tcvn_t_umma_wgrad.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp, vp]
+    lib.tcvn_t_umma_wgrad.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp, vp, sz, vp]
+    lib.tcvn_t_umma_wgrad_workspace_bytes.argtypes = [i32]
+    lib.tcvn_t_umma_wgrad_workspace_bytes.restype = sz
     lib.tcvn_t_umma_conv2_dgrad.argtypes = [vp, vp, i64, i32, i32, vp, vp]
     lib.tcvn_cnn_train_workspace_bytes.argtypes = [C.POINTER(CnnDesc), i32, i32]
     lib.tcvn_cnn_train_workspace_bytes.restype = sz

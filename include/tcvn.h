@@ -240,13 +240,16 @@ int tcvn_adamw_step(float* params, const float* grads, float* exp_avg, float* ex
 /* tcgen05 kernels of the bf16 training path on caller-provided row-major bf16 matrices (csrc/umma_train.cu).
  * Weight gradient with MN-major operands (the reduction runs over pixel rows):
  *   dw[item][k][n] += sum_m act(A[m + item_shift[item], item_col[item] + k]) * G[m, g_col0 + n],  k, n in [0,128)
- * dw is fp32 [n_items][128][128], accumulated (red.global); rows k >= item_valid[item] are not written; rows of A
+ * dw is fp32 [n_items][128][128], accumulated (every persistent CTA stores one partial sum into the workspace, a
+ * reduction kernel adds them to dw); rows k >= item_valid[item] receive zero; rows of A
  * outside [0, rows) read as zero; act = PReLU(scale*x + shift) from a_fold = [scale | shift | alpha] (each
  * a_fold_cols wide; columns >= a_fold_cols are forced to zero) or identity when a_fold is NULL.
  * Replaces autograd's weight gradient of nn.Conv2d (dense_net.py:21-38). */
+size_t tcvn_t_umma_wgrad_workspace_bytes(int n_items);
 int tcvn_t_umma_wgrad(const void* a_bf16, int64_t rows, int a_cols, int a_pitch, int n_items, const int32_t* item_col,
                       const int32_t* item_shift, const int32_t* item_valid, const float* a_fold, int a_fold_cols,
-                      const void* g_bf16, int g_cols, int g_pitch, int g_col0, float* dw, tcvn_stream_t stream);
+                      const void* g_bf16, int g_cols, int g_pitch, int g_col0, float* dw, void* workspace,
+                      size_t workspace_bytes, tcvn_stream_t stream);
 /* Input gradient of the 3x3 convolution as a 3-tap shifted GEMM:
  *   out[p][c] = sum_dy sum_k g2x[p + (1 - dy) * ring_wp][k] * wd[dy][c][k]   (ring rows of out are written as zero)
  * g2x bf16 [rows][128] (columns dx*32 + n hold G[p + 1 - dx][n]; 96.. zero), wd bf16 [3][128][128], out bf16 [rows][128] */

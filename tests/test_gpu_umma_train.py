@@ -28,9 +28,11 @@ def _wgrad(A, G, items, fold=None, g_col0=0):
     dw = torch.zeros(n, 128, 128, dtype=torch.float32, device=A.device)
     cols, shifts, valid = zip(*items)
     fold_cols = 0 if fold is None else fold.shape[1]
+    ws = torch.empty(L.tcvn_t_umma_wgrad_workspace_bytes(n), dtype=torch.uint8, device=A.device)
     tl.check(L.tcvn_t_umma_wgrad(tl.ptr(A), rows, A.shape[1], A.stride(0), n, _i32(cols), _i32(shifts), _i32(valid),
                                  tl.ptr(fold), fold_cols, tl.ptr(G), G.shape[1], G.stride(0), g_col0, tl.ptr(dw),
-                                 tl.stream_ptr(A.device)), "tcvn_t_umma_wgrad")
+                                 tl.ptr(ws), ws.numel(), tl.stream_ptr(A.device)), "tcvn_t_umma_wgrad")
+    torch.cuda.synchronize()
     return dw
 
 
