@@ -225,7 +225,7 @@ def run_train_leg(args, dev, rank, world, timed, sampler_index):
     out = {"metric": "events/sec, training step (forward + loss + backward + gradient all-reduce + AdamW)",
            "value": world * args.train_events * args.train_steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
            "ms_per_step": ms / args.train_steps, "steps": args.train_steps, "scaling": "weak",
-           "dtype": "f32" if args.train_precision == "fp32" else "bf16",
+           "dtype": "f32" if args.train_precision == "fp32" else "bf16 (activations + tcgen05 GEMM operands; fp32 accumulation, parameters, statistics, gradients of parameters)",
            "config": {"workload": f"BASELINE configs[2]: tutorial DenseNet TransformerCVN, {args.train_events} events/GPU "
                                   f"({images} images on rank 0), dropout {opts.dropout}, AdamW + clip {opts.gradient_clip}",
                       "parallelism": f"event-sharded x{world}, rank-local BatchNorm, NCCL all-reduce of the flat fp32 gradient "
