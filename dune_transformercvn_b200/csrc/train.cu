@@ -219,11 +219,28 @@ template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p,
 
 constexpr int kVecU = 4;  // rows in flight per thread
 
+// a raw 8-element packet as loaded from memory (converted to fp32 only when consumed: half the registers in flight)
+template <typename T> struct Raw8;
+template <> struct Raw8<float> { float4 a, b; };
+template <> struct Raw8<__nv_bfloat16> { uint4 a; };
+__device__ __forceinline__ void ldraw(const float* p, Raw8<float>& r) {
+  r.a = *reinterpret_cast<const float4*>(p); r.b = *reinterpret_cast<const float4*>(p + 4);
+}
+__device__ __forceinline__ void ldraw(const __nv_bfloat16* p, Raw8<__nv_bfloat16>& r) { r.a = *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void unpack8(const Raw8<float>& r, float (&f)[8]) {
+  f[0] = r.a.x; f[1] = r.a.y; f[2] = r.a.z; f[3] = r.a.w; f[4] = r.b.x; f[5] = r.b.y; f[6] = r.b.z; f[7] = r.b.w;
+}
+__device__ __forceinline__ void unpack8(const Raw8<__nv_bfloat16>& r, float (&f)[8]) {
+  const uint32_t w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+
 template <int MODE, typename TX, typename TD>
 __global__ void __launch_bounds__(256, 2) colsum_vec_kernel(const ColDev p, int tv) {
   // slabs are short (<= 64 rows per thread): fp32 partials per thread, doubles only across threads / CTAs
   constexpr int NS = MODE == 0 ? 2 : (MODE == 1 ? 3 : 1);
-  constexpr int U = MODE == 1 ? 2 : kVecU;
+  constexpr int U = (MODE == 1 && sizeof(TX) + sizeof(TD) > 4) ? 2 : kVecU;
   __shared__ double red[256][8];
   const TX* X = static_cast<const TX*>(p.X);
   const TD* D = static_cast<const TD*>(p.D);
@@ -249,33 +266,37 @@ __global__ void __launch_bounds__(256, 2) colsum_vec_kernel(const ColDev p, int 
       }
     }
     for (long long m0 = r_begin + ry; m0 < r_end; m0 += (long long)rpi * U) {
-      float x[U][8], d[U][8];
+      Raw8<TX> xr[U];
+      Raw8<TD> dr[U];
       bool ok[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long m = m0 + (long long)u * rpi;
         ok[u] = m < r_end && !is_ring(m, p.Hp, p.Wp);
         if (ok[u]) {
-          ld8<TX>(X + m * (long long)p.ldx + p.xcol0 + c, x[u]);
-          if (MODE == 1) ld8<TD>(D + m * (long long)p.ldd + p.dcol0 + c, d[u]);
+          ldraw(X + m * (long long)p.ldx + p.xcol0 + c, xr[u]);
+          if (MODE == 1) ldraw(D + m * (long long)p.ldd + p.dcol0 + c, dr[u]);
         }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (!ok[u]) continue;
+        float x[8], d[8];
+        unpack8(xr[u], x);
+        if (MODE == 1) unpack8(dr[u], d);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           if (MODE == 0) {
-            part[0][i] += x[u][i];
-            part[1][i] = fmaf(x[u][i], x[u][i], part[1][i]);
+            part[0][i] += x[i];
+            part[1][i] = fmaf(x[i], x[i], part[1][i]);
           } else if (MODE == 1) {
-            const float y = fmaf(x[u][i], sc[i], sh[i]);
-            const float g = y >= 0.f ? d[u][i] : d[u][i] * al[i];
+            const float y = fmaf(x[i], sc[i], sh[i]);
+            const float g = y >= 0.f ? d[i] : d[i] * al[i];
             part[0][i] += g;
-            part[1][i] = fmaf(g, (x[u][i] - mean[i]) * rstd[i], part[1][i]);
-            part[2][i] = fmaf(d[u][i], fminf(y, 0.f), part[2][i]);
+            part[1][i] = fmaf(g, (x[i] - mean[i]) * rstd[i], part[1][i]);
+            part[2][i] = fmaf(d[i], fminf(y, 0.f), part[2][i]);
           } else {
-            part[0][i] += x[u][i];
+            part[0][i] += x[i];
           }
         }
       }
@@ -300,6 +321,7 @@ __global__ void __launch_bounds__(256, 2) colsum_vec_kernel(const ColDev p, int 
 
 template <typename TX, typename TD, typename TO>
 __global__ void __launch_bounds__(256, 2) bnact_bwd_apply_vec_kernel(const BnBwdDev p, int tv, int rows_per_slab) {
+  constexpr int U = sizeof(TX) + sizeof(TD) + sizeof(TO) > 6 ? 2 : kVecU;
   const int rpi = 256 / tv;
   const int vx = threadIdx.x % tv, ry = threadIdx.x / tv;
   const int c = (blockIdx.x * tv + vx) * 8;
@@ -317,21 +339,23 @@ __global__ void __launch_bounds__(256, 2) bnact_bwd_apply_vec_kernel(const BnBwd
     mean[i] = p.fold[3 * fs + c + i]; rstd[i] = p.fold[4 * fs + c + i];
     mg[i] = (float)(p.sums[c + i] / p.count); mgx[i] = (float)(p.sums[p.C + c + i] / p.count);
   }
-  for (long long m0 = r_begin + ry; m0 < r_end; m0 += (long long)rpi * 2) {
-    float x[2][8], d[2][8], o[2][8];
-    int kind[2];  // 0 skip, 1 ring, 2 interior
+  for (long long m0 = r_begin + ry; m0 < r_end; m0 += (long long)rpi * U) {
+    Raw8<TX> xr[U];
+    Raw8<TD> dr[U];
+    Raw8<TO> orr[U];
+    int kind[U];  // 0 skip, 1 ring, 2 interior
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < U; ++u) {
       const long long m = m0 + (long long)u * rpi;
       kind[u] = m >= r_end ? 0 : (is_ring(m, p.Hp, p.Wp) ? 1 : 2);
       if (kind[u] == 2) {
-        ld8<TX>(X + m * (long long)p.ldx + p.xcol0 + c, x[u]);
-        ld8<TD>(D + m * (long long)p.ldd + p.dcol0 + c, d[u]);
-        if (p.accumulate) ld8<TO>(O + m * (long long)p.lddx + p.dxcol0 + c, o[u]);
+        ldraw(X + m * (long long)p.ldx + p.xcol0 + c, xr[u]);
+        ldraw(D + m * (long long)p.ldd + p.dcol0 + c, dr[u]);
+        if (p.accumulate) ldraw(O + m * (long long)p.lddx + p.dxcol0 + c, orr[u]);
       }
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < U; ++u) {
       const long long m = m0 + (long long)u * rpi;
       if (kind[u] == 0) continue;
       float v[8];
@@ -340,12 +364,16 @@ __global__ void __launch_bounds__(256, 2) bnact_bwd_apply_vec_kernel(const BnBwd
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = 0.f;
       } else {
+        float x[8], d[8], o[8];
+        unpack8(xr[u], x);
+        unpack8(dr[u], d);
+        if (p.accumulate) unpack8(orr[u], o);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float y = fmaf(x[u][i], sc[i], sh[i]);
-          const float g = y >= 0.f ? d[u][i] : d[u][i] * al[i];
-          v[i] = sc[i] * (g - mg[i] - (x[u][i] - mean[i]) * rstd[i] * mgx[i]);
-          if (p.accumulate) v[i] += o[u][i];
+          const float y = fmaf(x[i], sc[i], sh[i]);
+          const float g = y >= 0.f ? d[i] : d[i] * al[i];
+          v[i] = sc[i] * (g - mg[i] - (x[i] - mean[i]) * rstd[i] * mgx[i]);
+          if (p.accumulate) v[i] += o[i];
         }
       }
       st8<TO>(O + m * (long long)p.lddx + p.dxcol0 + c, v);
@@ -456,61 +484,79 @@ __global__ void bnact_fwd_kernel(const TX* __restrict__ X, int ldx, int xcol0, c
 template <typename TO>
 __global__ void stem_pool_fwd_kernel(const float* __restrict__ z, const float* __restrict__ fold, int Hs, int Ws, int C,
                                      TO* __restrict__ blk, int ld, int H, int W, long long total) {
+  // one thread = one pooled pixel x 4 channels (float4 loads of the 3x3 window); total counts those quads
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int c = (int)(idx % C);
-  long long r = idx / C;
+  const int cq = C >> 2;
+  const int c = (int)(idx % cq) * 4;
+  long long r = idx / cq;
   const int x = (int)(r % W); r /= W;
   const int y = (int)(r % H);
   const int n = (int)(r / H);
-  const float sc = fold[c], sh = fold[C + c], al = fold[2 * C + c];
-  float s = 0.f;
+  const float4 sc = *reinterpret_cast<const float4*>(fold + c), sh = *reinterpret_cast<const float4*>(fold + C + c),
+               al = *reinterpret_cast<const float4*>(fold + 2 * C + c);
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
   for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-    for (int dx = 0; dx < 3; ++dx)
-      s += prelu(fmaf(z[(((size_t)n * Hs + 2 * y + dy) * Ws + 2 * x + dx) * C + c], sc, sh), al);
-  blk[((size_t)n * (H + 2) * (W + 2) + (size_t)(y + 1) * (W + 2) + x + 1) * ld + c] = from_f32<TO>(s / 9.0f);
+    for (int dx = 0; dx < 3; ++dx) {
+      const float4 v = *reinterpret_cast<const float4*>(z + (((size_t)n * Hs + 2 * y + dy) * Ws + 2 * x + dx) * C + c);
+      s0 += prelu(fmaf(v.x, sc.x, sh.x), al.x);
+      s1 += prelu(fmaf(v.y, sc.y, sh.y), al.y);
+      s2 += prelu(fmaf(v.z, sc.z, sh.z), al.z);
+      s3 += prelu(fmaf(v.w, sc.w, sh.w), al.w);
+    }
+  TO* dst = blk + ((size_t)n * (H + 2) * (W + 2) + (size_t)(y + 1) * (W + 2) + x + 1) * ld + c;
+  dst[0] = from_f32<TO>(s0 / 9.0f); dst[1] = from_f32<TO>(s1 / 9.0f); dst[2] = from_f32<TO>(s2 / 9.0f); dst[3] = from_f32<TO>(s3 / 9.0f);
 }
 
 // gradient of the above w.r.t. the activated stem map: dA[n,oy,ox,c] = (1/9) sum of dP over the windows holding (oy,ox)
 __global__ void stem_pool_bwd_kernel(const float* __restrict__ dblk, int ld, int H, int W, int C, float* __restrict__ dA,
                                      int Hs, int Ws, long long total) {
+  // one thread = one stem pixel x 4 channels; window py covers rows 2py .. 2py+2
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int c = (int)(idx % C);
-  long long r = idx / C;
+  const int cq = C >> 2;
+  const int c = (int)(idx % cq) * 4;
+  long long r = idx / cq;
   const int ox = (int)(r % Ws); r /= Ws;
   const int oy = (int)(r % Hs);
   const int n = (int)(r / Hs);
-  float s = 0.f;
-  for (int py = max(0, (oy - 1) / 2); py <= min(H - 1, oy / 2); ++py) {
-    if (2 * py > oy || oy > 2 * py + 2) continue;
-    for (int px = max(0, (ox - 1) / 2); px <= min(W - 1, ox / 2); ++px) {
-      if (2 * px > ox || ox > 2 * px + 2) continue;
-      s += dblk[((size_t)n * (H + 2) * (W + 2) + (size_t)(py + 1) * (W + 2) + px + 1) * ld + c];
+  const int py_lo = oy >= 2 ? (oy - 1) >> 1 : 0, py_hi = min(H - 1, oy >> 1);
+  const int px_lo = ox >= 2 ? (ox - 1) >> 1 : 0, px_hi = min(W - 1, ox >> 1);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int py = py_lo; py <= py_hi; ++py)
+    for (int px = px_lo; px <= px_hi; ++px) {
+      const float4 v = *reinterpret_cast<const float4*>(dblk + ((size_t)n * (H + 2) * (W + 2) + (size_t)(py + 1) * (W + 2) + px + 1) * ld + c);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
-  }
-  dA[idx] = s / 9.0f;
+  *reinterpret_cast<float4*>(dA + (((size_t)n * Hs + oy) * Ws + ox) * C + c) = make_float4(s.x / 9.0f, s.y / 9.0f, s.z / 9.0f, s.w / 9.0f);
 }
 
 // AvgPool2d(2,2) backward: dA[ringed H x W rows, C] = 0.25 * dP[ringed H2 x W2 parent] (0 where the floor cropped)
 template <typename T>
 __global__ void pool2_bwd_kernel(const T* __restrict__ dP, int H2, int W2, int C, T* __restrict__ dA, int H, int W,
                                  long long total) {
+  // one thread = one ringed pixel x 8 channels; total counts those octets
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
-  const int c = (int)(idx % C);
-  long long r = idx / C;
+  const int cv = C >> 3;
+  const int c = (int)(idx % cv) * 8;
+  long long r = idx / cv;
   const int Wp = W + 2, Hp = H + 2;
   const int xx = (int)(r % Wp); r /= Wp;
   const int yy = (int)(r % Hp);
   const int n = (int)(r / Hp);
-  float v = 0.f;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 0.f;
   const int y = yy - 1, x = xx - 1;
-  if (y >= 0 && y < 2 * H2 && x >= 0 && x < 2 * W2)
-    v = 0.25f * to_f32<T>(dP[((size_t)n * (H2 + 2) * (W2 + 2) + (size_t)(y / 2 + 1) * (W2 + 2) + x / 2 + 1) * C + c]);
-  dA[idx] = from_f32<T>(v);
+  if (y >= 0 && y < 2 * H2 && x >= 0 && x < 2 * W2) {
+    ld8<T>(dP + ((size_t)n * (H2 + 2) * (W2 + 2) + (size_t)(y / 2 + 1) * (W2 + 2) + x / 2 + 1) * C + c, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= 0.25f;
+  }
+  st8<T>(dA + (((size_t)n * Hp + yy) * Wp + xx) * C + c, v);
 }
 
 // global average pool backward: dA[ringed rows, C] = dGap[n, c] / (H*W) on interior rows
@@ -552,9 +598,9 @@ __global__ void dropout_kernel(T* X, int ld, int col0, int C, long long m_total,
 // stem convolution for training: raw conv0 output (no bias fold) and its weight gradient, both hit-driven
 // ------------------------------------------------------------------------------------------------
 // z[n,oy,ox,c] = b[c] + sum over hits: one thread per (hit, output position) pair walks the 64 channels
-__global__ void stem_fill_bias_kernel(float* z, const float* __restrict__ bias, int C, long long total) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx < total) z[idx] = bias[idx % C];
+__global__ void stem_fill_bias_kernel(float* z, const float* __restrict__ bias, int C, long long total4) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one float4 per thread (C % 4 == 0)
+  if (idx < total4) reinterpret_cast<float4*>(z)[idx] = *reinterpret_cast<const float4*>(bias + (int)((idx * 4) % C));
 }
 
 // pixels NCHW fp32; for every non-zero input value scatter v*w into the <=16 outputs it reaches (atomic: training path)
@@ -627,7 +673,7 @@ int colsums_typed(int mode, const void* X, bool x_bf16, int ldx, int xcol0, cons
     const int gx = ceil_div(cv, tv);
     // short slabs: one slab = 16 row-steps of a CTA (<= 64 rows per thread), at most ~16 CTAs per SM in total
     long long vslabs = ceil_div_ll(m_total, (long long)rpi * kVecU * 4);
-    const long long cap = (long long)(148 * 16 / gx > 1 ? 148 * 16 / gx : 1);
+    const long long cap = (long long)(148 * 4 / gx > 1 ? 148 * 4 / gx : 1);
     if (vslabs > cap) vslabs = cap;
     p.rows_per_slab = (int)ceil_div_ll(m_total, vslabs);
     vslabs = ceil_div_ll(m_total, p.rows_per_slab);
@@ -687,8 +733,8 @@ int bnact_bwd_apply_typed(const void* D, bool d_bf16, int ldd, int dcol0, const 
     const int tv = cv < 32 ? cv : 32;
     const int rpi = 256 / tv;
     const int gx = ceil_div(cv, tv);
-    long long vslabs = ceil_div_ll(m_total, (long long)rpi * 2 * 4);
-    const long long cap = (long long)(148 * 16 / gx > 1 ? 148 * 16 / gx : 1);
+    long long vslabs = ceil_div_ll(m_total, (long long)rpi * kVecU * 2);
+    const long long cap = (long long)(148 * 8 / gx > 1 ? 148 * 8 / gx : 1);
     if (vslabs > cap) vslabs = cap;
     const int rows_per_slab = (int)ceil_div_ll(m_total, vslabs);
     const int slabs = (int)ceil_div_ll(m_total, rows_per_slab);
@@ -737,20 +783,21 @@ int bnact_fwd_typed(const void* X, bool x_bf16, int ldx, int xcol0, const float*
 int pool_typed(int kind, const void* src, const float* fold, void* dst, bool bf16, int n, int C, int H, int W, int H2, int W2,
                int ld, cudaStream_t stream) {
   if (n <= 0) return TCVN_OK;
+  if (C % 8 != 0 || ld % 4 != 0) return fail(TCVN_ERR_UNSUPPORTED, "pool: channel count %d / pitch %d must be multiples of 8 / 4", C, ld);
   typedef __nv_bfloat16 bf;
   long long total;
   switch (kind) {
     case 0:
-      total = (long long)n * H * W * C;
+      total = (long long)n * H * W * (C / 4);
       if (bf16) stem_pool_fwd_kernel<bf><<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const float*>(src), fold, H2, W2, C, static_cast<bf*>(dst), ld, H, W, total);
       else stem_pool_fwd_kernel<float><<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const float*>(src), fold, H2, W2, C, static_cast<float*>(dst), ld, H, W, total);
       break;
     case 1:   // gradient buffers of a block are fp32 in both precisions
-      total = (long long)n * H2 * W2 * C;
+      total = (long long)n * H2 * W2 * (C / 4);
       stem_pool_bwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const float*>(src), ld, H, W, C, static_cast<float*>(dst), H2, W2, total);
       break;
     case 2:
-      total = (long long)n * (H + 2) * (W + 2) * C;
+      total = (long long)n * (H + 2) * (W + 2) * (C / 8);
       if (bf16) pool2_bwd_kernel<bf><<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const bf*>(src), H2, W2, C, static_cast<bf*>(dst), H, W, total);
       else pool2_bwd_kernel<float><<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const float*>(src), H2, W2, C, static_cast<float*>(dst), H, W, total);
       break;
@@ -897,8 +944,8 @@ extern "C" int tcvn_t_stem_conv(const float* pixels, int n, int cin, int H, int 
   if (n <= 0) return TCVN_OK;
   const int Hs = (H + 6 - 7) / 2 + 1, Ws = (W + 6 - 7) / 2 + 1;
   if (dz == nullptr) {
-    const long long outs = (long long)n * Hs * Ws * C;
-    stem_fill_bias_kernel<<<(unsigned)ceil_div_ll(outs, 256), 256, 0, stream>>>(z, bias, C, outs);
+    const long long outs4 = (long long)n * Hs * Ws * C / 4;
+    stem_fill_bias_kernel<<<(unsigned)ceil_div_ll(outs4, 256), 256, 0, stream>>>(z, bias, C, outs4);
     TCVN_LAUNCH_CHECK();
   }
   const long long total = (long long)n * cin * H * W;
