@@ -600,7 +600,10 @@ __global__ void dropout_kernel(T* X, int ld, int col0, int C, long long m_total,
 // z[n,oy,ox,c] = b[c] + sum over hits: one thread per (hit, output position) pair walks the 64 channels
 __global__ void stem_fill_bias_kernel(float* z, const float* __restrict__ bias, int C, long long total4) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one float4 per thread (C % 4 == 0)
-  if (idx < total4) reinterpret_cast<float4*>(z)[idx] = *reinterpret_cast<const float4*>(bias + (int)((idx * 4) % C));
+  if (idx < total4) {   // the bias lives in the parameter arena: no alignment guarantee, scalar loads
+    const int c = (int)((idx * 4) % C);
+    reinterpret_cast<float4*>(z)[idx] = make_float4(__ldg(bias + c), __ldg(bias + c + 1), __ldg(bias + c + 2), __ldg(bias + c + 3));
+  }
 }
 
 // pixels NCHW fp32; for every non-zero input value scatter v*w into the <=16 outputs it reaches (atomic: training path)
