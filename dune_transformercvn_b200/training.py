@@ -172,6 +172,10 @@ class TrainEngine:
         self.exchange: Optional[GradientExchange] = None
         self.saved = None
         self._nbt: Optional[List[torch.Tensor]] = None
+        # the two pixel-map CNNs are independent until the token assembly: the (small, launch-bound) event CNN runs on
+        # a side stream under the (large) prong CNN, forward and backward
+        self.overlap_cnns = True
+        self._side: Optional[torch.cuda.Stream] = None
 
     def workspace(self, kind: str, nbytes: int, dev) -> torch.Tensor:
         buf = self.ws.get(kind)
@@ -206,6 +210,12 @@ class TrainEngine:
         pr_px = prong_pixels.contiguous().float()
         f32 = dict(dtype=torch.float32, device=dev)
         emb = {"event": torch.empty((b, pix + feat), **f32), "prong": torch.empty((t, pix), **f32)}
+        main = torch.cuda.current_stream(dev)
+        side = None
+        if self.overlap_cnns:
+            if self._side is None or self._side.device != dev:
+                self._side = torch.cuda.Stream(device=dev)
+            side = self._side
         for site, (tag, px, n) in enumerate((("event", ev_px, b), ("prong", pr_px, t)), start=1):
             d = self._cnn_desc(tag)
             if tuple(px.shape[1:]) != (d.in_channels, d.height, d.width):
@@ -214,8 +224,14 @@ class TrainEngine:
             if nbytes == 0:
                 raise _lib.TcvnError("tcvn_cnn_train_workspace_bytes: " + L.tcvn_last_error().decode())
             ws = self.workspace("cnn_" + tag, nbytes, dev)
+            use = side if (side is not None and tag == "event") else main
+            if use is side:
+                side.wait_stream(main)        # inputs, parameters and the workspace zero-fill were issued on main
             _lib.check(L.tcvn_cnn_train_forward(C.byref(d), prec, self.arena.ptr(tag), _lib.ptr(px), n, p_drop, BN_MOMENTUM, seed, site,
-                                                _lib.ptr(emb[tag]), _lib.ptr(ws), ws.numel(), st), f"tcvn_cnn_train_forward({tag})")
+                                                _lib.ptr(emb[tag]), _lib.ptr(ws), ws.numel(), C.c_void_p(use.cuda_stream)),
+                       f"tcvn_cnn_train_forward({tag})")
+        if side is not None:
+            main.wait_stream(side)
         sd = net.engine.seq_desc()
         pm = prong_mask.contiguous().to(torch.uint8)
         em = None if event_mask is None else event_mask.contiguous().to(torch.uint8)
@@ -268,15 +284,24 @@ class TrainEngine:
             lo = a.seg["combined"][0]
             ex.reduce(a.gflat[lo:])                       # combined embedding, encoder, both heads
             ex.reduce(a.grad_slice("position"))
-        # event CNN first: its (small) exchange then overlaps the long prong-CNN backward
+        # event CNN on the side stream (its small exchange then overlaps the long prong-CNN backward as well)
+        main = torch.cuda.current_stream(dev)
+        side = self._side if self.overlap_cnns else None
         for site, tag, px, n in ((1, "event", s["ev_px"], b), (2, "prong", s["pr_px"], t)):
             d = self._cnn_desc(tag)
             ws = self.ws["cnn_" + tag]
+            use = side if (side is not None and tag == "event") else main
+            if use is side:
+                side.wait_stream(main)
+                d_emb[tag].record_stream(side)
             _lib.check(L.tcvn_cnn_train_backward(C.byref(d), s["prec"], a.ptr(tag), a.ptr(tag, True), _lib.ptr(px), n, s["p_drop"], s["seed"],
-                                                 site, _lib.ptr(d_emb[tag]), _lib.ptr(ws), ws.numel(), st),
+                                                 site, _lib.ptr(d_emb[tag]), _lib.ptr(ws), ws.numel(), C.c_void_p(use.cuda_stream)),
                        f"tcvn_cnn_train_backward({tag})")
             if ex is not None:
-                ex.reduce(a.grad_slice(tag))
+                with torch.cuda.stream(use):
+                    ex.reduce(a.grad_slice(tag))
+        if side is not None:
+            main.wait_stream(side)
 
 
 class _TrainFn(torch.autograd.Function):
