@@ -3,6 +3,8 @@
 #include "common.cuh"
 #include "plan.h"
 
+#include <vector>
+
 namespace tcvn {
 
 // out[m, col0 + n] = epi( sum_t sum_k act(A[m + tap_off[t], k]) * W[t][k][n] )   (fp32 CUDA-core path)
@@ -50,6 +52,16 @@ int repack(const float* src, int n_log, int k_log, int taps, int c0, int c0p, in
            bool bf16, void* dst, cudaStream_t st, const float* row_bn_w = nullptr, const float* row_bn_rv = nullptr,
            float eps = 0.f);
 int pad_copy(const float* src, int n_log, float* dst, int n_out, cudaStream_t st);
+// a list of re-layouts executed in one launch per 96 entries (pack.cu).  k_major: 0 dst[tap][k][n], 1 dst[tap][n][k],
+// 2 conv2 weight -> Wd[dy][c][dx*32+n] bf16 (the conv2 input-gradient operand; the shape arguments are ignored
+// except taps*K_out*N_out = 3*128*128)
+struct RepackList {
+  struct Entry { unsigned char raw[80]; };
+  std::vector<Entry> items;
+  void add(const float* src, int n_log, int k_log, int taps, int c0, int c0p, int K_out, int N_out, int k_major, bool bf16,
+           void* dst);
+  int run(cudaStream_t st);
+};
 
 // train.cu: typed cores of the training primitives (bool *_bf16 = element type of that operand; false = fp32)
 int colsums_typed(int mode, const void* X, bool x_bf16, int ldx, int xcol0, const void* D, bool d_bf16, int ldd, int dcol0,

@@ -7,6 +7,8 @@
 #include "kernels.h"
 #include "plan.h"
 
+#include <string.h>
+
 namespace tcvn {
 
 struct FoldArgs {
@@ -75,6 +77,50 @@ __global__ void repack_kernel(const RepackArgs a) {
   else static_cast<float*>(a.dst)[idx] = v;
 }
 
+// many re-layouts in ONE launch (blockIdx.y = entry): the training walks rebuild ~120 weight layouts per CNN per step
+constexpr int kRepackBatch = 96;
+struct RepackBatchArgs { RepackArgs e[kRepackBatch]; };
+
+__device__ __forceinline__ void repack_one(const RepackArgs& a, long long idx) {
+  const long long total = (long long)a.taps * a.K_out * a.N_out;
+  if (idx >= total) return;
+  int tap, n, kp;
+  if (a.k_major == 2) {
+    // conv2 weight [n = 32][c = 128][dy][dx] -> Wd[dy][c][dx * 32 + n] (columns 96.. zero): input-gradient operand
+    const int col = (int)(idx & 127), c = (int)((idx >> 7) & 127), dy = (int)(idx >> 14);
+    float v = 0.f;
+    if (col < 96) v = a.src[((size_t)((col & 31) * 128 + c) * 3 + dy) * 3 + (col >> 5)];
+    static_cast<__nv_bfloat16*>(a.dst)[idx] = __float2bfloat16_rn(v);
+    return;
+  }
+  if (a.k_major) {
+    kp = (int)(idx % a.K_out);
+    n = (int)((idx / a.K_out) % a.N_out);
+    tap = (int)(idx / ((long long)a.K_out * a.N_out));
+  } else {
+    n = (int)(idx % a.N_out);
+    kp = (int)((idx / a.N_out) % a.K_out);
+    tap = (int)(idx / ((long long)a.K_out * a.N_out));
+  }
+  int k = -1;
+  if (kp < a.c0) k = kp;
+  else if (kp >= a.c0p) k = kp - (a.c0p - a.c0);
+  float v = 0.f;
+  if (k >= 0 && k < a.k_log && n < a.n_log) {
+    v = a.src[((size_t)n * a.k_log + k) * a.taps + tap];
+    if (a.row_bn_w) v *= a.row_bn_w[n] / sqrtf(a.row_bn_rv[n] + a.eps);
+  }
+  if (a.bf16) static_cast<__nv_bfloat16*>(a.dst)[idx] = __float2bfloat16_rn(v);
+  else static_cast<float*>(a.dst)[idx] = v;
+}
+
+__global__ void repack_batch_kernel(const __grid_constant__ RepackBatchArgs b) {
+  const RepackArgs& a = b.e[blockIdx.y];
+  const long long total = (long long)a.taps * a.K_out * a.N_out;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x)
+    repack_one(a, idx);
+}
+
 __global__ void pad_copy_kernel(const float* src, int n_log, float* dst, int n_out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_out) dst[i] = i < n_log ? src[i] : 0.f;
@@ -113,6 +159,31 @@ int repack(const float* src, int n_log, int k_log, int taps, int c0, int c0p, in
   const long long total = (long long)taps * K_out * N_out;
   repack_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(r);
   TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+void RepackList::add(const float* src, int n_log, int k_log, int taps, int c0, int c0p, int K_out, int N_out, int k_major,
+                     bool bf16, void* dst) {
+  RepackArgs r;
+  r.row_bn_w = nullptr; r.row_bn_rv = nullptr; r.eps = 0.f;
+  r.src = src; r.n_log = n_log; r.k_log = k_log; r.taps = taps; r.c0 = c0; r.c0p = c0p; r.K_out = K_out; r.N_out = N_out;
+  r.k_major = k_major; r.bf16 = bf16; r.dst = dst;
+  static_assert(sizeof(RepackArgs) == sizeof(RepackList::Entry), "RepackList::Entry must mirror RepackArgs");
+  Entry e;
+  memcpy(&e, &r, sizeof(r));
+  items.push_back(e);
+}
+
+int RepackList::run(cudaStream_t st) {
+  for (size_t i0 = 0; i0 < items.size(); i0 += kRepackBatch) {
+    const int n = (int)(items.size() - i0 < (size_t)kRepackBatch ? items.size() - i0 : kRepackBatch);
+    RepackBatchArgs b;
+    memcpy(b.e, items.data() + i0, sizeof(RepackArgs) * n);
+    dim3 grid(64, n);
+    repack_batch_kernel<<<grid, 256, 0, st>>>(b);
+    TCVN_LAUNCH_CHECK();
+  }
+  items.clear();
   return TCVN_OK;
 }
 

@@ -505,7 +505,7 @@ struct TrainPlan16 {
     T->lw = take((size_t)last.ctot * d.out_features * 4);
     T->lwt = take((size_t)last.ctot * d.out_features * 4);
     if ((size_t)last.ctot * d.out_features > max_dw) max_dw = (size_t)last.ctot * d.out_features;
-    if ((size_t)4 * 128 * 128 > max_dw) max_dw = (size_t)4 * 128 * 128;
+    max_dw += (size_t)4 * 128 * 128;   // a weight-gradient tile group behind the largest assembled matrix
     T->sA = take(max_rc * 2);
     T->sB = take(max_rc * 2);
     T->dmid = take(max_rows * mid * 2);
@@ -588,6 +588,16 @@ __global__ void unpack_conv2_grad_kernel(const float* __restrict__ dw, float* __
   dst[idx] += dw[(dy * 128 + k) * 128 + dx * 32 + n];
 }
 
+// dst[(k0 + it*128 + r) * ld + n0 + c] = dw[it][r][c] for the valid rows / columns of a weight-gradient tile group
+__global__ void scatter_wgrad_tiles_kernel(const float* __restrict__ dw, int n_items, int k0, int k_total, int n0, int n_valid,
+                                           float* __restrict__ dst, int ld) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_items * 128 * 128) return;
+  const int c = idx & 127, r = (idx >> 7) & 127, it = idx >> 14;
+  const int k = k0 + it * 128 + r;
+  if (k < k_total && c < n_valid) dst[(size_t)k * ld + n0 + c] = dw[idx];
+}
+
 __global__ void fill_f32_kernel(float* dst, int n, float v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = v;
@@ -653,32 +663,31 @@ struct TWalk16 {
     const CnnPlan& P = T.P;
     const tcvn_cnn_desc& d = P.d;
     const int mid = P.mid, g = d.growth;
-    TCVN_TRY(repack(arena + P.conv0_w, d.init_features, d.in_channels * 49, 1, NOGAP, NOGAP, d.in_channels * 49,
-                    d.init_features, false, false, f(T.w0), st));
+    RepackList R;   // every weight re-layout of the step in two or three launches
+    R.add(arena + P.conv0_w, d.init_features, d.in_channels * 49, 1, NOGAP, NOGAP, d.in_channels * 49, d.init_features, 0, false,
+          f(T.w0));
     for (size_t b = 0; b < P.blocks.size(); ++b) {
       const BlockPlan& B = P.blocks[b];
       const T16Block& X = T.blocks[b];
       for (size_t i = 0; i < B.layers.size(); ++i) {
         const LayerPlan& L = B.layers[i];
         const T16Layer& Y = X.layers[i];
-        TCVN_TRY(repack(arena + L.conv1_w, mid, L.cin, 1, B.c0, B.c0p, L.kpad, mid, true, true, h(Y.w1b), st));
-        TCVN_TRY(repack(arena + L.conv1_w, mid, L.cin, 1, B.c0, B.c0p, L.kphys, mid, false, true, h(Y.w1d), st));
-        TCVN_TRY(repack(arena + L.conv2_w, g, mid, 9, NOGAP, NOGAP, mid, g, true, true, h(Y.w2b), st));
-        pack_wd_kernel<<<ceil_div(3 * 128 * 128, 256), 256, 0, st>>>(arena + L.conv2_w, h(Y.wd));
-        TCVN_LAUNCH_CHECK();
+        R.add(arena + L.conv1_w, mid, L.cin, 1, B.c0, B.c0p, L.kpad, mid, 1, true, h(Y.w1b));
+        R.add(arena + L.conv1_w, mid, L.cin, 1, B.c0, B.c0p, L.kphys, mid, 0, true, h(Y.w1d));
+        R.add(arena + L.conv2_w, g, mid, 9, NOGAP, NOGAP, mid, g, 1, true, h(Y.w2b));
+        R.add(arena + L.conv2_w, g, mid, 3, NOGAP, NOGAP, 128, 128, 2, true, h(Y.wd));
       }
       if (B.has_transition) {
         const int n16 = B.tn_tiles * 128;
-        TCVN_TRY(repack(arena + B.tconv_w, B.tout, B.clog, 1, B.c0, B.c0p, B.tkpad, n16, true, true, h(X.wtb), st));
-        TCVN_TRY(repack(arena + B.tconv_w, B.tout, B.clog, 1, B.c0, B.c0p, B.ctot, X.gt_pitch, false, true, h(X.wtd), st));
+        R.add(arena + B.tconv_w, B.tout, B.clog, 1, B.c0, B.c0p, B.tkpad, n16, 1, true, h(X.wtb));
+        R.add(arena + B.tconv_w, B.tout, B.clog, 1, B.c0, B.c0p, B.ctot, X.gt_pitch, 0, true, h(X.wtd));
         TCVN_TRY(pad_copy(arena + B.tconv_b, B.tout, f(X.tb16), n16, st));
       }
     }
     const BlockPlan& last = P.blocks.back();
-    TCVN_TRY(repack(arena + P.lin_w, d.out_features, last.clog, 1, last.c0, last.c0p, last.ctot, d.out_features, false,
-                    false, f(T.lw), st));
-    TCVN_TRY(repack(arena + P.lin_w, d.out_features, last.clog, 1, last.c0, last.c0p, last.ctot, d.out_features, true,
-                    false, f(T.lwt), st));
+    R.add(arena + P.lin_w, d.out_features, last.clog, 1, last.c0, last.c0p, last.ctot, d.out_features, 0, false, f(T.lw));
+    R.add(arena + P.lin_w, d.out_features, last.clog, 1, last.c0, last.c0p, last.ctot, d.out_features, 1, false, f(T.lwt));
+    TCVN_TRY(R.run(st));
     fill_f32_kernel<<<4, 256, 0, st>>>(f(T.zeros), 1024, 0.f);
     TCVN_LAUNCH_CHECK();
     fill_f32_kernel<<<4, 256, 0, st>>>(f(T.ones), 1024, 1.f);
@@ -714,15 +723,16 @@ struct TWalk16 {
         float* f1 = f(Y.fold1);
         TCVN_TRY(finalize(s1, s2, L.kpad, L.norm1, B.c0, B.c0p, count, f1));
         // raw conv1 output (+ bias): the BN2 statistics are taken from exactly the bf16 values conv2 will read
+        // conv1 (+ bias), raw: the epilogue also accumulates the BN2 batch statistics from exactly the bf16 values it
+        // stores; conv2's epilogue applies Dropout and accumulates the statistics of the 32 new concat channels
+        double* sc2 = dbl(T.sums_scr);
+        TCVN_CUDA(cudaMemsetAsync(sc2, 0, sizeof(double) * 2 * mid, st));
         TCVN_TRY(launch_gemm(true, blk, rows, B.ctot, B.ctot, h(Y.w1b), mid, L.kpad, L.kphys, f1, f1 + L.kpad, f1 + 2 * L.kpad,
-                             arena + L.conv1_b, f(T.ones), h(Y.mid_raw), mid, mid, 1, B.Hp, B.Wp, st));
-        TCVN_TRY(stats_scratch(h(Y.mid_raw), true, mid, 0, mid, rows, B.Hp, B.Wp));
-        TCVN_TRY(finalize(dbl(T.sums_scr), dbl(T.sums_scr) + mid, mid, L.norm2, NOGAP, NOGAP, count, f(Y.fold2)));
+                             arena + L.conv1_b, f(T.ones), h(Y.mid_raw), mid, mid, 1, B.Hp, B.Wp, st, sc2, mid));
+        TCVN_TRY(finalize(sc2, sc2 + mid, mid, L.norm2, NOGAP, NOGAP, count, f(Y.fold2)));
         TCVN_TRY(bnact_fwd_typed(h(Y.mid_raw), true, mid, 0, f(Y.fold2), mid, mid, rows, B.Hp, B.Wp, h(Y.mid_act), true, mid, 0, st));
-        TCVN_TRY(umma_conv2_fwd(h(Y.mid_act), rows, h(Y.w2b), arena + L.conv2_b, blk, B.ctot, L.kphys, B.Hp, B.Wp, B.W, st));
-        TCVN_TRY(dropout_typed(blk, true, B.ctot, L.kphys, g, rows, seed, site * 4096 + b * 64 + i, p_drop, st));
-        TCVN_TRY(colsums_typed(0, blk, true, B.ctot, L.kphys, nullptr, false, 0, 0, nullptr, 0, g, rows, B.Hp, B.Wp, s1 + L.kphys,
-                               B.ctot, st));
+        TCVN_TRY(umma_conv2_fwd(h(Y.mid_act), rows, h(Y.w2b), arena + L.conv2_b, blk, B.ctot, L.kphys, B.Hp, B.Wp, B.W, st, p_drop,
+                                seed, site * 4096 + b * 64 + i, s1 + L.kphys, B.ctot));
       }
       if (B.has_transition) {
         const BlockPlan& Nx = P.blocks[b + 1];
@@ -827,9 +837,26 @@ struct TWalk16 {
         bf* gt = h(T.gt);
         to_bf16_pad_kernel<<<(unsigned)ceil_div_ll(rows * Xp.gt_pitch, 256), 256, 0, st>>>(gblk, B.ctot, Pv.toutp, rows, Xp.gt_pitch, gt);
         TCVN_LAUNCH_CHECK();
-        TCVN_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)Pv.ctot * Pv.toutp, st));
-        TCVN_TRY(wgrad_typed(h(Xp.pooled), true, Pv.ctot, rows, Pv.ctot, 1, nullptr, nullptr, nullptr, nullptr, B.Hp, B.Wp, gt, true,
-                             Xp.gt_pitch, 0, Pv.toutp, B.Hp, B.Wp, dwp, st));
+        // transition weight gradient dW[k][n] = sum_m pooled[m, k] * Gt[m, n] on the MN-major tensor-core kernel: groups
+        // of <= 4 x 128 input channels against 128-column tiles of Gt, scattered into the [ctot][toutp] scratch
+        {
+          float* tile = dwp + (size_t)Pv.ctot * Pv.toutp;   // [4][128][128] behind the assembled matrix
+          for (int k0 = 0; k0 < Pv.ctot; k0 += 512) {
+            const int n_items = ceil_div((Pv.ctot - k0 < 512 ? Pv.ctot - k0 : 512), 128);
+            int cols[4], shifts[4], valid[4];
+            for (int j = 0; j < n_items; ++j) {
+              cols[j] = k0 + 128 * j; shifts[j] = 0;
+              valid[j] = Pv.ctot - cols[j] < 128 ? Pv.ctot - cols[j] : 128;
+            }
+            for (int n0 = 0; n0 < Pv.toutp; n0 += 128) {
+              TCVN_TRY(umma_wgrad(h(Xp.pooled), rows, Pv.ctot, Pv.ctot, n_items, cols, shifts, valid, nullptr, nullptr, nullptr, 0, gt,
+                                  Xp.gt_pitch, Xp.gt_pitch, n0, f(T.parts), tile, false, st));
+              scatter_wgrad_tiles_kernel<<<ceil_div(n_items * 128 * 128, 256), 256, 0, st>>>(
+                  tile, n_items, k0, Pv.ctot, n0, Pv.toutp - n0 < 128 ? Pv.toutp - n0 : 128, dwp, Pv.toutp);
+              TCVN_LAUNCH_CHECK();
+            }
+          }
+        }
         TCVN_TRY(unpack(dwp, 1, Pv.ctot, Pv.toutp, Pv.tout, Pv.clog, Pv.c0, Pv.c0p, garena + Pv.tconv_w));
         TCVN_TRY(launch_gemm(false, gt, rows, Xp.gt_pitch, Xp.gt_pitch, h(Xp.wtd), Pv.ctot, Xp.gt_pitch, Xp.gt_pitch, nullptr, nullptr,
                              nullptr, f(T.zeros), f(T.ones), h(T.sA), Pv.ctot, Pv.ctot, ceil_div(Pv.ctot, 128), B.Hp, B.Wp, st));

@@ -111,6 +111,9 @@ struct GemmParams {
   const float *a_scale, *a_shift, *a_alpha;  // [kchunks*64] (TRANSFORM only)
   const float *o_shift, *o_alpha;            // [n_tiles_n*128]
   int Hp, Wp, num_tiles;   // num_tiles = m tiles * n_tiles_n
+  // training: per-column (sum, sum^2) of the bf16 values this kernel stores (ring rows are zero), accumulated into
+  // stats[0..128) and stats[stats_stride..+128) - the batch statistics of the BatchNorm that follows (n_tiles_n == 1)
+  double* stats; int stats_stride;
 };
 
 __device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
@@ -266,6 +269,8 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
     uint32_t* s_alpha2 = reinterpret_cast<uint32_t*>(s_shift + kMid);     // [64] bf16x2
     uint32_t acc_phase = 0;
     int it = 0;
+    double st_sum = 0.0, st_sq = 0.0;   // this thread's column (training statistics)
+    const int e_col = threadIdx.x - (10 + 4 * grp) * 32;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       if ((it & 1) != grp) continue;
       const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
@@ -333,9 +338,31 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
         ptx::tma_store_2d(&tmO, stg + kStageA, nt * kMid + 64, mt * kTileM);
         ptx::tma_store_commit();
       }
+      if (p.stats != nullptr) {
+        // column e_col of the staged tile (exactly the bf16 values being stored); rows beyond m_total hold zeros from
+        // the zero-filled A rows only if the shift is zero, so they are skipped explicitly
+        const uint8_t* colp = stg + (e_col >> 6) * kStageA + (e_col & 7) * 2;
+        const int chunk = (e_col & 63) >> 3;
+        const long long m0 = (long long)mt * kTileM;
+        const int rmax = (int)(p.m_total - m0 < kTileM ? p.m_total - m0 : kTileM);
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+        for (int r = 0; r < kTileM; ++r) {
+          const unsigned short raw = *reinterpret_cast<const unsigned short*>(colp + r * 128 + ((chunk ^ (r & 7)) << 4));
+          const float v = r < rmax ? __uint_as_float((uint32_t)raw << 16) : 0.f;
+          s1 += v;
+          s2 = fmaf(v, v, s2);
+        }
+        st_sum += (double)s1;
+        st_sq += (double)s2;
+      }
       acc_phase ^= 1;
     }
     if (issuer) ptx::tma_store_wait_all();
+    if (p.stats != nullptr && it > 0) {
+      atomicAdd(p.stats + e_col, st_sum);
+      atomicAdd(p.stats + p.stats_stride + e_col, st_sq);
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -367,7 +394,54 @@ struct Conv2Params {
   const float* bias;
   bf16* out;
   int ldo, col0, num_tiles;
+  // training: Dropout(p) on the 32 new channels (mask = hash(seed, site, row * 32 + channel), re-derived in backward) and
+  // their per-column (sum, sum^2) as stored (bf16), accumulated into stats[0..32) / stats[stats_stride..+32)
+  float p_drop; unsigned long long seed, site;
+  double* stats; int stats_stride;
 };
+
+__device__ __forceinline__ bool drop_keep_c2(unsigned long long seed, unsigned long long site, unsigned long long idx, float p) {
+  unsigned long long z = seed * 0x100000001b3ull + site * 0x9e3779b97f4a7c15ull + idx;   // same hash as train.cu
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  const uint32_t r = (uint32_t)((z ^ (z >> 31)) >> 32);
+  return (r >> 8) * (1.0f / 16777216.0f) >= p;
+}
+
+// lane j ends with the sum over the warp of v[j] (butterfly: 31 shuffles instead of 160)
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const bool up = lane & 16;
+    const float send = up ? v[i] : v[i + 16], keep = up ? v[i + 16] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const bool up = lane & 8;
+    const float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const bool up = lane & 4;
+    const float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const bool up = lane & 2;
+    const float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  {
+    const bool up = lane & 1;
+    const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
+    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+  }
+  return v[0];
+}
 
 __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmW,
@@ -462,6 +536,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
     const int R = p.Hp * p.Wp;
     float* ex_mine = s_exch + g * 64;
     int acc = 0; uint32_t acc_phase = 0;
+    double st_sum = 0.0, st_sq = 0.0;   // training statistics of column `lane`
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const long long m = (long long)tile * kC2Out + row - 1;  // output row of this lane
       bool ring = false;
@@ -501,15 +576,36 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
         if (lane == 31 && g < 3) r = s_exch[(g + 1) * 64 + 32 + j];
         o[j] = l + __uint_as_float(mid[j]) + r + s_bias[j];
       }
-      if (row >= 1 && row <= kC2Out && m < p.m_total) {
-        uint32_t w[16];
+      const bool row_ok = row >= 1 && row <= kC2Out && m < p.m_total;
+      if (p.p_drop > 0.f && row_ok && !ring) {
+        const float inv = 1.f / (1.f - p.p_drop);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) w[j] = ring ? 0u : pack_bf16(o[2 * j], o[2 * j + 1]);
+        for (int j = 0; j < 32; ++j)
+          o[j] = drop_keep_c2(p.seed, p.site, (unsigned long long)m * 32 + j, p.p_drop) ? o[j] * inv : 0.f;
+      }
+      uint32_t w[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) w[j] = (ring || !row_ok) ? 0u : pack_bf16(o[2 * j], o[2 * j + 1]);
+      if (row_ok) {
         uint4* dst = reinterpret_cast<uint4*>(p.out + m * p.ldo + p.col0);
 #pragma unroll
         for (int j = 0; j < 4; ++j) dst[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
       }
+      if (p.stats != nullptr) {   // warp-uniform
+        float v1[32], v2[32];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          v1[2 * j] = bf_lo(w[j]); v1[2 * j + 1] = bf_hi(w[j]);
+          v2[2 * j] = v1[2 * j] * v1[2 * j]; v2[2 * j + 1] = v1[2 * j + 1] * v1[2 * j + 1];
+        }
+        st_sum += (double)warp_transpose_sum(v1, lane);
+        st_sq += (double)warp_transpose_sum(v2, lane);
+      }
       if ((acc ^= 1) == 0) acc_phase ^= 1;
+    }
+    if (p.stats != nullptr) {
+      atomicAdd(p.stats + lane, st_sum);
+      atomicAdd(p.stats + p.stats_stride + lane, st_sq);
     }
   }
   ptx::tc_fence_before();
@@ -525,8 +621,9 @@ static inline const float* pf(const char* packed, size_t off) { return reinterpr
 int launch_gemm(bool transform, const void* A, long long rows, int a_cols, int a_pitch, const void* W, int w_rows,
                        int kpad, int kphys, const float* a_scale, const float* a_shift, const float* a_alpha,
                        const float* o_shift, const float* o_alpha, void* out, int out_cols, int out_pitch, int n_tiles_n,
-                       int Hp, int Wp, cudaStream_t st) {
+                       int Hp, int Wp, cudaStream_t st, double* stats, int stats_stride) {
   if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one chunk");
+  if (stats != nullptr && n_tiles_n != 1) return fail(TCVN_ERR_UNSUPPORTED, "epilogue statistics need a single N tile");
   const size_t smem = 1024 + kC1Stages * (kStageA + kStageW) + 4 * kStageA + 2 * 192 * 4 + (3 * kC1Stages + 4) * 8 + 16;
   static bool attr_done = false;
   if (!attr_done) {
@@ -542,6 +639,7 @@ int launch_gemm(bool transform, const void* A, long long rows, int a_cols, int a
   g.m_total = rows; g.kchunks = kpad / kKChunk; g.kphys = kphys; g.n_tiles_n = n_tiles_n;
   g.a_scale = a_scale; g.a_shift = a_shift; g.a_alpha = a_alpha; g.o_shift = o_shift; g.o_alpha = o_alpha;
   g.Hp = Hp; g.Wp = Wp;
+  g.stats = stats; g.stats_stride = stats_stride;
   g.num_tiles = (int)ceil_div_ll(rows, kTileM) * n_tiles_n;
   const int grid = g.num_tiles < sm_count() ? g.num_tiles : sm_count();
   if (transform) umma_gemm_kernel<true><<<grid, kC1Threads, smem, st>>>(tmA, tmW, tmO, g);
@@ -574,7 +672,8 @@ int umma_dense_layer_part(const CnnPlan& P, const BlockPlan& B, const LayerPlan&
 // out[:, col0 : col0+32] = conv3x3(mid) + bias over the ringed layout; mid bf16 [rows][128] activated with a zero ring,
 // w2 bf16 [9*32][128] (tap-major, K contiguous), out bf16 with pitch ldo
 int umma_conv2_fwd(const void* mid, long long rows, const void* w2, const float* bias, void* out, int ldo, int col0, int Hp,
-                   int Wp, int W, cudaStream_t st) {
+                   int Wp, int W, cudaStream_t st, float p_drop, unsigned long long seed, unsigned long long site,
+                   double* stats, int stats_stride) {
   if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one chunk");
   const int tiles = (int)ceil_div_ll(rows, kC2Out);
   const int grid = tiles < sm_count() ? tiles : sm_count();
@@ -593,6 +692,7 @@ int umma_conv2_fwd(const void* mid, long long rows, const void* w2, const float*
     return fail(TCVN_ERR_UNSUPPORTED, "feature map width %d needs a %d-row halo tile (max %d)", W, c2.halo_rows, halo_rows_max);
   c2.bias = bias;
   c2.out = static_cast<bf16*>(out); c2.ldo = ldo; c2.col0 = col0; c2.num_tiles = tiles;
+  c2.p_drop = p_drop; c2.seed = seed; c2.site = site; c2.stats = stats; c2.stats_stride = stats_stride;
   // Measured on B200: the 128B swizzle of a UMMA operand is a function of the absolute shared-memory address
   // (bits [4,7) ^= bits [7,10)), exactly as TMA wrote it, so a descriptor may start at ANY row of the haloed
   // tile with matrix-base-offset 0 (setting it to (addr >> 7) & 7 gives wrong results).
