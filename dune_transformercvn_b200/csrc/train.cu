@@ -14,9 +14,10 @@ namespace tcvn {
 
 __device__ __forceinline__ bool is_ring(long long m, int Hp, int Wp) {
   if (Hp <= 0) return false;
-  const int rr = (int)(m % ((long long)Hp * Wp));
-  const int y = rr / Wp, x = rr - y * Wp;
-  return y == 0 || y == Hp - 1 || x == 0 || x == Wp - 1;
+  // every launcher bounds the row count below 2^31: 32-bit division
+  const unsigned rr = (unsigned)m % (unsigned)(Hp * Wp);
+  const unsigned y = rr / (unsigned)Wp, x = rr - y * (unsigned)Wp;
+  return y == 0 || y == (unsigned)(Hp - 1) || x == 0 || x == (unsigned)(Wp - 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -219,6 +220,19 @@ template <> __device__ __forceinline__ void st8<__nv_bfloat16>(__nv_bfloat16* p,
 
 constexpr int kVecU = 4;  // rows in flight per thread
 
+// ring test on the row index within an image (rr < Hp*Wp < 65536): floor(rr / Wp) by reciprocal multiplication
+struct RingTest {
+  int Hp, Wp, R; unsigned inv;
+  __device__ __forceinline__ RingTest(int hp, int wp) : Hp(hp), Wp(wp), R(hp * wp), inv(wp > 0 ? (unsigned)((0x100000000ull + wp - 1) / wp) : 0u) {}
+  __device__ __forceinline__ int start(long long m) const { return R > 0 ? (int)(m % R) : 0; }
+  __device__ __forceinline__ int advance(int rr, int step) const { rr += step; return R > 0 ? (rr >= R ? rr % R : rr) : 0; }
+  __device__ __forceinline__ bool ring(int rr) const {
+    if (R <= 0) return false;
+    const int y = (int)__umulhi((unsigned)rr, inv), x = rr - y * Wp;
+    return y == 0 || y == Hp - 1 || x == 0 || x == Wp - 1;
+  }
+};
+
 // a raw 8-element packet as loaded from memory (converted to fp32 only when consumed: half the registers in flight)
 template <typename T> struct Raw8;
 template <> struct Raw8<float> { float4 a, b; };
@@ -265,6 +279,8 @@ __global__ void __launch_bounds__(256, 2) colsum_vec_kernel(const ColDev p, int 
         mean[i] = p.fold[3 * fs + c + i]; rstd[i] = p.fold[4 * fs + c + i];
       }
     }
+    const RingTest rt(p.Hp, p.Wp);
+    int rr0 = rt.start(r_begin + ry);
     for (long long m0 = r_begin + ry; m0 < r_end; m0 += (long long)rpi * U) {
       Raw8<TX> xr[U];
       Raw8<TD> dr[U];
@@ -272,7 +288,8 @@ __global__ void __launch_bounds__(256, 2) colsum_vec_kernel(const ColDev p, int 
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long m = m0 + (long long)u * rpi;
-        ok[u] = m < r_end && !is_ring(m, p.Hp, p.Wp);
+        ok[u] = m < r_end && !rt.ring(rr0);
+        rr0 = rt.advance(rr0, rpi);
         if (ok[u]) {
           ldraw(X + m * (long long)p.ldx + p.xcol0 + c, xr[u]);
           if (MODE == 1) ldraw(D + m * (long long)p.ldd + p.dcol0 + c, dr[u]);
@@ -339,6 +356,8 @@ __global__ void __launch_bounds__(256, 2) bnact_bwd_apply_vec_kernel(const BnBwd
     mean[i] = p.fold[3 * fs + c + i]; rstd[i] = p.fold[4 * fs + c + i];
     mg[i] = (float)(p.sums[c + i] / p.count); mgx[i] = (float)(p.sums[p.C + c + i] / p.count);
   }
+  const RingTest rt(p.Hp, p.Wp);
+  int rr0 = rt.start(r_begin + ry);
   for (long long m0 = r_begin + ry; m0 < r_end; m0 += (long long)rpi * U) {
     Raw8<TX> xr[U];
     Raw8<TD> dr[U];
@@ -347,7 +366,8 @@ __global__ void __launch_bounds__(256, 2) bnact_bwd_apply_vec_kernel(const BnBwd
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const long long m = m0 + (long long)u * rpi;
-      kind[u] = m >= r_end ? 0 : (is_ring(m, p.Hp, p.Wp) ? 1 : 2);
+      kind[u] = m >= r_end ? 0 : (rt.ring(rr0) ? 1 : 2);
+      rr0 = rt.advance(rr0, rpi);
       if (kind[u] == 2) {
         ldraw(X + m * (long long)p.ldx + p.xcol0 + c, xr[u]);
         ldraw(D + m * (long long)p.ldd + p.dcol0 + c, dr[u]);

@@ -536,25 +536,39 @@ __device__ __forceinline__ bool drop_keep16(unsigned long long seed, unsigned lo
 // with the layer's dropout mask applied (same (seed, site, element) hash as the forward pass)
 __global__ void g2x_kernel(const float* __restrict__ gblk, int ld, int col0, long long rows, int Hp, int Wp,
                            unsigned long long seed, unsigned long long stream_id, float p, bf* __restrict__ g2x) {
+  // one thread = one row x 8 channels (two float4 loads, 16-byte stores)
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * 32) return;
-  const int c = (int)(idx & 31);
-  const long long m = idx >> 5;
+  if (idx >= rows * 4) return;
+  const int c = (int)(idx & 3) * 8;
+  const long long m = idx >> 2;
   const int rr = (int)(m % ((long long)Hp * Wp));
   const int y = rr / Wp, x = rr - y * Wp;
-  float v = 0.f;
+  float v[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = 0.f;
   if (!(y == 0 || y == Hp - 1 || x == 0 || x == Wp - 1)) {
-    v = gblk[m * (long long)ld + col0 + c];
-    if (p > 0.f) v = drop_keep16(seed, stream_id, (unsigned long long)idx, p) ? v / (1.f - p) : 0.f;
+    const float4 a = *reinterpret_cast<const float4*>(gblk + m * (long long)ld + col0 + c);
+    const float4 b = *reinterpret_cast<const float4*>(gblk + m * (long long)ld + col0 + c + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    if (p > 0.f) {
+      const float inv = 1.f / (1.f - p);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = drop_keep16(seed, stream_id, (unsigned long long)m * 32 + c + i, p) ? v[i] * inv : 0.f;
+    }
   }
-  const bf h = __float2bfloat16_rn(v);
-  const bf z = __float2bfloat16_rn(0.f);
-  g2x[m * 128 + 32 + c] = h;
-  g2x[m * 128 + 96 + c] = z;
-  if (m > 0) g2x[(m - 1) * 128 + c] = h;
-  else g2x[64 + c] = z;
-  if (m + 1 < rows) g2x[(m + 1) * 128 + 64 + c] = h;
-  else g2x[m * 128 + c] = z;
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    w[i] = *reinterpret_cast<const uint32_t*>(&h2);
+  }
+  const uint4 hv = make_uint4(w[0], w[1], w[2], w[3]), zv = make_uint4(0u, 0u, 0u, 0u);
+  *reinterpret_cast<uint4*>(g2x + m * 128 + 32 + c) = hv;
+  *reinterpret_cast<uint4*>(g2x + m * 128 + 96 + c) = zv;
+  if (m > 0) *reinterpret_cast<uint4*>(g2x + (m - 1) * 128 + c) = hv;
+  else *reinterpret_cast<uint4*>(g2x + 64 + c) = zv;
+  if (m + 1 < rows) *reinterpret_cast<uint4*>(g2x + (m + 1) * 128 + 64 + c) = hv;
+  else *reinterpret_cast<uint4*>(g2x + m * 128 + c) = zv;
 }
 
 // fp32 gradient columns [0, cols) -> bf16 [rows][pitch], zero padded
@@ -799,7 +813,7 @@ struct TWalk16 {
         const T16Layer& Y = X.layers[i];
         float* f1 = f(Y.fold1);
         // gradient of the layer's 32 output channels (complete by now) -> bf16, dropout mask applied, 3 horizontal shifts
-        g2x_kernel<<<(unsigned)ceil_div_ll(rows * 32, 256), 256, 0, st>>>(gblk, B.ctot, L.kphys, rows, B.Hp, B.Wp, seed,
+        g2x_kernel<<<(unsigned)ceil_div_ll(rows * 4, 256), 256, 0, st>>>(gblk, B.ctot, L.kphys, rows, B.Hp, B.Wp, seed,
                                                                          site * 4096 + b * 64 + i, p_drop, g2x);
         TCVN_LAUNCH_CHECK();
         // conv biases: every convolution of the DenseNet feeds a train-mode BatchNorm (directly, or through the concat

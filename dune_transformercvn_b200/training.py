@@ -369,13 +369,14 @@ class TcvnAdamW(torch.optim.Optimizer):
 
     def _selector(self) -> torch.Tensor:
         a = self._arena
+        # cheap per-step key: which parameters currently carry a gradient (group membership is fixed after construction)
+        key = (a.flat.data_ptr(), tuple(p.grad is None for g in self.param_groups for p in g["params"]))
+        if a.select is not None and a.select_key == key:
+            return a.select
         by_ptr = {}
         for gi, g in enumerate(self.param_groups):
             for p in g["params"]:
                 by_ptr[p.data_ptr()] = (gi + 1, p)
-        key = tuple(sorted((ptr, gi, p.grad is not None) for ptr, (gi, p) in by_ptr.items()))
-        if a.select is not None and a.select_key == key:
-            return a.select
         sel = torch.zeros(a.total, dtype=torch.uint8)
         base = a.flat.data_ptr()
         for s in a.specs:
