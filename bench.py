@@ -171,7 +171,7 @@ def time_cpu_train(sample_events: int, steps: int, seed: int):
                       f"backward (dropout = identity), fp32 torch CPU autograd, {steps} timed steps"}
 
 
-def run_train_leg(args, dev, rank, world, timed, sampler_index):
+def run_train_leg(args, dev, rank, world, timed, train_events, with_cpu):
     """BASELINE configs[2]: DenseNet TransformerCVN training, event-sharded data parallel, NCCL gradient all-reduce.
     One step = densify -> train-mode forward -> focal loss -> hand-written backward (gradient exchange issued from
     inside it) -> fused clip + AdamW.  Every rank holds `--train-events` events (weak scaling)."""
@@ -188,9 +188,9 @@ def run_train_leg(args, dev, rank, world, timed, sampler_index):
         net.train_engine.exchange = training.GradientExchange()
     opt = training.TcvnAdamW(training.reference_param_groups(net, opts.l2_penalty), lr=opts.learning_rate,
                              max_grad_norm=opts.gradient_clip)
-    batch = make_inputs(args.train_events, 4321 + rank)
+    batch = make_inputs(train_events, 4321 + rank)
     g = torch.Generator().manual_seed(99 + rank)
-    ev_t = torch.randint(0, NUM_EVENT_CLASSES, (args.train_events,), generator=g)
+    ev_t = torch.randint(0, NUM_EVENT_CLASSES, (train_events,), generator=g)
     pr_t = torch.randint(0, NUM_PRONG_CLASSES, tuple(batch.prong_mask.shape), generator=g)
     pr_t[~batch.prong_mask] = -1
     host = batch.pin()
@@ -223,22 +223,24 @@ def run_train_leg(args, dev, rank, world, timed, sampler_index):
     images = batch.num_events + batch.num_prongs
     ex = net.train_engine.exchange
     out = {"metric": "events/sec, training step (forward + loss + backward + gradient all-reduce + AdamW)",
-           "value": world * args.train_events * args.train_steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+           "value": world * train_events * args.train_steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
            "ms_per_step": ms / args.train_steps, "steps": args.train_steps, "scaling": "weak",
            "dtype": "f32" if args.train_precision == "fp32" else "bf16 (activations + tcgen05 GEMM operands; fp32 accumulation, parameters, statistics, gradients of parameters)",
-           "config": {"workload": f"BASELINE configs[2]: tutorial DenseNet TransformerCVN, {args.train_events} events/GPU "
+           "config": {"workload": f"BASELINE configs[2]: tutorial DenseNet TransformerCVN, {train_events} events/GPU "
                                   f"({images} images on rank 0), dropout {opts.dropout}, AdamW + clip {opts.gradient_clip}",
                       "parallelism": f"event-sharded x{world}, rank-local BatchNorm, NCCL all-reduce of the flat fp32 gradient "
                                      f"arena in 4 slices issued from inside backward"},
-           "e2e": {"value": world * args.train_events * args.train_steps / (ms_e2e / 1e3), "unit": UNIT,
+           "e2e": {"value": world * train_events * args.train_steps / (ms_e2e / 1e3), "unit": UNIT,
                    "h2d_bytes_per_step": host.nbytes() + sum(t.numel() * t.element_size() for t in host_t),
                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.train_steps},
            "allreduce_bytes_per_step": 0 if ex is None else ex.bytes // max(1, (max(args.warmup, 3) + 2 * args.train_steps + 1)),
            "gpu_launches": launches, "images_per_s": world * images * args.train_steps / (ms / 1e3),
            "train_gflop_per_image": 14.39, "whole_net_tflops": images * 14.39e9 * args.train_steps / (ms / 1e3) / 1e12,
            "final_loss": loss_val}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and with_cpu and not args.no_cpu_baseline:
         out["cpu_baseline"] = time_cpu_train(2, 1, 4321)
+    del net, opt
+    torch.cuda.empty_cache()
     return out
 
 
@@ -378,9 +380,11 @@ def run_ours(args):
     sampler.join(timeout=2)
     value = world * args.events * args.steps / (ms / 1e3)
     e2e_value = world * args.events * args.steps / (ms_e2e / 1e3)
-    train = None
+    train = train_large = None
     if not args.no_train:
-        train = run_train_leg(args, dev, rank, world, timed, local)
+        train = run_train_leg(args, dev, rank, world, timed, args.train_events, True)
+        if args.train_events_large > 0:
+            train_large = run_train_leg(args, dev, rank, world, timed, args.train_events_large, False)
     h2d = host.nbytes()
     d2h = sum(t.numel() * t.element_size() for t in out_host)
 
@@ -413,7 +417,7 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "images_per_s": value * images / args.events,
             "whole_net_tflops": tflops, "roofline": roofline, "rooflines_other": extra_rooflines,
-            "cpu_baseline": cpu, "clocks": sampler.summary(), "train": train}
+            "cpu_baseline": cpu, "clocks": sampler.summary(), "train": train, "train_large_batch": train_large}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -448,6 +452,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true", help="skip the training leg (BASELINE configs[2]) reported under \"train\"")
     ap.add_argument("--train-events", type=int, default=16, help="events per GPU per training step (2023_08_07 JSON batch_size)")
+    ap.add_argument("--train-events-large", type=int, default=64, help="second training measurement at a larger per-GPU batch "
+                    "(SURVEY 8d: config 3 is also run at 64 events/GPU); 0 = skip")
     ap.add_argument("--train-steps", type=int, default=5)
     ap.add_argument("--train-precision", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--materialize", action="store_true", help="build the dense pixel maps (densify kernel) instead "

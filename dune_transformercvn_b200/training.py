@@ -64,6 +64,7 @@ class FlatArena:
         self.gviews: Dict[str, torch.Tensor] = {}
         self.select: Optional[torch.Tensor] = None   # per-element optimizer group id (0 = not optimised)
         self.select_key = None
+        self._probe = None
         self.seg: Dict[str, Tuple[int, int]] = {}
         for tag, prefix in _PREFIX.items():
             names = [s for s in self.specs if s.name.startswith(prefix)]
@@ -75,15 +76,12 @@ class FlatArena:
         return not name.startswith(_NO_GRAD_PREFIXES)
 
     def bound(self) -> bool:
-        if self.flat is None:
+        """Are the module's tensors still the views into the arena?  `.to()` / `.cuda()` move every tensor, so a sample
+        (first, last and a few in between) decides; a full walk over 778 tensors per step would cost ~1 ms of host time."""
+        if self.flat is None or self._probe is None:
             return False
         base = self.flat.data_ptr()
-        tensors = _tensors_of(self.net[0])
-        for s in self.specs:
-            t = tensors[s.name]
-            if t.data_ptr() != base + 4 * self.offset[s.name] or t.dtype != torch.float32:
-                return False
-        return True
+        return all(t.data_ptr() == base + off and t.dtype == torch.float32 for t, off in self._probe)
 
     def bind(self) -> None:
         """Move every float tensor into the arena (values preserved) and make the module's tensors views."""
@@ -100,6 +98,8 @@ class FlatArena:
             o = self.offset[s.name]
             tensors[s.name].data = flat[o:o + s.numel].view(s.shape)
         self.flat = flat
+        step = max(1, len(self.specs) // 8)
+        self._probe = [(tensors[sp.name], 4 * self.offset[sp.name]) for sp in (self.specs[::step] + self.specs[-1:])]
         self.gflat = torch.zeros(self.total, dtype=torch.float32, device=dev)
         self.gviews = {s.name: self.gflat[self.offset[s.name]:self.offset[s.name] + s.numel].view(s.shape)
                        for s in self.specs if s.is_param and self.has_grad(s.name)}

@@ -248,3 +248,22 @@ def test_sparse_direct_stem_equals_densify_then_forward(dev, precision):
             with torch.no_grad():
                 want_ev, want_pr = restate.sparse_forward(state, opts, batch)
             assert rel_err(ev_a.cpu(), want_ev) < FP32_TOL and rel_err(pr_a.cpu(), want_pr) < FP32_TOL
+
+
+# ------------------------------------------------------------------------------------------ config 5 shape
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_max_prong_count_ingest_and_forward(dev, precision, tol):
+    """BASELINE configs[4]: every event carries the dataset's maximum of 20 prongs (21-token sequences), sparse
+    Minkowski hits densified on the GPU and forwarded end to end; also the literal densify -> dense forward sequence."""
+    net, state, opts = _net(6, True, dev, precision=precision)
+    batch = synth.make_batch(2, seed=17, prongs_per_event=[20, 20])
+    gb = batch.to(dev)
+    with torch.no_grad():
+        ev, pr = net.forward_sparse(gb)
+        ev_m, pr_m = net.forward_sparse(gb, materialize=True)
+        want_ev, want_pr = restate.sparse_forward(state, opts, batch)
+    assert pr.shape == (2, 20, NUM_PRONG_CLASSES)
+    assert rel_err(ev.cpu(), want_ev) < tol and rel_err(pr.cpu(), want_pr) < tol
+    assert torch.equal(ev, ev_m) and torch.equal(pr, pr_m)          # COO-direct stem == densify kernel + dense stem
+    assert (ev.argmax(-1).cpu() == want_ev.argmax(-1)).all()
+    assert (pr.argmax(-1).cpu() == want_pr.argmax(-1)).all()
