@@ -79,6 +79,11 @@ int pool_typed(int kind, const void* src, const float* fold, void* dst, bool bf1
                int ld, cudaStream_t stream);
 int dropout_typed(void* X, bool bf16, int ld, int col0, int C, long long m_total, uint64_t seed, uint64_t stream_id, float p,
                   cudaStream_t stream);
+// BN1 backward with deferred mean corrections (train.cu): one pass O += sc * g and the three reductions into sums[3][C]
+int bn1_bwd_fused(const void* X, int ldx, const void* D, int ldd, const float* fold, int fold_stride, int C, float* O, int ldo,
+                  long long m_total, int ring_hp, int ring_wp, double* sums, cudaStream_t stream);
+int bn1_correct(float* G, int ldg, const void* X, int ldx, int C, long long m_total, int ring_hp, int ring_wp, const float* mean,
+                const float* rstd, const float* corrA, const float* corrB, cudaStream_t stream);
 int wgrad_typed(const void* A, bool a_bf16, int lda, long long m_total, int K, int taps, const int* tap_off, const float* a_scale,
                 const float* a_shift, const float* a_alpha, int a_ring_hp, int a_ring_wp, const void* G, bool g_bf16, int ldg,
                 int g_col0, int N, int g_ring_hp, int g_ring_wp, float* dW, cudaStream_t stream);

@@ -401,6 +401,116 @@ __global__ void __launch_bounds__(256, 2) bnact_bwd_apply_vec_kernel(const BnBwd
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// BN1 + PReLU1 backward of a dense layer with DEFERRED mean corrections (bf16 walk).  All BN1s of a block normalise
+// the same channels with the same statistics, so   d x = sum_i sc_i g_i  -  [sum_i sc_i mean(g_i)]  -  xhat [sum_i sc_i
+// mean(g_i xhat)]:  one pass per layer adds sc_i g_i to the fp32 gradient buffer AND reduces (sum g, sum g xhat,
+// sum dA min(y,0)); the two per-channel correction scalars are accumulated on the side and applied when a channel's
+// gradient is consumed.  Replaces the separate reduction pass + apply pass (X and D are read once instead of twice).
+// ------------------------------------------------------------------------------------------------
+struct Bn1FusedDev {
+  const __nv_bfloat16* X; int ldx;
+  const __nv_bfloat16* D; int ldd;
+  const float* fold; int fold_stride; int C;
+  float* O; int ldo;
+  long long m_total; int Hp, Wp, rows_per_slab;
+  double* sums;   // [3][C]
+};
+
+__global__ void __launch_bounds__(256, 2) bn1_bwd_fused_vec_kernel(const Bn1FusedDev p, int tv) {
+  constexpr int U = 2;
+  __shared__ double red[256][8];
+  const int rpi = 256 / tv;
+  const int vx = threadIdx.x % tv, ry = threadIdx.x / tv;
+  const int c = (blockIdx.x * tv + vx) * 8;
+  const bool active = c < p.C && ry < rpi;
+  const long long r_begin = (long long)blockIdx.y * p.rows_per_slab;
+  const long long r_end = min(p.m_total, r_begin + p.rows_per_slab);
+  float part[3][8];
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) part[j][i] = 0.f;
+  if (active) {
+    const int fs = p.fold_stride;
+    float sc[8], sh[8], al[8], mean[8], rstd[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sc[i] = p.fold[c + i]; sh[i] = p.fold[fs + c + i]; al[i] = p.fold[2 * fs + c + i];
+      mean[i] = p.fold[3 * fs + c + i]; rstd[i] = p.fold[4 * fs + c + i];
+    }
+    const RingTest rt(p.Hp, p.Wp);
+    int rr0 = rt.start(r_begin + ry);
+    for (long long m0 = r_begin + ry; m0 < r_end; m0 += (long long)rpi * U) {
+      Raw8<__nv_bfloat16> xr[U], dr[U];
+      Raw8<float> orr[U];
+      bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long m = m0 + (long long)u * rpi;
+        ok[u] = m < r_end && !rt.ring(rr0);
+        rr0 = rt.advance(rr0, rpi);
+        if (ok[u]) {
+          ldraw(p.X + m * (long long)p.ldx + c, xr[u]);
+          ldraw(p.D + m * (long long)p.ldd + c, dr[u]);
+          ldraw(p.O + m * (long long)p.ldo + c, orr[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        const long long m = m0 + (long long)u * rpi;
+        float x[8], d[8], o[8];
+        unpack8(xr[u], x); unpack8(dr[u], d); unpack8(orr[u], o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float y = fmaf(x[i], sc[i], sh[i]);
+          const float g = y >= 0.f ? d[i] : d[i] * al[i];
+          o[i] = fmaf(sc[i], g, o[i]);
+          part[0][i] += g;
+          part[1][i] = fmaf(g, (x[i] - mean[i]) * rstd[i], part[1][i]);
+          part[2][i] = fmaf(d[i], fminf(y, 0.f), part[2][i]);
+        }
+        st8<float>(p.O + m * (long long)p.ldo + c, o);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = (double)part[j][i];
+    __syncthreads();
+    if (active && ry == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        double sum = 0.0;
+        for (int r = 0; r < rpi; ++r) sum += red[r * tv + vx][i];
+        atomicAdd(p.sums + (size_t)j * p.C + c + i, sum);
+      }
+    }
+  }
+}
+
+// gradient of channels [0, C) made final: g -= corrA + xhat * corrB on interior rows (in place, fp32)
+__global__ void __launch_bounds__(256) bn1_correct_vec_kernel(float* __restrict__ G, int ldg, const __nv_bfloat16* __restrict__ X,
+                                                             int ldx, int C, long long m_total, int Hp, int Wp,
+                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                             const float* __restrict__ corrA, const float* __restrict__ corrB) {
+  const int cv = C / 8;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= m_total * cv) return;
+  const int c = (int)(idx % cv) * 8;
+  const long long m = idx / cv;
+  if (is_ring(m, Hp, Wp)) return;
+  float g[8], x[8];
+  ld8<float>(G + m * (long long)ldg + c, g);
+  ld8<__nv_bfloat16>(X + m * (long long)ldx + c, x);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) g[i] -= corrA[c + i] + (x[i] - mean[c + i]) * rstd[c + i] * corrB[c + i];
+  st8<float>(G + m * (long long)ldg + c, g);
+}
+
 template <typename TX, typename TO>
 __global__ void __launch_bounds__(256) bnact_fwd_vec_kernel(const TX* __restrict__ X, int ldx, int xcol0,
                                                             const float* __restrict__ fold, int fold_stride, int C,
@@ -830,6 +940,40 @@ int pool_typed(int kind, const void* src, const float* fold, void* dst, bool bf1
       else gap_bwd_kernel<float><<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const float*>(src), C, static_cast<float*>(dst), H, W, total);
       break;
   }
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+int bn1_bwd_fused(const void* X, int ldx, const void* D, int ldd, const float* fold, int fold_stride, int C, float* O, int ldo,
+                  long long m_total, int ring_hp, int ring_wp, double* sums, cudaStream_t stream) {
+  if (m_total <= 0 || C <= 0) return TCVN_OK;
+  if (C % 8 || ldx % 8 || ldd % 8 || ldo % 8) return fail(TCVN_ERR_UNSUPPORTED, "bn1_bwd_fused: widths must be multiples of 8");
+  Bn1FusedDev p{};
+  p.X = static_cast<const __nv_bfloat16*>(X); p.ldx = ldx; p.D = static_cast<const __nv_bfloat16*>(D); p.ldd = ldd;
+  p.fold = fold; p.fold_stride = fold_stride; p.C = C; p.O = O; p.ldo = ldo; p.m_total = m_total; p.Hp = ring_hp; p.Wp = ring_wp;
+  p.sums = sums;
+  const int cv = C / 8;
+  const int tv = cv < 32 ? cv : 32;
+  const int rpi = 256 / tv;
+  const int gx = ceil_div(cv, tv);
+  long long vslabs = ceil_div_ll(m_total, (long long)rpi * 2 * 4);
+  const long long cap = (long long)(148 * 4 / gx > 1 ? 148 * 4 / gx : 1);
+  if (vslabs > cap) vslabs = cap;
+  p.rows_per_slab = (int)ceil_div_ll(m_total, vslabs);
+  vslabs = ceil_div_ll(m_total, p.rows_per_slab);
+  dim3 grid(gx, (unsigned)vslabs);
+  bn1_bwd_fused_vec_kernel<<<grid, 256, 0, stream>>>(p, tv);
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+int bn1_correct(float* G, int ldg, const void* X, int ldx, int C, long long m_total, int ring_hp, int ring_wp, const float* mean,
+                const float* rstd, const float* corrA, const float* corrB, cudaStream_t stream) {
+  if (m_total <= 0 || C <= 0) return TCVN_OK;
+  if (C % 8 || ldx % 8 || ldg % 8) return fail(TCVN_ERR_UNSUPPORTED, "bn1_correct: widths must be multiples of 8");
+  const unsigned grid = (unsigned)ceil_div_ll(m_total * (C / 8), 256);
+  bn1_correct_vec_kernel<<<grid, 256, 0, stream>>>(G, ldg, static_cast<const __nv_bfloat16*>(X), ldx, C, m_total, ring_hp, ring_wp,
+                                                  mean, rstd, corrA, corrB);
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
 }

@@ -430,6 +430,7 @@ typedef __nv_bfloat16 bf;
 struct T16Layer { size_t w1b, w1d, w2b, wd, fold1, fold2, mid_raw, mid_act; };
 struct T16Block {
   size_t blk, gblk, sums, fold_t, pooled, wtb, wtd, tb16;
+  size_t bstat;   // [mean | rstd | corrA | corrB] x ctot floats: block statistics and the deferred BN1 corrections
   int gt_pitch;
   std::vector<T16Layer> layers;
 };
@@ -465,6 +466,7 @@ struct TrainPlan16 {
       X.blk = take(rows * B.ctot * 2);
       X.gblk = take(rows * B.ctot * 4);
       X.sums = take(2 * (size_t)B.ctot * 8);
+      X.bstat = take(4 * (size_t)B.ctot * 4);
       if (rows * B.ctot > max_rc) max_rc = rows * B.ctot;
       if (rows > max_rows) max_rows = rows;
       if (B.ctot > max_c) max_c = B.ctot;
@@ -535,21 +537,31 @@ __device__ __forceinline__ bool drop_keep16(unsigned long long seed, unsigned lo
 // G2x[m] = [ G[m+1] | G[m] | G[m-1] | 0 ] (4 x 32 bf16) from the fp32 gradient slice of a layer's 32 output channels,
 // with the layer's dropout mask applied (same (seed, site, element) hash as the forward pass)
 __global__ void g2x_kernel(const float* __restrict__ gblk, int ld, int col0, long long rows, int Hp, int Wp,
-                           unsigned long long seed, unsigned long long stream_id, float p, bf* __restrict__ g2x) {
-  // one thread = one row x 8 channels (two float4 loads, 16-byte stores)
+                           unsigned long long seed, unsigned long long stream_id, float p, const bf* __restrict__ blk,
+                           const float* __restrict__ bstat, int ctot, bf* __restrict__ g2x) {
+  // one thread = one row x 8 channels (two float4 loads, 16-byte stores).  The stored gradient lacks the deferred BN1
+  // mean corrections of the later layers: g -= corrA + xhat * corrB (bstat = [mean | rstd | corrA | corrB] x ctot)
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= rows * 4) return;
   const int c = (int)(idx & 3) * 8;
   const long long m = idx >> 2;
-  const int rr = (int)(m % ((long long)Hp * Wp));
-  const int y = rr / Wp, x = rr - y * Wp;
+  const unsigned rr = (unsigned)m % (unsigned)(Hp * Wp);
+  const unsigned y = rr / (unsigned)Wp, x = rr - y * (unsigned)Wp;
   float v[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) v[i] = 0.f;
-  if (!(y == 0 || y == Hp - 1 || x == 0 || x == Wp - 1)) {
+  if (!(y == 0 || y == (unsigned)(Hp - 1) || x == 0 || x == (unsigned)(Wp - 1))) {
     const float4 a = *reinterpret_cast<const float4*>(gblk + m * (long long)ld + col0 + c);
     const float4 b = *reinterpret_cast<const float4*>(gblk + m * (long long)ld + col0 + c + 4);
     v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    const uint4 xr = *reinterpret_cast<const uint4*>(blk + m * (long long)ld + col0 + c);
+    const uint32_t xw[4] = {xr.x, xr.y, xr.z, xr.w};
+    const float* st = bstat + col0 + c;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xv = (i & 1) ? __uint_as_float(xw[i >> 1] & 0xffff0000u) : __uint_as_float(xw[i >> 1] << 16);
+      v[i] -= st[2 * ctot + i] + (xv - st[i]) * st[ctot + i] * st[3 * ctot + i];
+    }
     if (p > 0.f) {
       const float inv = 1.f / (1.f - p);
 #pragma unroll
@@ -569,6 +581,38 @@ __global__ void g2x_kernel(const float* __restrict__ gblk, int ld, int col0, lon
   else *reinterpret_cast<uint4*>(g2x + 64 + c) = zv;
   if (m + 1 < rows) *reinterpret_cast<uint4*>(g2x + (m + 1) * 128 + 64 + c) = hv;
   else *reinterpret_cast<uint4*>(g2x + m * 128 + c) = zv;
+}
+
+// block statistics for the backward: bstat = [mean | rstd | corrA = 0 | corrB = 0] x ctot from the forward's (sum, sum^2)
+__global__ void blk_stats_kernel(const double* __restrict__ s1, const double* __restrict__ s2, double count, float eps, int ctot,
+                                 float* __restrict__ bstat) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= ctot) return;
+  const double mean = s1[p] / count;
+  double var = s2[p] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  bstat[p] = (float)mean;
+  bstat[ctot + p] = (float)(1.0 / sqrt(var + (double)eps));
+  bstat[2 * ctot + p] = 0.f;
+  bstat[3 * ctot + p] = 0.f;
+}
+
+// BN1 parameter gradients + the deferred corrections from the fused pass's reductions sums[3][C] (physical channels)
+__global__ void bn1_param_corr_kernel(const double* __restrict__ sums, int C, int c_log, int c0, int c0p,
+                                      const float* __restrict__ scale, double count, float* dgamma, float* dbeta, float* dalpha,
+                                      float* __restrict__ corrA, float* __restrict__ corrB) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= C) return;
+  int c = -1;
+  if (p < c0) c = p;
+  else if (p >= c0p) c = p - (c0p - c0);
+  if (c < 0 || c >= c_log) return;
+  const double S0 = sums[p], S1 = sums[C + p], S2 = sums[2 * C + p];
+  dbeta[c] += (float)S0;
+  dgamma[c] += (float)S1;
+  dalpha[c] += (float)S2;
+  corrA[p] += scale[p] * (float)(S0 / count);
+  corrB[p] += scale[p] * (float)(S1 / count);
 }
 
 // fp32 gradient columns [0, cols) -> bf16 [rows][pitch], zero padded
@@ -808,13 +852,16 @@ struct TWalk16 {
       float* gblk = f(X.gblk);
       bf* dmid = h(T.dmid);
       bf* g2x = h(T.g2x);
+      float* bstat = f(X.bstat);
+      blk_stats_kernel<<<ceil_div(B.ctot, 128), 128, 0, st>>>(dbl(X.sums), dbl(X.sums) + B.ctot, count, d.bn_eps, B.ctot, bstat);
+      TCVN_LAUNCH_CHECK();
       for (int i = (int)B.layers.size() - 1; i >= 0; --i) {
         const LayerPlan& L = B.layers[i];
         const T16Layer& Y = X.layers[i];
         float* f1 = f(Y.fold1);
         // gradient of the layer's 32 output channels (complete by now) -> bf16, dropout mask applied, 3 horizontal shifts
         g2x_kernel<<<(unsigned)ceil_div_ll(rows * 4, 256), 256, 0, st>>>(gblk, B.ctot, L.kphys, rows, B.Hp, B.Wp, seed,
-                                                                         site * 4096 + b * 64 + i, p_drop, g2x);
+                                                                        site * 4096 + b * 64 + i, p_drop, blk, bstat, B.ctot, g2x);
         TCVN_LAUNCH_CHECK();
         // conv biases: every convolution of the DenseNet feeds a train-mode BatchNorm (directly, or through the concat
         // buffer), which removes any per-channel constant, so their gradient is exactly zero; the reference's autograd
@@ -842,9 +889,22 @@ struct TWalk16 {
         }
         TCVN_TRY(launch_gemm(false, dmid, rows, mid, mid, h(Y.w1d), L.kphys, 128, 128, nullptr, nullptr, nullptr, f(T.zeros),
                              f(T.ones), h(T.sA), L.kphys, L.kphys, ceil_div(L.kphys, 128), B.Hp, B.Wp, st));
-        TCVN_TRY(bn_bwd(blk, true, B.ctot, h(T.sA), true, L.kphys, f1, L.kpad, L.kphys, count, rows, B.Hp, B.Wp, gblk, false, B.ctot,
-                        true, L.norm1, B.c0, B.c0p));
+        // BN1 + PReLU1 backward, one pass: gblk[:, :k] += sc * g and the three reductions; the mean corrections of the
+        // BatchNorm backward are deferred (bstat corrA / corrB) and applied where a channel's gradient is consumed
+        {
+          double* sm = dbl(T.sums_scr);
+          TCVN_CUDA(cudaMemsetAsync(sm, 0, sizeof(double) * 3 * L.kphys, st));
+          TCVN_TRY(bn1_bwd_fused(blk, B.ctot, h(T.sA), L.kphys, f1, L.kpad, L.kphys, gblk, B.ctot, rows, B.Hp, B.Wp, sm, st));
+          bn1_param_corr_kernel<<<ceil_div(L.kphys, 128), 128, 0, st>>>(sm, L.kphys, L.norm1.c, B.c0, B.c0p, f1, count,
+                                                                       garena + L.norm1.w, garena + L.norm1.b,
+                                                                       garena + L.norm1.alpha, bstat + 2 * B.ctot,
+                                                                       bstat + 3 * B.ctot);
+          TCVN_LAUNCH_CHECK();
+        }
       }
+      // the block-input channels leave the block: make their gradient final
+      TCVN_TRY(bn1_correct(gblk, B.ctot, blk, B.ctot, B.c0p, rows, B.Hp, B.Wp, bstat, bstat + B.ctot, bstat + 2 * B.ctot,
+                           bstat + 3 * B.ctot, st));
       if (b > 0) {
         const BlockPlan& Pv = P.blocks[b - 1];
         const T16Block& Xp = T.blocks[b - 1];

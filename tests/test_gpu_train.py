@@ -198,3 +198,47 @@ def test_gradients_accumulate_and_zero_grad(dev):
     net.zero_grad(set_to_none=True)
     step()
     assert rel_err(dict(net.named_parameters())[k].grad, g1) < 1e-3
+
+
+def test_bf16_training_path_tracks_fp32_path(dev):
+    """bf16 activations + tcgen05 GEMMs vs the fp32 parity path of this library on a 12-event batch (BatchNorm over
+    >= 12 images is well conditioned).  bf16 rounding through 30 train-mode-BN layers decorrelates gradients smoothly
+    with depth (measured: whole-gradient cosine 0.965-0.971, dense5 0.99 -> dense1 0.96, norm ratio 0.995-1.005;
+    PyTorch's CPU bf16 autocast shows 4-6 % logit error in train mode).  A wiring error (a wrong tap order, a
+    missing term) drives the cosine of a whole tensor kind to ~0, which is what this guards."""
+    opts = PathOptions.tutorial()
+    opts.dropout = 0.1
+    batch = synth.make_batch(12, seed=77, max_prongs=10)
+    db = batch.to(dev)
+    ev_px = densify(db.event_values, db.event_coords, (H, W), db.num_events, 255.0)
+    pr_px = densify(db.prong_values, db.prong_coords, (H, W), db.num_prongs, 255.0)
+    g = torch.Generator().manual_seed(5)
+    ev_t = torch.randint(0, NUM_EVENT_CLASSES, (12,), generator=g).to(dev)
+    pr_t = torch.randint(0, NUM_PRONG_CLASSES, tuple(batch.prong_mask.shape), generator=g)
+    pr_t[~batch.prong_mask] = -1
+    pr_t = pr_t.to(dev)
+    grads, outs = {}, {}
+    for prec in ("fp32", "bf16"):
+        net = NeutrinoDenseNetwork(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES, precision=prec)
+        net.load_state_dict(synth.init_state(net.specs, seed=2, perturb=True))
+        net = net.to(dev).train()
+        net.train_engine.step_index = 10          # same dropout masks in both precisions
+        ev, pr = net(db.features, db.extra, ev_px, db.event_mask, pr_px, db.prong_mask)
+        restate.training_loss(ev, pr, ev_t, pr_t, opts).backward()
+        grads[prec] = {n: p.grad.detach().double().clone() for n, p in net.named_parameters() if p.grad is not None}
+        outs[prec] = (ev.detach().double(), pr.detach().double())
+    assert rel_err(outs["bf16"][0], outs["fp32"][0]) < 8e-2 and rel_err(outs["bf16"][1], outs["fp32"][1]) < 8e-2
+    dot = na = nb = 0.0
+    worst = (2.0, "")
+    for n, ga in grads["fp32"].items():
+        gb = grads["bf16"][n]
+        d, a, b = float((ga * gb).sum()), float((ga * ga).sum()), float((gb * gb).sum())
+        dot += d; na += a; nb += b
+        if n.endswith(("conv1.bias", "conv2.bias", "conv.bias", "conv0.bias")) or "position" in n:
+            continue                                # exactly-zero gradients (rounding noise in fp32, zeros in bf16)
+        c = d / ((a * b) ** 0.5 + 1e-300)
+        if c < worst[0]:
+            worst = (c, n)
+    assert dot / (na * nb) ** 0.5 > 0.94, dot / (na * nb) ** 0.5
+    assert 0.97 < (nb / na) ** 0.5 < 1.03
+    assert worst[0] > 0.85, worst
