@@ -235,8 +235,9 @@ def test_bf16_training_path_tracks_fp32_path(dev):
         gb = grads["bf16"][n]
         d, a, b = float((ga * gb).sum()), float((ga * ga).sum()), float((gb * gb).sum())
         dot += d; na += a; nb += b
-        if a < 1e-8 * gtot:
-            continue    # biases in front of a train-mode BatchNorm, the position vector: exactly-zero gradients (noise)
+        if b == 0.0 or a < 1e-8 * gtot:
+            continue    # biases in front of a train-mode BatchNorm (left at exactly zero by the bf16 walk), the position
+                        # vector: exactly-zero gradients, pure rounding noise in the fp32 walk
         c = d / ((a * b) ** 0.5 + 1e-300)
         if c < worst[0]:
             worst = (c, n)
