@@ -515,22 +515,46 @@ template <typename TX, typename TO>
 __global__ void __launch_bounds__(256) bnact_fwd_vec_kernel(const TX* __restrict__ X, int ldx, int xcol0,
                                                             const float* __restrict__ fold, int fold_stride, int C,
                                                             long long m_total, int Hp, int Wp, TO* __restrict__ out, int ldo,
-                                                            int ocol0) {
-  const int cv = C / 8;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= m_total * cv) return;
-  const int c = (int)(idx % cv) * 8;
-  const long long m = idx / cv;
-  float v[8];
-  if (is_ring(m, Hp, Wp)) {
+                                                            int ocol0, int tv, int rows_per_slab) {
+  // a block is tv vector-columns x (256 / tv) rows walking a row slab: no per-element index division, the ring test is
+  // incremental, the per-channel constants are loaded once per thread
+  const int rpi = 256 / tv;
+  const int vx = threadIdx.x % tv, ry = threadIdx.x / tv;
+  const int c = (blockIdx.x * tv + vx) * 8;
+  if (c >= C || ry >= rpi) return;
+  const long long r_begin = (long long)blockIdx.y * rows_per_slab;
+  const long long r_end = min(m_total, r_begin + rows_per_slab);
+  float sc[8], sh[8], al[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = 0.f;
-  } else {
-    ld8<TX>(X + m * (long long)ldx + xcol0 + c, v);
+  for (int i = 0; i < 8; ++i) { sc[i] = fold[c + i]; sh[i] = fold[fold_stride + c + i]; al[i] = fold[2 * fold_stride + c + i]; }
+  const RingTest rt(Hp, Wp);
+  int rr0 = rt.start(r_begin + ry);
+  for (long long m0 = r_begin + ry; m0 < r_end; m0 += (long long)rpi * kVecU) {
+    Raw8<TX> xr[kVecU];
+    int kind[kVecU];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = prelu(fmaf(v[i], fold[c + i], fold[fold_stride + c + i]), fold[2 * fold_stride + c + i]);
+    for (int u = 0; u < kVecU; ++u) {
+      const long long m = m0 + (long long)u * rpi;
+      kind[u] = m >= r_end ? 0 : (rt.ring(rr0) ? 1 : 2);
+      rr0 = rt.advance(rr0, rpi);
+      if (kind[u] == 2) ldraw(X + m * (long long)ldx + xcol0 + c, xr[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < kVecU; ++u) {
+      if (kind[u] == 0) continue;
+      const long long m = m0 + (long long)u * rpi;
+      float v[8];
+      if (kind[u] == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      } else {
+        unpack8(xr[u], v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = prelu(fmaf(v[i], sc[i], sh[i]), al[i]);
+      }
+      st8<TO>(out + m * (long long)ldo + ocol0 + c, v);
+    }
   }
-  st8<TO>(out + m * (long long)ldo + ocol0 + c, v);
 }
 
 // batch statistics -> fold [scale | shift | alpha | mean | rstd], running-stat update (momentum, unbiased var)
@@ -615,14 +639,15 @@ template <typename TO>
 __global__ void stem_pool_fwd_kernel(const float* __restrict__ z, const float* __restrict__ fold, int Hs, int Ws, int C,
                                      TO* __restrict__ blk, int ld, int H, int W, long long total) {
   // one thread = one pooled pixel x 4 channels (float4 loads of the 3x3 window); total counts those quads
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int cq = C >> 2;
+  const long long idx64 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx64 >= total) return;
+  const unsigned idx = (unsigned)idx64;   // the launcher bounds total below 2^31: 32-bit divisions
+  const unsigned cq = (unsigned)C >> 2;
   const int c = (int)(idx % cq) * 4;
-  long long r = idx / cq;
-  const int x = (int)(r % W); r /= W;
-  const int y = (int)(r % H);
-  const int n = (int)(r / H);
+  unsigned r = idx / cq;
+  const int x = (int)(r % (unsigned)W); r /= (unsigned)W;
+  const int y = (int)(r % (unsigned)H);
+  const int n = (int)(r / (unsigned)H);
   const float4 sc = *reinterpret_cast<const float4*>(fold + c), sh = *reinterpret_cast<const float4*>(fold + C + c),
                al = *reinterpret_cast<const float4*>(fold + 2 * C + c);
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -644,14 +669,15 @@ __global__ void stem_pool_fwd_kernel(const float* __restrict__ z, const float* _
 __global__ void stem_pool_bwd_kernel(const float* __restrict__ dblk, int ld, int H, int W, int C, float* __restrict__ dA,
                                      int Hs, int Ws, long long total) {
   // one thread = one stem pixel x 4 channels; window py covers rows 2py .. 2py+2
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int cq = C >> 2;
+  const long long idx64 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx64 >= total) return;
+  const unsigned idx = (unsigned)idx64;   // the launcher bounds total below 2^31: 32-bit divisions
+  const unsigned cq = (unsigned)C >> 2;
   const int c = (int)(idx % cq) * 4;
-  long long r = idx / cq;
-  const int ox = (int)(r % Ws); r /= Ws;
-  const int oy = (int)(r % Hs);
-  const int n = (int)(r / Hs);
+  unsigned r = idx / cq;
+  const int ox = (int)(r % (unsigned)Ws); r /= (unsigned)Ws;
+  const int oy = (int)(r % (unsigned)Hs);
+  const int n = (int)(r / (unsigned)Hs);
   const int py_lo = oy >= 2 ? (oy - 1) >> 1 : 0, py_hi = min(H - 1, oy >> 1);
   const int px_lo = ox >= 2 ? (ox - 1) >> 1 : 0, px_hi = min(W - 1, ox >> 1);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -731,7 +757,7 @@ __global__ void dropout_kernel(T* X, int ld, int col0, int C, long long m_total,
 __global__ void stem_fill_bias_kernel(float* z, const float* __restrict__ bias, int C, long long total4) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one float4 per thread (C % 4 == 0)
   if (idx < total4) {   // the bias lives in the parameter arena: no alignment guarantee, scalar loads
-    const int c = (int)((idx * 4) % C);
+    const int c = (int)(((unsigned)idx * 4u) % (unsigned)C);   // the launcher bounds idx * 4 below 2^32: 32-bit modulo
     reinterpret_cast<float4*>(z)[idx] = make_float4(__ldg(bias + c), __ldg(bias + c + 1), __ldg(bias + c + 2), __ldg(bias + c + 3));
   }
 }
@@ -894,9 +920,17 @@ int bnact_fwd_typed(const void* X, bool x_bf16, int ldx, int xcol0, const float*
   typedef __nv_bfloat16 bf;
   if (x_bf16 && o_bf16 && C % 8 == 0 && ldx % 8 == 0 && xcol0 % 8 == 0 && ldo % 8 == 0 && ocol0 % 8 == 0 &&
       reinterpret_cast<uintptr_t>(X) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0) {
-    const unsigned vgrid = (unsigned)ceil_div_ll(m_total * (C / 8), 256);
+    const int cv = C / 8;
+    const int tv = cv < 32 ? cv : 32;
+    const int rpi = 256 / tv;
+    const int gx = ceil_div(cv, tv);
+    long long vslabs = ceil_div_ll(m_total, (long long)rpi * kVecU * 2);
+    const long long cap = (long long)(148 * 8 / gx > 1 ? 148 * 8 / gx : 1);
+    if (vslabs > cap) vslabs = cap;
+    const int rows_per_slab = (int)ceil_div_ll(m_total, vslabs);
+    dim3 vgrid(gx, (unsigned)ceil_div_ll(m_total, rows_per_slab));
     bnact_fwd_vec_kernel<bf, bf><<<vgrid, 256, 0, stream>>>(static_cast<const bf*>(X), ldx, xcol0, fold, fold_stride, C, m_total,
-                                                            ring_hp, ring_wp, static_cast<bf*>(out), ldo, ocol0);
+                                                            ring_hp, ring_wp, static_cast<bf*>(out), ldo, ocol0, tv, rows_per_slab);
     TCVN_LAUNCH_CHECK();
     return TCVN_OK;
   }
@@ -917,6 +951,8 @@ int pool_typed(int kind, const void* src, const float* fold, void* dst, bool bf1
                int ld, cudaStream_t stream) {
   if (n <= 0) return TCVN_OK;
   if (C % 8 != 0 || ld % 4 != 0) return fail(TCVN_ERR_UNSUPPORTED, "pool: channel count %d / pitch %d must be multiples of 8 / 4", C, ld);
+  if ((long long)n * (H2 > H ? H2 : H) * (W2 > W ? W2 : W) * C >= (1ll << 31) || (long long)n * (H + 2) * (W + 2) * C >= (1ll << 31))
+    return fail(TCVN_ERR_UNSUPPORTED, "pool: more than 2^31 elements in one launch (%d images)", n);
   typedef __nv_bfloat16 bf;
   long long total;
   switch (kind) {
@@ -1112,6 +1148,7 @@ extern "C" int tcvn_t_stem_conv(const float* pixels, int n, int cin, int H, int 
   const int Hs = (H + 6 - 7) / 2 + 1, Ws = (W + 6 - 7) / 2 + 1;
   if (dz == nullptr) {
     const long long outs4 = (long long)n * Hs * Ws * C / 4;
+    if (outs4 >= (1ll << 30)) return fail(TCVN_ERR_UNSUPPORTED, "t_stem_conv: %d images exceed 2^32 stem outputs in one launch", n);
     stem_fill_bias_kernel<<<(unsigned)ceil_div_ll(outs4, 256), 256, 0, stream>>>(z, bias, C, outs4);
     TCVN_LAUNCH_CHECK();
   }
