@@ -762,41 +762,62 @@ __global__ void stem_fill_bias_kernel(float* z, const float* __restrict__ bias, 
   }
 }
 
-// pixels NCHW fp32; for every non-zero input value scatter v*w into the <=16 outputs it reaches (atomic: training path)
-__global__ void stem_conv_scatter_kernel(const float* __restrict__ pixels, int cin, int H, int W, int Hs, int Ws,
-                                         const float* __restrict__ w /*[cin*49][C]*/, int C, float* __restrict__ z,
-                                         const float* __restrict__ dz, float* __restrict__ dw, long long total) {
-  // total = n * cin * H * W input values; one warp per 32 consecutive values, lanes then share the channel loop
-  const long long base = ((long long)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll;
-  const int lane = threadIdx.x & 31;
-  const long long idx = base + lane;
-  float v = 0.f;
-  if (idx < total) v = __ldg(pixels + idx);
-  unsigned nz = __ballot_sync(0xffffffffu, v != 0.f);
-  while (nz) {
-    const int src = __ffs(nz) - 1;
-    nz &= nz - 1;
-    const float val = __shfl_sync(0xffffffffu, v, src);
-    const long long e = base + src;
-    const int x = (int)(e % W);
-    long long r = e / W;
-    const int y = (int)(r % H); r /= H;
-    const int c = (int)(r % cin);
-    const int n = (int)(r / cin);
-    // outputs (oy, ox) with 2*oy - 3 + ky == y, ky in [0,7)
-    for (int ky = (y + 3) & 1; ky < 7; ky += 2) {
-      const int oy = (y + 3 - ky) >> 1;
-      if (oy < 0 || oy >= Hs) continue;
-      for (int kx = (x + 3) & 1; kx < 7; kx += 2) {
-        const int ox = (x + 3 - kx) >> 1;
-        if (ox < 0 || ox >= Ws) continue;
-        const size_t o = (((size_t)n * Hs + oy) * Ws + ox) * C;
-        const size_t wi = ((size_t)(c * 7 + ky) * 7 + kx) * C;
-        for (int ch = lane; ch < C; ch += 32) {
-          if (dz == nullptr) atomicAdd(z + o + ch, val * __ldg(w + wi + ch));
-          else atomicAdd(dw + wi + ch, val * __ldg(dz + o + ch));
+// pixels NCHW fp32; for every non-zero input value scatter v*w into the <=16 outputs it reaches (atomic: training path).
+// Persistent grid, one warp per 32 consecutive values per step, lanes then share the channel loop.  WGRAD: the filter
+// gradient is accumulated in shared memory (cin*49*C <= 9408 floats) and flushed once per CTA - global atomics on the
+// 9.4 k filter entries from every hit of the batch serialise otherwise.
+constexpr int kStemW = 3 * 49 * 64;
+template <bool WGRAD>
+__global__ void __launch_bounds__(256) stem_conv_scatter_kernel(const float* __restrict__ pixels, int cin, int H, int W, int Hs,
+                                                                int Ws, const float* __restrict__ w /*[cin*49][C]*/, int C,
+                                                                float* __restrict__ z, const float* __restrict__ dz,
+                                                                float* __restrict__ dw, unsigned total) {
+  __shared__ float sdw[WGRAD ? kStemW : 1];
+  const int nw = cin * 49 * C;
+  if (WGRAD) {
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) sdw[i] = 0.f;
+    __syncthreads();
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned step = gridDim.x * 8u * 32u;
+  for (unsigned base = (blockIdx.x * 8u + warp) * 32u; base < total; base += step) {
+    const unsigned idx = base + lane;
+    float v = 0.f;
+    if (idx < total) v = __ldg(pixels + idx);
+    unsigned nz = __ballot_sync(0xffffffffu, v != 0.f);
+    while (nz) {
+      const int src = __ffs(nz) - 1;
+      nz &= nz - 1;
+      const float val = __shfl_sync(0xffffffffu, v, src);
+      const unsigned e = base + src;
+      const int x = (int)(e % (unsigned)W);
+      unsigned r = e / (unsigned)W;
+      const int y = (int)(r % (unsigned)H); r /= (unsigned)H;
+      const int c = (int)(r % (unsigned)cin);
+      const int n = (int)(r / (unsigned)cin);
+      // outputs (oy, ox) with 2*oy - 3 + ky == y, ky in [0,7)
+      for (int ky = (y + 3) & 1; ky < 7; ky += 2) {
+        const int oy = (y + 3 - ky) >> 1;
+        if (oy < 0 || oy >= Hs) continue;
+        for (int kx = (x + 3) & 1; kx < 7; kx += 2) {
+          const int ox = (x + 3 - kx) >> 1;
+          if (ox < 0 || ox >= Ws) continue;
+          const size_t o = (((size_t)n * Hs + oy) * Ws + ox) * C;
+          const int wi = ((c * 7 + ky) * 7 + kx) * C;
+          for (int ch = lane; ch < C; ch += 32) {
+            if (!WGRAD) atomicAdd(z + o + ch, val * __ldg(w + wi + ch));
+            else atomicAdd(&sdw[wi + ch], val * __ldg(dz + o + ch));
+          }
         }
       }
+    }
+    if (base + step < base) break;   // unsigned wrap-around guard
+  }
+  if (WGRAD) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) {
+      const float a = sdw[i];
+      if (a != 0.f) atomicAdd(dw + i, a);
     }
   }
 }
@@ -805,8 +826,8 @@ __global__ void stem_conv_scatter_kernel(const float* __restrict__ pixels, int c
 // host wrappers
 // ------------------------------------------------------------------------------------------------
 static int slabs_for(long long rows, int* rows_per_slab) {
-  int slabs = (int)ceil_div_ll(rows, 2048);
-  if (slabs > 296) slabs = 296;
+  int slabs = (int)ceil_div_ll(rows, 256);
+  if (slabs > 592) slabs = 592;
   if (slabs < 1) slabs = 1;
   *rows_per_slab = (int)ceil_div_ll(rows, slabs);
   return (int)ceil_div_ll(rows, *rows_per_slab);
@@ -1153,8 +1174,12 @@ extern "C" int tcvn_t_stem_conv(const float* pixels, int n, int cin, int H, int 
     TCVN_LAUNCH_CHECK();
   }
   const long long total = (long long)n * cin * H * W;
-  stem_conv_scatter_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(pixels, cin, H, W, Hs, Ws, w, C, z, dz, dw,
-                                                                                   total);
+  if (total >= (1ll << 32) - (1ll << 22)) return fail(TCVN_ERR_UNSUPPORTED, "t_stem_conv: %d images exceed 2^32 pixel values in one launch", n);
+  if (cin * 49 * C > tcvn::kStemW) return fail(TCVN_ERR_UNSUPPORTED, "t_stem_conv: filter bank larger than %d entries", tcvn::kStemW);
+  long long want = ceil_div_ll(total, 256 * 8);
+  const int grid = (int)(want < 148 * 8 ? (want < 1 ? 1 : want) : 148 * 8);
+  if (dz == nullptr) stem_conv_scatter_kernel<false><<<grid, 256, 0, stream>>>(pixels, cin, H, W, Hs, Ws, w, C, z, dz, dw, (unsigned)total);
+  else stem_conv_scatter_kernel<true><<<grid, 256, 0, stream>>>(pixels, cin, H, W, Hs, Ws, w, C, z, dz, dw, (unsigned)total);
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
 }
