@@ -624,19 +624,6 @@ __global__ void to_bf16_pad_kernel(const float* __restrict__ src, int ld, int co
   dst[idx] = __float2bfloat16_rn(c < cols ? src[m * (long long)ld + c] : 0.f);
 }
 
-// conv2 weight [32][128][3][3] -> Wd[dy][c][dx*32 + n] bf16 (columns 96.. zero): the operand of the input-gradient GEMM
-__global__ void pack_wd_kernel(const float* __restrict__ w2, bf* __restrict__ wd) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 3 * 128 * 128) return;
-  const int col = idx & 127, c = (idx >> 7) & 127, dy = idx >> 14;
-  float v = 0.f;
-  if (col < 96) {
-    const int dx = col >> 5, n = col & 31;
-    v = w2[((n * 128 + c) * 3 + dy) * 3 + dx];
-  }
-  wd[idx] = __float2bfloat16_rn(v);
-}
-
 // conv2 weight gradient from the tensor-core layout dw[dy][k][dx*32 + n] -> += reference layout [n][k][dy][dx]
 __global__ void unpack_conv2_grad_kernel(const float* __restrict__ dw, float* __restrict__ dst) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -689,14 +676,6 @@ struct TWalk16 {
   int stats_scratch(const void* X, bool x_bf16, int ldx, int col0, int C, long long rows, int hp, int wp) {
     TCVN_CUDA(cudaMemsetAsync(dbl(T.sums_scr), 0, sizeof(double) * 2 * C, st));
     return colsums_typed(0, X, x_bf16, ldx, col0, nullptr, false, 0, 0, nullptr, 0, C, rows, hp, wp, dbl(T.sums_scr), C, st);
-  }
-
-  int bias_grad(const void* G, bool g_bf16, int ldg, int col0, int C, long long rows, int hp, int wp, float* dst) {
-    TCVN_CUDA(cudaMemsetAsync(dbl(T.sums_scr), 0, sizeof(double) * C, st));
-    TCVN_TRY(colsums_typed(2, G, g_bf16, ldg, col0, nullptr, false, 0, 0, nullptr, 0, C, rows, hp, wp, dbl(T.sums_scr), C, st));
-    add_sums_kernel<<<ceil_div(C, 128), 128, 0, st>>>(dbl(T.sums_scr), C, dst);
-    TCVN_LAUNCH_CHECK();
-    return TCVN_OK;
   }
 
   int bn_bwd(const void* X, bool x_bf16, int ldx, const void* D, bool d_bf16, int ldd, const float* fold, int fold_stride, int C,
@@ -756,7 +735,7 @@ struct TWalk16 {
   int forward(const float* pixels, float* emb) {
     const CnnPlan& P = T.P;
     const tcvn_cnn_desc& d = P.d;
-    const int n = T.n, C0 = d.init_features, mid = P.mid, g = d.growth;
+    const int n = T.n, C0 = d.init_features, mid = P.mid;
     TCVN_TRY(pack());
     const BlockPlan& B0 = P.blocks[0];
     const long long stem_rows = (long long)n * P.Hs * P.Ws;
@@ -827,7 +806,7 @@ struct TWalk16 {
   int backward(const float* pixels, float* d_emb) {
     const CnnPlan& P = T.P;
     const tcvn_cnn_desc& d = P.d;
-    const int n = T.n, C0 = d.init_features, mid = P.mid, g = d.growth, out = d.out_features;
+    const int n = T.n, C0 = d.init_features, mid = P.mid, out = d.out_features;
     const BlockPlan& last = P.blocks.back();
     const int nb = (int)P.blocks.size();
     float* dwp = f(T.dwp);
