@@ -171,6 +171,61 @@ def time_cpu_train(sample_events: int, steps: int, seed: int):
                       f"backward (dropout = identity), fp32 torch CPU autograd, {steps} timed steps"}
 
 
+def time_torch_eager_b200(dev, infer_events: int, train_events: int):
+    """the reference arithmetic run eagerly by PyTorch ON THE SAME B200 (ATen / cuDNN kernels; the
+    oracle port, since the reference tree is absent on the box) - the baseline the hand-written kernels have to beat.
+    fp32 and bf16 autocast; inference over `infer_events` events (eval), training forward + loss + backward (train-mode
+    BatchNorm, dropout = identity) over `train_events` events.  Bounded: a few seconds."""
+    from oracle import restate
+    restate.FUSED_ATEN = True     # BatchNorm / PReLU through the fused ATen ops the reference's modules call
+    state, opts = oracle_state_and_opts()
+    dstate = {k: v.to(dev) for k, v in state.items()}
+    out = {}
+
+    def timed_ms(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    b_inf = make_inputs(infer_events, 1234).to(dev)
+    b_tr = make_inputs(train_events, 4321).to(dev)
+    g = torch.Generator().manual_seed(99)
+    ev_t = torch.randint(0, 4, (train_events,), generator=g).to(dev)
+    pr_t = torch.randint(0, 8, tuple(b_tr.prong_mask.shape), generator=g)
+    pr_t[~b_tr.prong_mask.cpu()] = -1
+    pr_t = pr_t.to(dev)
+    tstate = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in dstate.items()}
+    for tag, ctx in (("fp32", None), ("bf16_autocast", torch.bfloat16)):
+        def infer():
+            with torch.no_grad(), torch.autocast("cuda", dtype=ctx, enabled=ctx is not None):
+                restate.sparse_forward(dstate, opts, b_inf)
+
+        def train():
+            for v in tstate.values():
+                if v.is_floating_point():
+                    v.grad = None
+            with torch.autocast("cuda", dtype=ctx, enabled=ctx is not None):
+                ev, pr = restate.sparse_forward(tstate, opts, b_tr, train=True)
+            restate.training_loss(ev.float(), pr.float(), ev_t, pr_t, opts).backward()
+
+        ms_i = timed_ms(infer, 3)
+        ms_t = timed_ms(train, 3)
+        out[tag] = {"inference_events_per_s": infer_events / (ms_i / 1e3), "inference_sample_events": infer_events,
+                    "train_events_per_s": train_events / (ms_t / 1e3), "train_sample_events": train_events}
+    out["what"] = ("oracle port of the reference modules (F.conv2d / F.batch_norm / F.prelu / torch.cat, i.e. the ATen + cuDNN kernels "
+                   "the reference's nn modules call) run eagerly on this GPU; train = forward + focal loss + autograd backward, no "
+                   "optimizer step")
+    restate.FUSED_ATEN = False
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_train_leg(args, dev, rank, world, timed, train_events, with_cpu):
     """BASELINE configs[2]: DenseNet TransformerCVN training, event-sharded data parallel, NCCL gradient all-reduce.
     One step = densify -> train-mode forward -> focal loss -> hand-written backward (gradient exchange issued from
@@ -401,9 +456,15 @@ def run_ours(args):
         roofline = {"bound": "tensor", "achieved": tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                     "frac": tflops / pk["bf16_sustained"], "traffic": None, "kernel": "whole DenseNet forward (fp32 path)"}
     cpu = None
+    eager = None
     if not args.no_cpu_baseline:
         v, cms, cores, sample = time_cpu_reference(4, 2, 1, 1234)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        if world == 1:
+            try:
+                eager = time_torch_eager_b200(dev, 64, args.train_events)
+            except Exception as e:   # a baseline must never take the benchmark down
+                eager = {"error": f"{type(e).__name__}: {e}"[:300]}
     launches = launches_timed  # counted by the library itself (tcvn_launch_count) around the timed region
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -417,7 +478,8 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "images_per_s": value * images / args.events,
             "whole_net_tflops": tflops, "roofline": roofline, "rooflines_other": extra_rooflines,
-            "cpu_baseline": cpu, "clocks": sampler.summary(), "train": train, "train_large_batch": train_large}
+            "cpu_baseline": cpu, "clocks": sampler.summary(), "train": train, "train_large_batch": train_large,
+            "torch_eager_b200": eager}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

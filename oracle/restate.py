@@ -8,6 +8,8 @@ unmodified reference by ``oracle/make_golden.py`` -> ``tests/golden/*.pt`` and
 
 Each function cites the reference lines it follows (paths relative to /root/reference).
 Dropout is the identity here (eval, or train with p=0): stochastic masks cannot be pinned.
+Device-agnostic (tensors stay on the device of the inputs): bench.py also times it with CUDA tensors as the
+"PyTorch eager on the same B200" baseline BASELINE.md asks for.
 """
 from __future__ import annotations
 
@@ -20,6 +22,9 @@ import torch.nn.functional as F
 BN_EPS = 1e-5
 BN_MOMENTUM = 0.1
 LN_EPS = 1e-5
+# bench.py's "PyTorch eager on the same B200" baseline sets this: BatchNorm / PReLU through the fused ATen ops the
+# reference's nn.BatchNorm2d / nn.PReLU modules call (same arithmetic; the elementwise restatement below is the oracle)
+FUSED_ATEN = False
 
 
 # ----------------------------------------------------------------------------- ingest
@@ -36,7 +41,7 @@ def densify(values: torch.Tensor, coords: torch.Tensor, h: int, w: int) -> torch
     """
     c = coords.long()
     n = int(c[-1, 0]) + 1
-    out = torch.zeros(n, values.shape[1], h, w, dtype=values.dtype)
+    out = torch.zeros(n, values.shape[1], h, w, dtype=values.dtype, device=values.device)
     out[c[:, 0], :, c[:, 1], c[:, 2]] = values
     return out
 
@@ -53,6 +58,10 @@ def _bn_prelu(state, bn: str, act: str, x: torch.Tensor, train: bool, stats: Opt
     """BatchNorm (torch defaults) followed by per-channel PReLU.  dense_net.py:19-20,30-31,85-86."""
     w, b = state[bn + ".weight"], state[bn + ".bias"]
     rm, rv = state[bn + ".running_mean"], state[bn + ".running_var"]
+    if FUSED_ATEN and stats is None:
+        y = F.batch_norm(x, rm.clone() if train else rm, rv.clone() if train else rv, w, b, training=train,
+                         momentum=BN_MOMENTUM, eps=BN_EPS)
+        return F.prelu(y, state[act + ".weight"])
     shape = [1, -1] + [1] * (x.dim() - 2)
     if train:
         dims = [0] + list(range(2, x.dim()))
@@ -130,11 +139,11 @@ def tokens_forward(state, event_emb: torch.Tensor, prong_emb: torch.Tensor, pron
     pos = state[pe + "event_position_embedding"]
     ev = torch.cat((event_emb, pos.expand(b, -1)), dim=1)
     t = prong_emb.shape[0]
-    pr = torch.cat((torch.zeros(t, feature_dim, dtype=prong_emb.dtype), prong_emb, pos.expand(t, -1)), dim=1)
+    pr = torch.cat((torch.zeros(t, feature_dim, dtype=prong_emb.dtype, device=prong_emb.device), prong_emb, pos.expand(t, -1)), dim=1)
     rows = torch.cat((ev, pr), dim=0) @ state[pe + "combined_embedding.linear.weight"].t()
     rows = _bn_prelu(state, pe + "combined_embedding.norm", pe + "combined_embedding.activation", rows, train, stats)
     i1, i2 = pack_indices(prong_mask)
-    padded = torch.zeros(b, l, rows.shape[1], dtype=rows.dtype)
+    padded = torch.zeros(b, l, rows.shape[1], dtype=rows.dtype, device=rows.device)
     padded[i1, i2] = rows[b:]
     tokens = torch.cat((rows[:b].unsqueeze(1), padded), dim=1)
     return tokens, torch.cat((event_mask, prong_mask), dim=1)
@@ -155,7 +164,7 @@ def encoder_forward(state, tokens: torch.Tensor, mask: torch.Tensor, num_layers:
     dh = d // num_heads
     m = mask.unsqueeze(-1).to(tokens.dtype)
     x = tokens * m
-    neg = torch.zeros(b, 1, 1, s, dtype=tokens.dtype).masked_fill(~mask.view(b, 1, 1, s), float("-inf"))
+    neg = torch.zeros(b, 1, 1, s, dtype=tokens.dtype, device=tokens.device).masked_fill(~mask.view(b, 1, 1, s), float("-inf"))
     for li in range(num_layers):
         p = f"encoder.encoder.layers.{li}."
         qkv = x @ state[p + "self_attn.in_proj_weight"].t() + state[p + "self_attn.in_proj_bias"]
