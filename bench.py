@@ -200,7 +200,7 @@ def time_torch_eager_b200(dev, infer_events: int, train_events: int):
     pr_t = torch.randint(0, 8, tuple(b_tr.prong_mask.shape), generator=g)
     pr_t[~b_tr.prong_mask.cpu()] = -1
     pr_t = pr_t.to(dev)
-    tstate = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in dstate.items()}
+    tstate = {k: (v.clone().requires_grad_(True) if v.is_floating_point() and "running_" not in k else v) for k, v in dstate.items()}
     for tag, ctx in (("fp32", None), ("bf16_autocast", torch.bfloat16)):
         def infer():
             with torch.no_grad(), torch.autocast("cuda", dtype=ctx, enabled=ctx is not None):

@@ -59,7 +59,7 @@ def _bn_prelu(state, bn: str, act: str, x: torch.Tensor, train: bool, stats: Opt
     w, b = state[bn + ".weight"], state[bn + ".bias"]
     rm, rv = state[bn + ".running_mean"], state[bn + ".running_var"]
     if FUSED_ATEN and stats is None:
-        y = F.batch_norm(x, rm.clone() if train else rm, rv.clone() if train else rv, w, b, training=train,
+        y = F.batch_norm(x, rm.detach().clone() if train else rm, rv.detach().clone() if train else rv, w, b, training=train,
                          momentum=BN_MOMENTUM, eps=BN_EPS)
         return F.prelu(y, state[act + ".weight"])
     shape = [1, -1] + [1] * (x.dim() - 2)
