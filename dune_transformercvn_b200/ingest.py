@@ -46,3 +46,27 @@ def densify(values: torch.Tensor, coords: torch.Tensor, image_size: Sequence[int
 def sparse_to_dense(features: torch.Tensor, coordinates: torch.Tensor, image_size) -> torch.Tensor:
     """Same contract as the reference function of this name (features already scaled by the caller)."""
     return densify(features, coordinates, image_size)
+
+
+def collate_sparse(coordinates, values, masks):
+    """Drop-in for ``MinkowskiCollection.collate_sparse`` (transformercvn/dataset/minkowski_dataset.py:34-47) for samples
+    that already live on the GPU: lists of per-event ``(nnz_e,3)`` int32 coordinates ``[image-in-event, y, x]``,
+    ``(nnz_e,C)`` values and ``(L,)`` bool masks -> ``(coords (nnz,3)`` with batch-global image indices, ``values
+    (nnz,C))``.  One scan + one pass over the hits on the device; no per-event ``.item()`` sync."""
+    import ctypes as C
+    if len(coordinates) == 0:
+        raise _lib.TcvnError("collate_sparse: empty batch")
+    _lib.require_cuda(coordinates[0], "collate_sparse(coordinates)")
+    L = _lib.load()
+    dev = coordinates[0].device
+    coords = torch.cat([c.to(torch.int32) for c in coordinates]).contiguous()
+    vals = torch.cat(list(values))
+    hits = torch.tensor([int(c.shape[0]) for c in coordinates], dtype=torch.int32).to(dev, non_blocking=True)  # shapes: host facts
+    m = torch.stack([mk.to(torch.uint8) for mk in masks]).contiguous()
+    b, slots = m.shape
+    nbytes = L.tcvn_collate_workspace_bytes(b)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    out = torch.empty_like(coords)
+    _lib.check(L.tcvn_collate_coords(_lib.ptr(coords), coords.shape[0], _lib.ptr(hits), None, _lib.ptr(m), b, slots, _lib.ptr(out),
+                                     _lib.ptr(ws), nbytes, _lib.stream_ptr(dev)), "tcvn_collate_coords")
+    return out, vals

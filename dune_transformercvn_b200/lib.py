@@ -23,6 +23,7 @@ MAX_BLOCKS, MAX_DECODER_LAYERS = 8, 8
 # every symbol include/tcvn.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = (
     "tcvn_abi_version", "tcvn_last_error", "tcvn_launch_count", "tcvn_densify",
+    "tcvn_collate_workspace_bytes", "tcvn_collate_coords",
     "tcvn_cnn_arena_floats", "tcvn_cnn_packed_bytes", "tcvn_cnn_pack", "tcvn_cnn_workspace_bytes",
     "tcvn_cnn_forward", "tcvn_cnn_forward_sparse", "tcvn_cnn_run_layer", "tcvn_cnn_read_stage",
     "tcvn_seq_packed_bytes", "tcvn_seq_pack", "tcvn_seq_workspace_bytes", "tcvn_seq_forward",
@@ -69,6 +70,9 @@ def load() -> C.CDLL:
     lib.tcvn_last_error.restype = C.c_char_p
     lib.tcvn_launch_count.restype = C.c_longlong
     lib.tcvn_densify.argtypes = [vp, vp, i32, i64, i32, i32, i32, i32, f32, vp, i32, vp]
+    lib.tcvn_collate_workspace_bytes.argtypes = [i32]
+    lib.tcvn_collate_workspace_bytes.restype = sz
+    lib.tcvn_collate_coords.argtypes = [vp, i64, vp, vp, vp, i32, i32, vp, vp, sz, vp]
     lib.tcvn_cnn_arena_floats.argtypes = [C.POINTER(CnnDesc)]
     lib.tcvn_cnn_arena_floats.restype = i64
     lib.tcvn_cnn_packed_bytes.argtypes = [C.POINTER(CnnDesc), i32]

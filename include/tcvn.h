@@ -71,6 +71,17 @@ int tcvn_densify(const int32_t* coords, const void* values, tcvn_value_dtype val
                  int channels, int n_images, int height, int width, float divisor, float* out,
                  tcvn_dense_layout layout, tcvn_stream_t stream);
 
+/* Collate: the events' COO hit lists concatenated in event order, image index still LOCAL to the event -> batch-global
+ * image indices (what tcvn_densify / tcvn_cnn_forward_sparse consume).
+ * Replaces: MinkowskiCollection.collate_sparse  transformercvn/dataset/minkowski_dataset.py:34-47 (Python loop,
+ *           coord[:,0] += images of all earlier events, one .item() sync per event).
+ * hits_per_event (n_events) int32; the number of images of an event is images_per_event[e] or, when that is NULL,
+ * the number of set flags in masks[e, 0..max_slots) (the reference uses mask.sum()).  coords_out may alias coords_in. */
+size_t tcvn_collate_workspace_bytes(int n_events);
+int tcvn_collate_coords(const int32_t* coords_in, int64_t nnz, const int32_t* hits_per_event, const int32_t* images_per_event,
+                        const uint8_t* masks, int n_events, int max_slots, int32_t* coords_out, void* workspace,
+                        size_t workspace_bytes, tcvn_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------
  * DenseNet pixel-map embedding.
  * Replaces: transformercvn/network/layers/dense_net.py:97-167 (DenseNet), :8-45 (Bottleneck),

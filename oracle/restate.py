@@ -46,6 +46,18 @@ def densify(values: torch.Tensor, coords: torch.Tensor, h: int, w: int) -> torch
     return out
 
 
+def collate_sparse(coordinates, values, masks):
+    """dataset/minkowski_dataset.py:34-47 (MinkowskiCollection.collate_sparse): column 0 of every event's coordinates
+    is offset by the number of images (mask.sum()) of all earlier events; lists are concatenated in event order."""
+    out, total = [], 0
+    for coord, mask in zip(coordinates, masks):
+        c = coord.clone()
+        c[:, 0] += total
+        out.append(c)
+        total += int(mask.sum())
+    return torch.cat(out), torch.cat(list(values))
+
+
 # ----------------------------------------------------------------------------- DenseNet
 class Stats:
     """Collects updated BN running statistics in train mode (momentum 0.1, unbiased var)."""

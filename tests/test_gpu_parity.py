@@ -267,3 +267,29 @@ def test_max_prong_count_ingest_and_forward(dev, precision, tol):
     assert torch.equal(ev, ev_m) and torch.equal(pr, pr_m)          # COO-direct stem == densify kernel + dense stem
     assert (ev.argmax(-1).cpu() == want_ev.argmax(-1)).all()
     assert (pr.argmax(-1).cpu() == want_pr.argmax(-1)).all()
+
+
+# ------------------------------------------------------------------------------------------ collate
+def test_collate_bit_exact_vs_golden_and_oracle(golden_dir, dev):
+    from dune_transformercvn_b200.ingest import collate_sparse
+    cases = torch.load(os.path.join(golden_dir, "collate.pt"))
+    for name, c in cases.items():
+        got_c, got_v = collate_sparse([t.to(dev) for t in c["coords"]], [t.to(dev) for t in c["values"]],
+                                      [t.to(dev) for t in c["masks"]])
+        assert got_c.dtype == torch.int32
+        assert torch.equal(got_c.cpu(), c["out_coords"]), name
+        assert torch.equal(got_v.cpu(), c["out_values"]), name
+    # a full-size batch: collate -> densify equals densify of the already-global list the generator makes
+    b = synth.make_batch(64, seed=9)
+    starts = torch.cumsum(torch.tensor([0] + b.prongs_per_event), 0)
+    per_event, vals, masks = [], [], []
+    img = b.prong_coords[:, 0].long()
+    for e, p in enumerate(b.prongs_per_event):
+        sel = (img >= starts[e]) & (img < starts[e + 1])
+        ce = b.prong_coords[sel].clone()
+        ce[:, 0] -= int(starts[e])
+        per_event.append(ce.to(dev)); vals.append(b.prong_values[sel].to(dev)); masks.append(b.prong_mask[e].to(dev))
+    got_c, got_v = collate_sparse(per_event, vals, masks)
+    assert torch.equal(got_c.cpu(), b.prong_coords) and torch.equal(got_v.cpu(), b.prong_values)
+    want_c, _ = restate.collate_sparse([t.cpu() for t in per_event], [t.cpu() for t in vals], [t.cpu() for t in masks])
+    assert torch.equal(got_c.cpu(), want_c)

@@ -84,3 +84,12 @@ def test_train_forward_backward_matches_reference(golden_dir, dtype, tol, gtol):
     for k, v in g["running"].items():
         ours = stats.updated[k].detach() if k in stats.updated else state[k]   # dead modules keep their buffers
         assert rel_err(ours, v) < 10 * tol, k
+
+
+def test_collate_matches_reference_golden(golden_dir):
+    """oracle.restate.collate_sparse against the frozen outputs of the reference's own MinkowskiCollection.collate_sparse."""
+    cases = torch.load(os.path.join(golden_dir, "collate.pt"))
+    for name, c in cases.items():
+        got_c, got_v = restate.collate_sparse(c["coords"], c["values"], c["masks"])
+        assert torch.equal(got_c, c["out_coords"]) and got_c.dtype == c["out_coords"].dtype, name
+        assert torch.equal(got_v, c["out_values"]), name
