@@ -451,7 +451,8 @@ def run_ours(args):
     pk = peaks()
     total_images = images  # per rank; every rank has the same expected count
     tflops = total_images * GFLOP_PER_IMAGE_FWD * 1e9 * args.steps / (ms / 1e3) / 1e12
-    roofline, extra_rooflines = kernel_rooflines(net, resident, batch, dev, pk, args) if args.precision == "bf16" else (None, {})
+    roofline, extra_rooflines = (kernel_rooflines(net, resident, batch, dev, pk, args)
+                                 if args.precision == "bf16" and not args.no_roofline else (None, {}))
     if roofline is None:
         roofline = {"bound": "tensor", "achieved": tflops, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                     "frac": tflops / pk["bf16_sustained"], "traffic": None, "kernel": "whole DenseNet forward (fp32 path)"}
@@ -512,6 +513,7 @@ def main():
     ap.add_argument("--events", type=int, default=256)
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the isolated layer-kernel timings (chunk-size sweeps)")
     ap.add_argument("--no-train", action="store_true", help="skip the training leg (BASELINE configs[2]) reported under \"train\"")
     ap.add_argument("--train-events", type=int, default=16, help="events per GPU per training step (2023_08_07 JSON batch_size)")
     ap.add_argument("--train-events-large", type=int, default=64, help="second training measurement at a larger per-GPU batch "

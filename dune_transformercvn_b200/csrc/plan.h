@@ -197,10 +197,11 @@ inline bool CnnPlan::build(const tcvn_cnn_desc& d, tcvn_precision prec, int n_im
   // workspace: block b is processed `chunk` images at a time; later blocks have smaller maps and take whole
   // multiples of the previous block's chunk so that their launches still fill the 148 SMs.  The chunk is sized
   // by a working-set budget (concat buffer + bottleneck intermediate).  Measured on B200 (scripts/sweep_budget.sh,
-  // 256-event batch): 48 MB 5.3k, 80 MB 6.6k, 160 MB 7.7k, 320 MB 8.7k, 768 MB 9.3k, 1024 MB 9.3k events/s - the
+  // 256-event batch; re-measured after conv1 became HBM-bound: 64 MB 6.1k, 128 MB 7.9k, 256 MB 9.1k, 768 MB 10.2k,
+  // 1536 MB 10.6k, 3072 MB 10.5k): 48 MB 5.3k, 80 MB 6.6k, 160 MB 7.7k, 320 MB 8.7k, 768 MB 9.3k, 1024 MB 9.3k events/s - the
   // layer kernels are issue/latency-bound, not HBM-bound, so keeping a chunk inside the 126 MB L2 buys nothing
   // yet and long persistent launches win; revisit when the kernels approach the memory roofline.
-  size_t l2_budget = (size_t)768 << 20;
+  size_t l2_budget = (size_t)1536 << 20;
   if (const char* e = getenv("TCVN_L2_BUDGET_MB")) { const int mb = atoi(e); if (mb > 0) l2_budget = (size_t)mb << 20; }
   // tiles of the two persistent kernels of a dense layer (128 / 126 rows) over `c` images: fraction of the
   // last wave of 148 CTAs that does useful work
