@@ -244,3 +244,51 @@ def test_bf16_training_path_tracks_fp32_path(dev):
     assert dot / (na * nb) ** 0.5 > 0.94, dot / (na * nb) ** 0.5
     assert 0.97 < (nb / na) ** 0.5 < 1.03
     assert worst[0] > 0.85, worst
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_training_loop_reduces_the_loss(dev, precision):
+    """End to end: train-mode forward, focal loss, hand-written backward, fused clip + AdamW, repeated on one batch.
+    The loss on that batch must fall (dropout on, as configured)."""
+    opts = PathOptions.tutorial()
+    torch.manual_seed(0)
+    net = NeutrinoDenseNetwork(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES, precision=precision).to(dev).train()
+    opt = training.TcvnAdamW(training.reference_param_groups(net, opts.l2_penalty), lr=2e-3, max_grad_norm=opts.gradient_clip)
+    batch = synth.make_batch(8, seed=3, max_prongs=6).to(dev)
+    g = torch.Generator().manual_seed(1)
+    ev_t = torch.randint(0, NUM_EVENT_CLASSES, (8,), generator=g).to(dev)
+    pr_t = torch.randint(0, NUM_PRONG_CLASSES, tuple(batch.prong_mask.shape), generator=g)
+    pr_t[~batch.prong_mask.cpu()] = -1
+    pr_t = pr_t.to(dev)
+    losses = []
+    for _ in range(25):
+        opt.zero_grad()
+        ev, pr = net.forward_sparse(batch)
+        loss = restate.training_loss(ev, pr, ev_t, pr_t, opts)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss.detach()))
+    assert all(l == l for l in losses), losses            # no NaN
+    assert sum(losses[-5:]) / 5 < 0.6 * sum(losses[:3]) / 3, losses
+    # the eval path sees the trained weights and running buffers
+    net.eval()
+    with torch.no_grad():
+        ev_e, _ = net.forward_sparse(batch)
+    assert torch.isfinite(ev_e).all()
+
+
+def test_training_at_the_maximum_prong_count(dev):
+    """BASELINE configs[4] shape in training: 20 prongs per event (21-token sequences), fp32 walk vs fp64 autograd over the oracle."""
+    opts, net, state, batch, db, ev_px, pr_px = _setup(dev, [20, 20], 0.0)
+    g = torch.Generator().manual_seed(8)
+    ev_t = torch.randint(0, NUM_EVENT_CLASSES, (2,), generator=g)
+    pr_t = torch.randint(0, NUM_PRONG_CLASSES, (2, 20), generator=g)
+    o_ev, o_pr, o_loss, o_grads, _ = _oracle(state, opts, batch, ev_t, pr_t)
+    ev, pr = net(db.features, db.extra, ev_px, db.event_mask, pr_px, db.prong_mask)
+    assert pr.shape == (2, 20, NUM_PRONG_CLASSES)
+    assert rel_err(ev.detach().cpu(), o_ev) < 1e-4 and rel_err(pr.detach().cpu(), o_pr) < 1e-4
+    loss = restate.training_loss(ev, pr, ev_t.to(dev), pr_t.to(dev), opts)
+    loss.backward()
+    n1 = sum(float((p.grad.double() ** 2).sum()) for p in net.parameters() if p.grad is not None) ** 0.5
+    n2 = sum(float((v ** 2).sum()) for v in o_grads.values()) ** 0.5
+    assert abs(float(loss.detach()) - o_loss) < 1e-4 * abs(o_loss) and abs(n1 - n2) < 2e-3 * n2
