@@ -169,7 +169,7 @@ constexpr int kStemRows = kStemIn;           // window rows (pixels, all channel
 
 // Phases (2)-(4) of the stem for one tile, shared by the dense-window and the COO-direct kernels: scatter the
 // compacted hits, then bias+BN0+PReLU0 and AvgPool2d(3, 2) into the ringed block buffer.
-template <typename TO, int C0>
+template <typename TO, int C0, bool WGLOBAL = false>
 __device__ __forceinline__ void stem_scatter_pool(const float* wsm, float* acc, const float4* hits, int nhits,
                                                   int* touched, int cin, float sc, float sh, float al, int ch, int own_py,
                                                   int own_px, int t, int n, int py0, int px0, TO* __restrict__ blk,
@@ -193,9 +193,10 @@ __device__ __forceinline__ void stem_scatter_pool(const float* wsm, float* acc, 
       if (cx <= kStemTC - 1 && kx >= 0) {
         const float* wp = wsm + (ky * 7 + kx) * C0 + ch;
         float a = acc[(cy * kStemTC + cx) * C0 + ch];
-        a = fmaf(hit.y, wp[0], a);
-        if (cin > 1) a = fmaf(hit.z, wp[49 * C0], a);
-        if (cin > 2) a = fmaf(hit.w, wp[2 * 49 * C0], a);
+        // WGLOBAL: the 37.6 KB filter bank stays in global memory (L1-resident, read-only path) so that two CTAs fit an SM
+        a = fmaf(hit.y, WGLOBAL ? __ldg(wp) : wp[0], a);
+        if (cin > 1) a = fmaf(hit.z, WGLOBAL ? __ldg(wp + 49 * C0) : wp[49 * C0], a);
+        if (cin > 2) a = fmaf(hit.w, WGLOBAL ? __ldg(wp + 2 * 49 * C0) : wp[2 * 49 * C0], a);
         acc[(cy * kStemTC + cx) * C0 + ch] = a;
         if (ch == 0) touched[cy * kStemTC + cx] = 1;
       }
@@ -391,7 +392,7 @@ __global__ void hit_offsets_kernel(const int32_t* __restrict__ coords, long long
 }
 
 template <typename TO, int C0, typename V>
-__global__ void __launch_bounds__(kStemThreads) stem_coo_kernel(const int32_t* __restrict__ coords,
+__global__ void __launch_bounds__(kStemThreads, 2) stem_coo_kernel(const int32_t* __restrict__ coords,
                                                                 const V* __restrict__ values,
                                                                 const long long* __restrict__ image_offsets, int image0,
                                                                 float divisor, int n_images, int cin, int H, int W,
@@ -400,13 +401,14 @@ __global__ void __launch_bounds__(kStemThreads) stem_coo_kernel(const int32_t* _
                                                                 const float* __restrict__ s_shift,
                                                                 const float* __restrict__ s_alpha, TO* __restrict__ blk,
                                                                 int ldo, int Hb, int Wb) {
+  // the kernel is issue/latency-bound (ncu: 41 % issue slots busy at 25 % occupancy with one 136 KB CTA per SM): the
+  // filter bank is read from global memory through the read-only path instead of a shared copy, which brings the
+  // CTA down to 98 KB and two CTAs onto every SM
   extern __shared__ __align__(16) float smem[];
-  float* wsm = smem;                                  // [cin*49][C0]
-  float* acc = wsm + cin * 49 * C0;                   // [289][C0]
+  float* acc = smem;                                  // [289][C0]
   float4* hits = reinterpret_cast<float4*>(acc + kStemTC * kStemTC * C0);  // [39*39] (packed yx, v0, v1, v2)
   __shared__ int wcount[kStemThreads / 32];
   __shared__ int touched[kStemTC * kStemTC];
-  for (int i = threadIdx.x; i < cin * 49 * C0; i += blockDim.x) wsm[i] = __ldg(w0 + i);
   const int tiles_x = (Wb + kStemTP - 1) / kStemTP, tiles_y = (Hb + kStemTP - 1) / kStemTP;
   const int per_image = tiles_x * tiles_y;
   const long long total = (long long)n_images * per_image;
@@ -463,8 +465,8 @@ __global__ void __launch_bounds__(kStemThreads) stem_coo_kernel(const int32_t* _
       __syncthreads();
     }
     __syncthreads();
-    stem_scatter_pool<TO, C0>(wsm, acc, hits, base < kCap ? base : kCap, touched, cin, sc, sh, al, ch, own_py, own_px, t, n,
-                              py0, px0, blk, ldo, Hb, Wb);
+    stem_scatter_pool<TO, C0, true>(w0, acc, hits, base < kCap ? base : kCap, touched, cin, sc, sh, al, ch, own_py, own_px, t, n,
+                                    py0, px0, blk, ldo, Hb, Wb);
   }
 }
 
@@ -483,8 +485,7 @@ int launch_stem_coo(const int32_t* coords, const void* values, bool values_u8, c
   const int Hs = (H + 6 - 7) / 2 + 1, Ws = (W + 6 - 7) / 2 + 1;
   if ((Hs - 3) / 2 + 1 != Hb || (Ws - 3) / 2 + 1 != Wb) return fail(TCVN_ERR_ARG, "stem: geometry mismatch");
   if (cin > 3) return fail(TCVN_ERR_UNSUPPORTED, "stem: %d input channels (kernel handles up to 3)", cin);
-  const size_t smem = ((size_t)cin * 49 * c0 + (size_t)kStemTC * kStemTC * c0) * sizeof(float) +
-                      (size_t)kStemIn * kStemIn * sizeof(float4);
+  const size_t smem = (size_t)kStemTC * kStemTC * c0 * sizeof(float) + (size_t)kStemIn * kStemIn * sizeof(float4);
   int sms = 148;
   {
     int dev = 0;
@@ -493,7 +494,7 @@ int launch_stem_coo(const int32_t* coords, const void* values, bool values_u8, c
   }
   const long long tiles = (long long)n * ((Wb + kStemTP - 1) / kStemTP) * ((Hb + kStemTP - 1) / kStemTP);
   if (tiles >= (1ll << 31)) return fail(TCVN_ERR_UNSUPPORTED, "stem: too many tiles in one chunk");
-  const int grid = (int)(tiles < (long long)sms ? tiles : (long long)sms);
+  const int grid = (int)(tiles < 2ll * sms ? tiles : 2ll * sms);   // two resident CTAs per SM
 #define TCVN_STEM_COO(TO, V)                                                                                          \
   do {                                                                                                                \
     TCVN_CUDA(cudaFuncSetAttribute(stem_coo_kernel<TO, 64, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
