@@ -498,6 +498,8 @@ int launch_stem_coo(const int32_t* coords, const void* values, bool values_u8, c
 #define TCVN_STEM_COO(TO, V)                                                                                          \
   do {                                                                                                                \
     TCVN_CUDA(cudaFuncSetAttribute(stem_coo_kernel<TO, 64, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    TCVN_CUDA(cudaFuncSetAttribute(stem_coo_kernel<TO, 64, V>, cudaFuncAttributePreferredSharedMemoryCarveout,          \
+                                   (int)cudaSharedmemCarveoutMaxShared));                                               \
     stem_coo_kernel<TO, 64, V><<<grid, kStemThreads, smem, stream>>>(coords, static_cast<const V*>(values), image_offsets, \
                                                                      image0, divisor, n, cin, H, W, w0, s_scale, s_shift, \
                                                                      s_alpha, static_cast<TO*>(blk), ldo, Hb, Wb);     \
