@@ -293,3 +293,22 @@ def test_collate_bit_exact_vs_golden_and_oracle(golden_dir, dev):
     assert torch.equal(got_c.cpu(), b.prong_coords) and torch.equal(got_v.cpu(), b.prong_values)
     want_c, _ = restate.collate_sparse([t.cpu() for t in per_event], [t.cpu() for t in vals], [t.cpu() for t in masks])
     assert torch.equal(got_c.cpu(), want_c)
+
+
+def test_bf16_top1_agreement_at_full_size(dev):
+    """BASELINE configs[1] size (256 events, 1679 maps): bf16 tcgen05 path vs the fp32 path of this library: logits within
+    2e-2, top-1 event / prong class agreement >= 99.9 % (north_star).  Measured: 1e-4 / 100 % (scripts/gpu_top1.py)."""
+    opts = PathOptions.tutorial()
+    batch = synth.make_batch(256, seed=1234, max_prongs=10).to(dev)
+    outs = {}
+    for prec in ("fp32", "bf16"):
+        net = NeutrinoDenseNetwork(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES, precision=prec)
+        net.load_state_dict(synth.init_state(net.specs, seed=1, perturb=True))
+        net = net.to(dev).eval()
+        with torch.no_grad():
+            outs[prec] = net.forward_sparse(batch)
+    (ev32, pr32), (ev16, pr16) = outs["fp32"], outs["bf16"]
+    m = batch.prong_mask
+    assert rel_err(ev16, ev32) < BF16_TOL and rel_err(pr16[m], pr32[m]) < BF16_TOL
+    assert float((ev16.argmax(-1) == ev32.argmax(-1)).float().mean()) >= 0.999
+    assert float((pr16.argmax(-1) == pr32.argmax(-1))[m].float().mean()) >= 0.999
