@@ -173,7 +173,7 @@ class _Engine:
         return out
 
     def cnn_sparse(self, tag: str, values: torch.Tensor, coords: torch.Tensor, n: int, prec: int,
-                   divisor: float = 255.0) -> torch.Tensor:
+                   divisor: float = 255.0, ws_kind: str = "cnn") -> torch.Tensor:
         """Pixel-map embedding straight from the COO hit list (the dense map is never built)."""
         L = _lib.load()
         net = self.owner[0]
@@ -195,7 +195,7 @@ class _Engine:
         if values.dim() != 2 or values.shape[1] != d.in_channels:
             raise _lib.TcvnError(f"{tag} hit values have shape {tuple(values.shape)}, expected (nnz,{d.in_channels})")
         nbytes = L.tcvn_cnn_workspace_bytes(C.byref(d), prec, n)
-        ws = self.workspace("cnn", nbytes, values.device)
+        ws = self.workspace(ws_kind, nbytes, values.device)
         _lib.check(L.tcvn_cnn_forward_sparse(C.byref(d), prec, _lib.ptr(self.packed[tag]), _lib.ptr(coords),
                                              _lib.ptr(values), vd, coords.shape[0], float(divisor), n, _lib.ptr(out),
                                              _lib.ptr(ws), ws.numel(), _lib.stream_ptr(values.device)),
@@ -347,6 +347,8 @@ class NeutrinoDenseNetwork(nn.Module):
                                                      num_event_classes)
         engine = _Engine(self)
         self._engine = (engine,)
+        self.overlap_cnns = True     # eval forward_sparse: event CNN on a side stream (+1.7 % at 256 events)
+        self._side = None
         for name, cls in (("prong_embedding", ProngEmbedding), ("encoder", ProngEncoder),
                           ("event_decoder", EventDecoder), ("prong_decoder", ProngDecoder)):
             m = cls()
@@ -411,8 +413,23 @@ class NeutrinoDenseNetwork(nn.Module):
         prec = _PRECISIONS[self.precision]
         _lib.require_cuda(batch.event_values, "event hit values")
         eng.ensure_packed(prec)
-        ev = eng.cnn_sparse("event", batch.event_values, batch.event_coords, batch.num_events, prec)
-        pr = eng.cnn_sparse("prong", batch.prong_values, batch.prong_coords, batch.num_prongs, prec)
+        if self.overlap_cnns:
+            # the two CNNs are independent: the event CNN runs on a side stream (own workspace) so that its launch
+            # prologues and wave tails overlap the prong CNN
+            dev = batch.event_values.device
+            main = torch.cuda.current_stream(dev)
+            if self._side is None or self._side.device != dev:
+                self._side = torch.cuda.Stream(device=dev)
+            side = self._side
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                ev = eng.cnn_sparse("event", batch.event_values, batch.event_coords, batch.num_events, prec, ws_kind="cnn_event")
+            pr = eng.cnn_sparse("prong", batch.prong_values, batch.prong_coords, batch.num_prongs, prec)
+            main.wait_stream(side)
+            ev.record_stream(main)
+        else:
+            ev = eng.cnn_sparse("event", batch.event_values, batch.event_coords, batch.num_events, prec)
+            pr = eng.cnn_sparse("prong", batch.prong_values, batch.prong_coords, batch.num_prongs, prec)
         _, _, ev_logits, pr_logits = eng.seq(_lib.SEQ_TOKENS | _lib.SEQ_ENCODER | _lib.SEQ_HEADS, ev, pr,
                                              batch.event_mask, batch.prong_mask)
         return ev_logits, pr_logits
