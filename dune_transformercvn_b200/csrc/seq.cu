@@ -444,6 +444,8 @@ extern "C" int tcvn_seq_forward(const tcvn_seq_desc* d, const void* packed, int 
   const int SR = ((1 + max_prongs + 7) & ~7) + 8;
   const size_t smem = ((size_t)SR * d->hidden * 5 + (size_t)SR * P.in_dim) * sizeof(float);
   TCVN_CUDA(cudaFuncSetAttribute(seq_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // latency-bound, one CTA per event: ask for the full shared-memory carve-out so that two CTAs are resident per SM
+  TCVN_CUDA(cudaFuncSetAttribute(seq_forward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared));
   seq_forward_kernel<<<n_events, kSeqThreads, smem, st>>>(make_dev(P, static_cast<const char*>(packed)), stages,
                                                           event_embedding, prong_embedding, event_mask, prong_mask,
                                                           offsets, n_events, max_prongs, tokens, hidden, event_logits,
