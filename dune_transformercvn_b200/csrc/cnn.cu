@@ -8,6 +8,8 @@
 //   tail:                embedding = PReLU(BN1d(Linear(mean_hw(PReLU(BN(blk[last]))))))
 // Images are processed in per-block chunks (plan.h) so a block's concat buffer stays L2-resident between its
 // layers while the small late blocks still get enough rows per launch to fill the machine.
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "plan.h"
 #include "umma.h"
@@ -32,11 +34,17 @@ struct Walk {
   const void* values = nullptr;
   bool values_u8 = false;
   float divisor = 0.f;
+  void* bins = nullptr;  // scratch of the binned COO stem (present when the caller sized the workspace with the nnz-aware query)
 
   int stem(int i0, int n) {
     const tcvn_cnn_desc& d = P.d;
     const size_t img_floats = (size_t)d.in_channels * d.height * d.width;
     const BlockPlan& B0 = P.blocks[0];
+    if (pixels == nullptr && bins != nullptr)
+      return launch_stem_coo_binned(coords, values, values_u8, reinterpret_cast<const long long*>(ws + P.ws_hitofs), i0, divisor,
+                                    n, d.in_channels, d.height, d.width, pf(pk, P.p_w0), pf(pk, P.p_s_scale),
+                                    pf(pk, P.p_s_shift), pf(pk, P.p_s_alpha), d.init_features, ws + B0.ws_blk, B0.ctot, B0.H,
+                                    B0.W, f32, bins, st);
     if (pixels == nullptr)
       return launch_stem_coo(coords, values, values_u8, reinterpret_cast<const long long*>(ws + P.ws_hitofs), i0, divisor,
                              n, d.in_channels, d.height, d.width, pf(pk, P.p_w0), pf(pk, P.p_s_scale),
@@ -169,6 +177,11 @@ extern "C" int tcvn_cnn_forward_sparse(const tcvn_cnn_desc* d, tcvn_precision pr
     return fail(TCVN_ERR_WORKSPACE, "cnn_forward_sparse: workspace %zu < %zu bytes", workspace_bytes, P.ws_bytes);
   Walk w{P, static_cast<const char*>(packed), nullptr, static_cast<char*>(workspace), stream, prec == TCVN_FP32};
   w.coords = coords; w.values = values; w.values_u8 = value_dtype == TCVN_VAL_U8; w.divisor = divisor;
+  {
+    const size_t base = align_up(P.ws_bytes, 1024);
+    const size_t extra = stem_bins_bytes(P.blocks[0].chunk, P.blocks[0].H, P.blocks[0].W, nnz);
+    if (workspace_bytes >= base + extra && nnz < (1ll << 29) && !getenv("TCVN_STEM_UNBINNED")) w.bins = w.ws + base;
+  }
   TCVN_TRY(launch_hit_offsets(coords, nnz, n_images, reinterpret_cast<long long*>(w.ws + P.ws_hitofs), stream));
   const int last = (int)P.blocks.size() - 1;
   const int top = P.blocks[last].chunk;
@@ -178,6 +191,12 @@ extern "C" int tcvn_cnn_forward_sparse(const tcvn_cnn_desc* d, tcvn_precision pr
     TCVN_TRY(w.tail(n, embedding + (size_t)i0 * d->out_features));
   }
   return TCVN_OK;
+}
+
+extern "C" size_t tcvn_cnn_workspace_bytes_sparse(const tcvn_cnn_desc* d, tcvn_precision prec, int n_images, int64_t nnz) {
+  CnnPlan P;
+  if (!d || nnz < 0 || !CnnPlan::build(*d, prec, n_images, &P)) { set_error("cnn: bad descriptor"); return 0; }
+  return align_up(P.ws_bytes, 1024) + stem_bins_bytes(P.blocks[0].chunk, P.blocks[0].H, P.blocks[0].W, nnz);
 }
 
 extern "C" int tcvn_cnn_run_layer(const tcvn_cnn_desc* d, tcvn_precision prec, const void* packed, void* workspace,

@@ -470,6 +470,188 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_coo_kernel(const int32_t
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Binned COO stem.  stem_coo_kernel makes every one of the 117 tiles of an image walk the image's whole hit list
+// (2 barriers per 512 hits) and zero its 74 KB of accumulators even when no hit falls into its window.  Here the
+// hits are first binned by tile - one thread per tile walks the image's hits IN ORDER, so every bin keeps the
+// order of the hit list and the result stays bit-identical - and the tile loop reads only its own bin; a tile
+// with an empty bin skips the accumulator pass and only stores the per-channel constant.
+//   tile_count / tile_start: [n_images * tiles_per_image (+1)] int32;  tile_hits: hit indices, <= 4 per hit
+// ------------------------------------------------------------------------------------------------
+constexpr int kBinChunk = 256;
+
+template <bool FILL>
+__global__ void __launch_bounds__(128) stem_bin_kernel(const int32_t* __restrict__ coords,
+                                                       const long long* __restrict__ image_offsets, int image0, int H, int W,
+                                                       int tiles_x, int tiles_y, int32_t* __restrict__ tile_count,
+                                                       const int32_t* __restrict__ tile_start, int32_t* __restrict__ tile_hits) {
+  __shared__ int sy[kBinChunk], sx[kBinChunk];
+  const int n = blockIdx.x;
+  const int per_image = tiles_x * tiles_y;
+  const long long lo = __ldg(image_offsets + image0 + n), hi = __ldg(image_offsets + image0 + n + 1);
+  for (int tile0 = 0; tile0 < per_image; tile0 += blockDim.x) {
+    const int tile = tile0 + threadIdx.x;
+    const bool live = tile < per_image;
+    const int iy0 = live ? 4 * (tile / tiles_x) * kStemTP - 3 : 0, ix0 = live ? 4 * (tile % tiles_x) * kStemTP - 3 : 0;
+    int cnt = 0;
+    int32_t* out = (FILL && live) ? tile_hits + tile_start[(size_t)n * per_image + tile] : nullptr;
+    for (long long h0 = lo; h0 < hi; h0 += kBinChunk) {
+      __syncthreads();
+      for (int k = threadIdx.x; k < kBinChunk; k += blockDim.x) {
+        const long long h = h0 + k;
+        int y = -100000, x = -100000;
+        if (h < hi) { y = __ldg(coords + 3 * h + 1); x = __ldg(coords + 3 * h + 2); }
+        if (y < 0 || y >= H || x < 0 || x >= W) { y = -100000; x = -100000; }   // out-of-map hits are dropped, as in stem_coo_kernel
+        sy[k] = y; sx[k] = x;
+      }
+      __syncthreads();
+      if (live) {
+        const int m = (int)(hi - h0 < kBinChunk ? hi - h0 : kBinChunk);
+        for (int k = 0; k < m; ++k) {
+          const unsigned yy = (unsigned)(sy[k] - iy0), xx = (unsigned)(sx[k] - ix0);
+          if (yy < (unsigned)kStemIn && xx < (unsigned)kStemIn) {
+            if (FILL) out[cnt] = (int32_t)(h0 + k);
+            ++cnt;
+          }
+        }
+      }
+    }
+    if (!FILL && live) tile_count[(size_t)n * per_image + tile] = cnt;
+  }
+}
+
+// exclusive scan of n int32 counts by one block (n is a few hundred thousand at most)
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __restrict__ counts, int n, int32_t* __restrict__ start) {
+  __shared__ int part[1024];
+  const int t = threadIdx.x;
+  const int per = (n + 1023) / 1024;
+  const int b = t * per, e = min(n, b + per);
+  int s = 0;
+  for (int i = b; i < e; ++i) s += counts[i];
+  part[t] = s;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const int v = t >= off ? part[t - off] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  int run = part[t] - s;
+  for (int i = b; i < e; ++i) { start[i] = run; run += counts[i]; }
+  if (t == 1023) start[n] = part[1023];
+}
+
+template <typename TO, int C0, typename V>
+__global__ void __launch_bounds__(kStemThreads, 2) stem_coo_binned_kernel(const int32_t* __restrict__ coords,
+                                                                          const V* __restrict__ values,
+                                                                          const int32_t* __restrict__ tile_count,
+                                                                          const int32_t* __restrict__ tile_start,
+                                                                          const int32_t* __restrict__ tile_hits, float divisor,
+                                                                          int n_images, int cin, int H, int W,
+                                                                          const float* __restrict__ w0,
+                                                                          const float* __restrict__ s_scale,
+                                                                          const float* __restrict__ s_shift,
+                                                                          const float* __restrict__ s_alpha,
+                                                                          TO* __restrict__ blk, int ldo, int Hb, int Wb) {
+  extern __shared__ __align__(16) float smem[];
+  float* acc = smem;                                  // [289][C0]
+  float4* hits = reinterpret_cast<float4*>(acc + kStemTC * kStemTC * C0);  // [39*39] (packed yx, v0, v1, v2)
+  __shared__ int touched[kStemTC * kStemTC];
+  const int tiles_x = (Wb + kStemTP - 1) / kStemTP, tiles_y = (Hb + kStemTP - 1) / kStemTP;
+  const int per_image = tiles_x * tiles_y;
+  const long long total = (long long)n_images * per_image;
+  const int t = threadIdx.x;
+  const int ch = t & (C0 - 1);
+  const int own_px = (t >> 6) & 1, own_py = t >> 7;
+  const float sc = __ldg(s_scale + ch), sh = __ldg(s_shift + ch), al = __ldg(s_alpha + ch);
+  constexpr int kCap = kStemIn * kStemIn;
+  for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const int n = (int)tile / per_image;
+    const int rem = (int)tile - n * per_image;
+    const int py0 = (rem / tiles_x) * kStemTP, px0 = (rem % tiles_x) * kStemTP;
+    const int iy0 = 4 * py0 - 3, ix0 = 4 * px0 - 3;
+    int cnt = __ldg(tile_count + tile);
+    if (cnt > kCap) cnt = kCap;
+    const int32_t* bin = tile_hits + __ldg(tile_start + tile);
+    __syncthreads();  // previous tile fully consumed
+    if (t < kStemTC * kStemTC) touched[t] = 0;
+    if (cnt > 0) {
+      float4* a4 = reinterpret_cast<float4*>(acc);
+      for (int i = t; i < kStemTC * kStemTC * C0 / 4; i += blockDim.x) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = t; k < cnt; k += blockDim.x) {
+        const long long h = __ldg(bin + k);
+        const int yy = __ldg(coords + 3 * h + 1) - iy0, xx = __ldg(coords + 3 * h + 2) - ix0;
+        float v[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          if (c < cin) {
+            float val = static_cast<float>(values[h * cin + c]);
+            if (divisor != 0.f) val = __fdiv_rn(val, divisor);  // same bits as the reference's v / 255.0
+            v[c] = val;
+          }
+        hits[k] = make_float4(__int_as_float(yy * 64 + xx), v[0], v[1], v[2]);
+      }
+    }
+    __syncthreads();
+    stem_scatter_pool<TO, C0, true>(w0, acc, hits, cnt, touched, cin, sc, sh, al, ch, own_py, own_px, t, n, py0, px0, blk, ldo,
+                                    Hb, Wb);
+  }
+}
+
+size_t stem_bins_bytes(int n_images, int Hb, int Wb, long long nnz) {
+  const size_t tiles = (size_t)n_images * ((Wb + kStemTP - 1) / kStemTP) * ((Hb + kStemTP - 1) / kStemTP);
+  return align_up((tiles + 1) * sizeof(int32_t), 256) * 2 + align_up((size_t)(4 * nnz + 4) * sizeof(int32_t), 256);
+}
+
+// same contract as launch_stem_coo; bins = scratch of stem_bins_bytes(n, Hb, Wb, nnz of these images) bytes
+int launch_stem_coo_binned(const int32_t* coords, const void* values, bool values_u8, const long long* image_offsets, int image0,
+                           float divisor, int n, int cin, int H, int W, const float* w0, const float* s_scale,
+                           const float* s_shift, const float* s_alpha, int c0, void* blk, int ldo, int Hb, int Wb, bool f32,
+                           void* bins, cudaStream_t stream) {
+  if (c0 != 64) return fail(TCVN_ERR_UNSUPPORTED, "stem: init_features %d (kernel is specialised for 64)", c0);
+  if (n == 0) return TCVN_OK;
+  const int Hs = (H + 6 - 7) / 2 + 1, Ws = (W + 6 - 7) / 2 + 1;
+  if ((Hs - 3) / 2 + 1 != Hb || (Ws - 3) / 2 + 1 != Wb) return fail(TCVN_ERR_ARG, "stem: geometry mismatch");
+  if (cin > 3) return fail(TCVN_ERR_UNSUPPORTED, "stem: %d input channels (kernel handles up to 3)", cin);
+  const int tiles_x = (Wb + kStemTP - 1) / kStemTP, tiles_y = (Hb + kStemTP - 1) / kStemTP;
+  const long long tiles = (long long)n * tiles_x * tiles_y;
+  if (tiles >= (1ll << 31) - 2048) return fail(TCVN_ERR_UNSUPPORTED, "stem: too many tiles in one chunk");
+  char* b = static_cast<char*>(bins);
+  int32_t* tile_count = reinterpret_cast<int32_t*>(b);
+  int32_t* tile_start = reinterpret_cast<int32_t*>(b + align_up((size_t)(tiles + 1) * sizeof(int32_t), 256));
+  int32_t* tile_hits = reinterpret_cast<int32_t*>(b + 2 * align_up((size_t)(tiles + 1) * sizeof(int32_t), 256));
+  stem_bin_kernel<false><<<n, 128, 0, stream>>>(coords, image_offsets, image0, H, W, tiles_x, tiles_y, tile_count, nullptr, nullptr);
+  TCVN_LAUNCH_CHECK();
+  scan_counts_kernel<<<1, 1024, 0, stream>>>(tile_count, (int)tiles, tile_start);
+  TCVN_LAUNCH_CHECK();
+  stem_bin_kernel<true><<<n, 128, 0, stream>>>(coords, image_offsets, image0, H, W, tiles_x, tiles_y, tile_count, tile_start, tile_hits);
+  TCVN_LAUNCH_CHECK();
+  const size_t smem = (size_t)kStemTC * kStemTC * c0 * sizeof(float) + (size_t)kStemIn * kStemIn * sizeof(float4);
+  int sms = 148;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int grid = (int)(tiles < 2ll * sms ? tiles : 2ll * sms);
+#define TCVN_STEM_BIN(TO, V)                                                                                                   \
+  do {                                                                                                                         \
+    TCVN_CUDA(cudaFuncSetAttribute(stem_coo_binned_kernel<TO, 64, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    TCVN_CUDA(cudaFuncSetAttribute(stem_coo_binned_kernel<TO, 64, V>, cudaFuncAttributePreferredSharedMemoryCarveout,          \
+                                   (int)cudaSharedmemCarveoutMaxShared));                                                      \
+    stem_coo_binned_kernel<TO, 64, V><<<grid, kStemThreads, smem, stream>>>(                                                   \
+        coords, static_cast<const V*>(values), tile_count, tile_start, tile_hits, divisor, n, cin, H, W, w0, s_scale, s_shift,  \
+        s_alpha, static_cast<TO*>(blk), ldo, Hb, Wb);                                                                          \
+  } while (0)
+  if (f32 && !values_u8) TCVN_STEM_BIN(float, float);
+  else if (f32 && values_u8) TCVN_STEM_BIN(float, uint8_t);
+  else if (!f32 && !values_u8) TCVN_STEM_BIN(__nv_bfloat16, float);
+  else TCVN_STEM_BIN(__nv_bfloat16, uint8_t);
+#undef TCVN_STEM_BIN
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
 int launch_hit_offsets(const int32_t* coords, long long nnz, int n_images, long long* offsets, cudaStream_t stream) {
   hit_offsets_kernel<<<ceil_div(n_images + 1, 128), 128, 0, stream>>>(coords, nnz, n_images, offsets);
   TCVN_LAUNCH_CHECK();

@@ -25,7 +25,7 @@ EXPORTS = (
     "tcvn_abi_version", "tcvn_last_error", "tcvn_launch_count", "tcvn_densify",
     "tcvn_collate_workspace_bytes", "tcvn_collate_coords",
     "tcvn_cnn_arena_floats", "tcvn_cnn_packed_bytes", "tcvn_cnn_pack", "tcvn_cnn_workspace_bytes",
-    "tcvn_cnn_forward", "tcvn_cnn_forward_sparse", "tcvn_cnn_run_layer", "tcvn_cnn_read_stage",
+    "tcvn_cnn_forward", "tcvn_cnn_forward_sparse", "tcvn_cnn_workspace_bytes_sparse", "tcvn_cnn_run_layer", "tcvn_cnn_read_stage",
     "tcvn_seq_packed_bytes", "tcvn_seq_pack", "tcvn_seq_workspace_bytes", "tcvn_seq_forward",
     "tcvn_t_gemm", "tcvn_t_wgrad", "tcvn_t_colsums", "tcvn_t_bn_finalize", "tcvn_t_bnact_bwd_apply", "tcvn_t_add_colsums",
     "tcvn_t_bnact_fwd", "tcvn_t_pool", "tcvn_t_dropout", "tcvn_t_stem_conv", "tcvn_t_layernorm", "tcvn_t_attention",
@@ -80,6 +80,8 @@ def load() -> C.CDLL:
     lib.tcvn_cnn_pack.argtypes = [C.POINTER(CnnDesc), i32, vp, vp, sz, vp]
     lib.tcvn_cnn_workspace_bytes.argtypes = [C.POINTER(CnnDesc), i32, i32]
     lib.tcvn_cnn_workspace_bytes.restype = sz
+    lib.tcvn_cnn_workspace_bytes_sparse.argtypes = [C.POINTER(CnnDesc), i32, i32, i64]
+    lib.tcvn_cnn_workspace_bytes_sparse.restype = sz
     lib.tcvn_cnn_forward.argtypes = [C.POINTER(CnnDesc), i32, vp, vp, i32, vp, vp, sz, vp]
     lib.tcvn_cnn_forward_sparse.argtypes = [C.POINTER(CnnDesc), i32, vp, vp, vp, i32, i64, f32, i32, vp, vp, sz, vp]
     lib.tcvn_cnn_run_layer.argtypes = [C.POINTER(CnnDesc), i32, vp, vp, sz, i32, i32, i32, i32, vp]

@@ -194,7 +194,7 @@ class _Engine:
         values = values.contiguous()
         if values.dim() != 2 or values.shape[1] != d.in_channels:
             raise _lib.TcvnError(f"{tag} hit values have shape {tuple(values.shape)}, expected (nnz,{d.in_channels})")
-        nbytes = L.tcvn_cnn_workspace_bytes(C.byref(d), prec, n)
+        nbytes = L.tcvn_cnn_workspace_bytes_sparse(C.byref(d), prec, n, coords.shape[0])
         ws = self.workspace(ws_kind, nbytes, values.device)
         _lib.check(L.tcvn_cnn_forward_sparse(C.byref(d), prec, _lib.ptr(self.packed[tag]), _lib.ptr(coords),
                                              _lib.ptr(values), vd, coords.shape[0], float(divisor), n, _lib.ptr(out),

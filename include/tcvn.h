@@ -116,6 +116,10 @@ size_t tcvn_cnn_workspace_bytes(const tcvn_cnn_desc* d, tcvn_precision prec, int
 int tcvn_cnn_forward(const tcvn_cnn_desc* d, tcvn_precision prec, const void* packed, const float* pixels,
                      int n_images, float* embedding, void* workspace, size_t workspace_bytes,
                      tcvn_stream_t stream);
+/* workspace for tcvn_cnn_forward_sparse including the scratch of the binned stem (hits binned by stem tile, order
+ * preserving; tiles without hits only store the per-channel constant).  With a workspace of only tcvn_cnn_workspace_bytes
+ * the sparse forward falls back to the unbinned stem kernel (same bits, slower). */
+size_t tcvn_cnn_workspace_bytes_sparse(const tcvn_cnn_desc* d, tcvn_precision prec, int n_images, int64_t nnz);
 /* Same forward fed straight from the Minkowski-format hit list: fuses sparse_to_dense and the
  * "/ divisor" of preprocess_pixels (trainers/neutrino_full_dense_trainer.py:15-24,59-60) into the stem,
  * so the dense 3 x H x W map is never built.  coords (nnz,3) int32 [image, y, x] sorted by image,
