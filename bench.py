@@ -135,17 +135,6 @@ def run_reference(args):
     emit(line)
 
 
-def focal_loss_mix(ev_logits, pr_logits, ev_t, pr_t, opts):
-    """The reference's loss (neutrino_full_base_trainer.py:148-177), which stays caller-side code: focal loss with
-    gamma, 0.9 event + 0.1 prong over slots with target >= 0."""
-    def focal(logits, t):
-        logp = torch.log_softmax(logits, dim=-1).gather(1, t.view(-1, 1)).squeeze(1)
-        return (-logp * (1 - logp.exp()) ** opts.loss_gamma).mean()
-    sel = pr_t >= 0
-    a = opts.event_prong_loss_proportion
-    return a * focal(ev_logits, ev_t) + (1 - a) * focal(pr_logits[sel], pr_t[sel])
-
-
 def time_cpu_train(sample_events: int, steps: int, seed: int):
     """Reference CPU training step (oracle port, fp32 torch autograd): forward + loss + backward."""
     from oracle import restate
@@ -228,10 +217,11 @@ def time_torch_eager_b200(dev, infer_events: int, train_events: int):
 
 def run_train_leg(args, dev, rank, world, timed, train_events, with_cpu):
     """BASELINE configs[2]: DenseNet TransformerCVN training, event-sharded data parallel, NCCL gradient all-reduce.
-    One step = densify -> train-mode forward -> focal loss -> hand-written backward (gradient exchange issued from
+    One step = densify -> train-mode forward -> fused focal loss (tcvn_loss_forward) -> hand-written backward (gradient exchange issued from
     inside it) -> fused clip + AdamW.  Every rank holds `--train-events` events (weak scaling)."""
     import torch.distributed as dist
     from dune_transformercvn_b200 import lib as tl
+    from dune_transformercvn_b200 import loss as tloss
     from dune_transformercvn_b200 import training
     from dune_transformercvn_b200.config import NUM_EVENT_CLASSES, NUM_PRONG_CLASSES, PathOptions
     from dune_transformercvn_b200.network import NeutrinoDenseNetwork
@@ -257,7 +247,7 @@ def run_train_leg(args, dev, rank, world, timed, train_events, with_cpu):
     def step(b, t):
         opt.zero_grad()
         ev, pr = net.forward_sparse(b)
-        loss = focal_loss_mix(ev, pr, t[0], t[1], opts)
+        loss, _ = tloss.training_loss(ev, pr, t[0], t[1], opts)   # one kernel: focal loss mix + d loss / d logits
         loss.backward()
         opt.step()
         return loss

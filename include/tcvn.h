@@ -304,6 +304,30 @@ int tcvn_seq_train_backward(const tcvn_seq_desc* d, const float* position, const
                             float* d_prong_logits, float* d_event_embedding, float* d_prong_embedding, void* workspace,
                             size_t workspace_bytes, tcvn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Loss and validation metrics on the device: one launch each, no host sync.
+ * tcvn_loss_forward replaces `loss` + the masked_select / log_softmax / softmax / argmax chain of `training_step`
+ * (trainers/neutrino_full_base_trainer.py:148-192): focal loss -log p_t (1 - p_t)^gamma (gamma 0: cross entropy),
+ * mean over the event rows and over the prong slots with target >= 0, out8 = {event_scale * event_loss +
+ * prong_scale * prong_loss, event_loss, prong_loss, event accuracy, prong accuracy, event rows, selected prong
+ * rows, 0}.  d_event_logits (B, E) / d_prong_logits (B, L, P) (both or neither) receive d total / d logits.
+ * prong_logits[b][l][:] starts at element b * prong_stride_event + l * prong_stride_slot (the network returns a
+ * transposed view); targets are int64, a prong target < 0 marks a padded slot. */
+int tcvn_loss_forward(const float* event_logits, const int64_t* event_targets, int n_events, int event_classes,
+                      const float* prong_logits, const int64_t* prong_targets, int max_prongs, int prong_classes,
+                      int64_t prong_stride_event, int64_t prong_stride_slot, float gamma, float event_scale,
+                      float prong_scale, float* out8, float* d_event_logits, float* d_prong_logits, tcvn_stream_t stream);
+/* d_* = g_* times the device scalar *upstream (the chain rule through the scalar loss), one launch for both */
+int tcvn_loss_backward(const float* upstream, const float* g_event, int64_t n_event, const float* g_prong, int64_t n_prong,
+                       float* d_event_logits, float* d_prong_logits, tcvn_stream_t stream);
+/* validation_step (trainers/neutrino_full_base_trainer.py:194-209): softmax probabilities of the event rows and of
+ * the prong slots with target >= 0 (other slots are written as zeros) and the accuracy state
+ * counters4 += {event hits, event rows, prong hits, selected prong rows} (torchmetrics Accuracy(task="multiclass")). */
+int tcvn_metrics_update(const float* event_logits, const int64_t* event_targets, int n_events, int event_classes,
+                        const float* prong_logits, const int64_t* prong_targets, int max_prongs, int prong_classes,
+                        int64_t prong_stride_event, int64_t prong_stride_slot, int64_t* counters4, float* event_prob,
+                        float* prong_prob, tcvn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
