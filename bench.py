@@ -215,6 +215,41 @@ def time_torch_eager_b200(dev, infer_events: int, train_events: int):
     return out
 
 
+def single_event_latency(dev, precision, prongs=6, reps=50):
+    """SURVEY 8f rank 3 (the LArSoft export surface, CreateCompiled.ipynb): one event = (1 + prongs) dense uint8 maps ->
+    probabilities + 128-d embeddings.  Latency of the captured CUDA-graph plan against the same call sequence launched
+    kernel by kernel, CUDA events, pixels resident."""
+    from dune_transformercvn_b200.config import NUM_EVENT_CLASSES, NUM_PRONG_CLASSES, PathOptions
+    from dune_transformercvn_b200.export import EventClassifier
+    from dune_transformercvn_b200.ingest import densify
+    from dune_transformercvn_b200.network import NeutrinoDenseNetwork
+    opts = PathOptions.tutorial()
+    net = NeutrinoDenseNetwork(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES, precision=precision).to(dev).eval()
+    from dune_transformercvn_b200 import synth
+    b = synth.make_batch(1, seed=77, prongs_per_event=[prongs]).to(dev)
+    n_pr = int(b.num_prongs)
+    ev = densify(b.event_values, b.event_coords, (H, W), 1, 1.0)
+    pr = densify(b.prong_values, b.prong_coords, (H, W), n_pr, 1.0)
+    px = torch.cat((ev, pr)).to(torch.uint8)
+    out = {"images": 1 + n_pr, "precision": precision}
+    for tag, graph in (("graph_us", True), ("launch_by_launch_us", False)):
+        clf = EventClassifier(net, "combined", use_graph=graph)
+        for _ in range(3):
+            clf(px)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            clf(px)
+        e1.record()
+        torch.cuda.synchronize()
+        out[tag] = e0.elapsed_time(e1) / reps * 1e3
+        clf.invalidate()
+    del net
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_train_leg(args, dev, rank, world, timed, train_events, with_cpu):
     """BASELINE configs[2]: DenseNet TransformerCVN training, event-sharded data parallel, NCCL gradient all-reduce.
     One step = densify -> train-mode forward -> fused focal loss (tcvn_loss_forward) -> hand-written backward (gradient exchange issued from
@@ -457,6 +492,12 @@ def run_ours(args):
                 eager = time_torch_eager_b200(dev, 64, args.train_events)
             except Exception as e:   # a baseline must never take the benchmark down
                 eager = {"error": f"{type(e).__name__}: {e}"[:300]}
+    single = None
+    if world == 1 and not args.no_train:
+        try:
+            single = single_event_latency(dev, args.precision)
+        except Exception as e:
+            single = {"error": f"{type(e).__name__}: {e}"[:300]}
     launches = launches_timed  # counted by the library itself (tcvn_launch_count) around the timed region
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -471,7 +512,7 @@ def run_ours(args):
             "gpu_launches": launches, "images_per_s": value * images / args.events,
             "whole_net_tflops": tflops, "roofline": roofline, "rooflines_other": extra_rooflines,
             "cpu_baseline": cpu, "clocks": sampler.summary(), "train": train, "train_large_batch": train_large,
-            "torch_eager_b200": eager}
+            "torch_eager_b200": eager, "single_event_latency": single}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

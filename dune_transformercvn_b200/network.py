@@ -153,7 +153,7 @@ class _Engine:
         return buf
 
     # ---- kernels -----------------------------------------------------------------------------
-    def cnn(self, tag: str, pixels: torch.Tensor, prec: int) -> torch.Tensor:
+    def cnn(self, tag: str, pixels: torch.Tensor, prec: int, ws_kind: str = "cnn") -> torch.Tensor:
         L = _lib.load()
         net = self.owner[0]
         pix, feat, _ = embedding_dims(net.options)
@@ -167,7 +167,7 @@ class _Engine:
             raise _lib.TcvnError(f"{tag} pixels have shape {tuple(pixels.shape)}, expected (N,{d.in_channels},{d.height},{d.width})")
         pixels = pixels.contiguous().float()
         nbytes = L.tcvn_cnn_workspace_bytes(C.byref(d), prec, n)
-        ws = self.workspace("cnn", nbytes, pixels.device)
+        ws = self.workspace(ws_kind, nbytes, pixels.device)
         _lib.check(L.tcvn_cnn_forward(C.byref(d), prec, _lib.ptr(self.packed[tag]), _lib.ptr(pixels), n, _lib.ptr(out),
                                       _lib.ptr(ws), ws.numel(), _lib.stream_ptr(pixels.device)), "tcvn_cnn_forward")
         return out

@@ -5,6 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
 from dune_transformercvn_b200 import training
+from dune_transformercvn_b200 import loss as tloss
 from dune_transformercvn_b200.config import NUM_EVENT_CLASSES, NUM_PRONG_CLASSES, PathOptions
 from dune_transformercvn_b200.network import NeutrinoDenseNetwork
 events = int(sys.argv[1]) if len(sys.argv) > 1 else 16
@@ -26,7 +27,7 @@ for overlap in (True, False):
         opt.zero_grad()
         ev, pr = net.forward_sparse(batch)
         t1 = time.perf_counter()
-        loss = bench.focal_loss_mix(ev, pr, ev_t, pr_t, opts)
+        loss, _ = tloss.training_loss(ev, pr, ev_t, pr_t, opts)
         t2 = time.perf_counter()
         loss.backward()
         t3 = time.perf_counter()

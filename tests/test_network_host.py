@@ -58,3 +58,20 @@ def test_cpu_call_fails_loudly(net):
     with pytest.raises(NotImplementedError):   # sub-modules on their own are eval-only
         net.prong_embedding(b.features, b.extra, ev, b.event_mask, ev, b.prong_mask)
     net.eval()
+
+
+def test_export_surface_traces_without_a_gpu_and_rejects_cpu_tensors(net):
+    """torch.export only runs the custom op's shape function, so the exported program can be built on a CPU-only host;
+    actually calling it on CPU tensors fails loudly (no fallback)."""
+    import torch
+    from dune_transformercvn_b200.export import EventClassifier, ExportableEventClassifier
+    from dune_transformercvn_b200.lib import TcvnError
+    net.eval()
+    clf = EventClassifier(net, "combined")
+    px = torch.zeros(4, 3, 400, 280, dtype=torch.uint8)
+    ep = torch.export.export(ExportableEventClassifier(clf), (px,))
+    assert "tcvn.classify_event" in str(ep.graph)
+    shapes = [tuple(n.meta["val"].shape) for n in ep.graph.nodes if n.op == "call_function" and "getitem" in str(n.target)]
+    assert shapes == [(4,), (3, 8), (128,), (3, 128)]
+    with pytest.raises(TcvnError):
+        clf(px)
