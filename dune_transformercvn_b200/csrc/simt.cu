@@ -169,11 +169,9 @@ constexpr int kStemRows = kStemIn;           // window rows (pixels, all channel
 
 // Phases (2)-(4) of the stem for one tile, shared by the dense-window and the COO-direct kernels: scatter the
 // compacted hits, then bias+BN0+PReLU0 and AvgPool2d(3, 2) into the ringed block buffer.
-template <typename TO, int C0, bool WGLOBAL = false>
-__device__ __forceinline__ void stem_scatter_pool(const float* wsm, float* acc, const float4* hits, int nhits,
-                                                  int* touched, int cin, float sc, float sh, float al, int ch, int own_py,
-                                                  int own_px, int t, int n, int py0, int px0, TO* __restrict__ blk,
-                                                  int ldo, int Hb, int Wb) {
+template <int C0, bool WGLOBAL>
+__device__ __forceinline__ void stem_scatter(const float* wsm, float* acc, const float4* hits, int nhits, int* touched, int cin,
+                                             int ch, int own_py, int own_px) {
   // ---- (2) scatter every hit into the conv outputs it reaches (input yy = 2*cy + ky)
   for (int h = 0; h < nhits; ++h) {
     const float4 hit = hits[h];
@@ -202,7 +200,11 @@ __device__ __forceinline__ void stem_scatter_pool(const float* wsm, float* acc, 
       }
     }
   }
-  __syncthreads();
+}
+
+template <typename TO, int C0>
+__device__ __forceinline__ void stem_pool(const float* acc, const int* touched, float sc, float sh, float al, int ch, int t, int n,
+                                          int py0, int px0, TO* __restrict__ blk, int ldo, int Hb, int Wb) {
   // ---- (3)+(4) bias + BN0 + PReLU0, AvgPool2d(3, 2) -> ringed block buffer.  A conv output no hit reached is
   // the per-channel constant PReLU(shift), so a pooling window of nine such outputs is a per-channel constant
   // too (evaluated with the same additions and division as the general case: the shortcut is bit-identical).
@@ -266,6 +268,17 @@ __device__ __forceinline__ void stem_scatter_pool(const float* wsm, float* acc, 
     const size_t row = (size_t)n * (Hb + 2) * (Wb + 2) + (size_t)(py0 + pyl + 1) * (Wb + 2) + (px0 + pxl + 1);
     blk[row * ldo + ch] = from_f32<TO>(s2 / 9.0f);
   }
+}
+
+// phases (2)-(4) back to back (dense-window and un-binned COO kernels)
+template <typename TO, int C0, bool WGLOBAL = false>
+__device__ __forceinline__ void stem_scatter_pool(const float* wsm, float* acc, const float4* hits, int nhits,
+                                                  int* touched, int cin, float sc, float sh, float al, int ch, int own_py,
+                                                  int own_px, int t, int n, int py0, int px0, TO* __restrict__ blk,
+                                                  int ldo, int Hb, int Wb) {
+  stem_scatter<C0, WGLOBAL>(wsm, acc, hits, nhits, touched, cin, ch, own_py, own_px);
+  __syncthreads();
+  stem_pool<TO, C0>(acc, touched, sc, sh, al, ch, t, n, py0, px0, blk, ldo, Hb, Wb);
 }
 
 template <typename TO, int C0>
@@ -479,13 +492,18 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_coo_kernel(const int32_t
 //   tile_count / tile_start: [n_images * tiles_per_image (+1)] int32;  tile_hits: hit indices, <= 4 per hit
 // ------------------------------------------------------------------------------------------------
 constexpr int kBinChunk = 256;
+constexpr int kHitBuf = 256;   // hit records staged per tile and buffer (two buffers: the next tile's arrive under this tile's work)
 
-template <bool FILL>
-__global__ void __launch_bounds__(128) stem_bin_kernel(const int32_t* __restrict__ coords,
-                                                       const long long* __restrict__ image_offsets, int image0, int H, int W,
-                                                       int tiles_x, int tiles_y, int32_t* __restrict__ tile_count,
-                                                       const int32_t* __restrict__ tile_start, int32_t* __restrict__ tile_hits) {
+// FILL = false: count the hits of every tile window.  FILL = true: write the tile's hit RECORDS
+// (window-relative position code, the up-to-3 values already divided) in hit-list order.
+template <bool FILL, typename V>
+__global__ void __launch_bounds__(128) stem_bin_kernel(const int32_t* __restrict__ coords, const V* __restrict__ values,
+                                                       const long long* __restrict__ image_offsets, int image0, int cin,
+                                                       float divisor, int H, int W, int tiles_x, int tiles_y,
+                                                       int32_t* __restrict__ tile_count, const int32_t* __restrict__ tile_start,
+                                                       float4* __restrict__ tile_recs) {
   __shared__ int sy[kBinChunk], sx[kBinChunk];
+  __shared__ float sv[FILL ? kBinChunk : 1][3];
   const int n = blockIdx.x;
   const int per_image = tiles_x * tiles_y;
   const long long lo = __ldg(image_offsets + image0 + n), hi = __ldg(image_offsets + image0 + n + 1);
@@ -494,7 +512,7 @@ __global__ void __launch_bounds__(128) stem_bin_kernel(const int32_t* __restrict
     const bool live = tile < per_image;
     const int iy0 = live ? 4 * (tile / tiles_x) * kStemTP - 3 : 0, ix0 = live ? 4 * (tile % tiles_x) * kStemTP - 3 : 0;
     int cnt = 0;
-    int32_t* out = (FILL && live) ? tile_hits + tile_start[(size_t)n * per_image + tile] : nullptr;
+    float4* out = (FILL && live) ? tile_recs + tile_start[(size_t)n * per_image + tile] : nullptr;
     for (long long h0 = lo; h0 < hi; h0 += kBinChunk) {
       __syncthreads();
       for (int k = threadIdx.x; k < kBinChunk; k += blockDim.x) {
@@ -503,6 +521,17 @@ __global__ void __launch_bounds__(128) stem_bin_kernel(const int32_t* __restrict
         if (h < hi) { y = __ldg(coords + 3 * h + 1); x = __ldg(coords + 3 * h + 2); }
         if (y < 0 || y >= H || x < 0 || x >= W) { y = -100000; x = -100000; }   // out-of-map hits are dropped, as in stem_coo_kernel
         sy[k] = y; sx[k] = x;
+        if (FILL) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            float val = 0.f;
+            if (h < hi && c < cin) {
+              val = static_cast<float>(values[h * cin + c]);
+              if (divisor != 0.f) val = __fdiv_rn(val, divisor);  // same bits as the reference's v / 255.0
+            }
+            sv[k][c] = val;
+          }
+        }
       }
       __syncthreads();
       if (live) {
@@ -510,7 +539,7 @@ __global__ void __launch_bounds__(128) stem_bin_kernel(const int32_t* __restrict
         for (int k = 0; k < m; ++k) {
           const unsigned yy = (unsigned)(sy[k] - iy0), xx = (unsigned)(sx[k] - ix0);
           if (yy < (unsigned)kStemIn && xx < (unsigned)kStemIn) {
-            if (FILL) out[cnt] = (int32_t)(h0 + k);
+            if (FILL) out[cnt] = make_float4(__int_as_float((int)(yy * 64 + xx)), sv[k][0], sv[k][1], sv[k][2]);
             ++cnt;
           }
         }
@@ -541,21 +570,27 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __rest
   if (t == 1023) start[n] = part[1023];
 }
 
-template <typename TO, int C0, typename V>
-__global__ void __launch_bounds__(kStemThreads, 2) stem_coo_binned_kernel(const int32_t* __restrict__ coords,
-                                                                          const V* __restrict__ values,
-                                                                          const int32_t* __restrict__ tile_count,
-                                                                          const int32_t* __restrict__ tile_start,
-                                                                          const int32_t* __restrict__ tile_hits, float divisor,
-                                                                          int n_images, int cin, int H, int W,
-                                                                          const float* __restrict__ w0,
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// The tile loop is a chain of short, dependent phases; what it must never do is wait for global memory.  The bin
+// bounds of the tile after next are loaded into registers and the records of the NEXT tile are copied into the second
+// staging buffer (cp.async) while this tile scatters and pools, so a tile starts with its hits already in shared memory.
+template <typename TO, int C0>
+__global__ void __launch_bounds__(kStemThreads, 2) stem_coo_binned_kernel(const int32_t* __restrict__ tile_start,
+                                                                          const float4* __restrict__ tile_recs,
+                                                                          int n_images, int cin, const float* __restrict__ w0,
                                                                           const float* __restrict__ s_scale,
                                                                           const float* __restrict__ s_shift,
                                                                           const float* __restrict__ s_alpha,
                                                                           TO* __restrict__ blk, int ldo, int Hb, int Wb) {
   extern __shared__ __align__(16) float smem[];
   float* acc = smem;                                  // [289][C0]
-  float4* hits = reinterpret_cast<float4*>(acc + kStemTC * kStemTC * C0);  // [39*39] (packed yx, v0, v1, v2)
+  float4* hitbuf = reinterpret_cast<float4*>(acc + kStemTC * kStemTC * C0);  // [2][kHitBuf] (packed yx, v0, v1, v2)
   __shared__ int touched[kStemTC * kStemTC];
   const int tiles_x = (Wb + kStemTP - 1) / kStemTP, tiles_y = (Hb + kStemTP - 1) / kStemTP;
   const int per_image = tiles_x * tiles_y;
@@ -565,42 +600,57 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_coo_binned_kernel(const 
   const int own_px = (t >> 6) & 1, own_py = t >> 7;
   const float sc = __ldg(s_scale + ch), sh = __ldg(s_shift + ch), al = __ldg(s_alpha + ch);
   constexpr int kCap = kStemIn * kStemIn;
-  for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
-    const int n = (int)tile / per_image;
-    const int rem = (int)tile - n * per_image;
+  const long long stride = gridDim.x;
+  long long tile = blockIdx.x;
+  if (tile >= total) return;
+  // bin bounds of this tile and the next one; records of this tile -> buffer 0
+  int b0 = __ldg(tile_start + tile), e0 = __ldg(tile_start + tile + 1);
+  int b1 = 0, e1 = 0;
+  if (tile + stride < total) { b1 = __ldg(tile_start + tile + stride); e1 = __ldg(tile_start + tile + stride + 1); }
+  if (t < min(e0 - b0, kHitBuf)) cp_async16(hitbuf + t, tile_recs + b0 + t);
+  cp_async_commit();
+  int cur = 0;
+  for (; tile < total; tile += stride) {
+    const int n = (int)(tile / per_image);
+    const int rem = (int)(tile - (long long)n * per_image);
     const int py0 = (rem / tiles_x) * kStemTP, px0 = (rem % tiles_x) * kStemTP;
-    const int iy0 = 4 * py0 - 3, ix0 = 4 * px0 - 3;
-    int cnt = __ldg(tile_count + tile);
+    int cnt = e0 - b0;
     if (cnt > kCap) cnt = kCap;
-    const int32_t* bin = tile_hits + __ldg(tile_start + tile);
-    __syncthreads();  // previous tile fully consumed
+    // bounds of the tile after next (consumed one iteration later), records of the next tile -> the other buffer
+    int b2 = 0, e2 = 0;
+    if (tile + 2 * stride < total) { b2 = __ldg(tile_start + tile + 2 * stride); e2 = __ldg(tile_start + tile + 2 * stride + 1); }
+    __syncthreads();  // previous tile fully consumed (its staging buffer, acc, touched)
+    if (t < min(e1 - b1, kHitBuf)) cp_async16(hitbuf + (cur ^ 1) * kHitBuf + t, tile_recs + b1 + t);
+    cp_async_commit();
     if (t < kStemTC * kStemTC) touched[t] = 0;
     if (cnt > 0) {
       float4* a4 = reinterpret_cast<float4*>(acc);
       for (int i = t; i < kStemTC * kStemTC * C0 / 4; i += blockDim.x) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      for (int k = t; k < cnt; k += blockDim.x) {
-        const long long h = __ldg(bin + k);
-        const int yy = __ldg(coords + 3 * h + 1) - iy0, xx = __ldg(coords + 3 * h + 2) - ix0;
-        float v[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          if (c < cin) {
-            float val = static_cast<float>(values[h * cin + c]);
-            if (divisor != 0.f) val = __fdiv_rn(val, divisor);  // same bits as the reference's v / 255.0
-            v[c] = val;
-          }
-        hits[k] = make_float4(__int_as_float(yy * 64 + xx), v[0], v[1], v[2]);
+    }
+    cp_async_wait<1>();   // this tile's records (committed one iteration ago) have landed
+    __syncthreads();
+    if (cnt > 0) {
+      float4* hb = hitbuf + cur * kHitBuf;
+      stem_scatter<C0, true>(w0, acc, hb, min(cnt, kHitBuf), touched, cin, ch, own_py, own_px);
+      for (int done = kHitBuf; done < cnt; done += kHitBuf) {   // dense windows only: further chunks, loaded in place
+        __syncthreads();
+        const int m = min(cnt - done, kHitBuf);
+        if (t < m) hb[t] = __ldg(tile_recs + b0 + done + t);
+        __syncthreads();
+        stem_scatter<C0, true>(w0, acc, hb, m, touched, cin, ch, own_py, own_px);
       }
     }
     __syncthreads();
-    stem_scatter_pool<TO, C0, true>(w0, acc, hits, cnt, touched, cin, sc, sh, al, ch, own_py, own_px, t, n, py0, px0, blk, ldo,
-                                    Hb, Wb);
+    stem_pool<TO, C0>(acc, touched, sc, sh, al, ch, t, n, py0, px0, blk, ldo, Hb, Wb);
+    b0 = b1; e0 = e1; b1 = b2; e1 = e2;
+    cur ^= 1;
   }
+  cp_async_wait<0>();
 }
 
 size_t stem_bins_bytes(int n_images, int Hb, int Wb, long long nnz) {
   const size_t tiles = (size_t)n_images * ((Wb + kStemTP - 1) / kStemTP) * ((Hb + kStemTP - 1) / kStemTP);
-  return align_up((tiles + 1) * sizeof(int32_t), 256) * 2 + align_up((size_t)(4 * nnz + 4) * sizeof(int32_t), 256);
+  return align_up((tiles + 1) * sizeof(int32_t), 256) * 2 + align_up((size_t)(4 * nnz + 4) * sizeof(float4), 256);
 }
 
 // same contract as launch_stem_coo; bins = scratch of stem_bins_bytes(n, Hb, Wb, nnz of these images) bytes
@@ -619,14 +669,23 @@ int launch_stem_coo_binned(const int32_t* coords, const void* values, bool value
   char* b = static_cast<char*>(bins);
   int32_t* tile_count = reinterpret_cast<int32_t*>(b);
   int32_t* tile_start = reinterpret_cast<int32_t*>(b + align_up((size_t)(tiles + 1) * sizeof(int32_t), 256));
-  int32_t* tile_hits = reinterpret_cast<int32_t*>(b + 2 * align_up((size_t)(tiles + 1) * sizeof(int32_t), 256));
-  stem_bin_kernel<false><<<n, 128, 0, stream>>>(coords, image_offsets, image0, H, W, tiles_x, tiles_y, tile_count, nullptr, nullptr);
-  TCVN_LAUNCH_CHECK();
-  scan_counts_kernel<<<1, 1024, 0, stream>>>(tile_count, (int)tiles, tile_start);
-  TCVN_LAUNCH_CHECK();
-  stem_bin_kernel<true><<<n, 128, 0, stream>>>(coords, image_offsets, image0, H, W, tiles_x, tiles_y, tile_count, tile_start, tile_hits);
-  TCVN_LAUNCH_CHECK();
-  const size_t smem = (size_t)kStemTC * kStemTC * c0 * sizeof(float) + (size_t)kStemIn * kStemIn * sizeof(float4);
+  float4* tile_recs = reinterpret_cast<float4*>(b + 2 * align_up((size_t)(tiles + 1) * sizeof(int32_t), 256));
+#define TCVN_STEM_BINS(V)                                                                                                       \
+  do {                                                                                                                          \
+    const V* vals = static_cast<const V*>(values);                                                                              \
+    stem_bin_kernel<false, V><<<n, 128, 0, stream>>>(coords, vals, image_offsets, image0, cin, divisor, H, W, tiles_x, tiles_y, \
+                                                      tile_count, nullptr, nullptr);                                            \
+    TCVN_LAUNCH_CHECK();                                                                                                        \
+    scan_counts_kernel<<<1, 1024, 0, stream>>>(tile_count, (int)tiles, tile_start);                                            \
+    TCVN_LAUNCH_CHECK();                                                                                                        \
+    stem_bin_kernel<true, V><<<n, 128, 0, stream>>>(coords, vals, image_offsets, image0, cin, divisor, H, W, tiles_x, tiles_y,  \
+                                                     tile_count, tile_start, tile_recs);                                        \
+    TCVN_LAUNCH_CHECK();                                                                                                        \
+  } while (0)
+  if (values_u8) TCVN_STEM_BINS(uint8_t);
+  else TCVN_STEM_BINS(float);
+#undef TCVN_STEM_BINS
+  const size_t smem = (size_t)kStemTC * kStemTC * c0 * sizeof(float) + (size_t)2 * kHitBuf * sizeof(float4);
   int sms = 148;
   {
     int dev = 0;
@@ -634,19 +693,16 @@ int launch_stem_coo_binned(const int32_t* coords, const void* values, bool value
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const int grid = (int)(tiles < 2ll * sms ? tiles : 2ll * sms);
-#define TCVN_STEM_BIN(TO, V)                                                                                                   \
-  do {                                                                                                                         \
-    TCVN_CUDA(cudaFuncSetAttribute(stem_coo_binned_kernel<TO, 64, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    TCVN_CUDA(cudaFuncSetAttribute(stem_coo_binned_kernel<TO, 64, V>, cudaFuncAttributePreferredSharedMemoryCarveout,          \
-                                   (int)cudaSharedmemCarveoutMaxShared));                                                      \
-    stem_coo_binned_kernel<TO, 64, V><<<grid, kStemThreads, smem, stream>>>(                                                   \
-        coords, static_cast<const V*>(values), tile_count, tile_start, tile_hits, divisor, n, cin, H, W, w0, s_scale, s_shift,  \
-        s_alpha, static_cast<TO*>(blk), ldo, Hb, Wb);                                                                          \
+#define TCVN_STEM_BIN(TO)                                                                                                  \
+  do {                                                                                                                     \
+    TCVN_CUDA(cudaFuncSetAttribute(stem_coo_binned_kernel<TO, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    TCVN_CUDA(cudaFuncSetAttribute(stem_coo_binned_kernel<TO, 64>, cudaFuncAttributePreferredSharedMemoryCarveout,          \
+                                   (int)cudaSharedmemCarveoutMaxShared));                                                  \
+    stem_coo_binned_kernel<TO, 64><<<grid, kStemThreads, smem, stream>>>(tile_start, tile_recs, n, cin, w0, s_scale, s_shift, \
+                                                                         s_alpha, static_cast<TO*>(blk), ldo, Hb, Wb);      \
   } while (0)
-  if (f32 && !values_u8) TCVN_STEM_BIN(float, float);
-  else if (f32 && values_u8) TCVN_STEM_BIN(float, uint8_t);
-  else if (!f32 && !values_u8) TCVN_STEM_BIN(__nv_bfloat16, float);
-  else TCVN_STEM_BIN(__nv_bfloat16, uint8_t);
+  if (f32) TCVN_STEM_BIN(float);
+  else TCVN_STEM_BIN(__nv_bfloat16);
 #undef TCVN_STEM_BIN
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;

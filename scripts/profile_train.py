@@ -6,6 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench
 from dune_transformercvn_b200 import training
+from dune_transformercvn_b200 import loss as tloss
 from dune_transformercvn_b200.config import NUM_EVENT_CLASSES, NUM_PRONG_CLASSES, PathOptions
 from dune_transformercvn_b200.network import NeutrinoDenseNetwork
 
@@ -25,7 +26,7 @@ pr_t = pr_t.to(dev)
 def step():
     opt.zero_grad()
     ev, pr = net.forward_sparse(batch)
-    loss = bench.focal_loss_mix(ev, pr, ev_t, pr_t, opts)
+    loss, _ = tloss.training_loss(ev, pr, ev_t, pr_t, opts)
     loss.backward()
     opt.step()
 
