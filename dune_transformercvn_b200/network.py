@@ -327,6 +327,11 @@ class ProngDecoder(_HeadBase):
 class NeutrinoDenseNetwork(nn.Module):
     """Same constructor and forward as the reference class of this name."""
 
+    cnn_kind = "dense"   # "sdxl" in NeutrinoSDXLNetwork (sdxl.py)
+
+    def _make_engine(self) -> "_Engine":
+        return _Engine(self)
+
     def __init__(self, options, features_dim: int, extra_dim: int, pixel_dim: int, num_prong_classes: int,
                  num_event_classes: int, image_size=(PIXEL_H, PIXEL_W), precision: str = "fp32", seed: int = 0):
         super().__init__()
@@ -344,8 +349,8 @@ class NeutrinoDenseNetwork(nn.Module):
         self.image_size = (int(image_size[0]), int(image_size[1]))
         self.precision = precision
         self.specs: List[TensorSpec] = network_specs(options, features_dim, extra_dim, pixel_dim, num_prong_classes,
-                                                     num_event_classes)
-        engine = _Engine(self)
+                                                     num_event_classes, cnn=self.cnn_kind)
+        engine = self._make_engine()
         self._engine = (engine,)
         self.overlap_cnns = True     # eval forward_sparse: event CNN on a side stream (+1.7 % at 256 events)
         self._side = None

@@ -97,6 +97,59 @@ def densenet_specs(prefix: str, in_ch: int, out_features: int, init_features: in
     yield from _prelu(o + "relu", out_features)
 
 
+def sdxl_block_channels(init_block_dim: int, out_features: int, repeat: int = 2, num_blocks: int = 4) -> List[int]:
+    """``block_out_channels`` of the --sdxl encoder (layers/sdxl_net.py:20-26): [64, 64, 128, 128, 256, 256, 512, 512, out]."""
+    ch: List[int] = []
+    dim = init_block_dim
+    for _ in range(num_blocks):
+        ch.extend([dim] * repeat)
+        dim *= 2
+    ch.append(out_features)
+    return ch
+
+
+def _gn(prefix: str, c: int) -> Iterator[TensorSpec]:
+    yield TensorSpec(prefix + ".weight", (c,), "ln_w", True)
+    yield TensorSpec(prefix + ".bias", (c,), "ln_b", True)
+
+
+def _resnet(prefix: str, cin: int, cout: int) -> Iterator[TensorSpec]:
+    yield from _gn(prefix + "norm1", cin)
+    yield from _conv(prefix + "conv1", cout, cin, 3)
+    yield from _gn(prefix + "norm2", cout)
+    yield from _conv(prefix + "conv2", cout, cout, 3)
+    if cin != cout:
+        yield from _conv(prefix + "conv_shortcut", cout, cin, 1)
+
+
+def sdxl_specs(prefix: str, in_ch: int, out_features: int, init_block_dim: int) -> Iterator[TensorSpec]:
+    """Tensors of ``SDXLNet`` (layers/sdxl_net.py:7-42) in module-registration order.  The encoder is
+    ``diffusers.models.vae.Encoder(down_block_types=("DownEncoderBlock2D",)*9, layers_per_block=2, norm_num_groups=1,
+    double_z=False)``; diffusers is not vendored by the reference (and absent here), so these names restate its
+    published module tree (conv_in / down_blocks.i.resnets.j / downsamplers.0.conv / mid_block.attentions.0 +
+    resnets / conv_norm_out / conv_out) - parity unpinned, SURVEY 8c."""
+    e = prefix + "encoder."
+    ch = sdxl_block_channels(init_block_dim, out_features)
+    yield from _conv(e + "conv_in", ch[0], in_ch, 3)
+    cin = ch[0]
+    for i, cout in enumerate(ch):
+        for j in range(2):
+            yield from _resnet(f"{e}down_blocks.{i}.resnets.{j}.", cin if j == 0 else cout, cout)
+        if i != len(ch) - 1:
+            yield from _conv(f"{e}down_blocks.{i}.downsamplers.0.conv", cout, cout, 3)
+        cin = cout
+    c = ch[-1]
+    a = e + "mid_block.attentions.0."
+    yield from _gn(a + "group_norm", c)
+    for n in ("to_q", "to_k", "to_v", "to_out.0"):
+        yield from _linear(a + n, c, c, True)
+    for j in range(2):
+        yield from _resnet(f"{e}mid_block.resnets.{j}.", c, c)
+    yield from _gn(e + "conv_norm_out", c)
+    yield from _conv(e + "conv_out", out_features, c, 3)
+    yield from _linear(prefix + "output_layer.1", out_features, out_features, True)
+
+
 def densenet_final_channels(init_features: int, growth: int, blocks: Sequence[int]) -> int:
     c = init_features
     for bi, nl in enumerate(blocks):
@@ -150,8 +203,8 @@ def prong_decoder_widths(options) -> List[int]:
 
 
 def network_specs(options, features_dim: int, extra_dim: int, pixel_dim: int,
-                  num_prong_classes: int, num_event_classes: int) -> List[TensorSpec]:
-    """All tensors of ``NeutrinoDenseNetwork`` in state_dict order."""
+                  num_prong_classes: int, num_event_classes: int, cnn: str = "dense") -> List[TensorSpec]:
+    """All tensors of ``NeutrinoDenseNetwork`` (``cnn="sdxl"``: ``NeutrinoSDXLNetwork``) in state_dict order."""
     pix, feat, pos = embedding_dims(options)
     hidden = options.hidden_dim
     bn1d = bool(options.linear_batch_norm)
@@ -168,8 +221,11 @@ def network_specs(options, features_dim: int, extra_dim: int, pixel_dim: int,
         cin = w
     cnn_in = pixel_dim * 256 if options.one_hot_pixels else pixel_dim
     for name, width in (("prong_pixel_embedding.", pix), ("event_pixel_embedding.", pix + feat)):
-        out.extend(densenet_specs(pe + name, cnn_in, width, options.initial_pixel_dim,
-                                  options.densenet_growth_rate, options.densenet_batch_norm_size, blocks))
+        if cnn == "sdxl":
+            out.extend(sdxl_specs(pe + name, cnn_in, width, options.initial_pixel_dim))
+        else:
+            out.extend(densenet_specs(pe + name, cnn_in, width, options.initial_pixel_dim,
+                                      options.densenet_growth_rate, options.densenet_batch_norm_size, blocks))
     out.extend(_linear_block(pe + "combined_embedding", feat + pix + pos, hidden, bn1d, prelu))
     for li in range(options.num_encoder_layers):
         p = f"encoder.encoder.layers.{li}."

@@ -1,0 +1,237 @@
+"""--sdxl variant of the drop-in network (BASELINE configs[3]): ``NeutrinoSDXLNetwork``.
+
+Reference: transformercvn/network/networks/neutrino_full_sdxl_network.py:6-21 (the base network with both pixel
+embeddings replaced by ``SDXLNet``), transformercvn/network/layers/sdxl_net.py:7-42 (``diffusers.models.vae.Encoder``
+with 9 ``DownEncoderBlock2D`` of widths [64, 64, 128, 128, 256, 256, 512, 512, out], GroupNorm with ONE group, then
+Flatten + Linear).  diffusers is un-vendored, unpinned third-party code that is absent here: the arithmetic follows its
+published layout (see oracle/restate_sdxl.py) and **parity is unpinned** (SURVEY 8c).
+
+Round-1 state: eval-mode forward, fp32, through the C ABI only - every convolution / linear layer is the shifted GEMM
+of the fp32 parity path (``tcvn_t_gemm`` over ringed channels-last maps, the residual add is its accumulate mode),
+GroupNorm+SiLU, the stride-2 patch gather and the NCHW->ringed conversion are ``csrc/sdxl.cu``.  The token assembly,
+encoder and heads are the fused sequence kernel shared with the DenseNet network.  Not built: train mode, the bf16
+tcgen05 path, attention over more than one spatial position (400x280 inputs reach the mid block at 1x1).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Tuple
+
+import torch
+
+from . import lib as _lib
+from .network import NeutrinoDenseNetwork, _Engine
+from .params import embedding_dims, network_specs, sdxl_block_channels
+
+GN_EPS = 1e-6
+_IMAGE_CHUNK = 16   # images per walk: ~150 MB of fp32 feature maps per image at 400x280
+
+
+def _taps3(wp: int):
+    return (C.c_int32 * 9)(*[(dy - 1) * wp + (dx - 1) for dy in range(3) for dx in range(3)])
+
+
+class _SdxlCnn:
+    """One SDXLNet: packed (GEMM-layout) weights and the layer walk."""
+
+    def __init__(self, prefix: str, in_ch: int, out_features: int, init_block_dim: int):
+        self.prefix = prefix
+        self.in_ch = in_ch
+        self.out = out_features
+        self.ch = sdxl_block_channels(init_block_dim, out_features)
+        self.w: Dict[str, torch.Tensor] = {}
+
+    # ---- packing: conv (Cout, Cin, kh, kw) -> [kh*kw][Cin][Cout]; linear (Cout, Cin) -> [Cin][Cout] -------------------
+    def pack(self, tensors: Dict[str, torch.Tensor]) -> None:
+        self.w.clear()
+        for name, t in tensors.items():
+            if not name.startswith(self.prefix):
+                continue
+            key = name[len(self.prefix):]
+            t = t.detach().float()
+            if t.dim() == 4:
+                co, ci, kh, kw = t.shape
+                t = t.permute(2, 3, 1, 0).reshape(kh * kw, ci, co)
+            elif t.dim() == 2:
+                t = t.t()
+            self.w[key] = t.contiguous()
+
+    # ---- primitives -------------------------------------------------------------------------------------------------
+    def _gemm(self, L, st, a, lda, rows, k, taps, tap_off, w, n_out, bias, out, ldo, ring, accumulate=False, a_offset=0):
+        a_ptr = C.c_void_p(a.data_ptr() + 4 * a_offset)
+        _lib.check(L.tcvn_t_gemm(a_ptr, lda, rows, k, taps, tap_off, _lib.ptr(w), n_out, None, 0, 0, _lib.ptr(bias),
+                                 _lib.ptr(out), ldo, 0, ring[0], ring[1], 1 if accumulate else 0, st), "tcvn_t_gemm")
+
+    def _conv3(self, L, st, name, a, n, h, w_, cin, cout, out=None, accumulate=False):
+        hp, wp = h + 2, w_ + 2
+        rows = n * hp * wp
+        if out is None:
+            out = torch.empty((rows, cout), dtype=torch.float32, device=a.device)
+        self._gemm(L, st, a, cin, rows, cin, 9, _taps3(wp), self.w[name + ".weight"], cout, self.w[name + ".bias"], out, cout,
+                   (hp, wp), accumulate)
+        return out
+
+    def _norm(self, L, st, name, x, n, h, w_, c, silu, sums):
+        out = torch.empty_like(x)
+        _lib.check(L.tcvn_sdxl_groupnorm(_lib.ptr(x), n, c, 1, h, w_, _lib.ptr(self.w[name + ".weight"]),
+                                         _lib.ptr(self.w[name + ".bias"]), GN_EPS, 1 if silu else 0, _lib.ptr(out),
+                                         _lib.ptr(sums), st), "tcvn_sdxl_groupnorm")
+        return out
+
+    def _resnet(self, L, st, p, x, n, h, w_, cin, cout, sums):
+        a = self._norm(L, st, p + "norm1", x, n, h, w_, cin, True, sums)
+        t = self._conv3(L, st, p + "conv1", a, n, h, w_, cin, cout)
+        a = self._norm(L, st, p + "norm2", t, n, h, w_, cout, True, sums)
+        if cin != cout:   # 1x1 shortcut into a new map, then conv2 accumulates onto it
+            rows = n * (h + 2) * (w_ + 2)
+            y = torch.empty((rows, cout), dtype=torch.float32, device=x.device)
+            self._gemm(L, st, x, cin, rows, cin, 1, None, self.w[p + "conv_shortcut.weight"], cout,
+                       self.w[p + "conv_shortcut.bias"], y, cout, (h + 2, w_ + 2))
+            x = y
+        self._conv3(L, st, p + "conv2", a, n, h, w_, cout, cout, out=x, accumulate=True)   # x += conv2(...) + bias
+        return x
+
+    # ---- the walk ---------------------------------------------------------------------------------------------------
+    def forward(self, pixels: torch.Tensor) -> torch.Tensor:
+        outs = [self._forward_chunk(pixels[i:i + _IMAGE_CHUNK]) for i in range(0, pixels.shape[0], _IMAGE_CHUNK)]
+        if not outs:
+            return torch.empty((0, self.out), dtype=torch.float32, device=pixels.device)
+        return torch.cat(outs) if len(outs) > 1 else outs[0]
+
+    def _forward_chunk(self, pixels: torch.Tensor) -> torch.Tensor:
+        L = _lib.load()
+        dev = pixels.device
+        st = _lib.stream_ptr(dev)
+        n, cin0, h, w_ = pixels.shape
+        if cin0 != self.in_ch:
+            raise _lib.TcvnError(f"sdxl: pixels have {cin0} channels, expected {self.in_ch}")
+        f32 = dict(dtype=torch.float32, device=dev)
+        sums = torch.empty(2 * n, dtype=torch.float64, device=dev)
+        pixels = pixels.contiguous().float()
+        ring = torch.empty((n * (h + 2) * (w_ + 2), cin0), **f32)
+        _lib.check(L.tcvn_sdxl_pixels_to_ring(_lib.ptr(pixels), n, cin0, h, w_, _lib.ptr(ring), st), "tcvn_sdxl_pixels_to_ring")
+        e = "encoder."
+        x = self._conv3(L, st, e + "conv_in", ring, n, h, w_, cin0, self.ch[0])
+        cin = self.ch[0]
+        for i, cout in enumerate(self.ch):
+            for j in range(2):
+                x = self._resnet(L, st, f"{e}down_blocks.{i}.resnets.{j}.", x, n, h, w_, cin if j == 0 else cout, cout, sums)
+            if i != len(self.ch) - 1:
+                if h < 2 or w_ < 2:
+                    raise _lib.TcvnError(f"sdxl: a {h}x{w_} map cannot be down-sampled again (input too small)")
+                ho, wo = h // 2, w_ // 2
+                rows = n * (ho + 2) * (wo + 2)
+                patches = torch.empty((rows, 9 * cout), **f32)
+                _lib.check(L.tcvn_sdxl_patch_s2(_lib.ptr(x), n, cout, h, w_, _lib.ptr(patches), st), "tcvn_sdxl_patch_s2")
+                d = f"{e}down_blocks.{i}.downsamplers.0.conv"
+                x = torch.empty((rows, cout), **f32)
+                self._gemm(L, st, patches, 9 * cout, rows, 9 * cout, 1, None, self.w[d + ".weight"], cout, self.w[d + ".bias"],
+                           x, cout, (ho + 2, wo + 2))
+                del patches
+                h, w_ = ho, wo
+            cin = cout
+        c = self.ch[-1]
+        if (h, w_) != (1, 1):
+            raise _lib.TcvnError(f"sdxl: the mid block is reached at {h}x{w_}; only the 1x1 case (400x280 inputs) is built")
+        m = e + "mid_block."
+        x = self._resnet(L, st, m + "resnets.0.", x, n, h, w_, c, c, sums)
+        # Attention over ONE position: softmax over a single key is 1, so out = to_out(to_v(group_norm(x))) + x
+        a = self._norm(L, st, m + "attentions.0.group_norm", x, n, h, w_, c, False, sums)
+        rows = n * 9
+        v = torch.empty((rows, c), **f32)
+        att = m + "attentions.0."
+        self._gemm(L, st, a, c, rows, c, 1, None, self.w[att + "to_v.weight"], c, self.w[att + "to_v.bias"], v, c, (3, 3))
+        self._gemm(L, st, v, c, rows, c, 1, None, self.w[att + "to_out.0.weight"], c, self.w[att + "to_out.0.bias"], x, c, (3, 3),
+                   accumulate=True)
+        x = self._resnet(L, st, m + "resnets.1.", x, n, h, w_, c, c, sums)
+        a = self._norm(L, st, e + "conv_norm_out", x, n, h, w_, c, True, sums)
+        z = self._conv3(L, st, e + "conv_out", a, n, h, w_, c, self.out)
+        out = torch.empty((n, self.out), **f32)
+        # Flatten + Linear on the interior row (index 4 of the 3x3 ringed map) of every image
+        self._gemm(L, st, z, 9 * self.out, n, self.out, 1, None, self.w["output_layer.1.weight"], self.out,
+                   self.w["output_layer.1.bias"], out, self.out, (0, 0), a_offset=4 * self.out)
+        return out
+
+
+class _SdxlEngine(_Engine):
+    """The dense engine with the two pixel-map CNNs swapped; the sequence stage (tokens, encoder, heads) is shared."""
+
+    def __init__(self, owner):
+        super().__init__(owner)
+        o = owner.options
+        pix, feat, _ = embedding_dims(o)
+        pe = "prong_embedding."
+        cnn_in = owner.pixel_dim
+        self.cnns = {"prong": _SdxlCnn(pe + "prong_pixel_embedding.", cnn_in, pix, o.initial_pixel_dim),
+                     "event": _SdxlCnn(pe + "event_pixel_embedding.", cnn_in, pix + feat, o.initial_pixel_dim)}
+
+    def ensure_packed(self, prec: int) -> None:
+        net = self.owner[0]
+        if self.frozen and self.key is not None and self.key[1] == prec:
+            return
+        tensors = dict(net.named_parameters())
+        tensors.update(dict(net.named_buffers()))
+        key = self._state_key(tensors, prec)
+        if key == self.key:
+            return
+        L = _lib.load()
+        dev = next(iter(tensors.values())).device
+        if dev.type != "cuda":
+            raise _lib.TcvnError("NeutrinoSDXLNetwork: parameters are on the CPU; move the module to a CUDA device "
+                                 "(this path has no CPU implementation)")
+        for cnn in self.cnns.values():
+            cnn.pack(tensors)
+        st = _lib.stream_ptr(dev)
+        pe = "prong_embedding."
+        sd = self.seq_desc()
+        nbytes = L.tcvn_seq_packed_bytes(C.byref(sd))
+        if nbytes == 0:
+            raise _lib.TcvnError("sequence descriptor rejected: " + L.tcvn_last_error().decode())
+        buf = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        position = tensors[pe + "event_position_embedding"].detach().reshape(-1).float().contiguous()
+        arenas = [self._arena(tensors, p) for p in (pe + "combined_embedding.", "encoder.", "event_decoder.", "prong_decoder.")]
+        _lib.check(L.tcvn_seq_pack(C.byref(sd), _lib.ptr(position), *[_lib.ptr(a) for a in arenas], _lib.ptr(buf), nbytes, st),
+                   "tcvn_seq_pack")
+        self.packed["seq"] = buf
+        self.key = key
+
+    def cnn(self, tag: str, pixels: torch.Tensor, prec: int, ws_kind: str = "cnn") -> torch.Tensor:
+        _lib.require_cuda(pixels, f"{tag} pixels")
+        net = self.owner[0]
+        if tuple(pixels.shape[2:]) != tuple(net.image_size):
+            raise _lib.TcvnError(f"{tag} pixels have shape {tuple(pixels.shape)}, expected (N,{net.pixel_dim},{net.image_size[0]},{net.image_size[1]})")
+        return self.cnns[tag].forward(pixels)
+
+    def cnn_sparse(self, tag, values, coords, n, prec, divisor: float = 255.0, ws_kind: str = "cnn"):
+        from .ingest import densify
+        return self.cnn(tag, densify(values, coords, self.owner[0].image_size, n, divisor), prec)
+
+
+class NeutrinoSDXLNetwork(NeutrinoDenseNetwork):
+    """Same constructor and forward as the reference class of this name
+    (networks/neutrino_full_sdxl_network.py:19-21); eval mode, fp32."""
+
+    cnn_kind = "sdxl"
+
+    def _make_engine(self):
+        return _SdxlEngine(self)
+
+    def __init__(self, options, features_dim: int, extra_dim: int, pixel_dim: int, num_prong_classes: int,
+                 num_event_classes: int, image_size=None, precision: str = "fp32", seed: int = 0):
+        if precision != "fp32":
+            raise _lib.TcvnError("NeutrinoSDXLNetwork: only the fp32 path is built (round 1)")
+        kw = {} if image_size is None else {"image_size": image_size}
+        super().__init__(options, features_dim, extra_dim, pixel_dim, num_prong_classes, num_event_classes,
+                         precision=precision, seed=seed, **kw)
+
+    def forward(self, features, extra, event_pixels, event_mask, prong_pixels, prong_mask):
+        if self.training:
+            raise NotImplementedError("NeutrinoSDXLNetwork: the train-mode forward / backward of the --sdxl variant is not "
+                                      "built (round 1: eval-mode inference, BASELINE configs[3]); call .eval(). There is "
+                                      "deliberately no PyTorch fallback")
+        return super().forward(features, extra, event_pixels, event_mask, prong_pixels, prong_mask)
+
+    def forward_sparse(self, batch, materialize: bool = True):
+        """/255 + sparse_to_dense (densify kernel) + network, as the --sdxl trainer does
+        (trainers/neutrino_full_sdxl_trainer.py:8 inherits neutrino_full_dense_trainer.py:46-66)."""
+        return super().forward_sparse(batch, materialize=True)

@@ -328,6 +328,21 @@ int tcvn_metrics_update(const float* event_logits, const int64_t* event_targets,
                         int64_t prong_stride_event, int64_t prong_stride_slot, int64_t* counters4, float* event_prob,
                         float* prong_prob, tcvn_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------
+ * --sdxl pixel-map CNN (BASELINE configs[3]; transformercvn/network/layers/sdxl_net.py:7-42, whose arithmetic is
+ * diffusers.models.vae.Encoder - un-vendored, unpinned third-party code: parity unpinned).  fp32 path:
+ * the convolutions are tcvn_t_gemm over ringed channels-last maps; these are the kernels the DenseNet does not have. */
+/* NCHW fp32 pixels -> ringed channels-last [n][(H+2)(W+2)][C], ring rows zero */
+int tcvn_sdxl_pixels_to_ring(const float* pixels_nchw, int n, int C, int H, int W, float* out_ring, tcvn_stream_t stream);
+/* torch.nn.GroupNorm(groups, C, eps) per image over the interior pixels (+ SiLU when silu != 0) of a ringed map;
+ * ring rows of out are zero.  sums_workspace: 2 * n * groups doubles (overwritten).  Replaces nn.GroupNorm + nn.SiLU
+ * of diffusers' ResnetBlock2D / Attention / conv_norm_out. */
+int tcvn_sdxl_groupnorm(const float* x_ring, int n, int C, int groups, int H, int W, const float* gamma, const float* beta,
+                        float eps, int silu, float* out_ring, double* sums_workspace, tcvn_stream_t stream);
+/* patches of diffusers' Downsample2D (F.pad(x, (0,1,0,1)) -> conv3x3 stride 2): out ringed at (H/2, W/2) with 9*C
+ * channels ordered (dy, dx, c), so that the convolution is a GEMM with K = 9*C */
+int tcvn_sdxl_patch_s2(const float* x_ring, int n, int C, int H, int W, float* out_ring, tcvn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

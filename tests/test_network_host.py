@@ -75,3 +75,29 @@ def test_export_surface_traces_without_a_gpu_and_rejects_cpu_tensors(net):
     assert shapes == [(4,), (3, 8), (128,), (3, 128)]
     with pytest.raises(TcvnError):
         clf(px)
+
+
+def test_sdxl_network_host_surface(tutorial_options):
+    """--sdxl variant: the state_dict follows diffusers' published Encoder module tree (parity unpinned, see
+    oracle/restate_sdxl.py), strict load round-trips, CPU calls and train mode fail loudly."""
+    import torch
+    from dune_transformercvn_b200.lib import TcvnError
+    from dune_transformercvn_b200.sdxl import NeutrinoSDXLNetwork
+    net = NeutrinoSDXLNetwork(tutorial_options, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES)
+    sd = net.state_dict()
+    p = "prong_embedding.event_pixel_embedding."
+    assert tuple(sd[p + "encoder.conv_in.weight"].shape) == (64, 3, 3, 3)
+    assert tuple(sd[p + "encoder.down_blocks.2.resnets.0.conv_shortcut.weight"].shape) == (128, 64, 1, 1)
+    assert (p + "encoder.down_blocks.8.downsamplers.0.conv.weight") not in sd
+    assert tuple(sd[p + "encoder.down_blocks.8.resnets.0.conv1.weight"].shape) == (288, 512, 3, 3)
+    assert tuple(sd[p + "encoder.mid_block.attentions.0.to_out.0.weight"].shape) == (288, 288)
+    assert tuple(sd[p + "output_layer.1.bias"].shape) == (288,)
+    assert "encoder.encoder.layers.5.linear2.weight" in sd and "prong_decoder.output_layer.weight" in sd
+    net.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=True)
+    net.eval()
+    z = torch.zeros(1, 3, 400, 280)
+    with pytest.raises(TcvnError):
+        net(torch.zeros(1, 1, 1), torch.zeros(1, 1), z, torch.ones(1, 1, dtype=torch.bool), z, torch.ones(1, 1, dtype=torch.bool))
+    net.train()
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 1, 1), torch.zeros(1, 1), z, torch.ones(1, 1, dtype=torch.bool), z, torch.ones(1, 1, dtype=torch.bool))
