@@ -66,13 +66,34 @@ class _FocalLossFn(torch.autograd.Function):
         return d_ev.to(ctx.dtypes[0]), d_pr.to(ctx.dtypes[1]), None, None, None, None, None
 
 
+def focal_loss_mix(ev_logits, pr_logits, ev_targets, pr_targets, gamma: float, event_scale: float,
+                   prong_scale: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """``event_scale * loss(event) + prong_scale * loss(prong rows with target >= 0)`` and the stats vector."""
+    out = _FocalLossFn.apply(ev_logits, pr_logits, ev_targets, pr_targets, float(gamma), float(event_scale), float(prong_scale))
+    return out[0], out.detach()
+
+
+def fused_training_step(self, batch, batch_idx):
+    """Drop-in body for ``NeutrinoFullBaseTrainer.training_step`` (neutrino_full_base_trainer.py:162-192), bound by
+    ``install(fused_loss=True)``: same logged names, same returned total loss, one kernel instead of the
+    masked_select / log_softmax / softmax / argmax chain (and no host sync)."""
+    event_targets, prong_targets, event_logits, prong_logits = self.shared_step(batch)
+    total, stats = focal_loss_mix(event_logits, prong_logits, event_targets, prong_targets, self.gamma,
+                                  self.event_loss_scale, self.prong_loss_scale)
+    self.log("prong_loss", stats[2])
+    self.log("event_loss", stats[1])
+    self.log("train_loss", stats[0])
+    self.log("train_event_accuracy", stats[3])
+    self.log("train_prong_accuracy", stats[4])
+    return total
+
+
 def training_loss(ev_logits, pr_logits, ev_targets, pr_targets, options) -> Tuple[torch.Tensor, torch.Tensor]:
     """``(total_loss, stats)``: total = a * event_loss + (1 - a) * prong_loss with a = ``event_prong_loss_proportion``
     (neutrino_full_base_trainer.py:67-68,177), differentiable w.r.t. both logits; ``stats`` is the detached device
     vector named by :data:`LOSS_FIELDS` (what ``training_step`` logs), read it without forcing a sync per step."""
     a = float(options.event_prong_loss_proportion)
-    out = _FocalLossFn.apply(ev_logits, pr_logits, ev_targets, pr_targets, float(options.loss_gamma), a, 1.0 - a)
-    return out[0], out.detach()
+    return focal_loss_mix(ev_logits, pr_logits, ev_targets, pr_targets, options.loss_gamma, a, 1.0 - a)
 
 
 def _auroc_macro(prob: torch.Tensor, target: torch.Tensor) -> torch.Tensor:

@@ -107,3 +107,23 @@ def test_device_metrics_match_torch_and_sklearn(dev):
     assert abs(got["prong_epoch_AUC"] - want_p) < 1e-5
     m.reset()
     assert int(m.counters.sum()) == 0 and not m.ev
+
+
+def test_fused_training_step_logs_what_the_reference_logs(dev):
+    """loss.fused_training_step bound on a stand-in trainer (Lightning is not installed): same logged names and values
+    as training_step (neutrino_full_base_trainer.py:162-192), returned loss differentiable."""
+    import types
+    ev, pr_lb, ev_t, pr_t = _case(8, 5, 4, 8, seed=9)
+    d_ev = ev.to(dev).requires_grad_(True)
+    logged = {}
+    me = types.SimpleNamespace(gamma=1.0, event_loss_scale=0.9, prong_loss_scale=0.1,
+                               shared_step=lambda batch: (ev_t.to(dev), pr_t.to(dev), d_ev, pr_lb.to(dev).transpose(0, 1)),
+                               log=lambda k, v: logged.__setitem__(k, float(v)))
+    total = tloss.fused_training_step(me, None, 0)
+    total.backward()
+    opts = PathOptions.tutorial()
+    want = restate.training_loss(ev.double(), pr_lb.double().transpose(0, 1), ev_t, pr_t, opts)
+    assert set(logged) == {"prong_loss", "event_loss", "train_loss", "train_event_accuracy", "train_prong_accuracy"}
+    assert abs(logged["train_loss"] - float(want)) < 2e-6 * abs(float(want))
+    assert abs(0.9 * logged["event_loss"] + 0.1 * logged["prong_loss"] - logged["train_loss"]) < 1e-6
+    assert d_ev.grad is not None and float(d_ev.grad.abs().sum()) > 0
