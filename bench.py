@@ -367,7 +367,7 @@ def kernel_rooflines(net, resident, batch, dev, pk, args):
                          "traffic": 755.3e6 * n / 194, "kernel": "umma_gemm_kernel<true> (BN+PReLU -> 1x1 conv -> BN+PReLU), "
                          f"dense1 layer 3, {n} images", "us_per_launch": us, "algorithmic_bytes": nbytes,
                          "peak_source": pk["source"] + " copy bandwidth",
-                         "traffic_source": "ncu dram__bytes_read+write, profiles/r1_conv1_gemm_194img.txt, scaled by images"}
+                         "traffic_source": "ncu dram__bytes_read+write, profiles/r1_conv1_194img.txt, scaled by images"}
         else:
             flops = pixels * 2 * 9 * 128 * 32
             tf = flops / (us * 1e-6) / 1e12
