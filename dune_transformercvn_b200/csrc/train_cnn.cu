@@ -14,6 +14,11 @@
 //     [0, k_i) after reading its own output gradient from channels [k_i, k_i+32).
 // Parameter gradients are ACCUMULATED into `grad_arena`, which has the arena's layout (reference state_dict
 // order); slots of the running buffers are left untouched.
+#include <map>
+#include <mutex>
+#include <stdlib.h>
+#include <utility>
+
 #include "kernels.h"
 #include "plan.h"
 #include "umma.h"
@@ -648,6 +653,29 @@ __global__ void fill_f32_kernel(float* dst, int n, float v) {
   if (i < n) dst[i] = v;
 }
 
+// Side stream of the bf16 backward walk: the weight-gradient branch of a bottleneck (wgrad GEMM -> partial-sum reduction ->
+// unpack into the gradient arena, twice per layer) depends only on tensors the input-gradient chain has already produced,
+// so it runs beside that chain instead of in front of it.  One (stream, 3 events) set per caller stream, created on first
+// use and kept for the life of the process; TCVN_WGRAD_STREAM=0 keeps everything on the caller's stream.
+struct AuxStream { cudaStream_t s = nullptr; cudaEvent_t e[3] = {nullptr, nullptr, nullptr}; };
+static AuxStream* aux_for(cudaStream_t main) {
+  static std::map<std::pair<int, cudaStream_t>, AuxStream> pool;
+  static std::mutex mu;
+  static const bool enabled = [] { const char* v = getenv("TCVN_WGRAD_STREAM"); return !(v && v[0] == '0'); }();
+  if (!enabled) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> g(mu);
+  auto key = std::make_pair(dev, main);
+  auto it = pool.find(key);
+  if (it != pool.end()) return &it->second;
+  AuxStream a;
+  if (cudaStreamCreateWithFlags(&a.s, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+  for (int i = 0; i < 3; ++i)
+    if (cudaEventCreateWithFlags(&a.e[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  return &(pool[key] = a);
+}
+
 struct TWalk16 {
   const TrainPlan16& T;
   float* arena;
@@ -797,8 +825,12 @@ struct TWalk16 {
   }
 
   int unpack(const float* dwp, int taps, int K_phys, int N_phys, int n_log, int k_log, int c0, int c0p, float* dst) {
+    return unpack_on(st, dwp, taps, K_phys, N_phys, n_log, k_log, c0, c0p, dst);
+  }
+  int unpack_on(cudaStream_t s, const float* dwp, int taps, int K_phys, int N_phys, int n_log, int k_log, int c0, int c0p,
+                float* dst) {
     const long long total = (long long)n_log * k_log * taps;
-    unpack_grad_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, st>>>(dwp, taps, K_phys, N_phys, n_log, k_log, c0, c0p, dst);
+    unpack_grad_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, s>>>(dwp, taps, K_phys, N_phys, n_log, k_log, c0, c0p, dst);
     TCVN_LAUNCH_CHECK();
     return TCVN_OK;
   }
@@ -834,10 +866,17 @@ struct TWalk16 {
       float* bstat = f(X.bstat);
       blk_stats_kernel<<<ceil_div(B.ctot, 128), 128, 0, st>>>(dbl(X.sums), dbl(X.sums) + B.ctot, count, d.bn_eps, B.ctot, bstat);
       TCVN_LAUNCH_CHECK();
+      AuxStream* ax = aux_for(st);
+      const cudaStream_t wst = ax ? ax->s : st;   // stream of the weight-gradient branch
+      bool side_pending = false;
       for (int i = (int)B.layers.size() - 1; i >= 0; --i) {
         const LayerPlan& L = B.layers[i];
         const T16Layer& Y = X.layers[i];
         float* f1 = f(Y.fold1);
+        if (side_pending) {   // the previous layer's weight gradients still read g2x / dmid, which this layer overwrites
+          TCVN_CUDA(cudaStreamWaitEvent(st, ax->e[2], 0));
+          side_pending = false;
+        }
         // gradient of the layer's 32 output channels (complete by now) -> bf16, dropout mask applied, 3 horizontal shifts
         g2x_kernel<<<(unsigned)ceil_div_ll(rows * 4, 256), 256, 0, st>>>(gblk, B.ctot, L.kphys, rows, B.Hp, B.Wp, seed,
                                                                         site * 4096 + b * 64 + i, p_drop, blk, bstat, B.ctot, g2x);
@@ -849,9 +888,13 @@ struct TWalk16 {
         // conv2 weight gradient: three vertical taps of the activated bottleneck map against G2x
         {
           const int cols[3] = {0, 0, 0}, shifts[3] = {-B.Wp, 0, B.Wp}, valid[3] = {128, 128, 128};
+          if (ax) {
+            TCVN_CUDA(cudaEventRecord(ax->e[0], st));        // g2x is complete
+            TCVN_CUDA(cudaStreamWaitEvent(wst, ax->e[0], 0));
+          }
           TCVN_TRY(umma_wgrad(h(Y.mid_act), rows, mid, mid, 3, cols, shifts, valid, nullptr, nullptr, nullptr, 0, g2x, 128, 128, 0,
-                              f(T.parts), dwp, false, st));
-          unpack_conv2_grad_kernel<<<ceil_div(32 * 128 * 9, 256), 256, 0, st>>>(dwp, garena + L.conv2_w);
+                              f(T.parts), dwp, false, wst));
+          unpack_conv2_grad_kernel<<<ceil_div(32 * 128 * 9, 256), 256, 0, wst>>>(dwp, garena + L.conv2_w);
           TCVN_LAUNCH_CHECK();
         }
         TCVN_TRY(umma_conv2_dgrad(g2x, h(Y.wd), rows, B.Hp, B.Wp, dmid, st));
@@ -862,9 +905,17 @@ struct TWalk16 {
           const int n_items = ceil_div(L.kphys, 128);
           int cols[4], shifts[4], valid[4];
           for (int j = 0; j < n_items; ++j) { cols[j] = 128 * j; shifts[j] = 0; valid[j] = L.kphys - 128 * j < 128 ? L.kphys - 128 * j : 128; }
+          if (ax) {
+            TCVN_CUDA(cudaEventRecord(ax->e[1], st));        // dmid holds the BN2 input gradient
+            TCVN_CUDA(cudaStreamWaitEvent(wst, ax->e[1], 0));
+          }
           TCVN_TRY(umma_wgrad(blk, rows, B.ctot, B.ctot, n_items, cols, shifts, valid, f1, f1 + L.kpad, f1 + 2 * L.kpad, L.kphys,
-                              dmid, mid, mid, 0, f(T.parts), dwp, false, st));
-          TCVN_TRY(unpack(dwp, 1, n_items * 128, 128, mid, L.cin, B.c0, B.c0p, garena + L.conv1_w));
+                              dmid, mid, mid, 0, f(T.parts), dwp, false, wst));
+          TCVN_TRY(unpack_on(wst, dwp, 1, n_items * 128, 128, mid, L.cin, B.c0, B.c0p, garena + L.conv1_w));
+          if (ax) {
+            TCVN_CUDA(cudaEventRecord(ax->e[2], wst));
+            side_pending = true;
+          }
         }
         TCVN_TRY(launch_gemm(false, dmid, rows, mid, mid, h(Y.w1d), L.kphys, 128, 128, nullptr, nullptr, nullptr, f(T.zeros),
                              f(T.ones), h(T.sA), L.kphys, L.kphys, ceil_div(L.kphys, 128), B.Hp, B.Wp, st));
@@ -881,6 +932,7 @@ struct TWalk16 {
           TCVN_LAUNCH_CHECK();
         }
       }
+      if (side_pending) TCVN_CUDA(cudaStreamWaitEvent(st, ax->e[2], 0));   // join: parts / dwp / the arena slots are final
       // the block-input channels leave the block: make their gradient final
       TCVN_TRY(bn1_correct(gblk, B.ctot, blk, B.ctot, B.c0p, rows, B.Hp, B.Wp, bstat, bstat + B.ctot, bstat + 2 * B.ctot,
                            bstat + 3 * B.ctot, st));
