@@ -96,7 +96,7 @@ int sm_count() {
 //   warps 10-17 two epilogue groups, one per TMEM accumulator: TMEM -> regs -> +shift, PReLU, ring rows -> 0,
 //               bf16 -> swizzled staging tile -> TMA store
 // ------------------------------------------------------------------------------------------------
-constexpr int kC1Stages = 5;
+constexpr int kC1Stages = 4;
 constexpr int kC1Threads = 576;
 constexpr int kTileM = 128;
 constexpr int kMid = 128;              // N tile = bottleneck width the kernels are specialised for
@@ -124,7 +124,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
 }
 __device__ __forceinline__ float prelu_fast(float v, float a) { return fmaf(a, fminf(v, 0.f), fmaxf(v, 0.f)); }
 
-template <bool TRANSFORM>
+// MMASHIFT (single N tile): the epilogue's "+ shift[n]" is done by the tensor core.  One extra K16 MMA per tile multiplies a
+// constant A tile (k0 = k1 = 1) with a B tile holding shift[n] split into two bf16 (k0 = hi, k1 = shift - hi: 16 mantissa
+// bits, products with 1.0 are exact), issued FIRST so that it also initialises the accumulator.  ncu showed the kernel
+// bound by the shared-memory data pipe (79 % LSU wavefronts), a third of them the epilogue's broadcast loads of the
+// per-column constants: this removes the 256 shift wavefronts per tile, and the slopes are read 8 columns per load.
+template <bool TRANSFORM, bool MMASHIFT>
 __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmW,
                                                                   const __grid_constant__ CUtensorMap tmO,
@@ -134,7 +139,9 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
   uint8_t* sA = smem;                                   // [stages][16 KB]
   uint8_t* sW = smem + kC1Stages * kStageA;             // [stages][16 KB]
   uint8_t* sOut = sW + kC1Stages * kStageW;             // [2 groups][2 halves][128 rows x 128 B], swizzled
-  float* s_epi = reinterpret_cast<float*>(sOut + 4 * kStageA);  // [2 groups][128 shift + 64 packed slopes]
+  uint8_t* sXA = sOut + 4 * kStageA;                    // [128 rows x 128 B]: k0 = k1 = 1.0, rest 0   (MMASHIFT)
+  uint8_t* sXB = sXA + kStageA;                         // [128 n x 128 B]: k0 = hi(shift[n]), k1 = lo(shift[n])
+  float* s_epi = reinterpret_cast<float*>(sXB + kStageW);  // [2 groups][128 shift + 64 packed slopes]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + 2 * 192);
   uint64_t* full = bars;                    // TMA -> transform (or MMA)
   uint64_t* ready = bars + kC1Stages;       // transform -> MMA
@@ -157,6 +164,21 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
     ptx::prefetch_tmap(&tmO);
   }
   if (warp == 0) ptx::tmem_alloc(tmem_slot, 256);
+  if (MMASHIFT) {
+    uint4* z = reinterpret_cast<uint4*>(sXA);
+    for (int i = threadIdx.x; i < (kStageA + kStageW) / 16; i += kC1Threads) z[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    if (threadIdx.x < kTileM) {   // row r: elements k0, k1 live in 16-byte chunk 0, stored at chunk position (r & 7)
+      const int r = threadIdx.x;
+      const float sv = __ldg(p.o_shift + r);
+      const bf16 hi = __float2bfloat16_rn(sv);
+      const bf16 lo = __float2bfloat16_rn(sv - __bfloat162float(hi));
+      *reinterpret_cast<uint32_t*>(sXA + r * 128 + ((r & 7) << 4)) = 0x3F803F80u;
+      *reinterpret_cast<uint32_t*>(sXB + r * 128 + ((r & 7) << 4)) =
+          (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+    }
+    ptx::fence_proxy_async_smem();
+  }
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
@@ -185,6 +207,9 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
         ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kMid;
+        if (MMASHIFT)   // accumulator := 1 * shift[n]
+          ptx::umma_bf16(d_tmem, ptx::umma_desc_join(ptx::kUmmaDescHiSw128, ptx::umma_desc_lo(ptx::smem_u32(sXA))),
+                         ptx::umma_desc_join(ptx::kUmmaDescHiSw128, ptx::umma_desc_lo(ptx::smem_u32(sXB))), idesc, 0);
         for (int kc = 0; kc < p.kchunks; ++kc) {
           ptx::mbar_wait(TRANSFORM ? &ready[stage] : &full[stage], phase);
           ptx::tc_fence_after();
@@ -193,7 +218,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             ptx::umma_bf16(d_tmem, ptx::umma_desc_join(ptx::kUmmaDescHiSw128, a_lo + 2 * k),
-                           ptx::umma_desc_join(ptx::kUmmaDescHiSw128, w_lo + 2 * k), idesc, (kc | k) != 0);
+                           ptx::umma_desc_join(ptx::kUmmaDescHiSw128, w_lo + 2 * k), idesc, MMASHIFT || (kc | k) != 0);
           ptx::umma_commit(&empty[stage]);
           if (++stage == kC1Stages) { stage = 0; phase ^= 1; }
         }
@@ -284,7 +309,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
       // this tile's epilogue constants -> shared memory (shift fp32, PReLU slopes as packed bf16 pairs)
       {
         const int e = threadIdx.x - (10 + 4 * grp) * 32;  // 0..127
-        s_shift[e] = __ldg(p.o_shift + nt * kMid + e);
+        if (!MMASHIFT) s_shift[e] = __ldg(p.o_shift + nt * kMid + e);
         if (e < kMid / 2) {
           const float2 a = __ldg(reinterpret_cast<const float2*>(p.o_alpha + nt * kMid) + e);
           const __nv_bfloat162 a2 = __floats2bfloat162_rn(a.x, a.y);
@@ -310,16 +335,18 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint32_t o[4];
+            const uint4 a4 = *reinterpret_cast<const uint4*>(s_alpha2 + (((c + hh) * 32 + q * 8) >> 1));   // slopes of 8 columns
+            const uint32_t a2w[4] = {a4.x, a4.y, a4.z, a4.w};
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const int n = (c + hh) * 32 + q * 8 + h * 4;
-              const float4 sh = *reinterpret_cast<const float4*>(s_shift + n);
-              const uint2 a2 = *reinterpret_cast<const uint2*>(s_alpha2 + (n >> 1));
+              float4 sh = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (!MMASHIFT) sh = *reinterpret_cast<const float4*>(s_shift + n);
               const int j = q * 8 + h * 4;
               const __nv_bfloat162 y0 = __floats2bfloat162_rn(__uint_as_float(r[j + 0]) + sh.x, __uint_as_float(r[j + 1]) + sh.y);
               const __nv_bfloat162 y1 = __floats2bfloat162_rn(__uint_as_float(r[j + 2]) + sh.z, __uint_as_float(r[j + 3]) + sh.w);
-              const __nv_bfloat162 p0 = __hfma2(*reinterpret_cast<const __nv_bfloat162*>(&a2.x), __hmin2(y0, zero2), __hmax2(y0, zero2));
-              const __nv_bfloat162 p1 = __hfma2(*reinterpret_cast<const __nv_bfloat162*>(&a2.y), __hmin2(y1, zero2), __hmax2(y1, zero2));
+              const __nv_bfloat162 p0 = __hfma2(*reinterpret_cast<const __nv_bfloat162*>(&a2w[2 * h]), __hmin2(y0, zero2), __hmax2(y0, zero2));
+              const __nv_bfloat162 p1 = __hfma2(*reinterpret_cast<const __nv_bfloat162*>(&a2w[2 * h + 1]), __hmin2(y1, zero2), __hmax2(y1, zero2));
               o[2 * h] = *reinterpret_cast<const uint32_t*>(&p0);
               o[2 * h + 1] = *reinterpret_cast<const uint32_t*>(&p1);
             }
@@ -624,11 +651,14 @@ int launch_gemm(bool transform, const void* A, long long rows, int a_cols, int a
                        int Hp, int Wp, cudaStream_t st, double* stats, int stats_stride) {
   if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one chunk");
   if (stats != nullptr && n_tiles_n != 1) return fail(TCVN_ERR_UNSUPPORTED, "epilogue statistics need a single N tile");
-  const size_t smem = 1024 + kC1Stages * (kStageA + kStageW) + 4 * kStageA + 2 * 192 * 4 + (3 * kC1Stages + 4) * 8 + 16;
+  const size_t smem = 1024 + kC1Stages * (kStageA + kStageW) + 4 * kStageA + kStageA + kStageW + 2 * 192 * 4 +
+                      (3 * kC1Stages + 4) * 8 + 16;
   static bool attr_done = false;
   if (!attr_done) {
-    TCVN_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    TCVN_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TCVN_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TCVN_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TCVN_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TCVN_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   CUtensorMap tmA, tmW, tmO;
@@ -642,8 +672,12 @@ int launch_gemm(bool transform, const void* A, long long rows, int a_cols, int a
   g.stats = stats; g.stats_stride = stats_stride;
   g.num_tiles = (int)ceil_div_ll(rows, kTileM) * n_tiles_n;
   const int grid = g.num_tiles < sm_count() ? g.num_tiles : sm_count();
-  if (transform) umma_gemm_kernel<true><<<grid, kC1Threads, smem, st>>>(tmA, tmW, tmO, g);
-  else umma_gemm_kernel<false><<<grid, kC1Threads, smem, st>>>(tmA, tmW, tmO, g);
+  static const bool mma_shift_on = [] { const char* v = getenv("TCVN_MMA_SHIFT"); return !(v && v[0] == '0'); }();
+  const bool ms = mma_shift_on && n_tiles_n == 1;
+  if (transform && ms) umma_gemm_kernel<true, true><<<grid, kC1Threads, smem, st>>>(tmA, tmW, tmO, g);
+  else if (transform) umma_gemm_kernel<true, false><<<grid, kC1Threads, smem, st>>>(tmA, tmW, tmO, g);
+  else if (ms) umma_gemm_kernel<false, true><<<grid, kC1Threads, smem, st>>>(tmA, tmW, tmO, g);
+  else umma_gemm_kernel<false, false><<<grid, kC1Threads, smem, st>>>(tmA, tmW, tmO, g);
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
 }
