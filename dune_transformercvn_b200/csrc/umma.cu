@@ -228,58 +228,77 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
     }
   } else if (warp < 10) {
     if (TRANSFORM) {
-      // thread owns 16-byte chunk `pc` of rows rb, rb+32, ... ; with the 128B swizzle the chunk at physical
-      // position pc of row r holds channels 8*(pc ^ (r & 7)); (rb + 32 i) & 7 == rb & 7, so a thread always
-      // sees the same 8 channels of a K chunk and keeps their BN/PReLU constants in registers.
+      // warp w owns channel group cg = w (8 channels of the K chunk) for all 128 rows, lane l the rows l, l+32, l+64,
+      // l+96.  With the 128B swizzle those channels sit at 16-byte position cg ^ (row & 7) of the row, and
+      // (l + 32 i) & 7 == l & 7: a thread always touches the same position, its constants stay in registers, a warp's
+      // 32 x 16 B access covers every bank four times (4 wavefronts per 512 B: the minimum), and - unlike a mapping
+      // with all 8 groups in one warp - the constant loads are warp-wide broadcasts.
       const int t = threadIdx.x - 64;
-      const int pc = t & 7, rb = t >> 3;
-      const int cg = pc ^ (rb & 7);
+      const int cg = t >> 5;
+      const int rb = lane, pc = cg ^ (lane & 7);
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          const int ch = kc * 64 + cg * 8;
-          const bool live = ch < p.kphys;  // kphys is a multiple of 8: a group is all-live or all-dead
-          float sc[8], sh[8], al[8];
-          {
-            const float4* s4 = reinterpret_cast<const float4*>(p.a_scale + ch);
-            const float4* h4 = reinterpret_cast<const float4*>(p.a_shift + ch);
-            const float4* a4 = reinterpret_cast<const float4*>(p.a_alpha + ch);
-            const float4 x0 = __ldg(s4), x1 = __ldg(s4 + 1), y0 = __ldg(h4), y1 = __ldg(h4 + 1), z0 = __ldg(a4), z1 = __ldg(a4 + 1);
-            sc[0] = x0.x; sc[1] = x0.y; sc[2] = x0.z; sc[3] = x0.w; sc[4] = x1.x; sc[5] = x1.y; sc[6] = x1.z; sc[7] = x1.w;
-            sh[0] = y0.x; sh[1] = y0.y; sh[2] = y0.z; sh[3] = y0.w; sh[4] = y1.x; sh[5] = y1.y; sh[6] = y1.z; sh[7] = y1.w;
-            al[0] = z0.x; al[1] = z0.y; al[2] = z0.z; al[3] = z0.w; al[4] = z1.x; al[5] = z1.y; al[6] = z1.z; al[7] = z1.w;
-          }
-          // BN in fp32, PReLU on packed bf16 pairs (max/min are exact; one rounding of slope * negative part)
-          __nv_bfloat162 al2[4];
+      const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
+      // the 8 channels' constants: BN in fp32, PReLU on packed bf16 pairs (max/min are exact; one rounding of slope *
+      // negative part)
+      struct Consts { float sc[8], sh[8]; __nv_bfloat162 al2[4]; bool live; };
+      auto load_consts = [&](int kc, Consts& c) {
+        const int ch = kc * 64 + cg * 8;
+        c.live = ch < p.kphys;  // kphys is a multiple of 8: a group is all-live or all-dead
+        const float4* s4 = reinterpret_cast<const float4*>(p.a_scale + ch);
+        const float4* h4 = reinterpret_cast<const float4*>(p.a_shift + ch);
+        const float4* a4 = reinterpret_cast<const float4*>(p.a_alpha + ch);
+        const float4 x0 = __ldg(s4), x1 = __ldg(s4 + 1), y0 = __ldg(h4), y1 = __ldg(h4 + 1), z0 = __ldg(a4), z1 = __ldg(a4 + 1);
+        c.sc[0] = x0.x; c.sc[1] = x0.y; c.sc[2] = x0.z; c.sc[3] = x0.w; c.sc[4] = x1.x; c.sc[5] = x1.y; c.sc[6] = x1.z; c.sc[7] = x1.w;
+        c.sh[0] = y0.x; c.sh[1] = y0.y; c.sh[2] = y0.z; c.sh[3] = y0.w; c.sh[4] = y1.x; c.sh[5] = y1.y; c.sh[6] = y1.z; c.sh[7] = y1.w;
+        c.al2[0] = __floats2bfloat162_rn(z0.x, z0.y); c.al2[1] = __floats2bfloat162_rn(z0.z, z0.w);
+        c.al2[2] = __floats2bfloat162_rn(z1.x, z1.y); c.al2[3] = __floats2bfloat162_rn(z1.z, z1.w);
+      };
+      auto do_chunk = [&](const Consts& c) {
+        if (lane == 0) ptx::mbar_wait(&full[stage], phase);  // one poller per warp keeps the LSU free
+        __syncwarp();
+        uint8_t* base = sA + stage * kStageA + rb * 128 + pc * 16;
+        if (c.live) {
+          uint4 v[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) al2[q] = __floats2bfloat162_rn(al[2 * q], al[2 * q + 1]);
-          const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
-          if (lane == 0) ptx::mbar_wait(&full[stage], phase);  // one poller per warp keeps the LSU free
-          __syncwarp();
-          uint8_t* base = sA + stage * kStageA + rb * 128 + pc * 16;
-          if (live) {
-            uint4 v[4];
+          for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const uint4*>(base + i * 32 * 128);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const uint4*>(base + i * 32 * 128);
+          for (int i = 0; i < 4; ++i) {
+            uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const __nv_bfloat162 y = __floats2bfloat162_rn(fmaf(bf_lo(w[q]), sc[2 * q], sh[2 * q]),
-                                                               fmaf(bf_hi(w[q]), sc[2 * q + 1], sh[2 * q + 1]));
-                const __nv_bfloat162 r = __hfma2(al2[q], __hmin2(y, zero2), __hmax2(y, zero2));
-                w[q] = *reinterpret_cast<const uint32_t*>(&r);
-              }
-              *reinterpret_cast<uint4*>(base + i * 32 * 128) = make_uint4(w[0], w[1], w[2], w[3]);
+            for (int q = 0; q < 4; ++q) {
+              const __nv_bfloat162 y = __floats2bfloat162_rn(fmaf(bf_lo(w[q]), c.sc[2 * q], c.sh[2 * q]),
+                                                             fmaf(bf_hi(w[q]), c.sc[2 * q + 1], c.sh[2 * q + 1]));
+              const __nv_bfloat162 r = __hfma2(c.al2[q], __hmin2(y, zero2), __hmax2(y, zero2));
+              w[q] = *reinterpret_cast<const uint32_t*>(&r);
             }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(base + i * 32 * 128) = make_uint4(0u, 0u, 0u, 0u);
+            *reinterpret_cast<uint4*>(base + i * 32 * 128) = make_uint4(w[0], w[1], w[2], w[3]);
           }
-          ptx::fence_proxy_async_smem();
-          ptx::mbar_arrive(&ready[stage]);
-          if (++stage == kC1Stages) { stage = 0; phase ^= 1; }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(base + i * 32 * 128) = make_uint4(0u, 0u, 0u, 0u);
+        }
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(&ready[stage]);
+        if (++stage == kC1Stages) { stage = 0; phase ^= 1; }
+      };
+      if (p.kchunks <= 2) {
+        // K <= 128 (dense block 1, the most expensive layers): the constants of both K chunks stay in registers for
+        // every tile of this CTA.  ncu: the per-chunk reloads were 40 % of the kernel's LSU wavefronts (35 k of 87 k per
+        // SM), more than the operand transform itself.
+        Consts c0, c1;
+        load_consts(0, c0);
+        load_consts(p.kchunks - 1, c1);
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+          do_chunk(c0);
+          if (p.kchunks == 2) do_chunk(c1);
+        }
+      } else {
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            Consts c;
+            load_consts(kc, c);
+            do_chunk(c);
+          }
         }
       }
     }
