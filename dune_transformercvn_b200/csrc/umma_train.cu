@@ -125,10 +125,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_kernel(const __grid_
     }
   } else if (warp < 10) {
     if (TRANSFORM) {
-      // thread owns 16-byte chunk `pc` of rows rb and rb + 32 of every box: channels 8 * (pc ^ (rb & 7)) of the box
+      // warp w owns channel group cg = w of every box, lane l its rows l and l + 32 (16-byte position cg ^ (l & 7) under
+      // the 128B swizzle): conflict-free, and the constant loads below are warp-wide broadcasts (with all 8 groups in one
+      // warp they cost more LSU wavefronts than the operand transform itself, cf. umma_gemm_kernel)
       const int t = threadIdx.x - 64;
-      const int pc = t & 7, rb = t >> 3;
-      const int cg = pc ^ (rb & 7);
+      const int cg = t >> 5;
+      const int rb = lane, pc = cg ^ (lane & 7);
       const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
