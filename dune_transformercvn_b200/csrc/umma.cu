@@ -426,7 +426,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
 // every warp boundary are exchanged through shared memory.
 // ------------------------------------------------------------------------------------------------
 constexpr int kC2Stages = 2;
-constexpr int kC2Threads = 192;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kC2Threads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 two epilogue groups (one per TMEM accumulator)
 constexpr int kGrowth = 32;
 constexpr int kBoxRows = 32;
 constexpr int kC2N = 3 * kGrowth;               // 96 accumulator columns: (dx, n)
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
   uint64_t* wfull = tempty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 2);
-  float* s_exch = s_bias + kGrowth;  // [4 warps][2][32]: lane 31's dx=0 block, lane 0's dx=2 block
+  float* s_exch = s_bias + kGrowth;  // [2 groups][4 warps][2][32]: lane 31's dx=0 block, lane 0's dx=2 block
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -577,13 +577,20 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
       }
     }
   } else {
+    // two epilogue groups of four warps, group == the TMEM accumulator it drains (tiles alternate): ncu showed the
+    // single group (tcgen05.ld, 64 lane shuffles, pack, store per tile) as the kernel's bottleneck - the MMA warp
+    // waited for a free accumulator with the tensor pipe 44 % active
+    const int grp = (warp - 2) >> 2;
     const int g = warp & 3;
     const int row = g * 32 + lane;
     const int R = p.Hp * p.Wp;
-    float* ex_mine = s_exch + g * 64;
-    int acc = 0; uint32_t acc_phase = 0;
+    float* s_exch_g = s_exch + grp * 256;
+    float* ex_mine = s_exch_g + g * 64;
+    const int acc = grp; uint32_t acc_phase = 0;
     double st_sum = 0.0, st_sq = 0.0;   // training statistics of column `lane`
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != grp) continue;
       const long long m = (long long)tile * kC2Out + row - 1;  // output row of this lane
       bool ring = false;
       {
@@ -603,7 +610,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty[acc]);
       // publish the boundary lanes, then pull the neighbours' values: Y[p-1] block 0, Y[p+1] block 2
-      ptx::named_bar_sync(3, 128);  // previous tile's exchange fully consumed
+      ptx::named_bar_sync(3 + grp, 128);  // previous tile's exchange fully consumed
       if (lane == 31) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) ex_mine[j] = __uint_as_float(left[j]);
@@ -612,14 +619,14 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
 #pragma unroll
         for (int j = 0; j < 32; ++j) ex_mine[32 + j] = __uint_as_float(right[j]);
       }
-      ptx::named_bar_sync(3, 128);
+      ptx::named_bar_sync(3 + grp, 128);
       float o[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         float l = __shfl_up_sync(0xffffffffu, __uint_as_float(left[j]), 1);
         float r = __shfl_down_sync(0xffffffffu, __uint_as_float(right[j]), 1);
-        if (lane == 0 && g > 0) l = s_exch[(g - 1) * 64 + j];
-        if (lane == 31 && g < 3) r = s_exch[(g + 1) * 64 + 32 + j];
+        if (lane == 0 && g > 0) l = s_exch_g[(g - 1) * 64 + j];
+        if (lane == 31 && g < 3) r = s_exch_g[(g + 1) * 64 + 32 + j];
         o[j] = l + __uint_as_float(mid[j]) + r + s_bias[j];
       }
       const bool row_ok = row >= 1 && row <= kC2Out && m < p.m_total;
@@ -647,7 +654,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
         st_sum += (double)warp_transpose_sum(v1, lane);
         st_sq += (double)warp_transpose_sum(v2, lane);
       }
-      if ((acc ^= 1) == 0) acc_phase ^= 1;
+      acc_phase ^= 1;
     }
     if (p.stats != nullptr) {
       atomicAdd(p.stats + lane, st_sum);
@@ -734,7 +741,7 @@ int umma_conv2_fwd(const void* mid, long long rows, const void* w2, const float*
   static bool attr_done = false;
   if (!attr_done) {
     TCVN_CUDA(cudaFuncSetAttribute(umma_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   1024 + kW2Bytes + kC2Stages * 2 * halo_rows_max * 128 + 1536));
+                                   1024 + kW2Bytes + kC2Stages * 2 * halo_rows_max * 128 + 2560));
     attr_done = true;
   }
   Conv2Params c2;
@@ -752,7 +759,7 @@ int umma_conv2_fwd(const void* mid, long long rows, const void* w2, const float*
   CUtensorMap tmM, tmW2;
   TCVN_TRY(make_map(mid, rows, kMid, kMid, 64, kBoxRows, &tmM));
   TCVN_TRY(make_map(w2, 9 * kGrowth, kMid, kMid, 64, kC2N, &tmW2));
-  const size_t smem2 = 1024 + kW2Bytes + (size_t)kC2Stages * 2 * c2.halo_rows * 128 + 1536;
+  const size_t smem2 = 1024 + kW2Bytes + (size_t)kC2Stages * 2 * c2.halo_rows * 128 + 2560;
   umma_conv2_kernel<<<grid, kC2Threads, smem2, st>>>(tmM, tmW2, c2);
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
