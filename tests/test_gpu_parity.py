@@ -312,3 +312,24 @@ def test_bf16_top1_agreement_at_full_size(dev):
     assert rel_err(ev16, ev32) < BF16_TOL and rel_err(pr16[m], pr32[m]) < BF16_TOL
     assert float((ev16.argmax(-1) == ev32.argmax(-1)).float().mean()) >= 0.999
     assert float((pr16.argmax(-1) == pr32.argmax(-1))[m].float().mean()) >= 0.999
+
+
+def test_prefetcher_stages_batches_in_order(dev):
+    """ingest.Prefetcher: batches copied on the copy stream come out in submission order and give bit-identical logits
+    to batches copied on the compute stream."""
+    from dune_transformercvn_b200.ingest import Prefetcher
+    net, state, opts = _net(3, True, dev, precision="bf16")
+    batches = [synth.make_batch(2, seed=40 + i, prongs_per_event=[1 + i, 2]).pin() for i in range(3)]
+    with torch.no_grad():
+        want = [tuple(t.clone() for t in net.forward_sparse(b.to(dev))) for b in batches]
+        pf = Prefetcher(dev)
+        pf.submit(batches[0])
+        got = []
+        for i in range(3):
+            if i + 1 < 3:
+                pf.submit(batches[i + 1])
+            got.append(tuple(t.clone() for t in net.forward_sparse(pf.take())))
+    for w, g in zip(want, got):
+        assert torch.equal(w[0], g[0]) and torch.equal(w[1], g[1])
+    with pytest.raises(tl.TcvnError):
+        pf.take()
