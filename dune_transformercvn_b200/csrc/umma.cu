@@ -499,9 +499,12 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
   uint8_t* sW = smem;
   uint8_t* sA = smem + kW2Bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sA + kC2Stages * stage_bytes);
-  uint64_t* full = bars;
-  uint64_t* empty = bars + kC2Stages;
-  uint64_t* tfull = bars + 2 * kC2Stages;
+  // the pipeline unit is HALF a haloed tile (64 of the 128 channels, <= 36 KB): four units in flight in the space of two
+  // tiles, a unit is refilled as soon as its 12 MMAs have completed - the kernel is bound by the latency of getting a
+  // haloed tile into shared memory, not by the tensor pipe
+  uint64_t* full = bars;                      // [stage][half]
+  uint64_t* empty = bars + 2 * kC2Stages;     // [stage][half]
+  uint64_t* tfull = bars + 4 * kC2Stages;
   uint64_t* tempty = tfull + 2;
   uint64_t* wfull = tempty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
@@ -510,7 +513,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kC2Stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2 * kC2Stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 128); }
     ptx::mbar_init(wfull, 1);
     ptx::fence_mbar_init();
@@ -532,13 +535,14 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
           ptx::tma_load_2d(sW + (dy * 2 + h) * kW2Slab, &tmW, wfull, h * 64, dy * kC2N);
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        ptx::mbar_wait(&empty[stage], phase ^ 1);
-        ptx::mbar_arrive_expect_tx(&full[stage], stage_bytes);
         const int row0 = tile * kC2Out - 1 - p.Wp;  // Y row 0 of the tile is output row tile*126 - 1
-        for (int h = 0; h < 2; ++h)
+        for (int h = 0; h < 2; ++h) {
+          ptx::mbar_wait(&empty[stage * 2 + h], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&full[stage * 2 + h], half_bytes);
           for (int b = 0; b < p.nbox; ++b)
-            ptx::tma_load_2d(sA + stage * stage_bytes + h * half_bytes + b * kBoxRows * 128, &tmA, &full[stage], h * 64,
+            ptx::tma_load_2d(sA + stage * stage_bytes + h * half_bytes + b * kBoxRows * 128, &tmA, &full[stage * 2 + h], h * 64,
                              row0 + b * kBoxRows);
+        }
         if (++stage == kC2Stages) { stage = 0; phase ^= 1; }
       }
     }
@@ -552,25 +556,28 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
-        ptx::mbar_wait(&full[stage], phase);
-        ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * 128;
         // descriptors differ only in their 14-bit start-address field, in 16-byte units: +8 per row of the
         // haloed tile (any row is a legal start: the 128B swizzle is a function of the absolute address),
         // +2 per K step of 16 channels
         const uint32_t a_lo = ptx::umma_desc_lo(ptx::smem_u32(sA + stage * stage_bytes));
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-          const uint32_t row_lo = a_lo + (uint32_t)(dy * p.Wp) * 8u;
+        for (int h = 0; h < 2; ++h) {
+          ptx::mbar_wait(&full[stage * 2 + h], phase);
+          ptx::tc_fence_after();
 #pragma unroll
-          for (int kk = 0; kk < 8; ++kk) {
-            const uint32_t al = row_lo + (kk >> 2) * half16 + (kk & 3) * 2u;
-            const uint32_t bl = w_lo + (dy * 2 + (kk >> 2)) * (kW2Slab >> 4) + (kk & 3) * 2u;
-            ptx::umma_bf16(d_tmem, ptx::umma_desc_join(ptx::kUmmaDescHiSw128, al),
-                           ptx::umma_desc_join(ptx::kUmmaDescHiSw128, bl), idesc, (dy | kk) != 0);
+          for (int dy = 0; dy < 3; ++dy) {
+            const uint32_t row_lo = a_lo + (uint32_t)(dy * p.Wp) * 8u + h * half16;
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint32_t al = row_lo + k4 * 2u;
+              const uint32_t bl = w_lo + (dy * 2 + h) * (kW2Slab >> 4) + k4 * 2u;
+              ptx::umma_bf16(d_tmem, ptx::umma_desc_join(ptx::kUmmaDescHiSw128, al),
+                             ptx::umma_desc_join(ptx::kUmmaDescHiSw128, bl), idesc, (h | dy | k4) != 0);
+            }
           }
+          ptx::umma_commit(&empty[stage * 2 + h]);
         }
-        ptx::umma_commit(&empty[stage]);
         ptx::umma_commit(&tfull[acc]);
         if (++stage == kC2Stages) { stage = 0; phase ^= 1; }
         if ((acc ^= 1) == 0) acc_phase ^= 1;
