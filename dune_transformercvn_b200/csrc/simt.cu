@@ -824,55 +824,67 @@ __device__ __forceinline__ void store_vec<__nv_bfloat16>(__nv_bfloat16* p, const
   *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// Persistent: a thread keeps ONE group of V channels (its 3 x V BN/PReLU constants stay in registers) and walks over
+// output pixels; with one (pixel, channel group) per thread the 24 scalar constant loads per thread - lanes 32 bytes
+// apart, 8 wavefronts each - were ten times the LSU work of the four 16-byte data loads (59 % of the HBM bandwidth).
+// blockDim.x = cv * rows with cv = c / V channel groups; lanes run over channel groups, so a pixel is read contiguously.
 template <typename T>
-__global__ void act_pool2_kernel(const T* __restrict__ blk, int H, int W, int ld, int c,
-                                 const float* __restrict__ scale, const float* __restrict__ shift,
-                                 const float* __restrict__ alpha, T* __restrict__ out, int H2, int W2,
-                                 long long total) {
+__global__ void __launch_bounds__(256) act_pool2_kernel(const T* __restrict__ blk, int H, int W, int ld, int c,
+                                                        const float* __restrict__ scale, const float* __restrict__ shift,
+                                                        const float* __restrict__ alpha, T* __restrict__ out, int H2, int W2,
+                                                        long long n_pixels, int cv) {
   constexpr int V = Vec16<T>::N;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int cv = c / V;
-  const int ch = (int)(idx % cv) * V;
-  long long r = idx / cv;
-  const int x = (int)(r % W2); r /= W2;
-  const int y = (int)(r % H2);
-  const int n = (int)(r / H2);
+  const int v = threadIdx.x % cv, ty = threadIdx.x / cv, rows = blockDim.x / cv;
+  const int ch = v * V;
+  float sc[V], sh[V], al[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) { sc[i] = __ldg(scale + ch + i); sh[i] = __ldg(shift + ch + i); al[i] = __ldg(alpha + ch + i); }
   const int Wp = W + 2;
-  const size_t row0 = (size_t)n * (H + 2) * Wp + (size_t)(2 * y + 1) * Wp + (2 * x + 1);
-  float sc[V], sh[V], al[V], s[V];
+  const long long per_image = (long long)H2 * W2;
+  for (long long px = (long long)blockIdx.x * rows + ty; px < n_pixels; px += (long long)gridDim.x * rows) {
+    const int n = (int)(px / per_image);
+    const int r = (int)(px - (long long)n * per_image);
+    const int y = r / W2, x = r - y * W2;
+    const size_t row0 = (size_t)n * (H + 2) * Wp + (size_t)(2 * y + 1) * Wp + (2 * x + 1);
+    float f[4][V];
 #pragma unroll
-  for (int i = 0; i < V; ++i) {
-    sc[i] = __ldg(scale + ch + i); sh[i] = __ldg(shift + ch + i); al[i] = __ldg(alpha + ch + i);
-    s[i] = 0.f;
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) load_vec<T>(blk + (row0 + (size_t)dy * Wp + dx) * ld + ch, f[dy * 2 + dx]);
+    float s[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) s[i] = 0.f;
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int i = 0; i < V; ++i) s[i] += prelu(fmaf(f[q][i], sc[i], sh[i]), al[i]);
+#pragma unroll
+    for (int i = 0; i < V; ++i) s[i] *= 0.25f;
+    const size_t orow = (size_t)n * (H2 + 2) * (W2 + 2) + (size_t)(y + 1) * (W2 + 2) + (x + 1);
+    store_vec<T>(out + orow * c + ch, s);
   }
-#pragma unroll
-  for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-    for (int dx = 0; dx < 2; ++dx) {
-      float f[V];
-      load_vec<T>(blk + (row0 + (size_t)dy * Wp + dx) * ld + ch, f);
-#pragma unroll
-      for (int i = 0; i < V; ++i) s[i] += prelu(fmaf(f[i], sc[i], sh[i]), al[i]);
-    }
-#pragma unroll
-  for (int i = 0; i < V; ++i) s[i] *= 0.25f;
-  const size_t orow = (size_t)n * (H2 + 2) * (W2 + 2) + (size_t)(y + 1) * (W2 + 2) + (x + 1);
-  store_vec<T>(out + orow * c + ch, s);
 }
 
 int launch_act_pool2(const void* blk, int n, int H, int W, int ld, int c, const float* scale, const float* shift,
                      const float* alpha, void* out, int H2, int W2, bool f32, cudaStream_t stream) {
   const int V = f32 ? 4 : 8;
   if (c % V || ld % V) return fail(TCVN_ERR_UNSUPPORTED, "act_pool2: channel count %d / pitch %d not a multiple of %d", c, ld, V);
-  const long long total = (long long)n * H2 * W2 * (c / V);
-  if (total == 0) return TCVN_OK;
-  const unsigned grid = (unsigned)ceil_div_ll(total, 256);
-  if (f32) act_pool2_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(blk), H, W, ld, c, scale, shift,
-                                                             alpha, static_cast<float*>(out), H2, W2, total);
-  else act_pool2_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(blk), H, W, ld, c,
-                                                                 scale, shift, alpha, static_cast<__nv_bfloat16*>(out),
-                                                                 H2, W2, total);
+  const int cv = c / V;
+  if (cv > 256) return fail(TCVN_ERR_UNSUPPORTED, "act_pool2: %d channels (at most %d)", c, 256 * V);
+  const long long n_pixels = (long long)n * H2 * W2;
+  if (n_pixels == 0) return TCVN_OK;
+  const int rows = 256 / cv;
+  const int threads = rows * cv;
+  long long blocks = ceil_div_ll(n_pixels, (long long)rows * 4);   // >= 4 pixels per thread
+  const long long cap = 148ll * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (f32) act_pool2_kernel<float><<<(unsigned)blocks, threads, 0, stream>>>(static_cast<const float*>(blk), H, W, ld, c, scale,
+                                                                             shift, alpha, static_cast<float*>(out), H2, W2,
+                                                                             n_pixels, cv);
+  else act_pool2_kernel<__nv_bfloat16><<<(unsigned)blocks, threads, 0, stream>>>(
+      static_cast<const __nv_bfloat16*>(blk), H, W, ld, c, scale, shift, alpha, static_cast<__nv_bfloat16*>(out), H2, W2, n_pixels,
+      cv);
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
 }

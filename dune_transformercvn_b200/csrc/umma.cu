@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
 // is the neighbouring TMEM lane, so each tile produces 126 output rows from 128 Y rows; the two lanes at
 // every warp boundary are exchanged through shared memory.
 // ------------------------------------------------------------------------------------------------
-constexpr int kC2Stages = 2;
+constexpr int kC2StagesMax = 4;   // haloed tiles in flight: as many as fit beside the 72 KB of weights (2 on the 99x69 maps, 3 from block 3 on)
 constexpr int kC2Threads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 two epilogue groups (one per TMEM accumulator)
 constexpr int kGrowth = 32;
 constexpr int kBoxRows = 32;
@@ -433,10 +433,12 @@ constexpr int kC2N = 3 * kGrowth;               // 96 accumulator columns: (dx, 
 constexpr int kC2Out = kTileM - 2;              // 126 output rows per tile
 constexpr int kW2Slab = kC2N * 128;             // 12 KB: [96 rows x 128 B] per (dy, half)
 constexpr int kW2Bytes = 3 * 2 * kW2Slab;       // 72 KB
+constexpr size_t kC2SmemMax = 227 * 1024;        // dynamic shared memory a CTA may ask for on sm_100
 
 struct Conv2Params {
   long long m_total;
   int Hp, Wp, halo_rows, nbox;  // halo_rows = nbox * kBoxRows >= 128 + 2*Wp
+  int stages;                   // haloed tiles in flight (2 .. kC2StagesMax)
   const float* bias;
   bf16* out;
   int ldo, col0, num_tiles;
@@ -498,13 +500,13 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
   const int stage_bytes = 2 * half_bytes;
   uint8_t* sW = smem;
   uint8_t* sA = smem + kW2Bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + kC2Stages * stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + p.stages * stage_bytes);
   // the pipeline unit is HALF a haloed tile (64 of the 128 channels, <= 36 KB): four units in flight in the space of two
   // tiles, a unit is refilled as soon as its 12 MMAs have completed - the kernel is bound by the latency of getting a
   // haloed tile into shared memory, not by the tensor pipe
   uint64_t* full = bars;                      // [stage][half]
-  uint64_t* empty = bars + 2 * kC2Stages;     // [stage][half]
-  uint64_t* tfull = bars + 4 * kC2Stages;
+  uint64_t* empty = bars + 2 * kC2StagesMax;  // [stage][half]
+  uint64_t* tfull = bars + 4 * kC2StagesMax;
   uint64_t* tempty = tfull + 2;
   uint64_t* wfull = tempty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
@@ -513,7 +515,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2 * kC2Stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2 * p.stages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 128); }
     ptx::mbar_init(wfull, 1);
     ptx::fence_mbar_init();
@@ -543,7 +545,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
             ptx::tma_load_2d(sA + stage * stage_bytes + h * half_bytes + b * kBoxRows * 128, &tmA, &full[stage * 2 + h], h * 64,
                              row0 + b * kBoxRows);
         }
-        if (++stage == kC2Stages) { stage = 0; phase ^= 1; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -579,7 +581,7 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
           ptx::umma_commit(&empty[stage * 2 + h]);
         }
         ptx::umma_commit(&tfull[acc]);
-        if (++stage == kC2Stages) { stage = 0; phase ^= 1; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
         if ((acc ^= 1) == 0) acc_phase ^= 1;
       }
     }
@@ -748,7 +750,7 @@ int umma_conv2_fwd(const void* mid, long long rows, const void* w2, const float*
   static bool attr_done = false;
   if (!attr_done) {
     TCVN_CUDA(cudaFuncSetAttribute(umma_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   1024 + kW2Bytes + kC2Stages * 2 * halo_rows_max * 128 + 2560));
+                                   (int)kC2SmemMax));
     attr_done = true;
   }
   Conv2Params c2;
@@ -757,6 +759,13 @@ int umma_conv2_fwd(const void* mid, long long rows, const void* w2, const float*
   c2.halo_rows = c2.nbox * kBoxRows;
   if (c2.halo_rows > halo_rows_max)
     return fail(TCVN_ERR_UNSUPPORTED, "feature map width %d needs a %d-row halo tile (max %d)", W, c2.halo_rows, halo_rows_max);
+  {
+    const size_t fixed = 1024 + kW2Bytes + 2560, per_stage = (size_t)2 * c2.halo_rows * 128;
+    int st_n = (int)((kC2SmemMax - fixed) / per_stage);
+    static const int st_cap = [] { const char* v = getenv("TCVN_C2_STAGES"); const int n = v ? atoi(v) : 0; return n >= 2 && n <= kC2StagesMax ? n : kC2StagesMax; }();
+    c2.stages = st_n > st_cap ? st_cap : st_n;
+    if (c2.stages < 2) return fail(TCVN_ERR_UNSUPPORTED, "conv2: a %d-row halo tile leaves no room for two stages", c2.halo_rows);
+  }
   c2.bias = bias;
   c2.out = static_cast<bf16*>(out); c2.ldo = ldo; c2.col0 = col0; c2.num_tiles = tiles;
   c2.p_drop = p_drop; c2.seed = seed; c2.site = site; c2.stats = stats; c2.stats_stride = stats_stride;
@@ -766,7 +775,7 @@ int umma_conv2_fwd(const void* mid, long long rows, const void* w2, const float*
   CUtensorMap tmM, tmW2;
   TCVN_TRY(make_map(mid, rows, kMid, kMid, 64, kBoxRows, &tmM));
   TCVN_TRY(make_map(w2, 9 * kGrowth, kMid, kMid, 64, kC2N, &tmW2));
-  const size_t smem2 = 1024 + kW2Bytes + (size_t)kC2Stages * 2 * c2.halo_rows * 128 + 2560;
+  const size_t smem2 = 1024 + kW2Bytes + (size_t)c2.stages * 2 * c2.halo_rows * 128 + 2560;
   umma_conv2_kernel<<<grid, kC2Threads, smem2, st>>>(tmM, tmW2, c2);
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
