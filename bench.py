@@ -400,6 +400,7 @@ def run_ours(args):
     net = NeutrinoDenseNetwork(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES, precision=args.precision)
     net = net.to(dev).eval()
     net.overlap_cnns = not args.no_overlap_cnns
+    net.partition_sms = args.partition_sms
     batch = make_inputs(args.events, 1234 + rank)
     images = batch.num_events + batch.num_prongs
     host = batch.pin()
@@ -554,6 +555,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-overlap-cnns", action="store_true", help="inference: run the event CNN and the prong CNN on one stream")
+    ap.add_argument("--partition-sms", action="store_true", help="inference: disjoint SM budgets for the two CNN streams (measured slower: 21.7 vs 21.2 ms)")
     ap.add_argument("--no-roofline", action="store_true", help="skip the isolated layer-kernel timings (chunk-size sweeps)")
     ap.add_argument("--no-train", action="store_true", help="skip the training leg (BASELINE configs[2]) reported under \"train\"")
     ap.add_argument("--train-events", type=int, default=16, help="events per GPU per training step (2023_08_07 JSON batch_size)")

@@ -73,6 +73,12 @@ int make_map(const void* base, long long rows, int cols, int pitch, int box_cols
   return TCVN_OK;
 }
 
+// SMs the persistent tcgen05 kernels launched from THIS host thread may occupy (0 = all).  The two pixel-map CNNs run on
+// two streams; with every kernel sized for the whole chip they only time-slice, with disjoint SM budgets they run side by
+// side and each stream's launch prologues (TMEM allocation, barrier setup, 72 KB of conv2 weights: ~7 us per launch) hide
+// under the other stream's kernels.
+static thread_local int g_sm_limit = 0;
+
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -81,8 +87,18 @@ int sm_count() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
-  return n;
+  return g_sm_limit > 0 && g_sm_limit < n ? g_sm_limit : n;
 }
+
+}  // namespace tcvn
+
+extern "C" int tcvn_set_sm_limit(int n_sms) {
+  if (n_sms < 0) return tcvn::fail(TCVN_ERR_ARG, "set_sm_limit: %d", n_sms);
+  tcvn::g_sm_limit = n_sms;
+  return TCVN_OK;
+}
+
+namespace tcvn {
 
 // ------------------------------------------------------------------------------------------------
 // GEMM with fused operand activation:  out[m, n] = PReLU_n( sum_k act_k(A[m, k]) * W[n, k] + shift[n] )

@@ -34,7 +34,7 @@ EXPORTS = (
     "tcvn_seq_train_workspace_bytes", "tcvn_seq_train_forward", "tcvn_seq_train_backward",
     "tcvn_t_umma_wgrad", "tcvn_t_umma_wgrad_workspace_bytes", "tcvn_t_umma_conv2_dgrad",
     "tcvn_loss_forward", "tcvn_loss_backward", "tcvn_metrics_update",
-    "tcvn_sdxl_pixels_to_ring", "tcvn_sdxl_groupnorm", "tcvn_sdxl_patch_s2",
+    "tcvn_sdxl_pixels_to_ring", "tcvn_sdxl_groupnorm", "tcvn_sdxl_patch_s2", "tcvn_set_sm_limit",
 )
 
 
@@ -135,6 +135,7 @@ def load() -> C.CDLL:
     lib.tcvn_sdxl_pixels_to_ring.argtypes = [vp, i32, i32, i32, i32, vp, vp]
     lib.tcvn_sdxl_groupnorm.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, f32, i32, vp, vp, vp]
     lib.tcvn_sdxl_patch_s2.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+    lib.tcvn_set_sm_limit.argtypes = [i32]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("tcvn_abi_version",):

@@ -304,6 +304,11 @@ int tcvn_seq_train_backward(const tcvn_seq_desc* d, const float* position, const
                             float* d_prong_logits, float* d_event_embedding, float* d_prong_embedding, void* workspace,
                             size_t workspace_bytes, tcvn_stream_t stream);
 
+/* SM budget of the persistent tcgen05 kernels launched from the calling host thread until the next call (0 = the whole
+ * chip).  Lets two independent walks on two streams (the event CNN and the prong CNN, neutrino_full_base_network.py:
+ * 99-104) run side by side on disjoint SMs instead of time-slicing. */
+int tcvn_set_sm_limit(int n_sms);
+
 /* ------------------------------------------------------------------------------------------
  * Loss and validation metrics on the device: one launch each, no host sync.
  * tcvn_loss_forward replaces `loss` + the masked_select / log_softmax / softmax / argmax chain of `training_step`
