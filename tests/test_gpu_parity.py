@@ -333,3 +333,19 @@ def test_prefetcher_stages_batches_in_order(dev):
         assert torch.equal(w[0], g[0]) and torch.equal(w[1], g[1])
     with pytest.raises(tl.TcvnError):
         pf.take()
+
+
+def test_sm_budgets_do_not_change_the_result(dev):
+    """tcvn_set_sm_limit only sizes the persistent grids: logits with disjoint SM budgets for the two CNN streams are
+    bit-identical to the default whole-chip launch (tile -> CTA assignment never enters the arithmetic)."""
+    net, state, opts = _net(3, True, dev, precision="bf16")
+    batch = synth.make_batch(6, seed=77, max_prongs=6).to(dev)
+    with torch.no_grad():
+        net.partition_sms = False
+        a = tuple(t.clone() for t in net.forward_sparse(batch))
+        net.partition_sms = True
+        b = tuple(t.clone() for t in net.forward_sparse(batch))
+        net.partition_sms = False
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    L = tl.load()
+    assert L.tcvn_set_sm_limit(-1) != 0 and L.tcvn_set_sm_limit(0) == 0
