@@ -17,6 +17,8 @@ of a module that calls it work.  There is no CPU implementation: CPU tensors rai
 """
 from __future__ import annotations
 
+import itertools
+import weakref
 from typing import Dict, Tuple
 
 import torch
@@ -142,15 +144,24 @@ class EventClassifier(nn.Module):
 
 
 # ---- torch.library custom op: the traceable / exportable form of the same call ----------------------------------
-_REGISTRY: Dict[int, "EventClassifier"] = {}
+# handle -> classifier; weak, so that a dropped classifier (network, workspaces, captured graphs) can be collected
+_REGISTRY: "weakref.WeakValueDictionary[int, EventClassifier]" = weakref.WeakValueDictionary()
+_handles = itertools.count(1)
 _op_defined = False
 
 
 def _register(mod: "EventClassifier") -> int:
     _define_op()
-    handle = len(_REGISTRY) + 1
+    handle = next(_handles)
     _REGISTRY[handle] = mod
     return handle
+
+
+def _lookup(handle: int) -> "EventClassifier":
+    mod = _REGISTRY.get(handle)
+    if mod is None:
+        raise _lib.TcvnError(f"tcvn::classify_event: classifier handle {handle} is gone (the EventClassifier was deleted)")
+    return mod
 
 
 def _define_op() -> None:
@@ -161,11 +172,11 @@ def _define_op() -> None:
 
     @torch.library.custom_op("tcvn::classify_event", mutates_args=())
     def classify_event(pixels: torch.Tensor, handle: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
-        return _REGISTRY[handle].classify(pixels)
+        return _lookup(handle).classify(pixels)
 
     @classify_event.register_fake
     def _(pixels, handle):
-        mod = _REGISTRY[handle]
+        mod = _lookup(handle)
         net = mod.network
         h, w = net.image_size
         n = pixels.numel() // (net.pixel_dim * h * w)
