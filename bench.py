@@ -517,7 +517,9 @@ def run_ours(args):
                        "ingest": "densify kernel -> dense maps" if args.materialize else "hit lists consumed by the stem (no dense map)",
                        "l2": "activations touched per step (%.1f GB at ~16 MB/image) exceed the 126 MB L2" % (images * 16e6 / 1e9)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "pipeline": "every timed step copies one batch of hit lists from pinned host memory (copy stream, one batch "
+                                "ahead: ingest.Prefetcher), runs one batch and copies its logits to pinned host memory"},
             "gpu_launches": launches, "images_per_s": value * images / args.events,
             "whole_net_tflops": tflops, "roofline": roofline, "rooflines_other": extra_rooflines,
             "cpu_baseline": cpu, "clocks": sampler.summary(), "train": train, "train_large_batch": train_large,
