@@ -127,3 +127,24 @@ def test_fused_training_step_logs_what_the_reference_logs(dev):
     assert abs(logged["train_loss"] - float(want)) < 2e-6 * abs(float(want))
     assert abs(0.9 * logged["event_loss"] + 0.1 * logged["prong_loss"] - logged["train_loss"]) < 1e-6
     assert d_ev.grad is not None and float(d_ev.grad.abs().sum()) > 0
+
+
+def test_fused_loss_matches_the_reference_golden(dev, golden_dir):
+    """tcvn_loss_forward against tests/golden/loss.pt: losses, accuracies and logit gradients the UNMODIFIED reference
+    `loss` / `training_step` arithmetic produced in fp64 (oracle/make_golden_loss.py)."""
+    import os
+    import types
+    cases = torch.load(os.path.join(golden_dir, "loss.pt"))
+    for name, c in cases.items():
+        ev = c["event_logits"].to(dev).requires_grad_(True)
+        pr = c["prong_logits"].to(dev).requires_grad_(True)
+        opts = types.SimpleNamespace(loss_gamma=c["gamma"], event_prong_loss_proportion=c["event_scale"])
+        total, stats = tloss.training_loss(ev, pr, c["event_targets"].to(dev), c["prong_targets"].to(dev), opts)
+        total.backward()
+        s = stats.cpu().double()
+        for got, want in ((float(total.detach()), c["total"]), (float(s[1]), c["event_loss"]), (float(s[2]), c["prong_loss"])):
+            assert abs(got - want) < 2e-6 * abs(want), name
+        assert abs(float(s[3]) - c["event_accuracy"]) < 1e-6 and abs(float(s[4]) - c["prong_accuracy"]) < 1e-6, name
+        ge, gp = c["d_event_logits"], c["d_prong_logits"]
+        assert float((ev.grad.cpu().double() - ge).abs().max()) < 1e-5 * float(ge.abs().max()), name
+        assert float((pr.grad.cpu().double() - gp).abs().max()) < 1e-5 * float(gp.abs().max()), name

@@ -93,3 +93,23 @@ def test_collate_matches_reference_golden(golden_dir):
         got_c, got_v = restate.collate_sparse(c["coords"], c["values"], c["masks"])
         assert torch.equal(got_c, c["out_coords"]) and got_c.dtype == c["out_coords"].dtype, name
         assert torch.equal(got_v, c["out_values"]), name
+
+
+def test_loss_matches_reference_golden(golden_dir):
+    """oracle.restate.focal_loss / training_loss against the frozen fp64 outputs of the reference's own
+    NeutrinoFullBaseTrainer.loss + the training_step masking (oracle/make_golden_loss.py): gamma 0 / 0.5 / 1 / 2."""
+    import types
+    cases = torch.load(os.path.join(golden_dir, "loss.pt"))
+    assert set(cases) == {"tutorial_gamma1", "cross_entropy", "gamma2", "gamma_half"}
+    for name, c in cases.items():
+        ev = c["event_logits"].double().requires_grad_(True)
+        pr = c["prong_logits"].double().requires_grad_(True)
+        opts = types.SimpleNamespace(loss_gamma=c["gamma"], event_prong_loss_proportion=c["event_scale"])
+        total = restate.training_loss(ev, pr, c["event_targets"], c["prong_targets"], opts)
+        total.backward()
+        assert abs(float(total) - c["total"]) < 1e-9 * abs(c["total"]), name
+        sel = c["prong_targets"] >= 0
+        assert abs(float(restate.focal_loss(ev.detach(), c["event_targets"], c["gamma"])) - c["event_loss"]) < 1e-9, name
+        assert abs(float(restate.focal_loss(pr.detach()[sel], c["prong_targets"][sel], c["gamma"])) - c["prong_loss"]) < 1e-9, name
+        assert float((ev.grad - c["d_event_logits"]).abs().max()) < 1e-10, name
+        assert float((pr.grad - c["d_prong_logits"]).abs().max()) < 1e-10, name
