@@ -256,3 +256,16 @@ def training_loss(ev_logits, pr_logits, ev_targets, pr_targets, options) -> torc
     lp = focal_loss(pr_logits[sel], pr_targets[sel], options.loss_gamma)
     a = options.event_prong_loss_proportion
     return a * le + (1 - a) * lp
+
+
+def export_combined(state, options, pixels: torch.Tensor):
+    """``DynamicCombinedNetwork.forward`` of CreateCompiled.ipynb cell 8 (log_pixels False): one event given as
+    (1 + Npng, 3, H, W) maps with 0..255 values -> (event probabilities, prong probabilities, event hidden vector,
+    prong hidden vectors).  Pinned on tests/golden/export.pt (oracle/make_golden_export.py)."""
+    px = pixels.float() / 255
+    n = px.shape[0]
+    taps: dict = {}
+    ev, pr = network_forward(state, options, px[:1], torch.ones(1, 1, dtype=torch.bool), px[1:],
+                             torch.ones(1, n - 1, dtype=torch.bool), taps=taps)
+    hidden = taps["hidden"]
+    return torch.softmax(ev[0], 0), torch.softmax(pr[0], 1), hidden[0, 0], hidden[1:, 0]

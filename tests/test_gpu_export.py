@@ -31,14 +31,8 @@ def _pixels(n_prongs, seed):
 
 
 def _oracle(state, opts, pixels):
-    px = pixels.float() / 255
-    n = px.shape[0]
-    taps = {}
     with torch.no_grad():
-        ev, pr = restate.network_forward(state, opts, px[:1], torch.ones(1, 1, dtype=torch.bool), px[1:],
-                                         torch.ones(1, n - 1, dtype=torch.bool), taps=taps)
-    hidden = taps["hidden"]
-    return torch.softmax(ev[0], 0), torch.softmax(pr[0], 1), hidden[0, 0], hidden[1:, 0]
+        return restate.export_combined(state, opts, pixels)
 
 
 @pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
@@ -79,3 +73,22 @@ def test_custom_op_runs_and_exports(dev):
     assert "tcvn.classify_event" in str(ep.graph)
     c = ep.module()(px)
     assert all(torch.equal(x, y) for x, y in zip(c, b))
+
+
+def test_event_classifier_matches_the_reference_golden(dev, golden_dir):
+    """EventClassifier (fp32 path, CUDA-graph plan) against tests/golden/export.pt: outputs of the notebook wrapper's
+    operation sequence on the UNMODIFIED reference network (oracle/make_golden_export.py); 1e-4 (north_star, fp32)."""
+    import os
+    g = torch.load(os.path.join(golden_dir, "export.pt"))
+    opts = PathOptions.tutorial()
+    net = NeutrinoDenseNetwork(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES)
+    state = synth.init_state(net.specs, seed=g["state_seed"], perturb=True)
+    assert synth.state_checksum(state) == pytest.approx(g["state_checksum"], rel=1e-12)
+    net.load_state_dict(state)
+    clf = EventClassifier(net.to(dev).eval(), "combined")
+    for name, c in g["events"].items():
+        px = _pixels(c["n_prongs"], c["batch_seed"])
+        assert int(px.long().sum()) == c["pixel_sum"]
+        got = clf(px.to(dev))
+        for a, k in zip(got, ("event_prob", "prong_prob", "event_features", "prong_features")):
+            assert rel_err(a.cpu(), c[k]) < 1e-4, (name, k)

@@ -113,3 +113,24 @@ def test_loss_matches_reference_golden(golden_dir):
         assert abs(float(restate.focal_loss(pr.detach()[sel], c["prong_targets"][sel], c["gamma"])) - c["prong_loss"]) < 1e-9, name
         assert float((ev.grad - c["d_event_logits"]).abs().max()) < 1e-10, name
         assert float((pr.grad - c["d_prong_logits"]).abs().max()) < 1e-10, name
+
+
+def test_export_surface_matches_reference_golden(golden_dir, tutorial_options):
+    """oracle.restate.export_combined against the frozen outputs of the notebook wrapper's operation sequence run on the
+    unmodified reference network (oracle/make_golden_export.py)."""
+    from dune_transformercvn_b200 import synth
+    from dune_transformercvn_b200.config import NUM_EVENT_CLASSES, NUM_PRONG_CLASSES
+    from dune_transformercvn_b200.params import network_specs
+    g = torch.load(os.path.join(golden_dir, "export.pt"))
+    specs = network_specs(tutorial_options, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES)
+    state = synth.init_state(specs, seed=g["state_seed"], perturb=True)
+    assert synth.state_checksum(state) == pytest.approx(g["state_checksum"], rel=1e-12)
+    c = g["events"]["one_prong"]        # the six-prong event is checked on the GPU (tests/test_gpu_export.py)
+    batch = synth.make_batch(1, seed=c["batch_seed"], prongs_per_event=[c["n_prongs"]])
+    px = torch.cat((restate.densify(batch.event_values.float(), batch.event_coords, 400, 280),
+                    restate.densify(batch.prong_values.float(), batch.prong_coords, 400, 280))).to(torch.uint8)
+    assert int(px.long().sum()) == c["pixel_sum"]
+    with torch.no_grad():
+        got = restate.export_combined(state, tutorial_options, px)
+    for a, k in zip(got, ("event_prob", "prong_prob", "event_features", "prong_features")):
+        assert rel_err(a, c[k]) < 2e-5, k
