@@ -83,6 +83,8 @@ int bnact_fwd_typed(const void* X, bool x_bf16, int ldx, int xcol0, const float*
                     int ring_hp, int ring_wp, void* out, bool o_bf16, int ldo, int ocol0, cudaStream_t stream);
 int pool_typed(int kind, const void* src, const float* fold, void* dst, bool bf16, int n, int C, int H, int W, int H2, int W2,
                int ld, cudaStream_t stream);
+int stem_conv_typed(const float* pixels, int n, int cin, int H, int W, const float* w, const float* bias, int C, float* z,
+                    const void* dz, bool dz_bf16, float* dw, cudaStream_t stream);
 int dropout_typed(void* X, bool bf16, int ld, int col0, int C, long long m_total, uint64_t seed, uint64_t stream_id, float p,
                   cudaStream_t stream);
 // BN1 backward with deferred mean corrections (train.cu): one pass O += sc * g and the three reductions into sums[3][C]

@@ -666,7 +666,8 @@ __global__ void stem_pool_fwd_kernel(const float* __restrict__ z, const float* _
 }
 
 // gradient of the above w.r.t. the activated stem map: dA[n,oy,ox,c] = (1/9) sum of dP over the windows holding (oy,ox)
-__global__ void stem_pool_bwd_kernel(const float* __restrict__ dblk, int ld, int H, int W, int C, float* __restrict__ dA,
+template <typename TO>
+__global__ void stem_pool_bwd_kernel(const float* __restrict__ dblk, int ld, int H, int W, int C, TO* __restrict__ dA,
                                      int Hs, int Ws, long long total) {
   // one thread = one stem pixel x 4 channels; window py covers rows 2py .. 2py+2
   const long long idx64 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -686,7 +687,13 @@ __global__ void stem_pool_bwd_kernel(const float* __restrict__ dblk, int ld, int
       const float4 v = *reinterpret_cast<const float4*>(dblk + ((size_t)n * (H + 2) * (W + 2) + (size_t)(py + 1) * (W + 2) + px + 1) * ld + c);
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
     }
-  *reinterpret_cast<float4*>(dA + (((size_t)n * Hs + oy) * Ws + ox) * C + c) = make_float4(s.x / 9.0f, s.y / 9.0f, s.z / 9.0f, s.w / 9.0f);
+  TO* dst = dA + (((size_t)n * Hs + oy) * Ws + ox) * C + c;
+  if (sizeof(TO) == 4) {
+    *reinterpret_cast<float4*>(dst) = make_float4(s.x / 9.0f, s.y / 9.0f, s.z / 9.0f, s.w / 9.0f);
+  } else {   // bf16 stem gradient map (bf16 walk): half the bytes of the three dense passes over it
+    const __nv_bfloat162 lo = __floats2bfloat162_rn(s.x / 9.0f, s.y / 9.0f), hi = __floats2bfloat162_rn(s.z / 9.0f, s.w / 9.0f);
+    *reinterpret_cast<uint2*>(dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+  }
 }
 
 // AvgPool2d(2,2) backward: dA[ringed H x W rows, C] = 0.25 * dP[ringed H2 x W2 parent] (0 where the floor cropped)
@@ -767,10 +774,10 @@ __global__ void stem_fill_bias_kernel(float* z, const float* __restrict__ bias, 
 // gradient is accumulated in shared memory (cin*49*C <= 9408 floats) and flushed once per CTA - global atomics on the
 // 9.4 k filter entries from every hit of the batch serialise otherwise.
 constexpr int kStemW = 3 * 49 * 64;
-template <bool WGRAD>
+template <bool WGRAD, typename TDZ = float>
 __global__ void __launch_bounds__(256) stem_conv_scatter_kernel(const float* __restrict__ pixels, int cin, int H, int W, int Hs,
                                                                 int Ws, const float* __restrict__ w /*[cin*49][C]*/, int C,
-                                                                float* __restrict__ z, const float* __restrict__ dz,
+                                                                float* __restrict__ z, const TDZ* __restrict__ dz,
                                                                 float* __restrict__ dw, unsigned total) {
   __shared__ float sdw[WGRAD ? kStemW : 1];
   const int nw = cin * 49 * C;
@@ -806,7 +813,7 @@ __global__ void __launch_bounds__(256) stem_conv_scatter_kernel(const float* __r
           const int wi = ((c * 7 + ky) * 7 + kx) * C;
           for (int ch = lane; ch < C; ch += 32) {
             if (!WGRAD) atomicAdd(z + o + ch, val * __ldg(w + wi + ch));
-            else atomicAdd(&sdw[wi + ch], val * __ldg(dz + o + ch));
+            else atomicAdd(&sdw[wi + ch], val * to_f32<TDZ>(dz[o + ch]));
           }
         }
       }
@@ -922,6 +929,7 @@ int bnact_bwd_apply_typed(const void* D, bool d_bf16, int ldd, int dcol0, const 
     if (!x_bf16 && !d_bf16 && !o_bf16) bnact_bwd_apply_vec_kernel<float, float, float><<<vgrid, 256, 0, stream>>>(p, tv, rows_per_slab);
     else if (x_bf16 && d_bf16 && o_bf16) bnact_bwd_apply_vec_kernel<bf, bf, bf><<<vgrid, 256, 0, stream>>>(p, tv, rows_per_slab);
     else if (x_bf16 && d_bf16 && !o_bf16) bnact_bwd_apply_vec_kernel<bf, bf, float><<<vgrid, 256, 0, stream>>>(p, tv, rows_per_slab);
+    else if (!x_bf16 && d_bf16 && o_bf16) bnact_bwd_apply_vec_kernel<float, bf, bf><<<vgrid, 256, 0, stream>>>(p, tv, rows_per_slab);
     else return fail(TCVN_ERR_UNSUPPORTED, "bnact_bwd_apply: type combination not instantiated");
     TCVN_LAUNCH_CHECK();
     return TCVN_OK;
@@ -930,6 +938,7 @@ int bnact_bwd_apply_typed(const void* D, bool d_bf16, int ldd, int dcol0, const 
   if (!x_bf16 && !d_bf16 && !o_bf16) bnact_bwd_apply_kernel<float, float, float><<<grid, 256, 0, stream>>>(p);
   else if (x_bf16 && d_bf16 && o_bf16) bnact_bwd_apply_kernel<bf, bf, bf><<<grid, 256, 0, stream>>>(p);
   else if (x_bf16 && d_bf16 && !o_bf16) bnact_bwd_apply_kernel<bf, bf, float><<<grid, 256, 0, stream>>>(p);
+  else if (!x_bf16 && d_bf16 && o_bf16) bnact_bwd_apply_kernel<float, bf, bf><<<grid, 256, 0, stream>>>(p);
   else return fail(TCVN_ERR_UNSUPPORTED, "bnact_bwd_apply: type combination not instantiated");
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
@@ -982,9 +991,10 @@ int pool_typed(int kind, const void* src, const float* fold, void* dst, bool bf1
       if (bf16) stem_pool_fwd_kernel<bf><<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const float*>(src), fold, H2, W2, C, static_cast<bf*>(dst), ld, H, W, total);
       else stem_pool_fwd_kernel<float><<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const float*>(src), fold, H2, W2, C, static_cast<float*>(dst), ld, H, W, total);
       break;
-    case 1:   // gradient buffers of a block are fp32 in both precisions
+    case 1:   // gradient buffers of a block are fp32 in both precisions; bf16 = element type of the stem gradient map dst
       total = (long long)n * H2 * W2 * (C / 4);
-      stem_pool_bwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const float*>(src), ld, H, W, C, static_cast<float*>(dst), H2, W2, total);
+      if (bf16) stem_pool_bwd_kernel<bf><<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const float*>(src), ld, H, W, C, static_cast<bf*>(dst), H2, W2, total);
+      else stem_pool_bwd_kernel<float><<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const float*>(src), ld, H, W, C, static_cast<float*>(dst), H2, W2, total);
       break;
     case 2:
       total = (long long)n * (H + 2) * (W + 2) * (C / 8);
@@ -1162,8 +1172,10 @@ extern "C" int tcvn_t_dropout(float* X, int ld, int col0, int C, int64_t m_total
 }
 
 // forward (dz == NULL): z[n,Hs,Ws,C] = bias + conv7x7s2p3(pixels);  backward (dz != NULL): dw[cin*49][C] += x (*) dz
-extern "C" int tcvn_t_stem_conv(const float* pixels, int n, int cin, int H, int W, const float* w, const float* bias, int C,
-                                float* z, const float* dz, float* dw, tcvn_stream_t stream) {
+namespace tcvn {
+// conv0 forward (dz == nullptr: z = bias + conv) or weight gradient (dw += pixels (x) dz); dz_bf16 = element type of dz
+int stem_conv_typed(const float* pixels, int n, int cin, int H, int W, const float* w, const float* bias, int C, float* z,
+                    const void* dz, bool dz_bf16, float* dw, cudaStream_t stream) {
   TCVN_CHECK_ARG(pixels && w && ((dz == nullptr && z && bias) || (dz && dw)), "t_stem_conv: bad arguments");
   if (n <= 0) return TCVN_OK;
   const int Hs = (H + 6 - 7) / 2 + 1, Ws = (W + 6 - 7) / 2 + 1;
@@ -1175,13 +1187,25 @@ extern "C" int tcvn_t_stem_conv(const float* pixels, int n, int cin, int H, int 
   }
   const long long total = (long long)n * cin * H * W;
   if (total >= (1ll << 32) - (1ll << 22)) return fail(TCVN_ERR_UNSUPPORTED, "t_stem_conv: %d images exceed 2^32 pixel values in one launch", n);
-  if (cin * 49 * C > tcvn::kStemW) return fail(TCVN_ERR_UNSUPPORTED, "t_stem_conv: filter bank larger than %d entries", tcvn::kStemW);
+  if (cin * 49 * C > kStemW) return fail(TCVN_ERR_UNSUPPORTED, "t_stem_conv: filter bank larger than %d entries", kStemW);
   long long want = ceil_div_ll(total, 256 * 8);
   const int grid = (int)(want < 148 * 8 ? (want < 1 ? 1 : want) : 148 * 8);
-  if (dz == nullptr) stem_conv_scatter_kernel<false><<<grid, 256, 0, stream>>>(pixels, cin, H, W, Hs, Ws, w, C, z, dz, dw, (unsigned)total);
-  else stem_conv_scatter_kernel<true><<<grid, 256, 0, stream>>>(pixels, cin, H, W, Hs, Ws, w, C, z, dz, dw, (unsigned)total);
+  if (dz == nullptr)
+    stem_conv_scatter_kernel<false><<<grid, 256, 0, stream>>>(pixels, cin, H, W, Hs, Ws, w, C, z, static_cast<const float*>(nullptr), dw, (unsigned)total);
+  else if (dz_bf16)
+    stem_conv_scatter_kernel<true, __nv_bfloat16><<<grid, 256, 0, stream>>>(pixels, cin, H, W, Hs, Ws, w, C, z,
+                                                                            static_cast<const __nv_bfloat16*>(dz), dw, (unsigned)total);
+  else
+    stem_conv_scatter_kernel<true><<<grid, 256, 0, stream>>>(pixels, cin, H, W, Hs, Ws, w, C, z, static_cast<const float*>(dz), dw,
+                                                             (unsigned)total);
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
+}
+}  // namespace tcvn
+
+extern "C" int tcvn_t_stem_conv(const float* pixels, int n, int cin, int H, int W, const float* w, const float* bias, int C,
+                                float* z, const float* dz, float* dw, tcvn_stream_t stream) {
+  return tcvn::stem_conv_typed(pixels, n, cin, H, W, w, bias, C, z, dz, false, dw, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -970,13 +970,15 @@ struct TWalk16 {
                         (long long)n * Pv.R, Pv.Hp, Pv.Wp, f(Xp.gblk), false, Pv.ctot, false, Pv.tnorm, Pv.c0, Pv.c0p));
       } else {
         const long long stem_rows = (long long)n * P.Hs * P.Ws;
-        float* dz0 = f(T.dz0);
-        TCVN_TRY(pool_typed(1, gblk, nullptr, dz0, false, n, C0, B.H, B.W, P.Hs, P.Ws, B.ctot, st));
-        TCVN_TRY(bn_bwd(f(T.z0), false, C0, dz0, false, C0, f(T.fold0), C0, C0, (double)stem_rows, stem_rows, 0, 0, dz0, false, C0,
+        // the gradient of the 64 x 200 x 140 stem map is bf16 here (three dense passes over it: pool backward, the BN0
+        // reductions, the BN0 apply); it feeds only conv0's weight gradient and the BN0 / PReLU0 parameter gradients
+        bf* dz0 = h(T.dz0);
+        TCVN_TRY(pool_typed(1, gblk, nullptr, dz0, true, n, C0, B.H, B.W, P.Hs, P.Ws, B.ctot, st));
+        TCVN_TRY(bn_bwd(f(T.z0), false, C0, dz0, true, C0, f(T.fold0), C0, C0, (double)stem_rows, stem_rows, 0, 0, dz0, true, C0,
                         false, P.norm0, NOGAP, NOGAP));
         const int k0 = d.in_channels * 49;
         TCVN_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)k0 * C0, st));
-        TCVN_TRY(tcvn_t_stem_conv(pixels, n, d.in_channels, d.height, d.width, f(T.w0), nullptr, C0, nullptr, dz0, dwp, st));
+        TCVN_TRY(stem_conv_typed(pixels, n, d.in_channels, d.height, d.width, f(T.w0), nullptr, C0, nullptr, dz0, true, dwp, st));
         TCVN_TRY(unpack(dwp, 1, k0, C0, C0, k0, NOGAP, NOGAP, garena + P.conv0_w));
       }
     }
