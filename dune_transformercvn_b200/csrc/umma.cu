@@ -329,7 +329,9 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
     uint32_t* s_alpha2 = reinterpret_cast<uint32_t*>(s_shift + kMid);     // [64] bf16x2
     uint32_t acc_phase = 0;
     int it = 0;
-    double st_sum = 0.0, st_sq = 0.0;   // this thread's column (training statistics)
+    float st1[8], st2[8];   // training statistics: this thread's 8 columns over its rows of every tile (fp32 partials)
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { st1[q] = 0.f; st2[q] = 0.f; }
     const int e_col = threadIdx.x - (10 + 4 * grp) * 32;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       if ((it & 1) != grp) continue;
@@ -401,29 +403,50 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
         ptx::tma_store_commit();
       }
       if (p.stats != nullptr) {
-        // column e_col of the staged tile (exactly the bf16 values being stored); rows beyond m_total hold zeros from
-        // the zero-filled A rows only if the shift is zero, so they are skipped explicitly
-        const uint8_t* colp = stg + (e_col >> 6) * kStageA + (e_col & 7) * 2;
-        const int chunk = (e_col & 63) >> 3;
+        // statistics of exactly the bf16 values being stored, read back from the staged tile 8 columns (16 bytes) at a
+        // time: thread e owns column group e & 15 on rows (e >> 4) + 8 i.  (One column per thread cost 128 two-byte
+        // loads per tile - as many LSU wavefronts as the operand transform - and made the train-mode kernel 35 % slower
+        // than the eval one.)  Rows beyond m_total hold shift-only values and are skipped explicitly.
+        const int sg = e_col & 15, r0 = e_col >> 4;
+        const uint8_t* gp = stg + (sg >> 3) * kStageA;
         const long long m0 = (long long)mt * kTileM;
         const int rmax = (int)(p.m_total - m0 < kTileM ? p.m_total - m0 : kTileM);
-        float s1 = 0.f, s2 = 0.f;
-#pragma unroll 8
-        for (int r = 0; r < kTileM; ++r) {
-          const unsigned short raw = *reinterpret_cast<const unsigned short*>(colp + r * 128 + ((chunk ^ (r & 7)) << 4));
-          const float v = r < rmax ? __uint_as_float((uint32_t)raw << 16) : 0.f;
-          s1 += v;
-          s2 = fmaf(v, v, s2);
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+          const int r = r0 + 8 * i;
+          if (r >= rmax) break;
+          const uint4 v = *reinterpret_cast<const uint4*>(gp + r * 128 + (((sg & 7) ^ (r & 7)) << 4));
+          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float a = bf_lo(w[q]), b = bf_hi(w[q]);
+            st1[2 * q] += a; st1[2 * q + 1] += b;
+            st2[2 * q] = fmaf(a, a, st2[2 * q]); st2[2 * q + 1] = fmaf(b, b, st2[2 * q + 1]);
+          }
         }
-        st_sum += (double)s1;
-        st_sq += (double)s2;
       }
       acc_phase ^= 1;
     }
     if (issuer) ptx::tma_store_wait_all();
-    if (p.stats != nullptr && it > 0) {
-      atomicAdd(p.stats + e_col, st_sum);
-      atomicAdd(p.stats + p.stats_stride + e_col, st_sq);
+    if (p.stats != nullptr) {
+      // per-CTA reduction through the (now idle) staging tile in a fixed order, then one double atomic per column
+      ptx::named_bar_sync(1 + grp, 128);          // the issuer's stores have drained the staging tile
+      float* red = reinterpret_cast<float*>(stg);  // [128 threads][16]
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { red[e_col * 16 + q] = st1[q]; red[e_col * 16 + 8 + q] = st2[q]; }
+      ptx::named_bar_sync(1 + grp, 128);
+      // column c = 8 * group + q  <-  threads e with (e & 15) == group, e = group + 16 j
+      const int cgp = e_col >> 3, cq = e_col & 7;
+      double a = 0.0, b = 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a += (double)red[(cgp + 16 * j) * 16 + cq];
+        b += (double)red[(cgp + 16 * j) * 16 + 8 + cq];
+      }
+      if (it > 0) {
+        atomicAdd(p.stats + e_col, a);
+        atomicAdd(p.stats + p.stats_stride + e_col, b);
+      }
     }
   }
   ptx::tc_fence_before();
