@@ -248,28 +248,38 @@ def test_bf16_training_path_tracks_fp32_path(dev):
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_training_loop_reduces_the_loss(dev, precision):
-    """End to end: train-mode forward, focal loss, hand-written backward, fused clip + AdamW, repeated on one batch.
-    The loss on that batch must fall (dropout on, as configured)."""
+    """End to end: train-mode forward, fused focal loss, hand-written backward, fused clip + AdamW, repeated on one batch
+    at 264x the configured learning rate.  The loss on that batch must fall to < 0.6 of its start (dropout on).
+
+    The bf16 step is not bit-reproducible and at this learning rate the ratio has a heavy tail: 48 repeats
+    (scripts/gpu_train_loop_ratio.py) gave a median of 0.20 with 3 values above 0.6 - so the bf16 variant gets up to three
+    attempts from the same initial state (probability of three misses < 0.1 %); fp32 (0.15-0.30) gets one."""
     opts = PathOptions.tutorial()
-    torch.manual_seed(0)
-    net = NeutrinoDenseNetwork(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES, precision=precision).to(dev).train()
-    opt = training.TcvnAdamW(training.reference_param_groups(net, opts.l2_penalty), lr=2e-3, max_grad_norm=opts.gradient_clip)
     batch = synth.make_batch(8, seed=3, max_prongs=6).to(dev)
     g = torch.Generator().manual_seed(1)
     ev_t = torch.randint(0, NUM_EVENT_CLASSES, (8,), generator=g).to(dev)
     pr_t = torch.randint(0, NUM_PRONG_CLASSES, tuple(batch.prong_mask.shape), generator=g)
     pr_t[~batch.prong_mask.cpu()] = -1
     pr_t = pr_t.to(dev)
-    losses = []
-    for _ in range(25):
-        opt.zero_grad()
-        ev, pr = net.forward_sparse(batch)
-        loss = restate.training_loss(ev, pr, ev_t, pr_t, opts)
-        loss.backward()
-        opt.step()
-        losses.append(float(loss.detach()))
-    assert all(l == l for l in losses), losses            # no NaN
-    assert sum(losses[-5:]) / 5 < 0.6 * sum(losses[:3]) / 3, losses
+    history = []
+    for attempt in range(3 if precision == "bf16" else 1):
+        torch.manual_seed(0)
+        net = NeutrinoDenseNetwork(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES, precision=precision).to(dev).train()
+        opt = training.TcvnAdamW(training.reference_param_groups(net, opts.l2_penalty), lr=2e-3, max_grad_norm=opts.gradient_clip)
+        losses = []
+        for _ in range(25):
+            opt.zero_grad()
+            ev, pr = net.forward_sparse(batch)
+            loss = restate.training_loss(ev, pr, ev_t, pr_t, opts)
+            loss.backward()
+            opt.step()
+            losses.append(float(loss.detach()))
+        assert all(l == l for l in losses), losses            # no NaN
+        history.append(losses)
+        if sum(losses[-5:]) / 5 < 0.6 * sum(losses[:3]) / 3:
+            break
+    else:
+        raise AssertionError(history)
     # the eval path sees the trained weights and running buffers
     net.eval()
     with torch.no_grad():
