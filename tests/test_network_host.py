@@ -101,3 +101,22 @@ def test_sdxl_network_host_surface(tutorial_options):
     net.train()
     with pytest.raises(NotImplementedError):
         net(torch.zeros(1, 1, 1), torch.zeros(1, 1), z, torch.ones(1, 1, dtype=torch.bool), z, torch.ones(1, 1, dtype=torch.bool))
+
+
+def test_loss_metrics_and_prefetcher_fail_loudly_without_cuda(tutorial_options):
+    """The device-side loss / metrics / staging helpers have no CPU implementation either."""
+    import torch
+    from dune_transformercvn_b200 import loss as tloss
+    from dune_transformercvn_b200.ingest import Prefetcher
+    from dune_transformercvn_b200.lib import TcvnError
+    ev, pr = torch.zeros(2, 4), torch.zeros(2, 3, 8)
+    ev_t, pr_t = torch.zeros(2, dtype=torch.long), torch.zeros(2, 3, dtype=torch.long)
+    with pytest.raises(TcvnError):
+        tloss.training_loss(ev, pr, ev_t, pr_t, tutorial_options)
+    with pytest.raises(TcvnError):
+        tloss.DeviceMetrics().update(ev, pr, ev_t, pr_t)
+    with pytest.raises(TcvnError):
+        tloss.DeviceMetrics().compute()
+    with pytest.raises(TcvnError):
+        Prefetcher("cpu")
+    assert tloss.LOSS_FIELDS[:3] == ("train_loss", "event_loss", "prong_loss")
