@@ -116,27 +116,43 @@ def time_cpu_reference(sample_events: int, steps: int, warmup: int, seed: int):
     return sample_events / mean, mean * 1e3, cores, sample
 
 
+def workload_config(args, images: int, world: int) -> dict:
+    """The `config` object of the JSON line: identical in both arms (the reference arm times a bounded sample of it)."""
+    return {"workload": f"BASELINE configs[1]: eval inference, {args.events} events/GPU "
+                        f"({images} images of 3x400x280 on rank 0), P~U[1,10], occupancy 1%/0.2%",
+            "precision": args.precision, "parallelism": f"event-sharded x{world}, no collective",
+            "ingest": "densify kernel -> dense maps" if args.materialize else "hit lists consumed by the stem (no dense map)",
+            "l2": "activations touched per step (%.1f GB at ~16 MB/image) exceed the 126 MB L2" % (images * 16e6 / 1e9)}
+
+
+REFERENCE_SAMPLE_EVENTS = 8   # events of the workload one CPU step covers (~1.5 s on 16 cores): K + W steps stay within minutes
+
+
 def run_reference(args):
+    """The reference's own CPU implementation of the path (oracle port: the reference tree is absent on the GPU box), all
+    host threads, EXACTLY --steps timed steps after --warmup untimed ones; every step is a bounded sample
+    (REFERENCE_SAMPLE_EVENTS events, drawn with the workload's own generator and seed) of the configured workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_events = 8
-    steps = max(1, min(args.steps, 5))
-    warmup = 1 if args.warmup > 0 else 0
-    value, ms, cores, sample = time_cpu_reference(sample_events, steps, warmup, 1234)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    value, ms, cores, sample = time_cpu_reference(REFERENCE_SAMPLE_EVENTS, steps, warmup, 1234)
+    full = make_inputs(args.events, 1234)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"BASELINE configs[1]: eval inference, {args.events} events/GPU, P~U[1,10], 3x400x280",
-                       "note": "CPU arm runs a bounded sample per step"},
+            "config": workload_config(args, full.num_events + full.num_prongs, world),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
 
 
-def time_cpu_train(sample_events: int, steps: int, seed: int):
-    """Reference CPU training step (oracle port, fp32 torch autograd): forward + loss + backward."""
+def time_cpu_train(sample_events: int = 8, steps: int = 3, warmup: int = 1, seed: int = 1234):
+    """BASELINE configs[0] / SURVEY 8(d): the reference's CPU training step (oracle port, fp32 torch autograd) on the
+    tutorial config - 8 events x <= 10 prongs, train mode, dropout 0.1, forward + focal loss + backward, all host threads,
+    1 warm-up + 3 timed iterations, median."""
     from oracle import restate
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -148,16 +164,22 @@ def time_cpu_train(sample_events: int, steps: int, seed: int):
     pr_t[~batch.prong_mask] = -1
     st = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in state.items()}
     times = []
-    for i in range(steps + 1):
+    torch.manual_seed(seed)
+    for i in range(warmup + steps):
+        for v in st.values():
+            if v.is_floating_point():
+                v.grad = None
         t0 = time.perf_counter()
-        ev, pr = restate.sparse_forward(st, opts, batch, train=True)
+        ev, pr = restate.sparse_forward(st, opts, batch, train=True, p_drop=float(opts.dropout))
         restate.training_loss(ev, pr, ev_t, pr_t, opts).backward()
-        if i:
+        if i >= warmup:
             times.append(time.perf_counter() - t0)
-    mean = sum(times) / len(times)
-    return {"value": sample_events / mean, "unit": "events/s", "cores": cores, "kind": "port",
-            "sample": f"{sample_events} events / {sample_events + batch.num_prongs} images per step, train forward + loss + "
-                      f"backward (dropout = identity), fp32 torch CPU autograd, {steps} timed steps"}
+    times.sort()
+    med = times[len(times) // 2]
+    return {"value": sample_events / med, "unit": "events/s", "cores": cores, "kind": "port", "ms_per_step": med * 1e3,
+            "sample": f"BASELINE configs[0]: {sample_events} events / {sample_events + batch.num_prongs} images per step, train-mode "
+                      f"forward + focal loss + backward, dropout {opts.dropout}, fp32 torch CPU autograd, {warmup} warm-up + "
+                      f"{steps} timed steps, median"}
 
 
 def time_torch_eager_b200(dev, infer_events: int, train_events: int):
@@ -250,10 +272,12 @@ def single_event_latency(dev, precision, prongs=6, reps=50):
     return out
 
 
-def run_train_leg(args, dev, rank, world, timed, train_events, with_cpu):
+def run_train_leg(args, dev, rank, world, timed, train_events, with_cpu, fixed_prongs=None, label="BASELINE configs[2]"):
     """BASELINE configs[2]: DenseNet TransformerCVN training, event-sharded data parallel, NCCL gradient all-reduce.
-    One step = densify -> train-mode forward -> fused focal loss (tcvn_loss_forward) -> hand-written backward (gradient exchange issued from
-    inside it) -> fused clip + AdamW.  Every rank holds `--train-events` events (weak scaling)."""
+    One step = densify (+ pixel noise) -> train-mode forward -> fused focal loss (tcvn_loss_forward) -> hand-written backward
+    (gradient exchange issued from inside it, joined at its end) -> fused clip + AdamW.  Every rank holds `--train-events`
+    events (weak scaling) with the SAME total prong count (synth.balanced_prongs: the slowest rank sets the step, so
+    unequal work would measure the draw, not the path); `fixed_prongs` = every event has that many (configs[4]: 20)."""
     import torch.distributed as dist
     from dune_transformercvn_b200 import lib as tl
     from dune_transformercvn_b200 import loss as tloss
@@ -265,10 +289,17 @@ def run_train_leg(args, dev, rank, world, timed, train_events, with_cpu):
     if world > 1:   # same initial weights everywhere (the constructor is seeded, this is DDP's broadcast)
         net.train_engine.arena.ensure()
         dist.broadcast(net.train_engine.arena.flat, src=0)
-        net.train_engine.exchange = training.GradientExchange()
+        # nothing to install: TrainEngine averages the gradient arena over the ranks as soon as torch.distributed is up
     opt = training.TcvnAdamW(training.reference_param_groups(net, opts.l2_penalty), lr=opts.learning_rate,
                              max_grad_norm=opts.gradient_clip)
-    batch = make_inputs(train_events, 4321 + rank)
+    from dune_transformercvn_b200 import synth
+    if fixed_prongs is not None:
+        batch = synth.make_batch(train_events, seed=4321 + rank, fixed_prongs=fixed_prongs)
+    elif args.unbalanced:
+        batch = make_inputs(train_events, 4321 + rank)
+    else:
+        ppe = synth.balanced_prongs(train_events, 4321 + rank, max_prongs=10, total=int(round(train_events * 5.5)))
+        batch = synth.make_batch(train_events, seed=4321 + rank, prongs_per_event=ppe)
     g = torch.Generator().manual_seed(99 + rank)
     ev_t = torch.randint(0, NUM_EVENT_CLASSES, (train_events,), generator=g)
     pr_t = torch.randint(0, NUM_PRONG_CLASSES, tuple(batch.prong_mask.shape), generator=g)
@@ -301,24 +332,55 @@ def run_train_leg(args, dev, rank, world, timed, train_events, with_cpu):
     ms_e2e = timed(step_e2e, args.train_steps)
     loss_val = float(loss_host[0])
     images = batch.num_events + batch.num_prongs
-    ex = net.train_engine.exchange
+    ex = net.train_engine.exchange if isinstance(net.train_engine.exchange, training.GradientExchange) else None
+    dp = None
+    if world > 1:
+        # data-parallel correctness on the hardware: after a step every rank must hold the SAME averaged gradient and the
+        # SAME parameters (fp64 checksums of both arenas, all-gathered), and the averaged gradient must equal the mean of
+        # the ranks' local gradients (one extra step with the exchange suspended)
+        a = net.train_engine.arena
+        opt.zero_grad()
+        ev, pr = net.forward_sparse(resident)
+        loss, _ = tloss.training_loss(ev, pr, res_t[0], res_t[1], opts)
+        loss.backward()
+        g_avg = a.gflat.clone()
+        saved_ex, net.train_engine.exchange = net.train_engine.exchange, None
+        opt.zero_grad()
+        net.train_engine.step_index -= 1                   # same dropout masks as the step above
+        ev, pr = net.forward_sparse(resident)
+        loss, _ = tloss.training_loss(ev, pr, res_t[0], res_t[1], opts)
+        loss.backward()
+        net.train_engine.exchange = saved_ex
+        g_mean = a.gflat.clone()
+        dist.all_reduce(g_mean, op=dist.ReduceOp.SUM)
+        g_mean /= world
+        sums = torch.stack((g_avg.double().sum(), g_avg.double().abs().sum(), a.flat.double().sum(), a.flat.double().abs().sum()))
+        gathered = [torch.empty_like(sums) for _ in range(world)]
+        dist.all_gather(gathered, sums)
+        gathered = torch.stack(gathered)
+        dp = {"dp_grad_checksum_equal": bool((gathered[:, :2] == gathered[0, :2]).all()),
+              "dp_param_checksum_equal": bool((gathered[:, 2:] == gathered[0, 2:]).all()),
+              "dp_grad_vs_mean_of_local_rel_err": float((g_avg - g_mean).norm() / g_mean.norm().clamp_min(1e-30)),
+              "grad_checksum": float(gathered[0, 0]), "param_checksum": float(gathered[0, 2])}
     out = {"metric": "events/sec, training step (forward + loss + backward + gradient all-reduce + AdamW)",
            "value": world * train_events * args.train_steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
            "ms_per_step": ms / args.train_steps, "steps": args.train_steps, "scaling": "weak",
            "dtype": "f32" if args.train_precision == "fp32" else "bf16 (activations + tcgen05 GEMM operands; fp32 accumulation, parameters, statistics, gradients of parameters)",
-           "config": {"workload": f"BASELINE configs[2]: tutorial DenseNet TransformerCVN, {train_events} events/GPU "
-                                  f"({images} images on rank 0), dropout {opts.dropout}, AdamW + clip {opts.gradient_clip}",
-                      "parallelism": f"event-sharded x{world}, rank-local BatchNorm, NCCL all-reduce of the flat fp32 gradient "
-                                     f"arena in 4 slices issued from inside backward"},
+           "config": {"workload": f"{label}: tutorial DenseNet TransformerCVN, {train_events} events/GPU "
+                                  f"({images} images on rank 0; {'P = %d for every event' % fixed_prongs if fixed_prongs else ('P~U[1,10]' if args.unbalanced else 'P~U[1,10] with equal total per rank')}), "
+                                  f"dropout {opts.dropout}, pixel noise {opts.pixel_noise_std}, AdamW + clip {opts.gradient_clip}",
+                      "parallelism": f"event-sharded x{world}, rank-local BatchNorm (rank 0's running buffers broadcast before every "
+                                     f"forward like DDP), NCCL all-reduce (AVG) of the flat fp32 gradient arena in 4 slices issued from "
+                                     f"inside backward"},
            "e2e": {"value": world * train_events * args.train_steps / (ms_e2e / 1e3), "unit": UNIT,
                    "h2d_bytes_per_step": host.nbytes() + sum(t.numel() * t.element_size() for t in host_t),
                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.train_steps},
            "allreduce_bytes_per_step": 0 if ex is None else ex.bytes // max(1, (max(args.warmup, 3) + 2 * args.train_steps + 1)),
            "gpu_launches": launches, "images_per_s": world * images * args.train_steps / (ms / 1e3),
            "train_gflop_per_image": 14.39, "whole_net_tflops": images * 14.39e9 * args.train_steps / (ms / 1e3) / 1e12,
-           "final_loss": loss_val}
+           "final_loss": loss_val, "data_parallel_check": dp}
     if rank == 0 and world == 1 and with_cpu and not args.no_cpu_baseline:
-        out["cpu_baseline"] = time_cpu_train(2, 1, 4321)
+        out["cpu_baseline"] = time_cpu_train()
     del net, opt
     torch.cuda.empty_cache()
     return out
@@ -361,7 +423,9 @@ def kernel_rooflines(net, resident, batch, dev, pk, args):
         torch.cuda.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / reps
         if which == 1:
-            nbytes = rows * k * 2 + 128 * k * 2 + rows * 128 * 2
+            # algorithmic bytes = real pixels x (K in + 128 out) bf16 + the weights; the zero ring rows the layout adds are
+            # overhead, not algorithm (they show up in `traffic`)
+            nbytes = pixels * k * 2 + 128 * k * 2 + pixels * 128 * 2
             gbs = nbytes / (us * 1e-6) / 1e9
             out[name] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
                          "traffic": 757.5e6 * n / 194, "kernel": "umma_gemm_kernel<true> (BN+PReLU -> 1x1 conv -> BN+PReLU), "
@@ -417,7 +481,8 @@ def run_ours(args):
             ev = densify(b.event_values, b.event_coords, (H, W), batch.num_events, 255.0, out=ev_buf)
             pr = densify(b.prong_values, b.prong_coords, (H, W), batch.num_prongs, 255.0, out=pr_buf)
             return net(b.features, b.extra, ev, b.event_mask, pr, b.prong_mask)
-        return net.forward_sparse(b)  # same arithmetic, the stem reads the hit lists directly
+        # same arithmetic, the stem reads the hit lists directly; the ~200 launches of the step replayed as one CUDA graph
+        return net.forward_sparse(b, graph=not args.no_graph)
 
     from dune_transformercvn_b200.ingest import Prefetcher
     prefetch = Prefetcher(dev)
@@ -463,10 +528,26 @@ def run_ours(args):
         l0 = tl.load().tcvn_launch_count()
         ms = timed(lambda: step(resident), args.steps)
         launches_timed = tl.load().tcvn_launch_count() - l0
+        if launches_timed == 0:    # graph replay: the library's host-side counter does not tick; one replay = the captured launches
+            launches_timed = net.graph_launches_per_replay * args.steps
         sampler.stop_flag.set()
         for _ in range(2):
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps)
+        config5 = None
+        if not args.no_config5:
+            # BASELINE configs[4]: the 2023_08_07 JSON (batch 16 per GPU) at the maximum prong count (20), timed from the COO
+            # hit lists resident on the GPU: ingest (hit lists -> stem) + forward end to end
+            b5 = synth.make_batch(16, seed=555 + rank, fixed_prongs=20)
+            r5 = b5.to(dev)
+            for _ in range(3):
+                net.forward_sparse(r5, graph=not args.no_graph)
+            ms5 = timed(lambda: net.forward_sparse(r5, graph=not args.no_graph), args.steps)
+            config5 = {"workload": "BASELINE configs[4]: fdhd_beam_2018prod_2023_08_07.json, 16 events/GPU x 20 prongs "
+                                   f"({b5.num_events + b5.num_prongs} images), COO hits resident -> logits",
+                       "inference": {"value": world * 16 * args.steps / (ms5 / 1e3), "unit": UNIT, "ms_per_step": ms5 / args.steps,
+                                     "images_per_s": world * (b5.num_events + b5.num_prongs) * args.steps / (ms5 / 1e3)}}
+            del r5
     sampler.join(timeout=2)
     value = world * args.events * args.steps / (ms / 1e3)
     e2e_value = world * args.events * args.steps / (ms_e2e / 1e3)
@@ -475,6 +556,9 @@ def run_ours(args):
         train = run_train_leg(args, dev, rank, world, timed, args.train_events, True)
         if args.train_events_large > 0:
             train_large = run_train_leg(args, dev, rank, world, timed, args.train_events_large, False)
+        if config5 is not None:
+            t5 = run_train_leg(args, dev, rank, world, timed, 16, False, fixed_prongs=20, label="BASELINE configs[4]")
+            config5["training"] = {k: t5[k] for k in ("value", "unit", "ms_per_step", "images_per_s", "whole_net_tflops", "gpu_launches")}
     h2d = host.nbytes()
     d2h = sum(t.numel() * t.element_size() for t in out_host)
 
@@ -494,7 +578,7 @@ def run_ours(args):
     cpu = None
     eager = None
     if not args.no_cpu_baseline:
-        v, cms, cores, sample = time_cpu_reference(4, 2, 1, 1234)
+        v, cms, cores, sample = time_cpu_reference(REFERENCE_SAMPLE_EVENTS, 3, 1, 1234)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         if world == 1:
             try:
@@ -511,11 +595,7 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[1]: eval inference, {args.events} events/GPU "
-                                   f"({images} images of 3x400x280 on rank 0), P~U[1,10], occupancy 1%/0.2%",
-                       "precision": args.precision, "parallelism": f"event-sharded x{world}, no collective",
-                       "ingest": "densify kernel -> dense maps" if args.materialize else "hit lists consumed by the stem (no dense map)",
-                       "l2": "activations touched per step (%.1f GB at ~16 MB/image) exceed the 126 MB L2" % (images * 16e6 / 1e9)},
+            "config": workload_config(args, images, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps,
                     "pipeline": "every timed step copies one batch of hit lists from pinned host memory (copy stream, one batch "
@@ -523,6 +603,7 @@ def run_ours(args):
             "gpu_launches": launches, "images_per_s": value * images / args.events,
             "whole_net_tflops": tflops, "roofline": roofline, "rooflines_other": extra_rooflines,
             "cpu_baseline": cpu, "clocks": sampler.summary(), "train": train, "train_large_batch": train_large,
+            "config5_max_prongs": config5, "launch_mode": "kernel by kernel" if args.no_graph else "CUDA graph replay per batch shape",
             "torch_eager_b200": eager, "single_event_latency": single}
     emit(line)
     if world > 1:
@@ -563,7 +644,12 @@ def main():
     ap.add_argument("--train-events", type=int, default=16, help="events per GPU per training step (2023_08_07 JSON batch_size)")
     ap.add_argument("--train-events-large", type=int, default=64, help="second training measurement at a larger per-GPU batch "
                     "(SURVEY 8d: config 3 is also run at 64 events/GPU); 0 = skip")
-    ap.add_argument("--train-steps", type=int, default=5)
+    ap.add_argument("--train-steps", type=int, default=20)
+    ap.add_argument("--unbalanced", action="store_true", help="training: independent prong draws per rank (unequal work) "
+                    "instead of an equal total per rank")
+    ap.add_argument("--no-config5", action="store_true", help="skip the BASELINE configs[4] leg (16 events x 20 prongs)")
+    ap.add_argument("--no-graph", action="store_true", help="inference: launch the step kernel by kernel instead of replaying "
+                    "its CUDA graph")
     ap.add_argument("--train-precision", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--materialize", action="store_true", help="build the dense pixel maps (densify kernel) instead "
                     "of feeding the stem from the hit lists")

@@ -20,10 +20,22 @@ __device__ __forceinline__ int64_t lower_bound_image(const int32_t* __restrict__
   return lo;
 }
 
+// standard normal from a counter hash of (seed, element): two 24-bit uniforms -> Box-Muller
+__device__ __forceinline__ float hash_normal(unsigned long long seed, unsigned long long idx) {
+  unsigned long long z = seed * 0x100000001b3ull + idx + 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  z ^= z >> 31;
+  const float u1 = ((float)(unsigned)(z >> 40) + 1.0f) * (1.0f / 16777216.0f);        // (0, 1]
+  const float u2 = (float)(unsigned)((z >> 16) & 0xffffffu) * (1.0f / 16777216.0f);   // [0, 1)
+  return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
 template <typename V>
 __global__ void __launch_bounds__(256) densify_nchw_kernel(const int32_t* __restrict__ coords, const V* __restrict__ values,
                                                            int64_t nnz, int channels, int height, int width,
-                                                           int rows_per_band, float divisor, float* __restrict__ out) {
+                                                           int rows_per_band, float divisor, float noise_std,
+                                                           unsigned long long seed, float* __restrict__ out) {
   const int image = blockIdx.y;
   const int y0 = blockIdx.x * rows_per_band;
   const int y1 = min(height, y0 + rows_per_band);
@@ -55,6 +67,8 @@ __global__ void __launch_bounds__(256) densify_nchw_kernel(const int32_t* __rest
     for (int c = 0; c < channels; ++c) {
       float v = static_cast<float>(values[h * channels + c]);
       if (divisor != 0.f) v = __fdiv_rn(v, divisor);  // IEEE division, same bits as torch's v / 255.0
+      // training-time pixel noise of preprocess_pixels (:62-65): v *= 1 + randn * std, one draw per stored value
+      if (noise_std != 0.f) v *= 1.0f + hash_normal(seed, (unsigned long long)h * channels + c) * noise_std;
       dst[c * plane] = v;
     }
   }
@@ -65,7 +79,15 @@ __global__ void __launch_bounds__(256) densify_nchw_kernel(const int32_t* __rest
 extern "C" int tcvn_densify(const int32_t* coords, const void* values, tcvn_value_dtype value_dtype, int64_t nnz,
                             int channels, int n_images, int height, int width, float divisor, float* out,
                             tcvn_dense_layout layout, tcvn_stream_t stream) {
+  return tcvn_densify_noise(coords, values, value_dtype, nnz, channels, n_images, height, width, divisor, 0.f, 0, out, layout,
+                            stream);
+}
+
+extern "C" int tcvn_densify_noise(const int32_t* coords, const void* values, tcvn_value_dtype value_dtype, int64_t nnz,
+                                  int channels, int n_images, int height, int width, float divisor, float noise_std,
+                                  uint64_t seed, float* out, tcvn_dense_layout layout, tcvn_stream_t stream) {
   using namespace tcvn;
+  TCVN_CHECK_ARG(noise_std >= 0.f, "densify: negative noise_std");
   TCVN_CHECK_ARG(layout == TCVN_NCHW_F32, "densify: unknown layout %d", (int)layout);
   TCVN_CHECK_ARG(n_images >= 0 && channels > 0 && height > 0 && width > 0 && nnz >= 0, "densify: bad sizes");
   TCVN_CHECK_ARG(n_images <= 65535, "densify: more than 65535 images in one call");
@@ -80,10 +102,10 @@ extern "C" int tcvn_densify(const int32_t* coords, const void* values, tcvn_valu
   dim3 grid(bands, n_images);
   if (value_dtype == TCVN_VAL_F32)
     densify_nchw_kernel<float><<<grid, 256, 0, stream>>>(coords, static_cast<const float*>(values), nnz, channels,
-                                                         height, width, rows, divisor, out);
+                                                         height, width, rows, divisor, noise_std, seed, out);
   else if (value_dtype == TCVN_VAL_U8)
     densify_nchw_kernel<uint8_t><<<grid, 256, 0, stream>>>(coords, static_cast<const uint8_t*>(values), nnz, channels,
-                                                           height, width, rows, divisor, out);
+                                                           height, width, rows, divisor, noise_std, seed, out);
   else
     return fail(TCVN_ERR_ARG, "densify: unknown value dtype %d", (int)value_dtype);
   TCVN_LAUNCH_CHECK();

@@ -69,12 +69,18 @@ struct RepackList {
   int run(cudaStream_t st);
 };
 
-// train.cu: typed cores of the training primitives (bool *_bf16 = element type of that operand; false = fp32)
+// train.cu: typed cores of the training primitives (bool *_bf16 = element type of that operand; false = fp32).
+// Column reductions are bit-reproducible: per-slab partial sums in fixed slots, added in a fixed order.
+size_t colsum_parts_bytes();   // scratch for the partial sums of one reduction
 int colsums_typed(int mode, const void* X, bool x_bf16, int ldx, int xcol0, const void* D, bool d_bf16, int ldd, int dcol0,
                   const float* fold, int fold_stride, int C, long long m_total, int ring_hp, int ring_wp, double* out,
-                  int out_stride, cudaStream_t stream);
+                  int out_stride, double* parts, cudaStream_t stream);
 int colsums_into(int mode, const float* X, int ldx, int xcol0, const float* D, int ldd, int dcol0, const float* fold, int C,
-                 long long m_total, int ring_hp, int ring_wp, double* out, int out_stride, cudaStream_t stream);
+                 long long m_total, int ring_hp, int ring_wp, double* out, int out_stride, double* parts, cudaStream_t stream);
+// partial sums only: parts[slab][ns][C], ns = 2 / 3 / 1 for mode 0 / 1 / 2; the consumer adds the slabs
+int colsums_parts(int mode, const void* X, bool x_bf16, int ldx, int xcol0, const void* D, bool d_bf16, int ldd, int dcol0,
+                  const float* fold, int fold_stride, int C, long long m_total, int ring_hp, int ring_wp, double* parts,
+                  int* n_slabs, cudaStream_t stream);
 int bnact_bwd_apply_typed(const void* D, bool d_bf16, int ldd, int dcol0, const void* X, bool x_bf16, int ldx, int xcol0,
                           const float* fold, int fold_stride, const double* sums, int C, double count, void* dX, bool o_bf16,
                           int lddx, int dxcol0, bool accumulate, long long m_total, int ring_hp, int ring_wp,
@@ -87,11 +93,15 @@ int stem_conv_typed(const float* pixels, int n, int cin, int H, int W, const flo
                     const void* dz, bool dz_bf16, float* dw, cudaStream_t stream);
 int dropout_typed(void* X, bool bf16, int ld, int col0, int C, long long m_total, uint64_t seed, uint64_t stream_id, float p,
                   cudaStream_t stream);
-// BN1 backward with deferred mean corrections (train.cu): one pass O += sc * g and the three reductions into sums[3][C]
-int bn1_bwd_fused(const void* X, int ldx, const void* D, int ldd, const float* fold, int fold_stride, int C, float* O, int ldo,
-                  long long m_total, int ring_hp, int ring_wp, double* sums, cudaStream_t stream);
-int bn1_correct(float* G, int ldg, const void* X, int ldx, int C, long long m_total, int ring_hp, int ring_wp, const float* mean,
-                const float* rstd, const float* corrA, const float* corrB, cudaStream_t stream);
+// BN1 + PReLU1 backward reductions of a dense layer (train.cu): parts[slab][3][C]
+int bn1_bwd_reduce(const void* X, int ldx, const void* D, int ldd, const float* fold, int fold_stride, int C, long long m_total,
+                   int ring_hp, int ring_wp, double* parts, int* n_slabs, cudaStream_t stream);
+// train_stem.cu: the stem of the training path, hit-driven and bit-reproducible
+int stem_train_slots(int n_images, int H, int W);
+int stem_train_forward(const float* pixels, int n, int cin, int H, int W, const float* w0, const float* bias, int C, float* z0,
+                       double* stat_parts, int* n_slots, cudaStream_t stream);
+int stem_train_wgrad(const float* pixels, int n, int cin, int H, int W, const void* dz_bf16, int C, float* dw_parts, int* n_slots,
+                     cudaStream_t stream);
 int wgrad_typed(const void* A, bool a_bf16, int lda, long long m_total, int K, int taps, const int* tap_off, const float* a_scale,
                 const float* a_shift, const float* a_alpha, int a_ring_hp, int a_ring_wp, const void* G, bool g_bf16, int ldg,
                 int g_col0, int N, int g_ring_hp, int g_ring_wp, float* dW, cudaStream_t stream);

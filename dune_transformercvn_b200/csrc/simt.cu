@@ -8,6 +8,7 @@
 //   tail        :147-162  BN -> PReLU -> AdaptiveAvgPool2d(1) -> Linear -> BN1d -> PReLU
 // Eval mode: every BatchNorm is the affine map folded by pack.cu.
 #include "kernels.h"
+#include "stem.cuh"
 
 namespace tcvn {
 
@@ -161,47 +162,6 @@ int launch_simt_gemm(const GemmArgs& a, cudaStream_t stream) {
 // fixed, (3) applies bias/BN/PReLU in place and (4) average-pools 3x3/2 into the output rows.  For a
 // dense input this degrades gracefully to the full convolution (the list holds the whole window).
 // ------------------------------------------------------------------------------------------------
-constexpr int kStemTP = 8;                   // pooled tile edge
-constexpr int kStemTC = 2 * kStemTP + 1;     // 17 conv outputs per edge
-constexpr int kStemIn = 2 * kStemTC + 5;     // 39 input pixels per edge
-constexpr int kStemThreads = 512;            // (cy mod 4) x (cx mod 2) x 64 channels
-constexpr int kStemRows = kStemIn;           // window rows (pixels, all channels together)
-
-// Phases (2)-(4) of the stem for one tile, shared by the dense-window and the COO-direct kernels: scatter the
-// compacted hits, then bias+BN0+PReLU0 and AvgPool2d(3, 2) into the ringed block buffer.
-template <int C0, bool WGLOBAL>
-__device__ __forceinline__ void stem_scatter(const float* wsm, float* acc, const float4* hits, int nhits, int* touched, int cin,
-                                             int ch, int own_py, int own_px) {
-  // ---- (2) scatter every hit into the conv outputs it reaches (input yy = 2*cy + ky)
-  for (int h = 0; h < nhits; ++h) {
-    const float4 hit = hits[h];
-    const int code = __float_as_int(hit.x);
-    const int yy = code >> 6, xx = code & 63;
-    // the unique cy in [cy_lo, cy_lo + 4) with cy % 4 == own_py, cy_lo = max(0, ceil((yy - 6) / 2))
-    const int cy_lo = yy > 6 ? (yy - 5) >> 1 : 0;
-    const int cy = cy_lo + ((own_py - cy_lo) & 3);
-    const int ky = yy - 2 * cy;
-    if (cy > kStemTC - 1 || ky < 0) continue;   // ky <= 6 by construction
-    const int cx_lo = xx > 6 ? (xx - 5) >> 1 : 0;
-    const int cx_a = cx_lo + ((own_px - cx_lo) & 1);
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int cx = cx_a + 2 * k;
-      const int kx = xx - 2 * cx;
-      if (cx <= kStemTC - 1 && kx >= 0) {
-        const float* wp = wsm + (ky * 7 + kx) * C0 + ch;
-        float a = acc[(cy * kStemTC + cx) * C0 + ch];
-        // WGLOBAL: the 37.6 KB filter bank stays in global memory (L1-resident, read-only path) so that two CTAs fit an SM
-        a = fmaf(hit.y, WGLOBAL ? __ldg(wp) : wp[0], a);
-        if (cin > 1) a = fmaf(hit.z, WGLOBAL ? __ldg(wp + 49 * C0) : wp[49 * C0], a);
-        if (cin > 2) a = fmaf(hit.w, WGLOBAL ? __ldg(wp + 2 * 49 * C0) : wp[2 * 49 * C0], a);
-        acc[(cy * kStemTC + cx) * C0 + ch] = a;
-        if (ch == 0) touched[cy * kStemTC + cx] = 1;
-      }
-    }
-  }
-}
-
 template <typename TO, int C0>
 __device__ __forceinline__ void stem_pool(const float* acc, const int* touched, float sc, float sh, float al, int ch, int t, int n,
                                           int py0, int px0, TO* __restrict__ blk, int ldo, int Hb, int Wb) {

@@ -112,8 +112,10 @@ struct ColDev {
   const void* D; int ldd; int dcol0;
   const float* fold; int fold_stride; int C;
   long long m_total; int Hp, Wp; int rows_per_slab;
-  double* out;  // [nsums][out_stride]
-  int out_stride;
+  // slab (blockIdx.y) s writes its partial sum j of column c to dst[s * slot_stride + j * sum_stride + c] with a plain
+  // store: no atomics, so a fixed-order reduction over the slabs (parts_reduce_kernel, or fused into the consumer) makes
+  // every statistic bit-reproducible
+  double* dst; long long slot_stride; int sum_stride;
 };
 
 struct BnBwdDev {
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const ColDev p) {
     for (int j = 0; j < NS; ++j) {
       double s = 0.0;
       for (int r = 0; r < 8; ++r) s += red[r][lane_c][j];
-      atomicAdd(p.out + (size_t)j * p.out_stride + c, s);
+      p.dst[(size_t)blockIdx.y * p.slot_stride + (size_t)j * p.sum_stride + c] = s;
     }
   }
 }
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(256, 2) colsum_vec_kernel(const ColDev p, int 
       for (int i = 0; i < 8; ++i) {
         double s = 0.0;
         for (int r = 0; r < rpi; ++r) s += red[r * tv + vx][i];
-        atomicAdd(p.out + (size_t)j * p.out_stride + c + i, s);
+        p.dst[(size_t)blockIdx.y * p.slot_stride + (size_t)j * p.sum_stride + c + i] = s;
       }
     }
   }
@@ -402,23 +404,23 @@ __global__ void __launch_bounds__(256, 2) bnact_bwd_apply_vec_kernel(const BnBwd
 }
 
 // ------------------------------------------------------------------------------------------------
-// BN1 + PReLU1 backward of a dense layer with DEFERRED mean corrections (bf16 walk).  All BN1s of a block normalise
-// the same channels with the same statistics, so   d x = sum_i sc_i g_i  -  [sum_i sc_i mean(g_i)]  -  xhat [sum_i sc_i
-// mean(g_i xhat)]:  one pass per layer adds sc_i g_i to the fp32 gradient buffer AND reduces (sum g, sum g xhat,
-// sum dA min(y,0)); the two per-channel correction scalars are accumulated on the side and applied when a channel's
-// gradient is consumed.  Replaces the separate reduction pass + apply pass (X and D are read once instead of twice).
+// BN1 + PReLU1 backward of a dense layer (bf16 walk), reduction half.  All BN1s of a block normalise the same channels
+// with the same statistics, so   d x = sum_i sc_i g_i  -  [sum_i sc_i mean(g_i)]  -  xhat [sum_i sc_i mean(g_i xhat)]:
+// this pass only reduces (sum g, sum g xhat, sum dA min(y,0)) of layer i into per-slab partial sums; the products
+// sc_i g_i are never stored - the consumer of a channel's gradient (grad_pull_kernel, train_cnn.cu) re-derives them from
+// the layers' input gradients dA_i (bf16, kept per layer) and applies the two accumulated correction scalars.  Round 1
+// added sc_i g_i into an fp32 block gradient here: 8 of the 12 bytes per element of the most expensive backward pass.
 // ------------------------------------------------------------------------------------------------
 struct Bn1FusedDev {
   const __nv_bfloat16* X; int ldx;
   const __nv_bfloat16* D; int ldd;
   const float* fold; int fold_stride; int C;
-  float* O; int ldo;
   long long m_total; int Hp, Wp, rows_per_slab;
-  double* sums;   // [3][C]
+  double* parts;   // [slabs][3][C]
 };
 
-__global__ void __launch_bounds__(256, 2) bn1_bwd_fused_vec_kernel(const Bn1FusedDev p, int tv) {
-  constexpr int U = 2;
+__global__ void __launch_bounds__(256, 2) bn1_bwd_reduce_vec_kernel(const Bn1FusedDev p, int tv) {
+  constexpr int U = 4;
   __shared__ double red[256][8];
   const int rpi = 256 / tv;
   const int vx = threadIdx.x % tv, ry = threadIdx.x / tv;
@@ -443,7 +445,6 @@ __global__ void __launch_bounds__(256, 2) bn1_bwd_fused_vec_kernel(const Bn1Fuse
     int rr0 = rt.start(r_begin + ry);
     for (long long m0 = r_begin + ry; m0 < r_end; m0 += (long long)rpi * U) {
       Raw8<__nv_bfloat16> xr[U], dr[U];
-      Raw8<float> orr[U];
       bool ok[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -453,25 +454,21 @@ __global__ void __launch_bounds__(256, 2) bn1_bwd_fused_vec_kernel(const Bn1Fuse
         if (ok[u]) {
           ldraw(p.X + m * (long long)p.ldx + c, xr[u]);
           ldraw(p.D + m * (long long)p.ldd + c, dr[u]);
-          ldraw(p.O + m * (long long)p.ldo + c, orr[u]);
         }
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (!ok[u]) continue;
-        const long long m = m0 + (long long)u * rpi;
-        float x[8], d[8], o[8];
-        unpack8(xr[u], x); unpack8(dr[u], d); unpack8(orr[u], o);
+        float x[8], d[8];
+        unpack8(xr[u], x); unpack8(dr[u], d);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float y = fmaf(x[i], sc[i], sh[i]);
           const float g = y >= 0.f ? d[i] : d[i] * al[i];
-          o[i] = fmaf(sc[i], g, o[i]);
           part[0][i] += g;
           part[1][i] = fmaf(g, (x[i] - mean[i]) * rstd[i], part[1][i]);
           part[2][i] = fmaf(d[i], fminf(y, 0.f), part[2][i]);
         }
-        st8<float>(p.O + m * (long long)p.ldo + c, o);
       }
     }
   }
@@ -486,29 +483,31 @@ __global__ void __launch_bounds__(256, 2) bn1_bwd_fused_vec_kernel(const Bn1Fuse
       for (int i = 0; i < 8; ++i) {
         double sum = 0.0;
         for (int r = 0; r < rpi; ++r) sum += red[r * tv + vx][i];
-        atomicAdd(p.sums + (size_t)j * p.C + c + i, sum);
+        p.parts[((size_t)blockIdx.y * 3 + j) * p.C + c + i] = sum;
       }
     }
   }
 }
 
-// gradient of channels [0, C) made final: g -= corrA + xhat * corrB on interior rows (in place, fp32)
-__global__ void __launch_bounds__(256) bn1_correct_vec_kernel(float* __restrict__ G, int ldg, const __nv_bfloat16* __restrict__ X,
-                                                             int ldx, int C, long long m_total, int Hp, int Wp,
-                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                             const float* __restrict__ corrA, const float* __restrict__ corrB) {
-  const int cv = C / 8;
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= m_total * cv) return;
-  const int c = (int)(idx % cv) * 8;
-  const long long m = idx / cv;
-  if (is_ring(m, Hp, Wp)) return;
-  float g[8], x[8];
-  ld8<float>(G + m * (long long)ldg + c, g);
-  ld8<__nv_bfloat16>(X + m * (long long)ldx + c, x);
+// out[j * out_stride + c] = sum over the slots of parts[slot][j][c], slots added in a fixed order: a block owns 16 columns,
+// its 16 slices each add every 16th slot (128-byte coalesced reads), then the slice sums are added in order
+__global__ void __launch_bounds__(256) parts_reduce_kernel(const double* __restrict__ parts, int n_slots, int ns, int C,
+                                                           double* __restrict__ out, int out_stride) {
+  __shared__ double red[16][17];
+  const int col = threadIdx.x & 15, slice = threadIdx.x >> 4;
+  const int q = blockIdx.x * 16 + col;   // flattened (sum j, column c)
+  const int total = ns * C;
+  double acc = 0.0;
+  if (q < total)
+    for (int s = slice; s < n_slots; s += 16) acc += parts[(size_t)s * total + q];
+  red[slice][col] = acc;
+  __syncthreads();
+  if (slice == 0 && q < total) {
+    double t = 0.0;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) g[i] -= corrA[c + i] + (x[i] - mean[c + i]) * rstd[c + i] * corrB[c + i];
-  st8<float>(G + m * (long long)ldg + c, g);
+    for (int k = 0; k < 16; ++k) t += red[k][col];
+    out[(size_t)(q / C) * out_stride + q % C] = t;
+  }
 }
 
 template <typename TX, typename TO>
@@ -840,16 +839,17 @@ static int slabs_for(long long rows, int* rows_per_slab) {
   return (int)ceil_div_ll(rows, *rows_per_slab);
 }
 
-// column sums ACCUMULATED into out[j * out_stride + c] (the caller zeroes it): the walker keeps one (sum, sum^2)
-// table per concat buffer and adds each layer's 32 new channels to it.  x_bf16 / d_bf16: element types of X / D.
-int colsums_typed(int mode, const void* X, bool x_bf16, int ldx, int xcol0, const void* D, bool d_bf16, int ldd, int dcol0,
-                  const float* fold, int fold_stride, int C, long long m_total, int ring_hp, int ring_wp, double* out,
-                  int out_stride, cudaStream_t stream) {
-  if (m_total <= 0 || C <= 0) return TCVN_OK;
+static inline int colsum_ns_of(int mode) { return mode == 0 ? 2 : (mode == 1 ? 3 : 1); }
+
+// per-slab partial column sums: dst[slab * slot_stride + j * sum_stride + c]; *n_slabs = slabs written.
+// one_slab forces a single slab (the result is then final).  x_bf16 / d_bf16: element types of X / D.
+static int colsums_launch(int mode, const void* X, bool x_bf16, int ldx, int xcol0, const void* D, bool d_bf16, int ldd, int dcol0,
+                          const float* fold, int fold_stride, int C, long long m_total, int ring_hp, int ring_wp, double* dst,
+                          long long slot_stride, int sum_stride, bool one_slab, int* n_slabs, cudaStream_t stream) {
   ColDev p{};
   p.X = X; p.ldx = ldx; p.xcol0 = xcol0; p.D = D; p.ldd = ldd; p.dcol0 = dcol0; p.fold = fold; p.fold_stride = fold_stride;
-  p.C = C; p.m_total = m_total; p.Hp = ring_hp; p.Wp = ring_wp; p.out = out; p.out_stride = out_stride;
-  const int slabs = slabs_for(m_total, &p.rows_per_slab);
+  p.C = C; p.m_total = m_total; p.Hp = ring_hp; p.Wp = ring_wp; p.dst = dst; p.slot_stride = slot_stride; p.sum_stride = sum_stride;
+  int slabs = slabs_for(m_total, &p.rows_per_slab);
   typedef __nv_bfloat16 bf;
   const bool vec = C % 8 == 0 && ldx % 8 == 0 && xcol0 % 8 == 0 && (mode != 1 || (ldd % 8 == 0 && dcol0 % 8 == 0)) &&
                    reinterpret_cast<uintptr_t>(X) % 32 == 0 && (mode != 1 || reinterpret_cast<uintptr_t>(D) % 32 == 0);
@@ -858,12 +858,14 @@ int colsums_typed(int mode, const void* X, bool x_bf16, int ldx, int xcol0, cons
     const int tv = cv < 32 ? cv : 32;
     const int rpi = 256 / tv;
     const int gx = ceil_div(cv, tv);
-    // short slabs: one slab = 16 row-steps of a CTA (<= 64 rows per thread), at most ~16 CTAs per SM in total
+    // short slabs: one slab = 16 row-steps of a CTA, at most ~4 CTAs per SM in total
     long long vslabs = ceil_div_ll(m_total, (long long)rpi * kVecU * 4);
     const long long cap = (long long)(148 * 4 / gx > 1 ? 148 * 4 / gx : 1);
     if (vslabs > cap) vslabs = cap;
+    if (one_slab) vslabs = 1;
     p.rows_per_slab = (int)ceil_div_ll(m_total, vslabs);
     vslabs = ceil_div_ll(m_total, p.rows_per_slab);
+    *n_slabs = (int)vslabs;
     dim3 vgrid(gx, (unsigned)vslabs);
 #define TCVN_COLSUM_V(MODE)                                                                              \
   do {                                                                                                   \
@@ -879,6 +881,14 @@ int colsums_typed(int mode, const void* X, bool x_bf16, int ldx, int xcol0, cons
     TCVN_LAUNCH_CHECK();
     return TCVN_OK;
   }
+  {
+    const long long cap = (long long)592 * 3 * 256 / ((long long)colsum_ns_of(mode) * C);   // capacity of the parts scratch
+    if (slabs > cap) slabs = (int)(cap < 1 ? 1 : cap);
+    if (one_slab) slabs = 1;
+    p.rows_per_slab = (int)ceil_div_ll(m_total, slabs);
+    slabs = (int)ceil_div_ll(m_total, p.rows_per_slab);
+  }
+  *n_slabs = slabs;
   dim3 grid(ceil_div(C, 32), slabs);
 #define TCVN_COLSUM(MODE)                                                                          \
   do {                                                                                             \
@@ -895,10 +905,47 @@ int colsums_typed(int mode, const void* X, bool x_bf16, int ldx, int xcol0, cons
   return TCVN_OK;
 }
 
+static inline int colsum_ns(int mode) { return colsum_ns_of(mode); }
+
+size_t colsum_parts_bytes() { return (size_t)592 * 3 * 256 * sizeof(double) + 4096; }
+
+// per-slab partial sums only: parts[slab][ns][C] (the consumer adds the slabs in a fixed order)
+int colsums_parts(int mode, const void* X, bool x_bf16, int ldx, int xcol0, const void* D, bool d_bf16, int ldd, int dcol0,
+                  const float* fold, int fold_stride, int C, long long m_total, int ring_hp, int ring_wp, double* parts,
+                  int* n_slabs, cudaStream_t stream) {
+  *n_slabs = 0;
+  if (m_total <= 0 || C <= 0) return TCVN_OK;
+  return colsums_launch(mode, X, x_bf16, ldx, xcol0, D, d_bf16, ldd, dcol0, fold, fold_stride, C, m_total, ring_hp, ring_wp, parts,
+                        (long long)colsum_ns(mode) * C, C, false, n_slabs, stream);
+}
+
+// column sums ASSIGNED to out[j * out_stride + c], bit-reproducible: per-slab partial sums in `parts` (scratch of
+// colsum_parts_bytes()) added in a fixed order; parts == nullptr -> one slab writing the result directly (small inputs /
+// test hooks).
+int colsums_typed(int mode, const void* X, bool x_bf16, int ldx, int xcol0, const void* D, bool d_bf16, int ldd, int dcol0,
+                  const float* fold, int fold_stride, int C, long long m_total, int ring_hp, int ring_wp, double* out,
+                  int out_stride, double* parts, cudaStream_t stream) {
+  if (C <= 0) return TCVN_OK;
+  const int ns = colsum_ns(mode);
+  if (m_total <= 0) {
+    for (int j = 0; j < ns; ++j) TCVN_CUDA(cudaMemsetAsync(out + (size_t)j * out_stride, 0, sizeof(double) * C, stream));
+    return TCVN_OK;
+  }
+  int slabs = 0;
+  if (parts == nullptr)
+    return colsums_launch(mode, X, x_bf16, ldx, xcol0, D, d_bf16, ldd, dcol0, fold, fold_stride, C, m_total, ring_hp, ring_wp, out,
+                          0, out_stride, true, &slabs, stream);
+  TCVN_TRY(colsums_launch(mode, X, x_bf16, ldx, xcol0, D, d_bf16, ldd, dcol0, fold, fold_stride, C, m_total, ring_hp, ring_wp,
+                          parts, (long long)ns * C, C, false, &slabs, stream));
+  parts_reduce_kernel<<<ceil_div(ns * C, 16), 256, 0, stream>>>(parts, slabs, ns, C, out, out_stride);
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
 int colsums_into(int mode, const float* X, int ldx, int xcol0, const float* D, int ldd, int dcol0, const float* fold, int C,
-                 long long m_total, int ring_hp, int ring_wp, double* out, int out_stride, cudaStream_t stream) {
+                 long long m_total, int ring_hp, int ring_wp, double* out, int out_stride, double* parts, cudaStream_t stream) {
   return colsums_typed(mode, X, false, ldx, xcol0, D, false, ldd, dcol0, fold, C, C, m_total, ring_hp, ring_wp, out, out_stride,
-                       stream);
+                       parts, stream);
 }
 
 // dX (+)= BN + PReLU backward of D at X (elementwise half); types: 0 = fp32, 1 = bf16
@@ -1011,36 +1058,28 @@ int pool_typed(int kind, const void* src, const float* fold, void* dst, bool bf1
   return TCVN_OK;
 }
 
-int bn1_bwd_fused(const void* X, int ldx, const void* D, int ldd, const float* fold, int fold_stride, int C, float* O, int ldo,
-                  long long m_total, int ring_hp, int ring_wp, double* sums, cudaStream_t stream) {
+// BN1 + PReLU1 backward reductions of a dense layer: parts[slab][3][C] (sum g, sum g xhat, sum dA min(y,0))
+int bn1_bwd_reduce(const void* X, int ldx, const void* D, int ldd, const float* fold, int fold_stride, int C, long long m_total,
+                   int ring_hp, int ring_wp, double* parts, int* n_slabs, cudaStream_t stream) {
+  *n_slabs = 0;
   if (m_total <= 0 || C <= 0) return TCVN_OK;
-  if (C % 8 || ldx % 8 || ldd % 8 || ldo % 8) return fail(TCVN_ERR_UNSUPPORTED, "bn1_bwd_fused: widths must be multiples of 8");
+  if (C % 8 || ldx % 8 || ldd % 8) return fail(TCVN_ERR_UNSUPPORTED, "bn1_bwd_reduce: widths must be multiples of 8");
   Bn1FusedDev p{};
   p.X = static_cast<const __nv_bfloat16*>(X); p.ldx = ldx; p.D = static_cast<const __nv_bfloat16*>(D); p.ldd = ldd;
-  p.fold = fold; p.fold_stride = fold_stride; p.C = C; p.O = O; p.ldo = ldo; p.m_total = m_total; p.Hp = ring_hp; p.Wp = ring_wp;
-  p.sums = sums;
+  p.fold = fold; p.fold_stride = fold_stride; p.C = C; p.m_total = m_total; p.Hp = ring_hp; p.Wp = ring_wp;
+  p.parts = parts;
   const int cv = C / 8;
   const int tv = cv < 32 ? cv : 32;
   const int rpi = 256 / tv;
   const int gx = ceil_div(cv, tv);
-  long long vslabs = ceil_div_ll(m_total, (long long)rpi * 2 * 4);
+  long long vslabs = ceil_div_ll(m_total, (long long)rpi * 4 * 4);
   const long long cap = (long long)(148 * 4 / gx > 1 ? 148 * 4 / gx : 1);
   if (vslabs > cap) vslabs = cap;
   p.rows_per_slab = (int)ceil_div_ll(m_total, vslabs);
   vslabs = ceil_div_ll(m_total, p.rows_per_slab);
+  *n_slabs = (int)vslabs;
   dim3 grid(gx, (unsigned)vslabs);
-  bn1_bwd_fused_vec_kernel<<<grid, 256, 0, stream>>>(p, tv);
-  TCVN_LAUNCH_CHECK();
-  return TCVN_OK;
-}
-
-int bn1_correct(float* G, int ldg, const void* X, int ldx, int C, long long m_total, int ring_hp, int ring_wp, const float* mean,
-                const float* rstd, const float* corrA, const float* corrB, cudaStream_t stream) {
-  if (m_total <= 0 || C <= 0) return TCVN_OK;
-  if (C % 8 || ldx % 8 || ldg % 8) return fail(TCVN_ERR_UNSUPPORTED, "bn1_correct: widths must be multiples of 8");
-  const unsigned grid = (unsigned)ceil_div_ll(m_total * (C / 8), 256);
-  bn1_correct_vec_kernel<<<grid, 256, 0, stream>>>(G, ldg, static_cast<const __nv_bfloat16*>(X), ldx, C, m_total, ring_hp, ring_wp,
-                                                  mean, rstd, corrA, corrB);
+  bn1_bwd_reduce_vec_kernel<<<grid, 256, 0, stream>>>(p, tv);
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
 }
@@ -1087,7 +1126,11 @@ int wgrad_typed(const void* A, bool a_bf16, int lda, long long m_total, int K, i
   g.a_ring_Hp = a_ring_hp; g.a_ring_Wp = a_ring_wp;
   g.G = G; g.ldg = ldg; g.g_col0 = g_col0; g.N = N; g.g_ring_Hp = g_ring_hp; g.g_ring_Wp = g_ring_wp;
   g.dW = dW;
-  const int slabs = slabs_for(m_total, &g.rows_per_slab);
+  int slabs = slabs_for(m_total, &g.rows_per_slab);
+  // up to 4096 rows (the sequence part, the CNN tail: every use of the bf16 walk) one CTA owns a result tile and walks all
+  // rows: a single writer per element, bit-reproducible.  Larger inputs (fp32 parity walk only) split the rows and add with
+  // float atomics.
+  if (m_total <= 4096) { slabs = 1; g.rows_per_slab = (int)m_total; }
   dim3 grid(ceil_div(K, kWgK), ceil_div(N, kWgN) * taps, slabs);
   typedef __nv_bfloat16 bf;
   if (!a_bf16 && !g_bf16) wgrad_kernel<float, float><<<grid, 256, 0, stream>>>(g);
@@ -1109,14 +1152,12 @@ extern "C" int tcvn_t_wgrad(const float* A, int lda, int64_t m_total, int K, int
 }
 
 // mode 0: sums[2][C] = (sum x, sum x^2); mode 1: sums[3][C] BN+PReLU backward reductions; mode 2: sums[1][C] = sum x.
-// sums is zeroed first.
+// sums is overwritten (one slab of rows per column block: bit-reproducible, meant for tests and small inputs).
 extern "C" int tcvn_t_colsums(int mode, const float* X, int ldx, int xcol0, const float* D, int ldd, int dcol0,
                               const float* fold, int C, int64_t m_total, int ring_hp, int ring_wp, double* sums,
                               tcvn_stream_t stream) {
   TCVN_CHECK_ARG(X && sums && mode >= 0 && mode <= 2 && (mode != 1 || (D && fold)), "t_colsums: bad arguments");
-  const int ns = mode == 0 ? 2 : (mode == 1 ? 3 : 1);
-  TCVN_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * ns * C, stream));
-  return colsums_into(mode, X, ldx, xcol0, D, ldd, dcol0, fold, C, m_total, ring_hp, ring_wp, sums, C, stream);
+  return colsums_into(mode, X, ldx, xcol0, D, ldd, dcol0, fold, C, m_total, ring_hp, ring_wp, sums, C, nullptr, stream);
 }
 
 extern "C" int tcvn_t_bn_finalize(const double* sums, int C, double count, const float* gamma, const float* beta,
@@ -1214,7 +1255,11 @@ extern "C" int tcvn_t_stem_conv(const float* pixels, int n, int cin, int H, int 
 // ------------------------------------------------------------------------------------------------
 namespace tcvn {
 
-__global__ void sumsq_kernel(const float* __restrict__ x, long long n, double* __restrict__ out) {
+constexpr int kMaxOptGroups = 4;
+constexpr int kSumsqBlocksMax = 148 * 8;
+
+// sum of squares, stage 1: one partial sum per block in its own slot (no atomics: the clip factor is bit-reproducible)
+__global__ void __launch_bounds__(256) sumsq_parts_kernel(const float* __restrict__ x, long long n, double* __restrict__ parts) {
   double acc = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const double v = x[i];
@@ -1227,60 +1272,94 @@ __global__ void sumsq_kernel(const float* __restrict__ x, long long n, double* _
     if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
     __syncthreads();
   }
-  if (threadIdx.x == 0) atomicAdd(out, red[0]);
+  if (threadIdx.x == 0) parts[blockIdx.x] = red[0];
 }
 
-__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                             long long n, float lr, float beta1, float beta2, float eps, float weight_decay, float bc1,
-                             float bc2_sqrt, const double* __restrict__ gnorm_sq, float max_norm, float grad_mul,
-                             const uint8_t* __restrict__ select, int select_id) {
-  float clip = grad_mul;
-  if (gnorm_sq != nullptr && max_norm > 0.f) {
-    const float norm = (float)sqrt(*gnorm_sq) * grad_mul;
-    const float coef = max_norm / (norm + 1e-6f);
+struct AdamGroup { float lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt; };
+struct AdamArgs {
+  float* p; const float* g; float* m; float* v; long long n;
+  const uint8_t* select;          // per element: 0 = not optimised, k = group k-1
+  int n_groups; AdamGroup grp[kMaxOptGroups];
+  const double* gnorm_parts; int n_parts;   // stage-1 partial sums of the squared gradient norm (nullptr: no clipping)
+  float max_norm, grad_mul;
+  double* gnorm_out;              // optional: the total norm squared, written by block 0
+};
+
+// every parameter group in ONE pass over the arenas; each block first adds the norm partials in the same fixed order
+__global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamArgs a) {
+  float clip = a.grad_mul;
+  if (a.gnorm_parts != nullptr && a.max_norm > 0.f) {
+    __shared__ double red[256];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < a.n_parts; i += 256) acc += a.gnorm_parts[i];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+      if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+      __syncthreads();
+    }
+    const double total = red[0];
+    if (a.gnorm_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *a.gnorm_out = total;
+    const float norm = (float)sqrt(total) * a.grad_mul;
+    const float coef = a.max_norm / (norm + 1e-6f);
     if (coef < 1.f) clip *= coef;
   }
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    if (select != nullptr && select[i] != select_id) continue;
-    const float grad = g[i] * clip;
-    float w = p[i] * (1.f - lr * weight_decay);
-    const float mi = beta1 * m[i] + (1.f - beta1) * grad;
-    const float vi = beta2 * v[i] + (1.f - beta2) * grad * grad;
-    m[i] = mi;
-    v[i] = vi;
-    const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    w -= (lr / bc1) * (mi / denom);
-    p[i] = w;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
+    const int gi = a.select != nullptr ? (int)a.select[i] : 1;
+    if (gi == 0 || gi > a.n_groups) continue;
+    const AdamGroup& h = a.grp[gi - 1];
+    const float grad = a.g[i] * clip;
+    float w = a.p[i] * (1.f - h.lr * h.weight_decay);
+    const float mi = h.beta1 * a.m[i] + (1.f - h.beta1) * grad;
+    const float vi = h.beta2 * a.v[i] + (1.f - h.beta2) * grad * grad;
+    a.m[i] = mi;
+    a.v[i] = vi;
+    const float denom = sqrtf(vi) / h.bc2_sqrt + h.eps;
+    w -= (h.lr / h.bc1) * (mi / denom);
+    a.p[i] = w;
   }
 }
 
 }  // namespace tcvn
 
-extern "C" int tcvn_sumsq(const float* x, int64_t n, double* out, int zero_first, tcvn_stream_t stream) {
-  TCVN_CHECK_ARG(x && out && n >= 0, "sumsq: bad arguments");
-  if (zero_first) TCVN_CUDA(cudaMemsetAsync(out, 0, sizeof(double), stream));
-  if (n == 0) return TCVN_OK;
-  int blocks = (int)tcvn::ceil_div_ll(n, 256 * 8);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  tcvn::sumsq_kernel<<<blocks, 256, 0, stream>>>(x, n, out);
-  TCVN_LAUNCH_CHECK();
-  return TCVN_OK;
-}
+extern "C" size_t tcvn_adamw_workspace_bytes(void) { return (size_t)(tcvn::kSumsqBlocksMax + 1) * sizeof(double); }
 
-extern "C" int tcvn_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr,
-                               double beta1, double beta2, double eps, double weight_decay, int64_t step,
-                               const double* gnorm_sq, float max_norm, float grad_mul, const uint8_t* select, int select_id,
-                               tcvn_stream_t stream) {
-  TCVN_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && n >= 0 && step >= 1, "adamw_step: bad arguments");
+// One optimizer step over the flat arenas: every parameter group (select[i] = group + 1, 0 = element not optimised) in one
+// launch, preceded - when max_norm > 0 - by the global gradient-norm reduction for Lightning's gradient_clip_val.
+// workspace: tcvn_adamw_workspace_bytes(); its last double receives the squared gradient norm.
+extern "C" int tcvn_adamw_fused(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
+                                const uint8_t* select, int n_groups, const double* lr, const double* beta1, const double* beta2,
+                                const double* eps, const double* weight_decay, const int64_t* step, float max_norm,
+                                float grad_mul, void* workspace, size_t workspace_bytes, tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && n >= 0 && lr && beta1 && beta2 && eps && weight_decay && step,
+                 "adamw_fused: null pointer");
+  TCVN_CHECK_ARG(n_groups >= 1 && n_groups <= tcvn::kMaxOptGroups, "adamw_fused: 1..%d parameter groups (got %d)",
+                 tcvn::kMaxOptGroups, n_groups);
+  TCVN_CHECK_ARG(n_groups == 1 || select, "adamw_fused: several groups need the per-element selector");
   if (n == 0) return TCVN_OK;
-  // bias corrections in double on the host, like torch.optim.AdamW's Python scalars
-  const float bc1 = (float)(1.0 - pow(beta1, (double)step));
-  const float bc2_sqrt = (float)sqrt(1.0 - pow(beta2, (double)step));
+  tcvn::AdamArgs a{};
+  a.p = params; a.g = grads; a.m = exp_avg; a.v = exp_avg_sq; a.n = n; a.select = select; a.n_groups = n_groups;
+  for (int k = 0; k < n_groups; ++k) {
+    TCVN_CHECK_ARG(step[k] >= 1, "adamw_fused: step must be >= 1");
+    // bias corrections in double on the host, like torch.optim.AdamW's Python scalars
+    a.grp[k].lr = (float)lr[k]; a.grp[k].beta1 = (float)beta1[k]; a.grp[k].beta2 = (float)beta2[k];
+    a.grp[k].eps = (float)eps[k]; a.grp[k].weight_decay = (float)weight_decay[k];
+    a.grp[k].bc1 = (float)(1.0 - pow(beta1[k], (double)step[k]));
+    a.grp[k].bc2_sqrt = (float)sqrt(1.0 - pow(beta2[k], (double)step[k]));
+  }
+  a.max_norm = max_norm; a.grad_mul = grad_mul;
+  if (max_norm > 0.f) {
+    TCVN_CHECK_ARG(workspace && workspace_bytes >= tcvn_adamw_workspace_bytes(), "adamw_fused: workspace too small for the norm");
+    double* parts = static_cast<double*>(workspace);
+    int blocks = (int)tcvn::ceil_div_ll(n, 256 * 8);
+    if (blocks > tcvn::kSumsqBlocksMax) blocks = tcvn::kSumsqBlocksMax;
+    tcvn::sumsq_parts_kernel<<<blocks, 256, 0, stream>>>(grads, n, parts);
+    TCVN_LAUNCH_CHECK();
+    a.gnorm_parts = parts; a.n_parts = blocks; a.gnorm_out = parts + tcvn::kSumsqBlocksMax;
+  }
   int blocks = (int)tcvn::ceil_div_ll(n, 256 * 4);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  tcvn::adamw_kernel<<<blocks, 256, 0, stream>>>(params, grads, exp_avg, exp_avg_sq, n, (float)lr, (float)beta1, (float)beta2,
-                                                  (float)eps, (float)weight_decay, bc1, bc2_sqrt, gnorm_sq, max_norm, grad_mul,
-                                                  select, select_id);
+  tcvn::adamw_multi_kernel<<<blocks, 256, 0, stream>>>(a);
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
 }

@@ -40,7 +40,7 @@ struct TrainPlan {
   int n;
   size_t w0, z0, fold0, fold_f, gap, dgap, lin, fold_o, lw, lwt;
   std::vector<TBlock> blocks;
-  size_t sA, sB, dmid, sums_scr, dwp;
+  size_t sA, sB, dmid, sums_scr, dwp, dparts;
   size_t bytes;
 
   static bool build(const tcvn_cnn_desc& d, int n, TrainPlan* T) {
@@ -107,6 +107,7 @@ struct TrainPlan {
     T->dmid = take(max_rows_mid);
     T->sums_scr = take(2 * 3 * (size_t)max_c);  // doubles
     T->dwp = take(max_dw);
+    T->dparts = take(colsum_parts_bytes() / 4);
     T->bytes = w;
     return true;
   }
@@ -215,13 +216,11 @@ struct TWalk {
   }
 
   int stats_scratch(const float* X, int ldx, int col0, int C, long long rows, int hp, int wp) {
-    TCVN_CUDA(cudaMemsetAsync(dbl(T.sums_scr), 0, sizeof(double) * 2 * C, st));
-    return colsums_into(0, X, ldx, col0, nullptr, 0, 0, nullptr, C, rows, hp, wp, dbl(T.sums_scr), C, st);
+    return colsums_into(0, X, ldx, col0, nullptr, 0, 0, nullptr, C, rows, hp, wp, dbl(T.sums_scr), C, dbl(T.dparts), st);
   }
 
   int bias_grad(const float* G, int ldg, int col0, int C, long long rows, int hp, int wp, float* dst) {
-    TCVN_CUDA(cudaMemsetAsync(dbl(T.sums_scr), 0, sizeof(double) * C, st));
-    TCVN_TRY(colsums_into(2, G, ldg, col0, nullptr, 0, 0, nullptr, C, rows, hp, wp, dbl(T.sums_scr), C, st));
+    TCVN_TRY(colsums_into(2, G, ldg, col0, nullptr, 0, 0, nullptr, C, rows, hp, wp, dbl(T.sums_scr), C, dbl(T.dparts), st));
     add_sums_kernel<<<ceil_div(C, 128), 128, 0, st>>>(dbl(T.sums_scr), C, dst);
     TCVN_LAUNCH_CHECK();
     return TCVN_OK;
@@ -231,8 +230,7 @@ struct TWalk {
   int bn_bwd(const float* X, int ldx, const float* D, int ldd, const float* fold, int C, double count, long long rows, int hp,
              int wp, float* dX, int lddx, bool accumulate, const BnArena& bn, int c0, int c0p) {
     double* s = dbl(T.sums_scr);
-    TCVN_CUDA(cudaMemsetAsync(s, 0, sizeof(double) * 3 * C, st));
-    TCVN_TRY(colsums_into(1, X, ldx, 0, D, ldd, 0, fold, C, rows, hp, wp, s, C, st));
+    TCVN_TRY(colsums_into(1, X, ldx, 0, D, ldd, 0, fold, C, rows, hp, wp, s, C, dbl(T.dparts), st));
     TCVN_TRY(tcvn_t_bnact_bwd_apply(D, ldd, 0, X, ldx, 0, fold, s, C, count, dX, lddx, 0, accumulate ? 1 : 0, rows, hp, wp,
                                     nullptr, nullptr, nullptr, st));
     bn_param_grads_map_kernel<<<ceil_div(bn.c, 128), 128, 0, st>>>(s, C, bn.c, c0, c0p, garena + bn.w, garena + bn.b,
@@ -307,7 +305,7 @@ struct TWalk {
       double* s1 = dbl(X.sums);
       double* s2 = s1 + B.ctot;
       TCVN_CUDA(cudaMemsetAsync(s1, 0, sizeof(double) * 2 * B.ctot, st));
-      TCVN_TRY(colsums_into(0, blk, B.ctot, 0, nullptr, 0, 0, nullptr, B.c0p, rows, B.Hp, B.Wp, s1, B.ctot, st));
+      TCVN_TRY(colsums_into(0, blk, B.ctot, 0, nullptr, 0, 0, nullptr, B.c0p, rows, B.Hp, B.Wp, s1, B.ctot, dbl(T.dparts), st));
       int tap_off[9];
       for (int t = 0; t < 9; ++t) tap_off[t] = (t / 3 - 1) * B.Wp + (t % 3 - 1);
       for (size_t i = 0; i < B.layers.size(); ++i) {
@@ -321,7 +319,7 @@ struct TWalk {
         TCVN_TRY(gemm(f(Y.mid), mid, rows, mid, 9, tap_off, f(Y.w2), g, f(Y.fold2), B.Hp, B.Wp, arena + L.conv2_b, blk, B.ctot,
                       L.kphys, B.Hp, B.Wp));
         TCVN_TRY(tcvn_t_dropout(blk, B.ctot, L.kphys, g, rows, seed, site * 4096 + b * 64 + i, p_drop, st));
-        TCVN_TRY(colsums_into(0, blk, B.ctot, L.kphys, nullptr, 0, 0, nullptr, g, rows, B.Hp, B.Wp, s1 + L.kphys, B.ctot, st));
+        TCVN_TRY(colsums_into(0, blk, B.ctot, L.kphys, nullptr, 0, 0, nullptr, g, rows, B.Hp, B.Wp, s1 + L.kphys, B.ctot, dbl(T.dparts), st));
       }
       if (B.has_transition) {
         const BlockPlan& Nx = P.blocks[b + 1];
@@ -432,7 +430,10 @@ struct TWalk {
 // =================================================================================================
 typedef __nv_bfloat16 bf;
 
-struct T16Layer { size_t w1b, w1d, w2b, wd, fold1, fold2, mid_raw, mid_act; };
+constexpr int kPullMax = 16;            // later layers of a block a gradient can be pulled from
+constexpr int kPullCtasMax = 148 * 4;   // grid (and bias-gradient slots) of grad_pull_kernel
+
+struct T16Layer { size_t w1b, w1d, w2b, wd, fold1, fold2, mid_raw, mid_act, dA1; };
 struct T16Block {
   size_t blk, gblk, sums, fold_t, pooled, wtb, wtd, tb16;
   size_t bstat;   // [mean | rstd | corrA | corrB] x ctot floats: block statistics and the deferred BN1 corrections
@@ -445,7 +446,7 @@ struct TrainPlan16 {
   int n;
   size_t w0, z0, fold0, fold_f, gap, dgap, lin, fold_o, lw, lwt;
   std::vector<T16Block> blocks;
-  size_t sA, sB, dmid, g2x, gt, dz0, sums_scr, dwp, parts, zeros, ones;
+  size_t sA, sB, dmid, g2x, gt, dz0, sums_scr, dwp, parts, zeros, ones, dparts, bias_parts;
   size_t bytes;
 
   static bool build(const tcvn_cnn_desc& d, int n, TrainPlan16* T) {
@@ -466,6 +467,7 @@ struct TrainPlan16 {
     T->blocks.clear();
     for (size_t b = 0; b < P.blocks.size(); ++b) {
       const BlockPlan& B = P.blocks[b];
+      if ((int)B.layers.size() > kPullMax + 1) return false;
       T16Block X;
       const size_t rows = N * B.R;
       X.blk = take(rows * B.ctot * 2);
@@ -485,6 +487,7 @@ struct TrainPlan16 {
         Y.fold2 = take(5 * (size_t)mid * 4);
         Y.mid_raw = take(rows * mid * 2);
         Y.mid_act = take(rows * mid * 2);
+        Y.dA1 = take(rows * L.kphys * 2);   // gradient of the layer's activated conv1 input: pulled by the earlier layers
         X.layers.push_back(Y);
       }
       X.fold_t = X.pooled = X.wtb = X.wtd = X.tb16 = 0;
@@ -518,12 +521,14 @@ struct TrainPlan16 {
     T->dmid = take(max_rows * mid * 2);
     T->g2x = take(max_rows * 128 * 2);
     T->gt = take((max_gt ? max_gt : 1) * 2);
-    T->dz0 = take(N * P.Hs * P.Ws * C0 * 4);
+    T->dz0 = take(N * P.Hs * P.Ws * C0 * 2);
     T->sums_scr = take(3 * (size_t)max_c * 8);
     T->dwp = take(max_dw * 4);
-    T->parts = take((size_t)148 * 4 * 128 * 128 * 4 + 4 * 128 * 128 * 4 * 8);   // per-CTA partial sums of the wgrad kernel
+    T->parts = take((size_t)148 * 4 * 128 * 128 * 4 + 4 * 128 * 128 * 4 * 8);   // per-CTA partial sums of the wgrad kernels
     T->zeros = take(1024 * 4);
     T->ones = take(1024 * 4);
+    T->dparts = take(colsum_parts_bytes());                 // per-slot partial sums (doubles) of every statistic / reduction
+    T->bias_parts = take((size_t)kPullCtasMax * 32 * 8);    // per-CTA partial sums of a conv2 bias gradient
     T->bytes = w;
     return true;
   }
@@ -539,53 +544,153 @@ __device__ __forceinline__ bool drop_keep16(unsigned long long seed, unsigned lo
   return (r >> 8) * (1.0f / 16777216.0f) >= p;
 }
 
-// G2x[m] = [ G[m+1] | G[m] | G[m-1] | 0 ] (4 x 32 bf16) from the fp32 gradient slice of a layer's 32 output channels,
-// with the layer's dropout mask applied (same (seed, site, element) hash as the forward pass)
-__global__ void g2x_kernel(const float* __restrict__ gblk, int ld, int col0, long long rows, int Hp, int Wp,
-                           unsigned long long seed, unsigned long long stream_id, float p, const bf* __restrict__ blk,
-                           const float* __restrict__ bstat, int ctot, bf* __restrict__ g2x) {
-  // one thread = one row x 8 channels (two float4 loads, 16-byte stores).  The stored gradient lacks the deferred BN1
-  // mean corrections of the later layers: g -= corrA + xhat * corrB (bstat = [mean | rstd | corrA | corrB] x ctot)
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * 4) return;
-  const int c = (int)(idx & 3) * 8;
-  const long long m = idx >> 2;
-  const unsigned rr = (unsigned)m % (unsigned)(Hp * Wp);
-  const unsigned y = rr / (unsigned)Wp, x = rr - y * (unsigned)Wp;
-  float v[8];
+__device__ __forceinline__ void ld8_bf(const bf* p, float (&f)[8]) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = 0.f;
-  if (!(y == 0 || y == (unsigned)(Hp - 1) || x == 0 || x == (unsigned)(Wp - 1))) {
-    const float4 a = *reinterpret_cast<const float4*>(gblk + m * (long long)ld + col0 + c);
-    const float4 b = *reinterpret_cast<const float4*>(gblk + m * (long long)ld + col0 + c + 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    const uint4 xr = *reinterpret_cast<const uint4*>(blk + m * (long long)ld + col0 + c);
-    const uint32_t xw[4] = {xr.x, xr.y, xr.z, xr.w};
-    const float* st = bstat + col0 + c;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float xv = (i & 1) ? __uint_as_float(xw[i >> 1] & 0xffff0000u) : __uint_as_float(xw[i >> 1] << 16);
-      v[i] -= st[2 * ctot + i] + (xv - st[i]) * st[ctot + i] * st[3 * ctot + i];
-    }
-    if (p > 0.f) {
-      const float inv = 1.f / (1.f - p);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = drop_keep16(seed, stream_id, (unsigned long long)m * 32 + c + i, p) ? v[i] * inv : 0.f;
-    }
-  }
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ uint4 pack8_bf(const float (&v)[8]) {
   uint32_t w[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const __nv_bfloat162 h2 = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
     w[i] = *reinterpret_cast<const uint32_t*>(&h2);
   }
-  const uint4 hv = make_uint4(w[0], w[1], w[2], w[3]), zv = make_uint4(0u, 0u, 0u, 0u);
-  *reinterpret_cast<uint4*>(g2x + m * 128 + 32 + c) = hv;
-  *reinterpret_cast<uint4*>(g2x + m * 128 + 96 + c) = zv;
-  if (m > 0) *reinterpret_cast<uint4*>(g2x + (m - 1) * 128 + c) = hv;
-  else *reinterpret_cast<uint4*>(g2x + 64 + c) = zv;
-  if (m + 1 < rows) *reinterpret_cast<uint4*>(g2x + (m + 1) * 128 + 64 + c) = hv;
-  else *reinterpret_cast<uint4*>(g2x + m * 128 + c) = zv;
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Gradient of concat channels [col0, col0 + ncols) of a dense block, PULLED from where it was produced.
+// All BN1s of a block normalise the same channels x with the same batch statistics, so the gradient of channel c is
+//     g[m,c] = ginit[m,c] + sum_{j in later layers} sc_j,c * prelu'_j(sc_j,c x + sh_j,c) * dA_j[m,c]  -  corrA[c]  -  xhat[m,c] corrB[c]
+// ginit = what the block's consumer (transition / final norm) left in the fp32 block gradient, dA_j = the bf16 input
+// gradient of layer j's conv1 (kept per layer), corrA / corrB = the accumulated mean corrections of the BN backward
+// (bn_param_reduce_kernel).  Round 1 PUSHED instead: every layer added sc_j g_j into the fp32 block gradient over all
+// its input channels (read 4 + write 4 bytes per element and layer, the most expensive pass of the backward walk).
+//   MODE 0  the 32 output channels of a layer -> Dropout mask (same (seed, site, element) hash as the forward) -> bf16
+//           G2x[m] = [G[m+1] | G[m] | G[m-1] | 0] (the operand of conv2's input / weight gradient kernels) and the
+//           per-CTA partial sums of conv2's bias gradient
+//   MODE 1  the block-input channels, fp32 in place (stem side of block 0)
+//   MODE 2  the block-input channels -> bf16 [rows][pitch] zero-padded (operand of the transition's gradient GEMMs)
+// ------------------------------------------------------------------------------------------------------------------
+struct PullSrc { const bf* dA; int ld; const float* fold; int fs; };
+struct PullArgs {
+  const float* ginit; int ldg;
+  const bf* blk; int ldb;
+  const float* bstat; int ctot;
+  int col0, ncols;
+  long long rows; int Hp, Wp;
+  int n_src; PullSrc src[kPullMax];
+  bf* g2x; float p; unsigned long long seed, site; double* bias_parts;   // MODE 0
+  float* out32; int ldo;                                                  // MODE 1
+  bf* out16; int pitch;                                                   // MODE 2
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(256) grad_pull_kernel(const PullArgs a) {
+  extern __shared__ float cst[];   // [n_src][3][ncols]: scale, shift, scale * slope
+  __shared__ float red[MODE == 0 ? 256 : 1][8];
+  const int tv = a.ncols >> 3, rpi = 256 / tv;
+  for (int i = threadIdx.x; i < a.n_src * a.ncols; i += 256) {
+    const int j = i / a.ncols, c = i - j * a.ncols;
+    const float* f = a.src[j].fold;
+    const int fs = a.src[j].fs;
+    const float sc = f[a.col0 + c];
+    cst[(j * 3 + 0) * a.ncols + c] = sc;
+    cst[(j * 3 + 1) * a.ncols + c] = f[fs + a.col0 + c];
+    cst[(j * 3 + 2) * a.ncols + c] = sc * f[2 * fs + a.col0 + c];
+  }
+  __syncthreads();
+  const int vx = threadIdx.x % tv, ry = threadIdx.x / tv;
+  const int c = vx * 8;
+  float bsum[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) bsum[i] = 0.f;
+  if (ry < rpi) {
+    float mean[8], rstd[8], cA[8], cB[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float* st = a.bstat + a.col0 + c + i;
+      mean[i] = st[0]; rstd[i] = st[a.ctot]; cA[i] = st[2 * a.ctot]; cB[i] = st[3 * a.ctot];
+    }
+    const unsigned R = (unsigned)(a.Hp * a.Wp);
+    const float inv_keep = 1.f / (1.f - a.p);
+    for (long long m = (long long)blockIdx.x * rpi + ry; m < a.rows; m += (long long)gridDim.x * rpi) {
+      const unsigned rr = (unsigned)m % R;
+      const unsigned y = rr / (unsigned)a.Wp, x_ = rr - y * (unsigned)a.Wp;
+      const bool ring = y == 0 || y == (unsigned)(a.Hp - 1) || x_ == 0 || x_ == (unsigned)(a.Wp - 1);
+      float v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.f;
+      if (!ring) {
+        const float4 g0 = *reinterpret_cast<const float4*>(a.ginit + m * (long long)a.ldg + a.col0 + c);
+        const float4 g1 = *reinterpret_cast<const float4*>(a.ginit + m * (long long)a.ldg + a.col0 + c + 4);
+        v[0] = g0.x; v[1] = g0.y; v[2] = g0.z; v[3] = g0.w; v[4] = g1.x; v[5] = g1.y; v[6] = g1.z; v[7] = g1.w;
+        float xv[8];
+        ld8_bf(a.blk + m * (long long)a.ldb + a.col0 + c, xv);
+        for (int j = 0; j < a.n_src; ++j) {
+          float d[8];
+          ld8_bf(a.src[j].dA + m * (long long)a.src[j].ld + a.col0 + c, d);
+          const float* k = cst + (j * 3) * a.ncols + c;
+          const float4 s0 = *reinterpret_cast<const float4*>(k), s1 = *reinterpret_cast<const float4*>(k + 4);
+          const float4 h0 = *reinterpret_cast<const float4*>(k + a.ncols), h1 = *reinterpret_cast<const float4*>(k + a.ncols + 4);
+          const float4 a0 = *reinterpret_cast<const float4*>(k + 2 * a.ncols), a1 = *reinterpret_cast<const float4*>(k + 2 * a.ncols + 4);
+          const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+          const float sa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = fmaf(d[i], fmaf(xv[i], sc[i], sh[i]) >= 0.f ? sc[i] : sa[i], v[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] -= cA[i] + (xv[i] - mean[i]) * rstd[i] * cB[i];
+        if (MODE == 0) {
+          if (a.p > 0.f) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              v[i] = drop_keep16(a.seed, a.site, (unsigned long long)m * 32 + c + i, a.p) ? v[i] * inv_keep : 0.f;
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) bsum[i] += v[i];
+        }
+      }
+      if (MODE == 0) {
+        const uint4 hv = pack8_bf(v), zv = make_uint4(0u, 0u, 0u, 0u);
+        bf* g2x = a.g2x;
+        *reinterpret_cast<uint4*>(g2x + m * 128 + 32 + c) = hv;
+        *reinterpret_cast<uint4*>(g2x + m * 128 + 96 + c) = zv;
+        if (m > 0) *reinterpret_cast<uint4*>(g2x + (m - 1) * 128 + c) = hv;
+        else *reinterpret_cast<uint4*>(g2x + 64 + c) = zv;
+        if (m + 1 < a.rows) *reinterpret_cast<uint4*>(g2x + (m + 1) * 128 + 64 + c) = hv;
+        else *reinterpret_cast<uint4*>(g2x + m * 128 + c) = zv;
+      } else if (MODE == 1) {
+        if (!ring) {
+          float* o = a.out32 + m * (long long)a.ldo + a.col0 + c;
+          *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        }
+      } else {
+        *reinterpret_cast<uint4*>(a.out16 + m * (long long)a.pitch + c) = pack8_bf(v);
+        if (vx == 0)
+          for (int z = a.ncols; z < a.pitch; z += 8)
+            *reinterpret_cast<uint4*>(a.out16 + m * (long long)a.pitch + z) = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  }
+  if (MODE == 0) {
+    // conv2 bias gradient: the CTA's row lanes are added in a fixed order, one slot per CTA
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = bsum[i];
+    __syncthreads();
+    if (ry == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        double s = 0.0;
+        for (int r = 0; r < rpi; ++r) s += (double)red[r * tv + vx][i];
+        a.bias_parts[(size_t)blockIdx.x * a.ncols + c + i] = s;
+      }
+    }
+  }
 }
 
 // block statistics for the backward: bstat = [mean | rstd | corrA = 0 | corrB = 0] x ctot from the forward's (sum, sum^2)
@@ -602,31 +707,138 @@ __global__ void blk_stats_kernel(const double* __restrict__ s1, const double* __
   bstat[3 * ctot + p] = 0.f;
 }
 
-// BN1 parameter gradients + the deferred corrections from the fused pass's reductions sums[3][C] (physical channels)
-__global__ void bn1_param_corr_kernel(const double* __restrict__ sums, int C, int c_log, int c0, int c0p,
-                                      const float* __restrict__ scale, double count, float* dgamma, float* dbeta, float* dalpha,
-                                      float* __restrict__ corrA, float* __restrict__ corrB) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= C) return;
+// ------------------------------------------------------------------------------------------------------------------
+// Consumers of the per-slot partial sums.  A block owns 16 columns; its 16 slices each add every 16th slot, then the
+// slice sums are added in order: the summation order is fixed, so every statistic is bit-reproducible.
+// ------------------------------------------------------------------------------------------------------------------
+// batch statistics -> fold over n_out physical channels + running-buffer update.  Channels [fresh.col0, +fresh.ncols) take
+// their (sum, sum^2) from the producer's slots, parts[slot][2][Cp], and store them into s1 / s2; all others read s1 / s2.
+struct Fresh { const double* parts; int n_slots, Cp, col0, ncols; };
+struct FinArgs16 {
+  double* s1; double* s2;
+  Fresh fresh;
+  int n_out, c_log, c0, c0p;
+  double count;
+  const float *gamma, *beta, *alpha;
+  float eps, momentum;
+  float *rm, *rv;
+  float* fold;
+};
+
+__global__ void __launch_bounds__(256) bn_finalize16_kernel(const FinArgs16 a) {
+  __shared__ double red[2][16][17];
+  const int col = threadIdx.x & 15, slice = threadIdx.x >> 4;
+  const int p = blockIdx.x * 16 + col;
+  const bool fresh = a.fresh.parts != nullptr && p < a.n_out && p >= a.fresh.col0 && p < a.fresh.col0 + a.fresh.ncols;
+  double x1 = 0.0, x2 = 0.0;
+  if (fresh) {
+    const int q = p - a.fresh.col0;
+    for (int s = slice; s < a.fresh.n_slots; s += 16) {
+      x1 += a.fresh.parts[((size_t)s * 2) * a.fresh.Cp + q];
+      x2 += a.fresh.parts[((size_t)s * 2 + 1) * a.fresh.Cp + q];
+    }
+  }
+  red[0][slice][col] = x1;
+  red[1][slice][col] = x2;
+  __syncthreads();
+  if (slice != 0 || p >= a.n_out) return;
+  double S1 = 0.0, S2 = 0.0;
+  if (fresh) {
+#pragma unroll
+    for (int k = 0; k < 16; ++k) { S1 += red[0][k][col]; S2 += red[1][k][col]; }
+    a.s1[p] = S1;
+    a.s2[p] = S2;
+  }
   int c = -1;
-  if (p < c0) c = p;
-  else if (p >= c0p) c = p - (c0p - c0);
-  if (c < 0 || c >= c_log) return;
-  const double S0 = sums[p], S1 = sums[C + p], S2 = sums[2 * C + p];
-  dbeta[c] += (float)S0;
-  dgamma[c] += (float)S1;
-  dalpha[c] += (float)S2;
-  corrA[p] += scale[p] * (float)(S0 / count);
-  corrB[p] += scale[p] * (float)(S1 / count);
+  if (p < a.c0) c = p;
+  else if (p >= a.c0p) c = p - (a.c0p - a.c0);
+  float sc = 0.f, sh = 0.f, al = 0.f, mu = 0.f, rs = 0.f;
+  if (c >= 0 && c < a.c_log) {
+    if (!fresh) { S1 = a.s1[p]; S2 = a.s2[p]; }
+    const double mean = S1 / a.count;
+    double var = S2 / a.count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    rs = (float)(1.0 / sqrt(var + (double)a.eps));
+    sc = a.gamma[c] * rs;
+    sh = a.beta[c] - (float)mean * sc;
+    al = a.alpha[c];
+    mu = (float)mean;
+    if (a.rm) {
+      const double unbiased = a.count > 1.0 ? var * a.count / (a.count - 1.0) : var;
+      a.rm[c] = (1.f - a.momentum) * a.rm[c] + a.momentum * (float)mean;
+      a.rv[c] = (1.f - a.momentum) * a.rv[c] + a.momentum * (float)unbiased;
+    }
+  }
+  a.fold[p] = sc;
+  a.fold[a.n_out + p] = sh;
+  a.fold[2 * a.n_out + p] = al;
+  a.fold[3 * a.n_out + p] = mu;
+  a.fold[4 * a.n_out + p] = rs;
 }
 
-// fp32 gradient columns [0, cols) -> bf16 [rows][pitch], zero padded
-__global__ void to_bf16_pad_kernel(const float* __restrict__ src, int ld, int cols, long long rows, int pitch, bf* __restrict__ dst) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= rows * pitch) return;
-  const int c = (int)(idx % pitch);
-  const long long m = idx / pitch;
-  dst[idx] = __float2bfloat16_rn(c < cols ? src[m * (long long)ld + c] : 0.f);
+// BN + PReLU backward reductions parts[slot][3][C] (sum g, sum g xhat, sum dA min(y,0); physical channels) ->
+//   sums_out[3][C] (optional: what the elementwise half of the backward reads), dgamma / dbeta / dalpha += (logical
+//   channels), the deferred BN1 corrections corrA += sc S0 / count, corrB += sc S1 / count (optional), and - second job,
+//   blocks >= main_blocks - a conv2 bias gradient: dbias[c] += sum over bias_slots of bias_parts[slot][bias_C]
+struct BnParamArgs {
+  const double* parts; int n_slots, C;
+  double* sums_out;
+  int c_log, c0, c0p;
+  float *dgamma, *dbeta, *dalpha;
+  const float* scale; double count; float* corrA; float* corrB;
+  const double* bias_parts; int bias_slots, bias_C; float* dbias;
+  int main_blocks;
+};
+
+__global__ void __launch_bounds__(256) bn_param_reduce_kernel(const BnParamArgs a) {
+  __shared__ double red[3][16][17];
+  const int col = threadIdx.x & 15, slice = threadIdx.x >> 4;
+  if ((int)blockIdx.x >= a.main_blocks) {
+    const int c = ((int)blockIdx.x - a.main_blocks) * 16 + col;
+    double x = 0.0;
+    if (c < a.bias_C)
+      for (int s = slice; s < a.bias_slots; s += 16) x += a.bias_parts[(size_t)s * a.bias_C + c];
+    red[0][slice][col] = x;
+    __syncthreads();
+    if (slice == 0 && c < a.bias_C) {
+      double t = 0.0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) t += red[0][k][col];
+      a.dbias[c] += (float)t;
+    }
+    return;
+  }
+  const int p = blockIdx.x * 16 + col;
+  double x[3] = {0.0, 0.0, 0.0};
+  if (p < a.C)
+    for (int s = slice; s < a.n_slots; s += 16) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) x[j] += a.parts[((size_t)s * 3 + j) * a.C + p];
+    }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) red[j][slice][col] = x[j];
+  __syncthreads();
+  if (slice != 0 || p >= a.C) return;
+  double S[3] = {0.0, 0.0, 0.0};
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+#pragma unroll
+    for (int k = 0; k < 16; ++k) S[j] += red[j][k][col];
+  if (a.sums_out) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) a.sums_out[(size_t)j * a.C + p] = S[j];
+  }
+  int c = -1;
+  if (p < a.c0) c = p;
+  else if (p >= a.c0p) c = p - (a.c0p - a.c0);
+  if (c < 0 || c >= a.c_log) return;
+  a.dbeta[c] += (float)S[0];
+  a.dgamma[c] += (float)S[1];
+  a.dalpha[c] += (float)S[2];
+  if (a.corrA) {
+    a.corrA[p] += a.scale[p] * (float)(S[0] / a.count);
+    a.corrB[p] += a.scale[p] * (float)(S[1] / a.count);
+  }
 }
 
 // conv2 weight gradient from the tensor-core layout dw[dy][k][dx*32 + n] -> += reference layout [n][k][dy][dx]
@@ -656,7 +868,8 @@ __global__ void fill_f32_kernel(float* dst, int n, float v) {
 // Side stream of the bf16 backward walk: the weight-gradient branch of a bottleneck (wgrad GEMM -> partial-sum reduction ->
 // unpack into the gradient arena, twice per layer) depends only on tensors the input-gradient chain has already produced,
 // so it runs beside that chain instead of in front of it.  One (stream, 3 events) set per caller stream, created on first
-// use and kept for the life of the process; TCVN_WGRAD_STREAM=0 keeps everything on the caller's stream.
+// use and kept for the life of the process; TCVN_WGRAD_STREAM=0 keeps everything on the caller's stream.  Both orders are
+// the same arithmetic (stream order only): the result is bit-identical either way.
 struct AuxStream { cudaStream_t s = nullptr; cudaEvent_t e[3] = {nullptr, nullptr, nullptr}; };
 static AuxStream* aux_for(cudaStream_t main) {
   static std::map<std::pair<int, cudaStream_t>, AuxStream> pool;
@@ -684,40 +897,51 @@ struct TWalk16 {
   cudaStream_t st;
   float p_drop, momentum;
   uint64_t seed, site;
+  Fresh pending{nullptr, 0, 0, 0, 0};   // statistics a producer kernel left in its slots for the next finalize
 
   float* f(size_t off) const { return reinterpret_cast<float*>(ws + off); }
   bf* h(size_t off) const { return reinterpret_cast<bf*>(ws + off); }
   double* dbl(size_t off) const { return reinterpret_cast<double*>(ws + off); }
 
-  int finalize(const double* s1, const double* s2, int n_out, const BnArena& bn, int c0, int c0p, double count, float* fold) {
-    FinArgs a;
-    a.s1 = s1; a.s2 = s2; a.n_out = n_out; a.c_log = bn.c; a.c0 = c0; a.c0p = c0p; a.count = count;
+  void produced(int n_slots, int Cp, int col0, int ncols) { pending = Fresh{dbl(T.dparts), n_slots, Cp, col0, ncols}; }
+
+  int finalize(double* s1, double* s2, int n_out, const BnArena& bn, int c0, int c0p, double count, float* fold) {
+    FinArgs16 a;
+    a.s1 = s1; a.s2 = s2; a.fresh = pending; a.n_out = n_out; a.c_log = bn.c; a.c0 = c0; a.c0p = c0p; a.count = count;
     a.gamma = arena + bn.w; a.beta = arena + bn.b; a.alpha = arena + bn.alpha;
     a.eps = T.P.d.bn_eps; a.momentum = momentum;
     a.rm = arena + bn.rm; a.rv = arena + bn.rv;
     a.fold = fold;
-    bn_finalize_map_kernel<<<ceil_div(n_out, 128), 128, 0, st>>>(a);
+    pending = Fresh{nullptr, 0, 0, 0, 0};
+    bn_finalize16_kernel<<<ceil_div(n_out, 16), 256, 0, st>>>(a);
     TCVN_LAUNCH_CHECK();
     return TCVN_OK;
   }
 
-  int stats_scratch(const void* X, bool x_bf16, int ldx, int col0, int C, long long rows, int hp, int wp) {
-    TCVN_CUDA(cudaMemsetAsync(dbl(T.sums_scr), 0, sizeof(double) * 2 * C, st));
-    return colsums_typed(0, X, x_bf16, ldx, col0, nullptr, false, 0, 0, nullptr, 0, C, rows, hp, wp, dbl(T.sums_scr), C, st);
+  // reduce the mode-1 partial sums in dparts: parameter gradients of `bn`, optionally the reduced sums (for the apply
+  // kernel), the deferred BN1 corrections, and a conv2 bias gradient from bias_parts
+  int param_reduce(int n_slots, int C, bool want_sums, const BnArena& bn, int c0, int c0p, const float* corr_scale, double count,
+                   float* corrA, float* corrB, int bias_slots, float* dbias) {
+    BnParamArgs a{};
+    a.parts = dbl(T.dparts); a.n_slots = n_slots; a.C = C; a.sums_out = want_sums ? dbl(T.sums_scr) : nullptr;
+    a.c_log = bn.c; a.c0 = c0; a.c0p = c0p;
+    a.dgamma = garena + bn.w; a.dbeta = garena + bn.b; a.dalpha = garena + bn.alpha;
+    a.scale = corr_scale; a.count = count; a.corrA = corrA; a.corrB = corrB;
+    a.bias_parts = dbl(T.bias_parts); a.bias_slots = bias_slots; a.bias_C = 32; a.dbias = dbias;
+    a.main_blocks = ceil_div(C, 16);
+    bn_param_reduce_kernel<<<a.main_blocks + (dbias ? 2 : 0), 256, 0, st>>>(a);
+    TCVN_LAUNCH_CHECK();
+    return TCVN_OK;
   }
 
+  // dX = backward of PReLU(BN(X)) given D = gradient of the activated value; parameter gradients of `bn`
   int bn_bwd(const void* X, bool x_bf16, int ldx, const void* D, bool d_bf16, int ldd, const float* fold, int fold_stride, int C,
-             double count, long long rows, int hp, int wp, void* dX, bool o_bf16, int lddx, bool accumulate, const BnArena& bn,
-             int c0, int c0p) {
-    double* s = dbl(T.sums_scr);
-    TCVN_CUDA(cudaMemsetAsync(s, 0, sizeof(double) * 3 * C, st));
-    TCVN_TRY(colsums_typed(1, X, x_bf16, ldx, 0, D, d_bf16, ldd, 0, fold, fold_stride, C, rows, hp, wp, s, C, st));
-    TCVN_TRY(bnact_bwd_apply_typed(D, d_bf16, ldd, 0, X, x_bf16, ldx, 0, fold, fold_stride, s, C, count, dX, o_bf16, lddx, 0,
-                                   accumulate, rows, hp, wp, st));
-    bn_param_grads_map_kernel<<<ceil_div(bn.c, 128), 128, 0, st>>>(s, C, bn.c, c0, c0p, garena + bn.w, garena + bn.b,
-                                                                   garena + bn.alpha);
-    TCVN_LAUNCH_CHECK();
-    return TCVN_OK;
+             double count, long long rows, int hp, int wp, void* dX, bool o_bf16, int lddx, const BnArena& bn, int c0, int c0p) {
+    int slabs = 0;
+    TCVN_TRY(colsums_parts(1, X, x_bf16, ldx, 0, D, d_bf16, ldd, 0, fold, fold_stride, C, rows, hp, wp, dbl(T.dparts), &slabs, st));
+    TCVN_TRY(param_reduce(slabs, C, true, bn, c0, c0p, nullptr, count, nullptr, nullptr, 0, nullptr));
+    return bnact_bwd_apply_typed(D, d_bf16, ldd, 0, X, x_bf16, ldx, 0, fold, fold_stride, dbl(T.sums_scr), C, count, dX, o_bf16, lddx,
+                                 0, false, rows, hp, wp, st);
   }
 
   int gemm32(const float* A, int lda, long long rows, int K, const float* W, int N, const float* bias, float* out, int ldo) {
@@ -767,9 +991,11 @@ struct TWalk16 {
     TCVN_TRY(pack());
     const BlockPlan& B0 = P.blocks[0];
     const long long stem_rows = (long long)n * P.Hs * P.Ws;
-    TCVN_TRY(tcvn_t_stem_conv(pixels, n, d.in_channels, d.height, d.width, f(T.w0), arena + P.conv0_b, C0, f(T.z0), nullptr,
-                              nullptr, st));
-    TCVN_TRY(stats_scratch(f(T.z0), false, C0, 0, C0, stem_rows, 0, 0));
+    int slots = 0;
+    // ---- stem: raw conv0 (+ bias) and its batch statistics in one hit-driven pass, then BN0 + PReLU0 + AvgPool(3,2)
+    TCVN_TRY(stem_train_forward(pixels, n, d.in_channels, d.height, d.width, f(T.w0), arena + P.conv0_b, C0, f(T.z0), dbl(T.dparts),
+                                &slots, st));
+    produced(slots, C0, 0, C0);
     TCVN_TRY(finalize(dbl(T.sums_scr), dbl(T.sums_scr) + C0, C0, P.norm0, NOGAP, NOGAP, (double)stem_rows, f(T.fold0)));
     TCVN_TRY(pool_typed(0, f(T.z0), f(T.fold0), h(T.blocks[0].blk), true, n, C0, B0.H, B0.W, P.Hs, P.Ws, B0.ctot, st));
     for (size_t b = 0; b < P.blocks.size(); ++b) {
@@ -780,24 +1006,26 @@ struct TWalk16 {
       bf* blk = h(X.blk);
       double* s1 = dbl(X.sums);
       double* s2 = s1 + B.ctot;
-      TCVN_CUDA(cudaMemsetAsync(s1, 0, sizeof(double) * 2 * B.ctot, st));
-      TCVN_TRY(colsums_typed(0, blk, true, B.ctot, 0, nullptr, false, 0, 0, nullptr, 0, B.c0p, rows, B.Hp, B.Wp, s1, B.ctot, st));
+      // statistics of the block-input channels; every later channel's statistics come out of the epilogue of the conv2
+      // that produces it.  Each producer leaves per-slot partial sums, the next finalize adds them in a fixed order.
+      TCVN_TRY(colsums_parts(0, blk, true, B.ctot, 0, nullptr, false, 0, 0, nullptr, 0, B.c0p, rows, B.Hp, B.Wp, dbl(T.dparts), &slots, st));
+      produced(slots, B.c0p, 0, B.c0p);
       for (size_t i = 0; i < B.layers.size(); ++i) {
         const LayerPlan& L = B.layers[i];
         const T16Layer& Y = X.layers[i];
         float* f1 = f(Y.fold1);
         TCVN_TRY(finalize(s1, s2, L.kpad, L.norm1, B.c0, B.c0p, count, f1));
-        // raw conv1 output (+ bias): the BN2 statistics are taken from exactly the bf16 values conv2 will read
-        // conv1 (+ bias), raw: the epilogue also accumulates the BN2 batch statistics from exactly the bf16 values it
-        // stores; conv2's epilogue applies Dropout and accumulates the statistics of the 32 new concat channels
+        // conv1 (+ bias), raw: the epilogue also takes the BN2 batch statistics from exactly the bf16 values it stores;
+        // conv2's epilogue applies Dropout and takes the statistics of the 32 new concat channels
         double* sc2 = dbl(T.sums_scr);
-        TCVN_CUDA(cudaMemsetAsync(sc2, 0, sizeof(double) * 2 * mid, st));
         TCVN_TRY(launch_gemm(true, blk, rows, B.ctot, B.ctot, h(Y.w1b), mid, L.kpad, L.kphys, f1, f1 + L.kpad, f1 + 2 * L.kpad,
-                             arena + L.conv1_b, f(T.ones), h(Y.mid_raw), mid, mid, 1, B.Hp, B.Wp, st, sc2, mid));
+                             arena + L.conv1_b, f(T.ones), h(Y.mid_raw), mid, mid, 1, B.Hp, B.Wp, st, dbl(T.dparts), &slots));
+        produced(slots, mid, 0, mid);
         TCVN_TRY(finalize(sc2, sc2 + mid, mid, L.norm2, NOGAP, NOGAP, count, f(Y.fold2)));
         TCVN_TRY(bnact_fwd_typed(h(Y.mid_raw), true, mid, 0, f(Y.fold2), mid, mid, rows, B.Hp, B.Wp, h(Y.mid_act), true, mid, 0, st));
         TCVN_TRY(umma_conv2_fwd(h(Y.mid_act), rows, h(Y.w2b), arena + L.conv2_b, blk, B.ctot, L.kphys, B.Hp, B.Wp, B.W, st, p_drop,
-                                seed, site * 4096 + b * 64 + i, s1 + L.kphys, B.ctot));
+                                seed, site * 4096 + b * 64 + i, dbl(T.dparts), &slots));
+        produced(slots, 32, L.kphys, 32);
       }
       if (B.has_transition) {
         const BlockPlan& Nx = P.blocks[b + 1];
@@ -817,7 +1045,8 @@ struct TWalk16 {
     const BlockPlan& last = P.blocks.back();
     const int out = d.out_features;
     TCVN_TRY(gemm32(f(T.gap), last.ctot, n, last.ctot, f(T.lw), out, nullptr, f(T.lin), out));
-    TCVN_TRY(stats_scratch(f(T.lin), false, out, 0, out, n, 0, 0));
+    TCVN_TRY(colsums_parts(0, f(T.lin), false, out, 0, nullptr, false, 0, 0, nullptr, 0, out, n, 0, 0, dbl(T.dparts), &slots, st));
+    produced(slots, out, 0, out);
     TCVN_TRY(finalize(dbl(T.sums_scr), dbl(T.sums_scr) + out, out, P.out_norm, NOGAP, NOGAP, (double)n, f(T.fold_o)));
     TCVN_TRY(tcvn_t_bnact_fwd(f(T.lin), out, 0, f(T.fold_o), out, n, 0, 0, emb, out, 0, st));
     TCVN_TRY(tcvn_t_dropout(emb, out, 0, out, n, seed, site * 4096 + 4095, p_drop, st));
@@ -835,6 +1064,38 @@ struct TWalk16 {
     return TCVN_OK;
   }
 
+  // gradient of channels [col0, col0 + ncols) of block b, pulled from the layers after `first_src - 1` (see grad_pull_kernel)
+  int pull(int mode, int b, int first_src, int col0, int ncols, long long rows, uint64_t drop_site, int* bias_slots, float* out32,
+           bf* out16, int pitch) {
+    const BlockPlan& B = T.P.blocks[b];
+    const T16Block& X = T.blocks[b];
+    PullArgs a{};
+    a.ginit = f(X.gblk); a.ldg = B.ctot; a.blk = h(X.blk); a.ldb = B.ctot; a.bstat = f(X.bstat); a.ctot = B.ctot;
+    a.col0 = col0; a.ncols = ncols; a.rows = rows; a.Hp = B.Hp; a.Wp = B.Wp;
+    a.n_src = 0;
+    for (int j = first_src; j < (int)B.layers.size(); ++j) {
+      if (a.n_src >= kPullMax) return fail(TCVN_ERR_UNSUPPORTED, "dense block with more than %d layers", kPullMax + 1);
+      a.src[a.n_src++] = PullSrc{h(X.layers[j].dA1), B.layers[j].kphys, f(X.layers[j].fold1), B.layers[j].kpad};
+    }
+    a.g2x = h(T.g2x); a.p = p_drop; a.seed = seed; a.site = drop_site; a.bias_parts = dbl(T.bias_parts);
+    a.out32 = out32; a.ldo = B.ctot; a.out16 = out16; a.pitch = pitch;
+    if (ncols % 8 || ncols > 2048) return fail(TCVN_ERR_UNSUPPORTED, "grad_pull: %d channels", ncols);
+    const int tv = ncols / 8, rpi = 256 / tv;
+    long long want = ceil_div_ll(rows, (long long)rpi * 4);
+    const int grid = (int)(want < 1 ? 1 : (want > kPullCtasMax ? kPullCtasMax : want));
+    const size_t smem = (size_t)a.n_src * 3 * ncols * sizeof(float);
+    if (mode == 0) {
+      grad_pull_kernel<0><<<grid, 256, smem, st>>>(a);
+      if (bias_slots) *bias_slots = grid;
+    } else if (mode == 1) {
+      grad_pull_kernel<1><<<grid, 256, smem, st>>>(a);
+    } else {
+      grad_pull_kernel<2><<<grid, 256, smem, st>>>(a);
+    }
+    TCVN_LAUNCH_CHECK();
+    return TCVN_OK;
+  }
+
   int backward(const float* pixels, float* d_emb) {
     const CnnPlan& P = T.P;
     const tcvn_cnn_desc& d = P.d;
@@ -844,7 +1105,7 @@ struct TWalk16 {
     float* dwp = f(T.dwp);
     // ---- tail (fp32)
     TCVN_TRY(tcvn_t_dropout(d_emb, out, 0, out, n, seed, site * 4096 + 4095, p_drop, st));
-    TCVN_TRY(bn_bwd(f(T.lin), false, out, d_emb, false, out, f(T.fold_o), out, out, (double)n, n, 0, 0, d_emb, false, out, false,
+    TCVN_TRY(bn_bwd(f(T.lin), false, out, d_emb, false, out, f(T.fold_o), out, out, (double)n, n, 0, 0, d_emb, false, out,
                     P.out_norm, NOGAP, NOGAP));
     TCVN_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)last.ctot * out, st));
     TCVN_TRY(tcvn_t_wgrad(f(T.gap), last.ctot, n, last.ctot, 1, nullptr, nullptr, 0, 0, d_emb, out, 0, out, 0, 0, dwp, st));
@@ -853,14 +1114,14 @@ struct TWalk16 {
     TCVN_TRY(pool_typed(3, f(T.dgap), nullptr, h(T.sA), true, n, last.ctot, last.H, last.W, 0, 0, last.ctot, st));
     TCVN_TRY(bn_bwd(h(T.blocks[nb - 1].blk), true, last.ctot, h(T.sA), true, last.ctot, f(T.fold_f), last.ctot, last.ctot,
                     (double)n * last.H * last.W, (long long)n * last.R, last.Hp, last.Wp, f(T.blocks[nb - 1].gblk), false,
-                    last.ctot, false, P.final_norm, last.c0, last.c0p));
+                    last.ctot, P.final_norm, last.c0, last.c0p));
     for (int b = nb - 1; b >= 0; --b) {
       const BlockPlan& B = P.blocks[b];
       const T16Block& X = T.blocks[b];
       const long long rows = (long long)n * B.R;
       const double count = (double)n * B.H * B.W;
       bf* blk = h(X.blk);
-      float* gblk = f(X.gblk);
+      float* gblk = f(X.gblk);   // what the block's consumer left: the layers only READ it (grad_pull_kernel)
       bf* dmid = h(T.dmid);
       bf* g2x = h(T.g2x);
       float* bstat = f(X.bstat);
@@ -877,14 +1138,12 @@ struct TWalk16 {
           TCVN_CUDA(cudaStreamWaitEvent(st, ax->e[2], 0));
           side_pending = false;
         }
-        // gradient of the layer's 32 output channels (complete by now) -> bf16, dropout mask applied, 3 horizontal shifts
-        g2x_kernel<<<(unsigned)ceil_div_ll(rows * 4, 256), 256, 0, st>>>(gblk, B.ctot, L.kphys, rows, B.Hp, B.Wp, seed,
-                                                                        site * 4096 + b * 64 + i, p_drop, blk, bstat, B.ctot, g2x);
-        TCVN_LAUNCH_CHECK();
-        // conv biases: every convolution of the DenseNet feeds a train-mode BatchNorm (directly, or through the concat
-        // buffer), which removes any per-channel constant, so their gradient is exactly zero; the reference's autograd
-        // produces rounding noise there (tests/golden/forward_train.pt: 1e-16).  The bf16 walk leaves them at zero
-        // instead of spending a reduction pass per layer on them (the fp32 parity walk computes them literally).
+        // gradient of the layer's 32 output channels (every later layer has produced its dA by now) -> bf16, dropout mask
+        // applied, 3 horizontal shifts; the same pass reduces conv2's bias gradient.  (conv1 / transition / conv0 biases
+        // feed a train-mode BatchNorm directly, which removes any per-channel constant: their gradient is exactly zero and
+        // stays zero here.  conv2's bias passes through Dropout first - mask * b / (1 - p) is not constant - so it has one.)
+        int bias_slots = 0;
+        TCVN_TRY(pull(0, b, i + 1, L.kphys, 32, rows, site * 4096 + b * 64 + i, &bias_slots, nullptr, nullptr, 0));
         // conv2 weight gradient: three vertical taps of the activated bottleneck map against G2x
         {
           const int cols[3] = {0, 0, 0}, shifts[3] = {-B.Wp, 0, B.Wp}, valid[3] = {128, 128, 128};
@@ -898,8 +1157,16 @@ struct TWalk16 {
           TCVN_LAUNCH_CHECK();
         }
         TCVN_TRY(umma_conv2_dgrad(g2x, h(Y.wd), rows, B.Hp, B.Wp, dmid, st));
-        TCVN_TRY(bn_bwd(h(Y.mid_raw), true, mid, dmid, true, mid, f(Y.fold2), mid, mid, count, rows, B.Hp, B.Wp, dmid, true, mid,
-                        false, L.norm2, NOGAP, NOGAP));
+        // BN2 + PReLU2 backward: reductions -> (parameter gradients, conv2 bias gradient) -> elementwise half, in place
+        {
+          int slabs = 0;
+          TCVN_TRY(colsums_parts(1, h(Y.mid_raw), true, mid, 0, dmid, true, mid, 0, f(Y.fold2), mid, mid, rows, B.Hp, B.Wp,
+                                 dbl(T.dparts), &slabs, st));
+          TCVN_TRY(param_reduce(slabs, mid, true, L.norm2, NOGAP, NOGAP, nullptr, count, nullptr, nullptr, bias_slots,
+                                garena + L.conv2_b));
+          TCVN_TRY(bnact_bwd_apply_typed(dmid, true, mid, 0, h(Y.mid_raw), true, mid, 0, f(Y.fold2), mid, dbl(T.sums_scr), mid, count,
+                                         dmid, true, mid, 0, false, rows, B.Hp, B.Wp, st));
+        }
         // conv1 weight gradient: 128-channel column blocks of the concat buffer, BN1 + PReLU1 applied in SMEM
         {
           const int n_items = ceil_div(L.kphys, 128);
@@ -917,31 +1184,24 @@ struct TWalk16 {
             side_pending = true;
           }
         }
+        // gradient of the activated conv1 input, kept per layer: the earlier layers pull their share from it
         TCVN_TRY(launch_gemm(false, dmid, rows, mid, mid, h(Y.w1d), L.kphys, 128, 128, nullptr, nullptr, nullptr, f(T.zeros),
-                             f(T.ones), h(T.sA), L.kphys, L.kphys, ceil_div(L.kphys, 128), B.Hp, B.Wp, st));
-        // BN1 + PReLU1 backward, one pass: gblk[:, :k] += sc * g and the three reductions; the mean corrections of the
-        // BatchNorm backward are deferred (bstat corrA / corrB) and applied where a channel's gradient is consumed
+                             f(T.ones), h(Y.dA1), L.kphys, L.kphys, ceil_div(L.kphys, 128), B.Hp, B.Wp, st));
+        // BN1 + PReLU1 backward, reduction half only: parameter gradients + the deferred mean corrections (bstat corrA / corrB)
         {
-          double* sm = dbl(T.sums_scr);
-          TCVN_CUDA(cudaMemsetAsync(sm, 0, sizeof(double) * 3 * L.kphys, st));
-          TCVN_TRY(bn1_bwd_fused(blk, B.ctot, h(T.sA), L.kphys, f1, L.kpad, L.kphys, gblk, B.ctot, rows, B.Hp, B.Wp, sm, st));
-          bn1_param_corr_kernel<<<ceil_div(L.kphys, 128), 128, 0, st>>>(sm, L.kphys, L.norm1.c, B.c0, B.c0p, f1, count,
-                                                                       garena + L.norm1.w, garena + L.norm1.b,
-                                                                       garena + L.norm1.alpha, bstat + 2 * B.ctot,
-                                                                       bstat + 3 * B.ctot);
-          TCVN_LAUNCH_CHECK();
+          int slabs = 0;
+          TCVN_TRY(bn1_bwd_reduce(blk, B.ctot, h(Y.dA1), L.kphys, f1, L.kpad, L.kphys, rows, B.Hp, B.Wp, dbl(T.dparts), &slabs, st));
+          TCVN_TRY(param_reduce(slabs, L.kphys, false, L.norm1, B.c0, B.c0p, f1, count, bstat + 2 * B.ctot, bstat + 3 * B.ctot, 0,
+                                nullptr));
         }
       }
       if (side_pending) TCVN_CUDA(cudaStreamWaitEvent(st, ax->e[2], 0));   // join: parts / dwp / the arena slots are final
-      // the block-input channels leave the block: make their gradient final
-      TCVN_TRY(bn1_correct(gblk, B.ctot, blk, B.ctot, B.c0p, rows, B.Hp, B.Wp, bstat, bstat + B.ctot, bstat + 2 * B.ctot,
-                           bstat + 3 * B.ctot, st));
       if (b > 0) {
         const BlockPlan& Pv = P.blocks[b - 1];
         const T16Block& Xp = T.blocks[b - 1];
         bf* gt = h(T.gt);
-        to_bf16_pad_kernel<<<(unsigned)ceil_div_ll(rows * Xp.gt_pitch, 256), 256, 0, st>>>(gblk, B.ctot, Pv.toutp, rows, Xp.gt_pitch, gt);
-        TCVN_LAUNCH_CHECK();
+        // the block-input channels leave the block: their final gradient, bf16 and zero-padded, for the transition's GEMMs
+        TCVN_TRY(pull(2, b, 0, 0, B.c0p, rows, 0, nullptr, nullptr, gt, Xp.gt_pitch));
         // transition weight gradient dW[k][n] = sum_m pooled[m, k] * Gt[m, n] on the MN-major tensor-core kernel: groups
         // of <= 4 x 128 input channels against 128-column tiles of Gt, scattered into the [ctot][toutp] scratch
         {
@@ -967,18 +1227,21 @@ struct TWalk16 {
                              nullptr, f(T.zeros), f(T.ones), h(T.sA), Pv.ctot, Pv.ctot, ceil_div(Pv.ctot, 128), B.Hp, B.Wp, st));
         TCVN_TRY(pool_typed(2, h(T.sA), nullptr, h(T.sB), true, n, Pv.ctot, Pv.H, Pv.W, B.H, B.W, Pv.ctot, st));
         TCVN_TRY(bn_bwd(h(Xp.blk), true, Pv.ctot, h(T.sB), true, Pv.ctot, f(Xp.fold_t), Pv.ctot, Pv.ctot, (double)n * Pv.H * Pv.W,
-                        (long long)n * Pv.R, Pv.Hp, Pv.Wp, f(Xp.gblk), false, Pv.ctot, false, Pv.tnorm, Pv.c0, Pv.c0p));
+                        (long long)n * Pv.R, Pv.Hp, Pv.Wp, f(Xp.gblk), false, Pv.ctot, Pv.tnorm, Pv.c0, Pv.c0p));
       } else {
         const long long stem_rows = (long long)n * P.Hs * P.Ws;
-        // the gradient of the 64 x 200 x 140 stem map is bf16 here (three dense passes over it: pool backward, the BN0
-        // reductions, the BN0 apply); it feeds only conv0's weight gradient and the BN0 / PReLU0 parameter gradients
+        // the stem side: final fp32 gradient of the 64 pooled stem channels in place, then AvgPool(3,2) backward into the
+        // bf16 gradient of the 64 x 200 x 140 stem map (it feeds only conv0's weight gradient and BN0 / PReLU0)
+        TCVN_TRY(pull(1, b, 0, 0, B.c0p, rows, 0, nullptr, gblk, nullptr, 0));
         bf* dz0 = h(T.dz0);
         TCVN_TRY(pool_typed(1, gblk, nullptr, dz0, true, n, C0, B.H, B.W, P.Hs, P.Ws, B.ctot, st));
         TCVN_TRY(bn_bwd(f(T.z0), false, C0, dz0, true, C0, f(T.fold0), C0, C0, (double)stem_rows, stem_rows, 0, 0, dz0, true, C0,
-                        false, P.norm0, NOGAP, NOGAP));
+                        P.norm0, NOGAP, NOGAP));
+        // conv0 weight gradient, hit-driven and bit-reproducible (train_stem.cu): per-CTA partial sums, added in order
         const int k0 = d.in_channels * 49;
-        TCVN_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)k0 * C0, st));
-        TCVN_TRY(stem_conv_typed(pixels, n, d.in_channels, d.height, d.width, f(T.w0), nullptr, C0, nullptr, dz0, true, dwp, st));
+        int slots = 0;
+        TCVN_TRY(stem_train_wgrad(pixels, n, d.in_channels, d.height, d.width, dz0, C0, f(T.parts), &slots, st));
+        TCVN_TRY(reduce_parts(f(T.parts), slots, (long long)k0 * C0, dwp, false, st));
         TCVN_TRY(unpack(dwp, 1, k0, C0, C0, k0, NOGAP, NOGAP, garena + P.conv0_w));
       }
     }

@@ -39,7 +39,7 @@ struct NetPlan {
   struct LayerWs { size_t qkv, P, ctx, pre1, st1, x1, h, hg, pre2, st2, x2, wqkv_t, wo_t, w1_t, w2_t; } lw[kMaxLayers];
   struct DecWs { size_t z, fold, a, w_t; } dw[TCVN_MAX_DECODER_LAYERS];
   // backward scratch
-  size_t g0, g1, g2, g3, gq, dhid;
+  size_t g0, g1, g2, g3, gq, dhid, dparts;
   size_t bytes;
 
   static bool build(const tcvn_seq_desc& d, int B, int L, int T, NetPlan* P) {
@@ -111,6 +111,7 @@ struct NetPlan {
     P->g0 = take(big * widest); P->g1 = take(big * widest); P->g2 = take(big * widest); P->g3 = take(big * widest);
     P->gq = take(R * 3 * D);
     P->dhid = take(R * D);
+    P->dparts = take(colsum_parts_bytes() / 4);   // per-slab partial sums of the column reductions
     P->bytes = w;
     return true;
   }
@@ -169,6 +170,7 @@ struct NWalk {
 
   float* f(size_t off) const { return reinterpret_cast<float*>(ws + off); }
   double* sums() const { return reinterpret_cast<double*>(ws + P.sums); }
+  double* dparts() const { return reinterpret_cast<double*>(ws + P.dparts); }
   uint8_t* smask() const { return reinterpret_cast<uint8_t*>(ws + P.smask); }
   int* offsets() const { return reinterpret_cast<int*>(ws + P.offsets); }
   uint64_t sid(int k) const { return 3ull * 4096 + (uint64_t)k; }
@@ -181,8 +183,7 @@ struct NWalk {
     return tcvn_t_gemm(X, ldx, rows, K, 1, nullptr, W, N, nullptr, 0, 0, bias, Y, ldy, 0, 0, 0, 0, st);
   }
   int bias_grad(const float* G, int ldg, int col0, int C, long long rows, float* dst) {
-    TCVN_CUDA(cudaMemsetAsync(sums(), 0, sizeof(double) * C, st));
-    TCVN_TRY(colsums_into(2, G, ldg, col0, nullptr, 0, 0, nullptr, C, rows, 0, 0, sums(), C, st));
+    TCVN_TRY(colsums_into(2, G, ldg, col0, nullptr, 0, 0, nullptr, C, rows, 0, 0, sums(), C, dparts(), st));
     add_sums1_kernel<<<ceil_div(C, 128), 128, 0, st>>>(sums(), C, dst);
     TCVN_LAUNCH_CHECK();
     return TCVN_OK;
@@ -198,8 +199,7 @@ struct NWalk {
   }
   int bn_fwd(const float* Z, int C, long long rows, const float* gamma, const float* beta, const float* alpha, float* rm,
              float* rv, float* fold, float* out) {
-    TCVN_CUDA(cudaMemsetAsync(sums(), 0, sizeof(double) * 2 * C, st));
-    TCVN_TRY(colsums_into(0, Z, C, 0, nullptr, 0, 0, nullptr, C, rows, 0, 0, sums(), C, st));
+    TCVN_TRY(colsums_into(0, Z, C, 0, nullptr, 0, 0, nullptr, C, rows, 0, 0, sums(), C, dparts(), st));
     Fin1 a;
     a.sums = sums(); a.C = C; a.count = (double)rows; a.gamma = gamma; a.beta = beta; a.alpha = alpha; a.eps = P.d.bn_eps;
     a.momentum = momentum; a.rm = rm; a.rv = rv; a.fold = fold;
@@ -209,8 +209,7 @@ struct NWalk {
   }
   // in place: D <- gradient w.r.t. the BatchNorm input; parameter gradients accumulated
   int bn_bwd(const float* Z, float* D, int C, long long rows, const float* fold, float* dgamma, float* dbeta, float* dalpha) {
-    TCVN_CUDA(cudaMemsetAsync(sums(), 0, sizeof(double) * 3 * C, st));
-    TCVN_TRY(colsums_into(1, Z, C, 0, D, C, 0, fold, C, rows, 0, 0, sums(), C, st));
+    TCVN_TRY(colsums_into(1, Z, C, 0, D, C, 0, fold, C, rows, 0, 0, sums(), C, dparts(), st));
     return tcvn_t_bnact_bwd_apply(D, C, 0, Z, C, 0, fold, sums(), C, (double)rows, D, C, 0, 0, rows, 0, 0, dgamma, dbeta, dalpha,
                                   st);
   }

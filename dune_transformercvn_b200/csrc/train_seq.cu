@@ -45,10 +45,10 @@ __global__ void ln_fwd_kernel(const float* __restrict__ a, const float* __restri
   if (lane == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
 }
 
-// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma ; dgamma += dy * xhat ; dbeta += dy
+// dx = rstd * (g - mean(g) - xhat * mean(g * xhat)), g = dy * gamma.  The parameter gradients are a column reduction over
+// the rows and are taken by ln_param_grads_kernel in a fixed order (float atomics here made the step irreproducible).
 __global__ void ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ pre, const float* __restrict__ stats,
-                              const float* __restrict__ gamma, int D, int R, float* __restrict__ dx, float* dgamma,
-                              float* dbeta) {
+                              const float* __restrict__ gamma, int D, int R, float* __restrict__ dx) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -65,8 +65,6 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy, const float* __restr
       g[i] = d * gamma[j];
       s1 += g[i];
       s2 = fmaf(g[i], xh[i], s2);
-      atomicAdd(dgamma + j, d * xh[i]);
-      atomicAdd(dbeta + j, d);
     }
   }
 #pragma unroll
@@ -79,6 +77,33 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy, const float* __restr
   for (int i = 0; i < 4; ++i) {
     const int j = lane + 32 * i;
     if (j < D) dx[(size_t)row * D + j] = rstd * (g[i] - s1 - xh[i] * s2);
+  }
+}
+
+// dgamma[j] += sum_r dy[r,j] * xhat[r,j] ; dbeta[j] += sum_r dy[r,j].  A block owns 32 columns, its 8 warps take every
+// 8th row, the 8 partial sums are added in order: one writer per element, fixed summation order.
+__global__ void __launch_bounds__(256) ln_param_grads_kernel(const float* __restrict__ dy, const float* __restrict__ pre,
+                                                             const float* __restrict__ stats, int D, int R, float* dgamma,
+                                                             float* dbeta) {
+  __shared__ float red[2][8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
+  float sg = 0.f, sb = 0.f;
+  if (j < D)
+    for (int r = w; r < R; r += 8) {
+      const float d = dy[(size_t)r * D + j];
+      sg = fmaf(d, (pre[(size_t)r * D + j] - stats[2 * r]) * stats[2 * r + 1], sg);
+      sb += d;
+    }
+  red[0][w][lane] = sg;
+  red[1][w][lane] = sb;
+  __syncthreads();
+  if (w == 0 && j < D) {
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a += red[0][k][lane]; b += red[1][k][lane]; }
+    dgamma[j] += a;
+    dbeta[j] += b;
   }
 }
 
@@ -137,47 +162,69 @@ __global__ void attn_fwd_kernel(const float* __restrict__ qkv, const uint8_t* __
   }
 }
 
-// backward of the above.  One thread per query row computes dQ; dK and dV are accumulated with atomics (the caller
-// zeroes dqkv).  The dropout mask is re-derived from (seed, stream, index).
-__global__ void attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ P, const float* __restrict__ dctx,
-                                const uint8_t* __restrict__ mask, int S, int heads, int D, float p_drop,
-                                unsigned long long seed, unsigned long long stream_id, float* __restrict__ dqkv) {
+// backward of the above, one (event, head) per warp.  Pass 1: query s derives its rows of dP (through the dropout mask,
+// re-derived from (seed, stream, index)) and dS into shared memory and its own dQ.  Pass 2: key t gathers dK[t] and
+// dV[t] over the queries in order - every element of dqkv has one writer and a fixed summation order (no atomics, no
+// memset of dqkv).
+__global__ void __launch_bounds__(32) attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ P,
+                                                      const float* __restrict__ dctx, const uint8_t* __restrict__ mask, int S,
+                                                      int heads, int D, float p_drop, unsigned long long seed,
+                                                      unsigned long long stream_id, float* __restrict__ dqkv) {
+  __shared__ float pv_s[32][33];   // [query][key]: what multiplied V in the forward pass
+  __shared__ float ds_s[32][33];   // [query][key]: gradient of the scaled scores
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int s = threadIdx.x;
-  if (s >= S) return;
   const int dh = D / heads;
   const float scale = rsqrtf((float)dh);
-  const float* prow = P + (((size_t)b * heads + h) * S + s) * S;
-  const float* dc = dctx + ((size_t)(b * S + s)) * D + h * dh;
-  const float* q = qkv + ((size_t)(b * S + s)) * 3 * D + h * dh;
-  float dP[32];
-  float dot = 0.f;  // sum_t dPsoft[t] * Psoft[t]
-  for (int t = 0; t < S; ++t) {
-    const float psoft = prow[t];
-    float keep = 1.f;
-    if (p_drop > 0.f)
-      keep = drop_keep(seed, stream_id, (((size_t)b * heads + h) * S + s) * S + t, p_drop) ? 1.f / (1.f - p_drop) : 0.f;
-    float d = 0.f;
-    const float* v = qkv + ((size_t)(b * S + t)) * 3 * D + 2 * D + h * dh;
-    for (int j = 0; j < dh; ++j) d = fmaf(dc[j], v[j], d);
-    const float pv = psoft * keep;  // what multiplied V in the forward pass
-    if (pv != 0.f)
-      for (int j = 0; j < dh; ++j) atomicAdd(dqkv + ((size_t)(b * S + t)) * 3 * D + 2 * D + h * dh + j, pv * dc[j]);
-    dP[t] = d * keep;
-    dot = fmaf(dP[t], psoft, dot);
+  if (s < S) {
+    const float* prow = P + (((size_t)b * heads + h) * S + s) * S;
+    const float* dc = dctx + ((size_t)(b * S + s)) * D + h * dh;
+    float dP[32];
+    float dot = 0.f;  // sum_t dPsoft[t] * Psoft[t]
+    for (int t = 0; t < S; ++t) {
+      const float psoft = prow[t];
+      float keep = 1.f;
+      if (p_drop > 0.f)
+        keep = drop_keep(seed, stream_id, (((size_t)b * heads + h) * S + s) * S + t, p_drop) ? 1.f / (1.f - p_drop) : 0.f;
+      float d = 0.f;
+      const float* v = qkv + ((size_t)(b * S + t)) * 3 * D + 2 * D + h * dh;
+      for (int j = 0; j < dh; ++j) d = fmaf(dc[j], v[j], d);
+      pv_s[s][t] = psoft * keep;
+      dP[t] = d * keep;
+      dot = fmaf(dP[t], psoft, dot);
+    }
+    float dq[16];
+    for (int j = 0; j < dh; ++j) dq[j] = 0.f;
+    for (int t = 0; t < S; ++t) {
+      float dS = 0.f;
+      if (mask[b * S + t]) {
+        dS = prow[t] * (dP[t] - dot) * scale;
+        const float* k = qkv + ((size_t)(b * S + t)) * 3 * D + D + h * dh;
+        for (int j = 0; j < dh; ++j) dq[j] = fmaf(dS, k[j], dq[j]);
+      }
+      ds_s[s][t] = dS;
+    }
+    for (int j = 0; j < dh; ++j) dqkv[((size_t)(b * S + s)) * 3 * D + h * dh + j] = dq[j];
   }
-  float dq[16];
-  for (int j = 0; j < dh; ++j) dq[j] = 0.f;
-  for (int t = 0; t < S; ++t) {
-    if (!mask[b * S + t]) continue;
-    const float dS = prow[t] * (dP[t] - dot);
-    const float* k = qkv + ((size_t)(b * S + t)) * 3 * D + D + h * dh;
+  __syncwarp();
+  if (s < S) {
+    const int t = s;   // this thread's key / value row
+    float dk[16], dv[16];
+    for (int j = 0; j < dh; ++j) { dk[j] = 0.f; dv[j] = 0.f; }
+    for (int q = 0; q < S; ++q) {
+      const float pv = pv_s[q][t], dS = ds_s[q][t];
+      const float* dc = dctx + ((size_t)(b * S + q)) * D + h * dh;
+      const float* qq = qkv + ((size_t)(b * S + q)) * 3 * D + h * dh;
+      for (int j = 0; j < dh; ++j) {
+        dv[j] = fmaf(pv, dc[j], dv[j]);
+        dk[j] = fmaf(dS, qq[j], dk[j]);
+      }
+    }
     for (int j = 0; j < dh; ++j) {
-      dq[j] = fmaf(dS * scale, k[j], dq[j]);
-      atomicAdd(dqkv + ((size_t)(b * S + t)) * 3 * D + D + h * dh + j, dS * scale * q[j]);
+      dqkv[((size_t)(b * S + t)) * 3 * D + D + h * dh + j] = dk[j];
+      dqkv[((size_t)(b * S + t)) * 3 * D + 2 * D + h * dh + j] = dv[j];
     }
   }
-  for (int j = 0; j < dh; ++j) atomicAdd(dqkv + ((size_t)(b * S + s)) * 3 * D + h * dh + j, dq[j]);
 }
 
 // elementwise helpers: kind 0 gelu fwd (out = gelu(x)); 1 gelu bwd (out = d * gelu'(x)); 2 out = a + b; 3 rows *= mask
@@ -276,7 +323,11 @@ extern "C" int tcvn_t_layernorm(int dir, const float* a, const float* b, int D, 
   TCVN_CHECK_ARG(a && gamma && pre && stats && out && D <= 128, "t_layernorm: bad arguments");
   if (R <= 0) return TCVN_OK;
   if (dir == 0) ln_fwd_kernel<<<ceil_div(R, 8), 256, 0, stream>>>(a, b, D, R, gamma, beta, eps, pre, stats, out);
-  else ln_bwd_kernel<<<ceil_div(R, 8), 256, 0, stream>>>(a, pre, stats, gamma, D, R, out, dgamma, dbeta);
+  else {
+    ln_bwd_kernel<<<ceil_div(R, 8), 256, 0, stream>>>(a, pre, stats, gamma, D, R, out);
+    TCVN_LAUNCH_CHECK();
+    if (dgamma && dbeta) ln_param_grads_kernel<<<ceil_div(D, 32), 256, 0, stream>>>(a, pre, stats, D, R, dgamma, dbeta);
+  }
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
 }
@@ -289,7 +340,6 @@ extern "C" int tcvn_t_attention(int dir, const float* qkv, const uint8_t* mask, 
   if (dir == 0) attn_fwd_kernel<<<B * heads, 32, 0, stream>>>(qkv, mask, S, heads, D, P, ctx_or_dctx, p_drop, seed, stream_id);
   else {
     TCVN_CHECK_ARG(dqkv, "t_attention: dqkv missing");
-    TCVN_CUDA(cudaMemsetAsync(dqkv, 0, sizeof(float) * (size_t)B * S * 3 * D, stream));
     attn_bwd_kernel<<<B * heads, 32, 0, stream>>>(qkv, P, ctx_or_dctx, mask, S, heads, D, p_drop, seed, stream_id, dqkv);
   }
   TCVN_LAUNCH_CHECK();

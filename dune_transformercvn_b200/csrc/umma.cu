@@ -79,15 +79,27 @@ int make_map(const void* base, long long rows, int cols, int pitch, int box_cols
 // under the other stream's kernels.
 static thread_local int g_sm_limit = 0;
 
+constexpr int kMaxDevices = 64;
+
 int sm_count() {
-  static int n = 0;
+  static int per_device[kMaxDevices] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int& n = per_device[dev >= 0 && dev < kMaxDevices ? dev : 0];
   if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
   }
   return g_sm_limit > 0 && g_sm_limit < n ? g_sm_limit : n;
+}
+
+// one-time-per-device flags of the launchers (cudaFuncSetAttribute is per device); `site` = a launcher id in [0, 8)
+bool& device_flag(int site) {
+  static bool flags[kMaxDevices][8] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDevices) dev = 0;
+  return flags[dev][site & 7];
 }
 
 }  // namespace tcvn
@@ -127,9 +139,10 @@ struct GemmParams {
   const float *a_scale, *a_shift, *a_alpha;  // [kchunks*64] (TRANSFORM only)
   const float *o_shift, *o_alpha;            // [n_tiles_n*128]
   int Hp, Wp, num_tiles;   // num_tiles = m tiles * n_tiles_n
-  // training: per-column (sum, sum^2) of the bf16 values this kernel stores (ring rows are zero), accumulated into
-  // stats[0..128) and stats[stats_stride..+128) - the batch statistics of the BatchNorm that follows (n_tiles_n == 1)
-  double* stats; int stats_stride;
+  // training: per-column (sum, sum^2) of the bf16 values this kernel stores (ring rows are zero) - the batch statistics of
+  // the BatchNorm that follows (n_tiles_n == 1).  Every (CTA, epilogue group) stores its partial sums in its own slot,
+  // stats[(2 * cta + group)][2][128]; the consumer adds the slots in a fixed order (no atomics: bit-reproducible).
+  double* stats;
 };
 
 __device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
@@ -429,7 +442,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
     }
     if (issuer) ptx::tma_store_wait_all();
     if (p.stats != nullptr) {
-      // per-CTA reduction through the (now idle) staging tile in a fixed order, then one double atomic per column
+      // per-group reduction through the (now idle) staging tile in a fixed order, then one store per column into the slot
       ptx::named_bar_sync(1 + grp, 128);          // the issuer's stores have drained the staging tile
       float* red = reinterpret_cast<float*>(stg);  // [128 threads][16]
 #pragma unroll
@@ -443,10 +456,9 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
         a += (double)red[(cgp + 16 * j) * 16 + cq];
         b += (double)red[(cgp + 16 * j) * 16 + 8 + cq];
       }
-      if (it > 0) {
-        atomicAdd(p.stats + e_col, a);
-        atomicAdd(p.stats + p.stats_stride + e_col, b);
-      }
+      double* slot = p.stats + (size_t)(2 * blockIdx.x + grp) * 2 * kMid;   // zeros when this group drained no tile
+      slot[e_col] = a;
+      slot[kMid + e_col] = b;
     }
   }
   ptx::tc_fence_before();
@@ -482,9 +494,10 @@ struct Conv2Params {
   bf16* out;
   int ldo, col0, num_tiles;
   // training: Dropout(p) on the 32 new channels (mask = hash(seed, site, row * 32 + channel), re-derived in backward) and
-  // their per-column (sum, sum^2) as stored (bf16), accumulated into stats[0..32) / stats[stats_stride..+32)
+  // their per-column (sum, sum^2) as stored (bf16): every epilogue warp stores its partial sums in its own slot,
+  // stats[(8 * cta + 4 * group + warp)][2][32], added in a fixed order by the consumer (no atomics)
   float p_drop; unsigned long long seed, site;
-  double* stats; int stats_stride;
+  double* stats;
 };
 
 __device__ __forceinline__ bool drop_keep_c2(unsigned long long seed, unsigned long long site, unsigned long long idx, float p) {
@@ -705,8 +718,9 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
       acc_phase ^= 1;
     }
     if (p.stats != nullptr) {
-      atomicAdd(p.stats + lane, st_sum);
-      atomicAdd(p.stats + p.stats_stride + lane, st_sq);
+      double* slot = p.stats + (size_t)(8 * blockIdx.x + 4 * grp + g) * 2 * kGrowth;
+      slot[lane] = st_sum;
+      slot[kGrowth + lane] = st_sq;
     }
   }
   ptx::tc_fence_before();
@@ -722,12 +736,12 @@ static inline const float* pf(const char* packed, size_t off) { return reinterpr
 int launch_gemm(bool transform, const void* A, long long rows, int a_cols, int a_pitch, const void* W, int w_rows,
                        int kpad, int kphys, const float* a_scale, const float* a_shift, const float* a_alpha,
                        const float* o_shift, const float* o_alpha, void* out, int out_cols, int out_pitch, int n_tiles_n,
-                       int Hp, int Wp, cudaStream_t st, double* stats, int stats_stride) {
+                       int Hp, int Wp, cudaStream_t st, double* stats, int* stat_slots) {
   if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one chunk");
   if (stats != nullptr && n_tiles_n != 1) return fail(TCVN_ERR_UNSUPPORTED, "epilogue statistics need a single N tile");
   const size_t smem = 1024 + kC1Stages * (kStageA + kStageW) + 4 * kStageA + kStageA + kStageW + 2 * 192 * 4 +
                       (3 * kC1Stages + 4) * 8 + 16;
-  static bool attr_done = false;
+  bool& attr_done = device_flag(1);   // per device: the attribute belongs to the device's copy of the function
   if (!attr_done) {
     TCVN_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     TCVN_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -743,9 +757,10 @@ int launch_gemm(bool transform, const void* A, long long rows, int a_cols, int a
   g.m_total = rows; g.kchunks = kpad / kKChunk; g.kphys = kphys; g.n_tiles_n = n_tiles_n;
   g.a_scale = a_scale; g.a_shift = a_shift; g.a_alpha = a_alpha; g.o_shift = o_shift; g.o_alpha = o_alpha;
   g.Hp = Hp; g.Wp = Wp;
-  g.stats = stats; g.stats_stride = stats_stride;
+  g.stats = stats;
   g.num_tiles = (int)ceil_div_ll(rows, kTileM) * n_tiles_n;
   const int grid = g.num_tiles < sm_count() ? g.num_tiles : sm_count();
+  if (stat_slots) *stat_slots = 2 * grid;
   static const bool mma_shift_on = [] { const char* v = getenv("TCVN_MMA_SHIFT"); return !(v && v[0] == '0'); }();
   const bool ms = mma_shift_on && n_tiles_n == 1;
   if (transform && ms) umma_gemm_kernel<true, true><<<grid, kC1Threads, smem, st>>>(tmA, tmW, tmO, g);
@@ -781,12 +796,13 @@ int umma_dense_layer_part(const CnnPlan& P, const BlockPlan& B, const LayerPlan&
 // w2 bf16 [9*32][128] (tap-major, K contiguous), out bf16 with pitch ldo
 int umma_conv2_fwd(const void* mid, long long rows, const void* w2, const float* bias, void* out, int ldo, int col0, int Hp,
                    int Wp, int W, cudaStream_t st, float p_drop, unsigned long long seed, unsigned long long site,
-                   double* stats, int stats_stride) {
+                   double* stats, int* stat_slots) {
   if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one chunk");
   const int tiles = (int)ceil_div_ll(rows, kC2Out);
   const int grid = tiles < sm_count() ? tiles : sm_count();
+  if (stat_slots) *stat_slots = 8 * grid;
   const int halo_rows_max = 288;
-  static bool attr_done = false;
+  bool& attr_done = device_flag(2);   // per device: the attribute belongs to the device's copy of the function
   if (!attr_done) {
     TCVN_CUDA(cudaFuncSetAttribute(umma_conv2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)kC2SmemMax));
@@ -807,7 +823,7 @@ int umma_conv2_fwd(const void* mid, long long rows, const void* w2, const float*
   }
   c2.bias = bias;
   c2.out = static_cast<bf16*>(out); c2.ldo = ldo; c2.col0 = col0; c2.num_tiles = tiles;
-  c2.p_drop = p_drop; c2.seed = seed; c2.site = site; c2.stats = stats; c2.stats_stride = stats_stride;
+  c2.p_drop = p_drop; c2.seed = seed; c2.site = site; c2.stats = stats;
   // Measured on B200: the 128B swizzle of a UMMA operand is a function of the absolute shared-memory address
   // (bits [4,7) ^= bits [7,10)), exactly as TMA wrote it, so a descriptor may start at ANY row of the haloed
   // tile with matrix-base-offset 0 (setting it to (addr >> 7) & 7 gives wrong results).

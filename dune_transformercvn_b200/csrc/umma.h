@@ -15,15 +15,19 @@ int umma_transition(const CnnPlan& P, const BlockPlan& B, const BlockPlan& Nx, c
 // shared with the training kernels (umma_train.cu)
 int make_map(const void* base, long long rows, int cols, int pitch, int box_cols, int box_rows, CUtensorMap* out);
 int sm_count();
+bool& device_flag(int site);
 // out[m, n] = PReLU_n( sum_k act_k(A[m, k]) * W[n, k] + shift[n] ), bf16 in / bf16 out, N tiles of 128 (see umma.cu)
 int launch_gemm(bool transform, const void* A, long long rows, int a_cols, int a_pitch, const void* W, int w_rows, int kpad,
                 int kphys, const float* a_scale, const float* a_shift, const float* a_alpha, const float* o_shift,
                 const float* o_alpha, void* out, int out_cols, int out_pitch, int n_tiles_n, int Hp, int Wp, cudaStream_t st,
-                double* stats = nullptr, int stats_stride = 0);
+                double* stats = nullptr, int* stat_slots = nullptr);
+// slots of the epilogue statistics (doubles [slots][2][128] for launch_gemm, [slots][2][32] for umma_conv2_fwd)
+constexpr int kUmmaStatSlotsMax = 8 * 148;
 int umma_conv2_fwd(const void* mid, long long rows, const void* w2, const float* bias, void* out, int ldo, int col0, int Hp,
                    int Wp, int W, cudaStream_t st, float p_drop = 0.f, unsigned long long seed = 0, unsigned long long site = 0,
-                   double* stats = nullptr, int stats_stride = 0);
+                   double* stats = nullptr, int* stat_slots = nullptr);
 size_t umma_wgrad_parts_bytes(int n_items);
+int reduce_parts(const float* parts, int n_parts, long long n, float* out, bool accumulate, cudaStream_t st);
 int umma_wgrad(const void* A, long long rows, int a_cols, int a_pitch, int n_items, const int* item_col, const int* item_shift,
                const int* item_valid, const float* a_scale, const float* a_shift, const float* a_alpha, int a_fold_cols,
                const void* G, int g_cols, int g_pitch, int g_col0, float* parts, float* dw, bool accumulate, cudaStream_t st);

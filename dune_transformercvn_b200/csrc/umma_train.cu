@@ -374,6 +374,16 @@ __global__ void __launch_bounds__(256) reduce_parts_kernel(const float4* __restr
 
 }  // namespace
 
+// out[i] (+)= sum_q parts[q][i], q in a fixed order (n floats per part, n % 4 == 0)
+int reduce_parts(const float* parts, int n_parts, long long n, float* out, bool accumulate, cudaStream_t st) {
+  if (n % 4) return fail(TCVN_ERR_ARG, "reduce_parts: %lld floats (must be a multiple of 4)", n);
+  const long long n4 = n / 4;
+  reduce_parts_kernel<<<(unsigned)ceil_div_ll(n4, 32), 256, 0, st>>>(reinterpret_cast<const float4*>(parts), n_parts, n4,
+                                                                     reinterpret_cast<float4*>(out), accumulate ? 1 : 0);
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
 constexpr int kWgMaxCtas = 148;  // per-CTA partial sums: the scratch is sized for this many
 size_t umma_wgrad_parts_bytes(int n_items) { return (size_t)kWgMaxCtas * n_items * 128 * 128 * sizeof(float); }
 
@@ -400,7 +410,7 @@ int umma_wgrad(const void* A, long long rows, int a_cols, int a_pitch, int n_ite
   if (stages < 2) return fail(TCVN_ERR_UNSUPPORTED, "umma_wgrad: stage of %d bytes leaves no room to pipeline", stage_bytes);
   p.stages = stages;
   const size_t smem = 1024 + (size_t)stages * stage_bytes + 26 * 8 + 16;
-  static bool attr_done = false;
+  bool& attr_done = device_flag(3);   // per device: the attribute belongs to the device's copy of the function
   if (!attr_done) {
     TCVN_CUDA(cudaFuncSetAttribute(umma_wgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     TCVN_CUDA(cudaFuncSetAttribute(umma_wgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -439,7 +449,7 @@ int umma_conv2_dgrad(const void* g2x, const void* wd, long long rows, int Hp, in
     return fail(TCVN_ERR_UNSUPPORTED, "feature map width %d needs a %d-row halo tile (max %d)", Wp - 2, p.halo_rows, halo_rows_max);
   p.out = static_cast<bf16*>(out); p.ldo = 128;
   p.num_tiles = (int)ceil_div_ll(rows, 128);
-  static bool attr_done = false;
+  bool& attr_done = device_flag(4);
   const size_t smem_max = 1024 + kDgWBytes + (size_t)kDgStages * halo_rows_max * 128 + 256;
   if (!attr_done) {
     TCVN_CUDA(cudaFuncSetAttribute(umma_conv2_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max));

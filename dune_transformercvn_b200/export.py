@@ -37,6 +37,7 @@ class _Plan:
         self.pixels = None
         self.out: Tuple[torch.Tensor, ...] = ()
         self.graph = None
+        self.generation = -1   # engine.generation at capture: the graph bakes in workspace / packed-block pointers
 
 
 class EventClassifier(nn.Module):
@@ -109,6 +110,10 @@ class EventClassifier(nn.Module):
             return ev, pr, h_ev.clone(), h_pr.clone()   # the two hidden vectors are views of one buffer
         key = (n, str(pixels.dtype), str(pixels.device))
         plan = self._plans.get(key)
+        if plan is not None and plan.generation != self.network.engine.generation:
+            # a workspace grew (a plan for more prongs, a batched forward on the same network) or the parameters were
+            # re-packed since this graph was captured: its pointers may be dangling.  Capture again over the current buffers.
+            plan = None
         if plan is None:
             plan = _Plan()
             plan.pixels = torch.empty_like(pixels, memory_format=torch.contiguous_format)
@@ -128,6 +133,7 @@ class EventClassifier(nn.Module):
                 with torch.cuda.graph(g):
                     plan.out = self._run(plan.pixels)
                 plan.graph = g
+                plan.generation = self.network.engine.generation
             self._plans[key] = plan
         else:
             plan.pixels.copy_(pixels)

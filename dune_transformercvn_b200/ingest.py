@@ -15,8 +15,10 @@ from . import lib as _lib
 
 
 def densify(values: torch.Tensor, coords: torch.Tensor, image_size: Sequence[int], num_images: Optional[int] = None,
-            divisor: float = 0.0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """(nnz,C) values [f32|u8] + (nnz,3) int32 [image,y,x] -> (N,C,H,W) fp32, value/divisor fused."""
+            divisor: float = 0.0, out: Optional[torch.Tensor] = None, noise_std: float = 0.0, seed: int = 0) -> torch.Tensor:
+    """(nnz,C) values [f32|u8] + (nnz,3) int32 [image,y,x] (sorted by image, as the reference's file format stores them)
+    -> (N,C,H,W) fp32, value/divisor fused.  ``noise_std`` > 0 also fuses the training-time multiplicative pixel noise of
+    ``preprocess_pixels`` (neutrino_full_dense_trainer.py:62-65), drawn from a counter hash of (seed, hit, channel)."""
     _lib.require_cuda(values, "densify(values)")
     _lib.require_cuda(coords, "densify(coords)")
     L = _lib.load()
@@ -38,8 +40,10 @@ def densify(values: torch.Tensor, coords: torch.Tensor, image_size: Sequence[int
     c = values.shape[1] if values.dim() == 2 else 1
     if out is None:
         out = torch.empty((num_images, c, h, w), dtype=torch.float32, device=values.device)
-    _lib.check(L.tcvn_densify(_lib.ptr(coords), _lib.ptr(values), vd, nnz, c, num_images, h, w, float(divisor),
-                              _lib.ptr(out), _lib.TCVN_NCHW_F32, _lib.stream_ptr(values.device)), "tcvn_densify")
+    with torch.cuda.device(values.device):
+        _lib.check(L.tcvn_densify_noise(_lib.ptr(coords), _lib.ptr(values), vd, nnz, c, num_images, h, w, float(divisor),
+                                        float(noise_std), int(seed) & 0xFFFFFFFFFFFFFFFF, _lib.ptr(out), _lib.TCVN_NCHW_F32,
+                                        _lib.stream_ptr(values.device)), "tcvn_densify_noise")
     return out
 
 

@@ -22,14 +22,14 @@ MAX_BLOCKS, MAX_DECODER_LAYERS = 8, 8
 
 # every symbol include/tcvn.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = (
-    "tcvn_abi_version", "tcvn_last_error", "tcvn_launch_count", "tcvn_densify",
+    "tcvn_abi_version", "tcvn_last_error", "tcvn_launch_count", "tcvn_densify", "tcvn_densify_noise",
     "tcvn_collate_workspace_bytes", "tcvn_collate_coords",
     "tcvn_cnn_arena_floats", "tcvn_cnn_packed_bytes", "tcvn_cnn_pack", "tcvn_cnn_workspace_bytes",
     "tcvn_cnn_forward", "tcvn_cnn_forward_sparse", "tcvn_cnn_workspace_bytes_sparse", "tcvn_cnn_run_layer", "tcvn_cnn_read_stage",
     "tcvn_seq_packed_bytes", "tcvn_seq_pack", "tcvn_seq_workspace_bytes", "tcvn_seq_forward",
     "tcvn_t_gemm", "tcvn_t_wgrad", "tcvn_t_colsums", "tcvn_t_bn_finalize", "tcvn_t_bnact_bwd_apply", "tcvn_t_add_colsums",
     "tcvn_t_bnact_fwd", "tcvn_t_pool", "tcvn_t_dropout", "tcvn_t_stem_conv", "tcvn_t_layernorm", "tcvn_t_attention",
-    "tcvn_t_eltwise", "tcvn_t_tokens", "tcvn_t_act_pool2", "tcvn_t_act_gap", "tcvn_sumsq", "tcvn_adamw_step",
+    "tcvn_t_eltwise", "tcvn_t_tokens", "tcvn_t_act_pool2", "tcvn_t_act_gap", "tcvn_adamw_workspace_bytes", "tcvn_adamw_fused",
     "tcvn_cnn_train_workspace_bytes", "tcvn_cnn_train_forward", "tcvn_cnn_train_backward",
     "tcvn_seq_train_workspace_bytes", "tcvn_seq_train_forward", "tcvn_seq_train_backward",
     "tcvn_t_umma_wgrad", "tcvn_t_umma_wgrad_workspace_bytes", "tcvn_t_umma_conv2_dgrad",
@@ -72,6 +72,7 @@ def load() -> C.CDLL:
     lib.tcvn_last_error.restype = C.c_char_p
     lib.tcvn_launch_count.restype = C.c_longlong
     lib.tcvn_densify.argtypes = [vp, vp, i32, i64, i32, i32, i32, i32, f32, vp, i32, vp]
+    lib.tcvn_densify_noise.argtypes = [vp, vp, i32, i64, i32, i32, i32, i32, f32, f32, C.c_uint64, vp, i32, vp]
     lib.tcvn_collate_workspace_bytes.argtypes = [i32]
     lib.tcvn_collate_workspace_bytes.restype = sz
     lib.tcvn_collate_coords.argtypes = [vp, i64, vp, vp, vp, i32, i32, vp, vp, sz, vp]
@@ -113,8 +114,9 @@ def load() -> C.CDLL:
     lib.tcvn_t_tokens.argtypes = [i32, i32, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]
     lib.tcvn_t_act_pool2.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, i32, i32, vp]
     lib.tcvn_t_act_gap.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp]
-    lib.tcvn_sumsq.argtypes = [vp, i64, vp, i32, vp]
-    lib.tcvn_adamw_step.argtypes = [vp, vp, vp, vp, i64, f64, f64, f64, f64, f64, i64, vp, f32, f32, vp, i32, vp]
+    lib.tcvn_adamw_workspace_bytes.argtypes = []
+    lib.tcvn_adamw_workspace_bytes.restype = sz
+    lib.tcvn_adamw_fused.argtypes = [vp, vp, vp, vp, i64, vp, i32, vp, vp, vp, vp, vp, vp, f32, f32, vp, sz, vp]
     lib.tcvn_t_umma_wgrad.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp, vp, sz, vp]
     lib.tcvn_t_umma_wgrad_workspace_bytes.argtypes = [i32]
     lib.tcvn_t_umma_wgrad_workspace_bytes.restype = sz

@@ -54,6 +54,10 @@ class _Engine:
         self.packed: Dict[str, torch.Tensor] = {}
         self.ws: Dict[Tuple, torch.Tensor] = {}
         self.frozen = False
+        # bumped whenever a workspace or a packed parameter block is (re)allocated: captured CUDA graphs bake those
+        # pointers in, so every plan records the generation it was captured under and is re-captured when it is stale
+        self.generation = 0
+        self._tensors: Optional[List[torch.Tensor]] = None
 
     # ---- descriptors ------------------------------------------------------------------------
     def cnn_desc(self, out_features: int) -> _lib.CnnDesc:
@@ -93,24 +97,31 @@ class _Engine:
         specs = [s for s in self.owner[0].specs if s.name.startswith(prefix) and s.in_arena]
         return torch.cat([tensors[s.name].detach().reshape(-1).float() for s in specs])
 
-    def _state_key(self, tensors: Dict[str, torch.Tensor], prec: int):
+    def _state_key(self, prec: int):
+        """(device, precision, sum of the tensors' in-place version counters, xor of their addresses): changes whenever
+        an optimizer step, ``load_state_dict`` or ``.to()`` touched any parameter or buffer.  The tensor objects are
+        listed once (the module tree never changes after construction); walking ``named_parameters()`` on every call
+        cost more host time than launching the step."""
+        if self._tensors is None:
+            net = self.owner[0]
+            self._tensors = [t for _, t in net.named_parameters()] + [t for _, t in net.named_buffers()]
         v = 0
         p = 0
-        for t in tensors.values():
+        for t in self._tensors:
             v += t._version
             p ^= t.data_ptr()
-        first = next(iter(tensors.values()))
-        return (str(first.device), prec, v, p)
+        return (str(self._tensors[0].device), prec, v, p)
 
     def ensure_packed(self, prec: int) -> None:
         net = self.owner[0]
         if self.frozen and self.key is not None and self.key[1] == prec:
             return
-        tensors = dict(net.named_parameters())
-        tensors.update(dict(net.named_buffers()))
-        key = self._state_key(tensors, prec)
+        key = self._state_key(prec)
         if key == self.key:
             return
+        tensors = dict(net.named_parameters())
+        tensors.update(dict(net.named_buffers()))
+        self.generation += 1
         L = _lib.load()
         dev = next(iter(tensors.values())).device
         if dev.type != "cuda":
@@ -150,6 +161,7 @@ class _Engine:
         if buf is None or buf.numel() < nbytes:
             buf = torch.zeros(nbytes, dtype=torch.uint8, device=dev)  # zero-filled once: ring rows stay finite
             self.ws[k] = buf
+            self.generation += 1   # graphs captured over the old buffer must not be replayed
         return buf
 
     # ---- kernels -----------------------------------------------------------------------------
@@ -358,6 +370,8 @@ class NeutrinoDenseNetwork(nn.Module):
         # persistent kernels of the other), so it is off by default
         self.partition_sms = False
         self._side = None
+        self._plans: Dict[Tuple, dict] = {}   # CUDA-graph plans of forward_sparse(graph=True), one per batch shape
+        self.graph_launches_per_replay = 0
         for name, cls in (("prong_embedding", ProngEmbedding), ("encoder", ProngEncoder),
                           ("event_decoder", EventDecoder), ("prong_decoder", ProngDecoder)):
             m = cls()
@@ -406,18 +420,75 @@ class NeutrinoDenseNetwork(nn.Module):
                                              prong_mask)
         return ev_logits, pr_logits
 
-    def forward_sparse(self, batch: "synth.SparseBatch", materialize: bool = False):
+    def forward_sparse(self, batch: "synth.SparseBatch", materialize: bool = False, graph: bool = False):
         """Trainer-level path (neutrino_full_base_trainer.py:113-116): /255 + sparse_to_dense + network.
 
         By default the stem consumes the hit lists directly (no dense map, no host sync);
-        ``materialize=True`` runs the literal sequence densify kernel -> dense forward instead."""
+        ``materialize=True`` runs the literal sequence densify kernel -> dense forward instead.
+        ``graph=True`` (eval only): the ~200 kernel launches of the step are captured once per batch SHAPE (events,
+        prong slots, images, hit counts) into a CUDA graph and replayed with one launch - the serving loop is then bound
+        by the kernels, not by the host issuing them.  A batch of another shape is captured on first sight (pad hit
+        lists with zero-valued hits / bucket the batch size upstream to bound the number of plans)."""
         if materialize:
             from .ingest import densify
-            ev = densify(batch.event_values, batch.event_coords, self.image_size, batch.num_events, 255.0)
-            pr = densify(batch.prong_values, batch.prong_coords, self.image_size, batch.num_prongs, 255.0)
+            # preprocess_pixels (neutrino_full_dense_trainer.py:59-66): /255, and in training the multiplicative Gaussian
+            # pixel noise, both fused into the densify kernel (a fresh counter-hash stream per step and per map kind)
+            std = float(getattr(self.options, "pixel_noise_std", 0.0)) if self.training else 0.0
+            seed = (torch.initial_seed() * 1000003 + self.train_engine.step_index + 1) * 2
+            ev = densify(batch.event_values, batch.event_coords, self.image_size, batch.num_events, 255.0, noise_std=std, seed=seed)
+            pr = densify(batch.prong_values, batch.prong_coords, self.image_size, batch.num_prongs, 255.0, noise_std=std,
+                         seed=seed + 1)
             return self.forward(batch.features, batch.extra, ev, batch.event_mask, pr, batch.prong_mask)
         if self.training:
             return self.forward_sparse(batch, materialize=True)
+        _lib.require_cuda(batch.event_values, "hit values")
+        with torch.cuda.device(batch.event_values.device):
+            if graph:
+                return self._forward_sparse_graph(batch)
+            return self._forward_sparse_eager(batch)
+
+    def _forward_sparse_graph(self, batch: "synth.SparseBatch"):
+        eng = self.engine
+        prec = _PRECISIONS[self.precision]
+        eng.ensure_packed(prec)     # a changed parameter re-packs and bumps eng.generation: stale plans are dropped below
+        key = (batch.num_events, batch.prong_mask.shape[1], batch.num_prongs, batch.event_coords.shape[0],
+               batch.prong_coords.shape[0], str(batch.event_values.dtype), str(batch.event_values.device), prec)
+        plan = self._plans.get(key)
+        if plan is not None and plan["generation"] != eng.generation:
+            plan = None
+        if plan is None:
+            dev = batch.event_values.device
+            static = synth.SparseBatch(*[t.clone().contiguous() for t in batch.tensors()], list(batch.prongs_per_event))
+            with torch.no_grad():
+                warm = torch.cuda.Stream(device=dev)
+                warm.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(warm):          # allocates the workspaces, sets the kernel attributes
+                    for _ in range(2):
+                        self._forward_sparse_eager(static)
+                torch.cuda.current_stream(dev).wait_stream(warm)
+                gen = eng.generation
+                was_frozen = eng.frozen
+                eng.frozen = True                       # no re-pack inside the capture
+                l0 = _lib.load().tcvn_launch_count()
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        out = self._forward_sparse_eager(static)
+                finally:
+                    eng.frozen = was_frozen
+                launches = _lib.load().tcvn_launch_count() - l0   # kernels of this library one replay executes
+            if len(self._plans) >= 16:                  # bounded: drop the oldest plan
+                self._plans.pop(next(iter(self._plans)))
+            plan = {"graph": g, "static": static, "out": out, "generation": gen, "launches": launches}
+            self._plans[key] = plan
+        else:
+            for dst, src in zip(plan["static"].tensors(), batch.tensors()):
+                dst.copy_(src, non_blocking=True)
+        plan["graph"].replay()
+        self.graph_launches_per_replay = plan["launches"]
+        return plan["out"][0].clone(), plan["out"][1].clone()
+
+    def _forward_sparse_eager(self, batch: "synth.SparseBatch"):
         eng = self.engine
         prec = _PRECISIONS[self.precision]
         _lib.require_cuda(batch.event_values, "event hit values")
@@ -447,7 +518,8 @@ class NeutrinoDenseNetwork(nn.Module):
             finally:
                 L.tcvn_set_sm_limit(0)
             main.wait_stream(side)
-            ev.record_stream(main)
+            if not torch.cuda.is_current_stream_capturing():
+                ev.record_stream(main)
         else:
             ev = eng.cnn_sparse("event", batch.event_values, batch.event_coords, batch.num_events, prec)
             pr = eng.cnn_sparse("prong", batch.prong_values, batch.prong_coords, batch.num_prongs, prec)

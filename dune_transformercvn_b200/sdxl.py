@@ -169,11 +169,12 @@ class _SdxlEngine(_Engine):
         net = self.owner[0]
         if self.frozen and self.key is not None and self.key[1] == prec:
             return
-        tensors = dict(net.named_parameters())
-        tensors.update(dict(net.named_buffers()))
-        key = self._state_key(tensors, prec)
+        key = self._state_key(prec)
         if key == self.key:
             return
+        tensors = dict(net.named_parameters())
+        tensors.update(dict(net.named_buffers()))
+        self.generation += 1
         L = _lib.load()
         dev = next(iter(tensors.values())).device
         if dev.type != "cuda":

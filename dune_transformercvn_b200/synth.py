@@ -58,6 +58,25 @@ class SparseBatch:
     def nbytes(self) -> int:
         return sum(t.numel() * t.element_size() for t in self.tensors())
 
+    def select_events(self, lo: int, hi: int) -> "SparseBatch":
+        """Events [lo, hi) as a batch of their own - the shard a data-parallel rank receives (hit lists re-based to the
+        shard's first image, masks trimmed to the shard's longest event, like the reference's collate of those events)."""
+        ppe = list(self.prongs_per_event)
+        p_lo, p_hi = sum(ppe[:lo]), sum(ppe[:hi])
+        width = max(ppe[lo:hi])
+
+        def cut(coords, values, a, b):
+            img = coords[:, 0]
+            keep = (img >= a) & (img < b)
+            c = coords[keep].clone()
+            c[:, 0] -= a
+            return c, values[keep].clone()
+
+        ec, ev = cut(self.event_coords, self.event_values, lo, hi)
+        pc, pv = cut(self.prong_coords, self.prong_values, p_lo, p_hi)
+        return SparseBatch(self.features[lo:hi, :width].clone(), self.extra[lo:hi].clone(), ec, ev, self.event_mask[lo:hi].clone(),
+                           pc, pv, self.prong_mask[lo:hi, :width].clone(), ppe[lo:hi])
+
 
 def _hits(rng: np.random.Generator, n_images: int, occupancy: float, h: int, w: int, value_dtype):
     n_hit = max(1, int(round(occupancy * h * w)))

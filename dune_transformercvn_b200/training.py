@@ -144,6 +144,21 @@ class GradientExchange:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.pending: List = []
         self.bytes = 0
+        self._buf_index: Optional[torch.Tensor] = None
+
+    def broadcast_buffers(self, arena: "FlatArena") -> None:
+        """torch DDP's ``broadcast_buffers=True`` default (what ``DDPStrategy()`` gives the reference, train.py:125): before
+        every forward rank 0's BatchNorm running statistics replace the other ranks'.  The float buffers live scattered in
+        the parameter arena, so they are gathered into one staging vector, broadcast (0.22 MB) and scattered back."""
+        if self.world == 1:
+            return
+        if self._buf_index is None or self._buf_index.device != arena.flat.device:
+            idx = [torch.arange(arena.offset[s.name], arena.offset[s.name] + s.numel) for s in arena.specs if not s.is_param]
+            self._buf_index = torch.cat(idx).to(arena.flat.device)
+        staging = arena.flat.index_select(0, self._buf_index)
+        self.dist.broadcast(staging, src=self.dist.get_global_rank(self.group, 0) if self.group is not None else 0,
+                            group=self.group)
+        arena.flat.index_copy_(0, self._buf_index, staging)
 
     def reduce(self, grad_slice: torch.Tensor) -> None:
         if self.world == 1:
@@ -169,7 +184,13 @@ class TrainEngine:
         self.arena = FlatArena(net)
         self.ws: Dict[str, torch.Tensor] = {}
         self.step_index = 0
-        self.exchange: Optional[GradientExchange] = None
+        # data parallelism (the reference's DDPStrategy, train.py:123-127).  "auto": as soon as torch.distributed is
+        # initialised with more than one rank, backward averages the gradient arena over the ranks (and forward takes
+        # rank 0's BatchNorm running buffers) - the hand-written backward fills .grad directly, so torch DDP's autograd
+        # hooks never fire for these parameters and wrapping the module in DDP alone would NOT average anything.
+        # None disables it; an explicit GradientExchange pins the process group.
+        self.exchange = "auto"
+        self.broadcast_buffers = True
         self.saved = None
         self._nbt: Optional[List[torch.Tensor]] = None
         # the two pixel-map CNNs are independent until the token assembly: the (small, launch-bound) event CNN runs on
@@ -190,13 +211,29 @@ class TrainEngine:
         pix, feat, _ = embedding_dims(net.options)
         return net.engine.cnn_desc(pix if tag == "prong" else pix + feat)
 
+    def _exchange(self) -> Optional[GradientExchange]:
+        if self.exchange == "auto":
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                self.exchange = GradientExchange()
+            else:
+                return None
+        return self.exchange
+
     def forward(self, event_pixels, event_mask, prong_pixels, prong_mask):
-        net = self.net[0]
-        L = _lib.load()
         for t, what in ((event_pixels, "event_pixels"), (prong_pixels, "prong_pixels"), (prong_mask, "prong_mask")):
             _lib.require_cuda(t, what)
+        with torch.cuda.device(event_pixels.device):   # the C ABI launches on the current device
+            return self._forward(event_pixels, event_mask, prong_pixels, prong_mask)
+
+    def _forward(self, event_pixels, event_mask, prong_pixels, prong_mask):
+        net = self.net[0]
+        L = _lib.load()
         dev = event_pixels.device
         self.arena.ensure()
+        ex = self._exchange()
+        if ex is not None and self.broadcast_buffers:
+            ex.broadcast_buffers(self.arena)
         net.engine.key = None  # running buffers (and soon the weights) change under the eval-path cache
         st = _lib.stream_ptr(dev)
         p_drop = float(net.options.dropout)
@@ -258,6 +295,10 @@ class TrainEngine:
     def backward(self, d_ev_logits: Optional[torch.Tensor], d_pr_logits: Optional[torch.Tensor]) -> None:
         if self.saved is None:
             raise _lib.TcvnError("backward without a train-mode forward (or called twice)")
+        with torch.cuda.device(self.saved["dev"]):
+            self._backward(d_ev_logits, d_pr_logits)
+
+    def _backward(self, d_ev_logits: Optional[torch.Tensor], d_pr_logits: Optional[torch.Tensor]) -> None:
         s, self.saved = self.saved, None
         net = self.net[0]
         L = _lib.load()
@@ -279,8 +320,10 @@ class TrainEngine:
                                              a.ptr("prong_decoder", True), _lib.ptr(s["pm"]), b, l, t, s["p_drop"], s["seed"],
                                              _lib.ptr(d_ev), _lib.ptr(d_pr), _lib.ptr(d_emb["event"]), _lib.ptr(d_emb["prong"]),
                                              _lib.ptr(ws), ws.numel(), st), "tcvn_seq_train_backward")
-        ex = self.exchange
+        ex = self._exchange()
         if ex is not None:
+            if ex.pending:
+                raise _lib.TcvnError("backward while a gradient exchange is in flight")
             lo = a.seg["combined"][0]
             ex.reduce(a.gflat[lo:])                       # combined embedding, encoder, both heads
             ex.reduce(a.grad_slice("position"))
@@ -302,6 +345,11 @@ class TrainEngine:
                     ex.reduce(a.grad_slice(tag))
         if side is not None:
             main.wait_stream(side)
+        if ex is not None:
+            # joined here, not in the optimizer: whoever reads .grad after backward() (Lightning's clip_grad_norm_, a stock
+            # torch optimizer, a test) sees the averaged gradient.  The collectives were issued as each sub-network's
+            # gradients became final, so they have been running under the rest of the backward pass.
+            ex.wait()
 
 
 class _TrainFn(torch.autograd.Function):
@@ -342,7 +390,7 @@ class TcvnAdamW(torch.optim.Optimizer):
         super().__init__(params, defaults)
         self.max_grad_norm = float(max_grad_norm)
         self._arena: Optional[FlatArena] = None
-        self._m = self._v = self._gnorm = None
+        self._m = self._v = self._ws = None
         self._steps = [0 for _ in self.param_groups]
 
     def attach(self, net) -> "TcvnAdamW":
@@ -354,8 +402,13 @@ class TcvnAdamW(torch.optim.Optimizer):
         dev = self._arena.flat.device
         self._m = torch.zeros_like(self._arena.flat)
         self._v = torch.zeros_like(self._arena.flat)
-        self._gnorm = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._ws = torch.zeros(_lib.load().tcvn_adamw_workspace_bytes(), dtype=torch.uint8, device=dev)
         return self
+
+    @property
+    def grad_norm_sq(self) -> Optional[torch.Tensor]:
+        """Squared global gradient norm of the last step (device scalar, only when ``max_grad_norm`` > 0)."""
+        return None if self._ws is None else self._ws.view(torch.float64)[-1]
 
     def _find_arena(self) -> None:
         for g in self.param_groups:
@@ -399,22 +452,22 @@ class TcvnAdamW(torch.optim.Optimizer):
         if self._arena is None or not self._arena.bound():
             self._find_arena()
         a = self._arena
-        if self._engine.exchange is not None:
-            self._engine.exchange.wait()
         L = _lib.load()
         st = _lib.stream_ptr(a.flat.device)
         sel = self._selector()
-        gn = None
-        if self.max_grad_norm > 0.0:
-            _lib.check(L.tcvn_sumsq(_lib.ptr(a.gflat), a.total, _lib.ptr(self._gnorm), 1, st), "tcvn_sumsq")
-            gn = _lib.ptr(self._gnorm)
-        for gi, g in enumerate(self.param_groups):
+        ng = len(self.param_groups)
+        dbl, i64 = C.c_double * ng, C.c_int64 * ng
+        for gi in range(ng):
             self._steps[gi] += 1
-            b1, b2 = g["betas"]
-            _lib.check(L.tcvn_adamw_step(_lib.ptr(a.flat), _lib.ptr(a.gflat), _lib.ptr(self._m), _lib.ptr(self._v), a.total,
-                                         float(g["lr"]), float(b1), float(b2), float(g["eps"]), float(g["weight_decay"]),
-                                         self._steps[gi], gn, self.max_grad_norm, 1.0, _lib.ptr(sel), gi + 1, st),
-                       "tcvn_adamw_step")
+        g = self.param_groups
+        # every group in one launch (+ one for the gradient norm when clipping)
+        with torch.cuda.device(a.flat.device):
+            _lib.check(L.tcvn_adamw_fused(
+                _lib.ptr(a.flat), _lib.ptr(a.gflat), _lib.ptr(self._m), _lib.ptr(self._v), a.total, _lib.ptr(sel), ng,
+                dbl(*[float(x["lr"]) for x in g]), dbl(*[float(x["betas"][0]) for x in g]),
+                dbl(*[float(x["betas"][1]) for x in g]), dbl(*[float(x["eps"]) for x in g]),
+                dbl(*[float(x["weight_decay"]) for x in g]), i64(*self._steps), self.max_grad_norm, 1.0,
+                _lib.ptr(self._ws), self._ws.numel(), st), "tcvn_adamw_fused")
         self._engine.net[0].engine.key = None
         return loss
 

@@ -70,6 +70,13 @@ long long tcvn_launch_count(void);
 int tcvn_densify(const int32_t* coords, const void* values, tcvn_value_dtype value_dtype, int64_t nnz,
                  int channels, int n_images, int height, int width, float divisor, float* out,
                  tcvn_dense_layout layout, tcvn_stream_t stream);
+/* Same with the training-time pixel noise of preprocess_pixels fused in (same file :62-65: values *= 1 + randn * std,
+ * std = options.pixel_noise_std): one standard-normal draw per stored value from a counter hash of (seed, hit, channel),
+ * so a (seed, input) pair always gives the same map.  noise_std == 0 is bit-identical to tcvn_densify.
+ * Hits must be sorted by image (the reference's index_put does not need that; its file format guarantees it). */
+int tcvn_densify_noise(const int32_t* coords, const void* values, tcvn_value_dtype value_dtype, int64_t nnz,
+                       int channels, int n_images, int height, int width, float divisor, float noise_std, uint64_t seed,
+                       float* out, tcvn_dense_layout layout, tcvn_stream_t stream);
 
 /* Collate: the events' COO hit lists concatenated in event order, image index still LOCAL to the event -> batch-global
  * image indices (what tcvn_densify / tcvn_cnn_forward_sparse consume).
@@ -241,16 +248,19 @@ int tcvn_t_tokens(int op, int dir, float* a, float* b, const float* pos, const u
 int tcvn_t_act_pool2(const float* blk, int n, int H, int W, int ld, int C, const float* fold, float* out, int H2, int W2,
                      tcvn_stream_t stream);
 int tcvn_t_act_gap(const float* blk, int n, int H, int W, int ld, int C, const float* fold, float* gap, tcvn_stream_t stream);
-/* sum of squares into a device double (global gradient norm, no host sync) */
-int tcvn_sumsq(const float* x, int64_t n, double* out, int zero_first, tcvn_stream_t stream);
-/* fused AdamW over a flat buffer; replaces torch.optim.AdamW.step (trainers/neutrino_base.py:109-130) and Lightning's
- * clip_grad_norm_ (train.py:140): grads are multiplied by grad_mul * min(1, max_norm / (sqrt(*gnorm_sq)*grad_mul + 1e-6)).
- * select (nullable, one byte per element): only elements with select[i] == select_id are updated - one call per
- * parameter group (the reference's decay / no-decay split, neutrino_base.py:116-128); 0 marks buffers and parameters
- * that receive no gradient */
-int tcvn_adamw_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, double lr, double beta1,
-                    double beta2, double eps, double weight_decay, int64_t step, const double* gnorm_sq, float max_norm,
-                    float grad_mul, const uint8_t* select, int select_id, tcvn_stream_t stream);
+/* fused AdamW over the flat arenas: ONE step of every parameter group in one launch; replaces torch.optim.AdamW.step
+ * (trainers/neutrino_base.py:109-130) and Lightning's clip_grad_norm_ (train.py:140).
+ * select (one byte per element; may be NULL for a single group): select[i] = k > 0 -> element i belongs to group k-1 (the
+ * reference's decay / no-decay split, neutrino_base.py:116-128); 0 marks buffers and parameters without a gradient.
+ * lr / beta1 / beta2 / eps / weight_decay / step: HOST arrays of n_groups entries (step >= 1 = the group's step count).
+ * max_norm > 0: the squared gradient norm is first reduced over the whole arena (one partial sum per block in the
+ * workspace, added in a fixed order: bit-reproducible, no host sync) and grads are multiplied by
+ * grad_mul * min(1, max_norm / (norm * grad_mul + 1e-6)); the last double of the workspace receives norm^2. */
+size_t tcvn_adamw_workspace_bytes(void);
+int tcvn_adamw_fused(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const uint8_t* select,
+                     int n_groups, const double* lr, const double* beta1, const double* beta2, const double* eps,
+                     const double* weight_decay, const int64_t* step, float max_norm, float grad_mul, void* workspace,
+                     size_t workspace_bytes, tcvn_stream_t stream);
 
 /* tcgen05 kernels of the bf16 training path on caller-provided row-major bf16 matrices (csrc/umma_train.cu).
  * Weight gradient with MN-major operands (the reduction runs over pixel rows):

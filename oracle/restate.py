@@ -94,8 +94,15 @@ def _conv(state, name: str, x: torch.Tensor, stride: int = 1, padding: int = 0) 
     return F.conv2d(x, state[name + ".weight"], state[name + ".bias"], stride=stride, padding=padding)
 
 
+def _drop(x: torch.Tensor, p: float, train: bool) -> torch.Tensor:
+    """nn.Dropout at the reference's sites (dense_net.py:39,161; prong_feature_embedding.py:23; encoder.py:21-22; the four
+    sites of nn.TransformerEncoderLayer).  p_drop = 0 (every parity test) is the identity."""
+    return F.dropout(x, p, training=True) if (train and p > 0.0) else x
+
+
 def densenet_forward(state, prefix: str, x: torch.Tensor, blocks, growth: int = 32, train: bool = False,
-                     stats: Optional[Stats] = None, taps: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+                     stats: Optional[Stats] = None, taps: Optional[Dict[str, torch.Tensor]] = None,
+                     p_drop: float = 0.0) -> torch.Tensor:
     """One pixel-map CNN.  dense_net.py:97-167 (stem :111-122, Bottleneck :8-45, Transition :78-94,
     tail :147-162).  ``taps`` receives named intermediates (NCHW) for per-stage parity checks."""
     f = prefix + "features."
@@ -112,7 +119,7 @@ def densenet_forward(state, prefix: str, x: torch.Tensor, blocks, growth: int = 
             y = _bn_prelu(state, p + "bottleneck_block.norm1", p + "bottleneck_block.relu1", x, train, stats)
             y = _conv(state, p + "bottleneck_block.conv1", y)
             y = _bn_prelu(state, p + "output_block.norm2", p + "output_block.relu2", y, train, stats)
-            y = _conv(state, p + "output_block.conv2", y, padding=1)
+            y = _drop(_conv(state, p + "output_block.conv2", y, padding=1), p_drop, train)
             x = torch.cat((x, y), dim=1)
         if taps is not None:
             taps[f"dense{bi + 1}"] = x
@@ -127,7 +134,7 @@ def densenet_forward(state, prefix: str, x: torch.Tensor, blocks, growth: int = 
     x = x.mean(dim=(2, 3))
     o = prefix + "output_block."
     x = x @ state[o + "linear.weight"].t()
-    x = _bn_prelu(state, o + "norm", o + "relu", x, train, stats)
+    x = _drop(_bn_prelu(state, o + "norm", o + "relu", x, train, stats), p_drop, train)
     if taps is not None:
         taps["embedding"] = x
     return x
@@ -142,7 +149,7 @@ def pack_indices(mask: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
 
 def tokens_forward(state, event_emb: torch.Tensor, prong_emb: torch.Tensor, prong_mask: torch.Tensor,
                    event_mask: torch.Tensor, feature_dim: int, train: bool = False,
-                   stats: Optional[Stats] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                   stats: Optional[Stats] = None, p_drop: float = 0.0) -> Tuple[torch.Tensor, torch.Tensor]:
     """networks/neutrino_full_base_network.py:99-125 with disable_smart_features=True
     (prong_feature_embedding.py:75-76 returns zeros).  NOTE :107 — prong rows get the *event*
     position embedding; ``prong_position_embedding`` is never read."""
@@ -153,7 +160,8 @@ def tokens_forward(state, event_emb: torch.Tensor, prong_emb: torch.Tensor, pron
     t = prong_emb.shape[0]
     pr = torch.cat((torch.zeros(t, feature_dim, dtype=prong_emb.dtype, device=prong_emb.device), prong_emb, pos.expand(t, -1)), dim=1)
     rows = torch.cat((ev, pr), dim=0) @ state[pe + "combined_embedding.linear.weight"].t()
-    rows = _bn_prelu(state, pe + "combined_embedding.norm", pe + "combined_embedding.activation", rows, train, stats)
+    rows = _drop(_bn_prelu(state, pe + "combined_embedding.norm", pe + "combined_embedding.activation", rows, train, stats),
+                 p_drop, train)
     i1, i2 = pack_indices(prong_mask)
     padded = torch.zeros(b, l, rows.shape[1], dtype=rows.dtype, device=rows.device)
     padded[i1, i2] = rows[b:]
@@ -168,7 +176,8 @@ def _layer_norm(x, w, b):
     return (x - mu) * torch.rsqrt(var + LN_EPS) * w + b
 
 
-def encoder_forward(state, tokens: torch.Tensor, mask: torch.Tensor, num_layers: int, num_heads: int) -> torch.Tensor:
+def encoder_forward(state, tokens: torch.Tensor, mask: torch.Tensor, num_layers: int, num_heads: int, train: bool = False,
+                    p_drop: float = 0.0) -> torch.Tensor:
     """layers/prong_custom_bert_encoder.py:57-75 around torch's post-norm TransformerEncoderLayer
     (:45-54): x=LN1(x+Wo.MHA(x)); x=LN2(x+W2.gelu_erf(W1 x)).  Keys of padded slots get -inf; the
     input and the output are multiplied by the mask.  Returns (S,B,D) like the reference."""
@@ -181,20 +190,20 @@ def encoder_forward(state, tokens: torch.Tensor, mask: torch.Tensor, num_layers:
         p = f"encoder.encoder.layers.{li}."
         qkv = x @ state[p + "self_attn.in_proj_weight"].t() + state[p + "self_attn.in_proj_bias"]
         q, k, v = (t.view(b, s, num_heads, dh).transpose(1, 2) for t in qkv.split(d, dim=-1))
-        att = torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh) + neg, dim=-1)
+        att = _drop(torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(dh) + neg, dim=-1), p_drop, train)
         ctx = (att @ v).transpose(1, 2).reshape(b, s, d)
         ctx = ctx @ state[p + "self_attn.out_proj.weight"].t() + state[p + "self_attn.out_proj.bias"]
-        x = _layer_norm(x + ctx, state[p + "norm1.weight"], state[p + "norm1.bias"])
+        x = _layer_norm(x + _drop(ctx, p_drop, train), state[p + "norm1.weight"], state[p + "norm1.bias"])
         hmid = x @ state[p + "linear1.weight"].t() + state[p + "linear1.bias"]
-        hmid = 0.5 * hmid * (1.0 + torch.erf(hmid / math.sqrt(2.0)))
+        hmid = _drop(0.5 * hmid * (1.0 + torch.erf(hmid / math.sqrt(2.0))), p_drop, train)
         ff = hmid @ state[p + "linear2.weight"].t() + state[p + "linear2.bias"]
-        x = _layer_norm(x + ff, state[p + "norm2.weight"], state[p + "norm2.bias"])
+        x = _layer_norm(x + _drop(ff, p_drop, train), state[p + "norm2.weight"], state[p + "norm2.bias"])
     return (x * m).transpose(0, 1).contiguous()
 
 
 # ----------------------------------------------------------------------------- heads
 def heads_forward(state, hidden: torch.Tensor, widths: List[int], stride: int, train: bool = False,
-                  stats: Optional[Stats] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                  stats: Optional[Stats] = None, p_drop: float = 0.0) -> Tuple[torch.Tensor, torch.Tensor]:
     """Event head: layers/prong_decoder.py:13-16 on token 0.  Prong head: prong_target_decoder.py:35-41
     over ALL L*B rows (padded rows included — they enter the BN1d batch statistics in train mode);
     caller-visible layout (B,L,C) per neutrino_full_base_network.py:186-188."""
@@ -204,8 +213,8 @@ def heads_forward(state, hidden: torch.Tensor, widths: List[int], stride: int, t
     for i, _ in enumerate(widths):
         base = f"prong_decoder.hidden_layers.{i * stride}"
         x = x @ state[base + ".weight"].t() + state[base + ".bias"]
-        x = _bn_prelu(state, f"prong_decoder.hidden_layers.{i * stride + 1}",
-                      f"prong_decoder.hidden_layers.{i * stride + 2}", x, train, stats)
+        x = _drop(_bn_prelu(state, f"prong_decoder.hidden_layers.{i * stride + 1}",
+                            f"prong_decoder.hidden_layers.{i * stride + 2}", x, train, stats), p_drop, train)
     x = x @ state["prong_decoder.output_layer.weight"].t() + state["prong_decoder.output_layer.bias"]
     return ev, x.reshape(l, b, -1).transpose(0, 1)
 
@@ -213,7 +222,7 @@ def heads_forward(state, hidden: torch.Tensor, widths: List[int], stride: int, t
 # ----------------------------------------------------------------------------- whole path
 def network_forward(state, options, event_pixels: torch.Tensor, event_mask: torch.Tensor,
                     prong_pixels: torch.Tensor, prong_mask: torch.Tensor, train: bool = False,
-                    stats: Optional[Stats] = None, taps: Optional[dict] = None):
+                    stats: Optional[Stats] = None, taps: Optional[dict] = None, p_drop: float = 0.0):
     """networks/neutrino_full_base_network.py:166-188."""
     from dune_transformercvn_b200.params import embedding_dims, prong_decoder_widths
     blocks = tuple(options.densenet_structure)
@@ -221,12 +230,12 @@ def network_forward(state, options, event_pixels: torch.Tensor, event_mask: torc
     _, feat, _ = embedding_dims(options)
     et = {} if taps is not None else None
     pt = {} if taps is not None else None
-    ev = densenet_forward(state, "prong_embedding.event_pixel_embedding.", event_pixels, blocks, g, train, stats, et)
-    pr = densenet_forward(state, "prong_embedding.prong_pixel_embedding.", prong_pixels, blocks, g, train, stats, pt)
-    tokens, mask = tokens_forward(state, ev, pr, prong_mask, event_mask, feat, train, stats)
-    hidden = encoder_forward(state, tokens, mask, options.num_encoder_layers, options.num_attention_heads)
+    ev = densenet_forward(state, "prong_embedding.event_pixel_embedding.", event_pixels, blocks, g, train, stats, et, p_drop)
+    pr = densenet_forward(state, "prong_embedding.prong_pixel_embedding.", prong_pixels, blocks, g, train, stats, pt, p_drop)
+    tokens, mask = tokens_forward(state, ev, pr, prong_mask, event_mask, feat, train, stats, p_drop)
+    hidden = encoder_forward(state, tokens, mask, options.num_encoder_layers, options.num_attention_heads, train, p_drop)
     stride = 3 + int(options.dropout > 0.0)
-    ev_logits, pr_logits = heads_forward(state, hidden, prong_decoder_widths(options), stride, train, stats)
+    ev_logits, pr_logits = heads_forward(state, hidden, prong_decoder_widths(options), stride, train, stats, p_drop)
     if taps is not None:
         taps.update(event_cnn=et, prong_cnn=pt, event_embedding=ev, prong_embedding=pr, tokens=tokens,
                     hidden=hidden)
@@ -234,12 +243,12 @@ def network_forward(state, options, event_pixels: torch.Tensor, event_mask: torc
 
 
 def sparse_forward(state, options, batch, h: int = 400, w: int = 280, train: bool = False, taps=None, stats=None,
-                   dtype=torch.float32):
+                   dtype=torch.float32, p_drop: float = 0.0):
     """Trainer-level path: preprocess -> densify -> network (neutrino_full_base_trainer.py:113-116).
     ``dtype``: the /255 is always done in fp32 like the reference; float64 only widens what follows."""
     ev = densify(preprocess_values(batch.event_values.float()), batch.event_coords, h, w).to(dtype)
     pr = densify(preprocess_values(batch.prong_values.float()), batch.prong_coords, h, w).to(dtype)
-    return network_forward(state, options, ev, batch.event_mask, pr, batch.prong_mask, train, stats, taps)
+    return network_forward(state, options, ev, batch.event_mask, pr, batch.prong_mask, train, stats, taps, p_drop)
 
 
 def focal_loss(logits: torch.Tensor, targets: torch.Tensor, gamma: float) -> torch.Tensor:

@@ -60,6 +60,31 @@ def test_event_classifier_matches_oracle_and_graph_replay_is_exact(dev, precisio
     assert [tuple(t.shape) for t in pid] == [(4,), (2, 8)] and [tuple(t.shape) for t in emb] == [(128,), (2, 128)]
 
 
+def test_graph_plans_survive_growing_workspaces(dev):
+    """a captured graph bakes in workspace / packed-block pointers.  Prong counts 1, 6, 1 make the second plan
+    grow the workspaces the first plan was captured over, and a batched forward on the same network grows them again;
+    every replay must still equal the un-captured call sequence bit for bit (stale plans are re-captured)."""
+    opts = PathOptions.tutorial()
+    net = NeutrinoDenseNetwork(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES, precision="bf16")
+    net.load_state_dict(synth.init_state(net.specs, seed=3, perturb=True))
+    net = net.to(dev).eval()
+    graphed = EventClassifier(net, "combined", use_graph=True)
+    plain = EventClassifier(net, "combined", use_graph=False)
+    big = synth.make_batch(6, seed=5, max_prongs=10).to(dev)
+    for i, (n_prongs, seed) in enumerate(((1, 12), (6, 11), (1, 14), (6, 15), (1, 16))):
+        px = _pixels(n_prongs, seed).to(dev)
+        got = graphed(px)
+        junk = torch.full((1 << 24,), float("nan"), device=dev)     # whatever the allocator hands out next is poisoned
+        del junk
+        if i == 2:
+            with torch.no_grad():
+                net.forward_sparse(big)                              # a larger batched forward: workspaces grow again
+        ref = plain(px)
+        for g, r in zip(got, ref):
+            assert torch.isfinite(g).all()
+            assert torch.equal(g, r), (i, n_prongs)
+
+
 def test_custom_op_runs_and_exports(dev):
     opts = PathOptions.tutorial()
     net = NeutrinoDenseNetwork(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES).to(dev).eval()

@@ -349,3 +349,47 @@ def test_sm_budgets_do_not_change_the_result(dev):
     assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
     L = tl.load()
     assert L.tcvn_set_sm_limit(-1) != 0 and L.tcvn_set_sm_limit(0) == 0
+
+
+def test_batched_inference_graph_replay_is_exact(dev):
+    """forward_sparse(graph=True): one CUDA-graph replay per batch shape must give the bits of the kernel-by-kernel launch,
+    for new data of the same shape, after a parameter change (re-pack -> stale plan re-captured), and for a second shape."""
+    opts = PathOptions.tutorial()
+    net = NeutrinoDenseNetwork(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES, precision="bf16")
+    net.load_state_dict(synth.init_state(net.specs, seed=4, perturb=True))
+    net = net.to(dev).eval()
+    with torch.no_grad():
+        for seed, events in ((1, 6), (2, 6), (3, 9), (4, 6)):
+            b = synth.make_batch(events, seed=seed, prongs_per_event=[3, 1, 4, 2, 5, 2, 1, 1, 3][:events]).to(dev)
+            want = net.forward_sparse(b)
+            got = net.forward_sparse(b, graph=True)
+            assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1]), (seed, events)
+        assert len(net._plans) == 2 and net.graph_launches_per_replay > 50
+        for p in net.parameters():                       # what an optimizer step or load_state_dict does
+            p.mul_(1.01)
+        want = net.forward_sparse(b)
+        got = net.forward_sparse(b, graph=True)
+        assert torch.equal(got[0], want[0]) and torch.equal(got[1], want[1])
+
+
+def test_training_pixel_noise_in_densify(dev):
+    """preprocess_pixels' training noise (neutrino_full_dense_trainer.py:62-65: v *= 1 + randn * std) fused into densify:
+    std = 0 is bit-identical to the plain kernel, the same seed repeats, and the multiplicative factors are standard
+    normal draws (mean 0, variance 1 within sampling error, no value touched where there is no hit)."""
+    from dune_transformercvn_b200.ingest import densify
+    b = synth.make_batch(4, seed=9, max_prongs=3).to(dev)
+    n = b.num_events
+    base = densify(b.event_values, b.event_coords, (H, W), n, 255.0)
+    assert torch.equal(densify(b.event_values, b.event_coords, (H, W), n, 255.0, noise_std=0.0, seed=5), base)
+    std = 0.05
+    a1 = densify(b.event_values, b.event_coords, (H, W), n, 255.0, noise_std=std, seed=5)
+    a2 = densify(b.event_values, b.event_coords, (H, W), n, 255.0, noise_std=std, seed=5)
+    a3 = densify(b.event_values, b.event_coords, (H, W), n, 255.0, noise_std=std, seed=6)
+    assert torch.equal(a1, a2) and not torch.equal(a1, a3)
+    hit = base != 0
+    assert torch.equal(a1 == 0, ~hit)
+    z = ((a1[hit] / base[hit]).double() - 1.0) / std
+    m = z.numel()
+    assert m > 10000
+    assert abs(float(z.mean())) < 5.0 / m ** 0.5 and abs(float(z.var()) - 1.0) < 8.0 * (2.0 / m) ** 0.5
+    assert 3.0 < float(z.abs().max()) < 6.5
