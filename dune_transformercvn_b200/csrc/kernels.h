@@ -104,7 +104,11 @@ int stem_train_wgrad(const float* pixels, int n, int cin, int H, int W, const vo
                      cudaStream_t stream);
 int wgrad_typed(const void* A, bool a_bf16, int lda, long long m_total, int K, int taps, const int* tap_off, const float* a_scale,
                 const float* a_shift, const float* a_alpha, int a_ring_hp, int a_ring_wp, const void* G, bool g_bf16, int ldg,
-                int g_col0, int N, int g_ring_hp, int g_ring_wp, float* dW, cudaStream_t stream);
+                int g_col0, int N, int g_ring_hp, int g_ring_wp, float* dW, cudaStream_t stream, float* parts = nullptr,
+                size_t parts_floats = 0);
+// dW[K][N] += A^T G over m_total rows (plain fp32 matrices); parts = scratch for per-slab partial results (nullable)
+int wgrad_f32(const float* A, int lda, long long m_total, int K, const float* G, int ldg, int N, float* dW, float* parts,
+              size_t parts_floats, cudaStream_t stream);
 
 #define TCVN_TRY(expr)                \
   do {                                \

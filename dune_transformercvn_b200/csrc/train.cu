@@ -9,6 +9,7 @@
 //     latter with the UNBIASED variance) with momentum 0.1;
 //   PReLU with one slope per channel; backward d(alpha) = sum(dy * min(x, 0)).
 #include "kernels.h"
+#include "umma.h"
 
 namespace tcvn {
 
@@ -29,7 +30,8 @@ struct WgradDev {
   int a_ring_Hp, a_ring_Wp;
   const void* G; int ldg; int g_col0; int N;
   int g_ring_Hp, g_ring_Wp;
-  float* dW;  // [taps][K][N], accumulated with atomics
+  float* dW;  // [taps][K][N], accumulated (atomics when several row slabs share it)
+  float* parts;  // non-null: slab z stores its partial result to parts[z][taps][K][N] instead (added later in a fixed order)
   int rows_per_slab;
 };
 
@@ -96,7 +98,11 @@ __global__ void __launch_bounds__(256) wgrad_kernel(const WgradDev g) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int k = k0 + tk + i, n = n0 + tn + j;
-      if (k < g.K && n < g.N) atomicAdd(g.dW + ((size_t)tap * g.K + k) * g.N + n, acc[i][j]);
+      if (k < g.K && n < g.N) {
+        const size_t o = ((size_t)tap * g.K + k) * g.N + n;
+        if (g.parts) g.parts[(size_t)blockIdx.z * g.taps * g.K * g.N + o] = acc[i][j];
+        else atomicAdd(g.dW + o, acc[i][j]);
+      }
     }
 }
 
@@ -498,8 +504,17 @@ __global__ void __launch_bounds__(256) parts_reduce_kernel(const double* __restr
   const int q = blockIdx.x * 16 + col;   // flattened (sum j, column c)
   const int total = ns * C;
   double acc = 0.0;
-  if (q < total)
-    for (int s = slice; s < n_slots; s += 16) acc += parts[(size_t)s * total + q];
+  if (q < total) {
+    int s = slice;
+    for (; s + 16 * 7 < n_slots; s += 16 * 8) {   // 8 independent loads in flight, added in slot order
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = parts[(size_t)(s + 16 * u) * total + q];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc += v[u];
+    }
+    for (; s < n_slots; s += 16) acc += parts[(size_t)s * total + q];
+  }
   red[slice][col] = acc;
   __syncthreads();
   if (slice == 0 && q < total) {
@@ -1117,7 +1132,8 @@ extern "C" int tcvn_t_gemm(const float* A, int lda, int64_t m_total, int K, int 
 namespace tcvn {
 int wgrad_typed(const void* A, bool a_bf16, int lda, long long m_total, int K, int taps, const int* tap_off, const float* a_scale,
                 const float* a_shift, const float* a_alpha, int a_ring_hp, int a_ring_wp, const void* G, bool g_bf16, int ldg,
-                int g_col0, int N, int g_ring_hp, int g_ring_wp, float* dW, cudaStream_t stream) {
+                int g_col0, int N, int g_ring_hp, int g_ring_wp, float* dW, cudaStream_t stream, float* parts,
+                size_t parts_floats) {
   if (m_total <= 0) return TCVN_OK;
   WgradDev g{};
   g.A = A; g.lda = lda; g.m_total = m_total; g.K = K; g.taps = taps;
@@ -1127,10 +1143,14 @@ int wgrad_typed(const void* A, bool a_bf16, int lda, long long m_total, int K, i
   g.G = G; g.ldg = ldg; g.g_col0 = g_col0; g.N = N; g.g_ring_Hp = g_ring_hp; g.g_ring_Wp = g_ring_wp;
   g.dW = dW;
   int slabs = slabs_for(m_total, &g.rows_per_slab);
-  // up to 4096 rows (the sequence part, the CNN tail: every use of the bf16 walk) one CTA owns a result tile and walks all
-  // rows: a single writer per element, bit-reproducible.  Larger inputs (fp32 parity walk only) split the rows and add with
-  // float atomics.
-  if (m_total <= 4096) { slabs = 1; g.rows_per_slab = (int)m_total; }
+  // Bit-reproducible whenever possible: with a scratch buffer every row slab stores its partial result in its own slot and
+  // the slots are added in a fixed order; without one, up to 4096 rows are walked by a single CTA per result tile (one
+  // writer per element).  Only larger inputs without scratch (the fp32 parity walk) add with float atomics.
+  const size_t n_out = (size_t)taps * K * N;
+  bool slotted = false;
+  if (slabs > 1 && parts != nullptr && n_out % 4 == 0 && n_out * slabs <= parts_floats) slotted = true;
+  else if (m_total <= 4096) { slabs = 1; g.rows_per_slab = (int)m_total; }
+  g.parts = slotted ? parts : nullptr;
   dim3 grid(ceil_div(K, kWgK), ceil_div(N, kWgN) * taps, slabs);
   typedef __nv_bfloat16 bf;
   if (!a_bf16 && !g_bf16) wgrad_kernel<float, float><<<grid, 256, 0, stream>>>(g);
@@ -1138,7 +1158,14 @@ int wgrad_typed(const void* A, bool a_bf16, int lda, long long m_total, int K, i
   else if (a_bf16) wgrad_kernel<bf, float><<<grid, 256, 0, stream>>>(g);
   else wgrad_kernel<float, bf><<<grid, 256, 0, stream>>>(g);
   TCVN_LAUNCH_CHECK();
+  if (slotted) TCVN_TRY(reduce_parts(parts, slabs, (long long)n_out, dW, true, stream));
   return TCVN_OK;
+}
+
+int wgrad_f32(const float* A, int lda, long long m_total, int K, const float* G, int ldg, int N, float* dW, float* parts,
+              size_t parts_floats, cudaStream_t stream) {
+  return wgrad_typed(A, false, lda, m_total, K, 1, nullptr, nullptr, nullptr, nullptr, 0, 0, G, false, ldg, 0, N, 0, 0, dW, stream,
+                     parts, parts_floats);
 }
 }  // namespace tcvn
 

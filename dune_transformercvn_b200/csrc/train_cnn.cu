@@ -733,9 +733,22 @@ __global__ void __launch_bounds__(256) bn_finalize16_kernel(const FinArgs16 a) {
   double x1 = 0.0, x2 = 0.0;
   if (fresh) {
     const int q = p - a.fresh.col0;
-    for (int s = slice; s < a.fresh.n_slots; s += 16) {
-      x1 += a.fresh.parts[((size_t)s * 2) * a.fresh.Cp + q];
-      x2 += a.fresh.parts[((size_t)s * 2 + 1) * a.fresh.Cp + q];
+    const double* base = a.fresh.parts + q;
+    const size_t cp = (size_t)a.fresh.Cp;
+    int s = slice;
+    for (; s + 16 * 3 < a.fresh.n_slots; s += 16 * 4) {   // 8 independent loads in flight, added in slot order
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        v[2 * u] = base[((size_t)(s + 16 * u) * 2) * cp];
+        v[2 * u + 1] = base[((size_t)(s + 16 * u) * 2 + 1) * cp];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { x1 += v[2 * u]; x2 += v[2 * u + 1]; }
+    }
+    for (; s < a.fresh.n_slots; s += 16) {
+      x1 += base[((size_t)s * 2) * cp];
+      x2 += base[((size_t)s * 2 + 1) * cp];
     }
   }
   red[0][slice][col] = x1;
@@ -796,8 +809,17 @@ __global__ void __launch_bounds__(256) bn_param_reduce_kernel(const BnParamArgs 
   if ((int)blockIdx.x >= a.main_blocks) {
     const int c = ((int)blockIdx.x - a.main_blocks) * 16 + col;
     double x = 0.0;
-    if (c < a.bias_C)
-      for (int s = slice; s < a.bias_slots; s += 16) x += a.bias_parts[(size_t)s * a.bias_C + c];
+    if (c < a.bias_C) {
+      int s = slice;
+      for (; s + 16 * 7 < a.bias_slots; s += 16 * 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = a.bias_parts[(size_t)(s + 16 * u) * a.bias_C + c];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x += v[u];
+      }
+      for (; s < a.bias_slots; s += 16) x += a.bias_parts[(size_t)s * a.bias_C + c];
+    }
     red[0][slice][col] = x;
     __syncthreads();
     if (slice == 0 && c < a.bias_C) {
@@ -810,11 +832,26 @@ __global__ void __launch_bounds__(256) bn_param_reduce_kernel(const BnParamArgs 
   }
   const int p = blockIdx.x * 16 + col;
   double x[3] = {0.0, 0.0, 0.0};
-  if (p < a.C)
-    for (int s = slice; s < a.n_slots; s += 16) {
+  if (p < a.C) {
+    const double* base = a.parts + p;
+    const size_t cc = (size_t)a.C;
+    int s = slice;
+    for (; s + 16 * 3 < a.n_slots; s += 16 * 4) {   // 12 independent loads in flight, added in slot order
+      double v[4][3];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) x[j] += a.parts[((size_t)s * 3 + j) * a.C + p];
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) v[u][j] = base[((size_t)(s + 16 * u) * 3 + j) * cc];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) x[j] += v[u][j];
     }
+    for (; s < a.n_slots; s += 16) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) x[j] += base[((size_t)s * 3 + j) * cc];
+    }
+  }
 #pragma unroll
   for (int j = 0; j < 3; ++j) red[j][slice][col] = x[j];
   __syncthreads();
@@ -1108,7 +1145,7 @@ struct TWalk16 {
     TCVN_TRY(bn_bwd(f(T.lin), false, out, d_emb, false, out, f(T.fold_o), out, out, (double)n, n, 0, 0, d_emb, false, out,
                     P.out_norm, NOGAP, NOGAP));
     TCVN_CUDA(cudaMemsetAsync(dwp, 0, sizeof(float) * (size_t)last.ctot * out, st));
-    TCVN_TRY(tcvn_t_wgrad(f(T.gap), last.ctot, n, last.ctot, 1, nullptr, nullptr, 0, 0, d_emb, out, 0, out, 0, 0, dwp, st));
+    TCVN_TRY(wgrad_f32(f(T.gap), last.ctot, n, last.ctot, d_emb, out, out, dwp, f(T.dparts), colsum_parts_bytes() / 4, st));
     TCVN_TRY(unpack(dwp, 1, last.ctot, out, out, last.clog, last.c0, last.c0p, garena + P.lin_w));
     TCVN_TRY(gemm32(d_emb, out, n, out, f(T.lwt), last.ctot, nullptr, f(T.dgap), last.ctot));
     TCVN_TRY(pool_typed(3, f(T.dgap), nullptr, h(T.sA), true, n, last.ctot, last.H, last.W, 0, 0, last.ctot, st));

@@ -193,7 +193,7 @@ struct NWalk {
   int lin_bwd(const float* dY, int lddy, long long rows, int n_out, const float* X, int ldx, int k_in, const float* W,
               float* dW, float* db, float* dX, int lddx) {
     if (db) TCVN_TRY(bias_grad(dY, lddy, 0, n_out, rows, db));
-    TCVN_TRY(tcvn_t_wgrad(dY, lddy, rows, n_out, 1, nullptr, nullptr, 0, 0, X, ldx, 0, k_in, 0, 0, dW, st));
+    TCVN_TRY(wgrad_f32(dY, lddy, rows, n_out, X, ldx, k_in, dW, reinterpret_cast<float*>(dparts()), colsum_parts_bytes() / 4, st));
     if (dX) TCVN_TRY(tcvn_t_gemm(dY, lddy, rows, n_out, 1, nullptr, W, k_in, nullptr, 0, 0, nullptr, dX, lddx, 0, 0, 0, 0, st));
     return TCVN_OK;
   }

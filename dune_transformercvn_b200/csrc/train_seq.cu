@@ -80,17 +80,17 @@ __global__ void ln_bwd_kernel(const float* __restrict__ dy, const float* __restr
   }
 }
 
-// dgamma[j] += sum_r dy[r,j] * xhat[r,j] ; dbeta[j] += sum_r dy[r,j].  A block owns 32 columns, its 8 warps take every
-// 8th row, the 8 partial sums are added in order: one writer per element, fixed summation order.
-__global__ void __launch_bounds__(256) ln_param_grads_kernel(const float* __restrict__ dy, const float* __restrict__ pre,
+// dgamma[j] += sum_r dy[r,j] * xhat[r,j] ; dbeta[j] += sum_r dy[r,j].  A block owns 32 columns, its 32 warps take every
+// 32nd row, the 32 partial sums are added in order: one writer per element, fixed summation order.
+__global__ void __launch_bounds__(1024) ln_param_grads_kernel(const float* __restrict__ dy, const float* __restrict__ pre,
                                                              const float* __restrict__ stats, int D, int R, float* dgamma,
                                                              float* dbeta) {
-  __shared__ float red[2][8][33];
+  __shared__ float red[2][32][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + lane;
   float sg = 0.f, sb = 0.f;
   if (j < D)
-    for (int r = w; r < R; r += 8) {
+    for (int r = w; r < R; r += 32) {
       const float d = dy[(size_t)r * D + j];
       sg = fmaf(d, (pre[(size_t)r * D + j] - stats[2 * r]) * stats[2 * r + 1], sg);
       sb += d;
@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) ln_param_grads_kernel(const float* __rest
   if (w == 0 && j < D) {
     float a = 0.f, b = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { a += red[0][k][lane]; b += red[1][k][lane]; }
+    for (int k = 0; k < 32; ++k) { a += red[0][k][lane]; b += red[1][k][lane]; }
     dgamma[j] += a;
     dbeta[j] += b;
   }
@@ -326,7 +326,7 @@ extern "C" int tcvn_t_layernorm(int dir, const float* a, const float* b, int D, 
   else {
     ln_bwd_kernel<<<ceil_div(R, 8), 256, 0, stream>>>(a, pre, stats, gamma, D, R, out);
     TCVN_LAUNCH_CHECK();
-    if (dgamma && dbeta) ln_param_grads_kernel<<<ceil_div(D, 32), 256, 0, stream>>>(a, pre, stats, D, R, dgamma, dbeta);
+    if (dgamma && dbeta) ln_param_grads_kernel<<<ceil_div(D, 32), 1024, 0, stream>>>(a, pre, stats, D, R, dgamma, dbeta);
   }
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;

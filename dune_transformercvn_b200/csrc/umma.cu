@@ -494,8 +494,8 @@ struct Conv2Params {
   bf16* out;
   int ldo, col0, num_tiles;
   // training: Dropout(p) on the 32 new channels (mask = hash(seed, site, row * 32 + channel), re-derived in backward) and
-  // their per-column (sum, sum^2) as stored (bf16): every epilogue warp stores its partial sums in its own slot,
-  // stats[(8 * cta + 4 * group + warp)][2][32], added in a fixed order by the consumer (no atomics)
+  // their per-column (sum, sum^2) as stored (bf16): the CTA's eight epilogue warps are added in a fixed order and stored in
+  // the CTA's own slot, stats[cta][2][32]; the consumer adds the slots in a fixed order (no atomics)
   float p_drop; unsigned long long seed, site;
   double* stats;
 };
@@ -718,9 +718,18 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
       acc_phase ^= 1;
     }
     if (p.stats != nullptr) {
-      double* slot = p.stats + (size_t)(8 * blockIdx.x + 4 * grp + g) * 2 * kGrowth;
-      slot[lane] = st_sum;
-      slot[kGrowth + lane] = st_sq;
+      // s_exch is idle by now (every tile's exchange has been consumed): [8 warps][2][32] doubles fit in its 2 KB
+      double* red = reinterpret_cast<double*>(s_exch);
+      ptx::named_bar_sync(5, 256);
+      red[((4 * grp + g) * 2) * kGrowth + lane] = st_sum;
+      red[((4 * grp + g) * 2 + 1) * kGrowth + lane] = st_sq;
+      ptx::named_bar_sync(5, 256);
+      if (grp == 0 && g < 2) {   // warp g reduces sum kind g over the eight warps in order
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[(w * 2 + g) * kGrowth + lane];
+        p.stats[((size_t)blockIdx.x * 2 + g) * kGrowth + lane] = t;
+      }
     }
   }
   ptx::tc_fence_before();
@@ -800,7 +809,7 @@ int umma_conv2_fwd(const void* mid, long long rows, const void* w2, const float*
   if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one chunk");
   const int tiles = (int)ceil_div_ll(rows, kC2Out);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  if (stat_slots) *stat_slots = 8 * grid;
+  if (stat_slots) *stat_slots = grid;
   const int halo_rows_max = 288;
   bool& attr_done = device_flag(2);   // per device: the attribute belongs to the device's copy of the function
   if (!attr_done) {
@@ -815,7 +824,7 @@ int umma_conv2_fwd(const void* mid, long long rows, const void* w2, const float*
   if (c2.halo_rows > halo_rows_max)
     return fail(TCVN_ERR_UNSUPPORTED, "feature map width %d needs a %d-row halo tile (max %d)", W, c2.halo_rows, halo_rows_max);
   {
-    const size_t fixed = 1024 + kW2Bytes + 2560, per_stage = (size_t)2 * c2.halo_rows * 128;
+    const size_t fixed = 1024 + kW2Bytes + 4864, per_stage = (size_t)2 * c2.halo_rows * 128;
     int st_n = (int)((kC2SmemMax - fixed) / per_stage);
     static const int st_cap = [] { const char* v = getenv("TCVN_C2_STAGES"); const int n = v ? atoi(v) : 0; return n >= 2 && n <= kC2StagesMax ? n : kC2StagesMax; }();
     c2.stages = st_n > st_cap ? st_cap : st_n;
@@ -830,7 +839,7 @@ int umma_conv2_fwd(const void* mid, long long rows, const void* w2, const float*
   CUtensorMap tmM, tmW2;
   TCVN_TRY(make_map(mid, rows, kMid, kMid, 64, kBoxRows, &tmM));
   TCVN_TRY(make_map(w2, 9 * kGrowth, kMid, kMid, 64, kC2N, &tmW2));
-  const size_t smem2 = 1024 + kW2Bytes + (size_t)c2.stages * 2 * c2.halo_rows * 128 + 2560;
+  const size_t smem2 = 1024 + kW2Bytes + (size_t)c2.stages * 2 * c2.halo_rows * 128 + 4864;
   umma_conv2_kernel<<<grid, kC2Threads, smem2, st>>>(tmM, tmW2, c2);
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
