@@ -878,15 +878,6 @@ __global__ void __launch_bounds__(256) bn_param_reduce_kernel(const BnParamArgs 
   }
 }
 
-// conv2 weight gradient from the tensor-core layout dw[dy][k][dx*32 + n] -> += reference layout [n][k][dy][dx]
-__global__ void unpack_conv2_grad_kernel(const float* __restrict__ dw, float* __restrict__ dst) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 32 * 128 * 9) return;
-  const int t = idx % 9, k = (idx / 9) & 127, n = idx / (9 * 128);
-  const int dy = t / 3, dx = t - dy * 3;
-  dst[idx] += dw[(dy * 128 + k) * 128 + dx * 32 + n];
-}
-
 // dst[(k0 + it*128 + r) * ld + n0 + c] = dw[it][r][c] for the valid rows / columns of a weight-gradient tile group
 __global__ void scatter_wgrad_tiles_kernel(const float* __restrict__ dw, int n_items, int k0, int k_total, int n0, int n_valid,
                                            float* __restrict__ dst, int ld) {
@@ -1189,9 +1180,7 @@ struct TWalk16 {
             TCVN_CUDA(cudaStreamWaitEvent(wst, ax->e[0], 0));
           }
           TCVN_TRY(umma_wgrad(h(Y.mid_act), rows, mid, mid, 3, cols, shifts, valid, nullptr, nullptr, nullptr, 0, g2x, 128, 128, 0,
-                              f(T.parts), dwp, false, wst));
-          unpack_conv2_grad_kernel<<<ceil_div(32 * 128 * 9, 256), 256, 0, wst>>>(dwp, garena + L.conv2_w);
-          TCVN_LAUNCH_CHECK();
+                              f(T.parts), garena + L.conv2_w, true, wst, 2));
         }
         TCVN_TRY(umma_conv2_dgrad(g2x, h(Y.wd), rows, B.Hp, B.Wp, dmid, st));
         // BN2 + PReLU2 backward: reductions -> (parameter gradients, conv2 bias gradient) -> elementwise half, in place
@@ -1214,8 +1203,7 @@ struct TWalk16 {
             TCVN_CUDA(cudaStreamWaitEvent(wst, ax->e[1], 0));
           }
           TCVN_TRY(umma_wgrad(blk, rows, B.ctot, B.ctot, n_items, cols, shifts, valid, f1, f1 + L.kpad, f1 + 2 * L.kpad, L.kphys,
-                              dmid, mid, mid, 0, f(T.parts), dwp, false, wst));
-          TCVN_TRY(unpack_on(wst, dwp, 1, n_items * 128, 128, mid, L.cin, B.c0, B.c0p, garena + L.conv1_w));
+                              dmid, mid, mid, 0, f(T.parts), garena + L.conv1_w, true, wst, 1, mid, L.cin, B.c0, B.c0p));
           if (ax) {
             TCVN_CUDA(cudaEventRecord(ax->e[2], wst));
             side_pending = true;

@@ -30,6 +30,9 @@ size_t umma_wgrad_parts_bytes(int n_items);
 int reduce_parts(const float* parts, int n_parts, long long n, float* out, bool accumulate, cudaStream_t st);
 int umma_wgrad(const void* A, long long rows, int a_cols, int a_pitch, int n_items, const int* item_col, const int* item_shift,
                const int* item_valid, const float* a_scale, const float* a_shift, const float* a_alpha, int a_fold_cols,
-               const void* G, int g_cols, int g_pitch, int g_col0, float* parts, float* dw, bool accumulate, cudaStream_t st);
+               const void* G, int g_cols, int g_pitch, int g_col0, float* parts, float* dw, bool accumulate, cudaStream_t st,
+               int map_mode = 0, int map_n_log = 0, int map_k_log = 0, int map_c0 = 0, int map_c0p = 0);
+// map_mode != 0: dw is the reference-layout gradient tensor and the per-CTA partial sums are ADDED to it re-laid out in the
+// same launch (1: 1x1 convolution dst[n][k] over logical channels; 2: 3x3 convolution dst[n][k][dy][dx]); see umma_train.cu
 int umma_conv2_dgrad(const void* g2x, const void* wd, long long rows, int Hp, int Wp, void* out, cudaStream_t st);
 }  // namespace tcvn

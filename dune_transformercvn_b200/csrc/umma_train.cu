@@ -372,6 +372,53 @@ __global__ void __launch_bounds__(256) reduce_parts_kernel(const float4* __restr
   }
 }
 
+// Same reduction, fused with the re-layout into the reference's weight-gradient tensor (one launch instead of reduce +
+// unpack): element e of the summed [.. ][128][128] result is ADDED to dst at
+//   mode 1 (1x1 convolution, items = 128-channel column blocks): e = kp * 128 + n  ->  dst[n][k], k = logical channel of
+//          the physical concat channel kp (alignment-padding channels [c0, c0p) are skipped), n < n_log, k < k_log
+//   mode 2 (3x3 convolution): e = (dy * 128 + k) * 128 + dx * 32 + n  ->  dst[n][k][dy][dx]  (columns >= 96 are padding)
+struct MapArgs { int mode, n_log, k_log, c0, c0p; };
+__global__ void __launch_bounds__(256) reduce_parts_map_kernel(const float4* __restrict__ parts, int n_parts, long long n4,
+                                                               const MapArgs a, float* __restrict__ dst) {
+  __shared__ float4 sh[8][32];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + lane;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n4) {
+#pragma unroll 4
+    for (int q = slice; q < n_parts; q += 8) {
+      const float4 v = __ldg(parts + (size_t)q * n4 + i);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  }
+  sh[slice][lane] = s;
+  __syncthreads();
+  if (slice == 0 && i < n4) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float4 v = sh[k][lane];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    const float tv[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long e = i * 4 + j;
+      const int col = (int)(e & 127);
+      const int row = (int)(e >> 7);
+      if (a.mode == 1) {
+        int k = -1;
+        if (row < a.c0) k = row;
+        else if (row >= a.c0p) k = row - (a.c0p - a.c0);
+        if (k >= 0 && k < a.k_log && col < a.n_log) dst[(size_t)col * a.k_log + k] += tv[j];
+      } else {
+        const int dy = row >> 7, k = row & 127, dx = col >> 5, n = col & 31;
+        if (dx < 3 && dy < 3) dst[(((size_t)n * 128 + k) * 3 + dy) * 3 + dx] += tv[j];
+      }
+    }
+  }
+}
+
 }  // namespace
 
 // out[i] (+)= sum_q parts[q][i], q in a fixed order (n floats per part, n % 4 == 0)
@@ -391,10 +438,11 @@ size_t umma_wgrad_parts_bytes(int n_items) { return (size_t)kWgMaxCtas * n_items
 // parts: scratch of umma_wgrad_parts_bytes(n_items) for the per-CTA partial sums
 int umma_wgrad(const void* A, long long rows, int a_cols, int a_pitch, int n_items, const int* item_col, const int* item_shift,
                const int* item_valid, const float* a_scale, const float* a_shift, const float* a_alpha, int a_fold_cols,
-               const void* G, int g_cols, int g_pitch, int g_col0, float* parts, float* dw, bool accumulate, cudaStream_t st) {
+               const void* G, int g_cols, int g_pitch, int g_col0, float* parts, float* dw, bool accumulate, cudaStream_t st,
+               int map_mode, int map_n_log, int map_k_log, int map_c0, int map_c0p) {
   if (n_items < 1 || n_items > 4) return fail(TCVN_ERR_ARG, "umma_wgrad: %d items (1..4)", n_items);
   if (rows <= 0) {
-    if (!accumulate) TCVN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)n_items * 128 * 128, st));
+    if (!accumulate && map_mode == 0) TCVN_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)n_items * 128 * 128, st));
     return TCVN_OK;
   }
   if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one launch");
@@ -428,6 +476,12 @@ int umma_wgrad(const void* A, long long rows, int a_cols, int a_pitch, int n_ite
   else umma_wgrad_kernel<false><<<grid, kWgThreads, smem, st>>>(tmA, tmG, p);
   TCVN_LAUNCH_CHECK();
   const long long n4 = (long long)n_items * 128 * 128 / 4;
+  if (map_mode != 0) {   // reduce the per-CTA partials straight into the reference-layout gradient tensor
+    MapArgs ma{map_mode, map_n_log, map_k_log, map_c0, map_c0p};
+    reduce_parts_map_kernel<<<(unsigned)ceil_div_ll(n4, 32), 256, 0, st>>>(reinterpret_cast<const float4*>(parts), grid, n4, ma, dw);
+    TCVN_LAUNCH_CHECK();
+    return TCVN_OK;
+  }
   reduce_parts_kernel<<<(unsigned)ceil_div_ll(n4, 32), 256, 0, st>>>(reinterpret_cast<const float4*>(parts), grid, n4,
                                                                      reinterpret_cast<float4*>(dw), accumulate ? 1 : 0);
   TCVN_LAUNCH_CHECK();
