@@ -386,6 +386,42 @@ def run_train_leg(args, dev, rank, world, timed, train_events, with_cpu, fixed_p
     return out
 
 
+SDXL_GFLOP_PER_IMAGE = 57.23   # 3x3 / 1x1 convolutions of the --sdxl encoder at 400x280 (block 0: 35.1, block 1: 8.8, block 2: 7.9, ...)
+
+
+def run_sdxl_leg(args, dev, timed, pk):
+    """BASELINE configs[3]: the --sdxl CNN variant (SDXL-style VAE encoder as the pixel-map embedding), eval inference over
+    `--sdxl-events` events, bf16 tensor-core walk (dune_transformercvn_b200/sdxl.py::_SdxlCnn16).  PARITY UNPINNED: the
+    reference's arithmetic lives in un-vendored, unpinned `diffusers`; held to oracle/restate_sdxl.py only."""
+    from dune_transformercvn_b200.config import NUM_EVENT_CLASSES, NUM_PRONG_CLASSES, PathOptions
+    from dune_transformercvn_b200.sdxl import NeutrinoSDXLNetwork
+    opts = PathOptions.tutorial()
+    net = NeutrinoSDXLNetwork(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES, precision="bf16").to(dev).eval()
+    batch = make_inputs(args.sdxl_events, 1234)
+    resident = batch.to(dev)
+    images = batch.num_events + batch.num_prongs
+    steps = 3
+    with torch.no_grad():
+        net.forward_sparse(resident)
+        net.freeze_packed(True)
+        net.forward_sparse(resident)
+        ms = timed(lambda: net.forward_sparse(resident), steps)
+    tf = images * SDXL_GFLOP_PER_IMAGE * 1e9 * steps / (ms / 1e3) / 1e12
+    out = {"metric": METRIC, "value": args.sdxl_events * steps / (ms / 1e3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+           "dtype": "bf16", "images_per_s": images * steps / (ms / 1e3),
+           "config": {"workload": f"BASELINE configs[3]: --sdxl CNN variant, eval inference, {args.sdxl_events} events "
+                                  f"({images} images of 3x400x280), hit lists resident -> densify -> logits",
+                      "parity": "unpinned (diffusers absent; oracle/restate_sdxl.py restates its published layout)"},
+           "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
+                        "frac": tf / pk["bf16_sustained"], "traffic": None,
+                        "kernel": "whole --sdxl network (every convolution = umma_gemm_kernel<false> in shifted-GEMM form)",
+                        "algorithmic_gflop_per_image": SDXL_GFLOP_PER_IMAGE,
+                        "peak_source": pk["source"] + " cuBLAS bf16 sustained (kernel timed inside a long step)"}}
+    del net, resident
+    torch.cuda.empty_cache()
+    return out
+
+
 def kernel_rooflines(net, resident, batch, dev, pk, args):
     """Times the two layer kernels of dense block 1 alone (CUDA events on the launching stream, inputs ~0.8 GB
     per launch, i.e. larger than L2).  Dominant kernel of the step = the fused-activation 1x1 GEMM family
@@ -585,6 +621,12 @@ def run_ours(args):
                 eager = time_torch_eager_b200(dev, 64, args.train_events)
             except Exception as e:   # a baseline must never take the benchmark down
                 eager = {"error": f"{type(e).__name__}: {e}"[:300]}
+    sdxl = None
+    if world == 1 and not args.no_sdxl:
+        try:
+            sdxl = run_sdxl_leg(args, dev, timed, pk)
+        except Exception as e:
+            sdxl = {"error": f"{type(e).__name__}: {e}"[:300]}
     single = None
     if world == 1 and not args.no_train:
         try:
@@ -603,7 +645,7 @@ def run_ours(args):
             "gpu_launches": launches, "images_per_s": value * images / args.events,
             "whole_net_tflops": tflops, "roofline": roofline, "rooflines_other": extra_rooflines,
             "cpu_baseline": cpu, "clocks": sampler.summary(), "train": train, "train_large_batch": train_large,
-            "config5_max_prongs": config5, "launch_mode": "kernel by kernel" if args.no_graph else "CUDA graph replay per batch shape",
+            "config5_max_prongs": config5, "sdxl_variant": sdxl, "launch_mode": "kernel by kernel" if args.no_graph else "CUDA graph replay per batch shape",
             "torch_eager_b200": eager, "single_event_latency": single}
     emit(line)
     if world > 1:
@@ -647,6 +689,8 @@ def main():
     ap.add_argument("--train-steps", type=int, default=20)
     ap.add_argument("--unbalanced", action="store_true", help="training: independent prong draws per rank (unequal work) "
                     "instead of an equal total per rank")
+    ap.add_argument("--no-sdxl", action="store_true", help="skip the BASELINE configs[3] leg (--sdxl CNN variant)")
+    ap.add_argument("--sdxl-events", type=int, default=256)
     ap.add_argument("--no-config5", action="store_true", help="skip the BASELINE configs[4] leg (16 events x 20 prongs)")
     ap.add_argument("--no-graph", action="store_true", help="inference: launch the step kernel by kernel instead of replaying "
                     "its CUDA graph")

@@ -135,6 +135,12 @@ constexpr int kXformThreads = 256;
 struct GemmParams {
   long long m_total;
   int kchunks, kphys;      // K chunks of 64; channels >= kphys are forced to zero by the transform
+  // shifted-GEMM form (3x3 convolutions of the --sdxl CNN): the K loop runs over n_taps row-shifted views of A
+  // (chunks_per_tap chunks each, rows m + tap_off[t]: a 3x3 tap is a constant row offset in the ringed layout, rows outside
+  // the matrix read as zero) followed by chunks2 chunks of a SECOND matrix (tmA2, no shift) - the residual input of a
+  // ResNet block (identity or 1x1-shortcut weights in the matching K range of W).  Plain GEMM: n_taps = 1, tap_off = {0}.
+  int n_taps, chunks_per_tap, chunks2;
+  int tap_off[9];
   int n_tiles_n;           // N tiles of 128 (1 for conv1)
   const float *a_scale, *a_shift, *a_alpha;  // [kchunks*64] (TRANSFORM only)
   const float *o_shift, *o_alpha;            // [n_tiles_n*128]
@@ -162,6 +168,7 @@ template <bool TRANSFORM, bool MMASHIFT>
 __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                   const __grid_constant__ CUtensorMap tmW,
                                                                   const __grid_constant__ CUtensorMap tmO,
+                                                                  const __grid_constant__ CUtensorMap tmA2,
                                                                   const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -191,6 +198,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmW);
     ptx::prefetch_tmap(&tmO);
+    ptx::prefetch_tmap(&tmA2);
   }
   if (warp == 0) ptx::tmem_alloc(tmem_slot, 256);
   if (MMASHIFT) {
@@ -218,10 +226,17 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
+        const int tap_chunks = p.n_taps * p.chunks_per_tap;
+        int tap = 0, kk = 0;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&full[stage], kStageA + kStageW);
-          ptx::tma_load_2d(sA + stage * kStageA, &tmA, &full[stage], kc * 64, mt * kTileM);
+          if (kc < tap_chunks) {
+            ptx::tma_load_2d(sA + stage * kStageA, &tmA, &full[stage], kk * 64, mt * kTileM + p.tap_off[tap]);
+            if (++kk == p.chunks_per_tap) { kk = 0; ++tap; }
+          } else {
+            ptx::tma_load_2d(sA + stage * kStageA, &tmA2, &full[stage], (kc - tap_chunks) * 64, mt * kTileM);
+          }
           ptx::tma_load_2d(sW + stage * kStageW, &tmW, &full[stage], kc * 64, nt * kMid);
           if (++stage == kC1Stages) { stage = 0; phase ^= 1; }
         }
@@ -764,6 +779,8 @@ int launch_gemm(bool transform, const void* A, long long rows, int a_cols, int a
   TCVN_TRY(make_map(out, rows, out_cols, out_pitch, 64, kTileM, &tmO));
   GemmParams g;
   g.m_total = rows; g.kchunks = kpad / kKChunk; g.kphys = kphys; g.n_tiles_n = n_tiles_n;
+  g.n_taps = 1; g.chunks_per_tap = g.kchunks; g.chunks2 = 0;
+  for (int t = 0; t < 9; ++t) g.tap_off[t] = 0;
   g.a_scale = a_scale; g.a_shift = a_shift; g.a_alpha = a_alpha; g.o_shift = o_shift; g.o_alpha = o_alpha;
   g.Hp = Hp; g.Wp = Wp;
   g.stats = stats;
@@ -772,10 +789,50 @@ int launch_gemm(bool transform, const void* A, long long rows, int a_cols, int a
   if (stat_slots) *stat_slots = 2 * grid;
   static const bool mma_shift_on = [] { const char* v = getenv("TCVN_MMA_SHIFT"); return !(v && v[0] == '0'); }();
   const bool ms = mma_shift_on && n_tiles_n == 1;
-  if (transform && ms) umma_gemm_kernel<true, true><<<grid, kC1Threads, smem, st>>>(tmA, tmW, tmO, g);
-  else if (transform) umma_gemm_kernel<true, false><<<grid, kC1Threads, smem, st>>>(tmA, tmW, tmO, g);
-  else if (ms) umma_gemm_kernel<false, true><<<grid, kC1Threads, smem, st>>>(tmA, tmW, tmO, g);
-  else umma_gemm_kernel<false, false><<<grid, kC1Threads, smem, st>>>(tmA, tmW, tmO, g);
+  if (transform && ms) umma_gemm_kernel<true, true><<<grid, kC1Threads, smem, st>>>(tmA, tmW, tmO, tmA, g);
+  else if (transform) umma_gemm_kernel<true, false><<<grid, kC1Threads, smem, st>>>(tmA, tmW, tmO, tmA, g);
+  else if (ms) umma_gemm_kernel<false, true><<<grid, kC1Threads, smem, st>>>(tmA, tmW, tmO, tmA, g);
+  else umma_gemm_kernel<false, false><<<grid, kC1Threads, smem, st>>>(tmA, tmW, tmO, tmA, g);
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+// Shifted GEMM on tcgen05 (3x3 / 1x1 convolutions of the --sdxl CNN over ringed channels-last bf16 maps):
+//   out[m, n] = sum_t sum_c A[m + tap_off[t], c] * W[n, t * a_cols + c]  +  sum_c X2[m, c] * W[n, n_taps * a_cols + c]  +  bias[n]
+// ring rows of `out` are written as zeros.  a_cols, x2_cols: multiples of 64; W bf16 [n_tiles * 128][n_taps * a_cols + x2_cols]
+// (K-major, zero rows beyond the real output width); X2 may be null (x2_cols = 0).
+int launch_gemm_shifted(const void* A, long long rows, int a_cols, int n_taps, const int* tap_off, const void* X2, int x2_cols,
+                        const void* W, int n_tiles_n, const float* bias, const float* ones, void* out, int out_cols, int Hp, int Wp,
+                        cudaStream_t st) {
+  if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one chunk");
+  if (a_cols % 64 || x2_cols % 64 || n_taps < 1 || n_taps > 9) return fail(TCVN_ERR_ARG, "launch_gemm_shifted: bad shape");
+  const size_t smem = 1024 + kC1Stages * (kStageA + kStageW) + 4 * kStageA + kStageA + kStageW + 2 * 192 * 4 +
+                      (3 * kC1Stages + 4) * 8 + 16;
+  bool& attr_done = device_flag(1);
+  if (!attr_done) {
+    TCVN_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TCVN_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TCVN_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    TCVN_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  const int ktot = n_taps * a_cols + x2_cols;
+  CUtensorMap tmA, tmW, tmO, tmX;
+  TCVN_TRY(make_map(A, rows, a_cols, a_cols, 64, kTileM, &tmA));
+  TCVN_TRY(make_map(W, (long long)n_tiles_n * kMid, ktot, ktot, 64, kMid, &tmW));
+  TCVN_TRY(make_map(out, rows, out_cols, out_cols, 64, kTileM, &tmO));
+  if (X2) TCVN_TRY(make_map(X2, rows, x2_cols, x2_cols, 64, kTileM, &tmX));
+  else tmX = tmA;
+  GemmParams g;
+  g.m_total = rows; g.kchunks = ktot / kKChunk; g.kphys = ktot; g.n_tiles_n = n_tiles_n;
+  g.n_taps = n_taps; g.chunks_per_tap = a_cols / kKChunk; g.chunks2 = x2_cols / kKChunk;
+  for (int t = 0; t < 9; ++t) g.tap_off[t] = t < n_taps && tap_off ? tap_off[t] : 0;
+  g.a_scale = g.a_shift = g.a_alpha = nullptr; g.o_shift = bias; g.o_alpha = ones;
+  g.Hp = Hp; g.Wp = Wp; g.stats = nullptr;
+  g.num_tiles = (int)ceil_div_ll(rows, kTileM) * n_tiles_n;
+  const int grid = g.num_tiles < sm_count() ? g.num_tiles : sm_count();
+  if (n_tiles_n == 1) umma_gemm_kernel<false, true><<<grid, kC1Threads, smem, st>>>(tmA, tmW, tmO, tmX, g);
+  else umma_gemm_kernel<false, false><<<grid, kC1Threads, smem, st>>>(tmA, tmW, tmO, tmX, g);
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
 }

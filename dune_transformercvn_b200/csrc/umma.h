@@ -21,6 +21,9 @@ int launch_gemm(bool transform, const void* A, long long rows, int a_cols, int a
                 int kphys, const float* a_scale, const float* a_shift, const float* a_alpha, const float* o_shift,
                 const float* o_alpha, void* out, int out_cols, int out_pitch, int n_tiles_n, int Hp, int Wp, cudaStream_t st,
                 double* stats = nullptr, int* stat_slots = nullptr);
+int launch_gemm_shifted(const void* A, long long rows, int a_cols, int n_taps, const int* tap_off, const void* X2, int x2_cols,
+                        const void* W, int n_tiles_n, const float* bias, const float* ones, void* out, int out_cols, int Hp, int Wp,
+                        cudaStream_t st);
 // slots of the epilogue statistics (doubles [slots][2][128] for launch_gemm, [slots][2][32] for umma_conv2_fwd)
 constexpr int kUmmaStatSlotsMax = 8 * 148;
 int umma_conv2_fwd(const void* mid, long long rows, const void* w2, const float* bias, void* out, int ldo, int col0, int Hp,

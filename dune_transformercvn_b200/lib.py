@@ -35,6 +35,8 @@ EXPORTS = (
     "tcvn_t_umma_wgrad", "tcvn_t_umma_wgrad_workspace_bytes", "tcvn_t_umma_conv2_dgrad",
     "tcvn_loss_forward", "tcvn_loss_backward", "tcvn_metrics_update",
     "tcvn_sdxl_pixels_to_ring", "tcvn_sdxl_groupnorm", "tcvn_sdxl_patch_s2", "tcvn_set_sm_limit",
+    "tcvn_sdxl16_patch27", "tcvn_sdxl16_groupnorm_workspace_bytes", "tcvn_sdxl16_groupnorm", "tcvn_sdxl16_patch_s2",
+    "tcvn_sdxl16_to_f32", "tcvn_sdxl16_conv",
 )
 
 
@@ -138,6 +140,13 @@ def load() -> C.CDLL:
     lib.tcvn_sdxl_groupnorm.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, f32, i32, vp, vp, vp]
     lib.tcvn_sdxl_patch_s2.argtypes = [vp, i32, i32, i32, i32, vp, vp]
     lib.tcvn_set_sm_limit.argtypes = [i32]
+    lib.tcvn_sdxl16_patch27.argtypes = [vp, i32, i32, i32, i32, f32, vp, vp]
+    lib.tcvn_sdxl16_groupnorm_workspace_bytes.argtypes = [i32]
+    lib.tcvn_sdxl16_groupnorm_workspace_bytes.restype = sz
+    lib.tcvn_sdxl16_groupnorm.argtypes = [vp, i32, i32, i32, i32, vp, vp, f32, i32, vp, vp, sz, vp]
+    lib.tcvn_sdxl16_patch_s2.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+    lib.tcvn_sdxl16_to_f32.argtypes = [vp, i64, vp, vp]
+    lib.tcvn_sdxl16_conv.argtypes = [vp, i64, i32, i32, vp, vp, i32, vp, i32, vp, vp, vp, i32, i32, i32, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ("tcvn_abi_version",):

@@ -113,10 +113,10 @@ class _SdxlCnn:
         e = "encoder."
         x = self._conv3(L, st, e + "conv_in", ring, n, h, w_, cin0, self.ch[0])
         cin = self.ch[0]
-        for i, cout in enumerate(self.ch):
+        for i, cout in enumerate(self.ch[:-1]):
             for j in range(2):
                 x = self._resnet(L, st, f"{e}down_blocks.{i}.resnets.{j}.", x, n, h, w_, cin if j == 0 else cout, cout, sums)
-            if i != len(self.ch) - 1:
+            if True:
                 if h < 2 or w_ < 2:
                     raise _lib.TcvnError(f"sdxl: a {h}x{w_} map cannot be down-sampled again (input too small)")
                 ho, wo = h // 2, w_ // 2
@@ -130,9 +130,22 @@ class _SdxlCnn:
                 del patches
                 h, w_ = ho, wo
             cin = cout
-        c = self.ch[-1]
         if (h, w_) != (1, 1):
             raise _lib.TcvnError(f"sdxl: the mid block is reached at {h}x{w_}; only the 1x1 case (400x280 inputs) is built")
+        return self._tail(L, st, x, n, cin)
+
+    def _tail(self, L, st, x: torch.Tensor, n: int, cin: int) -> torch.Tensor:
+        """The 1x1-spatial end of the encoder on a ringed fp32 map [n*9][cin]: last down block, mid block (ResNet, attention
+        over one position, ResNet), GroupNorm + SiLU + conv_out, Flatten + Linear."""
+        dev = x.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        sums = torch.empty(2 * n, dtype=torch.float64, device=dev)
+        e = "encoder."
+        h = w_ = 1
+        i, cout = len(self.ch) - 1, self.ch[-1]
+        for j in range(2):
+            x = self._resnet(L, st, f"{e}down_blocks.{i}.resnets.{j}.", x, n, h, w_, cin if j == 0 else cout, cout, sums)
+        c = self.ch[-1]
         m = e + "mid_block."
         x = self._resnet(L, st, m + "resnets.0.", x, n, h, w_, c, c, sums)
         # Attention over ONE position: softmax over a single key is 1, so out = to_out(to_v(group_norm(x))) + x
@@ -153,6 +166,134 @@ class _SdxlCnn:
         return out
 
 
+def _pad_to(v: int, a: int) -> int:
+    return (v + a - 1) // a * a
+
+
+class _SdxlCnn16(_SdxlCnn):
+    """bf16 / tcgen05 walk of one SDXLNet (round 2).  Down blocks 0..7 (400x280 ... 3x2 maps, 99.9 % of the FLOPs) run on
+    the tensor cores: every 3x3 convolution is ONE shifted GEMM (``tcvn_sdxl16_conv``: nine row-shifted views of the
+    activated map as the K loop), and a ResNet block's residual add / 1x1 shortcut rides in the same GEMM as a trailing K
+    segment over the block input with identity / shortcut weights.  The 1x1-spatial tail (last down block, mid block,
+    conv_out, Linear: 9 rows per image) stays on the fp32 kernels of the base class."""
+
+    image_chunk = 48   # images per walk: ~60 MB of bf16 maps per image at 400x280
+
+    def pack(self, tensors: Dict[str, torch.Tensor]) -> None:
+        super().pack(tensors)     # fp32 GEMM layouts for the tail
+        self.w16: Dict[str, Tuple[torch.Tensor, torch.Tensor, int, int]] = {}
+        dev = None
+        raw = {n[len(self.prefix):]: t.detach().float() for n, t in tensors.items() if n.startswith(self.prefix)}
+        dev = next(iter(raw.values())).device
+        self.ones = torch.ones(1024, dtype=torch.float32, device=dev)
+
+        def conv_k(wt: torch.Tensor, cin_pad: int) -> torch.Tensor:
+            """(Cout, Cin, kh, kw) -> [Cout][kh*kw*cin_pad], K index = tap * cin_pad + c"""
+            co, ci, kh, kw = wt.shape
+            out = torch.zeros((co, kh * kw, cin_pad), dtype=torch.float32, device=wt.device)
+            out[:, :, :ci] = wt.permute(0, 2, 3, 1).reshape(co, kh * kw, ci)
+            return out.reshape(co, kh * kw * cin_pad)
+
+        def finish(key: str, wk: torch.Tensor, bias: torch.Tensor) -> None:
+            co, k = wk.shape
+            n_tiles = _pad_to(co, 128) // 128
+            w = torch.zeros((n_tiles * 128, _pad_to(k, 64)), dtype=torch.float32, device=wk.device)
+            w[:co, :k] = wk
+            b = torch.zeros(n_tiles * 128, dtype=torch.float32, device=wk.device)
+            b[:co] = bias
+            self.w16[key] = (w.to(torch.bfloat16).contiguous(), b, n_tiles, co)
+
+        e = "encoder."
+        # conv_in: one 64-wide K chunk, column (tap, channel) with stride 3 (tcvn_sdxl16_patch27)
+        wt = raw[e + "conv_in.weight"]
+        co, ci = wt.shape[0], wt.shape[1]
+        wk = torch.zeros((co, 64), dtype=torch.float32, device=dev)
+        for c in range(ci):
+            wk[:, c:27:3] = wt[:, c].reshape(co, 9)
+        finish("conv_in", wk, raw[e + "conv_in.bias"])
+        cin = self.ch[0]
+        for i, cout in enumerate(self.ch[:-1]):
+            for j in range(2):
+                p = f"{e}down_blocks.{i}.resnets.{j}."
+                c_in = cin if j == 0 else cout
+                finish(p + "conv1", conv_k(raw[p + "conv1.weight"], c_in), raw[p + "conv1.bias"])
+                w2 = conv_k(raw[p + "conv2.weight"], cout)
+                if c_in != cout:   # 1x1 shortcut as the trailing K segment
+                    tail = raw[p + "conv_shortcut.weight"].reshape(cout, c_in)
+                    bias = raw[p + "conv2.bias"] + raw[p + "conv_shortcut.bias"]
+                else:              # identity: out = conv2(a) + x
+                    tail = torch.eye(cout, dtype=torch.float32, device=dev)
+                    bias = raw[p + "conv2.bias"]
+                finish(p + "conv2", torch.cat((w2, tail), dim=1), bias)
+            d = f"{e}down_blocks.{i}.downsamplers.0.conv"
+            finish(d, conv_k(raw[d + ".weight"], cout), raw[d + ".bias"])
+            cin = cout
+
+    def _conv16(self, L, st, key, a, rows, a_cols, taps, wp, x2, x2_cols, hp_wp):
+        w, b, n_tiles, co = self.w16[key]
+        out = torch.empty((rows, co), dtype=torch.bfloat16, device=a.device)
+        _lib.check(L.tcvn_sdxl16_conv(_lib.ptr(a), rows, a_cols, taps, _taps3(wp) if taps == 9 else None, _lib.ptr(x2), x2_cols,
+                                      _lib.ptr(w), n_tiles, _lib.ptr(b), _lib.ptr(self.ones), _lib.ptr(out), co, hp_wp[0], hp_wp[1],
+                                      st), "tcvn_sdxl16_conv")
+        return out
+
+    def _norm16(self, L, st, name, x, n, h, w_, c, ws):
+        out = torch.empty_like(x)
+        _lib.check(L.tcvn_sdxl16_groupnorm(_lib.ptr(x), n, c, h, w_, _lib.ptr(self.w[name + ".weight"]), _lib.ptr(self.w[name + ".bias"]),
+                                           GN_EPS, 1, _lib.ptr(out), _lib.ptr(ws), ws.numel(), st), "tcvn_sdxl16_groupnorm")
+        return out
+
+    def forward(self, pixels: torch.Tensor) -> torch.Tensor:
+        outs = [self._forward_chunk(pixels[i:i + self.image_chunk]) for i in range(0, pixels.shape[0], self.image_chunk)]
+        if not outs:
+            return torch.empty((0, self.out), dtype=torch.float32, device=pixels.device)
+        return torch.cat(outs) if len(outs) > 1 else outs[0]
+
+    def _forward_chunk(self, pixels: torch.Tensor) -> torch.Tensor:
+        L = _lib.load()
+        dev = pixels.device
+        st = _lib.stream_ptr(dev)
+        n, cin0, h, w_ = pixels.shape
+        if cin0 != self.in_ch or cin0 > 3:
+            raise _lib.TcvnError(f"sdxl bf16: pixels have {cin0} channels, expected {self.in_ch} (<= 3)")
+        pixels = pixels.contiguous().float()
+        ws = torch.empty(L.tcvn_sdxl16_groupnorm_workspace_bytes(n), dtype=torch.uint8, device=dev)
+        e = "encoder."
+        hp, wp = h + 2, w_ + 2
+        rows = n * hp * wp
+        patches = torch.empty((rows, 64), dtype=torch.bfloat16, device=dev)
+        _lib.check(L.tcvn_sdxl16_patch27(_lib.ptr(pixels), n, cin0, h, w_, 0.0, _lib.ptr(patches), st), "tcvn_sdxl16_patch27")
+        x = self._conv16(L, st, "conv_in", patches, rows, 64, 1, wp, None, 0, (hp, wp))
+        del patches
+        cin = self.ch[0]
+        for i, cout in enumerate(self.ch[:-1]):
+            hp, wp = h + 2, w_ + 2
+            rows = n * hp * wp
+            for j in range(2):
+                p = f"{e}down_blocks.{i}.resnets.{j}."
+                c_in = cin if j == 0 else cout
+                a = self._norm16(L, st, p + "norm1", x, n, h, w_, c_in, ws)
+                t = self._conv16(L, st, p + "conv1", a, rows, c_in, 9, wp, None, 0, (hp, wp))
+                a = self._norm16(L, st, p + "norm2", t, n, h, w_, cout, ws)
+                x = self._conv16(L, st, p + "conv2", a, rows, cout, 9, wp, x, c_in, (hp, wp))   # conv2(a) + shortcut(x) + biases
+            if h < 2 or w_ < 2:
+                raise _lib.TcvnError(f"sdxl: a {h}x{w_} map cannot be down-sampled again (input too small)")
+            ho, wo = h // 2, w_ // 2
+            orows = n * (ho + 2) * (wo + 2)
+            pt = torch.empty((orows, 9 * cout), dtype=torch.bfloat16, device=dev)
+            _lib.check(L.tcvn_sdxl16_patch_s2(_lib.ptr(x), n, cout, h, w_, _lib.ptr(pt), st), "tcvn_sdxl16_patch_s2")
+            x = self._conv16(L, st, f"{e}down_blocks.{i}.downsamplers.0.conv", pt, orows, 9 * cout, 1, wo + 2, None, 0, (ho + 2, wo + 2))
+            del pt
+            h, w_ = ho, wo
+            cin = cout
+        if (h, w_) != (1, 1):
+            raise _lib.TcvnError(f"sdxl: the mid block is reached at {h}x{w_}; only the 1x1 case (400x280 inputs) is built")
+        x32 = torch.empty(tuple(x.shape), dtype=torch.float32, device=dev)
+        _lib.check(L.tcvn_sdxl16_to_f32(_lib.ptr(x), x.numel(), _lib.ptr(x32), st), "tcvn_sdxl16_to_f32")
+        return self._tail(L, st, x32, n, cin)
+
+
+
 class _SdxlEngine(_Engine):
     """The dense engine with the two pixel-map CNNs swapped; the sequence stage (tokens, encoder, heads) is shared."""
 
@@ -162,8 +303,9 @@ class _SdxlEngine(_Engine):
         pix, feat, _ = embedding_dims(o)
         pe = "prong_embedding."
         cnn_in = owner.pixel_dim
-        self.cnns = {"prong": _SdxlCnn(pe + "prong_pixel_embedding.", cnn_in, pix, o.initial_pixel_dim),
-                     "event": _SdxlCnn(pe + "event_pixel_embedding.", cnn_in, pix + feat, o.initial_pixel_dim)}
+        cls = _SdxlCnn16 if owner.precision == "bf16" else _SdxlCnn
+        self.cnns = {"prong": cls(pe + "prong_pixel_embedding.", cnn_in, pix, o.initial_pixel_dim),
+                     "event": cls(pe + "event_pixel_embedding.", cnn_in, pix + feat, o.initial_pixel_dim)}
 
     def ensure_packed(self, prec: int) -> None:
         net = self.owner[0]
@@ -219,8 +361,8 @@ class NeutrinoSDXLNetwork(NeutrinoDenseNetwork):
 
     def __init__(self, options, features_dim: int, extra_dim: int, pixel_dim: int, num_prong_classes: int,
                  num_event_classes: int, image_size=None, precision: str = "fp32", seed: int = 0):
-        if precision != "fp32":
-            raise _lib.TcvnError("NeutrinoSDXLNetwork: only the fp32 path is built (round 1)")
+        if precision not in ("fp32", "bf16"):
+            raise _lib.TcvnError("NeutrinoSDXLNetwork: precision must be fp32 (CUDA-core parity path) or bf16 (tcgen05 path)")
         kw = {} if image_size is None else {"image_size": image_size}
         super().__init__(options, features_dim, extra_dim, pixel_dim, num_prong_classes, num_event_classes,
                          precision=precision, seed=seed, **kw)

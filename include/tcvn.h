@@ -358,6 +358,27 @@ int tcvn_sdxl_groupnorm(const float* x_ring, int n, int C, int groups, int H, in
  * channels ordered (dy, dx, c), so that the convolution is a GEMM with K = 9*C */
 int tcvn_sdxl_patch_s2(const float* x_ring, int n, int C, int H, int W, float* out_ring, tcvn_stream_t stream);
 
+/* bf16 / tcgen05 path of the same CNN (csrc/sdxl16.cu, csrc/umma.cu): ringed channels-last bf16 maps [n*(H+2)*(W+2)][C].
+ *   tcvn_sdxl16_patch27    conv_in's 3x3 patches of the NCHW fp32 pixels as one 64-wide bf16 K chunk: column (dy*3+dx)*3 + c
+ *   tcvn_sdxl16_groupnorm  GroupNorm(1 group) (+ SiLU) per image, bit-reproducible statistics; C % 8 == 0
+ *   tcvn_sdxl16_patch_s2   patches [rows_out][9*C] of the stride-2 convolution behind F.pad(x, (0,1,0,1))
+ *   tcvn_sdxl16_conv       the convolution itself on the tensor cores, as a shifted GEMM:
+ *        out[m, n] = sum_t sum_c A[m + tap_off[t], c] W[n, t*a_cols + c] + sum_c X2[m, c] W[n, n_taps*a_cols + c] + bias[n]
+ *      (a 3x3 tap is a constant row offset of the ringed layout; X2 = the ResNet block's residual input, with identity or
+ *      1x1-shortcut weights in its K range, so the residual add costs no extra pass; ring rows of out are written as
+ *      zeros).  a_cols, x2_cols: multiples of 64.  W bf16 [n_tiles*128][n_taps*a_cols + x2_cols] K-major, zero rows
+ *      beyond the real output width; bias / ones: fp32 [n_tiles*128].
+ *   tcvn_sdxl16_to_f32     bf16 -> fp32 (the 1x1-spatial tail runs the fp32 kernels above) */
+int tcvn_sdxl16_patch27(const float* pixels_nchw, int n, int C, int H, int W, float divisor, void* out_bf16, tcvn_stream_t stream);
+size_t tcvn_sdxl16_groupnorm_workspace_bytes(int n);
+int tcvn_sdxl16_groupnorm(const void* x_bf16, int n, int C, int H, int W, const float* gamma, const float* beta, float eps, int silu,
+                          void* out_bf16, void* workspace, size_t workspace_bytes, tcvn_stream_t stream);
+int tcvn_sdxl16_patch_s2(const void* x_bf16, int n, int C, int H, int W, void* out_bf16, tcvn_stream_t stream);
+int tcvn_sdxl16_to_f32(const void* x_bf16, int64_t count, float* out, tcvn_stream_t stream);
+int tcvn_sdxl16_conv(const void* a_bf16, int64_t rows, int a_cols, int n_taps, const int32_t* tap_off, const void* x2_bf16,
+                     int x2_cols, const void* w_bf16, int n_tiles, const float* bias_padded, const float* ones_padded,
+                     void* out_bf16, int out_cols, int ring_hp, int ring_wp, tcvn_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

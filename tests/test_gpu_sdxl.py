@@ -86,3 +86,113 @@ def test_sdxl_kernels_against_torch(dev):
     got = y.view(n, ho + 2, wo + 2, co)[:, 1:-1, 1:-1].permute(0, 3, 1, 2).cpu()
     assert tuple(want.shape[2:]) == (ho, wo)
     assert rel_err(got, want) < 1e-5
+
+
+def _ring16(x, dev):
+    """NCHW fp32 -> ringed channels-last bf16 [n*(H+2)*(W+2)][C] on the device"""
+    n, c, h, w = x.shape
+    ring = torch.zeros(n, h + 2, w + 2, c)
+    ring[:, 1:-1, 1:-1] = x.permute(0, 2, 3, 1)
+    return ring.reshape(-1, c).to(dev).to(torch.bfloat16).contiguous()
+
+
+def _unring(y, n, h, w):
+    c = y.shape[1]
+    return y.float().view(n, h + 2, w + 2, c)[:, 1:-1, 1:-1].permute(0, 3, 1, 2).cpu()
+
+
+def test_sdxl16_tensor_core_conv_against_torch(dev):
+    """tcvn_sdxl16_conv (tcgen05 shifted GEMM): a 3x3 convolution with the residual input riding as a trailing K segment
+    (identity weights, and a 1x1 shortcut with a channel change), on an odd-sized map that spans several 128-row tiles and
+    images; tcvn_sdxl16_groupnorm and the stride-2 patch path.  bf16 operands, fp32 accumulation: 2e-2 of the output range."""
+    import torch.nn.functional as F
+    from dune_transformercvn_b200 import lib as tl
+    from dune_transformercvn_b200.sdxl import _taps3
+    L = tl.load()
+    st = tl.stream_ptr(dev)
+    g = torch.Generator().manual_seed(1)
+    n, h, w = 3, 25, 17
+    hp, wp = h + 2, w + 2
+    rows = n * hp * wp
+    ones = torch.ones(1024, device=dev)
+    for cin, cout in ((64, 64), (64, 128), (128, 256)):
+        a = torch.randn(n, cout, h, w, generator=g)           # activated map entering conv2
+        x = torch.randn(n, cin, h, w, generator=g)            # the block input (residual)
+        wt = torch.randn(cout, cout, 3, 3, generator=g) * 0.05
+        b = torch.randn(cout, generator=g)
+        if cin == cout:
+            tail, want_res = torch.eye(cout), x
+        else:
+            ws = torch.randn(cout, cin, generator=g) * 0.1
+            tail, want_res = ws, F.conv2d(x, ws.view(cout, cin, 1, 1))
+        a16, x16 = _ring16(a, dev), _ring16(x, dev)
+        want = F.conv2d(a16.float().cpu().view(n, hp, wp, cout)[:, 1:-1, 1:-1].permute(0, 3, 1, 2), wt.bfloat16().float(), b, padding=1)
+        want = want + (want_res.bfloat16().float() if cin == cout else
+                       F.conv2d(x.bfloat16().float(), tail.bfloat16().float().view(cout, cin, 1, 1)))
+        wk = torch.cat((wt.permute(0, 2, 3, 1).reshape(cout, 9 * cout), tail), dim=1)
+        n_tiles = (cout + 127) // 128
+        wpad = torch.zeros(n_tiles * 128, wk.shape[1])
+        wpad[:cout] = wk
+        bpad = torch.zeros(n_tiles * 128)
+        bpad[:cout] = b
+        d_w, d_b = wpad.to(dev).to(torch.bfloat16).contiguous(), bpad.to(dev)
+        out = torch.empty(rows, cout, dtype=torch.bfloat16, device=dev)
+        tl.check(L.tcvn_sdxl16_conv(tl.ptr(a16), rows, cout, 9, _taps3(wp), tl.ptr(x16), cin, tl.ptr(d_w), n_tiles, tl.ptr(d_b),
+                                    tl.ptr(ones), tl.ptr(out), cout, hp, wp, st), "sdxl16_conv")
+        got = _unring(out, n, h, w)
+        assert rel_err(got, want) < 2e-2, (cin, cout, rel_err(got, want))
+        ring = out.float().view(n, hp, wp, cout)
+        assert float(ring[:, 0].abs().max()) == 0.0 and float(ring[:, :, -1].abs().max()) == 0.0    # zero ring rows
+    # GroupNorm(1) + SiLU, bf16
+    c = 64
+    x = torch.randn(n, c, h, w, generator=g) * 2 + 0.5
+    x16 = _ring16(x, dev)
+    gamma, beta = (torch.rand(c, generator=g) + 0.5).to(dev), torch.randn(c, generator=g).to(dev)
+    ws = torch.empty(L.tcvn_sdxl16_groupnorm_workspace_bytes(n), dtype=torch.uint8, device=dev)
+    out = torch.empty_like(x16)
+    tl.check(L.tcvn_sdxl16_groupnorm(tl.ptr(x16), n, c, h, w, tl.ptr(gamma), tl.ptr(beta), 1e-6, 1, tl.ptr(out), tl.ptr(ws), ws.numel(),
+                                     st), "sdxl16_groupnorm")
+    xin = x16.float().cpu().view(n, hp, wp, c)[:, 1:-1, 1:-1].permute(0, 3, 1, 2)
+    want = F.silu(F.group_norm(xin, 1, gamma.cpu(), beta.cpu(), 1e-6))
+    assert rel_err(_unring(out, n, h, w), want) < 1e-2
+    # Downsample2D: pad (0,1,0,1) + conv 3x3 stride 2 as patches + plain GEMM
+    wt, b = torch.randn(c, c, 3, 3, generator=g) * 0.05, torch.randn(c, generator=g)
+    ho, wo = h // 2, w // 2
+    orows = n * (ho + 2) * (wo + 2)
+    pt = torch.empty(orows, 9 * c, dtype=torch.bfloat16, device=dev)
+    tl.check(L.tcvn_sdxl16_patch_s2(tl.ptr(x16), n, c, h, w, tl.ptr(pt), st), "sdxl16_patch_s2")
+    wpad = torch.zeros(128, 9 * c)
+    wpad[:c] = wt.permute(0, 2, 3, 1).reshape(c, 9 * c)
+    bpad = torch.zeros(128)
+    bpad[:c] = b
+    d_w, d_b = wpad.to(dev).to(torch.bfloat16).contiguous(), bpad.to(dev)
+    y = torch.empty(orows, c, dtype=torch.bfloat16, device=dev)
+    tl.check(L.tcvn_sdxl16_conv(tl.ptr(pt), orows, 9 * c, 1, None, None, 0, tl.ptr(d_w), 1, tl.ptr(d_b), tl.ptr(ones), tl.ptr(y), c,
+                                ho + 2, wo + 2, st), "sdxl16_conv(patches)")
+    want = F.conv2d(F.pad(xin, (0, 1, 0, 1)), wt.bfloat16().float(), b, stride=2)
+    assert rel_err(_unring(y, n, ho, wo), want) < 2e-2
+
+
+def test_sdxl_bf16_forward_tracks_oracle(dev):
+    """The tcgen05 walk of the --sdxl network against the (unpinned) oracle: bf16 tolerance 2e-2 on the logits (north_star's
+    bf16 bound), embeddings within 5e-2 of their range; top-1 classes agree."""
+    opts = PathOptions.tutorial()
+    net = NeutrinoSDXLNetwork(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES, precision="bf16")
+    state = synth.init_state(net.specs, seed=4, perturb=True)
+    net.load_state_dict(state, strict=True)
+    net = net.to(dev).eval()
+    batch = synth.make_batch(2, seed=8, prongs_per_event=[2, 1])
+    ev = restate.densify(restate.preprocess_values(batch.event_values), batch.event_coords, H, W)
+    pr = restate.densify(restate.preprocess_values(batch.prong_values), batch.prong_coords, H, W)
+    taps = {}
+    with torch.no_grad():
+        want_ev, want_pr = restate_sdxl.network_forward(state, opts, ev, batch.event_mask, pr, batch.prong_mask, taps=taps)
+        eng = net.engine
+        eng.ensure_packed(1)
+        got_pe = eng.cnn("prong", pr.to(dev), 1)
+        got_ev, got_pr = net.forward_sparse(batch.to(dev))
+    e_emb = rel_err(got_pe.cpu(), taps["prong_embedding"])
+    e_ev, e_pr = rel_err(got_ev.cpu(), want_ev), rel_err(got_pr.cpu(), want_pr)
+    print("sdxl bf16: embedding", e_emb, "event logits", e_ev, "prong logits", e_pr)
+    assert e_emb < 5e-2 and e_ev < 2e-2 and e_pr < 2e-2
+    assert torch.equal(got_ev.argmax(1).cpu(), want_ev.argmax(1))
