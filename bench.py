@@ -354,7 +354,10 @@ def run_train_leg(args, dev, rank, world, timed, train_events, with_cpu, fixed_p
         g_mean = a.gflat.clone()
         dist.all_reduce(g_mean, op=dist.ReduceOp.SUM)
         g_mean /= world
-        sums = torch.stack((g_avg.double().sum(), g_avg.double().abs().sum(), a.flat.double().sum(), a.flat.double().abs().sum()))
+        # parameters only: the arena also holds the BatchNorm running buffers, which are rank-local between two forwards
+        # by design (each rank updates them from its own shard; rank 0's are broadcast before the next forward, like DDP)
+        params = a.flat[opt._selector() > 0].double()
+        sums = torch.stack((g_avg.double().sum(), g_avg.double().abs().sum(), params.sum(), params.abs().sum()))
         gathered = [torch.empty_like(sums) for _ in range(world)]
         dist.all_gather(gathered, sums)
         gathered = torch.stack(gathered)

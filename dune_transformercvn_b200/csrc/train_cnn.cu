@@ -725,8 +725,10 @@ struct FinArgs16 {
   float* fold;
 };
 
-__global__ void __launch_bounds__(256) bn_finalize16_kernel(const FinArgs16 a) {
-  __shared__ double red[2][16][17];
+constexpr int kRedSlices = 64;   // slices per 16-column block of the slot reductions (1024 threads)
+
+__global__ void __launch_bounds__(1024) bn_finalize16_kernel(const FinArgs16 a) {
+  __shared__ double red[2][kRedSlices][17];
   const int col = threadIdx.x & 15, slice = threadIdx.x >> 4;
   const int p = blockIdx.x * 16 + col;
   const bool fresh = a.fresh.parts != nullptr && p < a.n_out && p >= a.fresh.col0 && p < a.fresh.col0 + a.fresh.ncols;
@@ -736,17 +738,17 @@ __global__ void __launch_bounds__(256) bn_finalize16_kernel(const FinArgs16 a) {
     const double* base = a.fresh.parts + q;
     const size_t cp = (size_t)a.fresh.Cp;
     int s = slice;
-    for (; s + 16 * 3 < a.fresh.n_slots; s += 16 * 4) {   // 8 independent loads in flight, added in slot order
+    for (; s + kRedSlices * 3 < a.fresh.n_slots; s += kRedSlices * 4) {   // 8 independent loads in flight, added in slot order
       double v[8];
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        v[2 * u] = base[((size_t)(s + 16 * u) * 2) * cp];
-        v[2 * u + 1] = base[((size_t)(s + 16 * u) * 2 + 1) * cp];
+        v[2 * u] = base[((size_t)(s + kRedSlices * u) * 2) * cp];
+        v[2 * u + 1] = base[((size_t)(s + kRedSlices * u) * 2 + 1) * cp];
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) { x1 += v[2 * u]; x2 += v[2 * u + 1]; }
     }
-    for (; s < a.fresh.n_slots; s += 16) {
+    for (; s < a.fresh.n_slots; s += kRedSlices) {
       x1 += base[((size_t)s * 2) * cp];
       x2 += base[((size_t)s * 2 + 1) * cp];
     }
@@ -757,8 +759,8 @@ __global__ void __launch_bounds__(256) bn_finalize16_kernel(const FinArgs16 a) {
   if (slice != 0 || p >= a.n_out) return;
   double S1 = 0.0, S2 = 0.0;
   if (fresh) {
-#pragma unroll
-    for (int k = 0; k < 16; ++k) { S1 += red[0][k][col]; S2 += red[1][k][col]; }
+#pragma unroll 8
+    for (int k = 0; k < kRedSlices; ++k) { S1 += red[0][k][col]; S2 += red[1][k][col]; }
     a.s1[p] = S1;
     a.s2[p] = S2;
   }
@@ -803,29 +805,29 @@ struct BnParamArgs {
   int main_blocks;
 };
 
-__global__ void __launch_bounds__(256) bn_param_reduce_kernel(const BnParamArgs a) {
-  __shared__ double red[3][16][17];
+__global__ void __launch_bounds__(1024) bn_param_reduce_kernel(const BnParamArgs a) {
+  __shared__ double red[3][kRedSlices][17];
   const int col = threadIdx.x & 15, slice = threadIdx.x >> 4;
   if ((int)blockIdx.x >= a.main_blocks) {
     const int c = ((int)blockIdx.x - a.main_blocks) * 16 + col;
     double x = 0.0;
     if (c < a.bias_C) {
       int s = slice;
-      for (; s + 16 * 7 < a.bias_slots; s += 16 * 8) {
-        double v[8];
+      for (; s + kRedSlices * 3 < a.bias_slots; s += kRedSlices * 4) {
+        double v[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = a.bias_parts[(size_t)(s + 16 * u) * a.bias_C + c];
+        for (int u = 0; u < 4; ++u) v[u] = a.bias_parts[(size_t)(s + kRedSlices * u) * a.bias_C + c];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) x += v[u];
+        for (int u = 0; u < 4; ++u) x += v[u];
       }
-      for (; s < a.bias_slots; s += 16) x += a.bias_parts[(size_t)s * a.bias_C + c];
+      for (; s < a.bias_slots; s += kRedSlices) x += a.bias_parts[(size_t)s * a.bias_C + c];
     }
     red[0][slice][col] = x;
     __syncthreads();
     if (slice == 0 && c < a.bias_C) {
       double t = 0.0;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) t += red[0][k][col];
+#pragma unroll 8
+      for (int k = 0; k < kRedSlices; ++k) t += red[0][k][col];
       a.dbias[c] += (float)t;
     }
     return;
@@ -836,18 +838,18 @@ __global__ void __launch_bounds__(256) bn_param_reduce_kernel(const BnParamArgs 
     const double* base = a.parts + p;
     const size_t cc = (size_t)a.C;
     int s = slice;
-    for (; s + 16 * 3 < a.n_slots; s += 16 * 4) {   // 12 independent loads in flight, added in slot order
+    for (; s + kRedSlices * 3 < a.n_slots; s += kRedSlices * 4) {   // 12 independent loads in flight, added in slot order
       double v[4][3];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) v[u][j] = base[((size_t)(s + 16 * u) * 3 + j) * cc];
+        for (int j = 0; j < 3; ++j) v[u][j] = base[((size_t)(s + kRedSlices * u) * 3 + j) * cc];
 #pragma unroll
       for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int j = 0; j < 3; ++j) x[j] += v[u][j];
     }
-    for (; s < a.n_slots; s += 16) {
+    for (; s < a.n_slots; s += kRedSlices) {
 #pragma unroll
       for (int j = 0; j < 3; ++j) x[j] += base[((size_t)s * 3 + j) * cc];
     }
@@ -859,8 +861,8 @@ __global__ void __launch_bounds__(256) bn_param_reduce_kernel(const BnParamArgs 
   double S[3] = {0.0, 0.0, 0.0};
 #pragma unroll
   for (int j = 0; j < 3; ++j)
-#pragma unroll
-    for (int k = 0; k < 16; ++k) S[j] += red[j][k][col];
+#pragma unroll 8
+    for (int k = 0; k < kRedSlices; ++k) S[j] += red[j][k][col];
   if (a.sums_out) {
 #pragma unroll
     for (int j = 0; j < 3; ++j) a.sums_out[(size_t)j * a.C + p] = S[j];
@@ -941,7 +943,7 @@ struct TWalk16 {
     a.rm = arena + bn.rm; a.rv = arena + bn.rv;
     a.fold = fold;
     pending = Fresh{nullptr, 0, 0, 0, 0};
-    bn_finalize16_kernel<<<ceil_div(n_out, 16), 256, 0, st>>>(a);
+    bn_finalize16_kernel<<<ceil_div(n_out, 16), 1024, 0, st>>>(a);
     TCVN_LAUNCH_CHECK();
     return TCVN_OK;
   }
@@ -957,7 +959,7 @@ struct TWalk16 {
     a.scale = corr_scale; a.count = count; a.corrA = corrA; a.corrB = corrB;
     a.bias_parts = dbl(T.bias_parts); a.bias_slots = bias_slots; a.bias_C = 32; a.dbias = dbias;
     a.main_blocks = ceil_div(C, 16);
-    bn_param_reduce_kernel<<<a.main_blocks + (dbias ? 2 : 0), 256, 0, st>>>(a);
+    bn_param_reduce_kernel<<<a.main_blocks + (dbias ? 2 : 0), 1024, 0, st>>>(a);
     TCVN_LAUNCH_CHECK();
     return TCVN_OK;
   }
