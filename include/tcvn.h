@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TCVN_ABI_VERSION 1
+#define TCVN_ABI_VERSION 2
 #define TCVN_MAX_BLOCKS 8
 #define TCVN_MAX_DECODER_LAYERS 8
 

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert sorted(tl.EXPORTS) == declared
     for name in declared:
         assert hasattr(L, name), name
-    assert L.tcvn_abi_version() == 1
+    assert L.tcvn_abi_version() == 2
 
 
 def test_host_side_size_queries_match_python_inventory():
