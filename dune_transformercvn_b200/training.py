@@ -196,8 +196,6 @@ class TrainEngine:
         # the two pixel-map CNNs are independent until the token assembly: the (small, launch-bound) event CNN runs on
         # a side stream under the (large) prong CNN, forward and backward
         self.overlap_cnns = True
-        self.threaded_issue = True     # issue the two CNN walks from two host threads (see _issue)
-        self._pool = None
         self._side: Optional[torch.cuda.Stream] = None
 
     def workspace(self, kind: str, nbytes: int, dev) -> torch.Tensor:
@@ -214,29 +212,12 @@ class TrainEngine:
         return net.engine.cnn_desc(pix if tag == "prong" else pix + feat)
 
     def _issue(self, dev, fn, what: str, calls) -> None:
-        """Run the C walks of the two pixel-map CNNs.  Each walk is ~400-800 kernel launches issued by ONE ctypes call (the
-        GIL is released for its duration); with a side stream the event-CNN walk is issued from a helper thread while this
-        thread issues the prong-CNN walk, so neither stream waits for the other's launches to be queued (at 16 events the
-        host needed 2 ms per walk to queue the launches, during which the other stream sat idle).  The arithmetic and the
-        per-stream order are unchanged: results are bit-identical to the sequential issue order."""
-        def run(tag, args):
-            with torch.cuda.device(dev):
-                return fn(*args)
-        if len({id(use) for _, use, _, _ in calls}) < 2 or not self.threaded_issue:
-            for tag, _, args, _ in calls:
-                _lib.check(fn(*args), f"{what}({tag})")
-            return
-        if self._pool is None:
-            from concurrent.futures import ThreadPoolExecutor
-            self._pool = ThreadPoolExecutor(max_workers=1, thread_name_prefix="tcvn-issue")
-        (tag_a, _, args_a, _), (tag_b, _, args_b, _) = calls
-        fut = self._pool.submit(run, tag_a, args_a)       # event CNN (side stream) from the helper thread
-        rc_b = fn(*args_b)                                 # prong CNN (caller's stream) from this thread
-        rc_a = fut.result()
-        # the error text is thread-local in the library: report the code of the helper's call, the text of ours
-        if rc_a != 0:
-            raise _lib.TcvnError(f"{what}({tag_a}) failed ({rc_a}) on the helper thread")
-        _lib.check(rc_b, f"{what}({tag_b})")
+        """Run the C walks of the two pixel-map CNNs, each ~400-800 kernel launches issued by ONE ctypes call.
+        Measured (round 2, scripts/gpu_train_host_bound.py): issuing the two walks from two host threads does NOT help -
+        launches into one CUDA context serialise on the driver's lock (4 events: 10.8 ms per step either way, 6.3 us of
+        host time per launch), so they are issued one after the other."""
+        for tag, _, args, _ in calls:
+            _lib.check(fn(*args), f"{what}({tag})")
 
     def _exchange(self) -> Optional[GradientExchange]:
         if self.exchange == "auto":
