@@ -98,10 +98,14 @@ int bn1_bwd_reduce(const void* X, int ldx, const void* D, int ldd, const float* 
                    int ring_hp, int ring_wp, double* parts, int* n_slabs, cudaStream_t stream);
 // train_stem.cu: the stem of the training path, hit-driven and bit-reproducible
 int stem_train_slots(int n_images, int H, int W);
-int stem_train_forward(const float* pixels, int n, int cin, int H, int W, const float* w0, const float* bias, int C, float* z0,
+int stem_train_forward(const float* pixels, int n, int cin, int H, int W, const float* w0, const float* bias, int C, void* z0_bf16,
                        double* stat_parts, int* n_slots, cudaStream_t stream);
 int stem_train_wgrad(const float* pixels, int n, int cin, int H, int W, const void* dz_bf16, int C, float* dw_parts, int* n_slots,
                      cudaStream_t stream);
+// AvgPool2d(3, 2) of act(z0) into block 0 (forward) and its backward, all-bf16 maps, 8 channels per thread (train.cu)
+int stem_pool16_forward(const void* z0_bf16, const float* fold, void* blk_bf16, int n, int C, int H, int W, int Hs, int Ws, int ld,
+                        cudaStream_t stream);
+int stem_pool16_backward(const void* dblk_bf16, int ld, void* dz_bf16, int n, int C, int H, int W, int Hs, int Ws, cudaStream_t stream);
 int wgrad_typed(const void* A, bool a_bf16, int lda, long long m_total, int K, int taps, const int* tap_off, const float* a_scale,
                 const float* a_shift, const float* a_alpha, int a_ring_hp, int a_ring_wp, const void* G, bool g_bf16, int ldg,
                 int g_col0, int N, int g_ring_hp, int g_ring_wp, float* dW, cudaStream_t stream, float* parts = nullptr,

@@ -710,6 +710,64 @@ __global__ void stem_pool_bwd_kernel(const float* __restrict__ dblk, int ld, int
   }
 }
 
+// the same pair on all-bf16 maps (bf16 walk), one thread = one pixel x 8 channels (16-byte loads / stores)
+__global__ void __launch_bounds__(256) stem_pool16_fwd_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ fold, int Hs,
+                                                             int Ws, int C, __nv_bfloat16* __restrict__ blk, int ld, int H, int W,
+                                                             long long total) {
+  const long long idx64 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx64 >= total) return;
+  const unsigned idx = (unsigned)idx64;
+  const unsigned cv = (unsigned)C >> 3;
+  const int c = (int)(idx % cv) * 8;
+  unsigned r = idx / cv;
+  const int x = (int)(r % (unsigned)W); r /= (unsigned)W;
+  const int y = (int)(r % (unsigned)H);
+  const int n = (int)(r / (unsigned)H);
+  float sc[8], sh[8], al[8], s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { sc[i] = fold[c + i]; sh[i] = fold[C + c + i]; al[i] = fold[2 * C + c + i]; s[i] = 0.f; }
+#pragma unroll
+  for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) {
+      float v[8];
+      ld8<__nv_bfloat16>(z + (((size_t)n * Hs + 2 * y + dy) * Ws + 2 * x + dx) * C + c, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += prelu(fmaf(v[i], sc[i], sh[i]), al[i]);
+    }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] /= 9.0f;
+  st8<__nv_bfloat16>(blk + ((size_t)n * (H + 2) * (W + 2) + (size_t)(y + 1) * (W + 2) + x + 1) * ld + c, s);
+}
+
+__global__ void __launch_bounds__(256) stem_pool16_bwd_kernel(const __nv_bfloat16* __restrict__ dblk, int ld, int H, int W, int C,
+                                                             __nv_bfloat16* __restrict__ dA, int Hs, int Ws, long long total) {
+  const long long idx64 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx64 >= total) return;
+  const unsigned idx = (unsigned)idx64;
+  const unsigned cv = (unsigned)C >> 3;
+  const int c = (int)(idx % cv) * 8;
+  unsigned r = idx / cv;
+  const int ox = (int)(r % (unsigned)Ws); r /= (unsigned)Ws;
+  const int oy = (int)(r % (unsigned)Hs);
+  const int n = (int)(r / (unsigned)Hs);
+  const int py_lo = oy >= 2 ? (oy - 1) >> 1 : 0, py_hi = min(H - 1, oy >> 1);
+  const int px_lo = ox >= 2 ? (ox - 1) >> 1 : 0, px_hi = min(W - 1, ox >> 1);
+  float s[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] = 0.f;
+  for (int py = py_lo; py <= py_hi; ++py)
+    for (int px = px_lo; px <= px_hi; ++px) {
+      float v[8];
+      ld8<__nv_bfloat16>(dblk + ((size_t)n * (H + 2) * (W + 2) + (size_t)(py + 1) * (W + 2) + px + 1) * ld + c, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s[i] += v[i];
+    }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s[i] /= 9.0f;
+  st8<__nv_bfloat16>(dA + (((size_t)n * Hs + oy) * Ws + ox) * C + c, s);
+}
+
 // AvgPool2d(2,2) backward: dA[ringed H x W rows, C] = 0.25 * dP[ringed H2 x W2 parent] (0 where the floor cropped)
 template <typename T>
 __global__ void pool2_bwd_kernel(const T* __restrict__ dP, int H2, int W2, int C, T* __restrict__ dA, int H, int W,
@@ -1074,6 +1132,29 @@ int pool_typed(int kind, const void* src, const float* fold, void* dst, bool bf1
 }
 
 // BN1 + PReLU1 backward reductions of a dense layer: parts[slab][3][C] (sum g, sum g xhat, sum dA min(y,0))
+int stem_pool16_forward(const void* z0_bf16, const float* fold, void* blk_bf16, int n, int C, int H, int W, int Hs, int Ws, int ld,
+                        cudaStream_t stream) {
+  if (n <= 0) return TCVN_OK;
+  if (C % 8 || ld % 8) return fail(TCVN_ERR_UNSUPPORTED, "stem_pool16: widths must be multiples of 8");
+  const long long total = (long long)n * H * W * (C / 8);
+  if (total >= (1ll << 31) || (long long)n * Hs * Ws * (C / 8) >= (1ll << 31)) return fail(TCVN_ERR_UNSUPPORTED, "stem_pool16: too many images in one launch (%d)", n);
+  stem_pool16_fwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(z0_bf16), fold, Hs, Ws, C,
+                                                                               static_cast<__nv_bfloat16*>(blk_bf16), ld, H, W, total);
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+int stem_pool16_backward(const void* dblk_bf16, int ld, void* dz_bf16, int n, int C, int H, int W, int Hs, int Ws, cudaStream_t stream) {
+  if (n <= 0) return TCVN_OK;
+  if (C % 8 || ld % 8) return fail(TCVN_ERR_UNSUPPORTED, "stem_pool16: widths must be multiples of 8");
+  const long long total = (long long)n * Hs * Ws * (C / 8);
+  if (total >= (1ll << 31)) return fail(TCVN_ERR_UNSUPPORTED, "stem_pool16: too many images in one launch (%d)", n);
+  stem_pool16_bwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dblk_bf16), ld, H, W, C,
+                                                                               static_cast<__nv_bfloat16*>(dz_bf16), Hs, Ws, total);
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
 int bn1_bwd_reduce(const void* X, int ldx, const void* D, int ldd, const float* fold, int fold_stride, int C, long long m_total,
                    int ring_hp, int ring_wp, double* parts, int* n_slabs, cudaStream_t stream) {
   *n_slabs = 0;

@@ -459,7 +459,7 @@ struct TrainPlan16 {
     const size_t N = (size_t)(n < 1 ? 1 : n);
     const int C0 = d.init_features, mid = P.mid, g = d.growth;
     T->w0 = take((size_t)d.in_channels * 49 * C0 * 4);
-    T->z0 = take(N * P.Hs * P.Ws * C0 * 4);
+    T->z0 = take(N * P.Hs * P.Ws * C0 * 2);
     T->fold0 = take(5 * C0 * 4);
     size_t max_rc = 0, max_rows = 0, max_gt = 0, max_dw = (size_t)d.in_channels * 49 * C0;
     int max_c = C0 > d.out_features ? C0 : d.out_features;
@@ -471,7 +471,7 @@ struct TrainPlan16 {
       T16Block X;
       const size_t rows = N * B.R;
       X.blk = take(rows * B.ctot * 2);
-      X.gblk = take(rows * B.ctot * 4);
+      X.gblk = take(rows * B.ctot * 2);   // gradient of the block's channels as its consumer left it (bf16; only READ by the layers)
       X.sums = take(2 * (size_t)B.ctot * 8);
       X.bstat = take(4 * (size_t)B.ctot * 4);
       if (rows * B.ctot > max_rc) max_rc = rows * B.ctot;
@@ -564,26 +564,25 @@ __device__ __forceinline__ uint4 pack8_bf(const float (&v)[8]) {
 // Gradient of concat channels [col0, col0 + ncols) of a dense block, PULLED from where it was produced.
 // All BN1s of a block normalise the same channels x with the same batch statistics, so the gradient of channel c is
 //     g[m,c] = ginit[m,c] + sum_{j in later layers} sc_j,c * prelu'_j(sc_j,c x + sh_j,c) * dA_j[m,c]  -  corrA[c]  -  xhat[m,c] corrB[c]
-// ginit = what the block's consumer (transition / final norm) left in the fp32 block gradient, dA_j = the bf16 input
+// ginit = what the block's consumer (transition / final norm) left in the bf16 block gradient, dA_j = the bf16 input
 // gradient of layer j's conv1 (kept per layer), corrA / corrB = the accumulated mean corrections of the BN backward
 // (bn_param_reduce_kernel).  Round 1 PUSHED instead: every layer added sc_j g_j into the fp32 block gradient over all
 // its input channels (read 4 + write 4 bytes per element and layer, the most expensive pass of the backward walk).
 //   MODE 0  the 32 output channels of a layer -> Dropout mask (same (seed, site, element) hash as the forward) -> bf16
 //           G2x[m] = [G[m+1] | G[m] | G[m-1] | 0] (the operand of conv2's input / weight gradient kernels) and the
 //           per-CTA partial sums of conv2's bias gradient
-//   MODE 1  the block-input channels, fp32 in place (stem side of block 0)
-//   MODE 2  the block-input channels -> bf16 [rows][pitch] zero-padded (operand of the transition's gradient GEMMs)
+//   MODE 2  the block-input channels -> bf16 [rows][pitch] zero-padded (operand of the transition's gradient GEMMs; for
+//           block 0 the input of the stem's pooling backward)
 // ------------------------------------------------------------------------------------------------------------------
 struct PullSrc { const bf* dA; int ld; const float* fold; int fs; };
 struct PullArgs {
-  const float* ginit; int ldg;
+  const bf* ginit; int ldg;
   const bf* blk; int ldb;
   const float* bstat; int ctot;
   int col0, ncols;
   long long rows; int Hp, Wp;
   int n_src; PullSrc src[kPullMax];
   bf* g2x; float p; unsigned long long seed, site; double* bias_parts;   // MODE 0
-  float* out32; int ldo;                                                  // MODE 1
   bf* out16; int pitch;                                                   // MODE 2
 };
 
@@ -624,9 +623,7 @@ __global__ void __launch_bounds__(256) grad_pull_kernel(const PullArgs a) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = 0.f;
       if (!ring) {
-        const float4 g0 = *reinterpret_cast<const float4*>(a.ginit + m * (long long)a.ldg + a.col0 + c);
-        const float4 g1 = *reinterpret_cast<const float4*>(a.ginit + m * (long long)a.ldg + a.col0 + c + 4);
-        v[0] = g0.x; v[1] = g0.y; v[2] = g0.z; v[3] = g0.w; v[4] = g1.x; v[5] = g1.y; v[6] = g1.z; v[7] = g1.w;
+        ld8_bf(a.ginit + m * (long long)a.ldg + a.col0 + c, v);
         float xv[8];
         ld8_bf(a.blk + m * (long long)a.ldb + a.col0 + c, xv);
         for (int j = 0; j < a.n_src; ++j) {
@@ -663,12 +660,6 @@ __global__ void __launch_bounds__(256) grad_pull_kernel(const PullArgs a) {
         else *reinterpret_cast<uint4*>(g2x + 64 + c) = zv;
         if (m + 1 < a.rows) *reinterpret_cast<uint4*>(g2x + (m + 1) * 128 + 64 + c) = hv;
         else *reinterpret_cast<uint4*>(g2x + m * 128 + c) = zv;
-      } else if (MODE == 1) {
-        if (!ring) {
-          float* o = a.out32 + m * (long long)a.ldo + a.col0 + c;
-          *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
-        }
       } else {
         *reinterpret_cast<uint4*>(a.out16 + m * (long long)a.pitch + c) = pack8_bf(v);
         if (vx == 0)
@@ -1023,11 +1014,11 @@ struct TWalk16 {
     const long long stem_rows = (long long)n * P.Hs * P.Ws;
     int slots = 0;
     // ---- stem: raw conv0 (+ bias) and its batch statistics in one hit-driven pass, then BN0 + PReLU0 + AvgPool(3,2)
-    TCVN_TRY(stem_train_forward(pixels, n, d.in_channels, d.height, d.width, f(T.w0), arena + P.conv0_b, C0, f(T.z0), dbl(T.dparts),
+    TCVN_TRY(stem_train_forward(pixels, n, d.in_channels, d.height, d.width, f(T.w0), arena + P.conv0_b, C0, h(T.z0), dbl(T.dparts),
                                 &slots, st));
     produced(slots, C0, 0, C0);
     TCVN_TRY(finalize(dbl(T.sums_scr), dbl(T.sums_scr) + C0, C0, P.norm0, NOGAP, NOGAP, (double)stem_rows, f(T.fold0)));
-    TCVN_TRY(pool_typed(0, f(T.z0), f(T.fold0), h(T.blocks[0].blk), true, n, C0, B0.H, B0.W, P.Hs, P.Ws, B0.ctot, st));
+    TCVN_TRY(stem_pool16_forward(h(T.z0), f(T.fold0), h(T.blocks[0].blk), n, C0, B0.H, B0.W, P.Hs, P.Ws, B0.ctot, st));
     for (size_t b = 0; b < P.blocks.size(); ++b) {
       const BlockPlan& B = P.blocks[b];
       const T16Block& X = T.blocks[b];
@@ -1095,12 +1086,12 @@ struct TWalk16 {
   }
 
   // gradient of channels [col0, col0 + ncols) of block b, pulled from the layers after `first_src - 1` (see grad_pull_kernel)
-  int pull(int mode, int b, int first_src, int col0, int ncols, long long rows, uint64_t drop_site, int* bias_slots, float* out32,
-           bf* out16, int pitch) {
+  int pull(int mode, int b, int first_src, int col0, int ncols, long long rows, uint64_t drop_site, int* bias_slots, bf* out16,
+           int pitch) {
     const BlockPlan& B = T.P.blocks[b];
     const T16Block& X = T.blocks[b];
     PullArgs a{};
-    a.ginit = f(X.gblk); a.ldg = B.ctot; a.blk = h(X.blk); a.ldb = B.ctot; a.bstat = f(X.bstat); a.ctot = B.ctot;
+    a.ginit = h(X.gblk); a.ldg = B.ctot; a.blk = h(X.blk); a.ldb = B.ctot; a.bstat = f(X.bstat); a.ctot = B.ctot;
     a.col0 = col0; a.ncols = ncols; a.rows = rows; a.Hp = B.Hp; a.Wp = B.Wp;
     a.n_src = 0;
     for (int j = first_src; j < (int)B.layers.size(); ++j) {
@@ -1108,7 +1099,7 @@ struct TWalk16 {
       a.src[a.n_src++] = PullSrc{h(X.layers[j].dA1), B.layers[j].kphys, f(X.layers[j].fold1), B.layers[j].kpad};
     }
     a.g2x = h(T.g2x); a.p = p_drop; a.seed = seed; a.site = drop_site; a.bias_parts = dbl(T.bias_parts);
-    a.out32 = out32; a.ldo = B.ctot; a.out16 = out16; a.pitch = pitch;
+    a.out16 = out16; a.pitch = pitch;
     if (ncols % 8 || ncols > 2048) return fail(TCVN_ERR_UNSUPPORTED, "grad_pull: %d channels", ncols);
     const int tv = ncols / 8, rpi = 256 / tv;
     long long want = ceil_div_ll(rows, (long long)rpi * 4);
@@ -1117,8 +1108,6 @@ struct TWalk16 {
     if (mode == 0) {
       grad_pull_kernel<0><<<grid, 256, smem, st>>>(a);
       if (bias_slots) *bias_slots = grid;
-    } else if (mode == 1) {
-      grad_pull_kernel<1><<<grid, 256, smem, st>>>(a);
     } else {
       grad_pull_kernel<2><<<grid, 256, smem, st>>>(a);
     }
@@ -1143,7 +1132,7 @@ struct TWalk16 {
     TCVN_TRY(gemm32(d_emb, out, n, out, f(T.lwt), last.ctot, nullptr, f(T.dgap), last.ctot));
     TCVN_TRY(pool_typed(3, f(T.dgap), nullptr, h(T.sA), true, n, last.ctot, last.H, last.W, 0, 0, last.ctot, st));
     TCVN_TRY(bn_bwd(h(T.blocks[nb - 1].blk), true, last.ctot, h(T.sA), true, last.ctot, f(T.fold_f), last.ctot, last.ctot,
-                    (double)n * last.H * last.W, (long long)n * last.R, last.Hp, last.Wp, f(T.blocks[nb - 1].gblk), false,
+                    (double)n * last.H * last.W, (long long)n * last.R, last.Hp, last.Wp, h(T.blocks[nb - 1].gblk), true,
                     last.ctot, P.final_norm, last.c0, last.c0p));
     for (int b = nb - 1; b >= 0; --b) {
       const BlockPlan& B = P.blocks[b];
@@ -1151,7 +1140,6 @@ struct TWalk16 {
       const long long rows = (long long)n * B.R;
       const double count = (double)n * B.H * B.W;
       bf* blk = h(X.blk);
-      float* gblk = f(X.gblk);   // what the block's consumer left: the layers only READ it (grad_pull_kernel)
       bf* dmid = h(T.dmid);
       bf* g2x = h(T.g2x);
       float* bstat = f(X.bstat);
@@ -1173,7 +1161,7 @@ struct TWalk16 {
         // feed a train-mode BatchNorm directly, which removes any per-channel constant: their gradient is exactly zero and
         // stays zero here.  conv2's bias passes through Dropout first - mask * b / (1 - p) is not constant - so it has one.)
         int bias_slots = 0;
-        TCVN_TRY(pull(0, b, i + 1, L.kphys, 32, rows, site * 4096 + b * 64 + i, &bias_slots, nullptr, nullptr, 0));
+        TCVN_TRY(pull(0, b, i + 1, L.kphys, 32, rows, site * 4096 + b * 64 + i, &bias_slots, nullptr, 0));
         // conv2 weight gradient: three vertical taps of the activated bottleneck map against G2x
         {
           const int cols[3] = {0, 0, 0}, shifts[3] = {-B.Wp, 0, B.Wp}, valid[3] = {128, 128, 128};
@@ -1184,12 +1172,12 @@ struct TWalk16 {
           TCVN_TRY(umma_wgrad(h(Y.mid_act), rows, mid, mid, 3, cols, shifts, valid, nullptr, nullptr, nullptr, 0, g2x, 128, 128, 0,
                               f(T.parts), garena + L.conv2_w, true, wst, 2));
         }
-        TCVN_TRY(umma_conv2_dgrad(g2x, h(Y.wd), rows, B.Hp, B.Wp, dmid, st));
-        // BN2 + PReLU2 backward: reductions -> (parameter gradients, conv2 bias gradient) -> elementwise half, in place
+        // conv2 input gradient; its epilogue also takes the BN2 + PReLU2 backward reductions from the values it stores
+        // (round 1 / early round 2: a separate column-sum pass over dmid and mid_raw, 512 bytes per row)
         {
           int slabs = 0;
-          TCVN_TRY(colsums_parts(1, h(Y.mid_raw), true, mid, 0, dmid, true, mid, 0, f(Y.fold2), mid, mid, rows, B.Hp, B.Wp,
-                                 dbl(T.dparts), &slabs, st));
+          TCVN_TRY(umma_conv2_dgrad(g2x, h(Y.wd), rows, B.Hp, B.Wp, dmid, st, h(Y.mid_raw), f(Y.fold2), dbl(T.dparts), &slabs));
+          // reduce the slots -> (parameter gradients, conv2 bias gradient), then the elementwise half in place
           TCVN_TRY(param_reduce(slabs, mid, true, L.norm2, NOGAP, NOGAP, nullptr, count, nullptr, nullptr, bias_slots,
                                 garena + L.conv2_b));
           TCVN_TRY(bnact_bwd_apply_typed(dmid, true, mid, 0, h(Y.mid_raw), true, mid, 0, f(Y.fold2), mid, dbl(T.sums_scr), mid, count,
@@ -1228,7 +1216,7 @@ struct TWalk16 {
         const T16Block& Xp = T.blocks[b - 1];
         bf* gt = h(T.gt);
         // the block-input channels leave the block: their final gradient, bf16 and zero-padded, for the transition's GEMMs
-        TCVN_TRY(pull(2, b, 0, 0, B.c0p, rows, 0, nullptr, nullptr, gt, Xp.gt_pitch));
+        TCVN_TRY(pull(2, b, 0, 0, B.c0p, rows, 0, nullptr, gt, Xp.gt_pitch));
         // transition weight gradient dW[k][n] = sum_m pooled[m, k] * Gt[m, n] on the MN-major tensor-core kernel: groups
         // of <= 4 x 128 input channels against 128-column tiles of Gt, scattered into the [ctot][toutp] scratch
         {
@@ -1254,15 +1242,16 @@ struct TWalk16 {
                              nullptr, f(T.zeros), f(T.ones), h(T.sA), Pv.ctot, Pv.ctot, ceil_div(Pv.ctot, 128), B.Hp, B.Wp, st));
         TCVN_TRY(pool_typed(2, h(T.sA), nullptr, h(T.sB), true, n, Pv.ctot, Pv.H, Pv.W, B.H, B.W, Pv.ctot, st));
         TCVN_TRY(bn_bwd(h(Xp.blk), true, Pv.ctot, h(T.sB), true, Pv.ctot, f(Xp.fold_t), Pv.ctot, Pv.ctot, (double)n * Pv.H * Pv.W,
-                        (long long)n * Pv.R, Pv.Hp, Pv.Wp, f(Xp.gblk), false, Pv.ctot, Pv.tnorm, Pv.c0, Pv.c0p));
+                        (long long)n * Pv.R, Pv.Hp, Pv.Wp, h(Xp.gblk), true, Pv.ctot, Pv.tnorm, Pv.c0, Pv.c0p));
       } else {
         const long long stem_rows = (long long)n * P.Hs * P.Ws;
-        // the stem side: final fp32 gradient of the 64 pooled stem channels in place, then AvgPool(3,2) backward into the
-        // bf16 gradient of the 64 x 200 x 140 stem map (it feeds only conv0's weight gradient and BN0 / PReLU0)
-        TCVN_TRY(pull(1, b, 0, 0, B.c0p, rows, 0, nullptr, gblk, nullptr, 0));
+        // the stem side: final gradient of the 64 pooled stem channels (bf16), AvgPool(3,2) backward into the gradient of the
+        // 64 x 200 x 140 stem map (it feeds only conv0's weight gradient and BN0 / PReLU0), BN0 + PReLU0 backward in place
+        bf* g0 = h(T.sA);
+        TCVN_TRY(pull(2, b, 0, 0, B.c0p, rows, 0, nullptr, g0, B.c0p));
         bf* dz0 = h(T.dz0);
-        TCVN_TRY(pool_typed(1, gblk, nullptr, dz0, true, n, C0, B.H, B.W, P.Hs, P.Ws, B.ctot, st));
-        TCVN_TRY(bn_bwd(f(T.z0), false, C0, dz0, true, C0, f(T.fold0), C0, C0, (double)stem_rows, stem_rows, 0, 0, dz0, true, C0,
+        TCVN_TRY(stem_pool16_backward(g0, B.c0p, dz0, n, C0, B.H, B.W, P.Hs, P.Ws, st));
+        TCVN_TRY(bn_bwd(h(T.z0), true, C0, dz0, true, C0, f(T.fold0), C0, C0, (double)stem_rows, stem_rows, 0, 0, dz0, true, C0,
                         P.norm0, NOGAP, NOGAP));
         // conv0 weight gradient, hit-driven and bit-reproducible (train_stem.cu): per-CTA partial sums, added in order
         const int k0 = d.in_channels * 49;

@@ -5,7 +5,7 @@
 // land in fixed slots that a later kernel adds in a fixed order.  (Round 1 scattered hits with float atomics: the one-ulp
 // run-to-run differences of z0 were amplified by the 67 train-mode BatchNorms to 20 % of the gradient.)
 //
-//   MODE 0  z0[n, cy, cx, :] = b + conv7x7s2p3(pixels)   and  parts[cta][2][C0] = per-CTA (sum z, sum z^2) in double
+//   MODE 0  z0[n, cy, cx, :] = bf16(b + conv7x7s2p3(pixels))   and  parts[cta][2][C0] = per-CTA (sum z, sum z^2) in double
 //   MODE 1  parts[cta][cin*49][C0] = sum over the CTA's tiles of  x[2cy-3+ky, 2cx-3+kx, c] * dz[n, cy, cx, :]
 #include "kernels.h"
 #include "stem.cuh"
@@ -20,7 +20,7 @@ struct StemTrainArgs {
   const float* pixels; int n_images, cin, H, W, Hs, Ws;
   const float* w0;        // [cin*49][C0]           (MODE 0)
   const float* bias;      // [C0]                   (MODE 0)
-  float* z0;              // [n, Hs, Ws, C0] fp32   (MODE 0)
+  __nv_bfloat16* z0;      // [n, Hs, Ws, C0] bf16   (MODE 0)
   double* stat_parts;     // [grid][2][C0]          (MODE 0)
   const __nv_bfloat16* dz; // [n, Hs, Ws, C0] bf16  (MODE 1)
   float* dw_parts;        // [grid][cin*49][C0]     (MODE 1)
@@ -154,8 +154,10 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_train_kernel(const StemT
         const int cyl = p >> 4, cxl = p & 15;
         const int cy = cy0 + cyl, cx = cx0 + cxl;
         if (cy < a.Hs && cx < a.Ws) {
-          const float z = acc[(cyl * kStemTC + cxl) * C0 + ch] + bias;
-          a.z0[(((size_t)n * a.Hs + cy) * a.Ws + cx) * C0 + ch] = z;
+          // stored (and counted in the statistics) as bf16: three more passes read this map (pooling, BN0 backward x 2)
+          const __nv_bfloat16 zb = __float2bfloat16_rn(acc[(cyl * kStemTC + cxl) * C0 + ch] + bias);
+          a.z0[(((size_t)n * a.Hs + cy) * a.Ws + cx) * C0 + ch] = zb;
+          const float z = __bfloat162float(zb);
           st1 += (double)z;
           st2 += (double)z * (double)z;
         }
@@ -220,14 +222,14 @@ static int stem_train_check(int cin, int C) {
   return TCVN_OK;
 }
 
-// z0 = bias + conv0(pixels), stat_parts[slots][2][C] = per-CTA (sum, sum^2) of z0 by channel
-int stem_train_forward(const float* pixels, int n, int cin, int H, int W, const float* w0, const float* bias, int C, float* z0,
+// z0 (bf16) = bias + conv0(pixels), stat_parts[slots][2][C] = per-CTA (sum, sum^2) of the stored z0 by channel
+int stem_train_forward(const float* pixels, int n, int cin, int H, int W, const float* w0, const float* bias, int C, void* z0_bf16,
                        double* stat_parts, int* n_slots, cudaStream_t stream) {
   TCVN_TRY(stem_train_check(cin, C));
   StemTrainArgs a{};
   a.pixels = pixels; a.n_images = n; a.cin = cin; a.H = H; a.W = W;
   a.Hs = (H + 6 - 7) / 2 + 1; a.Ws = (W + 6 - 7) / 2 + 1;
-  a.w0 = w0; a.bias = bias; a.z0 = z0; a.stat_parts = stat_parts;
+  a.w0 = w0; a.bias = bias; a.z0 = static_cast<__nv_bfloat16*>(z0_bf16); a.stat_parts = stat_parts;
   const int grid = stem_train_slots(n, H, W);
   *n_slots = grid;
   const size_t smem = ((size_t)cin * 49 * 64 + (size_t)kStemTC * kStemTC * 64) * 4 + (size_t)kStemIn * kStemIn * 16;

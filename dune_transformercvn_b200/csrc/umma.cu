@@ -524,40 +524,6 @@ __device__ __forceinline__ bool drop_keep_c2(unsigned long long seed, unsigned l
   return (r >> 8) * (1.0f / 16777216.0f) >= p;
 }
 
-// lane j ends with the sum over the warp of v[j] (butterfly: 31 shuffles instead of 160)
-__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const bool up = lane & 16;
-    const float send = up ? v[i] : v[i + 16], keep = up ? v[i + 16] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const bool up = lane & 8;
-    const float send = up ? v[i] : v[i + 8], keep = up ? v[i + 8] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const bool up = lane & 4;
-    const float send = up ? v[i] : v[i + 4], keep = up ? v[i + 4] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const bool up = lane & 2;
-    const float send = up ? v[i] : v[i + 2], keep = up ? v[i + 2] : v[i];
-    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  {
-    const bool up = lane & 1;
-    const float send = up ? v[0] : v[1], keep = up ? v[1] : v[0];
-    v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-  }
-  return v[0];
-}
-
 __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                    const __grid_constant__ CUtensorMap tmW,
                                                                    const Conv2Params p) {

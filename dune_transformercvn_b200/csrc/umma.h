@@ -37,5 +37,8 @@ int umma_wgrad(const void* A, long long rows, int a_cols, int a_pitch, int n_ite
                int map_mode = 0, int map_n_log = 0, int map_k_log = 0, int map_c0 = 0, int map_c0p = 0);
 // map_mode != 0: dw is the reference-layout gradient tensor and the per-CTA partial sums are ADDED to it re-laid out in the
 // same launch (1: 1x1 convolution dst[n][k] over logical channels; 2: 3x3 convolution dst[n][k][dy][dx]); see umma_train.cu
-int umma_conv2_dgrad(const void* g2x, const void* wd, long long rows, int Hp, int Wp, void* out, cudaStream_t st);
+// red_x != null: the BN2 + PReLU2 backward reductions are fused into the epilogue (see DgradParams): red_parts[slots][3][128]
+int umma_conv2_dgrad(const void* g2x, const void* wd, long long rows, int Hp, int Wp, void* out, cudaStream_t st,
+                     const void* red_x = nullptr, const float* red_fold = nullptr, double* red_parts = nullptr,
+                     int* red_slots = nullptr);
 }  // namespace tcvn

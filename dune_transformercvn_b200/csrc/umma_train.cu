@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) umma_wgrad_kernel(const __grid_
 // ------------------------------------------------------------------------------------------------
 // conv2 input gradient.  One stage = one 64-column half of the haloed G2x tile.
 // ------------------------------------------------------------------------------------------------
-constexpr int kDgThreads = 192;   // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int kDgThreads = 320;   // warp 0 TMA, warp 1 MMA, warps 2-5 / 6-9 two epilogue groups (one per TMEM accumulator)
 constexpr int kDgStages = 3;
 constexpr int kDgBoxRows = 32;
 constexpr int kDgWSlab = 128 * 128;            // [128 out channels x 64 k] bf16
@@ -215,6 +215,12 @@ struct DgradParams {
   int Hp, Wp, halo_rows, nbox;
   bf16* out; int ldo;
   int num_tiles;
+  // BatchNorm2 + PReLU2 backward reductions fused into the epilogue (training walk): with x = the raw conv1 output
+  // (bf16 [rows][128]) and fold = [scale | shift | alpha | mean | rstd] x 128 of BN2, every CTA stores
+  //   red_parts[cta][3][128] = (sum g, sum g xhat, sum d min(y, 0)),  y = scale x + shift, g = d (y >= 0 ? 1 : alpha),
+  // over its rows, d = the bf16 value this kernel stores.  The consumer adds the CTAs in a fixed order (no atomics).
+  // Replaces a separate pass over d and x (512 bytes per row).
+  const bf16* red_x; const float* red_fold; double* red_parts;
 };
 
 __global__ void __launch_bounds__(kDgThreads, 1) umma_conv2_dgrad_kernel(const __grid_constant__ CUtensorMap tmG,
@@ -232,8 +238,16 @@ __global__ void __launch_bounds__(kDgThreads, 1) umma_conv2_dgrad_kernel(const _
   uint64_t* tempty = tfull + 2;
   uint64_t* wfull = tempty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+  __shared__ float4 s_red[128];     // fused BN2 backward reductions: (scale, shift, rstd, -mean * rstd) per column
+  __shared__ float s_red_al[128];   // ... and the PReLU slope
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (p.red_parts != nullptr && threadIdx.x < 128) {
+    const int c = threadIdx.x;
+    const float sc = p.red_fold[c], sh = p.red_fold[128 + c], mu = p.red_fold[3 * 128 + c], rs = p.red_fold[4 * 128 + c];
+    s_red[c] = make_float4(sc, sh, rs, -mu * rs);
+    s_red_al[c] = p.red_fold[2 * 128 + c];
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < kDgStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 128); }
@@ -299,11 +313,19 @@ __global__ void __launch_bounds__(kDgThreads, 1) umma_conv2_dgrad_kernel(const _
       }
     }
   } else {
+    // two epilogue groups of four warps, group == the TMEM accumulator it drains (tiles alternate)
+    const int grp = (warp - 2) >> 2;
     const int g = warp & 3;
     const int row = g * 32 + lane;
     const int R = p.Hp * p.Wp;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    const int acc = grp; uint32_t acc_phase = 0;
+    const bool red = p.red_parts != nullptr;
+    float racc[4][3];   // lane j: column c * 32 + j of the three reductions over this warp's rows of every tile
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { racc[c][0] = 0.f; racc[c][1] = 0.f; racc[c][2] = 0.f; }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+      if ((it & 1) != grp) continue;
       const long long m = (long long)tile * 128 + row;
       bool ring = false;
       {
@@ -311,6 +333,7 @@ __global__ void __launch_bounds__(kDgThreads, 1) umma_conv2_dgrad_kernel(const _
         const int y = rr / p.Wp, x = rr - y * p.Wp;
         ring = y == 0 || y == p.Hp - 1 || x == 0 || x == p.Wp - 1;
       }
+      const bool live = m < p.m_total && !ring;
       if (lane == 0) ptx::mbar_wait(&tfull[acc], acc_phase);
       __syncwarp();
       ptx::tc_fence_after();
@@ -319,22 +342,66 @@ __global__ void __launch_bounds__(kDgThreads, 1) umma_conv2_dgrad_kernel(const _
       for (int c = 0; c < 4; ++c) {
         uint32_t r[32];
         ptx::tmem_ld_32x32(t_addr + c * 32, r);
-        ptx::tmem_ld_wait();
-        if (m < p.m_total) {
-          uint32_t w[16];
+        uint4 xr[4];
+        if (red && live) {
+          const uint4* xp = reinterpret_cast<const uint4*>(p.red_x + m * 128 + c * 32);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-            w[j] = ring ? 0u : *reinterpret_cast<const uint32_t*>(&h2);
-          }
+          for (int j = 0; j < 4; ++j) xr[j] = __ldg(xp + j);
+        }
+        ptx::tmem_ld_wait();
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const __nv_bfloat162 h2 = __floats2bfloat162_rn(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+          w[j] = ring ? 0u : *reinterpret_cast<const uint32_t*>(&h2);
+        }
+        if (m < p.m_total) {
           uint4* dst = reinterpret_cast<uint4*>(p.out + m * p.ldo + c * 32);
 #pragma unroll
           for (int j = 0; j < 4; ++j) dst[j] = make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
         }
+        if (red) {   // warp-uniform
+          float q0[32], q1[32], q2[32];
+          const uint32_t xw[16] = {xr[0].x, xr[0].y, xr[0].z, xr[0].w, xr[1].x, xr[1].y, xr[1].z, xr[1].w,
+                                   xr[2].x, xr[2].y, xr[2].z, xr[2].w, xr[3].x, xr[3].y, xr[3].z, xr[3].w};
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float4 k = s_red[c * 32 + j];              // (scale, shift, rstd, -mean * rstd): warp-wide broadcast
+            const float al = s_red_al[c * 32 + j];
+            const uint32_t dw = w[j >> 1], xx = xw[j >> 1];
+            const float d = live ? ((j & 1) ? bfh(dw) : bfl(dw)) : 0.f;
+            const float x = live ? ((j & 1) ? bfh(xx) : bfl(xx)) : 0.f;
+            const float y = fmaf(x, k.x, k.y);
+            const float gg = y >= 0.f ? d : d * al;
+            q0[j] = gg;
+            q1[j] = gg * fmaf(x, k.z, k.w);
+            q2[j] = d * fminf(y, 0.f);
+          }
+          racc[c][0] += warp_transpose_sum(q0, lane);
+          racc[c][1] += warp_transpose_sum(q1, lane);
+          racc[c][2] += warp_transpose_sum(q2, lane);
+        }
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(&tempty[acc]);
-      if ((acc ^= 1) == 0) acc_phase ^= 1;
+      acc_phase ^= 1;
+    }
+    if (red) {
+      // the eight epilogue warps' partial sums are added in a fixed order through the (now idle) pipeline stages
+      float* sred = reinterpret_cast<float*>(sA);   // [8 warps][3][128]
+      const int wi = grp * 4 + g;
+      ptx::named_bar_sync(1, 256);                  // every MMA of this CTA has completed: the stages are free
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int q = 0; q < 3; ++q) sred[(wi * 3 + q) * 128 + c * 32 + lane] = racc[c][q];
+      ptx::named_bar_sync(1, 256);
+      for (int o = threadIdx.x - 64; o < 3 * 128; o += 256) {
+        double t = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += (double)sred[k * 3 * 128 + o];
+        p.red_parts[(size_t)blockIdx.x * 3 * 128 + o] = t;
+      }
     }
   }
   ptx::tc_fence_before();
@@ -491,7 +558,9 @@ int umma_wgrad(const void* A, long long rows, int a_cols, int a_pitch, int n_ite
 // out[p][c] (bf16 [rows, 128], ring rows zero) = sum_dy sum_k G2x[p + (1 - dy) * Wp][k] * Wd[dy][c][k]
 //   G2x  bf16 [rows, 128]: columns dx*32 + n = G[p + 1 - dx][n], columns 96.. zero
 //   Wd   bf16 [3][128][128]: Wd[dy][c][dx*32 + n] = w2[n][c][dy][dx], columns 96.. zero
-int umma_conv2_dgrad(const void* g2x, const void* wd, long long rows, int Hp, int Wp, void* out, cudaStream_t st) {
+int umma_conv2_dgrad(const void* g2x, const void* wd, long long rows, int Hp, int Wp, void* out, cudaStream_t st,
+                     const void* red_x, const float* red_fold, double* red_parts, int* red_slots) {
+  if (red_slots) *red_slots = 0;
   if (rows <= 0) return TCVN_OK;
   if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one launch");
   DgradParams p{};
@@ -502,6 +571,7 @@ int umma_conv2_dgrad(const void* g2x, const void* wd, long long rows, int Hp, in
   if (p.halo_rows > halo_rows_max)
     return fail(TCVN_ERR_UNSUPPORTED, "feature map width %d needs a %d-row halo tile (max %d)", Wp - 2, p.halo_rows, halo_rows_max);
   p.out = static_cast<bf16*>(out); p.ldo = 128;
+  p.red_x = static_cast<const bf16*>(red_x); p.red_fold = red_fold; p.red_parts = red_x ? red_parts : nullptr;
   p.num_tiles = (int)ceil_div_ll(rows, 128);
   bool& attr_done = device_flag(4);
   const size_t smem_max = 1024 + kDgWBytes + (size_t)kDgStages * halo_rows_max * 128 + 256;
@@ -514,6 +584,7 @@ int umma_conv2_dgrad(const void* g2x, const void* wd, long long rows, int Hp, in
   TCVN_TRY(make_map(wd, 3 * 128, 128, 128, 64, 128, &tmW));
   const size_t smem = 1024 + kDgWBytes + (size_t)kDgStages * p.halo_rows * 128 + 256;
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
+  if (red_slots) *red_slots = p.red_parts ? grid : 0;
   umma_conv2_dgrad_kernel<<<grid, kDgThreads, smem, st>>>(tmG, tmW, p);
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
@@ -542,5 +613,5 @@ extern "C" int tcvn_t_umma_wgrad(const void* a_bf16, int64_t rows, int a_cols, i
 extern "C" int tcvn_t_umma_conv2_dgrad(const void* g2x_bf16, const void* wd_bf16, int64_t rows, int ring_hp, int ring_wp,
                                        void* out_bf16, tcvn_stream_t stream) {
   TCVN_CHECK_ARG(g2x_bf16 && wd_bf16 && out_bf16 && ring_hp >= 3 && ring_wp >= 3, "t_umma_conv2_dgrad: bad arguments");
-  return tcvn::umma_conv2_dgrad(g2x_bf16, wd_bf16, rows, ring_hp, ring_wp, out_bf16, stream);
+  return tcvn::umma_conv2_dgrad(g2x_bf16, wd_bf16, rows, ring_hp, ring_wp, out_bf16, stream, nullptr, nullptr, nullptr, nullptr);
 }
