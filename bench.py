@@ -310,13 +310,27 @@ def run_train_leg(args, dev, rank, world, timed, train_events, with_cpu, fixed_p
     res_t = (ev_t.to(dev), pr_t.to(dev))
     loss_host = torch.empty(1).pin_memory()
 
-    def step(b, t):
+    def eager_step(b, t):
         opt.zero_grad()
         ev, pr = net.forward_sparse(b)
         loss, _ = tloss.training_loss(ev, pr, t[0], t[1], opts)   # one kernel: focal loss mix + d loss / d logits
         loss.backward()
         opt.step()
         return loss
+
+    # the whole step as ONE CUDA graph per batch shape (training.GraphedTrainStep); the synthetic batch has a fixed shape
+    mode = "kernel by kernel"
+    step = eager_step
+    if not args.no_train_graph:
+        try:
+            graphed = training.GraphedTrainStep(net, opt, opts)
+            graphed(resident, res_t[0], res_t[1])
+            torch.cuda.synchronize()
+            step = lambda b, t: graphed(b, t[0], t[1])   # noqa: E731
+            mode = "CUDA graph replay per batch shape"
+        except Exception as e:   # capture not possible here (e.g. a collective that cannot be captured): launch eagerly
+            mode = f"kernel by kernel (graph capture failed: {type(e).__name__}: {str(e)[:120]})"
+            step = eager_step
 
     def step_e2e():
         b = host.to(dev, non_blocking=True)
@@ -328,6 +342,8 @@ def run_train_leg(args, dev, rank, world, timed, train_events, with_cpu, fixed_p
     l0 = tl.load().tcvn_launch_count()
     ms = timed(lambda: step(resident, res_t), args.train_steps)
     launches = tl.load().tcvn_launch_count() - l0
+    if launches == 0 and step is not eager_step:     # graph replay: the library's host-side launch counter does not tick
+        launches = graphed.launches_per_replay * args.train_steps
     step_e2e()
     ms_e2e = timed(step_e2e, args.train_steps)
     loss_val = float(loss_host[0])
@@ -381,7 +397,7 @@ def run_train_leg(args, dev, rank, world, timed, train_events, with_cpu, fixed_p
            "allreduce_bytes_per_step": 0 if ex is None else ex.bytes // max(1, (max(args.warmup, 3) + 2 * args.train_steps + 1)),
            "gpu_launches": launches, "images_per_s": world * images * args.train_steps / (ms / 1e3),
            "train_gflop_per_image": 14.39, "whole_net_tflops": images * 14.39e9 * args.train_steps / (ms / 1e3) / 1e12,
-           "final_loss": loss_val, "data_parallel_check": dp}
+           "final_loss": loss_val, "data_parallel_check": dp, "launch_mode": mode}
     if rank == 0 and world == 1 and with_cpu and not args.no_cpu_baseline:
         out["cpu_baseline"] = time_cpu_train()
     del net, opt
@@ -695,6 +711,8 @@ def main():
     ap.add_argument("--no-sdxl", action="store_true", help="skip the BASELINE configs[3] leg (--sdxl CNN variant)")
     ap.add_argument("--sdxl-events", type=int, default=256)
     ap.add_argument("--no-config5", action="store_true", help="skip the BASELINE configs[4] leg (16 events x 20 prongs)")
+    ap.add_argument("--no-train-graph", action="store_true", help="training: launch the step kernel by kernel instead of replaying "
+                    "its CUDA graph")
     ap.add_argument("--no-graph", action="store_true", help="inference: launch the step kernel by kernel instead of replaying "
                     "its CUDA graph")
     ap.add_argument("--train-precision", default="bf16", choices=["fp32", "bf16"])

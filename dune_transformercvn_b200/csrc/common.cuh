@@ -25,6 +25,12 @@ int fail(int code, const char* fmt, ...);
       return ::tcvn::fail(TCVN_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
   } while (0)
 
+// device pointer whose value every seeded kernel launched from this host thread adds to its seed (tcvn_set_seed_offset)
+const unsigned long long* seed_offset_ptr();
+__device__ __forceinline__ unsigned long long seed_with_offset(unsigned long long seed, const unsigned long long* off) {
+  return off ? seed + __ldg(off) : seed;
+}
+
 // every kernel launch of the library goes through this: counts launches for tcvn_launch_count()
 void count_launch();
 #define TCVN_LAUNCH_CHECK()        \

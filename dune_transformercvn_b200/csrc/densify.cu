@@ -35,7 +35,9 @@ template <typename V>
 __global__ void __launch_bounds__(256) densify_nchw_kernel(const int32_t* __restrict__ coords, const V* __restrict__ values,
                                                            int64_t nnz, int channels, int height, int width,
                                                            int rows_per_band, float divisor, float noise_std,
-                                                           unsigned long long seed, float* __restrict__ out) {
+                                                           unsigned long long seed0, const unsigned long long* seed_off,
+                                                           float* __restrict__ out) {
+  const unsigned long long seed = seed_with_offset(seed0, seed_off);
   const int image = blockIdx.y;
   const int y0 = blockIdx.x * rows_per_band;
   const int y1 = min(height, y0 + rows_per_band);
@@ -102,10 +104,10 @@ extern "C" int tcvn_densify_noise(const int32_t* coords, const void* values, tcv
   dim3 grid(bands, n_images);
   if (value_dtype == TCVN_VAL_F32)
     densify_nchw_kernel<float><<<grid, 256, 0, stream>>>(coords, static_cast<const float*>(values), nnz, channels,
-                                                         height, width, rows, divisor, noise_std, seed, out);
+                                                         height, width, rows, divisor, noise_std, seed, seed_offset_ptr(), out);
   else if (value_dtype == TCVN_VAL_U8)
     densify_nchw_kernel<uint8_t><<<grid, 256, 0, stream>>>(coords, static_cast<const uint8_t*>(values), nnz, channels,
-                                                           height, width, rows, divisor, noise_std, seed, out);
+                                                           height, width, rows, divisor, noise_std, seed, seed_offset_ptr(), out);
   else
     return fail(TCVN_ERR_ARG, "densify: unknown value dtype %d", (int)value_dtype);
   TCVN_LAUNCH_CHECK();

@@ -817,8 +817,9 @@ __device__ __forceinline__ uint32_t mix32(uint64_t z) {  // splitmix64 finaliser
 }
 
 template <typename T>
-__global__ void dropout_kernel(T* X, int ld, int col0, int C, long long m_total, unsigned long long seed,
-                               unsigned long long stream_id, float p) {
+__global__ void dropout_kernel(T* X, int ld, int col0, int C, long long m_total, unsigned long long seed0,
+                               unsigned long long stream_id, float p, const unsigned long long* seed_off) {
+  const unsigned long long seed = seed_with_offset(seed0, seed_off);
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= m_total * C) return;
   const int c = (int)(idx % C);
@@ -1184,8 +1185,8 @@ int dropout_typed(void* X, bool bf16, int ld, int col0, int C, long long m_total
                   cudaStream_t stream) {
   if (p == 0.f || m_total <= 0) return TCVN_OK;
   const unsigned grid = (unsigned)ceil_div_ll(m_total * C, 256);
-  if (bf16) dropout_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<__nv_bfloat16*>(X), ld, col0, C, m_total, seed, stream_id, p);
-  else dropout_kernel<float><<<grid, 256, 0, stream>>>(static_cast<float*>(X), ld, col0, C, m_total, seed, stream_id, p);
+  if (bf16) dropout_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<__nv_bfloat16*>(X), ld, col0, C, m_total, seed, stream_id, p, seed_offset_ptr());
+  else dropout_kernel<float><<<grid, 256, 0, stream>>>(static_cast<float*>(X), ld, col0, C, m_total, seed, stream_id, p, seed_offset_ptr());
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
 }
@@ -1391,10 +1392,25 @@ struct AdamArgs {
   const double* gnorm_parts; int n_parts;   // stage-1 partial sums of the squared gradient norm (nullptr: no clipping)
   float max_norm, grad_mul;
   double* gnorm_out;              // optional: the total norm squared, written by block 0
+  // device-resident overrides (a captured CUDA graph of the step bakes the by-value arguments in):
+  const long long* step_dev;      // optimizer step count (>= 1): bias corrections are then computed on the device
+  const float* lr_dev;            // [n_groups] learning rates (the LR scheduler's per-step values)
 };
 
 // every parameter group in ONE pass over the arenas; each block first adds the norm partials in the same fixed order
 __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamArgs a) {
+  __shared__ AdamGroup sgrp[kMaxOptGroups];
+  if (threadIdx.x < a.n_groups) {
+    AdamGroup h = a.grp[threadIdx.x];
+    if (a.lr_dev) h.lr = a.lr_dev[threadIdx.x];
+    if (a.step_dev) {
+      const double st = (double)*a.step_dev;
+      h.bc1 = (float)(1.0 - pow((double)h.beta1, st));
+      h.bc2_sqrt = (float)sqrt(1.0 - pow((double)h.beta2, st));
+    }
+    sgrp[threadIdx.x] = h;
+  }
+  __syncthreads();
   float clip = a.grad_mul;
   if (a.gnorm_parts != nullptr && a.max_norm > 0.f) {
     __shared__ double red[256];
@@ -1415,7 +1431,7 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamArgs a) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n; i += (long long)gridDim.x * blockDim.x) {
     const int gi = a.select != nullptr ? (int)a.select[i] : 1;
     if (gi == 0 || gi > a.n_groups) continue;
-    const AdamGroup& h = a.grp[gi - 1];
+    const AdamGroup& h = sgrp[gi - 1];
     const float grad = a.g[i] * clip;
     float w = a.p[i] * (1.f - h.lr * h.weight_decay);
     const float mi = h.beta1 * a.m[i] + (1.f - h.beta1) * grad;
@@ -1438,7 +1454,8 @@ extern "C" size_t tcvn_adamw_workspace_bytes(void) { return (size_t)(tcvn::kSums
 extern "C" int tcvn_adamw_fused(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n,
                                 const uint8_t* select, int n_groups, const double* lr, const double* beta1, const double* beta2,
                                 const double* eps, const double* weight_decay, const int64_t* step, float max_norm,
-                                float grad_mul, void* workspace, size_t workspace_bytes, tcvn_stream_t stream) {
+                                float grad_mul, void* workspace, size_t workspace_bytes, const int64_t* step_dev,
+                                const float* lr_dev, tcvn_stream_t stream) {
   TCVN_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && n >= 0 && lr && beta1 && beta2 && eps && weight_decay && step,
                  "adamw_fused: null pointer");
   TCVN_CHECK_ARG(n_groups >= 1 && n_groups <= tcvn::kMaxOptGroups, "adamw_fused: 1..%d parameter groups (got %d)",
@@ -1456,6 +1473,7 @@ extern "C" int tcvn_adamw_fused(float* params, const float* grads, float* exp_av
     a.grp[k].bc2_sqrt = (float)sqrt(1.0 - pow(beta2[k], (double)step[k]));
   }
   a.max_norm = max_norm; a.grad_mul = grad_mul;
+  a.step_dev = reinterpret_cast<const long long*>(step_dev); a.lr_dev = lr_dev;
   if (max_norm > 0.f) {
     TCVN_CHECK_ARG(workspace && workspace_bytes >= tcvn_adamw_workspace_bytes(), "adamw_fused: workspace too small for the norm");
     double* parts = static_cast<double*>(workspace);

@@ -582,7 +582,7 @@ struct PullArgs {
   int col0, ncols;
   long long rows; int Hp, Wp;
   int n_src; PullSrc src[kPullMax];
-  bf* g2x; float p; unsigned long long seed, site; double* bias_parts;   // MODE 0
+  bf* g2x; float p; unsigned long long seed, site; const unsigned long long* seed_off; double* bias_parts;   // MODE 0
   bf* out16; int pitch;                                                   // MODE 2
 };
 
@@ -615,6 +615,7 @@ __global__ void __launch_bounds__(256) grad_pull_kernel(const PullArgs a) {
     }
     const unsigned R = (unsigned)(a.Hp * a.Wp);
     const float inv_keep = 1.f / (1.f - a.p);
+    const unsigned long long seed = seed_with_offset(a.seed, a.seed_off);
     for (long long m = (long long)blockIdx.x * rpi + ry; m < a.rows; m += (long long)gridDim.x * rpi) {
       const unsigned rr = (unsigned)m % R;
       const unsigned y = rr / (unsigned)a.Wp, x_ = rr - y * (unsigned)a.Wp;
@@ -645,7 +646,7 @@ __global__ void __launch_bounds__(256) grad_pull_kernel(const PullArgs a) {
           if (a.p > 0.f) {
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              v[i] = drop_keep16(a.seed, a.site, (unsigned long long)m * 32 + c + i, a.p) ? v[i] * inv_keep : 0.f;
+              v[i] = drop_keep16(seed, a.site, (unsigned long long)m * 32 + c + i, a.p) ? v[i] * inv_keep : 0.f;
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) bsum[i] += v[i];
@@ -1098,7 +1099,7 @@ struct TWalk16 {
       if (a.n_src >= kPullMax) return fail(TCVN_ERR_UNSUPPORTED, "dense block with more than %d layers", kPullMax + 1);
       a.src[a.n_src++] = PullSrc{h(X.layers[j].dA1), B.layers[j].kphys, f(X.layers[j].fold1), B.layers[j].kpad};
     }
-    a.g2x = h(T.g2x); a.p = p_drop; a.seed = seed; a.site = drop_site; a.bias_parts = dbl(T.bias_parts);
+    a.g2x = h(T.g2x); a.p = p_drop; a.seed = seed; a.site = drop_site; a.seed_off = seed_offset_ptr(); a.bias_parts = dbl(T.bias_parts);
     a.out16 = out16; a.pitch = pitch;
     if (ncols % 8 || ncols > 2048) return fail(TCVN_ERR_UNSUPPORTED, "grad_pull: %d channels", ncols);
     const int tv = ncols / 8, rpi = 256 / tv;

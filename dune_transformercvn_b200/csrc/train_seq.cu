@@ -120,8 +120,9 @@ __device__ __forceinline__ bool drop_keep(unsigned long long seed, unsigned long
 // multi-head attention over one event and one head per CTA; S <= 32 tokens, one thread per query.
 // qkv[R][3D]; P[b][h][S][S] = softmax probabilities (saved BEFORE dropout; the mask is re-derived from the seed); ctx[R][D]
 __global__ void attn_fwd_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ mask, int S, int heads, int D,
-                                float* __restrict__ P, float* __restrict__ ctx, float p_drop, unsigned long long seed,
-                                unsigned long long stream_id) {
+                                float* __restrict__ P, float* __restrict__ ctx, float p_drop, unsigned long long seed0,
+                                unsigned long long stream_id, const unsigned long long* seed_off) {
+  const unsigned long long seed = seed_with_offset(seed0, seed_off);
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int s = threadIdx.x;
   if (s >= S) return;
@@ -168,8 +169,10 @@ __global__ void attn_fwd_kernel(const float* __restrict__ qkv, const uint8_t* __
 // memset of dqkv).
 __global__ void __launch_bounds__(32) attn_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ P,
                                                       const float* __restrict__ dctx, const uint8_t* __restrict__ mask, int S,
-                                                      int heads, int D, float p_drop, unsigned long long seed,
-                                                      unsigned long long stream_id, float* __restrict__ dqkv) {
+                                                      int heads, int D, float p_drop, unsigned long long seed0,
+                                                      unsigned long long stream_id, float* __restrict__ dqkv,
+                                                      const unsigned long long* seed_off) {
+  const unsigned long long seed = seed_with_offset(seed0, seed_off);
   __shared__ float pv_s[32][33];   // [query][key]: what multiplied V in the forward pass
   __shared__ float ds_s[32][33];   // [query][key]: gradient of the scaled scores
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
@@ -337,10 +340,10 @@ extern "C" int tcvn_t_attention(int dir, const float* qkv, const uint8_t* mask, 
                                 tcvn_stream_t stream) {
   TCVN_CHECK_ARG(qkv && mask && P && ctx_or_dctx && S <= 32 && D / heads <= 16, "t_attention: bad arguments");
   if (B <= 0) return TCVN_OK;
-  if (dir == 0) attn_fwd_kernel<<<B * heads, 32, 0, stream>>>(qkv, mask, S, heads, D, P, ctx_or_dctx, p_drop, seed, stream_id);
+  if (dir == 0) attn_fwd_kernel<<<B * heads, 32, 0, stream>>>(qkv, mask, S, heads, D, P, ctx_or_dctx, p_drop, seed, stream_id, seed_offset_ptr());
   else {
     TCVN_CHECK_ARG(dqkv, "t_attention: dqkv missing");
-    attn_bwd_kernel<<<B * heads, 32, 0, stream>>>(qkv, P, ctx_or_dctx, mask, S, heads, D, p_drop, seed, stream_id, dqkv);
+    attn_bwd_kernel<<<B * heads, 32, 0, stream>>>(qkv, P, ctx_or_dctx, mask, S, heads, D, p_drop, seed, stream_id, dqkv, seed_offset_ptr());
   }
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;

@@ -511,7 +511,7 @@ struct Conv2Params {
   // training: Dropout(p) on the 32 new channels (mask = hash(seed, site, row * 32 + channel), re-derived in backward) and
   // their per-column (sum, sum^2) as stored (bf16): the CTA's eight epilogue warps are added in a fixed order and stored in
   // the CTA's own slot, stats[cta][2][32]; the consumer adds the slots in a fixed order (no atomics)
-  float p_drop; unsigned long long seed, site;
+  float p_drop; unsigned long long seed, site; const unsigned long long* seed_off;
   double* stats;
 };
 
@@ -674,9 +674,10 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
       const bool row_ok = row >= 1 && row <= kC2Out && m < p.m_total;
       if (p.p_drop > 0.f && row_ok && !ring) {
         const float inv = 1.f / (1.f - p.p_drop);
+        const unsigned long long seed = seed_with_offset(p.seed, p.seed_off);
 #pragma unroll
         for (int j = 0; j < 32; ++j)
-          o[j] = drop_keep_c2(p.seed, p.site, (unsigned long long)m * 32 + j, p.p_drop) ? o[j] * inv : 0.f;
+          o[j] = drop_keep_c2(seed, p.site, (unsigned long long)m * 32 + j, p.p_drop) ? o[j] * inv : 0.f;
       }
       uint32_t w[16];
 #pragma unroll
@@ -855,7 +856,7 @@ int umma_conv2_fwd(const void* mid, long long rows, const void* w2, const float*
   }
   c2.bias = bias;
   c2.out = static_cast<bf16*>(out); c2.ldo = ldo; c2.col0 = col0; c2.num_tiles = tiles;
-  c2.p_drop = p_drop; c2.seed = seed; c2.site = site; c2.stats = stats;
+  c2.p_drop = p_drop; c2.seed = seed; c2.site = site; c2.seed_off = seed_offset_ptr(); c2.stats = stats;
   // Measured on B200: the 128B swizzle of a UMMA operand is a function of the absolute shared-memory address
   // (bits [4,7) ^= bits [7,10)), exactly as TMA wrote it, so a descriptor may start at ANY row of the haloed
   // tile with matrix-base-offset 0 (setting it to (addr >> 7) & 7 gives wrong results).

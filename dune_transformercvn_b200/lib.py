@@ -29,7 +29,7 @@ EXPORTS = (
     "tcvn_seq_packed_bytes", "tcvn_seq_pack", "tcvn_seq_workspace_bytes", "tcvn_seq_forward",
     "tcvn_t_gemm", "tcvn_t_wgrad", "tcvn_t_colsums", "tcvn_t_bn_finalize", "tcvn_t_bnact_bwd_apply", "tcvn_t_add_colsums",
     "tcvn_t_bnact_fwd", "tcvn_t_pool", "tcvn_t_dropout", "tcvn_t_stem_conv", "tcvn_t_layernorm", "tcvn_t_attention",
-    "tcvn_t_eltwise", "tcvn_t_tokens", "tcvn_t_act_pool2", "tcvn_t_act_gap", "tcvn_adamw_workspace_bytes", "tcvn_adamw_fused",
+    "tcvn_t_eltwise", "tcvn_t_tokens", "tcvn_t_act_pool2", "tcvn_t_act_gap", "tcvn_adamw_workspace_bytes", "tcvn_adamw_fused", "tcvn_set_seed_offset",
     "tcvn_cnn_train_workspace_bytes", "tcvn_cnn_train_forward", "tcvn_cnn_train_backward",
     "tcvn_seq_train_workspace_bytes", "tcvn_seq_train_forward", "tcvn_seq_train_backward",
     "tcvn_t_umma_wgrad", "tcvn_t_umma_wgrad_workspace_bytes", "tcvn_t_umma_conv2_dgrad",
@@ -118,7 +118,8 @@ def load() -> C.CDLL:
     lib.tcvn_t_act_gap.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp]
     lib.tcvn_adamw_workspace_bytes.argtypes = []
     lib.tcvn_adamw_workspace_bytes.restype = sz
-    lib.tcvn_adamw_fused.argtypes = [vp, vp, vp, vp, i64, vp, i32, vp, vp, vp, vp, vp, vp, f32, f32, vp, sz, vp]
+    lib.tcvn_adamw_fused.argtypes = [vp, vp, vp, vp, i64, vp, i32, vp, vp, vp, vp, vp, vp, f32, f32, vp, sz, vp, vp, vp]
+    lib.tcvn_set_seed_offset.argtypes = [vp]
     lib.tcvn_t_umma_wgrad.argtypes = [vp, i64, i32, i32, i32, vp, vp, vp, vp, i32, vp, i32, i32, i32, vp, vp, sz, vp]
     lib.tcvn_t_umma_wgrad_workspace_bytes.argtypes = [i32]
     lib.tcvn_t_umma_wgrad_workspace_bytes.restype = sz

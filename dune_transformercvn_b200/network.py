@@ -434,10 +434,16 @@ class NeutrinoDenseNetwork(nn.Module):
             # preprocess_pixels (neutrino_full_dense_trainer.py:59-66): /255, and in training the multiplicative Gaussian
             # pixel noise, both fused into the densify kernel (a fresh counter-hash stream per step and per map kind)
             std = float(getattr(self.options, "pixel_noise_std", 0.0)) if self.training else 0.0
-            seed = (torch.initial_seed() * 1000003 + self.train_engine.step_index + 1) * 2
-            ev = densify(batch.event_values, batch.event_coords, self.image_size, batch.num_events, 255.0, noise_std=std, seed=seed)
-            pr = densify(batch.prong_values, batch.prong_coords, self.image_size, batch.num_prongs, 255.0, noise_std=std,
-                         seed=seed + 1)
+            seed, seed_off = self.train_engine.seed_args()      # (value, device-resident per-step offset or None)
+            L = _lib.load()
+            L.tcvn_set_seed_offset(seed_off if std > 0.0 else None)
+            try:
+                ev = densify(batch.event_values, batch.event_coords, self.image_size, batch.num_events, 255.0, noise_std=std,
+                             seed=seed ^ 0xA5A5A5A500000000)
+                pr = densify(batch.prong_values, batch.prong_coords, self.image_size, batch.num_prongs, 255.0, noise_std=std,
+                             seed=seed ^ 0x5A5A5A5A00000000)
+            finally:
+                L.tcvn_set_seed_offset(None)
             return self.forward(batch.features, batch.extra, ev, batch.event_mask, pr, batch.prong_mask)
         if self.training:
             return self.forward_sparse(batch, materialize=True)

@@ -191,6 +191,9 @@ class TrainEngine:
         # None disables it; an explicit GradientExchange pins the process group.
         self.exchange = "auto"
         self.broadcast_buffers = True
+        # CUDA-graph mode (GraphedTrainStep): the per-step part of every random seed lives in this device int64 counter
+        # instead of the kernel arguments, so a replayed graph draws fresh dropout masks / pixel noise
+        self.seed_counter: Optional[torch.Tensor] = None
         self.saved = None
         self._nbt: Optional[List[torch.Tensor]] = None
         # the two pixel-map CNNs are independent until the token assembly: the (small, launch-bound) event CNN runs on
@@ -219,6 +222,13 @@ class TrainEngine:
         for tag, _, args, _ in calls:
             _lib.check(fn(*args), f"{what}({tag})")
 
+    def seed_args(self) -> Tuple[int, Optional[int]]:
+        """(seed value, device pointer of the seed offset or None) of the NEXT training step."""
+        base = torch.initial_seed() * 1000003
+        if self.seed_counter is not None:
+            return base & 0xFFFFFFFFFFFF, self.seed_counter.data_ptr()
+        return (base + self.step_index + 1) & 0xFFFFFFFFFFFF, None
+
     def _exchange(self) -> Optional[GradientExchange]:
         if self.exchange == "auto":
             import torch.distributed as dist
@@ -232,9 +242,15 @@ class TrainEngine:
         for t, what in ((event_pixels, "event_pixels"), (prong_pixels, "prong_pixels"), (prong_mask, "prong_mask")):
             _lib.require_cuda(t, what)
         with torch.cuda.device(event_pixels.device):   # the C ABI launches on the current device
-            return self._forward(event_pixels, event_mask, prong_pixels, prong_mask)
+            seed, off = self.seed_args()
+            L = _lib.load()
+            L.tcvn_set_seed_offset(off)
+            try:
+                return self._forward(event_pixels, event_mask, prong_pixels, prong_mask, seed, off)
+            finally:
+                L.tcvn_set_seed_offset(None)
 
-    def _forward(self, event_pixels, event_mask, prong_pixels, prong_mask):
+    def _forward(self, event_pixels, event_mask, prong_pixels, prong_mask, seed, seed_off):
         net = self.net[0]
         L = _lib.load()
         dev = event_pixels.device
@@ -247,7 +263,6 @@ class TrainEngine:
         p_drop = float(net.options.dropout)
         prec = _lib.TCVN_BF16 if net.precision == "bf16" else _lib.TCVN_FP32
         self.step_index += 1
-        seed = (torch.initial_seed() * 1000003 + self.step_index) & 0xFFFFFFFFFFFF
         b, l = prong_mask.shape
         t = prong_pixels.shape[0]
         pix, feat, _ = embedding_dims(net.options)
@@ -298,14 +313,20 @@ class TrainEngine:
                          if name.endswith("num_batches_tracked") and not name.startswith(_NO_GRAD_PREFIXES)]
         if self._nbt:
             torch._foreach_add_(self._nbt, 1)
-        self.saved = dict(ev_px=ev_px, pr_px=pr_px, pm=pm, b=b, l=l, t=t, seed=seed, p_drop=p_drop, dev=dev, prec=prec)
+        self.saved = dict(ev_px=ev_px, pr_px=pr_px, pm=pm, b=b, l=l, t=t, seed=seed, seed_off=seed_off, p_drop=p_drop, dev=dev,
+                          prec=prec)
         return ev_logits, pr_logits
 
     def backward(self, d_ev_logits: Optional[torch.Tensor], d_pr_logits: Optional[torch.Tensor]) -> None:
         if self.saved is None:
             raise _lib.TcvnError("backward without a train-mode forward (or called twice)")
         with torch.cuda.device(self.saved["dev"]):
-            self._backward(d_ev_logits, d_pr_logits)
+            L = _lib.load()
+            L.tcvn_set_seed_offset(self.saved["seed_off"])   # backward runs on autograd's thread: the offset is per thread
+            try:
+                self._backward(d_ev_logits, d_pr_logits)
+            finally:
+                L.tcvn_set_seed_offset(None)
 
     def _backward(self, d_ev_logits: Optional[torch.Tensor], d_pr_logits: Optional[torch.Tensor]) -> None:
         s, self.saved = self.saved, None
@@ -403,6 +424,7 @@ class TcvnAdamW(torch.optim.Optimizer):
         self.max_grad_norm = float(max_grad_norm)
         self._arena: Optional[FlatArena] = None
         self._m = self._v = self._ws = None
+        self.device_state: Optional[Tuple[torch.Tensor, torch.Tensor]] = None   # (step int64[1], lr float32[groups]): graph mode
         self._steps = [0 for _ in self.param_groups]
 
     def attach(self, net) -> "TcvnAdamW":
@@ -479,7 +501,9 @@ class TcvnAdamW(torch.optim.Optimizer):
                 dbl(*[float(x["lr"]) for x in g]), dbl(*[float(x["betas"][0]) for x in g]),
                 dbl(*[float(x["betas"][1]) for x in g]), dbl(*[float(x["eps"]) for x in g]),
                 dbl(*[float(x["weight_decay"]) for x in g]), i64(*self._steps), self.max_grad_norm, 1.0,
-                _lib.ptr(self._ws), self._ws.numel(), st), "tcvn_adamw_fused")
+                _lib.ptr(self._ws), self._ws.numel(),
+                None if self.device_state is None else _lib.ptr(self.device_state[0]),
+                None if self.device_state is None else _lib.ptr(self.device_state[1]), st), "tcvn_adamw_fused")
         self._engine.net[0].engine.key = None
         return loss
 
@@ -524,6 +548,125 @@ class TcvnAdamW(torch.optim.Optimizer):
                 self._m[o:o + s.numel].copy_(stt["exp_avg"].reshape(-1))
                 self._v[o:o + s.numel].copy_(stt["exp_avg_sq"].reshape(-1))
                 self._steps[gi] = int(stt["step"])
+
+
+class GraphedTrainStep:
+    """One whole training step - zero_grad, densify (+ pixel noise), train-mode forward, fused focal loss, hand-written
+    backward (+ gradient exchange), clip + AdamW - captured ONCE per batch shape into a CUDA graph and replayed with a
+    single launch.  The step is ~1600 kernel launches; at the reference's batch sizes (2-16 events per GPU) issuing them
+    costs more host time (6 us each) than the GPU needs to run them.
+
+    What changes from step to step lives in device memory, not in kernel arguments: the step counter (dropout / noise seed
+    offset, AdamW bias corrections) and the scheduler's learning rates (copied in before every replay).  Results are the
+    same arithmetic as the eager step; the seed sequence differs (base + counter instead of base + host step index).
+
+    A graph is keyed by the batch SHAPE (events, prong slots, images, hit counts).  Training data with a different shape in
+    every step (variable prong counts) re-captures every time - use the eager step there (``graph=False`` in bench.py)."""
+
+    def __init__(self, net, optimizer: "TcvnAdamW", options, max_plans: int = 8):
+        from . import loss as _loss
+        self.net, self.opt, self.options, self._loss = net, optimizer, options, _loss
+        self.plans: Dict[Tuple, dict] = {}
+        self.max_plans = max_plans
+        self.stream: Optional[torch.cuda.Stream] = None
+        self.step_dev = self.lr_dev = self.lr_host = None
+        self._mirror = 0                 # host copy of step_dev
+        self.launches_per_replay = 0
+
+    def _body(self, batch, ev_t, pr_t):
+        self.step_dev.add_(1)
+        self.opt.zero_grad()
+        ev, pr = self.net.forward_sparse(batch)
+        loss, _ = self._loss.training_loss(ev, pr, ev_t, pr_t, self.options)
+        loss.backward()
+        self.opt.step()
+        return loss.detach()
+
+    def _setup(self, dev) -> None:
+        if self.opt._arena is None or not self.opt._arena.bound():
+            self.opt._find_arena()
+        ng = len(self.opt.param_groups)
+        self.step_dev = torch.tensor([self.opt._steps[0]], dtype=torch.int64, device=dev)
+        self._mirror = self.opt._steps[0]
+        self.lr_dev = torch.zeros(ng, dtype=torch.float32, device=dev)
+        self.lr_host = torch.zeros(ng, dtype=torch.float32).pin_memory()
+        self.stream = torch.cuda.Stream(device=dev)
+
+    def __call__(self, batch, ev_targets, pr_targets) -> torch.Tensor:
+        dev = batch.event_values.device
+        if self.step_dev is None:
+            self._setup(dev)
+        eng = self.net.train_engine
+        key = (batch.num_events, batch.prong_mask.shape[1], batch.num_prongs, batch.event_coords.shape[0], batch.prong_coords.shape[0],
+               str(batch.event_values.dtype), tuple(pr_targets.shape))
+        for gi, g in enumerate(self.opt.param_groups):
+            self.lr_host[gi] = float(g["lr"])
+        self.lr_dev.copy_(self.lr_host, non_blocking=True)
+        if self._mirror != self.opt._steps[0]:       # eager optimizer steps were taken in between: resynchronise the counter
+            self.step_dev.fill_(self.opt._steps[0])
+            self._mirror = self.opt._steps[0]
+        plan = self.plans.get(key)
+        if plan is None:
+            plan = self._capture(key, batch, ev_targets, pr_targets)
+        else:
+            for dst, src in zip(plan["inputs"], list(batch.tensors()) + [ev_targets, pr_targets]):
+                dst.copy_(src, non_blocking=True)
+        plan["graph"].replay()
+        # host mirrors of what the graph advanced on the device
+        eng.step_index += 1
+        self.opt._steps = [s + 1 for s in self.opt._steps]
+        self._mirror += 1
+        self.net.engine.key = None
+        self.launches_per_replay = plan["launches"]
+        return plan["loss"]
+
+    def _capture(self, key, batch, ev_t, pr_t) -> dict:
+        from . import synth
+        dev = batch.event_values.device
+        eng, opt = self.net.train_engine, self.opt
+        static = synth.SparseBatch(*[t.clone().contiguous() for t in batch.tensors()], list(batch.prongs_per_event))
+        t0, t1 = ev_t.clone(), pr_t.clone()
+        cur = torch.cuda.current_stream(dev)
+        # device-resident mode for the engine and the optimizer; snapshot everything a step mutates, run ONE real step to
+        # allocate the workspaces / build the caches, restore, then record (recording executes nothing)
+        eng.arena.ensure()
+        eng.seed_counter = self.step_dev
+        opt.device_state = (self.step_dev, self.lr_dev)
+        try:
+            return self._capture_inner(key, static, t0, t1, dev, cur)
+        finally:       # eager steps outside this class keep their host-side seeds / step counts
+            eng.seed_counter = None
+            opt.device_state = None
+
+    def _capture_inner(self, key, static, t0, t1, dev, cur) -> dict:
+        eng, opt = self.net.train_engine, self.opt
+        nbt = [b for n, b in self.net.named_buffers() if n.endswith("num_batches_tracked")]
+        snap = (eng.arena.flat.clone(), opt._m.clone(), opt._v.clone(), self.step_dev.clone(), [b.clone() for b in nbt],
+                eng.step_index, list(opt._steps))
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            self._body(static, t0, t1)
+        cur.wait_stream(self.stream)
+
+        def restore():
+            eng.arena.flat.copy_(snap[0]); opt._m.copy_(snap[1]); opt._v.copy_(snap[2]); self.step_dev.copy_(snap[3])
+            for b, v in zip(nbt, snap[4]):
+                b.copy_(v)
+            eng.step_index, opt._steps = snap[5], list(snap[6])
+
+        restore()
+        torch.cuda.synchronize(dev)
+        l0 = _lib.load().tcvn_launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=self.stream, capture_error_mode="relaxed"):
+            loss = self._body(static, t0, t1)
+        launches = _lib.load().tcvn_launch_count() - l0
+        eng.step_index, opt._steps = snap[5], list(snap[6])    # recording advanced the host mirrors only
+        if len(self.plans) >= self.max_plans:
+            self.plans.pop(next(iter(self.plans)))
+        plan = {"graph": g, "inputs": list(static.tensors()) + [t0, t1], "loss": loss, "launches": launches}
+        self.plans[key] = plan
+        return plan
 
 
 def register() -> None:

@@ -255,12 +255,19 @@ int tcvn_t_act_gap(const float* blk, int n, int H, int W, int ld, int C, const f
  * lr / beta1 / beta2 / eps / weight_decay / step: HOST arrays of n_groups entries (step >= 1 = the group's step count).
  * max_norm > 0: the squared gradient norm is first reduced over the whole arena (one partial sum per block in the
  * workspace, added in a fixed order: bit-reproducible, no host sync) and grads are multiplied by
- * grad_mul * min(1, max_norm / (norm * grad_mul + 1e-6)); the last double of the workspace receives norm^2. */
+ * grad_mul * min(1, max_norm / (norm * grad_mul + 1e-6)); the last double of the workspace receives norm^2.
+ * step_dev / lr_dev (device pointers, may be NULL): when given, the step count (bias corrections, computed on the device
+ * in double) and the per-group learning rates are READ FROM DEVICE MEMORY instead of the host arrays, so a captured CUDA
+ * graph of the training step stays valid from step to step. */
 size_t tcvn_adamw_workspace_bytes(void);
 int tcvn_adamw_fused(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, const uint8_t* select,
                      int n_groups, const double* lr, const double* beta1, const double* beta2, const double* eps,
                      const double* weight_decay, const int64_t* step, float max_norm, float grad_mul, void* workspace,
-                     size_t workspace_bytes, tcvn_stream_t stream);
+                     size_t workspace_bytes, const int64_t* step_dev, const float* lr_dev, tcvn_stream_t stream);
+/* Every seeded kernel (dropout masks, training pixel noise) launched from the calling host thread after this call adds
+ * *device_ptr to the seed argument it was given (NULL: off).  With the step counter in device memory a replayed CUDA
+ * graph draws fresh masks; forward and backward of one step read the same value. */
+int tcvn_set_seed_offset(const uint64_t* device_ptr);
 
 /* tcgen05 kernels of the bf16 training path on caller-provided row-major bf16 matrices (csrc/umma_train.cu).
  * Weight gradient with MN-major operands (the reduction runs over pixel rows):

@@ -349,6 +349,64 @@ def test_bf16_training_step_against_fp64_oracle(dev):
     assert ours["worst_tensor"][0] > 0.88 and ours["median_tensor_cosine"] > 0.95, ours["worst_tensor"]
 
 
+def test_graphed_train_step_matches_eager_steps(dev):
+    """training.GraphedTrainStep (the whole step as one CUDA graph per batch shape): with dropout and pixel noise off the
+    seed plays no role, so three replayed steps must leave EXACTLY the parameters, optimizer moments and running buffers
+    of three eager steps (same kernels, same order of arithmetic; step count and learning rate read from device memory,
+    with the learning rate changed between steps like a scheduler does).  With dropout on, consecutive replays on the same
+    batch must draw different masks (the seed offset lives in device memory) and the loss must still go down."""
+    from dune_transformercvn_b200 import loss as tloss
+    opts = PathOptions.tutorial()
+    opts.dropout = 0.0
+    opts.pixel_noise_std = 0.0
+    batch = synth.make_batch(6, seed=3, max_prongs=5).to(dev)
+    g = torch.Generator().manual_seed(1)
+    ev_t = torch.randint(0, NUM_EVENT_CLASSES, (6,), generator=g).to(dev)
+    pr_t = torch.randint(0, NUM_PRONG_CLASSES, tuple(batch.prong_mask.shape), generator=g)
+    pr_t[~batch.prong_mask.cpu()] = -1
+    pr_t = pr_t.to(dev)
+    lrs = (1e-3, 5e-4, 2e-3)
+    finals = []
+    for graphed in (False, True):
+        net = NeutrinoDenseNetwork(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES, precision="bf16")
+        net.load_state_dict(synth.init_state(net.specs, seed=2, perturb=True))
+        net = net.to(dev).train()
+        opt = training.TcvnAdamW(training.reference_param_groups(net, opts.l2_penalty), lr=1e-3, max_grad_norm=opts.gradient_clip)
+        stepper = training.GraphedTrainStep(net, opt, opts) if graphed else None
+        losses = []
+        for lr in lrs:
+            for grp in opt.param_groups:
+                grp["lr"] = lr
+            if graphed:
+                losses.append(float(stepper(batch, ev_t, pr_t)))
+            else:
+                opt.zero_grad()
+                ev, pr = net.forward_sparse(batch)
+                loss, _ = tloss.training_loss(ev, pr, ev_t, pr_t, opts)
+                loss.backward()
+                opt.step()
+                losses.append(float(loss.detach()))
+        sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+        finals.append((losses, net.train_engine.arena.flat.clone(), opt._m.clone(), opt._v.clone(), sd, list(opt._steps)))
+    assert finals[0][0] == finals[1][0], (finals[0][0], finals[1][0])
+    for a, b, what in zip(finals[0][1:4], finals[1][1:4], ("parameters + buffers", "exp_avg", "exp_avg_sq")):
+        assert torch.equal(a, b), what
+    assert all(torch.equal(finals[0][4][k], finals[1][4][k]) for k in finals[0][4]) and finals[0][5] == finals[1][5] == [3, 3]
+    # dropout on: fresh masks per replay, and the replayed steps train
+    opts = PathOptions.tutorial()
+    torch.manual_seed(0)
+    net = NeutrinoDenseNetwork(opts, 1, 1, 3, NUM_PRONG_CLASSES, NUM_EVENT_CLASSES, precision="bf16").to(dev).train()
+    opt = training.TcvnAdamW(training.reference_param_groups(net, opts.l2_penalty), lr=0.0, max_grad_norm=opts.gradient_clip)
+    stepper = training.GraphedTrainStep(net, opt, opts)
+    l = [float(stepper(batch, ev_t, pr_t)) for _ in range(3)]           # lr = 0: only the masks / noise differ
+    assert len(set(l)) == 3, l
+    for grp in opt.param_groups:
+        grp["lr"] = 2e-3
+    l = [float(stepper(batch, ev_t, pr_t)) for _ in range(25)]
+    assert all(x == x for x in l) and sum(l[-5:]) / 5 < 0.6 * sum(l[:3]) / 3, l
+    assert len(stepper.plans) == 1 and stepper.launches_per_replay > 500
+
+
 def test_two_shard_step_averages_like_ddp(dev):
     """Data-parallel parity ("N-rank result == single-process emulation that runs each rank's shard
     through the reference network with rank-local BN statistics and averages the gradients", train.py:123-127).  One
