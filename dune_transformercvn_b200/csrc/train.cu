@@ -1384,7 +1384,7 @@ __global__ void __launch_bounds__(256) sumsq_parts_kernel(const float* __restric
   if (threadIdx.x == 0) parts[blockIdx.x] = red[0];
 }
 
-struct AdamGroup { float lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt; };
+struct AdamGroup { float lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt; double beta1d, beta2d; };
 struct AdamArgs {
   float* p; const float* g; float* m; float* v; long long n;
   const uint8_t* select;          // per element: 0 = not optimised, k = group k-1
@@ -1405,8 +1405,8 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamArgs a) {
     if (a.lr_dev) h.lr = a.lr_dev[threadIdx.x];
     if (a.step_dev) {
       const double st = (double)*a.step_dev;
-      h.bc1 = (float)(1.0 - pow((double)h.beta1, st));
-      h.bc2_sqrt = (float)sqrt(1.0 - pow((double)h.beta2, st));
+      h.bc1 = (float)(1.0 - pow(h.beta1d, st));          // the host path's expression, in double, on the device
+      h.bc2_sqrt = (float)sqrt(1.0 - pow(h.beta2d, st));
     }
     sgrp[threadIdx.x] = h;
   }
@@ -1469,6 +1469,7 @@ extern "C" int tcvn_adamw_fused(float* params, const float* grads, float* exp_av
     // bias corrections in double on the host, like torch.optim.AdamW's Python scalars
     a.grp[k].lr = (float)lr[k]; a.grp[k].beta1 = (float)beta1[k]; a.grp[k].beta2 = (float)beta2[k];
     a.grp[k].eps = (float)eps[k]; a.grp[k].weight_decay = (float)weight_decay[k];
+    a.grp[k].beta1d = beta1[k]; a.grp[k].beta2d = beta2[k];
     a.grp[k].bc1 = (float)(1.0 - pow(beta1[k], (double)step[k]));
     a.grp[k].bc2_sqrt = (float)sqrt(1.0 - pow(beta2[k], (double)step[k]));
   }
