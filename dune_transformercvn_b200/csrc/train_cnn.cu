@@ -432,6 +432,7 @@ typedef __nv_bfloat16 bf;
 
 constexpr int kPullMax = 16;            // later layers of a block a gradient can be pulled from
 constexpr int kPullCtasMax = 148 * 4;   // grid (and bias-gradient slots) of grad_pull_kernel
+constexpr long long kFuseDgradRows = 160000;   // up to here the BN2 backward reductions are fused into the dgrad epilogue
 
 struct T16Layer { size_t w1b, w1d, w2b, wd, fold1, fold2, mid_raw, mid_act, dA1; };
 struct T16Block {
@@ -544,12 +545,6 @@ __device__ __forceinline__ bool drop_keep16(unsigned long long seed, unsigned lo
   return (r >> 8) * (1.0f / 16777216.0f) >= p;
 }
 
-__device__ __forceinline__ void ld8_bf(const bf* p, float (&f)[8]) {
-  const uint4 v = *reinterpret_cast<const uint4*>(p);
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
-}
 __device__ __forceinline__ uint4 pack8_bf(const float (&v)[8]) {
   uint32_t w[4];
 #pragma unroll
@@ -616,56 +611,95 @@ __global__ void __launch_bounds__(256) grad_pull_kernel(const PullArgs a) {
     const unsigned R = (unsigned)(a.Hp * a.Wp);
     const float inv_keep = 1.f / (1.f - a.p);
     const unsigned long long seed = seed_with_offset(a.seed, a.seed_off);
-    for (long long m = (long long)blockIdx.x * rpi + ry; m < a.rows; m += (long long)gridDim.x * rpi) {
-      const unsigned rr = (unsigned)m % R;
-      const unsigned y = rr / (unsigned)a.Wp, x_ = rr - y * (unsigned)a.Wp;
-      const bool ring = y == 0 || y == (unsigned)(a.Hp - 1) || x_ == 0 || x_ == (unsigned)(a.Wp - 1);
-      float v[8];
+    // U rows in flight per thread: all their loads are issued before any is consumed (ncu, round 2: with one row per
+    // iteration the kernel ran at 31-41 % of the HBM bandwidth, latency-bound at 22 % occupancy)
+    constexpr int U = 2;
+    const long long stride = (long long)gridDim.x * rpi;
+    for (long long m0 = (long long)blockIdx.x * rpi + ry; m0 < a.rows; m0 += U * stride) {
+      bool ring[U], inside[U];
+      uint4 gi[U], xi[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = 0.f;
-      if (!ring) {
-        ld8_bf(a.ginit + m * (long long)a.ldg + a.col0 + c, v);
-        float xv[8];
-        ld8_bf(a.blk + m * (long long)a.ldb + a.col0 + c, xv);
-        for (int j = 0; j < a.n_src; ++j) {
-          float d[8];
-          ld8_bf(a.src[j].dA + m * (long long)a.src[j].ld + a.col0 + c, d);
-          const float* k = cst + (j * 3) * a.ncols + c;
-          const float4 s0 = *reinterpret_cast<const float4*>(k), s1 = *reinterpret_cast<const float4*>(k + 4);
-          const float4 h0 = *reinterpret_cast<const float4*>(k + a.ncols), h1 = *reinterpret_cast<const float4*>(k + a.ncols + 4);
-          const float4 a0 = *reinterpret_cast<const float4*>(k + 2 * a.ncols), a1 = *reinterpret_cast<const float4*>(k + 2 * a.ncols + 4);
-          const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-          const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
-          const float sa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = fmaf(d[i], fmaf(xv[i], sc[i], sh[i]) >= 0.f ? sc[i] : sa[i], v[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] -= cA[i] + (xv[i] - mean[i]) * rstd[i] * cB[i];
-        if (MODE == 0) {
-          if (a.p > 0.f) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              v[i] = drop_keep16(seed, a.site, (unsigned long long)m * 32 + c + i, a.p) ? v[i] * inv_keep : 0.f;
-          }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) bsum[i] += v[i];
+      for (int u = 0; u < U; ++u) {
+        const long long m = m0 + u * stride;
+        inside[u] = m < a.rows;
+        const unsigned rr = (unsigned)(inside[u] ? m : 0) % R;
+        const unsigned y = rr / (unsigned)a.Wp, x_ = rr - y * (unsigned)a.Wp;
+        ring[u] = y == 0 || y == (unsigned)(a.Hp - 1) || x_ == 0 || x_ == (unsigned)(a.Wp - 1);
+        if (inside[u] && !ring[u]) {
+          gi[u] = *reinterpret_cast<const uint4*>(a.ginit + m * (long long)a.ldg + a.col0 + c);
+          xi[u] = *reinterpret_cast<const uint4*>(a.blk + m * (long long)a.ldb + a.col0 + c);
         }
       }
-      if (MODE == 0) {
-        const uint4 hv = pack8_bf(v), zv = make_uint4(0u, 0u, 0u, 0u);
-        bf* g2x = a.g2x;
-        *reinterpret_cast<uint4*>(g2x + m * 128 + 32 + c) = hv;
-        *reinterpret_cast<uint4*>(g2x + m * 128 + 96 + c) = zv;
-        if (m > 0) *reinterpret_cast<uint4*>(g2x + (m - 1) * 128 + c) = hv;
-        else *reinterpret_cast<uint4*>(g2x + 64 + c) = zv;
-        if (m + 1 < a.rows) *reinterpret_cast<uint4*>(g2x + (m + 1) * 128 + 64 + c) = hv;
-        else *reinterpret_cast<uint4*>(g2x + m * 128 + c) = zv;
-      } else {
-        *reinterpret_cast<uint4*>(a.out16 + m * (long long)a.pitch + c) = pack8_bf(v);
-        if (vx == 0)
-          for (int z = a.ncols; z < a.pitch; z += 8)
-            *reinterpret_cast<uint4*>(a.out16 + m * (long long)a.pitch + z) = make_uint4(0u, 0u, 0u, 0u);
+      float v[U][8], xv[U][8];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { v[u][i] = 0.f; xv[u][i] = 0.f; }
+        if (inside[u] && !ring[u]) {
+          const uint32_t gw[4] = {gi[u].x, gi[u].y, gi[u].z, gi[u].w}, xw[4] = {xi[u].x, xi[u].y, xi[u].z, xi[u].w};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            v[u][2 * i] = __uint_as_float(gw[i] << 16); v[u][2 * i + 1] = __uint_as_float(gw[i] & 0xffff0000u);
+            xv[u][2 * i] = __uint_as_float(xw[i] << 16); xv[u][2 * i + 1] = __uint_as_float(xw[i] & 0xffff0000u);
+          }
+        }
+      }
+      for (int j = 0; j < a.n_src; ++j) {
+        uint4 di[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (inside[u] && !ring[u])
+            di[u] = *reinterpret_cast<const uint4*>(a.src[j].dA + (m0 + u * stride) * (long long)a.src[j].ld + a.col0 + c);
+        const float* k = cst + (j * 3) * a.ncols + c;
+        const float4 s0 = *reinterpret_cast<const float4*>(k), s1 = *reinterpret_cast<const float4*>(k + 4);
+        const float4 h0 = *reinterpret_cast<const float4*>(k + a.ncols), h1 = *reinterpret_cast<const float4*>(k + a.ncols + 4);
+        const float4 a0 = *reinterpret_cast<const float4*>(k + 2 * a.ncols), a1 = *reinterpret_cast<const float4*>(k + 2 * a.ncols + 4);
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const float sa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (!(inside[u] && !ring[u])) continue;
+          const uint32_t dw[4] = {di[u].x, di[u].y, di[u].z, di[u].w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float d = (i & 1) ? __uint_as_float(dw[i >> 1] & 0xffff0000u) : __uint_as_float(dw[i >> 1] << 16);
+            v[u][i] = fmaf(d, fmaf(xv[u][i], sc[i], sh[i]) >= 0.f ? sc[i] : sa[i], v[u][i]);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!inside[u]) continue;
+        const long long m = m0 + u * stride;
+        if (!ring[u]) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[u][i] -= cA[i] + (xv[u][i] - mean[i]) * rstd[i] * cB[i];
+          if (MODE == 0) {
+            if (a.p > 0.f) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                v[u][i] = drop_keep16(seed, a.site, (unsigned long long)m * 32 + c + i, a.p) ? v[u][i] * inv_keep : 0.f;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) bsum[i] += v[u][i];
+          }
+        }
+        if (MODE == 0) {
+          const uint4 hv = pack8_bf(v[u]), zv = make_uint4(0u, 0u, 0u, 0u);
+          bf* g2x = a.g2x;
+          *reinterpret_cast<uint4*>(g2x + m * 128 + 32 + c) = hv;
+          *reinterpret_cast<uint4*>(g2x + m * 128 + 96 + c) = zv;
+          if (m > 0) *reinterpret_cast<uint4*>(g2x + (m - 1) * 128 + c) = hv;
+          else *reinterpret_cast<uint4*>(g2x + 64 + c) = zv;
+          if (m + 1 < a.rows) *reinterpret_cast<uint4*>(g2x + (m + 1) * 128 + 64 + c) = hv;
+          else *reinterpret_cast<uint4*>(g2x + m * 128 + c) = zv;
+        } else {
+          *reinterpret_cast<uint4*>(a.out16 + m * (long long)a.pitch + c) = pack8_bf(v[u]);
+          if (vx == 0)
+            for (int z = a.ncols; z < a.pitch; z += 8)
+              *reinterpret_cast<uint4*>(a.out16 + m * (long long)a.pitch + z) = make_uint4(0u, 0u, 0u, 0u);
+        }
       }
     }
   }
@@ -1173,11 +1207,19 @@ struct TWalk16 {
           TCVN_TRY(umma_wgrad(h(Y.mid_act), rows, mid, mid, 3, cols, shifts, valid, nullptr, nullptr, nullptr, 0, g2x, 128, 128, 0,
                               f(T.parts), garena + L.conv2_w, true, wst, 2));
         }
-        // conv2 input gradient; its epilogue also takes the BN2 + PReLU2 backward reductions from the values it stores
-        // (round 1 / early round 2: a separate column-sum pass over dmid and mid_raw, 512 bytes per row)
+        // conv2 input gradient, then the BN2 + PReLU2 backward reductions over (dmid, mid_raw).  On small maps the reductions
+        // ride in the dgrad epilogue (one launch and one pass over dmid less); on large maps they stay a separate
+        // HBM-bound pass: ncu (profiles/r2_dgrad_fused_block1.txt) shows the fused epilogue bound by the LSU pipe - 372 warp
+        // shuffles + 256 shared-memory broadcasts per row - at 0.31 ns per row against 0.25 ns for dgrad + column sums
         {
           int slabs = 0;
-          TCVN_TRY(umma_conv2_dgrad(g2x, h(Y.wd), rows, B.Hp, B.Wp, dmid, st, h(Y.mid_raw), f(Y.fold2), dbl(T.dparts), &slabs));
+          if (rows <= kFuseDgradRows) {
+            TCVN_TRY(umma_conv2_dgrad(g2x, h(Y.wd), rows, B.Hp, B.Wp, dmid, st, h(Y.mid_raw), f(Y.fold2), dbl(T.dparts), &slabs));
+          } else {
+            TCVN_TRY(umma_conv2_dgrad(g2x, h(Y.wd), rows, B.Hp, B.Wp, dmid, st));
+            TCVN_TRY(colsums_parts(1, h(Y.mid_raw), true, mid, 0, dmid, true, mid, 0, f(Y.fold2), mid, mid, rows, B.Hp, B.Wp,
+                                   dbl(T.dparts), &slabs, st));
+          }
           // reduce the slots -> (parameter gradients, conv2 bias gradient), then the elementwise half in place
           TCVN_TRY(param_reduce(slabs, mid, true, L.norm2, NOGAP, NOGAP, nullptr, count, nullptr, nullptr, bias_slots,
                                 garena + L.conv2_b));

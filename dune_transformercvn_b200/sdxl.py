@@ -244,12 +244,17 @@ class _SdxlCnn16(_SdxlCnn):
         return out
 
     def forward(self, pixels: torch.Tensor) -> torch.Tensor:
-        outs = [self._forward_chunk(pixels[i:i + self.image_chunk]) for i in range(0, pixels.shape[0], self.image_chunk)]
-        if not outs:
+        n = pixels.shape[0]
+        if n == 0:
             return torch.empty((0, self.out), dtype=torch.float32, device=pixels.device)
-        return torch.cat(outs) if len(outs) > 1 else outs[0]
+        # the big maps are walked in chunks of images; the 1x1-spatial tail (26 small fp32 GEMMs whose cost is reading
+        # their weights: 5 ms per call whatever the image count) runs ONCE over all images
+        maps = [self._forward_chunk(pixels[i:i + self.image_chunk]) for i in range(0, n, self.image_chunk)]
+        x32 = torch.cat(maps) if len(maps) > 1 else maps[0]
+        return self._tail(_lib.load(), _lib.stream_ptr(pixels.device), x32, n, self.ch[-2])
 
     def _forward_chunk(self, pixels: torch.Tensor) -> torch.Tensor:
+        """Down blocks 0..7 of a chunk of images on the tensor cores -> its ringed fp32 1x1 maps [n*9][512]."""
         L = _lib.load()
         dev = pixels.device
         st = _lib.stream_ptr(dev)
@@ -290,7 +295,7 @@ class _SdxlCnn16(_SdxlCnn):
             raise _lib.TcvnError(f"sdxl: the mid block is reached at {h}x{w_}; only the 1x1 case (400x280 inputs) is built")
         x32 = torch.empty(tuple(x.shape), dtype=torch.float32, device=dev)
         _lib.check(L.tcvn_sdxl16_to_f32(_lib.ptr(x), x.numel(), _lib.ptr(x32), st), "tcvn_sdxl16_to_f32")
-        return self._tail(L, st, x32, n, cin)
+        return x32
 
 
 
