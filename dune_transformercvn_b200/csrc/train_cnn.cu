@@ -582,7 +582,7 @@ struct PullArgs {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(256) grad_pull_kernel(const PullArgs a) {
+__global__ void __launch_bounds__(256, 2) grad_pull_kernel(const PullArgs a) {
   extern __shared__ float cst[];   // [n_src][3][ncols]: scale, shift, scale * slope
   __shared__ float red[MODE == 0 ? 256 : 1][8];
   const int tv = a.ncols >> 3, rpi = 256 / tv;

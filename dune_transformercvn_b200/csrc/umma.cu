@@ -141,6 +141,8 @@ struct GemmParams {
   // ResNet block (identity or 1x1-shortcut weights in the matching K range of W).  Plain GEMM: n_taps = 1, tap_off = {0}.
   int n_taps, chunks_per_tap, chunks2;
   int tap_off[9];
+  int ntile;               // output channels per N tile: 128, or 64 (the 64-channel layers of the --sdxl CNN: half the MMA
+                           // work and half the weight traffic of a zero-padded 128-wide tile)
   int n_tiles_n;           // N tiles of 128 (1 for conv1)
   const float *a_scale, *a_shift, *a_alpha;  // [kchunks*64] (TRANSFORM only)
   const float *o_shift, *o_alpha;            // [n_tiles_n*128]
@@ -230,21 +232,21 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
         int tap = 0, kk = 0;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full[stage], kStageA + kStageW);
+          ptx::mbar_arrive_expect_tx(&full[stage], kStageA + p.ntile * 128);
           if (kc < tap_chunks) {
             ptx::tma_load_2d(sA + stage * kStageA, &tmA, &full[stage], kk * 64, mt * kTileM + p.tap_off[tap]);
             if (++kk == p.chunks_per_tap) { kk = 0; ++tap; }
           } else {
             ptx::tma_load_2d(sA + stage * kStageA, &tmA2, &full[stage], (kc - tap_chunks) * 64, mt * kTileM);
           }
-          ptx::tma_load_2d(sW + stage * kStageW, &tmW, &full[stage], kc * 64, nt * kMid);
+          ptx::tma_load_2d(sW + stage * kStageW, &tmW, &full[stage], kc * 64, nt * p.ntile);
           if (++stage == kC1Stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = ptx::umma_idesc_bf16(kTileM, kMid);
+      const uint32_t idesc = ptx::umma_idesc_bf16(kTileM, p.ntile);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
@@ -374,9 +376,9 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
       // this tile's epilogue constants -> shared memory (shift fp32, PReLU slopes as packed bf16 pairs)
       {
         const int e = threadIdx.x - (10 + 4 * grp) * 32;  // 0..127
-        if (!MMASHIFT) s_shift[e] = __ldg(p.o_shift + nt * kMid + e);
+        if (!MMASHIFT) s_shift[e] = __ldg(p.o_shift + nt * p.ntile + e);
         if (e < kMid / 2) {
-          const float2 a = __ldg(reinterpret_cast<const float2*>(p.o_alpha + nt * kMid) + e);
+          const float2 a = __ldg(reinterpret_cast<const float2*>(p.o_alpha + nt * p.ntile) + e);
           const __nv_bfloat162 a2 = __floats2bfloat162_rn(a.x, a.y);
           s_alpha2[e] = *reinterpret_cast<const uint32_t*>(&a2);
         }
@@ -387,7 +389,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
       if (issuer) ptx::tma_store_wait_read();  // this group's previous store has drained the staging tile
       ptx::named_bar_sync(1 + grp, 128);
 #pragma unroll 1
-      for (int c = 0; c < 4; c += 2) {
+      for (int c = 0; c < (p.ntile >> 5); c += 2) {
         uint32_t r0[32], r1[32];
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(g * 32) << 16) + grp * kMid + c * 32, r0);
         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(g * 32) << 16) + grp * kMid + c * 32 + 32, r1);
@@ -426,8 +428,8 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
       ptx::fence_proxy_async_smem();
       ptx::named_bar_sync(1 + grp, 128);
       if (issuer) {
-        ptx::tma_store_2d(&tmO, stg, nt * kMid, mt * kTileM);
-        ptx::tma_store_2d(&tmO, stg + kStageA, nt * kMid + 64, mt * kTileM);
+        ptx::tma_store_2d(&tmO, stg, nt * p.ntile, mt * kTileM);
+        if (p.ntile > 64) ptx::tma_store_2d(&tmO, stg + kStageA, nt * p.ntile + 64, mt * kTileM);
         ptx::tma_store_commit();
       }
       if (p.stats != nullptr) {
@@ -746,7 +748,7 @@ int launch_gemm(bool transform, const void* A, long long rows, int a_cols, int a
   TCVN_TRY(make_map(out, rows, out_cols, out_pitch, 64, kTileM, &tmO));
   GemmParams g;
   g.m_total = rows; g.kchunks = kpad / kKChunk; g.kphys = kphys; g.n_tiles_n = n_tiles_n;
-  g.n_taps = 1; g.chunks_per_tap = g.kchunks; g.chunks2 = 0;
+  g.n_taps = 1; g.chunks_per_tap = g.kchunks; g.chunks2 = 0; g.ntile = kMid;
   for (int t = 0; t < 9; ++t) g.tap_off[t] = 0;
   g.a_scale = a_scale; g.a_shift = a_shift; g.a_alpha = a_alpha; g.o_shift = o_shift; g.o_alpha = o_alpha;
   g.Hp = Hp; g.Wp = Wp;
@@ -784,15 +786,16 @@ int launch_gemm_shifted(const void* A, long long rows, int a_cols, int n_taps, c
     attr_done = true;
   }
   const int ktot = n_taps * a_cols + x2_cols;
+  const int ntile = (n_tiles_n == 1 && out_cols <= 64) ? 64 : kMid;
   CUtensorMap tmA, tmW, tmO, tmX;
   TCVN_TRY(make_map(A, rows, a_cols, a_cols, 64, kTileM, &tmA));
-  TCVN_TRY(make_map(W, (long long)n_tiles_n * kMid, ktot, ktot, 64, kMid, &tmW));
+  TCVN_TRY(make_map(W, (long long)n_tiles_n * kMid, ktot, ktot, 64, ntile, &tmW));
   TCVN_TRY(make_map(out, rows, out_cols, out_cols, 64, kTileM, &tmO));
   if (X2) TCVN_TRY(make_map(X2, rows, x2_cols, x2_cols, 64, kTileM, &tmX));
   else tmX = tmA;
   GemmParams g;
   g.m_total = rows; g.kchunks = ktot / kKChunk; g.kphys = ktot; g.n_tiles_n = n_tiles_n;
-  g.n_taps = n_taps; g.chunks_per_tap = a_cols / kKChunk; g.chunks2 = x2_cols / kKChunk;
+  g.n_taps = n_taps; g.chunks_per_tap = a_cols / kKChunk; g.chunks2 = x2_cols / kKChunk; g.ntile = ntile;
   for (int t = 0; t < 9; ++t) g.tap_off[t] = t < n_taps && tap_off ? tap_off[t] : 0;
   g.a_scale = g.a_shift = g.a_alpha = nullptr; g.o_shift = bias; g.o_alpha = ones;
   g.Hp = Hp; g.Wp = Wp; g.stats = nullptr;
