@@ -58,16 +58,41 @@ def test_training_on_cpu_fails_loudly(net):
     assert len(groups[0]["params"]) == 464 and len(groups[1]["params"]) == 314
 
 
+class _FakeSpec:
+    def __init__(self, name, numel, is_param):
+        self.name, self.numel, self.is_param = name, numel, is_param
+
+
+class _FakeArena:
+    """The part of FlatArena the exchange touches: parameters and BatchNorm buffers interleaved in one flat vector."""
+
+    def __init__(self, rank):
+        self.specs = [_FakeSpec("w0", 4, True), _FakeSpec("bn.running_mean", 3, False), _FakeSpec("w1", 2, True),
+                      _FakeSpec("bn.running_var", 3, False)]
+        self.offset, cur = {}, 0
+        for s in self.specs:
+            self.offset[s.name] = cur
+            cur += s.numel
+        self.flat = torch.arange(cur, dtype=torch.float32) + 100.0 * rank
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        ex = training.GradientExchange()
+        # what TrainEngine does on its own once torch.distributed is up with > 1 rank ("auto")
+        eng = training.TrainEngine.__new__(training.TrainEngine)
+        eng.exchange = "auto"
+        ex = eng._exchange()
+        assert isinstance(ex, training.GradientExchange) and ex.world == world and eng._exchange() is ex
         g = torch.arange(10, dtype=torch.float32) * (rank + 1)
         ex.reduce(g[6:])          # slices are exchanged as soon as they are final, in backward order
         ex.reduce(g[:6])
         ex.wait()
-        torch.save(g, out + f".{rank}")
+        assert not ex.pending
+        arena = _FakeArena(rank)
+        ex.broadcast_buffers(arena)      # DDP's broadcast_buffers: rank 0's running statistics, parameters untouched
+        torch.save((g, arena.flat), out + f".{rank}")
     finally:
         dist.destroy_process_group()
 
@@ -77,5 +102,18 @@ def test_gradient_exchange_world2_gloo(tmp_path):
     out = str(tmp_path / "g")
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     want = torch.arange(10, dtype=torch.float32) * 1.5     # mean of x1 and x2
+    base = torch.arange(12, dtype=torch.float32)
+    buf = torch.zeros(12, dtype=torch.bool)
+    buf[4:7] = True
+    buf[9:12] = True
     for r in range(2):
-        assert torch.allclose(torch.load(out + f".{r}"), want)
+        g, flat = torch.load(out + f".{r}")
+        assert torch.allclose(g, want)
+        assert torch.equal(flat[buf], base[buf])                      # buffers: rank 0's values everywhere
+        assert torch.equal(flat[~buf], base[~buf] + 100.0 * r)        # parameters: left alone
+
+
+def test_no_exchange_without_a_process_group():
+    eng = training.TrainEngine.__new__(training.TrainEngine)
+    eng.exchange = "auto"
+    assert eng._exchange() is None and eng.exchange == "auto"
