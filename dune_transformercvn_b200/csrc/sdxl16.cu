@@ -220,6 +220,25 @@ extern "C" int tcvn_sdxl16_groupnorm(const void* x_bf16, int n, int C, int H, in
   return TCVN_OK;
 }
 
+// stat[img] = (mean, rstd) of GroupNorm(1 group) over a ringed bf16 map, without the elementwise pass (the consumer applies
+// it on operand load: tcvn_sdxl16_conv2d_c64).  workspace: tcvn_sdxl16_groupnorm_workspace_bytes(n)
+extern "C" int tcvn_sdxl16_gn_stats(const void* x_bf16, int n, int C, int H, int W, float eps, void* out_stat, void* workspace,
+                                    size_t workspace_bytes, tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(x_bf16 && out_stat && workspace && n >= 0 && C > 0 && C % 8 == 0 && H > 0 && W > 0, "sdxl16_gn_stats: bad arguments");
+  if (n == 0) return TCVN_OK;
+  if (workspace_bytes < tcvn_sdxl16_groupnorm_workspace_bytes(n))
+    return fail(TCVN_ERR_WORKSPACE, "sdxl16_gn_stats: workspace %zu < %zu bytes", workspace_bytes, tcvn_sdxl16_groupnorm_workspace_bytes(n));
+  const long long vecs = (long long)(H + 2) * (W + 2) * C / 8;
+  int slabs = (int)ceil_div_ll(vecs, 256 * 8);
+  if (slabs > kGnSlabs) slabs = kGnSlabs;
+  double* parts = static_cast<double*>(workspace);
+  gn_stats16_kernel<<<dim3(slabs, n), 256, 0, stream>>>(static_cast<const bf*>(x_bf16), vecs, parts);
+  TCVN_LAUNCH_CHECK();
+  gn_finalize16_kernel<<<ceil_div(n, 128), 128, 0, stream>>>(parts, n, slabs, (double)H * W * C, eps, static_cast<float2*>(out_stat));
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
 extern "C" int tcvn_sdxl16_patch_s2(const void* x_bf16, int n, int C, int H, int W, void* out_bf16, tcvn_stream_t stream) {
   TCVN_CHECK_ARG(x_bf16 && out_bf16 && n >= 0 && C > 0 && C % 8 == 0 && H >= 2 && W >= 2, "sdxl16_patch_s2: bad arguments");
   if (n == 0) return TCVN_OK;

@@ -381,6 +381,20 @@ size_t tcvn_sdxl16_groupnorm_workspace_bytes(int n);
 int tcvn_sdxl16_groupnorm(const void* x_bf16, int n, int C, int H, int W, const float* gamma, const float* beta, float eps, int silu,
                           void* out_bf16, void* workspace, size_t workspace_bytes, tcvn_stream_t stream);
 int tcvn_sdxl16_patch_s2(const void* x_bf16, int n, int C, int H, int W, void* out_bf16, tcvn_stream_t stream);
+/* The 64 -> 64 channel 3x3 convolutions of the full-resolution stages (72 % of the network's FLOPs) as ONE fused tcgen05
+ * kernel over 2-D tiles (csrc/umma_conv2d.cu):  out = conv3x3(silu(GroupNorm(x))) + bias (+ residual).  A haloed 18 x 10 pixel
+ * patch is loaded once per 16 x 8 output tile through a 4-D tensor map, GroupNorm + SiLU are applied in place in shared
+ * memory, the nine taps are nine UMMA descriptors into that patch, and the epilogue takes the statistics of the NEXT
+ * GroupNorm from the values it stores (per-tile slots, fixed-order sum).
+ *   in_stat [n] float2 (mean, rstd) of x (tcvn_sdxl16_gn_stats, or a previous call's out_stat); gamma / beta [64]
+ *   w_bf16  [9*64][64]: row t*64 + n, column k = weight[n][k][t/3][t%3];  residual may be NULL
+ *   stat_parts (may be NULL): tcvn_sdxl16_conv2d_stat_bytes(n, H, W) of scratch; out_stat (may be NULL): [n] float2 of out */
+size_t tcvn_sdxl16_conv2d_stat_bytes(int n, int H, int W);
+int tcvn_sdxl16_conv2d_c64(const void* x_bf16, int n, int H, int W, const void* in_stat, const float* gamma, const float* beta,
+                           const void* w_bf16, const float* bias, const void* residual_bf16, void* out_bf16, void* stat_parts,
+                           void* out_stat, float eps, tcvn_stream_t stream);
+int tcvn_sdxl16_gn_stats(const void* x_bf16, int n, int C, int H, int W, float eps, void* out_stat, void* workspace,
+                         size_t workspace_bytes, tcvn_stream_t stream);
 int tcvn_sdxl16_to_f32(const void* x_bf16, int64_t count, float* out, tcvn_stream_t stream);
 int tcvn_sdxl16_conv(const void* a_bf16, int64_t rows, int a_cols, int n_taps, const int32_t* tap_off, const void* x2_bf16,
                      int x2_cols, const void* w_bf16, int n_tiles, const float* bias_padded, const float* ones_padded,

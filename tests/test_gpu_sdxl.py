@@ -196,3 +196,51 @@ def test_sdxl_bf16_forward_tracks_oracle(dev):
     print("sdxl bf16: embedding", e_emb, "event logits", e_ev, "prong logits", e_pr)
     assert e_emb < 5e-2 and e_ev < 2e-2 and e_pr < 2e-2
     assert torch.equal(got_ev.argmax(1).cpu(), want_ev.argmax(1))
+
+
+def test_sdxl16_conv2d_c64_fused_kernel_against_torch(dev):
+    """tcvn_sdxl16_conv2d_c64 (2-D tiles, GroupNorm + SiLU on operand load, residual + next-GroupNorm statistics in the
+    epilogue) against torch on odd-sized maps that need partial tiles in both directions and several images."""
+    import torch.nn.functional as F
+    from dune_transformercvn_b200 import lib as tl
+    L = tl.load()
+    st = tl.stream_ptr(dev)
+    g = torch.Generator().manual_seed(3)
+    c = 64
+    for n, h, w in ((3, 25, 17), (2, 50, 35)):
+        hp, wp = h + 2, w + 2
+        x = torch.randn(n, c, h, w, generator=g) * 1.5 + 0.3
+        res = torch.randn(n, c, h, w, generator=g)
+        wt = torch.randn(c, c, 3, 3, generator=g) * 0.05
+        b = torch.randn(c, generator=g)
+        gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g) * 0.3
+        x16, r16 = _ring16(x, dev), _ring16(res, dev)
+        xin = x16.float().cpu().view(n, hp, wp, c)[:, 1:-1, 1:-1].permute(0, 3, 1, 2)
+        rin = r16.float().cpu().view(n, hp, wp, c)[:, 1:-1, 1:-1].permute(0, 3, 1, 2)
+        # statistics of the input, by the library's own kernel
+        ws = torch.empty(L.tcvn_sdxl16_groupnorm_workspace_bytes(n), dtype=torch.uint8, device=dev)
+        stat_in = torch.empty(n, 2, device=dev)
+        tl.check(L.tcvn_sdxl16_gn_stats(tl.ptr(x16), n, c, h, w, 1e-6, tl.ptr(stat_in), tl.ptr(ws), ws.numel(), st), "gn_stats")
+        mean = xin.mean(dim=(1, 2, 3))
+        var = xin.var(dim=(1, 2, 3), unbiased=False)
+        assert rel_err(stat_in[:, 0].cpu(), mean) < 1e-4 and rel_err(stat_in[:, 1].cpu(), torch.rsqrt(var + 1e-6)) < 1e-4
+        wk = wt.permute(2, 3, 0, 1).reshape(9 * c, c).contiguous().to(dev).to(torch.bfloat16)
+        d_b, d_g, d_be = b.to(dev), gamma.to(dev), beta.to(dev)
+        parts = torch.empty(L.tcvn_sdxl16_conv2d_stat_bytes(n, h, w), dtype=torch.uint8, device=dev)
+        for with_res in (False, True):
+            out = torch.full((n * hp * wp, c), 7.0, dtype=torch.bfloat16, device=dev)      # poisoned: every row must be written
+            stat_out = torch.empty(n, 2, device=dev)
+            tl.check(L.tcvn_sdxl16_conv2d_c64(tl.ptr(x16), n, h, w, tl.ptr(stat_in), tl.ptr(d_g), tl.ptr(d_be), tl.ptr(wk), tl.ptr(d_b),
+                                              tl.ptr(r16) if with_res else None, tl.ptr(out), tl.ptr(parts), tl.ptr(stat_out), 1e-6, st),
+                     "conv2d_c64")
+            torch.cuda.synchronize()
+            a = F.silu(F.group_norm(xin, 1, gamma, beta, 1e-6)).bfloat16().float()
+            want = F.conv2d(a, wt.bfloat16().float(), b, padding=1) + (rin if with_res else 0.0)
+            got = _unring(out, n, h, w)
+            assert rel_err(got, want) < 2e-2, (n, h, w, with_res, rel_err(got, want))
+            ring = out.float().view(n, hp, wp, c)
+            assert float(ring[:, 0].abs().max()) == 0.0 and float(ring[:, -1].abs().max()) == 0.0
+            assert float(ring[:, :, 0].abs().max()) == 0.0 and float(ring[:, :, -1].abs().max()) == 0.0
+            o = got.bfloat16().float()
+            assert rel_err(stat_out[:, 0].cpu(), o.mean(dim=(1, 2, 3))) < 2e-3
+            assert rel_err(stat_out[:, 1].cpu(), torch.rsqrt(o.var(dim=(1, 2, 3), unbiased=False) + 1e-6)) < 2e-3
