@@ -182,6 +182,7 @@ class _SdxlCnn16(_SdxlCnn):
     def pack(self, tensors: Dict[str, torch.Tensor]) -> None:
         super().pack(tensors)     # fp32 GEMM layouts for the tail
         self.w16: Dict[str, Tuple[torch.Tensor, torch.Tensor, int, int]] = {}
+        self.w2d: Dict[str, Tuple[torch.Tensor, torch.Tensor]] = {}   # 64 -> 64 3x3 convs for the fused 2-D tile kernel
         dev = None
         raw = {n[len(self.prefix):]: t.detach().float() for n, t in tensors.items() if n.startswith(self.prefix)}
         dev = next(iter(raw.values())).device
@@ -216,6 +217,12 @@ class _SdxlCnn16(_SdxlCnn):
             for j in range(2):
                 p = f"{e}down_blocks.{i}.resnets.{j}."
                 c_in = cin if j == 0 else cout
+                if c_in == 64 and cout == 64:   # [9*64][64]: row t*64 + n, column k = weight[n][k][t/3][t%3]
+                    for cv in ("conv1", "conv2"):
+                        wt = raw[p + cv + ".weight"]
+                        self.w2d[p + cv] = (wt.permute(2, 3, 0, 1).reshape(9 * 64, 64).to(torch.bfloat16).contiguous(),
+                                            raw[p + cv + ".bias"].contiguous())
+                    continue
                 finish(p + "conv1", conv_k(raw[p + "conv1.weight"], c_in), raw[p + "conv1.bias"])
                 w2 = conv_k(raw[p + "conv2.weight"], cout)
                 if c_in != cout:   # 1x1 shortcut as the trailing K segment
@@ -242,6 +249,33 @@ class _SdxlCnn16(_SdxlCnn):
         _lib.check(L.tcvn_sdxl16_groupnorm(_lib.ptr(x), n, c, h, w_, _lib.ptr(self.w[name + ".weight"]), _lib.ptr(self.w[name + ".bias"]),
                                            GN_EPS, 1, _lib.ptr(out), _lib.ptr(ws), ws.numel(), st), "tcvn_sdxl16_groupnorm")
         return out
+
+    def _resnets_c64(self, L, st, block: str, x, n, h, w_, ws):
+        """The two ResNet blocks of a 64-channel stage on the fused 2-D tile kernel: GroupNorm + SiLU applied on operand load,
+        residual added and the next GroupNorm's statistics taken in the epilogue - four tensor-core launches, no activated
+        map, no separate statistics pass except at the stage's entry."""
+        dev = x.device
+        rows = n * (h + 2) * (w_ + 2)
+        stat = torch.empty((n, 2), dtype=torch.float32, device=dev)
+        _lib.check(L.tcvn_sdxl16_gn_stats(_lib.ptr(x), n, 64, h, w_, GN_EPS, _lib.ptr(stat), _lib.ptr(ws), ws.numel(), st),
+                   "tcvn_sdxl16_gn_stats")
+        parts = torch.empty(L.tcvn_sdxl16_conv2d_stat_bytes(n, h, w_), dtype=torch.uint8, device=dev)
+        for j in range(2):
+            p = f"{block}resnets.{j}."
+            for cv, nm, res in (("conv1", "norm1", None), ("conv2", "norm2", x)):
+                wk, bias = self.w2d[p + cv]
+                out = torch.empty((rows, 64), dtype=torch.bfloat16, device=dev)
+                stat_out = torch.empty((n, 2), dtype=torch.float32, device=dev)
+                _lib.check(L.tcvn_sdxl16_conv2d_c64(_lib.ptr(x if cv == "conv1" else t), n, h, w_, _lib.ptr(stat),
+                                                    _lib.ptr(self.w[p + nm + ".weight"]), _lib.ptr(self.w[p + nm + ".bias"]),
+                                                    _lib.ptr(wk), _lib.ptr(bias), _lib.ptr(res), _lib.ptr(out), _lib.ptr(parts),
+                                                    _lib.ptr(stat_out), GN_EPS, st), "tcvn_sdxl16_conv2d_c64")
+                if cv == "conv1":
+                    t = out
+                else:
+                    x = out
+                stat = stat_out
+        return x
 
     def forward(self, pixels: torch.Tensor) -> torch.Tensor:
         n = pixels.shape[0]
@@ -274,7 +308,9 @@ class _SdxlCnn16(_SdxlCnn):
         for i, cout in enumerate(self.ch[:-1]):
             hp, wp = h + 2, w_ + 2
             rows = n * hp * wp
-            for j in range(2):
+            if cin == 64 and cout == 64:
+                x = self._resnets_c64(L, st, f"{e}down_blocks.{i}.", x, n, h, w_, ws)
+            for j in range(2 if not (cin == 64 and cout == 64) else 0):
                 p = f"{e}down_blocks.{i}.resnets.{j}."
                 c_in = cin if j == 0 else cout
                 a = self._norm16(L, st, p + "norm1", x, n, h, w_, c_in, ws)
