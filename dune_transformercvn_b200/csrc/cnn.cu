@@ -35,16 +35,17 @@ struct Walk {
   bool values_u8 = false;
   float divisor = 0.f;
   void* bins = nullptr;  // scratch of the binned COO stem (present when the caller sized the workspace with the nnz-aware query)
+  int n_binned = 0;      // images / hits the bins were built for (the whole call)
+  long long nnz_binned = 0;
 
   int stem(int i0, int n) {
     const tcvn_cnn_desc& d = P.d;
     const size_t img_floats = (size_t)d.in_channels * d.height * d.width;
     const BlockPlan& B0 = P.blocks[0];
     if (pixels == nullptr && bins != nullptr)
-      return launch_stem_coo_binned(coords, values, values_u8, reinterpret_cast<const long long*>(ws + P.ws_hitofs), i0, divisor,
-                                    n, d.in_channels, d.height, d.width, pf(pk, P.p_w0), pf(pk, P.p_s_scale),
-                                    pf(pk, P.p_s_shift), pf(pk, P.p_s_alpha), d.init_features, ws + B0.ws_blk, B0.ctot, B0.H,
-                                    B0.W, f32, bins, st);
+      return launch_stem_coo_binned(i0, n, n_binned, nnz_binned, d.in_channels, d.height, d.width, pf(pk, P.p_w0),
+                                    pf(pk, P.p_s_scale), pf(pk, P.p_s_shift), pf(pk, P.p_s_alpha), d.init_features,
+                                    ws + B0.ws_blk, B0.ctot, B0.H, B0.W, f32, bins, st);
     if (pixels == nullptr)
       return launch_stem_coo(coords, values, values_u8, reinterpret_cast<const long long*>(ws + P.ws_hitofs), i0, divisor,
                              n, d.in_channels, d.height, d.width, pf(pk, P.p_w0), pf(pk, P.p_s_scale),
@@ -179,10 +180,15 @@ extern "C" int tcvn_cnn_forward_sparse(const tcvn_cnn_desc* d, tcvn_precision pr
   w.coords = coords; w.values = values; w.values_u8 = value_dtype == TCVN_VAL_U8; w.divisor = divisor;
   {
     const size_t base = align_up(P.ws_bytes, 1024);
-    const size_t extra = stem_bins_bytes(P.blocks[0].chunk, P.blocks[0].H, P.blocks[0].W, nnz);
-    if (workspace_bytes >= base + extra && nnz < (1ll << 29) && !getenv("TCVN_STEM_UNBINNED")) w.bins = w.ws + base;
+    const size_t extra = stem_bins_bytes(n_images, P.blocks[0].H, P.blocks[0].W, nnz);
+    if (workspace_bytes >= base + extra && nnz < (1ll << 28) && !getenv("TCVN_STEM_UNBINNED")) w.bins = w.ws + base;
   }
   TCVN_TRY(launch_hit_offsets(coords, nnz, n_images, reinterpret_cast<long long*>(w.ws + P.ws_hitofs), stream));
+  if (w.bins) {
+    w.n_binned = n_images; w.nnz_binned = nnz;
+    TCVN_TRY(launch_stem_bin(coords, values, w.values_u8, reinterpret_cast<const long long*>(w.ws + P.ws_hitofs), n_images, nnz,
+                             d->in_channels, divisor, d->height, d->width, P.blocks[0].H, P.blocks[0].W, w.bins, stream));
+  }
   const int last = (int)P.blocks.size() - 1;
   const int top = P.blocks[last].chunk;
   for (int i0 = 0; i0 < n_images; i0 += top) {
@@ -196,7 +202,7 @@ extern "C" int tcvn_cnn_forward_sparse(const tcvn_cnn_desc* d, tcvn_precision pr
 extern "C" size_t tcvn_cnn_workspace_bytes_sparse(const tcvn_cnn_desc* d, tcvn_precision prec, int n_images, int64_t nnz) {
   CnnPlan P;
   if (!d || nnz < 0 || !CnnPlan::build(*d, prec, n_images, &P)) { set_error("cnn: bad descriptor"); return 0; }
-  return align_up(P.ws_bytes, 1024) + stem_bins_bytes(P.blocks[0].chunk, P.blocks[0].H, P.blocks[0].W, nnz);
+  return align_up(P.ws_bytes, 1024) + stem_bins_bytes(n_images, P.blocks[0].H, P.blocks[0].W, nnz);
 }
 
 extern "C" int tcvn_cnn_run_layer(const tcvn_cnn_desc* d, tcvn_precision prec, const void* packed, void* workspace,

@@ -35,12 +35,14 @@ int launch_stem_coo(const int32_t* coords, const void* values, bool values_u8, c
                     float divisor, int n, int cin, int H, int W, const float* w0, const float* s_scale,
                     const float* s_shift, const float* s_alpha, int c0, void* blk, int ldo, int Hb, int Wb, bool f32,
                     cudaStream_t stream);
-// binned variant: hits are first binned by tile (order-preserving), empty tiles only store the constant
+// binned variant (stem_coo.cu): the hits of ALL images of a call are binned once by 4 x 4-pooled-pixel tile
+// (order-preserving), then every block-0 chunk runs the warp-per-tile kernel over its images
 size_t stem_bins_bytes(int n_images, int Hb, int Wb, long long nnz);
-int launch_stem_coo_binned(const int32_t* coords, const void* values, bool values_u8, const long long* image_offsets, int image0,
-                           float divisor, int n, int cin, int H, int W, const float* w0, const float* s_scale,
-                           const float* s_shift, const float* s_alpha, int c0, void* blk, int ldo, int Hb, int Wb, bool f32,
-                           void* bins, cudaStream_t stream);
+int launch_stem_bin(const int32_t* coords, const void* values, bool values_u8, const long long* image_offsets, int n_images,
+                    long long nnz, int cin, float divisor, int H, int W, int Hb, int Wb, void* bins, cudaStream_t stream);
+int launch_stem_coo_binned(int image0, int n, int n_images_binned, long long nnz_binned, int cin, int H, int W, const float* w0,
+                           const float* s_scale, const float* s_shift, const float* s_alpha, int c0, void* blk, int ldo, int Hb,
+                           int Wb, bool f32, const void* bins, cudaStream_t stream);
 // transition front half: BN + PReLU + AvgPool2d(2,2) of a ringed block buffer into a ringed buffer of the next geometry
 int launch_act_pool2(const void* blk, int n, int H, int W, int ld, int c, const float* scale, const float* shift,
                      const float* alpha, void* out, int H2, int W2, bool f32, cudaStream_t stream);

@@ -178,7 +178,7 @@ __device__ __forceinline__ void stem_pool(const float* acc, const int* touched, 
   float c_pool = 0.f;
 #pragma unroll
   for (int k = 0; k < 9; ++k) c_pool += c_act;
-  c_pool /= 9.0f;
+  c_pool = pool_avg9<TO>(c_pool);
   if (t < C0) pool_const[t] = from_f32<TO>(c_pool);
   if (t < 32) {  // one warp classifies the 64 pooled pixels (2 per lane) and compacts the reached ones in order
     int cnt = 0;
@@ -226,7 +226,7 @@ __device__ __forceinline__ void stem_pool(const float* acc, const int* touched, 
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) s2 += prelu(fmaf(acc[(base + dy * kStemTC + dx) * C0 + ch], sc, sh), al);
     const size_t row = (size_t)n * (Hb + 2) * (Wb + 2) + (size_t)(py0 + pyl + 1) * (Wb + 2) + (px0 + pxl + 1);
-    blk[row * ldo + ch] = from_f32<TO>(s2 / 9.0f);
+    blk[row * ldo + ch] = from_f32<TO>(pool_avg9<TO>(s2));
   }
 }
 
@@ -441,231 +441,6 @@ __global__ void __launch_bounds__(kStemThreads, 2) stem_coo_kernel(const int32_t
     stem_scatter_pool<TO, C0, true>(w0, acc, hits, base < kCap ? base : kCap, touched, cin, sc, sh, al, ch, own_py, own_px, t, n,
                                     py0, px0, blk, ldo, Hb, Wb);
   }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Binned COO stem.  stem_coo_kernel makes every one of the 117 tiles of an image walk the image's whole hit list
-// (2 barriers per 512 hits) and zero its 74 KB of accumulators even when no hit falls into its window.  Here the
-// hits are first binned by tile - one thread per tile walks the image's hits IN ORDER, so every bin keeps the
-// order of the hit list and the result stays bit-identical - and the tile loop reads only its own bin; a tile
-// with an empty bin skips the accumulator pass and only stores the per-channel constant.
-//   tile_count / tile_start: [n_images * tiles_per_image (+1)] int32;  tile_hits: hit indices, <= 4 per hit
-// ------------------------------------------------------------------------------------------------
-constexpr int kBinChunk = 256;
-constexpr int kHitBuf = 256;   // hit records staged per tile and buffer (two buffers: the next tile's arrive under this tile's work)
-
-// FILL = false: count the hits of every tile window.  FILL = true: write the tile's hit RECORDS
-// (window-relative position code, the up-to-3 values already divided) in hit-list order.
-template <bool FILL, typename V>
-__global__ void __launch_bounds__(128) stem_bin_kernel(const int32_t* __restrict__ coords, const V* __restrict__ values,
-                                                       const long long* __restrict__ image_offsets, int image0, int cin,
-                                                       float divisor, int H, int W, int tiles_x, int tiles_y,
-                                                       int32_t* __restrict__ tile_count, const int32_t* __restrict__ tile_start,
-                                                       float4* __restrict__ tile_recs) {
-  __shared__ int sy[kBinChunk], sx[kBinChunk];
-  __shared__ float sv[FILL ? kBinChunk : 1][3];
-  const int n = blockIdx.x;
-  const int per_image = tiles_x * tiles_y;
-  const long long lo = __ldg(image_offsets + image0 + n), hi = __ldg(image_offsets + image0 + n + 1);
-  for (int tile0 = 0; tile0 < per_image; tile0 += blockDim.x) {
-    const int tile = tile0 + threadIdx.x;
-    const bool live = tile < per_image;
-    const int iy0 = live ? 4 * (tile / tiles_x) * kStemTP - 3 : 0, ix0 = live ? 4 * (tile % tiles_x) * kStemTP - 3 : 0;
-    int cnt = 0;
-    float4* out = (FILL && live) ? tile_recs + tile_start[(size_t)n * per_image + tile] : nullptr;
-    for (long long h0 = lo; h0 < hi; h0 += kBinChunk) {
-      __syncthreads();
-      for (int k = threadIdx.x; k < kBinChunk; k += blockDim.x) {
-        const long long h = h0 + k;
-        int y = -100000, x = -100000;
-        if (h < hi) { y = __ldg(coords + 3 * h + 1); x = __ldg(coords + 3 * h + 2); }
-        if (y < 0 || y >= H || x < 0 || x >= W) { y = -100000; x = -100000; }   // out-of-map hits are dropped, as in stem_coo_kernel
-        sy[k] = y; sx[k] = x;
-        if (FILL) {
-#pragma unroll
-          for (int c = 0; c < 3; ++c) {
-            float val = 0.f;
-            if (h < hi && c < cin) {
-              val = static_cast<float>(values[h * cin + c]);
-              if (divisor != 0.f) val = __fdiv_rn(val, divisor);  // same bits as the reference's v / 255.0
-            }
-            sv[k][c] = val;
-          }
-        }
-      }
-      __syncthreads();
-      if (live) {
-        const int m = (int)(hi - h0 < kBinChunk ? hi - h0 : kBinChunk);
-        for (int k = 0; k < m; ++k) {
-          const unsigned yy = (unsigned)(sy[k] - iy0), xx = (unsigned)(sx[k] - ix0);
-          if (yy < (unsigned)kStemIn && xx < (unsigned)kStemIn) {
-            if (FILL) out[cnt] = make_float4(__int_as_float((int)(yy * 64 + xx)), sv[k][0], sv[k][1], sv[k][2]);
-            ++cnt;
-          }
-        }
-      }
-    }
-    if (!FILL && live) tile_count[(size_t)n * per_image + tile] = cnt;
-  }
-}
-
-// exclusive scan of n int32 counts by one block (n is a few hundred thousand at most)
-__global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __restrict__ counts, int n, int32_t* __restrict__ start) {
-  __shared__ int part[1024];
-  const int t = threadIdx.x;
-  const int per = (n + 1023) / 1024;
-  const int b = t * per, e = min(n, b + per);
-  int s = 0;
-  for (int i = b; i < e; ++i) s += counts[i];
-  part[t] = s;
-  __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {
-    const int v = t >= off ? part[t - off] : 0;
-    __syncthreads();
-    part[t] += v;
-    __syncthreads();
-  }
-  int run = part[t] - s;
-  for (int i = b; i < e; ++i) { start[i] = run; run += counts[i]; }
-  if (t == 1023) start[n] = part[1023];
-}
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src)
-               : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// The tile loop is a chain of short, dependent phases; what it must never do is wait for global memory.  The bin
-// bounds of the tile after next are loaded into registers and the records of the NEXT tile are copied into the second
-// staging buffer (cp.async) while this tile scatters and pools, so a tile starts with its hits already in shared memory.
-template <typename TO, int C0>
-__global__ void __launch_bounds__(kStemThreads, 2) stem_coo_binned_kernel(const int32_t* __restrict__ tile_start,
-                                                                          const float4* __restrict__ tile_recs,
-                                                                          int n_images, int cin, const float* __restrict__ w0,
-                                                                          const float* __restrict__ s_scale,
-                                                                          const float* __restrict__ s_shift,
-                                                                          const float* __restrict__ s_alpha,
-                                                                          TO* __restrict__ blk, int ldo, int Hb, int Wb) {
-  extern __shared__ __align__(16) float smem[];
-  float* acc = smem;                                  // [289][C0]
-  float4* hitbuf = reinterpret_cast<float4*>(acc + kStemTC * kStemTC * C0);  // [2][kHitBuf] (packed yx, v0, v1, v2)
-  __shared__ int touched[kStemTC * kStemTC];
-  const int tiles_x = (Wb + kStemTP - 1) / kStemTP, tiles_y = (Hb + kStemTP - 1) / kStemTP;
-  const int per_image = tiles_x * tiles_y;
-  const long long total = (long long)n_images * per_image;
-  const int t = threadIdx.x;
-  const int ch = t & (C0 - 1);
-  const int own_px = (t >> 6) & 1, own_py = t >> 7;
-  const float sc = __ldg(s_scale + ch), sh = __ldg(s_shift + ch), al = __ldg(s_alpha + ch);
-  constexpr int kCap = kStemIn * kStemIn;
-  const long long stride = gridDim.x;
-  long long tile = blockIdx.x;
-  if (tile >= total) return;
-  // bin bounds of this tile and the next one; records of this tile -> buffer 0
-  int b0 = __ldg(tile_start + tile), e0 = __ldg(tile_start + tile + 1);
-  int b1 = 0, e1 = 0;
-  if (tile + stride < total) { b1 = __ldg(tile_start + tile + stride); e1 = __ldg(tile_start + tile + stride + 1); }
-  if (t < min(e0 - b0, kHitBuf)) cp_async16(hitbuf + t, tile_recs + b0 + t);
-  cp_async_commit();
-  int cur = 0;
-  for (; tile < total; tile += stride) {
-    const int n = (int)(tile / per_image);
-    const int rem = (int)(tile - (long long)n * per_image);
-    const int py0 = (rem / tiles_x) * kStemTP, px0 = (rem % tiles_x) * kStemTP;
-    int cnt = e0 - b0;
-    if (cnt > kCap) cnt = kCap;
-    // bounds of the tile after next (consumed one iteration later), records of the next tile -> the other buffer
-    int b2 = 0, e2 = 0;
-    if (tile + 2 * stride < total) { b2 = __ldg(tile_start + tile + 2 * stride); e2 = __ldg(tile_start + tile + 2 * stride + 1); }
-    __syncthreads();  // previous tile fully consumed (its staging buffer, acc, touched)
-    if (t < min(e1 - b1, kHitBuf)) cp_async16(hitbuf + (cur ^ 1) * kHitBuf + t, tile_recs + b1 + t);
-    cp_async_commit();
-    if (t < kStemTC * kStemTC) touched[t] = 0;
-    if (cnt > 0) {
-      float4* a4 = reinterpret_cast<float4*>(acc);
-      for (int i = t; i < kStemTC * kStemTC * C0 / 4; i += blockDim.x) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    cp_async_wait<1>();   // this tile's records (committed one iteration ago) have landed
-    __syncthreads();
-    if (cnt > 0) {
-      float4* hb = hitbuf + cur * kHitBuf;
-      stem_scatter<C0, true>(w0, acc, hb, min(cnt, kHitBuf), touched, cin, ch, own_py, own_px);
-      for (int done = kHitBuf; done < cnt; done += kHitBuf) {   // dense windows only: further chunks, loaded in place
-        __syncthreads();
-        const int m = min(cnt - done, kHitBuf);
-        if (t < m) hb[t] = __ldg(tile_recs + b0 + done + t);
-        __syncthreads();
-        stem_scatter<C0, true>(w0, acc, hb, m, touched, cin, ch, own_py, own_px);
-      }
-    }
-    __syncthreads();
-    stem_pool<TO, C0>(acc, touched, sc, sh, al, ch, t, n, py0, px0, blk, ldo, Hb, Wb);
-    b0 = b1; e0 = e1; b1 = b2; e1 = e2;
-    cur ^= 1;
-  }
-  cp_async_wait<0>();
-}
-
-size_t stem_bins_bytes(int n_images, int Hb, int Wb, long long nnz) {
-  const size_t tiles = (size_t)n_images * ((Wb + kStemTP - 1) / kStemTP) * ((Hb + kStemTP - 1) / kStemTP);
-  return align_up((tiles + 1) * sizeof(int32_t), 256) * 2 + align_up((size_t)(4 * nnz + 4) * sizeof(float4), 256);
-}
-
-// same contract as launch_stem_coo; bins = scratch of stem_bins_bytes(n, Hb, Wb, nnz of these images) bytes
-int launch_stem_coo_binned(const int32_t* coords, const void* values, bool values_u8, const long long* image_offsets, int image0,
-                           float divisor, int n, int cin, int H, int W, const float* w0, const float* s_scale,
-                           const float* s_shift, const float* s_alpha, int c0, void* blk, int ldo, int Hb, int Wb, bool f32,
-                           void* bins, cudaStream_t stream) {
-  if (c0 != 64) return fail(TCVN_ERR_UNSUPPORTED, "stem: init_features %d (kernel is specialised for 64)", c0);
-  if (n == 0) return TCVN_OK;
-  const int Hs = (H + 6 - 7) / 2 + 1, Ws = (W + 6 - 7) / 2 + 1;
-  if ((Hs - 3) / 2 + 1 != Hb || (Ws - 3) / 2 + 1 != Wb) return fail(TCVN_ERR_ARG, "stem: geometry mismatch");
-  if (cin > 3) return fail(TCVN_ERR_UNSUPPORTED, "stem: %d input channels (kernel handles up to 3)", cin);
-  const int tiles_x = (Wb + kStemTP - 1) / kStemTP, tiles_y = (Hb + kStemTP - 1) / kStemTP;
-  const long long tiles = (long long)n * tiles_x * tiles_y;
-  if (tiles >= (1ll << 31) - 2048) return fail(TCVN_ERR_UNSUPPORTED, "stem: too many tiles in one chunk");
-  char* b = static_cast<char*>(bins);
-  int32_t* tile_count = reinterpret_cast<int32_t*>(b);
-  int32_t* tile_start = reinterpret_cast<int32_t*>(b + align_up((size_t)(tiles + 1) * sizeof(int32_t), 256));
-  float4* tile_recs = reinterpret_cast<float4*>(b + 2 * align_up((size_t)(tiles + 1) * sizeof(int32_t), 256));
-#define TCVN_STEM_BINS(V)                                                                                                       \
-  do {                                                                                                                          \
-    const V* vals = static_cast<const V*>(values);                                                                              \
-    stem_bin_kernel<false, V><<<n, 128, 0, stream>>>(coords, vals, image_offsets, image0, cin, divisor, H, W, tiles_x, tiles_y, \
-                                                      tile_count, nullptr, nullptr);                                            \
-    TCVN_LAUNCH_CHECK();                                                                                                        \
-    scan_counts_kernel<<<1, 1024, 0, stream>>>(tile_count, (int)tiles, tile_start);                                            \
-    TCVN_LAUNCH_CHECK();                                                                                                        \
-    stem_bin_kernel<true, V><<<n, 128, 0, stream>>>(coords, vals, image_offsets, image0, cin, divisor, H, W, tiles_x, tiles_y,  \
-                                                     tile_count, tile_start, tile_recs);                                        \
-    TCVN_LAUNCH_CHECK();                                                                                                        \
-  } while (0)
-  if (values_u8) TCVN_STEM_BINS(uint8_t);
-  else TCVN_STEM_BINS(float);
-#undef TCVN_STEM_BINS
-  const size_t smem = (size_t)kStemTC * kStemTC * c0 * sizeof(float) + (size_t)2 * kHitBuf * sizeof(float4);
-  int sms = 148;
-  {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
-  const int grid = (int)(tiles < 2ll * sms ? tiles : 2ll * sms);
-#define TCVN_STEM_BIN(TO)                                                                                                  \
-  do {                                                                                                                     \
-    TCVN_CUDA(cudaFuncSetAttribute(stem_coo_binned_kernel<TO, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    TCVN_CUDA(cudaFuncSetAttribute(stem_coo_binned_kernel<TO, 64>, cudaFuncAttributePreferredSharedMemoryCarveout,          \
-                                   (int)cudaSharedmemCarveoutMaxShared));                                                  \
-    stem_coo_binned_kernel<TO, 64><<<grid, kStemThreads, smem, stream>>>(tile_start, tile_recs, n, cin, w0, s_scale, s_shift, \
-                                                                         s_alpha, static_cast<TO*>(blk), ldo, Hb, Wb);      \
-  } while (0)
-  if (f32) TCVN_STEM_BIN(float);
-  else TCVN_STEM_BIN(__nv_bfloat16);
-#undef TCVN_STEM_BIN
-  TCVN_LAUNCH_CHECK();
-  return TCVN_OK;
 }
 
 int launch_hit_offsets(const int32_t* coords, long long nnz, int n_images, long long* offsets, cudaStream_t stream) {

@@ -11,6 +11,14 @@ constexpr int kStemIn = 2 * kStemTC + 5;     // 39 input pixels per edge
 constexpr int kStemThreads = 512;            // (cy mod 4) x (cx mod 2) x 64 channels
 constexpr int kStemRows = kStemIn;           // window rows (pixels, all channels together)
 
+// AvgPool2d(3, 2) divides the window sum by 9.  fp32 path: the reference's division.  bf16 path: the product with 1/9
+// (at most one fp32 ulp away, far below the bf16 rounding that follows; a division is ~10 instructions per value).
+template <typename TO> __device__ __forceinline__ float pool_avg9(float s) { return s / 9.0f; }
+template <> __device__ __forceinline__ float pool_avg9<__nv_bfloat16>(float s) { return s * (1.0f / 9.0f); }
+template <typename TO> __device__ __forceinline__ float2 pool_avg9(float2 s) {
+  return make_float2(pool_avg9<TO>(s.x), pool_avg9<TO>(s.y));
+}
+
 // Phases (2)-(4) of the stem for one tile, shared by the dense-window and the COO-direct kernels: scatter the
 // compacted hits, then bias+BN0+PReLU0 and AvgPool2d(3, 2) into the ringed block buffer.
 template <int C0, bool WGLOBAL>
