@@ -17,8 +17,11 @@
 //     nine times, so the transform costs 23 KB per tile): the activated map is never materialised; pixels outside the
 //     image (the conv's zero padding) are forced to zero AFTER the activation;
 //   * the epilogue adds bias and the ResNet block's residual input, writes zeros on the ring, and takes the NEXT
-//     GroupNorm's statistics from the values it stores: (sum, sum^2) per tile in a fixed slot (added in a fixed order by
-//     gn_tiles_finalize_kernel: bit-reproducible, no atomics).
+//     GroupNorm's statistics from the fp32 values it is about to round: (sum, sum^2) per tile in a fixed slot (added in a
+//     fixed order by gn_tiles_finalize_kernel: bit-reproducible, no atomics).
+// The SIMT side is what bounds the kernel (ncu, profiles/r2_sdxl_conv2d_c64*.txt): the transform and the epilogue work in
+// packed fp32 pairs (FFMA2 / FADD2), SiLU costs one MUFU (tanh.approx) instead of two, and everything that does not depend
+// on the tile (patch-row coordinates, swizzled slots) is hoisted out of the tile loop.
 // A ResNet block of the 64-channel stages is therefore two launches of this kernel and two tiny finalize launches.
 #include "ptx.cuh"
 #include "umma.h"
@@ -38,7 +41,8 @@ constexpr int kStages = 4;
 constexpr int kC = 64;                                // channels in = channels out
 constexpr int kWTap = kC * 128;                       // one filter tap: [64 n][64 k] bf16 = 8 KB
 constexpr int kWBytes = 9 * kWTap;                    // 72 KB
-constexpr int kThreads = 576;                         // warp 0 TMA, warp 1 MMA, warps 2-9 transform, warps 10-17 two epilogue groups
+constexpr int kThreads = 608;                         // warp 0 TMA, warp 1 MMA, warps 2-9 transform, warps 10-17 two epilogue groups, warp 18 residual TMA
+constexpr int kOutBytes = kTY * kTX * 128;            // one output / residual tile: 128 pixels x 128 bytes
 constexpr int kXform = 256;
 constexpr uint32_t kDescHiPatch = ((uint32_t)(kPX * 128) >> 4) | (1u << 14) | (2u << 29);   // SBO = 1280 B | version | SWIZZLE_128B
 
@@ -48,8 +52,7 @@ struct Conv2dParams {
   const float* bias;                 // [64]
   const float2* in_stat;             // [n_img] (mean, rstd) of the input's GroupNorm
   const float* gamma; const float* beta;   // [64]
-  const bf16* residual;              // optional [n_img * Hp * Wp][64]
-  bf16* out;                         // [n_img * Hp * Wp][64]
+  int has_residual;                  // the residual map is read through tmR
   double* stat_parts;                // optional [num_tiles][2]
 };
 
@@ -59,25 +62,39 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
-__device__ __forceinline__ float silu(float v) { return __fdividef(v, 1.f + __expf(-v)); }
+__device__ __forceinline__ float tanh_approx(float v) {
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(v));
+  return t;
+}
+// silu(y) = y * sigmoid(y) = h + h * tanh(h), h = y / 2: one MUFU per value instead of two (ex2 + rcp); tanh.approx is good
+// to 2^-11 relative, i.e. the result is within 2.4e-4 |y| - a sixteenth of the bf16 rounding that follows
+__device__ __forceinline__ float2 silu_half2(float2 h) {
+  return __ffma2_rn(h, make_float2(tanh_approx(h.x), tanh_approx(h.y)), h);
+}
 
 __global__ void __launch_bounds__(kThreads, 1) umma_conv2d_c64_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                       const __grid_constant__ CUtensorMap tmW,
+                                                                      const __grid_constant__ CUtensorMap tmR,
+                                                                      const __grid_constant__ CUtensorMap tmO,
                                                                       const Conv2dParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = smem;                                   // [9][64 n x 128 B]
   uint8_t* sA = smem + kWBytes;                         // [stages][180 rows x 128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + kStages * kStageStride);
+  uint8_t* sO = sA + kStages * kStageStride;            // [2 epilogue groups][128 pixels x 128 B]: residual in, result out
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sO + 2 * kOutBytes);
   uint64_t* full = bars;                     // TMA -> transform
   uint64_t* ready = bars + kStages;          // transform -> MMA
   uint64_t* empty = bars + 2 * kStages;      // MMA -> TMA
   uint64_t* tfull = bars + 3 * kStages;      // MMA -> epilogue [2]
   uint64_t* tempty = tfull + 2;              // epilogue -> MMA [2]
   uint64_t* wfull = tempty + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
-  float* s_stat = reinterpret_cast<float*>(tmem_slot + 2);   // [2 groups][4 warps][2]
-  float* s_bias = s_stat + 16;                                // [64]
+  uint64_t* rfull = wfull + 1;               // residual TMA -> epilogue [2]
+  uint64_t* rempty = rfull + 2;              // epilogue (tile stored) -> residual TMA [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rempty + 2);
+  float* s_stat = reinterpret_cast<float*>(tmem_slot + 2);   // [2 tile parities][2 groups][4 warps][2]
+  float* s_bias = s_stat + 32;                                // [64]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -86,11 +103,16 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv2d_c64_kernel(const __gr
       ptx::mbar_init(&ready[s], kXform);
       ptx::mbar_init(&empty[s], 1);
     }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 128); }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 128);
+      ptx::mbar_init(&rfull[a], 1); ptx::mbar_init(&rempty[a], 1);
+    }
     ptx::mbar_init(wfull, 1);
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tmX);
     ptx::prefetch_tmap(&tmW);
+    ptx::prefetch_tmap(&tmR);
+    ptx::prefetch_tmap(&tmO);
   }
   if (threadIdx.x < kC) s_bias[threadIdx.x] = p.bias[threadIdx.x];
   if (warp == 0) ptx::tmem_alloc(tmem_slot, 128);
@@ -142,50 +164,96 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv2d_c64_kernel(const __gr
         if ((acc ^= 1) == 0) acc_phase ^= 1;
       }
     }
+  } else if (warp == 18) {
+    // residual tiles -> the epilogue groups' staging buffers (the buffer is free once the previous tile's TMA store has read it)
+    if (lane == 0) {
+      uint32_t ph[2] = {0u, 0u};
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+        const int grp = it & 1;
+        const int img = tile / per_img, rem = tile - img * per_img;
+        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        ptx::mbar_wait(&rempty[grp], ph[grp] ^ 1);
+        if (p.has_residual) {
+          ptx::mbar_arrive_expect_tx(&rfull[grp], kOutBytes);
+          ptx::tma_load_4d(sO + grp * kOutBytes, &tmR, &rfull[grp], 0, tx * kTX, ty * kTY, img);
+        } else {
+          ptx::mbar_arrive(&rfull[grp]);
+        }
+        ph[grp] ^= 1;
+      }
+    }
   } else if (warp < 10) {
     // GroupNorm + SiLU in place.  Thread t owns channel group cg = t & 7 (its gamma / beta stay in registers) on patch rows
     // (t >> 3) + 32 k; under the 128B swizzle those channels sit at 16-byte position cg ^ (row & 7): a warp touches four whole
     // rows per step, conflict-free.
     const int t = threadIdx.x - 64;
     const int cg = t & 7, r0 = t >> 3;
-    float ga[8], be[8];
+    float2 ga[4], be[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { ga[i] = __ldg(p.gamma + cg * 8 + i); be[i] = __ldg(p.beta + cg * 8 + i); }
+    for (int i = 0; i < 4; ++i) {
+      ga[i] = make_float2(__ldg(p.gamma + cg * 8 + 2 * i), __ldg(p.gamma + cg * 8 + 2 * i + 1));
+      be[i] = make_float2(__ldg(p.beta + cg * 8 + 2 * i), __ldg(p.beta + cg * 8 + 2 * i + 1));
+    }
+    // this thread's patch rows r0 + 32 k never change: (py, px) and the swizzled 16-byte slot of each are loop constants
+    constexpr int kIter = (kPatchRows + 31) / 32;
+    int pyx[kIter], slot[kIter];
+#pragma unroll
+    for (int k = 0; k < kIter; ++k) {
+      const int r = r0 + 32 * k;
+      pyx[k] = r < kPatchRows ? ((r / kPX) << 8) | (r % kPX) : -1;
+      slot[k] = r * 128 + ((cg ^ (r & 7)) << 4);
+    }
     int stage = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+    int tile = blockIdx.x;
+    float2 st = tile < p.num_tiles ? __ldg(p.in_stat + tile / per_img) : make_float2(0.f, 0.f);
+    for (; tile < p.num_tiles; tile += gridDim.x) {
       const int img = tile / per_img, rem = tile - img * per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-      const float2 st = __ldg(p.in_stat + img);
-      float sc[8], sh[8];
+      // (mean, rstd) of the NEXT tile's image is fetched under this tile's work
+      const int nxt = tile + gridDim.x;
+      const float2 st_next = nxt < p.num_tiles ? __ldg(p.in_stat + nxt / per_img) : make_float2(0.f, 0.f);
+      float2 hsc[4], hsh[4];   // y / 2 = v * hsc + hsh
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { sc[i] = st.y * ga[i]; sh[i] = fmaf(-st.x, sc[i], be[i]); }
+      for (int i = 0; i < 4; ++i) {
+        hsc[i] = make_float2(0.5f * st.y * ga[i].x, 0.5f * st.y * ga[i].y);
+        hsh[i] = make_float2(fmaf(-st.x, hsc[i].x, 0.5f * be[i].x), fmaf(-st.x, hsc[i].y, 0.5f * be[i].y));
+      }
+      const int y0 = ty * kTY - 1, x0 = tx * kTX - 1;          // ringed coordinates of the patch origin
       if (lane == 0) ptx::mbar_wait(&full[stage], phase);
       __syncwarp();
       uint8_t* base = sA + stage * kStageStride;
-      for (int r = r0; r < kPatchRows; r += 32) {
-        const int py = r / kPX, px = r - py * kPX;
-        const int yy = ty * kTY - 1 + py, xx = tx * kTX - 1 + px;       // ringed coordinates of this patch pixel
-        uint4* q = reinterpret_cast<uint4*>(base + r * 128 + ((cg ^ (r & 7)) << 4));
+#pragma unroll
+      for (int k = 0; k < kIter; ++k) {
+        if (pyx[k] < 0) continue;
+        const int yy = y0 + (pyx[k] >> 8), xx = x0 + (pyx[k] & 255);
+        uint4* q = reinterpret_cast<uint4*>(base + slot[k]);
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);       // ring / outside the image: the convolution's zero padding
         if (yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W) {
           const uint4 v = *q;
           const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-          uint32_t o[4];
+          uint32_t u[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            o[i] = pack2(silu(fmaf(bflo(w[i]), sc[2 * i], sh[2 * i])), silu(fmaf(bfhi(w[i]), sc[2 * i + 1], sh[2 * i + 1])));
-          *q = make_uint4(o[0], o[1], o[2], o[3]);
-        } else {
-          *q = make_uint4(0u, 0u, 0u, 0u);      // ring / outside the image: the convolution's zero padding
+          for (int i = 0; i < 4; ++i) {
+            const float2 y = silu_half2(__ffma2_rn(make_float2(bflo(w[i]), bfhi(w[i])), hsc[i], hsh[i]));
+            u[i] = pack2(y.x, y.y);
+          }
+          o = make_uint4(u[0], u[1], u[2], u[3]);
         }
+        *q = o;
       }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(&ready[stage]);
       if (++stage == kStages) { stage = 0; phase ^= 1; }
+      st = st_next;
     }
   } else {
     const int grp = (warp - 10) >> 2;   // epilogue group == TMEM accumulator it drains
     const int g = warp & 3;             // TMEM lane quarter this warp may read
     const int row = g * 32 + lane;      // pixel of the tile: (row >> 3, row & 7)
+    // this pixel's 128 bytes of the staging tile (128B-swizzled like every TMA tile): chunk j sits at j ^ (row & 7)
+    uint8_t* srow = sO + grp * kOutBytes + row * 128;
+    const int sw = row & 7;
     uint32_t acc_phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
@@ -193,70 +261,74 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv2d_c64_kernel(const __gr
       const int img = tile / per_img, rem = tile - img * per_img;
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       const int yy = ty * kTY + (row >> 3), xx = tx * kTX + (row & 7);
-      const bool inb = yy < p.Hp && xx < p.Wp;
       const bool interior = yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W;
-      const size_t prow = ((size_t)img * p.Hp + yy) * p.Wp + xx;
-      uint4 res[8];
-      if (p.residual != nullptr && interior) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + prow * kC);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) res[j] = __ldg(rp + j);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) res[j] = make_uint4(0u, 0u, 0u, 0u);
-      }
+      if (lane == 0) ptx::mbar_wait(&rfull[grp], acc_phase);   // staging tile free (and the residual landed in it)
+      __syncwarp();
       if (lane == 0) ptx::mbar_wait(&tfull[grp], acc_phase);
       __syncwarp();
       ptx::tc_fence_after();
-      uint32_t r0[32], r1[32];
-      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(g * 32) << 16) + grp * kC, r0);
-      ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(g * 32) << 16) + grp * kC + 32, r1);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive(&tempty[grp]);
-      float s1 = 0.f, s2 = 0.f;
-      uint4 o[8];
+      // bias + residual in packed fp32 pairs; the NEXT GroupNorm's statistics are taken from the fp32 values (the bf16
+      // rounding of the stored copy is zero-mean noise three orders below the variance).  Two halves of 32 channels keep
+      // the register footprint under the 96 this 19-warp CTA allows.
+      float2 s1 = make_float2(0.f, 0.f), s2 = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const uint32_t* r = j < 4 ? r0 : r1;
-        const int b = (j & 3) * 8;
-        const uint32_t rw[4] = {res[j].x, res[j].y, res[j].z, res[j].w};
-        uint32_t w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float lo = __uint_as_float(r[b + 2 * i]) + s_bias[j * 8 + 2 * i] + bflo(rw[i]);
-          const float hi = __uint_as_float(r[b + 2 * i + 1]) + s_bias[j * 8 + 2 * i + 1] + bfhi(rw[i]);
-          w[i] = interior ? pack2(lo, hi) : 0u;
-          const float a = bflo(w[i]), c = bfhi(w[i]);     // statistics of exactly the stored bf16 values
-          s1 += a + c;
-          s2 = fmaf(a, a, fmaf(c, c, s2));
+      for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(g * 32) << 16) + grp * kC + half * 32, r);
+        ptx::tmem_ld_wait();
+        if (half == 1) {
+          ptx::tc_fence_before();
+          ptx::mbar_arrive(&tempty[grp]);
         }
-        o[j] = make_uint4(w[0], w[1], w[2], w[3]);
-      }
-      if (inb) {
-        uint4* dst = reinterpret_cast<uint4*>(p.out + prow * kC);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) dst[j] = o[j];
+        for (int jj = 0; jj < 4; ++jj) {
+          const int j = half * 4 + jj;
+          uint4* slot = reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4));
+          const uint4 res = p.has_residual ? *slot : make_uint4(0u, 0u, 0u, 0u);
+          const uint32_t rw[4] = {res.x, res.y, res.z, res.w};
+          uint32_t w[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float2 v = make_float2(__uint_as_float(r[jj * 8 + 2 * i]), __uint_as_float(r[jj * 8 + 2 * i + 1]));
+            v = __fadd2_rn(v, *reinterpret_cast<const float2*>(s_bias + j * 8 + 2 * i));
+            v = __fadd2_rn(v, make_float2(bflo(rw[i]), bfhi(rw[i])));
+            w[i] = pack2(v.x, v.y);
+            s1 = __fadd2_rn(s1, v);
+            s2 = __ffma2_rn(v, v, s2);
+          }
+          // ring pixels store zeros; pixels beyond the map are clipped by the TMA store
+          *slot = interior ? make_uint4(w[0], w[1], w[2], w[3]) : make_uint4(0u, 0u, 0u, 0u);
+        }
       }
+      if (!interior) { s1 = make_float2(0.f, 0.f); s2 = make_float2(0.f, 0.f); }   // ... and count for nothing
+      float* stat_slot = s_stat + (((it >> 1) & 1) * 2 + grp) * 8;   // double-buffered by this group's tile parity
       if (p.stat_parts != nullptr) {   // warp-uniform
+        float t1 = s1.x + s1.y, t2 = s2.x + s2.y;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
-          s1 += __shfl_xor_sync(0xffffffffu, s1, d);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+          t1 += __shfl_xor_sync(0xffffffffu, t1, d);
+          t2 += __shfl_xor_sync(0xffffffffu, t2, d);
         }
-        ptx::named_bar_sync(1 + grp, 128);          // the previous tile's slot of this group has been consumed
-        if (lane == 0) { s_stat[(grp * 4 + g) * 2] = s1; s_stat[(grp * 4 + g) * 2 + 1] = s2; }
-        ptx::named_bar_sync(1 + grp, 128);
-        if (g == 0 && lane == 0) {
+        if (lane == 0) { stat_slot[g * 2] = t1; stat_slot[g * 2 + 1] = t2; }
+      }
+      ptx::fence_proxy_async_smem();              // the tile rows written above -> visible to the TMA store
+      ptx::named_bar_sync(1 + grp, 128);
+      if (g == 0 && lane == 0) {
+        ptx::tma_store_4d(&tmO, sO + grp * kOutBytes, 0, tx * kTX, ty * kTY, img);
+        ptx::tma_store_commit();
+        if (p.stat_parts != nullptr) {
           double a = 0.0, b = 0.0;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) { a += (double)s_stat[(grp * 4 + k) * 2]; b += (double)s_stat[(grp * 4 + k) * 2 + 1]; }
+          for (int k = 0; k < 4; ++k) { a += (double)stat_slot[k * 2]; b += (double)stat_slot[k * 2 + 1]; }
           p.stat_parts[(size_t)tile * 2] = a;
           p.stat_parts[(size_t)tile * 2 + 1] = b;
         }
+        ptx::tma_store_wait_read();               // the store has read the tile out of shared memory
+        ptx::mbar_arrive(&rempty[grp]);           // -> the next residual tile may land
       }
       acc_phase ^= 1;
     }
+    if (g == 0 && lane == 0) ptx::tma_store_wait_all();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -292,7 +364,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-int make_map_4d(const void* base, int C, int Wp, int Hp, int n, CUtensorMap* out) {
+int make_map_4d(const void* base, int C, int Wp, int Hp, int n, int box_x, int box_y, CUtensorMap* out) {
   void* fp = nullptr;
   cudaDriverEntryPointQueryResult q;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
@@ -300,7 +372,7 @@ int make_map_4d(const void* base, int C, int Wp, int Hp, int n, CUtensorMap* out
   EncodeTiledFn fn = reinterpret_cast<EncodeTiledFn>(fp);
   cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)Wp, (cuuint64_t)Hp, (cuuint64_t)n};
   cuuint64_t gstride[3] = {(cuuint64_t)C * 2, (cuuint64_t)Wp * C * 2, (cuuint64_t)Hp * Wp * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)kPX, (cuuint32_t)kPY, 1};
+  cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)box_x, (cuuint32_t)box_y, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -337,19 +409,21 @@ extern "C" int tcvn_sdxl16_conv2d_c64(const void* x_bf16, int n, int H, int W, c
   if (tiles >= (1ll << 31)) return fail(TCVN_ERR_UNSUPPORTED, "sdxl16_conv2d_c64: too many tiles in one launch");
   p.num_tiles = (int)tiles;
   p.bias = bias; p.in_stat = static_cast<const float2*>(in_stat); p.gamma = gamma; p.beta = beta;
-  p.residual = static_cast<const bf16*>(residual_bf16); p.out = static_cast<bf16*>(out_bf16);
+  p.has_residual = residual_bf16 != nullptr;
   p.stat_parts = static_cast<double*>(stat_parts);
-  CUtensorMap tmX, tmW;
-  TCVN_TRY(make_map_4d(x_bf16, kC, p.Wp, p.Hp, n, &tmX));
+  CUtensorMap tmX, tmW, tmR, tmO;
+  TCVN_TRY(make_map_4d(x_bf16, kC, p.Wp, p.Hp, n, kPX, kPY, &tmX));
+  TCVN_TRY(make_map_4d(residual_bf16 ? residual_bf16 : out_bf16, kC, p.Wp, p.Hp, n, kTX, kTY, &tmR));
+  TCVN_TRY(make_map_4d(out_bf16, kC, p.Wp, p.Hp, n, kTX, kTY, &tmO));
   TCVN_TRY(make_map(w_bf16, 9 * kC, kC, kC, 64, kC, &tmW));
-  const size_t smem = 1024 + kWBytes + (size_t)kStages * kStageStride + (3 * kStages + 5) * 8 + 16 + (16 + 64) * 4;
+  const size_t smem = 1024 + kWBytes + (size_t)kStages * kStageStride + 2 * kOutBytes + (3 * kStages + 9) * 8 + 16 + (32 + 64) * 4;
   bool& attr_done = device_flag(5);
   if (!attr_done) {
     TCVN_CUDA(cudaFuncSetAttribute(umma_conv2d_c64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
   const int grid = p.num_tiles < sm_count() ? p.num_tiles : sm_count();
-  umma_conv2d_c64_kernel<<<grid, kThreads, smem, stream>>>(tmX, tmW, p);
+  umma_conv2d_c64_kernel<<<grid, kThreads, smem, stream>>>(tmX, tmW, tmR, tmO, p);
   TCVN_LAUNCH_CHECK();
   if (out_stat) {
     gn_tiles_finalize_kernel<<<n, 256, 0, stream>>>(p.stat_parts, p.tiles_x * p.tiles_y, (double)H * W * kC, eps,
