@@ -74,22 +74,43 @@ struct SeqDev {
 enum { EPI_BIAS = 0, EPI_AFFINE_PRELU = 1, EPI_BIAS_GELU = 2, EPI_NONE = 3 };
 
 // y[s][n] = epi( sum_k x[s][k] * Wt[k][n] ) for s < S; x, y in shared memory; Wt [K][N] in global (n contiguous).
+// A thread owns output column n for 16 rows at a time (a <= 16-token sequence reads every weight once); k advances four
+// at a time: four weight loads in flight (eight with the unroll) and one 16-byte broadcast read of x per row - the loop is
+// a chain of L2 latencies otherwise.  The sum over k keeps its ascending order.
 template <int EPI>
 __device__ void linear_rows(const float* __restrict__ Wt, const float* __restrict__ p0, const float* __restrict__ p1,
                             const float* __restrict__ p2, const float* x, int ldx, int K, int N, int S, float* y,
                             int ldy) {
+  constexpr int R = 16;
+  const bool vec = ((ldx | K) & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
   for (int n = threadIdx.x; n < N; n += blockDim.x) {
-    for (int s0 = 0; s0 < S; s0 += 8) {
-      float acc[8];
+    for (int s0 = 0; s0 < S; s0 += R) {
+      float acc[R];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-      for (int k = 0; k < K; ++k) {
-        const float w = __ldg(Wt + (size_t)k * N + n);
+      for (int i = 0; i < R; ++i) acc[i] = 0.f;
+      if (vec) {
+#pragma unroll 2
+        for (int k = 0; k < K; k += 4) {
+          const float w0 = __ldg(Wt + (size_t)k * N + n), w1 = __ldg(Wt + (size_t)(k + 1) * N + n);
+          const float w2 = __ldg(Wt + (size_t)(k + 2) * N + n), w3 = __ldg(Wt + (size_t)(k + 3) * N + n);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(x[(s0 + i) * ldx + k], w, acc[i]);  // rows >= S are scratch
+          for (int i = 0; i < R; ++i) {   // rows >= S are scratch
+            const float4 xv = *reinterpret_cast<const float4*>(x + (s0 + i) * ldx + k);
+            acc[i] = fmaf(xv.x, w0, acc[i]);
+            acc[i] = fmaf(xv.y, w1, acc[i]);
+            acc[i] = fmaf(xv.z, w2, acc[i]);
+            acc[i] = fmaf(xv.w, w3, acc[i]);
+          }
+        }
+      } else {
+        for (int k = 0; k < K; ++k) {
+          const float w = __ldg(Wt + (size_t)k * N + n);
+#pragma unroll
+          for (int i = 0; i < R; ++i) acc[i] = fmaf(x[(s0 + i) * ldx + k], w, acc[i]);
+        }
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < R; ++i) {
         if (s0 + i >= S) break;
         float v = acc[i];
         if (EPI == EPI_BIAS) v += __ldg(p0 + n);
@@ -138,7 +159,7 @@ __device__ void add_layernorm(float* x, const float* r, int S, int D, const floa
   }
 }
 
-__global__ void __launch_bounds__(kSeqThreads) seq_forward_kernel(const SeqDev P, int stages,
+__global__ void __launch_bounds__(kSeqThreads, 2) seq_forward_kernel(const SeqDev P, int stages,
                                                                   const float* __restrict__ event_emb,
                                                                   const float* __restrict__ prong_emb,
                                                                   const uint8_t* __restrict__ event_mask,
@@ -150,9 +171,9 @@ __global__ void __launch_bounds__(kSeqThreads) seq_forward_kernel(const SeqDev P
   const int b = blockIdx.x;
   const int S = 1 + L;
   const int D = P.D;
-  // buffers are sized by the batch's sequence length (rows rounded up to 8, plus 8 rows of slack the
-  // 8-row register tiles of linear_rows may read), so several events fit one SM
-  const int SR = ((S + 7) & ~7) + 8;
+  // buffers are sized by the batch's sequence length (rows rounded up to the 16-row register tiles of linear_rows),
+  // so several events fit one SM
+  const int SR = (S + 15) & ~15;
   float* x = sm;                          // [SR][D]     current hidden state
   float* big = x + SR * D;                // [SR][3D]    token inputs / qkv / ffn hidden
   float* ctx = big + SR * 3 * D;          // [SR][D]     attention context / sub-layer output
@@ -441,7 +462,7 @@ extern "C" int tcvn_seq_forward(const tcvn_seq_desc* d, const void* packed, int 
   cudaStream_t st = stream;
   prong_offsets_kernel<<<1, 256, 0, st>>>(prong_mask, n_events, max_prongs, offsets);
   TCVN_LAUNCH_CHECK();
-  const int SR = ((1 + max_prongs + 7) & ~7) + 8;
+  const int SR = (1 + max_prongs + 15) & ~15;
   const size_t smem = ((size_t)SR * d->hidden * 5 + (size_t)SR * P.in_dim) * sizeof(float);
   TCVN_CUDA(cudaFuncSetAttribute(seq_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   // latency-bound, one CTA per event: ask for the full shared-memory carve-out so that two CTAs are resident per SM

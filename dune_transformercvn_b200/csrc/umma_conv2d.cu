@@ -49,6 +49,7 @@ constexpr uint32_t kDescHiPatch = ((uint32_t)(kPX * 128) >> 4) | (1u << 14) | (2
 struct Conv2dParams {
   int n_img, H, W, Hp, Wp;
   int tiles_x, tiles_y, num_tiles;
+  unsigned long long magic_img, magic_row;   // ceil(2^40 / tiles per image), ceil(2^40 / tiles_x): q = n * magic >> 40
   const float* bias;                 // [64]
   const float2* in_stat;             // [n_img] (mean, rstd) of the input's GroupNorm
   const float* gamma; const float* beta;   // [64]
@@ -62,6 +63,14 @@ __device__ __forceinline__ uint32_t pack2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+// tile -> (image, tile row, tile column) without integer divisions (exact for n * d < 2^40, checked by the launcher)
+__device__ __forceinline__ void tile_coords(const Conv2dParams& p, int tile, int per_img, int& img, int& ty, int& tx) {
+  img = (int)(((unsigned long long)(unsigned)tile * p.magic_img) >> 40);
+  const int rem = tile - img * per_img;
+  ty = (int)(((unsigned long long)(unsigned)rem * p.magic_row) >> 40);
+  tx = rem - ty * p.tiles_x;
+}
+
 __device__ __forceinline__ float tanh_approx(float v) {
   float t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(v));
@@ -128,9 +137,9 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv2d_c64_kernel(const __gr
       for (int t = 0; t < 9; ++t) ptx::tma_load_2d(sW + t * kWTap, &tmW, wfull, 0, t * kC);
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int img = tile / per_img, rem = tile - img * per_img;
-        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-        ptx::mbar_wait(&empty[stage], phase ^ 1);
+        int img, ty, tx;
+        tile_coords(p, tile, per_img, img, ty, tx);
+        ptx::mbar_wait_long(&empty[stage], phase ^ 1);
         ptx::mbar_arrive_expect_tx(&full[stage], kPatchBytes);
         // patch origin = output tile origin - 1 in ringed coordinates (may be -1: zero-filled)
         ptx::tma_load_4d(sA + stage * kStageStride, &tmX, &full[stage], 0, tx * kTX - 1, ty * kTY - 1, img);
@@ -171,9 +180,9 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv2d_c64_kernel(const __gr
       int it = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
         const int grp = it & 1;
-        const int img = tile / per_img, rem = tile - img * per_img;
-        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-        ptx::mbar_wait(&rempty[grp], ph[grp] ^ 1);
+        int img, ty, tx;
+        tile_coords(p, tile, per_img, img, ty, tx);
+        ptx::mbar_wait_long(&rempty[grp], ph[grp] ^ 1);
         if (p.has_residual) {
           ptx::mbar_arrive_expect_tx(&rfull[grp], kOutBytes);
           ptx::tma_load_4d(sO + grp * kOutBytes, &tmR, &rfull[grp], 0, tx * kTX, ty * kTY, img);
@@ -206,13 +215,15 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv2d_c64_kernel(const __gr
     }
     int stage = 0; uint32_t phase = 0;
     int tile = blockIdx.x;
-    float2 st = tile < p.num_tiles ? __ldg(p.in_stat + tile / per_img) : make_float2(0.f, 0.f);
+    float2 st = make_float2(0.f, 0.f);
+    if (tile < p.num_tiles) st = __ldg(p.in_stat + (int)(((unsigned long long)(unsigned)tile * p.magic_img) >> 40));
     for (; tile < p.num_tiles; tile += gridDim.x) {
-      const int img = tile / per_img, rem = tile - img * per_img;
-      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      int img, ty, tx;
+      tile_coords(p, tile, per_img, img, ty, tx);
       // (mean, rstd) of the NEXT tile's image is fetched under this tile's work
       const int nxt = tile + gridDim.x;
-      const float2 st_next = nxt < p.num_tiles ? __ldg(p.in_stat + nxt / per_img) : make_float2(0.f, 0.f);
+      float2 st_next = make_float2(0.f, 0.f);
+      if (nxt < p.num_tiles) st_next = __ldg(p.in_stat + (int)(((unsigned long long)(unsigned)nxt * p.magic_img) >> 40));
       float2 hsc[4], hsh[4];   // y / 2 = v * hsc + hsh
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -222,25 +233,33 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv2d_c64_kernel(const __gr
       const int y0 = ty * kTY - 1, x0 = tx * kTX - 1;          // ringed coordinates of the patch origin
       if (lane == 0) ptx::mbar_wait(&full[stage], phase);
       __syncwarp();
-      uint8_t* base = sA + stage * kStageStride;
+      const uint32_t base = ptx::smem_u32(sA + stage * kStageStride);
+      auto activate = [&](uint4 v) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t u[4];
 #pragma unroll
-      for (int k = 0; k < kIter; ++k) {
-        if (pyx[k] < 0) continue;
-        const int yy = y0 + (pyx[k] >> 8), xx = x0 + (pyx[k] & 255);
-        uint4* q = reinterpret_cast<uint4*>(base + slot[k]);
-        uint4 o = make_uint4(0u, 0u, 0u, 0u);       // ring / outside the image: the convolution's zero padding
-        if (yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W) {
-          const uint4 v = *q;
-          const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-          uint32_t u[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 y = silu_half2(__ffma2_rn(make_float2(bflo(w[i]), bfhi(w[i])), hsc[i], hsh[i]));
-            u[i] = pack2(y.x, y.y);
-          }
-          o = make_uint4(u[0], u[1], u[2], u[3]);
+        for (int i = 0; i < 4; ++i) {
+          const float2 y = silu_half2(__ffma2_rn(make_float2(bflo(w[i]), bfhi(w[i])), hsc[i], hsh[i]));
+          u[i] = pack2(y.x, y.y);
         }
-        *q = o;
+        return make_uint4(u[0], u[1], u[2], u[3]);
+      };
+      if (y0 >= 1 && y0 + kPY - 1 <= p.H && x0 >= 1 && x0 + kPX - 1 <= p.W) {
+        // the whole patch lies inside the image (most tiles): no per-pixel tests
+#pragma unroll
+        for (int k = 0; k < kIter; ++k) {
+          if (pyx[k] < 0) continue;
+          ptx::sts128(base + slot[k], activate(ptx::lds128(base + slot[k])));
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < kIter; ++k) {
+          if (pyx[k] < 0) continue;
+          const int yy = y0 + (pyx[k] >> 8), xx = x0 + (pyx[k] & 255);
+          uint4 o = make_uint4(0u, 0u, 0u, 0u);       // ring / outside the image: the convolution's zero padding
+          if (yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W) o = activate(ptx::lds128(base + slot[k]));
+          ptx::sts128(base + slot[k], o);
+        }
       }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(&ready[stage]);
@@ -252,19 +271,19 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv2d_c64_kernel(const __gr
     const int g = warp & 3;             // TMEM lane quarter this warp may read
     const int row = g * 32 + lane;      // pixel of the tile: (row >> 3, row & 7)
     // this pixel's 128 bytes of the staging tile (128B-swizzled like every TMA tile): chunk j sits at j ^ (row & 7)
-    uint8_t* srow = sO + grp * kOutBytes + row * 128;
+    const uint32_t srow = ptx::smem_u32(sO + grp * kOutBytes + row * 128);
     const int sw = row & 7;
     uint32_t acc_phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       if ((it & 1) != grp) continue;
-      const int img = tile / per_img, rem = tile - img * per_img;
-      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      int img, ty, tx;
+      tile_coords(p, tile, per_img, img, ty, tx);
       const int yy = ty * kTY + (row >> 3), xx = tx * kTX + (row & 7);
       const bool interior = yy >= 1 && yy <= p.H && xx >= 1 && xx <= p.W;
-      if (lane == 0) ptx::mbar_wait(&rfull[grp], acc_phase);   // staging tile free (and the residual landed in it)
+      if (lane == 0) ptx::mbar_wait_long(&rfull[grp], acc_phase);   // staging tile free (and the residual landed in it)
       __syncwarp();
-      if (lane == 0) ptx::mbar_wait(&tfull[grp], acc_phase);
+      if (lane == 0) ptx::mbar_wait_long(&tfull[grp], acc_phase);
       __syncwarp();
       ptx::tc_fence_after();
       // bias + residual in packed fp32 pairs; the NEXT GroupNorm's statistics are taken from the fp32 values (the bf16
@@ -283,21 +302,23 @@ __global__ void __launch_bounds__(kThreads, 1) umma_conv2d_c64_kernel(const __gr
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
           const int j = half * 4 + jj;
-          uint4* slot = reinterpret_cast<uint4*>(srow + ((j ^ sw) << 4));
-          const uint4 res = p.has_residual ? *slot : make_uint4(0u, 0u, 0u, 0u);
+          const uint32_t slot = srow + ((j ^ sw) << 4);
+          const uint4 res = p.has_residual ? ptx::lds128(slot) : make_uint4(0u, 0u, 0u, 0u);
           const uint32_t rw[4] = {res.x, res.y, res.z, res.w};
+          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + j * 8), b1 = *reinterpret_cast<const float4*>(s_bias + j * 8 + 4);
+          const float2 bias2[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
           uint32_t w[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             float2 v = make_float2(__uint_as_float(r[jj * 8 + 2 * i]), __uint_as_float(r[jj * 8 + 2 * i + 1]));
-            v = __fadd2_rn(v, *reinterpret_cast<const float2*>(s_bias + j * 8 + 2 * i));
+            v = __fadd2_rn(v, bias2[i]);
             v = __fadd2_rn(v, make_float2(bflo(rw[i]), bfhi(rw[i])));
             w[i] = pack2(v.x, v.y);
             s1 = __fadd2_rn(s1, v);
             s2 = __ffma2_rn(v, v, s2);
           }
           // ring pixels store zeros; pixels beyond the map are clipped by the TMA store
-          *slot = interior ? make_uint4(w[0], w[1], w[2], w[3]) : make_uint4(0u, 0u, 0u, 0u);
+          ptx::sts128(slot, interior ? make_uint4(w[0], w[1], w[2], w[3]) : make_uint4(0u, 0u, 0u, 0u));
         }
       }
       if (!interior) { s1 = make_float2(0.f, 0.f); s2 = make_float2(0.f, 0.f); }   // ... and count for nothing
@@ -408,6 +429,10 @@ extern "C" int tcvn_sdxl16_conv2d_c64(const void* x_bf16, int n, int H, int W, c
   const long long tiles = (long long)n * p.tiles_x * p.tiles_y;
   if (tiles >= (1ll << 31)) return fail(TCVN_ERR_UNSUPPORTED, "sdxl16_conv2d_c64: too many tiles in one launch");
   p.num_tiles = (int)tiles;
+  const unsigned long long per_img = (unsigned long long)p.tiles_x * p.tiles_y;
+  if ((unsigned long long)tiles * per_img >= (1ull << 40)) return fail(TCVN_ERR_UNSUPPORTED, "sdxl16_conv2d_c64: too many tiles in one launch");
+  p.magic_img = ((1ull << 40) + per_img - 1) / per_img;
+  p.magic_row = ((1ull << 40) + p.tiles_x - 1) / p.tiles_x;
   p.bias = bias; p.in_stat = static_cast<const float2*>(in_stat); p.gamma = gamma; p.beta = beta;
   p.has_residual = residual_bf16 != nullptr;
   p.stat_parts = static_cast<double*>(stat_parts);
