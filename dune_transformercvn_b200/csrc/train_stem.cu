@@ -1,12 +1,19 @@
 // Stem of the TRAINING path (dense_net.py:112-118 under autograd): raw conv0 output + its batch statistics, and conv0's
-// weight gradient.  Both are hit-driven like the inference stem (simt.cu) and both are bit-reproducible: a persistent CTA
-// walks 16 x 16 tiles of conv outputs in a fixed order, the non-zero pixels of the tile's input window are compacted in
-// a fixed order (ballot + prefix sums), every accumulator has exactly one owner thread, and the per-CTA partial results
-// land in fixed slots that a later kernel adds in a fixed order.  (Round 1 scattered hits with float atomics: the one-ulp
-// run-to-run differences of z0 were amplified by the 67 train-mode BatchNorms to 20 % of the gradient.)
+// weight gradient.  Both are hit-driven (the pixel maps are 0.2-1 % occupied) and bit-reproducible: every accumulator has
+// exactly one owner, the summation orders are fixed by the geometry, and per-CTA partial results land in fixed slots that
+// a later kernel adds in a fixed order.  (Round 1 scattered hits with float atomics: the one-ulp run-to-run differences
+// of z0 were amplified by the 67 train-mode BatchNorms to 20 % of the gradient.)
 //
-//   MODE 0  z0[n, cy, cx, :] = bf16(b + conv7x7s2p3(pixels))   and  parts[cta][2][C0] = per-CTA (sum z, sum z^2) in double
-//   MODE 1  parts[cta][cin*49][C0] = sum over the CTA's tiles of  x[2cy-3+ky, 2cx-3+kx, c] * dz[n, cy, cx, :]
+// Round 2, second version: like the inference stem (stem_coo.cu) the work unit belongs to ONE WARP - no CTA barriers, no
+// accumulator zeroing, lane l owns channels 2l, 2l+1:
+//   forward   a warp takes an 8 x 8 tile of conv outputs, reads the tile's 21 x 21 input window from the dense pixel map
+//             (63 loads in flight), and every non-zero pixel - found by ballot, row by row, left to right - adds v * w[tap] to
+//             the <= 4 x 4 outputs it reaches; a 64-bit mask of touched outputs replaces the zeroing pass.
+//             z0[n, cy, cx, :] = bf16(b + conv) for every output of the tile, and the tile's (sum z, sum z^2) - the untouched
+//             outputs are count x the constant, exactly - go to the CTA's slot.
+//   wgrad     a warp takes one input row of one image, finds its non-zero pixels the same way and adds
+//             x[c] * dz[n, cy, cx, :] into its own [cin*49][64] accumulator in shared memory; the warps of a CTA are added
+//             in warp order into the CTA's slot.
 #include "kernels.h"
 #include "stem.cuh"
 
@@ -14,197 +21,224 @@ namespace tcvn {
 
 namespace {
 
-constexpr int kTileC = 16;   // conv outputs per tile edge that the tile OWNS (it evaluates 17: the stem_scatter geometry)
+constexpr int kFT = 8;                  // conv outputs per tile edge
+constexpr int kFWin = 2 * kFT + 5;      // 21 input pixels per edge
+constexpr int kFWarps = 10;             // forward: warps per CTA (16 KB of accumulators each)
+constexpr int kGWarps = 5;              // wgrad: warps per CTA (37 KB of accumulators each)
+constexpr int kGChunks = 12;            // wgrad: 32-pixel chunks of an input row held in registers (W <= 384)
 
 struct StemTrainArgs {
   const float* pixels; int n_images, cin, H, W, Hs, Ws;
-  const float* w0;        // [cin*49][C0]           (MODE 0)
-  const float* bias;      // [C0]                   (MODE 0)
-  __nv_bfloat16* z0;      // [n, Hs, Ws, C0] bf16   (MODE 0)
-  double* stat_parts;     // [grid][2][C0]          (MODE 0)
-  const __nv_bfloat16* dz; // [n, Hs, Ws, C0] bf16  (MODE 1)
-  float* dw_parts;        // [grid][cin*49][C0]     (MODE 1)
+  const float* w0;        // [cin*49][C0]           (forward)
+  const float* bias;      // [C0]                   (forward)
+  __nv_bfloat16* z0;      // [n, Hs, Ws, C0] bf16   (forward)
+  double* stat_parts;     // [grid][2][C0]          (forward)
+  const __nv_bfloat16* dz; // [n, Hs, Ws, C0] bf16  (wgrad)
+  float* dw_parts;        // [grid][cin*49][C0]     (wgrad)
 };
 
-template <int MODE, int C0>
-__global__ void __launch_bounds__(kStemThreads, 1) stem_train_kernel(const StemTrainArgs a) {
+__device__ __forceinline__ __nv_bfloat162 bf2(float2 v) { return __float22bfloat162_rn(v); }
+
+__global__ void __launch_bounds__(kFWarps * 32, 1) stem_train_fwd_kernel(const StemTrainArgs a) {
+  constexpr int C0 = 64;
   extern __shared__ __align__(16) float smem[];
-  // MODE 0: filter bank [cin*49][C0] | accumulators [289][C0] | hits      MODE 1: dz tile [256][C0] bf16 | hits
-  float* wsm = smem;
-  float* acc = MODE == 0 ? wsm + a.cin * 49 * C0 : smem;
-  __nv_bfloat16* dzs = reinterpret_cast<__nv_bfloat16*>(smem);
-  float4* hits = MODE == 0 ? reinterpret_cast<float4*>(acc + kStemTC * kStemTC * C0)
-                           : reinterpret_cast<float4*>(smem + kTileC * kTileC * C0 / 2);
-  __shared__ int row_count[kStemRows];
-  __shared__ int row_start[kStemRows + 1];
-  __shared__ int touched[kStemTC * kStemTC];
-  const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-  const int ch = t & (C0 - 1);
-  if (MODE == 0)
-    for (int i = t; i < a.cin * 49 * C0; i += blockDim.x) wsm[i] = __ldg(a.w0 + i);
-  const int tiles_x = (a.Ws + kTileC - 1) / kTileC, tiles_y = (a.Hs + kTileC - 1) / kTileC;
+  // filter bank per (tap, lane): {w[c0][2l], w[c0][2l+1], w[c1][2l], w[c1][2l+1]} and {w[c2][2l], w[c2][2l+1]}
+  float4* wA = reinterpret_cast<float4*>(smem);                      // [49][32]
+  float2* wB = reinterpret_cast<float2*>(smem + 49 * 32 * 4);        // [49][32]
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  float2* acc = reinterpret_cast<float2*>(smem + 147 * C0 + warp * kFT * kFT * C0) + lane;   // [64 outputs][32 lanes]
+  for (int i = t; i < 49 * 32; i += blockDim.x) {
+    const int tap = i >> 5, c = 2 * (i & 31);
+    float w[3][2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      w[k][0] = k < a.cin ? __ldg(a.w0 + (k * 49 + tap) * C0 + c) : 0.f;
+      w[k][1] = k < a.cin ? __ldg(a.w0 + (k * 49 + tap) * C0 + c + 1) : 0.f;
+    }
+    wA[i] = make_float4(w[0][0], w[0][1], w[1][0], w[1][1]);
+    wB[i] = make_float2(w[2][0], w[2][1]);
+  }
+  __syncthreads();
+  wA += lane; wB += lane;
+  const int ch = 2 * lane;
+  const float2 bias = make_float2(__ldg(a.bias + ch), __ldg(a.bias + ch + 1));
+  const __nv_bfloat162 zconst = bf2(bias);                 // an output no pixel reaches
+  const float2 zc = __bfloat1622float2(zconst);
+  double st1[2] = {0.0, 0.0}, st2[2] = {0.0, 0.0};         // this lane's two channels over all tiles of this warp
+
+  const int tiles_x = (a.Ws + kFT - 1) / kFT, tiles_y = (a.Hs + kFT - 1) / kFT;
   const int per_image = tiles_x * tiles_y;
   const long long total = (long long)a.n_images * per_image;
   const size_t plane = (size_t)a.H * a.W;
-  // the window of the NEXT tile is loaded into registers while this tile is processed (cf. stem_fused_kernel)
-  float v[3][2][3];
-  auto load_window = [&](long long tile_id) {
-    const int n = (int)(tile_id / per_image);
-    const int rem = (int)(tile_id - (long long)n * per_image);
-    const int iy0 = 2 * (rem / tiles_x) * kTileC - 3, ix0 = 2 * (rem % tiles_x) * kTileC - 3;
-    const float* img = a.pixels + (size_t)n * a.cin * plane;
-#pragma unroll
-    for (int rs = 0; rs < 3; ++rs) {
-      const int yy = warp + 16 * rs, y = iy0 + yy;
-#pragma unroll
-      for (int cs = 0; cs < 2; ++cs) {
-        const int xx = lane + 32 * cs, x = ix0 + xx;
-        const bool ok = yy < kStemIn && xx < kStemIn && y >= 0 && y < a.H && x >= 0 && x < a.W;
-#pragma unroll
-        for (int c = 0; c < 3; ++c) v[rs][cs][c] = (ok && c < a.cin) ? __ldg(img + c * plane + (size_t)y * a.W + x) : 0.f;
-      }
-    }
-  };
-  // MODE 0 state: statistics of this thread's channel over the positions it writes
-  double st1 = 0.0, st2 = 0.0;
-  const float bias = MODE == 0 ? __ldg(a.bias + ch) : 0.f;
-  // MODE 1 state: this thread's filter taps tg, tg + 8, ... (7 or 6 of the 49) x 3 input channels
-  const int tg = t >> 6;
-  float dwacc[7][3];
-  int tap_ky[7], tap_kx[7];   // ky = 99 marks the missing seventh tap
-#pragma unroll
-  for (int q = 0; q < 7; ++q) {
-    dwacc[q][0] = 0.f; dwacc[q][1] = 0.f; dwacc[q][2] = 0.f;
-    const int tap = tg + 8 * q;
-    tap_ky[q] = tap < 49 ? tap / 7 : 99;
-    tap_kx[q] = tap % 7;
-  }
-
-  if ((long long)blockIdx.x < total) load_window(blockIdx.x);
-  for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+  for (long long tile = (long long)blockIdx.x * kFWarps + warp; tile < total; tile += (long long)gridDim.x * kFWarps) {
     const int n = (int)(tile / per_image);
     const int rem = (int)(tile - (long long)n * per_image);
-    const int cy0 = (rem / tiles_x) * kTileC, cx0 = (rem % tiles_x) * kTileC;
-    __syncthreads();  // previous tile fully consumed
-    // ---- compact the non-zero pixels of the window: rows in order, columns in order
-    unsigned m0[3], m1[3];
+    const int tyi = rem / tiles_x;
+    const int cy0 = tyi * kFT, cx0 = (rem - tyi * tiles_x) * kFT;
+    const int iy0 = 2 * cy0 - 3, ix0 = 2 * cx0 - 3;
+    // ---- the 21 x 21 x cin window, lane = column: all loads issued before the first use
+    const float* img = a.pixels + (size_t)n * a.cin * plane;
+    float v[kFWin][3];
+    const int x = ix0 + lane;
+    const bool xok = lane < kFWin && x >= 0 && x < a.W;
 #pragma unroll
-    for (int rs = 0; rs < 3; ++rs) {
-      const int yy = warp + 16 * rs;
-      m0[rs] = __ballot_sync(0xffffffffu, v[rs][0][0] != 0.f || v[rs][0][1] != 0.f || v[rs][0][2] != 0.f);
-      m1[rs] = __ballot_sync(0xffffffffu, v[rs][1][0] != 0.f || v[rs][1][1] != 0.f || v[rs][1][2] != 0.f);
-      if (lane == 0 && yy < kStemIn) row_count[yy] = __popc(m0[rs]) + __popc(m1[rs]);
-    }
-    if (MODE == 0) {
-      float4* a4 = reinterpret_cast<float4*>(acc);
-      for (int i = t; i < kStemTC * kStemTC * C0 / 4; i += blockDim.x) a4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (t < kStemTC * kStemTC) touched[t] = 0;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      int run = 0;
-      for (int base = 0; base < kStemRows; base += 32) {
-        const int r = base + lane;
-        const int c = r < kStemRows ? row_count[r] : 0;
-        int incl = c;
+    for (int yy = 0; yy < kFWin; ++yy) {
+      const int y = iy0 + yy;
+      const bool ok = xok && y >= 0 && y < a.H;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-          const int up = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += up;
-        }
-        if (r < kStemRows) row_start[r] = run + incl - c;
-        run += __shfl_sync(0xffffffffu, incl, 31);
-      }
-      if (lane == 0) row_start[kStemRows] = run;
+      for (int c = 0; c < 3; ++c) v[yy][c] = (ok && c < a.cin) ? __ldg(img + c * plane + (size_t)y * a.W + x) : 0.f;
     }
-    __syncthreads();
-    const int nhits = row_start[kStemRows];
+    // ---- scatter, rows in order, columns in order (the order of the dense-window kernels: same bits)
+    unsigned long long mask = 0ull;
 #pragma unroll
-    for (int rs = 0; rs < 3; ++rs) {
-      const int yy = warp + 16 * rs;
-      if (yy < kStemIn) {
-        const int base = row_start[yy];
-        const unsigned below = (1u << lane) - 1u;
-        if (m0[rs] >> lane & 1u)
-          hits[base + __popc(m0[rs] & below)] = make_float4(__int_as_float(yy * 64 + lane), v[rs][0][0], v[rs][0][1], v[rs][0][2]);
-        if (m1[rs] >> lane & 1u)
-          hits[base + __popc(m0[rs]) + __popc(m1[rs] & below)] =
-              make_float4(__int_as_float(yy * 64 + lane + 32), v[rs][1][0], v[rs][1][1], v[rs][1][2]);
-      }
-    }
-    if (tile + gridDim.x < total) load_window(tile + gridDim.x);  // in flight during the rest of this tile
-    if (MODE == 1 && nhits > 0) {
-      // gradient tile of the owned conv outputs (zero outside the map), 16-byte loads
-      constexpr int VPR = C0 / 8;   // uint4 per position
-      for (int i = t; i < kTileC * kTileC * VPR; i += blockDim.x) {
-        const int p = i / VPR, q = i - p * VPR;
-        const int cy = cy0 + (p >> 4), cx = cx0 + (p & 15);
-        uint4 g = make_uint4(0u, 0u, 0u, 0u);
-        if (cy < a.Hs && cx < a.Ws)
-          g = __ldg(reinterpret_cast<const uint4*>(a.dz + (((size_t)n * a.Hs + cy) * a.Ws + cx) * C0) + q);
-        reinterpret_cast<uint4*>(dzs)[i] = g;
-      }
-    }
-    __syncthreads();
-    if (MODE == 0) {
-      stem_scatter<C0, false>(wsm, acc, hits, nhits, touched, a.cin, ch, t >> 7, (t >> 6) & 1);
-      __syncthreads();
-      // owned outputs -> z0 (+ bias); 8 positions x C0 channels per step, 256 bytes per position
-      for (int p = t >> 6; p < kTileC * kTileC; p += kStemThreads / C0) {
-        const int cyl = p >> 4, cxl = p & 15;
-        const int cy = cy0 + cyl, cx = cx0 + cxl;
-        if (cy < a.Hs && cx < a.Ws) {
-          // stored (and counted in the statistics) as bf16: three more passes read this map (pooling, BN0 backward x 2)
-          const __nv_bfloat16 zb = __float2bfloat16_rn(acc[(cyl * kStemTC + cxl) * C0 + ch] + bias);
-          a.z0[(((size_t)n * a.Hs + cy) * a.Ws + cx) * C0 + ch] = zb;
-          const float z = __bfloat162float(zb);
-          st1 += (double)z;
-          st2 += (double)z * (double)z;
+    for (int yy = 0; yy < kFWin; ++yy) {
+      unsigned m = __ballot_sync(0xffffffffu, v[yy][0] != 0.f || v[yy][1] != 0.f || v[yy][2] != 0.f);
+      const int cy_lo = yy > 6 ? (yy - 5) >> 1 : 0, cy_hi = min(kFT - 1, yy >> 1);
+      while (m) {
+        const int xx = __ffs((int)m) - 1;
+        m &= m - 1u;
+        const float v0 = __shfl_sync(0xffffffffu, v[yy][0], xx), v1 = __shfl_sync(0xffffffffu, v[yy][1], xx),
+                    v2 = __shfl_sync(0xffffffffu, v[yy][2], xx);
+        const float2 vv0 = make_float2(v0, v0), vv1 = make_float2(v1, v1), vv2 = make_float2(v2, v2);
+        const int cx_lo = xx > 6 ? (xx - 5) >> 1 : 0, cx_hi = min(kFT - 1, xx >> 1);
+        const int ncx = cx_hi - cx_lo + 1;                 // 1..4
+        const unsigned long long run = (1ull << ncx) - 1ull;
+        for (int cy = cy_lo; cy <= cy_hi; ++cy) {
+          const int pos0 = cy * kFT + cx_lo;
+          const int tap0 = (yy - 2 * cy) * 7 + xx - 2 * cx_lo;
+          const unsigned field = (unsigned)(mask >> pos0);   // bit j: output j of the run was touched
+          float2 s[4];
+          float4 wa[4];
+          float2 wb[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int jj = min(j, ncx - 1);                  // a slot beyond the run repeats a legal address, is not stored
+            wa[j] = wA[(tap0 - 2 * jj) * 32];
+            wb[j] = wB[(tap0 - 2 * jj) * 32];
+            s[j] = make_float2(0.f, 0.f);
+            if ((field >> jj) & 1u) s[j] = acc[(pos0 + jj) * 32];
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            s[j] = __ffma2_rn(vv0, make_float2(wa[j].x, wa[j].y), s[j]);
+            s[j] = __ffma2_rn(vv1, make_float2(wa[j].z, wa[j].w), s[j]);
+            s[j] = __ffma2_rn(vv2, wb[j], s[j]);
+            if (j < ncx) acc[(pos0 + j) * 32] = s[j];
+          }
+          mask |= run << pos0;
         }
       }
-    } else {
-      for (int h = 0; h < nhits; ++h) {
-        const float4 hit = hits[h];
-        const int code = __float_as_int(hit.x);
-        const int yy = code >> 6, xx = code & 63;
+    }
+    // ---- z0 = bf16(conv + bias) for every output of the tile, statistics of exactly the stored values
+    float2 t1 = make_float2(0.f, 0.f), t2 = make_float2(0.f, 0.f);
+    int n_const = 0;
+    __nv_bfloat16* zrow = a.z0 + (((size_t)n * a.Hs + cy0) * a.Ws + cx0) * C0 + ch;
 #pragma unroll
-        for (int q = 0; q < 7; ++q) {
-          const int dy = yy - tap_ky[q], dx = xx - tap_kx[q];
-          if (dy >= 0 && dx >= 0 && !((dy | dx) & 1) && dy < 2 * kTileC && dx < 2 * kTileC) {
-            const float g = __bfloat162float(dzs[((dy >> 1) * kTileC + (dx >> 1)) * C0 + ch]);
-            dwacc[q][0] = fmaf(hit.y, g, dwacc[q][0]);
-            dwacc[q][1] = fmaf(hit.z, g, dwacc[q][1]);
-            dwacc[q][2] = fmaf(hit.w, g, dwacc[q][2]);
+    for (int cyl = 0; cyl < kFT; ++cyl) {
+      if (cy0 + cyl >= a.Hs) break;
+      const unsigned bits = (unsigned)(mask >> (cyl * kFT)) & 255u;
+#pragma unroll
+      for (int cxl = 0; cxl < kFT; ++cxl) {
+        if (cx0 + cxl >= a.Ws) break;
+        __nv_bfloat162 zb = zconst;
+        if ((bits >> cxl) & 1u) {
+          zb = bf2(__fadd2_rn(acc[(cyl * kFT + cxl) * 32], bias));
+          const float2 z = __bfloat1622float2(zb);
+          t1 = __fadd2_rn(t1, z);
+          t2 = __ffma2_rn(z, z, t2);
+        } else {
+          ++n_const;
+        }
+        *reinterpret_cast<__nv_bfloat162*>(zrow + ((size_t)cyl * a.Ws + cxl) * C0) = zb;
+      }
+    }
+    st1[0] += (double)t1.x + (double)n_const * (double)zc.x;
+    st1[1] += (double)t1.y + (double)n_const * (double)zc.y;
+    st2[0] += (double)t2.x + (double)n_const * ((double)zc.x * (double)zc.x);
+    st2[1] += (double)t2.y + (double)n_const * ((double)zc.y * (double)zc.y);
+    __syncwarp();
+  }
+  // per-CTA statistics: the warps of a channel are added in warp order
+  __syncthreads();
+  double* red = reinterpret_cast<double*>(smem + 147 * C0);   // [warps][2][C0]
+  red[(warp * 2) * C0 + ch] = st1[0]; red[(warp * 2) * C0 + ch + 1] = st1[1];
+  red[(warp * 2 + 1) * C0 + ch] = st2[0]; red[(warp * 2 + 1) * C0 + ch + 1] = st2[1];
+  __syncthreads();
+  if (t < 2 * C0) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < kFWarps; ++k) s += red[(size_t)k * 2 * C0 + t];
+    a.stat_parts[(size_t)blockIdx.x * 2 * C0 + t] = s;
+  }
+}
+
+__global__ void __launch_bounds__(kGWarps * 32, 1) stem_train_wgrad_kernel(const StemTrainArgs a) {
+  constexpr int C0 = 64;
+  extern __shared__ __align__(16) float smem[];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int taps = a.cin * 49;
+  float2* dw = reinterpret_cast<float2*>(smem + (size_t)warp * 147 * C0) + lane;   // [c * 49 + tap][32 lanes]
+  for (int i = 0; i < taps; ++i) dw[i * 32] = make_float2(0.f, 0.f);
+  const size_t plane = (size_t)a.H * a.W;
+  const long long total = (long long)a.n_images * a.H;   // work unit: one input row of one image
+  const int chunks = (a.W + 31) / 32;
+  for (long long u = (long long)blockIdx.x * kGWarps + warp; u < total; u += (long long)gridDim.x * kGWarps) {
+    const int n = (int)(u / a.H);
+    const int y = (int)(u - (long long)n * a.H);
+    const float* row = a.pixels + (size_t)n * a.cin * plane + (size_t)y * a.W;
+    float v[kGChunks][3];
+#pragma unroll
+    for (int q = 0; q < kGChunks; ++q) {
+      const int x = q * 32 + lane;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[q][c] = (q < chunks && x < a.W && c < a.cin) ? __ldg(row + c * plane + x) : 0.f;
+    }
+    // conv rows this input row feeds: ky = y + 3 - 2 cy in [0, 6]
+    const int cy_lo = y > 3 ? (y - 2) >> 1 : 0, cy_hi = min(a.Hs - 1, (y + 3) >> 1);
+#pragma unroll
+    for (int q = 0; q < kGChunks; ++q) {
+      unsigned m = __ballot_sync(0xffffffffu, v[q][0] != 0.f || v[q][1] != 0.f || v[q][2] != 0.f);
+      while (m) {
+        const int src = __ffs((int)m) - 1;
+        m &= m - 1u;
+        const int x = q * 32 + src;
+        const float v0 = __shfl_sync(0xffffffffu, v[q][0], src), v1 = __shfl_sync(0xffffffffu, v[q][1], src),
+                    v2 = __shfl_sync(0xffffffffu, v[q][2], src);
+        const float2 vv[3] = {make_float2(v0, v0), make_float2(v1, v1), make_float2(v2, v2)};
+        const int cx_lo = x > 3 ? (x - 2) >> 1 : 0, cx_hi = min(a.Ws - 1, (x + 3) >> 1);
+        for (int cy = cy_lo; cy <= cy_hi; ++cy) {
+          const int ky = y + 3 - 2 * cy;
+          const __nv_bfloat16* grow = a.dz + (((size_t)n * a.Hs + cy) * a.Ws) * C0 + 2 * lane;
+          float2 g[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int cx = min(cx_lo + j, cx_hi);
+            g[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(grow + (size_t)cx * C0));
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (cx_lo + j > cx_hi) break;
+            const int tap = ky * 7 + (x + 3 - 2 * (cx_lo + j));
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              if (c >= a.cin) break;
+              float2* d = dw + (c * 49 + tap) * 32;
+              *d = __ffma2_rn(vv[c], g[j], *d);
+            }
           }
         }
       }
     }
   }
-  if (MODE == 0) {
-    // per-CTA statistics: the 8 position lanes of a channel are added in a fixed order
-    __syncthreads();
-    double* red = reinterpret_cast<double*>(acc);   // [8][C0][2]
-    red[((t >> 6) * C0 + ch) * 2] = st1;
-    red[((t >> 6) * C0 + ch) * 2 + 1] = st2;
-    __syncthreads();
-    if (t < C0) {
-      double s1 = 0.0, s2 = 0.0;
+  // the warps of the CTA, added in warp order -> the CTA's slot
+  __syncthreads();
+  float* part = a.dw_parts + (size_t)blockIdx.x * taps * C0;
+  for (int i = t; i < taps * C0; i += blockDim.x) {
+    const int r = i / C0, c = i - r * C0;
+    float s = 0.f;
 #pragma unroll
-      for (int k = 0; k < kStemThreads / C0; ++k) { s1 += red[(k * C0 + t) * 2]; s2 += red[(k * C0 + t) * 2 + 1]; }
-      a.stat_parts[((size_t)blockIdx.x * 2) * C0 + t] = s1;
-      a.stat_parts[((size_t)blockIdx.x * 2 + 1) * C0 + t] = s2;
-    }
-  } else {
-    float* part = a.dw_parts + (size_t)blockIdx.x * a.cin * 49 * C0;
-#pragma unroll
-    for (int q = 0; q < 7; ++q) {
-      const int tap = tg + 8 * q;
-      if (tap < 49) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          if (c < a.cin) part[(c * 49 + tap) * C0 + ch] = dwacc[q][c];
-      }
-    }
+    for (int w = 0; w < kGWarps; ++w) s += smem[(size_t)w * 147 * C0 + (r * 32 + (c >> 1)) * 2 + (c & 1)];
+    part[i] = s;
   }
 }
 
@@ -212,9 +246,8 @@ __global__ void __launch_bounds__(kStemThreads, 1) stem_train_kernel(const StemT
 
 // slots of the per-CTA partial results (MODE 0: doubles [slots][2][C0]; MODE 1: floats [slots][cin*49][C0])
 int stem_train_slots(int n_images, int H, int W) {
-  const int Hs = (H + 6 - 7) / 2 + 1, Ws = (W + 6 - 7) / 2 + 1;
-  const long long tiles = (long long)n_images * ceil_div(Hs, kTileC) * ceil_div(Ws, kTileC);
-  return (int)(tiles < 148 ? (tiles < 1 ? 1 : tiles) : 148);
+  (void)H; (void)W;
+  return n_images < 1 ? 1 : 148;   // upper bound of both kernels' grids (one slot per CTA)
 }
 
 static int stem_train_check(int cin, int C) {
@@ -230,11 +263,13 @@ int stem_train_forward(const float* pixels, int n, int cin, int H, int W, const 
   a.pixels = pixels; a.n_images = n; a.cin = cin; a.H = H; a.W = W;
   a.Hs = (H + 6 - 7) / 2 + 1; a.Ws = (W + 6 - 7) / 2 + 1;
   a.w0 = w0; a.bias = bias; a.z0 = static_cast<__nv_bfloat16*>(z0_bf16); a.stat_parts = stat_parts;
-  const int grid = stem_train_slots(n, H, W);
+  const long long tiles = (long long)n * ceil_div(a.Hs, kFT) * ceil_div(a.Ws, kFT);
+  const long long want = ceil_div_ll(tiles, kFWarps);
+  const int grid = (int)(want < 148 ? (want < 1 ? 1 : want) : 148);
   *n_slots = grid;
-  const size_t smem = ((size_t)cin * 49 * 64 + (size_t)kStemTC * kStemTC * 64) * 4 + (size_t)kStemIn * kStemIn * 16;
-  TCVN_CUDA(cudaFuncSetAttribute(stem_train_kernel<0, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  stem_train_kernel<0, 64><<<grid, kStemThreads, smem, stream>>>(a);
+  const size_t smem = ((size_t)147 * 64 + (size_t)kFWarps * kFT * kFT * 64) * 4;
+  TCVN_CUDA(cudaFuncSetAttribute(stem_train_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  stem_train_fwd_kernel<<<grid, kFWarps * 32, smem, stream>>>(a);
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
 }
@@ -247,11 +282,13 @@ int stem_train_wgrad(const float* pixels, int n, int cin, int H, int W, const vo
   a.pixels = pixels; a.n_images = n; a.cin = cin; a.H = H; a.W = W;
   a.Hs = (H + 6 - 7) / 2 + 1; a.Ws = (W + 6 - 7) / 2 + 1;
   a.dz = static_cast<const __nv_bfloat16*>(dz_bf16); a.dw_parts = dw_parts;
-  const int grid = stem_train_slots(n, H, W);
+  if (W > 32 * kGChunks) return fail(TCVN_ERR_UNSUPPORTED, "training stem: image width %d (weight-gradient kernel holds rows of <= %d pixels)", W, 32 * kGChunks);
+  const long long want = ceil_div_ll((long long)n * H, kGWarps);
+  const int grid = (int)(want < 148 ? (want < 1 ? 1 : want) : 148);
   *n_slots = grid;
-  const size_t smem = (size_t)kTileC * kTileC * 64 * 2 + (size_t)kStemIn * kStemIn * 16;
-  TCVN_CUDA(cudaFuncSetAttribute(stem_train_kernel<1, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  stem_train_kernel<1, 64><<<grid, kStemThreads, smem, stream>>>(a);
+  const size_t smem = (size_t)kGWarps * 147 * 64 * 4;
+  TCVN_CUDA(cudaFuncSetAttribute(stem_train_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  stem_train_wgrad_kernel<<<grid, kGWarps * 32, smem, stream>>>(a);
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
 }
