@@ -736,7 +736,7 @@ __global__ void __launch_bounds__(256) stem_pool16_fwd_kernel(const __nv_bfloat1
       for (int i = 0; i < 8; ++i) s[i] += prelu(fmaf(v[i], sc[i], sh[i]), al[i]);
     }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s[i] /= 9.0f;
+  for (int i = 0; i < 8; ++i) s[i] *= (1.0f / 9.0f);   // bf16 path: a product (<= 1 fp32 ulp from the quotient, 10x fewer instructions)
   st8<__nv_bfloat16>(blk + ((size_t)n * (H + 2) * (W + 2) + (size_t)(y + 1) * (W + 2) + x + 1) * ld + c, s);
 }
 
@@ -764,7 +764,7 @@ __global__ void __launch_bounds__(256) stem_pool16_bwd_kernel(const __nv_bfloat1
       for (int i = 0; i < 8; ++i) s[i] += v[i];
     }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) s[i] /= 9.0f;
+  for (int i = 0; i < 8; ++i) s[i] *= (1.0f / 9.0f);   // bf16 path: a product (<= 1 fp32 ulp from the quotient, 10x fewer instructions)
   st8<__nv_bfloat16>(dA + (((size_t)n * Hs + oy) * Ws + ox) * C + c, s);
 }
 

@@ -24,7 +24,7 @@ namespace {
 constexpr int kFT = 8;                  // conv outputs per tile edge
 constexpr int kFWin = 2 * kFT + 5;      // 21 input pixels per edge
 constexpr int kFWarps = 10;             // forward: warps per CTA (16 KB of accumulators each)
-constexpr int kGWarps = 5;              // wgrad: warps per CTA (37 KB of accumulators each)
+constexpr int kGWarps = 6;              // wgrad: warps per CTA (37 KB of accumulators each)
 constexpr int kGChunks = 12;            // wgrad: 32-pixel chunks of an input row held in registers (W <= 384)
 
 struct StemTrainArgs {
@@ -38,6 +38,48 @@ struct StemTrainArgs {
 };
 
 __device__ __forceinline__ __nv_bfloat162 bf2(float2 v) { return __float22bfloat162_rn(v); }
+
+// All non-zero pixels of one window row (ballot m, lane = window column), left to right: each adds v * w[tap] to the <= 4 x 4
+// conv outputs it reaches.  NOT inlined: the caller's row loop is unrolled 21 times (the window lives in registers), and 21
+// copies of this body made the kernel instruction-cache-bound (ncu: no_instruction was the top stall).
+__device__ __noinline__ unsigned long long stem_scatter_row(unsigned m, float r0, float r1, float r2, int yy, unsigned long long mask,
+                                                            float2* acc, const float4* wA, const float2* wB) {
+  const int cy_lo = yy > 6 ? (yy - 5) >> 1 : 0, cy_hi = min(kFT - 1, yy >> 1);
+  while (m) {
+    const int xx = __ffs((int)m) - 1;
+    m &= m - 1u;
+    const float v0 = __shfl_sync(0xffffffffu, r0, xx), v1 = __shfl_sync(0xffffffffu, r1, xx), v2 = __shfl_sync(0xffffffffu, r2, xx);
+    const float2 vv0 = make_float2(v0, v0), vv1 = make_float2(v1, v1), vv2 = make_float2(v2, v2);
+    const int cx_lo = xx > 6 ? (xx - 5) >> 1 : 0, cx_hi = min(kFT - 1, xx >> 1);
+    const int ncx = cx_hi - cx_lo + 1;                 // 1..4
+    const unsigned long long run = (1ull << ncx) - 1ull;
+    for (int cy = cy_lo; cy <= cy_hi; ++cy) {
+      const int pos0 = cy * kFT + cx_lo;
+      const int tap0 = (yy - 2 * cy) * 7 + xx - 2 * cx_lo;
+      const unsigned field = (unsigned)(mask >> pos0);   // bit j: output j of the run was touched
+      float2 s[4];
+      float4 wa[4];
+      float2 wb[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int jj = min(j, ncx - 1);                  // a slot beyond the run repeats a legal address, is not stored
+        wa[j] = wA[(tap0 - 2 * jj) * 32];
+        wb[j] = wB[(tap0 - 2 * jj) * 32];
+        s[j] = make_float2(0.f, 0.f);
+        if ((field >> jj) & 1u) s[j] = acc[(pos0 + jj) * 32];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        s[j] = __ffma2_rn(vv0, make_float2(wa[j].x, wa[j].y), s[j]);
+        s[j] = __ffma2_rn(vv1, make_float2(wa[j].z, wa[j].w), s[j]);
+        s[j] = __ffma2_rn(vv2, wb[j], s[j]);
+        if (j < ncx) acc[(pos0 + j) * 32] = s[j];
+      }
+      mask |= run << pos0;
+    }
+  }
+  return mask;
+}
 
 __global__ void __launch_bounds__(kFWarps * 32, 1) stem_train_fwd_kernel(const StemTrainArgs a) {
   constexpr int C0 = 64;
@@ -92,48 +134,14 @@ __global__ void __launch_bounds__(kFWarps * 32, 1) stem_train_fwd_kernel(const S
     unsigned long long mask = 0ull;
 #pragma unroll
     for (int yy = 0; yy < kFWin; ++yy) {
-      unsigned m = __ballot_sync(0xffffffffu, v[yy][0] != 0.f || v[yy][1] != 0.f || v[yy][2] != 0.f);
-      const int cy_lo = yy > 6 ? (yy - 5) >> 1 : 0, cy_hi = min(kFT - 1, yy >> 1);
-      while (m) {
-        const int xx = __ffs((int)m) - 1;
-        m &= m - 1u;
-        const float v0 = __shfl_sync(0xffffffffu, v[yy][0], xx), v1 = __shfl_sync(0xffffffffu, v[yy][1], xx),
-                    v2 = __shfl_sync(0xffffffffu, v[yy][2], xx);
-        const float2 vv0 = make_float2(v0, v0), vv1 = make_float2(v1, v1), vv2 = make_float2(v2, v2);
-        const int cx_lo = xx > 6 ? (xx - 5) >> 1 : 0, cx_hi = min(kFT - 1, xx >> 1);
-        const int ncx = cx_hi - cx_lo + 1;                 // 1..4
-        const unsigned long long run = (1ull << ncx) - 1ull;
-        for (int cy = cy_lo; cy <= cy_hi; ++cy) {
-          const int pos0 = cy * kFT + cx_lo;
-          const int tap0 = (yy - 2 * cy) * 7 + xx - 2 * cx_lo;
-          const unsigned field = (unsigned)(mask >> pos0);   // bit j: output j of the run was touched
-          float2 s[4];
-          float4 wa[4];
-          float2 wb[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int jj = min(j, ncx - 1);                  // a slot beyond the run repeats a legal address, is not stored
-            wa[j] = wA[(tap0 - 2 * jj) * 32];
-            wb[j] = wB[(tap0 - 2 * jj) * 32];
-            s[j] = make_float2(0.f, 0.f);
-            if ((field >> jj) & 1u) s[j] = acc[(pos0 + jj) * 32];
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            s[j] = __ffma2_rn(vv0, make_float2(wa[j].x, wa[j].y), s[j]);
-            s[j] = __ffma2_rn(vv1, make_float2(wa[j].z, wa[j].w), s[j]);
-            s[j] = __ffma2_rn(vv2, wb[j], s[j]);
-            if (j < ncx) acc[(pos0 + j) * 32] = s[j];
-          }
-          mask |= run << pos0;
-        }
-      }
+      const unsigned m = __ballot_sync(0xffffffffu, v[yy][0] != 0.f || v[yy][1] != 0.f || v[yy][2] != 0.f);
+      if (m) mask = stem_scatter_row(m, v[yy][0], v[yy][1], v[yy][2], yy, mask, acc, wA, wB);
     }
     // ---- z0 = bf16(conv + bias) for every output of the tile, statistics of exactly the stored values
     float2 t1 = make_float2(0.f, 0.f), t2 = make_float2(0.f, 0.f);
     int n_const = 0;
     __nv_bfloat16* zrow = a.z0 + (((size_t)n * a.Hs + cy0) * a.Ws + cx0) * C0 + ch;
-#pragma unroll
+#pragma unroll 1
     for (int cyl = 0; cyl < kFT; ++cyl) {
       if (cy0 + cyl >= a.Hs) break;
       const unsigned bits = (unsigned)(mask >> (cyl * kFT)) & 255u;
@@ -172,6 +180,52 @@ __global__ void __launch_bounds__(kFWarps * 32, 1) stem_train_fwd_kernel(const S
   }
 }
 
+// All non-zero pixels of one 32-pixel chunk of an input row (ballot m), left to right: x[c] * dz[n, cy, cx, :] into this
+// warp's accumulators.  Not inlined (the caller's chunk loop is unrolled: the row lives in registers).
+__device__ __noinline__ void stem_wgrad_chunk(unsigned m, float r0, float r1, float r2, int x0, int y, int cin, int Hs, int Ws,
+                                              const __nv_bfloat16* dz_img, float2* dw) {
+  constexpr int C0 = 64;
+  // conv rows this input row feeds: ky = y + 3 - 2 cy in [0, 6]
+  const int cy_lo = y > 3 ? (y - 2) >> 1 : 0, cy_hi = min(Hs - 1, (y + 3) >> 1);
+  while (m) {
+    const int src = __ffs((int)m) - 1;
+    m &= m - 1u;
+    const int x = x0 + src;
+    const float v0 = __shfl_sync(0xffffffffu, r0, src), v1 = __shfl_sync(0xffffffffu, r1, src), v2 = __shfl_sync(0xffffffffu, r2, src);
+    const float2 vv[3] = {make_float2(v0, v0), make_float2(v1, v1), make_float2(v2, v2)};
+    const int cx_lo = x > 3 ? (x - 2) >> 1 : 0, cx_hi = min(Ws - 1, (x + 3) >> 1);
+    // the <= 4 x 4 gradient vectors this pixel meets, all loads in flight before the first use (the kernel is a chain of
+    // L2 latencies otherwise: ncu long_scoreboard 6 cycles per issue with one row of loads at a time)
+    float2 g[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int cy = min(cy_lo + i, cy_hi);
+      const __nv_bfloat16* grow = dz_img + ((size_t)cy * Ws) * C0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int cx = min(cx_lo + j, cx_hi);
+        g[i][j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(grow + (size_t)cx * C0));
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (cy_lo + i > cy_hi) break;
+      const int ky = y + 3 - 2 * (cy_lo + i);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (cx_lo + j > cx_hi) break;
+        const int tap = ky * 7 + (x + 3 - 2 * (cx_lo + j));
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (c >= cin) break;
+          float2* d = dw + (c * 49 + tap) * 32;
+          *d = __ffma2_rn(vv[c], g[i][j], *d);
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kGWarps * 32, 1) stem_train_wgrad_kernel(const StemTrainArgs a) {
   constexpr int C0 = 64;
   extern __shared__ __align__(16) float smem[];
@@ -193,41 +247,11 @@ __global__ void __launch_bounds__(kGWarps * 32, 1) stem_train_wgrad_kernel(const
 #pragma unroll
       for (int c = 0; c < 3; ++c) v[q][c] = (q < chunks && x < a.W && c < a.cin) ? __ldg(row + c * plane + x) : 0.f;
     }
-    // conv rows this input row feeds: ky = y + 3 - 2 cy in [0, 6]
-    const int cy_lo = y > 3 ? (y - 2) >> 1 : 0, cy_hi = min(a.Hs - 1, (y + 3) >> 1);
+    const __nv_bfloat16* dz_img = a.dz + ((size_t)n * a.Hs * a.Ws) * C0 + 2 * lane;
 #pragma unroll
     for (int q = 0; q < kGChunks; ++q) {
-      unsigned m = __ballot_sync(0xffffffffu, v[q][0] != 0.f || v[q][1] != 0.f || v[q][2] != 0.f);
-      while (m) {
-        const int src = __ffs((int)m) - 1;
-        m &= m - 1u;
-        const int x = q * 32 + src;
-        const float v0 = __shfl_sync(0xffffffffu, v[q][0], src), v1 = __shfl_sync(0xffffffffu, v[q][1], src),
-                    v2 = __shfl_sync(0xffffffffu, v[q][2], src);
-        const float2 vv[3] = {make_float2(v0, v0), make_float2(v1, v1), make_float2(v2, v2)};
-        const int cx_lo = x > 3 ? (x - 2) >> 1 : 0, cx_hi = min(a.Ws - 1, (x + 3) >> 1);
-        for (int cy = cy_lo; cy <= cy_hi; ++cy) {
-          const int ky = y + 3 - 2 * cy;
-          const __nv_bfloat16* grow = a.dz + (((size_t)n * a.Hs + cy) * a.Ws) * C0 + 2 * lane;
-          float2 g[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int cx = min(cx_lo + j, cx_hi);
-            g[j] = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(grow + (size_t)cx * C0));
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            if (cx_lo + j > cx_hi) break;
-            const int tap = ky * 7 + (x + 3 - 2 * (cx_lo + j));
-#pragma unroll
-            for (int c = 0; c < 3; ++c) {
-              if (c >= a.cin) break;
-              float2* d = dw + (c * 49 + tap) * 32;
-              *d = __ffma2_rn(vv[c], g[j], *d);
-            }
-          }
-        }
-      }
+      const unsigned m = __ballot_sync(0xffffffffu, v[q][0] != 0.f || v[q][1] != 0.f || v[q][2] != 0.f);
+      if (m) stem_wgrad_chunk(m, v[q][0], v[q][1], v[q][2], q * 32, y, a.cin, a.Hs, a.Ws, dz_img, dw);
     }
   }
   // the warps of the CTA, added in warp order -> the CTA's slot
