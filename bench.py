@@ -433,7 +433,7 @@ def run_sdxl_leg(args, dev, timed, pk):
                       "parity": "unpinned (diffusers absent; oracle/restate_sdxl.py restates its published layout)"},
            "roofline": {"bound": "tensor", "achieved": tf, "peak": pk["bf16_sustained"], "unit": "TFLOP/s",
                         "frac": tf / pk["bf16_sustained"], "traffic": None,
-                        "kernel": "whole --sdxl network (every convolution = umma_gemm_kernel<false> in shifted-GEMM form)",
+                        "kernel": "whole --sdxl network (64-channel 3x3 convolutions: umma_conv2d_c64_kernel, fused 2-D tiles; wider stages: umma_gemm_kernel<false> in shifted-GEMM form)",
                         "algorithmic_gflop_per_image": SDXL_GFLOP_PER_IMAGE,
                         "peak_source": pk["source"] + " cuBLAS bf16 sustained (kernel timed inside a long step)"}}
     del net, resident
