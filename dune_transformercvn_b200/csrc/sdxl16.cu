@@ -169,6 +169,31 @@ __global__ void __launch_bounds__(256) patch_s2_16_kernel(const bf* __restrict__
   }
 }
 
+// space-to-depth input of the stride-2 3x3 convolution behind F.pad(x, (0, 1, 0, 1)): out has the OUTPUT's ringed geometry
+// [n][(Ho+2)(Wo+2)][4*C]; column group g = 2*py + px of ringed position (i+1, j+1) holds x[2i+py][2j+px] (0 outside the map;
+// the bottom / right ring positions carry the row 2*Ho / column 2*Wo an odd-sized map still has).  Tap (dy, dx) of the
+// convolution is then group (dy & 1, dx & 1) shifted by (dy >> 1, dx >> 1): nine row-shifted views of ONE matrix, 512 B
+// per output pixel instead of the 1152 B of materialised patches.
+__global__ void __launch_bounds__(256) s2d_16_kernel(const bf* __restrict__ x, int n, int C, int H, int W, int Ho, int Wo,
+                                                     bf* __restrict__ out) {
+  const int Wp = W + 2, Hp = H + 2, Wop = Wo + 2, Hop = Ho + 2;
+  const int cv = C >> 3;
+  const long long total = (long long)n * Hop * Wop * 4 * cv;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % cv) * 8;
+    long long r = idx / cv;
+    const int g = (int)(r & 3); r >>= 2;
+    const long long orow = r;
+    const int j = (int)(r % Wop) - 1; r /= Wop;
+    const int i = (int)(r % Hop) - 1;
+    const int img = (int)(r / Hop);
+    const int y = 2 * i + (g >> 1), xx = 2 * j + (g & 1);
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (i >= 0 && j >= 0 && y < H && xx < W) v = __ldg(reinterpret_cast<const uint4*>(x + (((long long)img * Hp + y + 1) * Wp + xx + 1) * C + c));
+    *reinterpret_cast<uint4*>(out + (orow * 4 + g) * C + c) = v;
+  }
+}
+
 __global__ void bf16_to_f32_kernel(const bf* __restrict__ x, long long n, float* __restrict__ out) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = __bfloat162float(x[i]);
@@ -247,6 +272,34 @@ extern "C" int tcvn_sdxl16_patch_s2(const void* x_bf16, int n, int C, int H, int
       static_cast<const bf*>(x_bf16), n, C, H, W, Ho, Wo, static_cast<bf*>(out_bf16));
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
+}
+
+extern "C" int tcvn_sdxl16_s2d(const void* x_bf16, int n, int C, int H, int W, void* out_bf16, tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(x_bf16 && out_bf16 && n >= 0 && C > 0 && C % 64 == 0 && H >= 2 && W >= 2, "sdxl16_s2d: bad arguments");
+  if (n == 0) return TCVN_OK;
+  const int Ho = H / 2, Wo = W / 2;
+  s2d_16_kernel<<<grid_for((long long)n * (Ho + 2) * (Wo + 2) * 4 * (C / 8)), 256, 0, stream>>>(
+      static_cast<const bf*>(x_bf16), n, C, H, W, Ho, Wo, static_cast<bf*>(out_bf16));
+  TCVN_LAUNCH_CHECK();
+  return TCVN_OK;
+}
+
+// stride-2 3x3 convolution over the space-to-depth matrix of tcvn_sdxl16_s2d: out[rows][out_cols] in the output's ringed
+// geometry (ring_hp x ring_wp), ring rows zero; w_bf16 [n_tiles * 128][9 * C] tap-major like tcvn_sdxl16_conv
+extern "C" int tcvn_sdxl16_conv_s2(const void* s2d_bf16, int64_t rows, int C, const void* w_bf16, int n_tiles, const float* bias_padded,
+                                   const float* ones_padded, void* out_bf16, int out_cols, int ring_hp, int ring_wp,
+                                   tcvn_stream_t stream) {
+  TCVN_CHECK_ARG(s2d_bf16 && w_bf16 && bias_padded && ones_padded && out_bf16 && rows >= 0 && C > 0 && C % 64 == 0 && n_tiles >= 1 &&
+                     ring_hp >= 3 && ring_wp >= 3 && out_cols % 8 == 0, "sdxl16_conv_s2: bad arguments");
+  if (rows == 0) return TCVN_OK;
+  int tap_off[9], tap_col[9];
+  for (int t = 0; t < 9; ++t) {
+    const int dy = t / 3, dx = t % 3;
+    tap_off[t] = (dy >> 1) * ring_wp + (dx >> 1);
+    tap_col[t] = ((dy & 1) * 2 + (dx & 1)) * C;
+  }
+  return launch_gemm_shifted(s2d_bf16, rows, C, 9, tap_off, nullptr, 0, w_bf16, n_tiles, bias_padded, ones_padded, out_bf16, out_cols,
+                             ring_hp, ring_wp, stream, 4 * C, tap_col);
 }
 
 extern "C" int tcvn_sdxl16_to_f32(const void* x_bf16, int64_t count, float* out, tcvn_stream_t stream) {

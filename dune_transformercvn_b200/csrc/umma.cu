@@ -141,6 +141,7 @@ struct GemmParams {
   // ResNet block (identity or 1x1-shortcut weights in the matching K range of W).  Plain GEMM: n_taps = 1, tap_off = {0}.
   int n_taps, chunks_per_tap, chunks2;
   int tap_off[9];
+  int tap_col[9];   // first column of every tap in A (0: all taps read the same columns)
   int ntile;               // output channels per N tile: 128, or 64 (the 64-channel layers of the --sdxl CNN: half the MMA
                            // work and half the weight traffic of a zero-padded 128-wide tile)
   int n_tiles_n;           // N tiles of 128 (1 for conv1)
@@ -234,7 +235,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
           ptx::mbar_wait(&empty[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&full[stage], kStageA + p.ntile * 128);
           if (kc < tap_chunks) {
-            ptx::tma_load_2d(sA + stage * kStageA, &tmA, &full[stage], kk * 64, mt * kTileM + p.tap_off[tap]);
+            ptx::tma_load_2d(sA + stage * kStageA, &tmA, &full[stage], kk * 64 + p.tap_col[tap], mt * kTileM + p.tap_off[tap]);
             if (++kk == p.chunks_per_tap) { kk = 0; ++tap; }
           } else {
             ptx::tma_load_2d(sA + stage * kStageA, &tmA2, &full[stage], (kc - tap_chunks) * 64, mt * kTileM);
@@ -749,6 +750,7 @@ int launch_gemm(bool transform, const void* A, long long rows, int a_cols, int a
   GemmParams g;
   g.m_total = rows; g.kchunks = kpad / kKChunk; g.kphys = kphys; g.n_tiles_n = n_tiles_n;
   g.n_taps = 1; g.chunks_per_tap = g.kchunks; g.chunks2 = 0; g.ntile = kMid;
+  for (int t = 0; t < 9; ++t) g.tap_col[t] = 0;
   for (int t = 0; t < 9; ++t) g.tap_off[t] = 0;
   g.a_scale = a_scale; g.a_shift = a_shift; g.a_alpha = a_alpha; g.o_shift = o_shift; g.o_alpha = o_alpha;
   g.Hp = Hp; g.Wp = Wp;
@@ -772,7 +774,8 @@ int launch_gemm(bool transform, const void* A, long long rows, int a_cols, int a
 // (K-major, zero rows beyond the real output width); X2 may be null (x2_cols = 0).
 int launch_gemm_shifted(const void* A, long long rows, int a_cols, int n_taps, const int* tap_off, const void* X2, int x2_cols,
                         const void* W, int n_tiles_n, const float* bias, const float* ones, void* out, int out_cols, int Hp, int Wp,
-                        cudaStream_t st) {
+                        cudaStream_t st, int a_pitch, const int* tap_col) {
+  if (a_pitch <= 0) a_pitch = a_cols;
   if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one chunk");
   if (a_cols % 64 || x2_cols % 64 || n_taps < 1 || n_taps > 9) return fail(TCVN_ERR_ARG, "launch_gemm_shifted: bad shape");
   const size_t smem = 1024 + kC1Stages * (kStageA + kStageW) + 4 * kStageA + kStageA + kStageW + 2 * 192 * 4 +
@@ -788,7 +791,7 @@ int launch_gemm_shifted(const void* A, long long rows, int a_cols, int n_taps, c
   const int ktot = n_taps * a_cols + x2_cols;
   const int ntile = (n_tiles_n == 1 && out_cols <= 64) ? 64 : kMid;
   CUtensorMap tmA, tmW, tmO, tmX;
-  TCVN_TRY(make_map(A, rows, a_cols, a_cols, 64, kTileM, &tmA));
+  TCVN_TRY(make_map(A, rows, a_pitch, a_pitch, 64, kTileM, &tmA));
   TCVN_TRY(make_map(W, (long long)n_tiles_n * kMid, ktot, ktot, 64, ntile, &tmW));
   TCVN_TRY(make_map(out, rows, out_cols, out_cols, 64, kTileM, &tmO));
   if (X2) TCVN_TRY(make_map(X2, rows, x2_cols, x2_cols, 64, kTileM, &tmX));
@@ -797,6 +800,7 @@ int launch_gemm_shifted(const void* A, long long rows, int a_cols, int n_taps, c
   g.m_total = rows; g.kchunks = ktot / kKChunk; g.kphys = ktot; g.n_tiles_n = n_tiles_n;
   g.n_taps = n_taps; g.chunks_per_tap = a_cols / kKChunk; g.chunks2 = x2_cols / kKChunk; g.ntile = ntile;
   for (int t = 0; t < 9; ++t) g.tap_off[t] = t < n_taps && tap_off ? tap_off[t] : 0;
+  for (int t = 0; t < 9; ++t) g.tap_col[t] = t < n_taps && tap_col ? tap_col[t] : 0;
   g.a_scale = g.a_shift = g.a_alpha = nullptr; g.o_shift = bias; g.o_alpha = ones;
   g.Hp = Hp; g.Wp = Wp; g.stats = nullptr;
   g.num_tiles = (int)ceil_div_ll(rows, kTileM) * n_tiles_n;

@@ -23,7 +23,9 @@ int launch_gemm(bool transform, const void* A, long long rows, int a_cols, int a
                 double* stats = nullptr, int* stat_slots = nullptr);
 int launch_gemm_shifted(const void* A, long long rows, int a_cols, int n_taps, const int* tap_off, const void* X2, int x2_cols,
                         const void* W, int n_tiles_n, const float* bias, const float* ones, void* out, int out_cols, int Hp, int Wp,
-                        cudaStream_t st);
+                        cudaStream_t st, int a_pitch = 0, const int* tap_col = nullptr);
+// a_pitch > a_cols with tap_col: every tap reads its own a_cols-wide column group of a wider A (space-to-depth input of a
+// stride-2 convolution: tap (dy, dx) = parity group (dy & 1, dx & 1) shifted by (dy >> 1, dx >> 1))
 // slots of the epilogue statistics (doubles [slots][2][128] for launch_gemm, [slots][2][32] for umma_conv2_fwd)
 constexpr int kUmmaStatSlotsMax = 8 * 148;
 int umma_conv2_fwd(const void* mid, long long rows, const void* w2, const float* bias, void* out, int ldo, int col0, int Hp,

@@ -35,7 +35,7 @@ EXPORTS = (
     "tcvn_t_umma_wgrad", "tcvn_t_umma_wgrad_workspace_bytes", "tcvn_t_umma_conv2_dgrad",
     "tcvn_loss_forward", "tcvn_loss_backward", "tcvn_metrics_update",
     "tcvn_sdxl_pixels_to_ring", "tcvn_sdxl_groupnorm", "tcvn_sdxl_patch_s2", "tcvn_set_sm_limit",
-    "tcvn_sdxl16_patch27", "tcvn_sdxl16_groupnorm_workspace_bytes", "tcvn_sdxl16_groupnorm", "tcvn_sdxl16_patch_s2",
+    "tcvn_sdxl16_patch27", "tcvn_sdxl16_groupnorm_workspace_bytes", "tcvn_sdxl16_groupnorm", "tcvn_sdxl16_patch_s2", "tcvn_sdxl16_s2d", "tcvn_sdxl16_conv_s2",
     "tcvn_sdxl16_to_f32", "tcvn_sdxl16_conv", "tcvn_sdxl16_conv2d_stat_bytes", "tcvn_sdxl16_conv2d_c64", "tcvn_sdxl16_gn_stats",
 )
 
@@ -146,6 +146,8 @@ def load() -> C.CDLL:
     lib.tcvn_sdxl16_groupnorm_workspace_bytes.restype = sz
     lib.tcvn_sdxl16_groupnorm.argtypes = [vp, i32, i32, i32, i32, vp, vp, f32, i32, vp, vp, sz, vp]
     lib.tcvn_sdxl16_patch_s2.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+    lib.tcvn_sdxl16_s2d.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+    lib.tcvn_sdxl16_conv_s2.argtypes = [vp, i64, i32, vp, i32, vp, vp, vp, i32, i32, i32, vp]
     lib.tcvn_sdxl16_to_f32.argtypes = [vp, i64, vp, vp]
     lib.tcvn_sdxl16_conv2d_stat_bytes.argtypes = [i32, i32, i32]
     lib.tcvn_sdxl16_conv2d_stat_bytes.restype = sz

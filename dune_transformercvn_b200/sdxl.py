@@ -321,9 +321,14 @@ class _SdxlCnn16(_SdxlCnn):
                 raise _lib.TcvnError(f"sdxl: a {h}x{w_} map cannot be down-sampled again (input too small)")
             ho, wo = h // 2, w_ // 2
             orows = n * (ho + 2) * (wo + 2)
-            pt = torch.empty((orows, 9 * cout), dtype=torch.bfloat16, device=dev)
-            _lib.check(L.tcvn_sdxl16_patch_s2(_lib.ptr(x), n, cout, h, w_, _lib.ptr(pt), st), "tcvn_sdxl16_patch_s2")
-            x = self._conv16(L, st, f"{e}down_blocks.{i}.downsamplers.0.conv", pt, orows, 9 * cout, 1, wo + 2, None, 0, (ho + 2, wo + 2))
+            # stride-2 convolution: nine shifted views of the space-to-depth matrix (512 B per output pixel instead of 1152 B
+            # of materialised patches)
+            pt = torch.empty((orows, 4 * cout), dtype=torch.bfloat16, device=dev)
+            _lib.check(L.tcvn_sdxl16_s2d(_lib.ptr(x), n, cout, h, w_, _lib.ptr(pt), st), "tcvn_sdxl16_s2d")
+            wd, bd, n_tiles, co = self.w16[f"{e}down_blocks.{i}.downsamplers.0.conv"]
+            x = torch.empty((orows, co), dtype=torch.bfloat16, device=dev)
+            _lib.check(L.tcvn_sdxl16_conv_s2(_lib.ptr(pt), orows, cout, _lib.ptr(wd), n_tiles, _lib.ptr(bd), _lib.ptr(self.ones),
+                                             _lib.ptr(x), co, ho + 2, wo + 2, st), "tcvn_sdxl16_conv_s2")
             del pt
             h, w_ = ho, wo
             cin = cout

@@ -381,6 +381,11 @@ size_t tcvn_sdxl16_groupnorm_workspace_bytes(int n);
 int tcvn_sdxl16_groupnorm(const void* x_bf16, int n, int C, int H, int W, const float* gamma, const float* beta, float eps, int silu,
                           void* out_bf16, void* workspace, size_t workspace_bytes, tcvn_stream_t stream);
 int tcvn_sdxl16_patch_s2(const void* x_bf16, int n, int C, int H, int W, void* out_bf16, tcvn_stream_t stream);
+/* The same stride-2 convolution without materialised patches: tcvn_sdxl16_s2d writes the space-to-depth matrix
+ * [n * (H/2+2) * (W/2+2)][4*C] (C % 64 == 0), tcvn_sdxl16_conv_s2 reads it as nine row-shifted, column-grouped views. */
+int tcvn_sdxl16_s2d(const void* x_bf16, int n, int C, int H, int W, void* out_bf16, tcvn_stream_t stream);
+int tcvn_sdxl16_conv_s2(const void* s2d_bf16, int64_t rows, int C, const void* w_bf16, int n_tiles, const float* bias_padded,
+                        const float* ones_padded, void* out_bf16, int out_cols, int ring_hp, int ring_wp, tcvn_stream_t stream);
 /* The 64 -> 64 channel 3x3 convolutions of the full-resolution stages (72 % of the network's FLOPs) as ONE fused tcgen05
  * kernel over 2-D tiles (csrc/umma_conv2d.cu):  out = conv3x3(silu(GroupNorm(x))) + bias (+ residual).  A haloed 18 x 10 pixel
  * patch is loaded once per 16 x 8 output tile through a 4-D tensor map, GroupNorm + SiLU are applied in place in shared

@@ -171,6 +171,28 @@ def test_sdxl16_tensor_core_conv_against_torch(dev):
                                 ho + 2, wo + 2, st), "sdxl16_conv(patches)")
     want = F.conv2d(F.pad(xin, (0, 1, 0, 1)), wt.bfloat16().float(), b, stride=2)
     assert rel_err(_unring(y, n, ho, wo), want) < 2e-2
+    # the same convolution without patches: space-to-depth matrix + nine shifted, column-grouped views (the product path);
+    # the K chunks reach the MMA in the same order, so the two results are the same bits
+    sd = torch.empty(orows, 4 * c, dtype=torch.bfloat16, device=dev)
+    tl.check(L.tcvn_sdxl16_s2d(tl.ptr(x16), n, c, h, w, tl.ptr(sd), st), "sdxl16_s2d")
+    y2 = torch.empty(orows, c, dtype=torch.bfloat16, device=dev)
+    tl.check(L.tcvn_sdxl16_conv_s2(tl.ptr(sd), orows, c, tl.ptr(d_w), 1, tl.ptr(d_b), tl.ptr(ones), tl.ptr(y2), c, ho + 2, wo + 2, st),
+             "sdxl16_conv_s2")
+    assert torch.equal(y2, y)
+    # odd map sizes: the last row / column of the map is reached through the ring positions of the space-to-depth matrix
+    for (h2, w2) in ((7, 9), (35, 25)):
+        xo = torch.randn(n, c, h2, w2, generator=g)
+        xo16 = _ring16(xo, dev)
+        ho2, wo2 = h2 // 2, w2 // 2
+        r2 = n * (ho2 + 2) * (wo2 + 2)
+        sd = torch.empty(r2, 4 * c, dtype=torch.bfloat16, device=dev)
+        tl.check(L.tcvn_sdxl16_s2d(tl.ptr(xo16), n, c, h2, w2, tl.ptr(sd), st), "sdxl16_s2d")
+        y3 = torch.empty(r2, c, dtype=torch.bfloat16, device=dev)
+        tl.check(L.tcvn_sdxl16_conv_s2(tl.ptr(sd), r2, c, tl.ptr(d_w), 1, tl.ptr(d_b), tl.ptr(ones), tl.ptr(y3), c, ho2 + 2, wo2 + 2, st),
+                 "sdxl16_conv_s2")
+        xin2 = xo16.float().cpu().view(n, h2 + 2, w2 + 2, c)[:, 1:-1, 1:-1].permute(0, 3, 1, 2)
+        want2 = F.conv2d(F.pad(xin2, (0, 1, 0, 1)), wt.bfloat16().float(), b, stride=2)
+        assert rel_err(_unring(y3, n, ho2, wo2), want2) < 2e-2, (h2, w2)
 
 
 def test_sdxl_bf16_forward_tracks_oracle(dev):
