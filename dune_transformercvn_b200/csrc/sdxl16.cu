@@ -134,12 +134,25 @@ __global__ void __launch_bounds__(256) gn_apply16_kernel(const bf* __restrict__ 
     for (int k = 0; k < 8; ++k) f[k] = 0.f;
     if (!(y == 0 || y == Hp - 1 || xx == 0 || xx == Wp - 1)) {
       unpack8(__ldg(reinterpret_cast<const uint4*>(x + r * C + c)), f);
-      const float2 st = stat[img];
+      const float2 st = __ldg(stat + img);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c)), b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+      const float ga[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float be[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      // silu(v) = h + h * tanh(h), h = v / 2 (one MUFU per value, see umma_conv2d.cu); packed fp32 pairs
+      const float half = silu ? 0.5f : 1.0f;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float v = (f[k] - st.x) * st.y * __ldg(gamma + c + k) + __ldg(beta + c + k);
-        if (silu) v = v / (1.f + __expf(-v));
-        f[k] = v;
+      for (int k = 0; k < 8; k += 2) {
+        const float2 sc = make_float2(half * st.y * ga[k], half * st.y * ga[k + 1]);
+        const float2 sh = make_float2(fmaf(-st.x, sc.x, half * be[k]), fmaf(-st.x, sc.y, half * be[k + 1]));
+        float2 h = __ffma2_rn(make_float2(f[k], f[k + 1]), sc, sh);
+        if (silu) {
+          float tx, ty;
+          asm("tanh.approx.f32 %0, %1;" : "=f"(tx) : "f"(h.x));
+          asm("tanh.approx.f32 %0, %1;" : "=f"(ty) : "f"(h.y));
+          h = __ffma2_rn(h, make_float2(tx, ty), h);
+        }
+        f[k] = h.x; f[k + 1] = h.y;
       }
     }
     *reinterpret_cast<uint4*>(out + r * C + c) = pack8(f);
