@@ -9,7 +9,9 @@
  * Conventions
  *   - every function returns 0 on success or a negative tcvn_status; tcvn_last_error() gives
  *     a thread-local message.  Nothing throws, nothing allocates device memory, nothing
- *     synchronises the stream: the caller owns every buffer and the stream.
+ *     synchronises the stream: the caller owns every buffer and the stream.  Host-side state is
+ *     per calling thread only: the error text, the seed-offset / SM-budget settings below and a
+ *     bounded memo of encoded TMA tensor maps (csrc/umma.cu: make_map); there are no locks.
  *   - all pointers except descriptors are DEVICE pointers unless the name ends in _host.
  *   - workspace sizes are queried with the matching *_bytes function.
  *   - "arena" = the fp32 tensors of a reference sub-module's state_dict, concatenated in
