@@ -250,6 +250,37 @@ def test_sparse_direct_stem_equals_densify_then_forward(dev, precision):
             assert rel_err(ev_a.cpu(), want_ev) < FP32_TOL and rel_err(pr_a.cpu(), want_pr) < FP32_TOL
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_sparse_direct_stem_dense_windows_and_borders(dev, precision):
+    """The warp-per-tile stem (csrc/stem_coo.cu) on inputs that leave its sparse fast paths: windows holding hundreds of
+    hits (record lists longer than one 32-lane batch), a completely filled image, hits on all four borders and corners, and
+    hits outside the map (dropped, as by the densify kernel).  Bit-identical to densify -> dense-window stem."""
+    net, state, opts = _net(2, True, dev, precision=precision)
+    batch = synth.make_batch(2, seed=21, prongs_per_event=[2, 2], event_occupancy=0.55, prong_occupancy=0.25)
+    # prong image 1: every pixel is a hit; prong image 3: only border / corner hits plus two coordinates outside the map
+    pc, pv = batch.prong_coords, batch.prong_values
+    keep = (pc[:, 0] != 1) & (pc[:, 0] != 3)
+    yy, xx = torch.meshgrid(torch.arange(H, dtype=torch.int32), torch.arange(W, dtype=torch.int32), indexing="ij")
+    full_c = torch.stack((torch.full_like(yy, 1), yy, xx), -1).reshape(-1, 3)
+    g = torch.Generator().manual_seed(3)
+    full_v = torch.rand(full_c.shape[0], 3, generator=g).to(pv.dtype)
+    edge = [(0, 0), (0, W - 1), (H - 1, 0), (H - 1, W - 1), (0, 137), (H - 1, 5), (200, 0), (17, W - 1), (1, 1), (H, 3), (5, W)]
+    edge_c = torch.tensor([[3, y, x] for (y, x) in sorted(edge)], dtype=torch.int32)
+    edge_v = torch.rand(edge_c.shape[0], 3, generator=g).to(pv.dtype)
+    parts_c = [pc[keep & (pc[:, 0] < 1)], full_c, pc[keep & (pc[:, 0] == 2)], edge_c]
+    parts_v = [pv[keep & (pc[:, 0] < 1)], full_v, pv[keep & (pc[:, 0] == 2)], edge_v]
+    batch.prong_coords, batch.prong_values = torch.cat(parts_c), torch.cat(parts_v)
+    gb = batch.to(dev)
+    with torch.no_grad():
+        ev_a, pr_a = net.forward_sparse(gb)
+        # the dense maps for the comparison are built without the two out-of-map hits (sparse_to_dense would raise on them)
+        inside = (batch.prong_coords[:, 1] < H) & (batch.prong_coords[:, 2] < W)
+        batch.prong_coords, batch.prong_values = batch.prong_coords[inside], batch.prong_values[inside]
+        ev_b, pr_b = net.forward_sparse(batch.to(dev), materialize=True)
+    assert torch.isfinite(ev_a).all() and torch.isfinite(pr_a).all()
+    assert torch.equal(ev_a, ev_b) and torch.equal(pr_a, pr_b)
+
+
 # ------------------------------------------------------------------------------------------ config 5 shape
 @pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
 def test_max_prong_count_ingest_and_forward(dev, precision, tol):
