@@ -126,7 +126,6 @@ def workload_config(args, images: int, world: int) -> dict:
 
 
 REFERENCE_SAMPLE_EVENTS = 8   # events of the workload one CPU step covers (~1.5 s on 16 cores): K + W steps stay within minutes
-SETTLE_STEPS = 25             # untimed extra steps of the inference leg after the warm-up (clock / power settling)
 
 
 def run_reference(args):
@@ -580,10 +579,6 @@ def run_ours(args):
         for _ in range(max(args.warmup, 3)):
             step(resident)
         net.freeze_packed(True)
-        # clocks and power management settle for ~0.5 s of load before anything is timed (the W warm-up steps above are
-        # 0.1 s; without this the first timed loop ran up to 3 % slower than the end-to-end loop that follows it)
-        for _ in range(SETTLE_STEPS):
-            step(resident)
         sampler = ClockSampler(local)
         sampler.start()
         l0 = tl.load().tcvn_launch_count()
@@ -659,7 +654,7 @@ def run_ours(args):
         except Exception as e:
             single = {"error": f"{type(e).__name__}: {e}"[:300]}
     launches = launches_timed  # counted by the library itself (tcvn_launch_count) around the timed region
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "settle_steps": SETTLE_STEPS,
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": workload_config(args, images, world),
