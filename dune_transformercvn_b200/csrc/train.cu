@@ -289,6 +289,19 @@ __global__ void __launch_bounds__(256, 2) colsum_vec_kernel(const ColDev p, int 
     }
     const RingTest rt(p.Hp, p.Wp);
     int rr0 = rt.start(r_begin + ry);
+    // BN2 backward reductions of the bf16 walk on packed fp32 pairs (8 instead of ~14 instructions per element: the
+    // generic loop below ran issue-bound at 54 % of the HBM bandwidth on dense block 1)
+    constexpr bool kPacked = MODE == 1 && sizeof(TX) == 2 && sizeof(TD) == 2;
+    float2 q0[4], q1[4], q2[4], sc2[4], sh2[4], al2[4], rs2[4], nm2[4];
+    if (kPacked) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        q0[i] = q1[i] = q2[i] = make_float2(0.f, 0.f);
+        sc2[i] = make_float2(sc[2 * i], sc[2 * i + 1]); sh2[i] = make_float2(sh[2 * i], sh[2 * i + 1]);
+        al2[i] = make_float2(al[2 * i], al[2 * i + 1]); rs2[i] = make_float2(rstd[2 * i], rstd[2 * i + 1]);
+        nm2[i] = make_float2(-mean[2 * i] * rstd[2 * i], -mean[2 * i + 1] * rstd[2 * i + 1]);
+      }
+    }
     for (long long m0 = r_begin + ry; m0 < r_end; m0 += (long long)rpi * U) {
       Raw8<TX> xr[U];
       Raw8<TD> dr[U];
@@ -306,6 +319,22 @@ __global__ void __launch_bounds__(256, 2) colsum_vec_kernel(const ColDev p, int 
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (!ok[u]) continue;
+        if (kPacked) {
+          uint32_t xw[4], dw[4];
+          memcpy(xw, &xr[u], 16);
+          memcpy(dw, &dr[u], 16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 x = make_float2(__uint_as_float(xw[i] << 16), __uint_as_float(xw[i] & 0xffff0000u));
+            const float2 d = make_float2(__uint_as_float(dw[i] << 16), __uint_as_float(dw[i] & 0xffff0000u));
+            const float2 y = __ffma2_rn(x, sc2[i], sh2[i]);
+            const float2 g = __fmul2_rn(d, make_float2(y.x >= 0.f ? 1.f : al2[i].x, y.y >= 0.f ? 1.f : al2[i].y));
+            q0[i] = __fadd2_rn(q0[i], g);
+            q1[i] = __ffma2_rn(g, __ffma2_rn(x, rs2[i], nm2[i]), q1[i]);
+            q2[i] = __ffma2_rn(d, make_float2(fminf(y.x, 0.f), fminf(y.y, 0.f)), q2[i]);
+          }
+          continue;
+        }
         float x[8], d[8];
         unpack8(xr[u], x);
         if (MODE == 1) unpack8(dr[u], d);
@@ -324,6 +353,14 @@ __global__ void __launch_bounds__(256, 2) colsum_vec_kernel(const ColDev p, int 
             part[0][i] += x[i];
           }
         }
+      }
+    }
+    if (kPacked) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        part[0][2 * i] = q0[i].x; part[0][2 * i + 1] = q0[i].y;
+        part[1][2 * i] = q1[i].x; part[1][2 * i + 1] = q1[i].y;
+        if (NS > 2) { part[NS - 1][2 * i] = q2[i].x; part[NS - 1][2 * i + 1] = q2[i].y; }
       }
     }
   }
@@ -406,6 +443,82 @@ __global__ void __launch_bounds__(256, 2) bnact_bwd_apply_vec_kernel(const BnBwd
       }
       st8<TO>(O + m * (long long)p.lddx + p.dxcol0 + c, v);
     }
+  }
+}
+
+// The bf16 form of the pass above, written for the instruction budget: ncu on the generic kernel showed 28 instructions
+// per element at IPC 2.0 and 25 % occupancy - issue-bound at 56 % of the HBM bandwidth, not memory-bound.  Here
+//     dx = d * (y >= 0 ? sc : sc * alpha) + (x * B + A),   B = -sc * rstd * mean(g xhat),  A = -sc * mean(g) - B * mean
+// is evaluated on packed fp32 pairs (one FFMA2 each for y, x * B + A and the final product: 6 instructions per element),
+// with five constants per channel instead of seven.  (x at bf16 precision: folding `mean` into A costs nothing.)
+__global__ void __launch_bounds__(256, 2) bnact_bwd_apply16_kernel(const BnBwdDev p, int tv, int rows_per_slab) {
+  typedef __nv_bfloat16 bf;
+  constexpr int U = kVecU;
+  const int rpi = 256 / tv;
+  const int vx = threadIdx.x % tv, ry = threadIdx.x / tv;
+  const int c = (blockIdx.x * tv + vx) * 8;
+  if (c >= p.C || ry >= rpi) return;
+  const bf* X = static_cast<const bf*>(p.X);
+  const bf* D = static_cast<const bf*>(p.D);
+  bf* O = static_cast<bf*>(p.dX);
+  const long long r_begin = (long long)blockIdx.y * rows_per_slab;
+  const long long r_end = min(p.m_total, r_begin + rows_per_slab);
+  const int fs = p.fold_stride;
+  float2 sc[4], sh[4], sn[4], B[4], A[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float k[2][5];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int ch = c + 2 * i + h;
+      const float s = p.fold[ch], al = p.fold[2 * fs + ch], mean = p.fold[3 * fs + ch], rstd = p.fold[4 * fs + ch];
+      const float mg = (float)(p.sums[ch] / p.count), mgx = (float)(p.sums[p.C + ch] / p.count);
+      const float b = -s * rstd * mgx;
+      k[h][0] = s; k[h][1] = p.fold[fs + ch]; k[h][2] = s * al; k[h][3] = b; k[h][4] = fmaf(-b, mean, -s * mg);
+    }
+    sc[i] = make_float2(k[0][0], k[1][0]); sh[i] = make_float2(k[0][1], k[1][1]); sn[i] = make_float2(k[0][2], k[1][2]);
+    B[i] = make_float2(k[0][3], k[1][3]); A[i] = make_float2(k[0][4], k[1][4]);
+  }
+  const RingTest rt(p.Hp, p.Wp);
+  int rr0 = rt.start(r_begin + ry);
+  const bf* xp = X + (r_begin + ry) * (long long)p.ldx + p.xcol0 + c;
+  const bf* dp = D + (r_begin + ry) * (long long)p.ldd + p.dcol0 + c;
+  bf* op = O + (r_begin + ry) * (long long)p.lddx + p.dxcol0 + c;
+  const long long xs = (long long)rpi * p.ldx, ds = (long long)rpi * p.ldd, os = (long long)rpi * p.lddx;
+  for (long long m0 = r_begin + ry; m0 < r_end; m0 += (long long)rpi * U) {
+    uint4 xr[U], dr[U];
+    int kind[U];  // 0 skip, 1 ring, 2 interior
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      kind[u] = m0 + (long long)u * rpi >= r_end ? 0 : (rt.ring(rr0) ? 1 : 2);
+      rr0 = rt.advance(rr0, rpi);
+      if (kind[u] == 2) {
+        xr[u] = *reinterpret_cast<const uint4*>(xp + u * xs);
+        dr[u] = *reinterpret_cast<const uint4*>(dp + u * ds);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (kind[u] == 0) continue;
+      uint4 out = make_uint4(0u, 0u, 0u, 0u);
+      if (kind[u] == 2) {
+        const uint32_t xw[4] = {xr[u].x, xr[u].y, xr[u].z, xr[u].w}, dw[4] = {dr[u].x, dr[u].y, dr[u].z, dr[u].w};
+        uint32_t ow[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 x = make_float2(__uint_as_float(xw[i] << 16), __uint_as_float(xw[i] & 0xffff0000u));
+          const float2 d = make_float2(__uint_as_float(dw[i] << 16), __uint_as_float(dw[i] & 0xffff0000u));
+          const float2 y = __ffma2_rn(x, sc[i], sh[i]);
+          const float2 s = make_float2(y.x >= 0.f ? sc[i].x : sn[i].x, y.y >= 0.f ? sc[i].y : sn[i].y);
+          const float2 v = __ffma2_rn(d, s, __ffma2_rn(x, B[i], A[i]));
+          const __nv_bfloat162 h = __float22bfloat162_rn(v);
+          ow[i] = *reinterpret_cast<const uint32_t*>(&h);
+        }
+        out = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      }
+      *reinterpret_cast<uint4*>(op + u * os) = out;
+    }
+    xp += U * xs; dp += U * ds; op += U * os;
   }
 }
 
@@ -1048,6 +1161,7 @@ int bnact_bwd_apply_typed(const void* D, bool d_bf16, int ldd, int dcol0, const 
     const int slabs = (int)ceil_div_ll(m_total, rows_per_slab);
     dim3 vgrid(gx, slabs);
     if (!x_bf16 && !d_bf16 && !o_bf16) bnact_bwd_apply_vec_kernel<float, float, float><<<vgrid, 256, 0, stream>>>(p, tv, rows_per_slab);
+    else if (x_bf16 && d_bf16 && o_bf16 && !accumulate) bnact_bwd_apply16_kernel<<<vgrid, 256, 0, stream>>>(p, tv, rows_per_slab);
     else if (x_bf16 && d_bf16 && o_bf16) bnact_bwd_apply_vec_kernel<bf, bf, bf><<<vgrid, 256, 0, stream>>>(p, tv, rows_per_slab);
     else if (x_bf16 && d_bf16 && !o_bf16) bnact_bwd_apply_vec_kernel<bf, bf, float><<<vgrid, 256, 0, stream>>>(p, tv, rows_per_slab);
     else if (!x_bf16 && d_bf16 && o_bf16) bnact_bwd_apply_vec_kernel<float, bf, bf><<<vgrid, 256, 0, stream>>>(p, tv, rows_per_slab);
