@@ -562,6 +562,15 @@ __global__ void __launch_bounds__(256, 2) bn1_bwd_reduce_vec_kernel(const Bn1Fus
     }
     const RingTest rt(p.Hp, p.Wp);
     int rr0 = rt.start(r_begin + ry);
+    // packed fp32 pairs, as in colsum_vec_kernel<1>
+    float2 q0[4], q1[4], q2[4], sc2[4], sh2[4], al2[4], rs2[4], nm2[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      q0[i] = q1[i] = q2[i] = make_float2(0.f, 0.f);
+      sc2[i] = make_float2(sc[2 * i], sc[2 * i + 1]); sh2[i] = make_float2(sh[2 * i], sh[2 * i + 1]);
+      al2[i] = make_float2(al[2 * i], al[2 * i + 1]); rs2[i] = make_float2(rstd[2 * i], rstd[2 * i + 1]);
+      nm2[i] = make_float2(-mean[2 * i] * rstd[2 * i], -mean[2 * i + 1] * rstd[2 * i + 1]);
+    }
     for (long long m0 = r_begin + ry; m0 < r_end; m0 += (long long)rpi * U) {
       Raw8<__nv_bfloat16> xr[U], dr[U];
       bool ok[U];
@@ -578,17 +587,24 @@ __global__ void __launch_bounds__(256, 2) bn1_bwd_reduce_vec_kernel(const Bn1Fus
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         if (!ok[u]) continue;
-        float x[8], d[8];
-        unpack8(xr[u], x); unpack8(dr[u], d);
+        const uint32_t xw[4] = {xr[u].a.x, xr[u].a.y, xr[u].a.z, xr[u].a.w}, dw[4] = {dr[u].a.x, dr[u].a.y, dr[u].a.z, dr[u].a.w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float y = fmaf(x[i], sc[i], sh[i]);
-          const float g = y >= 0.f ? d[i] : d[i] * al[i];
-          part[0][i] += g;
-          part[1][i] = fmaf(g, (x[i] - mean[i]) * rstd[i], part[1][i]);
-          part[2][i] = fmaf(d[i], fminf(y, 0.f), part[2][i]);
+        for (int i = 0; i < 4; ++i) {
+          const float2 x = make_float2(__uint_as_float(xw[i] << 16), __uint_as_float(xw[i] & 0xffff0000u));
+          const float2 d = make_float2(__uint_as_float(dw[i] << 16), __uint_as_float(dw[i] & 0xffff0000u));
+          const float2 y = __ffma2_rn(x, sc2[i], sh2[i]);
+          const float2 g = __fmul2_rn(d, make_float2(y.x >= 0.f ? 1.f : al2[i].x, y.y >= 0.f ? 1.f : al2[i].y));
+          q0[i] = __fadd2_rn(q0[i], g);
+          q1[i] = __ffma2_rn(g, __ffma2_rn(x, rs2[i], nm2[i]), q1[i]);
+          q2[i] = __ffma2_rn(d, make_float2(fminf(y.x, 0.f), fminf(y.y, 0.f)), q2[i]);
         }
       }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      part[0][2 * i] = q0[i].x; part[0][2 * i + 1] = q0[i].y;
+      part[1][2 * i] = q1[i].x; part[1][2 * i + 1] = q1[i].y;
+      part[2][2 * i] = q2[i].x; part[2][2 * i + 1] = q2[i].y;
     }
   }
 #pragma unroll
@@ -885,13 +901,15 @@ __global__ void __launch_bounds__(256) stem_pool16_bwd_kernel(const __nv_bfloat1
 template <typename T>
 __global__ void pool2_bwd_kernel(const T* __restrict__ dP, int H2, int W2, int C, T* __restrict__ dA, int H, int W,
                                  long long total) {
-  // one thread = one ringed pixel x 8 channels; total counts those octets
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int cv = C >> 3;
+  // one thread = one ringed pixel x 8 channels; total counts those octets.  Index arithmetic in 32 bits (the launcher keeps
+  // rows * C / 8 below 2^31): with 64-bit divisions this pass was issue-bound at 2.0-2.8 TB/s.
+  const long long idx64 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx64 >= total) return;
+  const unsigned idx = (unsigned)idx64;
+  const unsigned cv = (unsigned)C >> 3;
+  const unsigned Wp = W + 2, Hp = H + 2;
   const int c = (int)(idx % cv) * 8;
-  long long r = idx / cv;
-  const int Wp = W + 2, Hp = H + 2;
+  unsigned r = idx / cv;
   const int xx = (int)(r % Wp); r /= Wp;
   const int yy = (int)(r % Hp);
   const int n = (int)(r / Hp);
@@ -904,7 +922,7 @@ __global__ void pool2_bwd_kernel(const T* __restrict__ dP, int H2, int W2, int C
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] *= 0.25f;
   }
-  st8<T>(dA + (((size_t)n * Hp + yy) * Wp + xx) * C + c, v);
+  st8<T>(dA + (size_t)idx64 * 8, v);
 }
 
 // global average pool backward: dA[ringed rows, C] = dGap[n, c] / (H*W) on interior rows
@@ -1233,6 +1251,7 @@ int pool_typed(int kind, const void* src, const float* fold, void* dst, bool bf1
       break;
     case 2:
       total = (long long)n * (H + 2) * (W + 2) * (C / 8);
+      if (total >= (1ll << 31)) return fail(TCVN_ERR_UNSUPPORTED, "pool2 backward: too many images in one launch (%d)", n);
       if (bf16) pool2_bwd_kernel<bf><<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const bf*>(src), H2, W2, C, static_cast<bf*>(dst), H, W, total);
       else pool2_bwd_kernel<float><<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const float*>(src), H2, W2, C, static_cast<float*>(dst), H, W, total);
       break;
