@@ -407,7 +407,7 @@ def test_graphed_train_step_matches_eager_steps(dev):
     for grp in opt.param_groups:
         grp["lr"] = 2e-3
     l = [float(stepper(batch, ev_t, pr_t)) for _ in range(25)]
-    assert all(x == x for x in l) and sum(l[-5:]) / 5 < 0.6 * sum(l[:3]) / 3, l
+    assert all(x == x for x in l) and sum(l[-5:]) / 5 < 0.6 * l[0], l
     assert len(stepper.plans) == 1 and stepper.launches_per_replay > 500
 
 
