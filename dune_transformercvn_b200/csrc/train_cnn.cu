@@ -602,11 +602,15 @@ __global__ void __launch_bounds__(256, 2) grad_pull_kernel(const PullArgs a) {
 #pragma unroll
   for (int i = 0; i < 8; ++i) bsum[i] = 0.f;
   if (ry < rpi) {
-    float mean[8], rstd[8], cA[8], cB[8];
+    // deferred BN1 mean corrections: v -= corrA + xhat * corrB  =  v - K0 - x * K1  (x is a bf16 value: folding the mean
+    // into K0 costs nothing; two constants per channel instead of four keep the kernel at two CTAs per SM without spills)
+    float K0[8], K1[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float* st = a.bstat + a.col0 + c + i;
-      mean[i] = st[0]; rstd[i] = st[a.ctot]; cA[i] = st[2 * a.ctot]; cB[i] = st[3 * a.ctot];
+      const float mean = st[0], rstd = st[a.ctot], cA = st[2 * a.ctot], cB = st[3 * a.ctot];
+      K1[i] = rstd * cB;
+      K0[i] = fmaf(-mean, K1[i], cA);
     }
     const unsigned R = (unsigned)(a.Hp * a.Wp);
     const float inv_keep = 1.f / (1.f - a.p);
@@ -644,12 +648,17 @@ __global__ void __launch_bounds__(256, 2) grad_pull_kernel(const PullArgs a) {
           }
         }
       }
-      for (int j = 0; j < a.n_src; ++j) {
-        uint4 di[U];
+      // the sources one ahead: the gradient rows of source j + 1 are in flight while source j is consumed
+      uint4 di[U], dn[U];
+      auto fetch = [&](int j, uint4 (&d)[U]) {
 #pragma unroll
         for (int u = 0; u < U; ++u)
           if (inside[u] && !ring[u])
-            di[u] = *reinterpret_cast<const uint4*>(a.src[j].dA + (m0 + u * stride) * (long long)a.src[j].ld + a.col0 + c);
+            d[u] = *reinterpret_cast<const uint4*>(a.src[j].dA + (m0 + u * stride) * (long long)a.src[j].ld + a.col0 + c);
+      };
+      if (a.n_src > 0) fetch(0, di);
+      for (int j = 0; j < a.n_src; ++j) {
+        if (j + 1 < a.n_src) fetch(j + 1, dn);
         const float* k = cst + (j * 3) * a.ncols + c;
         const float4 s0 = *reinterpret_cast<const float4*>(k), s1 = *reinterpret_cast<const float4*>(k + 4);
         const float4 h0 = *reinterpret_cast<const float4*>(k + a.ncols), h1 = *reinterpret_cast<const float4*>(k + a.ncols + 4);
@@ -667,6 +676,8 @@ __global__ void __launch_bounds__(256, 2) grad_pull_kernel(const PullArgs a) {
             v[u][i] = fmaf(d, fmaf(xv[u][i], sc[i], sh[i]) >= 0.f ? sc[i] : sa[i], v[u][i]);
           }
         }
+#pragma unroll
+        for (int u = 0; u < U; ++u) di[u] = dn[u];
       }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
@@ -674,7 +685,7 @@ __global__ void __launch_bounds__(256, 2) grad_pull_kernel(const PullArgs a) {
         const long long m = m0 + u * stride;
         if (!ring[u]) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[u][i] -= cA[i] + (xv[u][i] - mean[i]) * rstd[i] * cB[i];
+          for (int i = 0; i < 8; ++i) v[u][i] -= fmaf(xv[u][i], K1[i], K0[i]);
           if (MODE == 0) {
             if (a.p > 0.f) {
 #pragma unroll
