@@ -843,15 +843,14 @@ __global__ void stem_pool_bwd_kernel(const float* __restrict__ dblk, int ld, int
 __global__ void __launch_bounds__(256) stem_pool16_fwd_kernel(const __nv_bfloat16* __restrict__ z, const float* __restrict__ fold, int Hs,
                                                              int Ws, int C, __nv_bfloat16* __restrict__ blk, int ld, int H, int W,
                                                              long long total) {
-  const long long idx64 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx64 >= total) return;
-  const unsigned idx = (unsigned)idx64;
+  // grid (column octets of a pooled row, pooled row, image): one small division per thread instead of three
+  (void)total;
   const unsigned cv = (unsigned)C >> 3;
-  const int c = (int)(idx % cv) * 8;
-  unsigned r = idx / cv;
-  const int x = (int)(r % (unsigned)W); r /= (unsigned)W;
-  const int y = (int)(r % (unsigned)H);
-  const int n = (int)(r / (unsigned)H);
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (unsigned)W * cv) return;
+  const int x = (int)(t / cv);
+  const int c = (int)(t - (unsigned)x * cv) * 8;
+  const int y = blockIdx.y, n = blockIdx.z;
   float sc[8], sh[8], al[8], s[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { sc[i] = fold[c + i]; sh[i] = fold[C + c + i]; al[i] = fold[2 * C + c + i]; s[i] = 0.f; }
@@ -871,15 +870,14 @@ __global__ void __launch_bounds__(256) stem_pool16_fwd_kernel(const __nv_bfloat1
 
 __global__ void __launch_bounds__(256) stem_pool16_bwd_kernel(const __nv_bfloat16* __restrict__ dblk, int ld, int H, int W, int C,
                                                              __nv_bfloat16* __restrict__ dA, int Hs, int Ws, long long total) {
-  const long long idx64 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx64 >= total) return;
-  const unsigned idx = (unsigned)idx64;
+  // grid (column octets of a stem row, stem row, image)
+  (void)total;
   const unsigned cv = (unsigned)C >> 3;
-  const int c = (int)(idx % cv) * 8;
-  unsigned r = idx / cv;
-  const int ox = (int)(r % (unsigned)Ws); r /= (unsigned)Ws;
-  const int oy = (int)(r % (unsigned)Hs);
-  const int n = (int)(r / (unsigned)Hs);
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (unsigned)Ws * cv) return;
+  const int ox = (int)(t / cv);
+  const int c = (int)(t - (unsigned)ox * cv) * 8;
+  const int oy = blockIdx.y, n = blockIdx.z;
   const int py_lo = oy >= 2 ? (oy - 1) >> 1 : 0, py_hi = min(H - 1, oy >> 1);
   const int px_lo = ox >= 2 ? (ox - 1) >> 1 : 0, px_hi = min(W - 1, ox >> 1);
   float s[8];
@@ -1272,7 +1270,9 @@ int stem_pool16_forward(const void* z0_bf16, const float* fold, void* blk_bf16, 
   if (C % 8 || ld % 8) return fail(TCVN_ERR_UNSUPPORTED, "stem_pool16: widths must be multiples of 8");
   const long long total = (long long)n * H * W * (C / 8);
   if (total >= (1ll << 31) || (long long)n * Hs * Ws * (C / 8) >= (1ll << 31)) return fail(TCVN_ERR_UNSUPPORTED, "stem_pool16: too many images in one launch (%d)", n);
-  stem_pool16_fwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(z0_bf16), fold, Hs, Ws, C,
+  if (H > 65535 || n > 65535) return fail(TCVN_ERR_UNSUPPORTED, "stem_pool16: grid too large (%d rows, %d images)", H, n);
+  const int tpr = W * (C / 8), nb = ceil_div(tpr, 256), bs = (ceil_div(tpr, nb) + 31) & ~31;   // threads per pooled row, evenly split
+  stem_pool16_fwd_kernel<<<dim3((unsigned)nb, (unsigned)H, (unsigned)n), bs, 0, stream>>>(static_cast<const __nv_bfloat16*>(z0_bf16), fold, Hs, Ws, C,
                                                                                static_cast<__nv_bfloat16*>(blk_bf16), ld, H, W, total);
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
@@ -1283,7 +1283,9 @@ int stem_pool16_backward(const void* dblk_bf16, int ld, void* dz_bf16, int n, in
   if (C % 8 || ld % 8) return fail(TCVN_ERR_UNSUPPORTED, "stem_pool16: widths must be multiples of 8");
   const long long total = (long long)n * Hs * Ws * (C / 8);
   if (total >= (1ll << 31)) return fail(TCVN_ERR_UNSUPPORTED, "stem_pool16: too many images in one launch (%d)", n);
-  stem_pool16_bwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(dblk_bf16), ld, H, W, C,
+  if (Hs > 65535 || n > 65535) return fail(TCVN_ERR_UNSUPPORTED, "stem_pool16: grid too large (%d rows, %d images)", Hs, n);
+  const int tpr = Ws * (C / 8), nb = ceil_div(tpr, 256), bs = (ceil_div(tpr, nb) + 31) & ~31;
+  stem_pool16_bwd_kernel<<<dim3((unsigned)nb, (unsigned)Hs, (unsigned)n), bs, 0, stream>>>(static_cast<const __nv_bfloat16*>(dblk_bf16), ld, H, W, C,
                                                                                static_cast<__nv_bfloat16*>(dz_bf16), Hs, Ws, total);
   TCVN_LAUNCH_CHECK();
   return TCVN_OK;
