@@ -1063,7 +1063,7 @@ static int colsums_launch(int mode, const void* X, bool x_bf16, int ldx, int xco
     const int gx = ceil_div(cv, tv);
     // short slabs: one slab = 16 row-steps of a CTA, at most ~4 CTAs per SM in total
     long long vslabs = ceil_div_ll(m_total, (long long)rpi * kVecU * 4);
-    const long long cap = (long long)(148 * 4 / gx > 1 ? 148 * 4 / gx : 1);
+    const long long cap = (long long)(148 * 2 / gx > 1 ? 148 * 2 / gx : 1);
     if (vslabs > cap) vslabs = cap;
     if (one_slab) vslabs = 1;
     p.rows_per_slab = (int)ceil_div_ll(m_total, vslabs);
@@ -1305,7 +1305,7 @@ int bn1_bwd_reduce(const void* X, int ldx, const void* D, int ldd, const float* 
   const int rpi = 256 / tv;
   const int gx = ceil_div(cv, tv);
   long long vslabs = ceil_div_ll(m_total, (long long)rpi * 4 * 4);
-  const long long cap = (long long)(148 * 4 / gx > 1 ? 148 * 4 / gx : 1);
+  const long long cap = (long long)(148 * 2 / gx > 1 ? 148 * 2 / gx : 1);
   if (vslabs > cap) vslabs = cap;
   p.rows_per_slab = (int)ceil_div_ll(m_total, vslabs);
   vslabs = ceil_div_ll(m_total, p.rows_per_slab);
