@@ -1171,7 +1171,7 @@ int bnact_bwd_apply_typed(const void* D, bool d_bf16, int ldd, int dcol0, const 
     const int rpi = 256 / tv;
     const int gx = ceil_div(cv, tv);
     long long vslabs = ceil_div_ll(m_total, (long long)rpi * kVecU * 2);
-    const long long cap = (long long)(148 * 8 / gx > 1 ? 148 * 8 / gx : 1);
+    const long long cap = (long long)(148 * 2 / gx > 1 ? 148 * 2 / gx : 1);
     if (vslabs > cap) vslabs = cap;
     const int rows_per_slab = (int)ceil_div_ll(m_total, vslabs);
     const int slabs = (int)ceil_div_ll(m_total, rows_per_slab);
