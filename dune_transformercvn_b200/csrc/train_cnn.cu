@@ -431,7 +431,7 @@ struct TWalk {
 typedef __nv_bfloat16 bf;
 
 constexpr int kPullMax = 16;            // later layers of a block a gradient can be pulled from
-constexpr int kPullCtasMax = 148 * 4;   // grid (and bias-gradient slots) of grad_pull_kernel
+constexpr int kPullCtasMax = 148 * 2;   // grid (and bias-gradient slots) of grad_pull_kernel
 constexpr long long kFuseDgradRows = 160000;   // up to here the BN2 backward reductions are fused into the dgrad epilogue
 
 struct T16Layer { size_t w1b, w1d, w2b, wd, fold1, fold2, mid_raw, mid_act, dA1; };
