@@ -49,7 +49,12 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const GemmDev g) {
   const int bk = tid / BT, bn = (tid % BT) * 4;
   const bool transform = g.a_scale != nullptr;
 
-  for (int t = 0; t < g.taps; ++t) {
+  // k-steps of all taps as one sequence; the operands of step i + 1 are loaded into registers while step i is computed
+  // from shared memory (with the loads issued right before the barrier the small GEMMs of the sequence part - 8 to 24
+  // steps - were a chain of exposed global-memory latencies: 22 us per launch whatever the size)
+  float av[4];
+  float4 bv;
+  auto load = [&](int t, int k0) {
     const long long gm = m0 + ar + g.tap_off[t];
     bool row_ok = gm >= 0 && gm < g.m_total;
     if (row_ok && g.a_ring_Hp > 0) {
@@ -59,38 +64,42 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const GemmDev g) {
     }
     const TA* arow = A + (row_ok ? gm : 0) * (long long)g.lda;
     const float* Wt = g.W + (size_t)t * g.K * g.N;
-    for (int k0 = 0; k0 < g.K; k0 += kBK) {
-      float av[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int k = k0 + akq + i;
-        float v = 0.f;
-        if (row_ok && k < g.K) {
-          v = to_f32<TA>(arow[k]);
-          if (transform) v = prelu(fmaf(v, __ldg(g.a_scale + k), __ldg(g.a_shift + k)), __ldg(g.a_alpha + k));
-        }
-        av[i] = v;
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + akq + i;
+      float v = 0.f;
+      if (row_ok && k < g.K) {
+        v = to_f32<TA>(arow[k]);
+        if (transform) v = prelu(fmaf(v, __ldg(g.a_scale + k), __ldg(g.a_shift + k)), __ldg(g.a_alpha + k));
       }
-      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (bk < kBK && k0 + bk < g.K && n0 + bn < g.N)
-        bv = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)(k0 + bk) * g.N + n0 + bn));
-      __syncthreads();
+      av[i] = v;
+    }
+    bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bk < kBK && k0 + bk < g.K && n0 + bn < g.N)
+      bv = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)(k0 + bk) * g.N + n0 + bn));
+  };
+  int t = 0, k0 = 0;
+  load(0, 0);
+  while (t < g.taps) {
+    __syncthreads();
 #pragma unroll
-      for (int i = 0; i < 4; ++i) As[akq + i][ar] = av[i];
-      if (bk < kBK) *reinterpret_cast<float4*>(&Bs[bk][bn]) = bv;
-      __syncthreads();
+    for (int i = 0; i < 4; ++i) As[akq + i][ar] = av[i];
+    if (bk < kBK) *reinterpret_cast<float4*>(&Bs[bk][bn]) = bv;
+    __syncthreads();
+    k0 += kBK;
+    if (k0 >= g.K) { k0 = 0; ++t; }
+    if (t < g.taps) load(t, k0);
 #pragma unroll
-      for (int k = 0; k < kBK; ++k) {
-        const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-        const float a[4] = {a4.x, a4.y, a4.z, a4.w};
-        float b[TN];
+    for (int k = 0; k < kBK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+      float b[TN];
 #pragma unroll
-        for (int j = 0; j < TN; ++j) b[j] = Bs[k][tx * TN + j];
+      for (int j = 0; j < TN; ++j) b[j] = Bs[k][tx * TN + j];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-      }
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
   }
   TO* out = static_cast<TO*>(g.out);
