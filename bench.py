@@ -483,11 +483,11 @@ def kernel_rooflines(net, resident, batch, dev, pk, args):
             nbytes = pixels * k * 2 + 128 * k * 2 + pixels * 128 * 2
             gbs = nbytes / (us * 1e-6) / 1e9
             out[name] = {"bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
-                         "traffic": 756.4e6 * n / 194, "kernel": "umma_gemm_kernel<true> (BN+PReLU -> 1x1 conv -> BN+PReLU), "
+                         "traffic": 653.8e6 * n / 194, "kernel": "umma_gemm_kernel<true> (BN+PReLU -> 1x1 conv -> BN+PReLU), "
                          f"dense1 layer 3, {n} images", "us_per_launch": us, "algorithmic_bytes": nbytes,
                          "peak_source": pk["source"] + " copy bandwidth",
-                         "traffic_source": "ncu dram__bytes_read+write (445.3 + 311.1 MB at 194 images), profiles/r2_conv1_194img.txt, "
-                                           "scaled by images"}
+                         "traffic_source": "ncu dram__bytes_read+write (356.3 + 297.5 MB at 194 images; part of the output is still "
+                                           "dirty in L2 when the kernel ends), profiles/r2_conv1_dram_bytes_wres.csv, scaled by images"}
         else:
             flops = pixels * 2 * 9 * 128 * 32
             tf = flops / (us * 1e-6) / 1e12

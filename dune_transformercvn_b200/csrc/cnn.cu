@@ -45,15 +45,15 @@ struct Walk {
     if (pixels == nullptr && bins != nullptr)
       return launch_stem_coo_binned(i0, n, n_binned, nnz_binned, d.in_channels, d.height, d.width, pf(pk, P.p_w0),
                                     pf(pk, P.p_s_scale), pf(pk, P.p_s_shift), pf(pk, P.p_s_alpha), d.init_features,
-                                    ws + B0.ws_blk, B0.ctot, B0.H, B0.W, f32, bins, st);
+                                    ws + B0.ws_blk, B0.ld, B0.H, B0.W, f32, bins, st);
     if (pixels == nullptr)
       return launch_stem_coo(coords, values, values_u8, reinterpret_cast<const long long*>(ws + P.ws_hitofs), i0, divisor,
                              n, d.in_channels, d.height, d.width, pf(pk, P.p_w0), pf(pk, P.p_s_scale),
-                             pf(pk, P.p_s_shift), pf(pk, P.p_s_alpha), d.init_features, ws + B0.ws_blk, B0.ctot, B0.H,
+                             pf(pk, P.p_s_shift), pf(pk, P.p_s_alpha), d.init_features, ws + B0.ws_blk, B0.ld, B0.H,
                              B0.W, f32, st);
     return launch_stem(pixels + (size_t)i0 * img_floats, n, d.in_channels, d.height, d.width, pf(pk, P.p_w0),
                        pf(pk, P.p_s_scale), pf(pk, P.p_s_shift), pf(pk, P.p_s_alpha), d.init_features, ws + B0.ws_blk,
-                       B0.ctot, B0.H, B0.W, f32, st);
+                       B0.ld, B0.H, B0.W, f32, st);
   }
 
   int dense_block(const BlockPlan& B, int n) {
@@ -64,7 +64,7 @@ struct Walk {
     for (const LayerPlan& L : B.layers) {
       if (f32) {
         GemmArgs g{};
-        g.A = blk; g.lda = B.ctot; g.m_total = rows; g.K = L.kphys; g.taps = 1; g.tap_off[0] = 0;
+        g.A = blk; g.lda = B.ld; g.m_total = rows; g.K = L.kphys; g.taps = 1; g.tap_off[0] = 0;
         g.W = pf(pk, L.p_w1); g.N = P.mid;
         g.a_scale = pf(pk, L.p_a_scale); g.a_shift = pf(pk, L.p_a_shift); g.a_alpha = pf(pk, L.p_a_alpha);
         g.o_scale = pf(pk, L.p_o_scale); g.o_shift = pf(pk, L.p_o_shift); g.o_alpha = pf(pk, L.p_o_alpha);
@@ -76,7 +76,7 @@ struct Walk {
         for (int t = 0; t < 9; ++t) c.tap_off[t] = (t / 3 - 1) * B.Wp + (t % 3 - 1);
         c.W = pf(pk, L.p_w2); c.N = d.growth;
         c.o_shift = pf(pk, L.p_b2);
-        c.out = blk; c.ldo = B.ctot; c.out_col0 = L.kphys; c.ring_Hp = B.Hp; c.ring_Wp = B.Wp;
+        c.out = blk; c.ldo = B.ld; c.out_col0 = L.kphys; c.ring_Hp = B.Hp; c.ring_Wp = B.Wp;
         c.a_is_f32 = true; c.out_is_f32 = true;
         TCVN_TRY(launch_simt_gemm(c, st));
       } else {
@@ -91,16 +91,16 @@ struct Walk {
     const BlockPlan& B = P.blocks[b];
     const BlockPlan& Nx = P.blocks[b + 1];
     void* pool = ws + P.ws_pool;
-    TCVN_TRY(launch_act_pool2(ws + B.ws_blk, n, B.H, B.W, B.ctot, B.ctot, pf(pk, B.p_t_scale), pf(pk, B.p_t_shift),
+    TCVN_TRY(launch_act_pool2(ws + B.ws_blk, n, B.H, B.W, B.ld, B.ctot, pf(pk, B.p_t_scale), pf(pk, B.p_t_shift),
                               pf(pk, B.p_t_alpha), pool, Nx.H, Nx.W, f32, st));
     if (!f32)
-      return umma_transition(P, B, Nx, pk, pool, ws + Nx.ws_blk + (size_t)j * Nx.R * Nx.ctot * P.esize,
+      return umma_transition(P, B, Nx, pk, pool, ws + Nx.ws_blk + (size_t)j * Nx.R * Nx.ld * P.esize,
                              (long long)n * Nx.R, st);
     GemmArgs g{};
     g.A = pool; g.lda = B.ctot; g.m_total = (long long)n * Nx.R; g.K = B.ctot; g.taps = 1; g.tap_off[0] = 0;
     g.W = pf(pk, B.p_tw); g.N = B.toutp;
     g.o_shift = pf(pk, B.p_tb);
-    g.out = ws + Nx.ws_blk + (size_t)j * Nx.R * Nx.ctot * P.esize; g.ldo = Nx.ctot; g.out_col0 = 0;
+    g.out = ws + Nx.ws_blk + (size_t)j * Nx.R * Nx.ld * P.esize; g.ldo = Nx.ld; g.out_col0 = 0;
     g.ring_Hp = Nx.Hp; g.ring_Wp = Nx.Wp;
     g.a_is_f32 = f32; g.out_is_f32 = f32;
     return launch_simt_gemm(g, st);
@@ -125,7 +125,7 @@ struct Walk {
     const tcvn_cnn_desc& d = P.d;
     const BlockPlan& last = P.blocks.back();
     float* gap = reinterpret_cast<float*>(ws + P.ws_gap);
-    TCVN_TRY(launch_act_gap(ws + last.ws_blk, n, last.H, last.W, last.ctot, last.ctot, pf(pk, P.p_f_scale),
+    TCVN_TRY(launch_act_gap(ws + last.ws_blk, n, last.H, last.W, last.ld, last.ctot, pf(pk, P.p_f_scale),
                             pf(pk, P.p_f_shift), pf(pk, P.p_f_alpha), gap, f32, st));
     GemmArgs g{};
     g.A = gap; g.lda = last.ctot; g.m_total = n; g.K = last.ctot; g.taps = 1; g.tap_off[0] = 0;
@@ -148,7 +148,7 @@ extern "C" int tcvn_cnn_forward(const tcvn_cnn_desc* d, tcvn_precision prec, con
   if (n_images == 0) return TCVN_OK;
   TCVN_CHECK_ARG(pixels && embedding, "cnn_forward: null pointer");
   CnnPlan P;
-  TCVN_CHECK_ARG(CnnPlan::build(*d, prec, n_images, &P), "cnn_forward: bad descriptor");
+  TCVN_CHECK_ARG(CnnPlan::build(*d, prec, n_images, &P, true), "cnn_forward: bad descriptor");
   if (workspace_bytes < P.ws_bytes)
     return fail(TCVN_ERR_WORKSPACE, "cnn_forward: workspace %zu < %zu bytes", workspace_bytes, P.ws_bytes);
   Walk w{P, static_cast<const char*>(packed), pixels, static_cast<char*>(workspace), stream, prec == TCVN_FP32};
@@ -173,7 +173,7 @@ extern "C" int tcvn_cnn_forward_sparse(const tcvn_cnn_desc* d, tcvn_precision pr
   if (n_images == 0) return TCVN_OK;
   TCVN_CHECK_ARG(embedding && (nnz == 0 || (coords && values)), "cnn_forward_sparse: null pointer");
   CnnPlan P;
-  TCVN_CHECK_ARG(CnnPlan::build(*d, prec, n_images, &P), "cnn_forward_sparse: bad descriptor");
+  TCVN_CHECK_ARG(CnnPlan::build(*d, prec, n_images, &P, true), "cnn_forward_sparse: bad descriptor");
   if (workspace_bytes < P.ws_bytes)
     return fail(TCVN_ERR_WORKSPACE, "cnn_forward_sparse: workspace %zu < %zu bytes", workspace_bytes, P.ws_bytes);
   Walk w{P, static_cast<const char*>(packed), nullptr, static_cast<char*>(workspace), stream, prec == TCVN_FP32};
@@ -201,7 +201,7 @@ extern "C" int tcvn_cnn_forward_sparse(const tcvn_cnn_desc* d, tcvn_precision pr
 
 extern "C" size_t tcvn_cnn_workspace_bytes_sparse(const tcvn_cnn_desc* d, tcvn_precision prec, int n_images, int64_t nnz) {
   CnnPlan P;
-  if (!d || nnz < 0 || !CnnPlan::build(*d, prec, n_images, &P)) { set_error("cnn: bad descriptor"); return 0; }
+  if (!d || nnz < 0 || !CnnPlan::build(*d, prec, n_images, &P, true)) { set_error("cnn: bad descriptor"); return 0; }
   return align_up(P.ws_bytes, 1024) + stem_bins_bytes(n_images, P.blocks[0].H, P.blocks[0].W, nnz);
 }
 
@@ -211,7 +211,7 @@ extern "C" int tcvn_cnn_run_layer(const tcvn_cnn_desc* d, tcvn_precision prec, c
   TCVN_CHECK_ARG(d && packed && workspace, "cnn_run_layer: null pointer");
   TCVN_CHECK_ARG(prec == TCVN_BF16, "cnn_run_layer: only the tcgen05 path has separately launchable layer kernels");
   CnnPlan P;
-  TCVN_CHECK_ARG(CnnPlan::build(*d, prec, n_images, &P), "cnn_run_layer: bad descriptor");
+  TCVN_CHECK_ARG(CnnPlan::build(*d, prec, n_images, &P, true), "cnn_run_layer: bad descriptor");
   if (workspace_bytes < P.ws_bytes)
     return fail(TCVN_ERR_WORKSPACE, "cnn_run_layer: workspace %zu < %zu bytes", workspace_bytes, P.ws_bytes);
   TCVN_CHECK_ARG(block >= 0 && block < (int)P.blocks.size(), "cnn_run_layer: no block %d", block);
@@ -228,7 +228,7 @@ extern "C" int tcvn_cnn_read_stage(const tcvn_cnn_desc* d, tcvn_precision prec, 
                                    tcvn_stream_t stream) {
   TCVN_CHECK_ARG(d && workspace && channels && h && w, "cnn_read_stage: null pointer");
   CnnPlan P;
-  TCVN_CHECK_ARG(CnnPlan::build(*d, prec, n_images, &P), "cnn_read_stage: bad descriptor");
+  TCVN_CHECK_ARG(CnnPlan::build(*d, prec, n_images, &P, true), "cnn_read_stage: bad descriptor");
   TCVN_CHECK_ARG(n_images <= P.chunk, "cnn_read_stage: only the last chunk (%d images) is still in the workspace", P.chunk);
   TCVN_CHECK_ARG(stage >= 0 && stage <= 2 * (int)P.blocks.size() - 1, "cnn_read_stage: no stage %d", stage);
   const int b = stage == 0 ? 0 : (stage % 2 == 1 ? (stage - 1) / 2 : stage / 2);
@@ -237,6 +237,6 @@ extern "C" int tcvn_cnn_read_stage(const tcvn_cnn_desc* d, tcvn_precision prec, 
   const int c = (stage % 2 == 1) ? B.clog : B.c0;
   *channels = c; *h = B.H; *w = B.W;
   if (out == nullptr) return TCVN_OK;
-  return launch_ring_to_nchw(static_cast<const char*>(workspace) + B.ws_blk, n_images, B.H, B.W, B.ctot, c, B.c0,
+  return launch_ring_to_nchw(static_cast<const char*>(workspace) + B.ws_blk, n_images, B.H, B.W, B.ld, c, B.c0,
                              B.c0p - B.c0, out, prec == TCVN_FP32, stream);
 }

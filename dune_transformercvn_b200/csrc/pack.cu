@@ -205,7 +205,7 @@ extern "C" size_t tcvn_cnn_packed_bytes(const tcvn_cnn_desc* d, tcvn_precision p
 
 extern "C" size_t tcvn_cnn_workspace_bytes(const tcvn_cnn_desc* d, tcvn_precision prec, int n_images) {
   CnnPlan P;
-  if (!d || !CnnPlan::build(*d, prec, n_images, &P)) { set_error("cnn: bad descriptor"); return 0; }
+  if (!d || !CnnPlan::build(*d, prec, n_images, &P, true)) { set_error("cnn: bad descriptor"); return 0; }
   return P.ws_bytes;
 }
 

@@ -42,6 +42,12 @@ struct LayerPlan {
 struct BlockPlan {
   int H, W, Hp, Wp, R;  // interior size, padded size, rows per image (Hp*Wp)
   int c0, c0p, ctot;    // logical / padded input channels, physical channels of the block buffer
+  int ld;               // row pitch of the block buffer in elements.  Eval walk: ctot rounded up to 64 channels, so that a
+                        // row is a whole number of 128-byte lines and every 64-channel TMA box row is exactly ONE line.
+                        // ncu on block 1 (ctot = 160, 320-byte rows): a 128-byte box row straddled two lines on every
+                        // second row and DRAM fills whole lines - conv1 read 192 B per row for K = 64 and the whole
+                        // 320 B for K = 96 / 128.  The pad channels are never written and never read (the tensor maps
+                        // clip at ctot).  Training walk: ld == ctot (its passes read whole rows).
   int clog;             // logical output channels (c0 + growth*layers)
   std::vector<LayerPlan> layers;
   // transition after this block (absent after the last one)
@@ -86,7 +92,7 @@ struct CnnPlan {
   int chunk;
   size_t ws_stem, ws_mid, ws_pool, ws_gap, ws_hitofs, ws_bytes;
 
-  static bool build(const tcvn_cnn_desc& d, tcvn_precision prec, int n_images, CnnPlan* out);
+  static bool build(const tcvn_cnn_desc& d, tcvn_precision prec, int n_images, CnnPlan* out, bool pad_pitch = false);
   // physical channel of logical channel c inside block b's buffer
   int phys(int b, int c) const {
     const BlockPlan& B = blocks[b];
@@ -94,9 +100,10 @@ struct CnnPlan {
   }
 };
 
-inline bool CnnPlan::build(const tcvn_cnn_desc& d, tcvn_precision prec, int n_images, CnnPlan* out) {
+inline bool CnnPlan::build(const tcvn_cnn_desc& d, tcvn_precision prec, int n_images, CnnPlan* out, bool pad_pitch) {
   if (d.num_blocks < 1 || d.num_blocks > TCVN_MAX_BLOCKS) return false;
   if (d.in_channels < 1 || d.init_features < 1 || d.growth < 1 || d.bn_size < 1 || d.out_features < 1) return false;
+  static const bool pad_on = [] { const char* v = getenv("TCVN_PAD_PITCH"); return !(v && v[0] == '0'); }();   // A/B switch
   CnnPlan& P = *out;
   P.d = d;
   P.prec = prec;
@@ -134,6 +141,7 @@ inline bool CnnPlan::build(const tcvn_cnn_desc& d, tcvn_precision prec, int n_im
     const int nl = d.block_layers[b];
     if (nl < 0) return false;
     B.ctot = B.c0p + nl * d.growth;
+    B.ld = pad_pitch && pad_on ? round_up(B.ctot, kKChunk) : B.ctot;
     B.clog = c + nl * d.growth;
     for (int i = 0; i < nl; ++i) {
       LayerPlan L;
@@ -213,7 +221,7 @@ inline bool CnnPlan::build(const tcvn_cnn_desc& d, tcvn_precision prec, int n_im
   };
   int prev = 0;
   for (auto& B : P.blocks) {
-    const size_t per_image = (size_t)B.R * (B.ctot + P.mid) * P.esize;
+    const size_t per_image = (size_t)B.R * (B.ld + P.mid) * P.esize;
     int c = (int)(l2_budget / per_image);
     if (c < 1) c = 1;
     if (prev) c = c / prev * prev;
@@ -243,7 +251,7 @@ inline bool CnnPlan::build(const tcvn_cnn_desc& d, tcvn_precision prec, int n_im
   P.ws_stem = 0;  // the stem is fused with its pooling: no pre-pool map in memory
   size_t mid_rows = 0, pool_elems = 0;
   for (auto& B : P.blocks) {
-    B.ws_blk = wtake((size_t)B.chunk * B.R * (size_t)B.ctot * P.esize);
+    B.ws_blk = wtake((size_t)B.chunk * B.R * (size_t)B.ld * P.esize);
     if ((size_t)B.chunk * B.R > mid_rows) mid_rows = (size_t)B.chunk * B.R;
   }
   for (size_t b = 0; b + 1 < P.blocks.size(); ++b) {

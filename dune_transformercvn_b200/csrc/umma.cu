@@ -63,9 +63,14 @@ int make_map(const void* base, long long rows, int cols, int pitch, int box_cols
   cuuint64_t gstride[1] = {(cuuint64_t)pitch * sizeof(bf16)};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
+  static const CUtensorMapL2promotion promo = [] {
+    const char* v = getenv("TCVN_TMAP_PROMO");
+    const int n = v ? atoi(v) : 0;
+    return n == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : n == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+         : n == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  }();
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(TCVN_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%d pitch=%d box=%dx%d", (int)r, rows,
                 cols, pitch, box_cols, box_rows);
@@ -125,7 +130,9 @@ namespace tcvn {
 //   warps 10-17 two epilogue groups, one per TMEM accumulator: TMEM -> regs -> +shift, PReLU, ring rows -> 0,
 //               bf16 -> swizzled staging tile -> TMA store
 // ------------------------------------------------------------------------------------------------
-constexpr int kC1Stages = 4;
+constexpr int kC1Stages = 4;     // pipeline stages when the weights stream with the activations (one A + one W chunk per stage)
+constexpr int kC1StagesMax = 8;  // ... and when the weights are resident (K <= 256, one N tile): the 16 KB W slots become A stages
+constexpr int kC1Acc = 4;       // TMEM accumulators (all 512 columns): the MMA warp runs up to two tiles ahead of each epilogue group
 constexpr int kC1Threads = 576;
 constexpr int kTileM = 128;
 constexpr int kMid = 128;              // N tile = bottleneck width the kernels are specialised for
@@ -153,6 +160,11 @@ struct GemmParams {
   // the BatchNorm that follows (n_tiles_n == 1).  Every (CTA, epilogue group) stores its partial sums in its own slot,
   // stats[(2 * cta + group)][2][128]; the consumer adds the slots in a fixed order (no atomics: bit-reproducible).
   double* stats;
+  // weights-resident mode (kchunks <= 4, one N tile: every conv1 of dense blocks 1-2): the whole [128 x K] weight matrix is
+  // loaded once per CTA and the pipeline has `stages` A-only stages.  The clock-stamp trace of the streaming form showed a
+  // stage cycle of 3.2 us (1.2-2.2 us of it TMA latency under load) with 4 stages in flight: 0.8 us per chunk, below what
+  // HBM delivers - the kernel was bound by bytes in flight, not by bandwidth, the epilogue or the tensor pipe.
+  int wres, stages;
 };
 
 __device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
@@ -177,34 +189,36 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                   // [stages][16 KB]
-  uint8_t* sW = smem + kC1Stages * kStageA;             // [stages][16 KB]
-  uint8_t* sOut = sW + kC1Stages * kStageW;             // [2 groups][2 halves][128 rows x 128 B], swizzled
+  uint8_t* sW = smem + p.stages * kStageA;              // [stages][16 KB], or [kchunks][16 KB] resident
+  uint8_t* sOut = sW + (p.wres ? p.kchunks : p.stages) * kStageW;   // [2 groups][2 halves][128 rows x 128 B], swizzled
   uint8_t* sXA = sOut + 4 * kStageA;                    // [128 rows x 128 B]: k0 = k1 = 1.0, rest 0   (MMASHIFT)
   uint8_t* sXB = sXA + kStageA;                         // [128 n x 128 B]: k0 = hi(shift[n]), k1 = lo(shift[n])
   float* s_epi = reinterpret_cast<float*>(sXB + kStageW);  // [2 groups][128 shift + 64 packed slopes]
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + 2 * 192);
   uint64_t* full = bars;                    // TMA -> transform (or MMA)
-  uint64_t* ready = bars + kC1Stages;       // transform -> MMA
-  uint64_t* empty = bars + 2 * kC1Stages;   // MMA -> TMA
-  uint64_t* tfull = bars + 3 * kC1Stages;   // MMA -> epilogue   [2]
-  uint64_t* tempty = tfull + 2;             // epilogue -> MMA   [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* ready = bars + kC1StagesMax;       // transform -> MMA
+  uint64_t* empty = bars + 2 * kC1StagesMax;   // MMA -> TMA
+  uint64_t* tfull = bars + 3 * kC1StagesMax;   // MMA -> epilogue   [kC1Acc]
+  uint64_t* tempty = tfull + kC1Acc;        // epilogue -> MMA   [kC1Acc]
+  uint64_t* wfull = tempty + kC1Acc;           // resident weight chunk kc has landed   [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kC1Stages; ++s) {
+    for (int kc = 0; kc < 4; ++kc) ptx::mbar_init(&wfull[kc], 1);
+    for (int s = 0; s < kC1StagesMax; ++s) {
       ptx::mbar_init(&full[s], 1);
       ptx::mbar_init(&ready[s], kXformThreads);
       ptx::mbar_init(&empty[s], 1);
     }
-    for (int a = 0; a < 2; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 128); }
+    for (int a = 0; a < kC1Acc; ++a) { ptx::mbar_init(&tfull[a], 1); ptx::mbar_init(&tempty[a], 128); }
     ptx::fence_mbar_init();
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmW);
     ptx::prefetch_tmap(&tmO);
     ptx::prefetch_tmap(&tmA2);
   }
-  if (warp == 0) ptx::tmem_alloc(tmem_slot, 256);
+  if (warp == 0) ptx::tmem_alloc(tmem_slot, kC1Acc * kMid);
   if (MMASHIFT) {
     uint4* z = reinterpret_cast<uint4*>(sXA);
     for (int i = threadIdx.x; i < (kStageA + kStageW) / 16; i += kC1Threads) z[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -228,21 +242,27 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      if (p.wres) {   // one barrier per chunk: the first tile's MMAs start as soon as THEIR chunk is there
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          ptx::mbar_arrive_expect_tx(&wfull[kc], p.ntile * 128);
+          ptx::tma_load_2d(sW + kc * kStageW, &tmW, &wfull[kc], kc * 64, 0);
+        }
+      }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
         const int tap_chunks = p.n_taps * p.chunks_per_tap;
         int tap = 0, kk = 0;
         for (int kc = 0; kc < p.kchunks; ++kc) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&full[stage], kStageA + p.ntile * 128);
+          ptx::mbar_arrive_expect_tx(&full[stage], kStageA + (p.wres ? 0 : p.ntile * 128));
           if (kc < tap_chunks) {
             ptx::tma_load_2d(sA + stage * kStageA, &tmA, &full[stage], kk * 64 + p.tap_col[tap], mt * kTileM + p.tap_off[tap]);
             if (++kk == p.chunks_per_tap) { kk = 0; ++tap; }
           } else {
             ptx::tma_load_2d(sA + stage * kStageA, &tmA2, &full[stage], (kc - tap_chunks) * 64, mt * kTileM);
           }
-          ptx::tma_load_2d(sW + stage * kStageW, &tmW, &full[stage], kc * 64, nt * p.ntile);
-          if (++stage == kC1Stages) { stage = 0; phase ^= 1; }
+          if (!p.wres) ptx::tma_load_2d(sW + stage * kStageW, &tmW, &full[stage], kc * 64, nt * p.ntile);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -251,6 +271,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
       const uint32_t idesc = ptx::umma_idesc_bf16(kTileM, p.ntile);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      bool w_pending = p.wres != 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
@@ -260,18 +281,20 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
                          ptx::umma_desc_join(ptx::kUmmaDescHiSw128, ptx::umma_desc_lo(ptx::smem_u32(sXB))), idesc, 0);
         for (int kc = 0; kc < p.kchunks; ++kc) {
           ptx::mbar_wait(TRANSFORM ? &ready[stage] : &full[stage], phase);
+          if (w_pending) ptx::mbar_wait(&wfull[kc], 0);
           ptx::tc_fence_after();
           const uint32_t a_lo = ptx::umma_desc_lo(ptx::smem_u32(sA + stage * kStageA));
-          const uint32_t w_lo = ptx::umma_desc_lo(ptx::smem_u32(sW + stage * kStageW));
+          const uint32_t w_lo = ptx::umma_desc_lo(ptx::smem_u32(sW + (p.wres ? kc : stage) * kStageW));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             ptx::umma_bf16(d_tmem, ptx::umma_desc_join(ptx::kUmmaDescHiSw128, a_lo + 2 * k),
                            ptx::umma_desc_join(ptx::kUmmaDescHiSw128, w_lo + 2 * k), idesc, MMASHIFT || (kc | k) != 0);
           ptx::umma_commit(&empty[stage]);
-          if (++stage == kC1Stages) { stage = 0; phase ^= 1; }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
+        w_pending = false;
         ptx::umma_commit(&tfull[acc]);
-        if ((acc ^= 1) == 0) acc_phase ^= 1;
+        if (++acc == kC1Acc) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (warp < 10) {
@@ -327,7 +350,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
         }
         ptx::fence_proxy_async_smem();
         ptx::mbar_arrive(&ready[stage]);
-        if (++stage == kC1Stages) { stage = 0; phase ^= 1; }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       };
       if (p.kchunks <= 2) {
         // K <= 128 (dense block 1, the most expensive layers): the constants of both K chunks stay in registers for
@@ -359,8 +382,8 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
     uint8_t* stg = sOut + grp * 2 * kStageA;
     float* s_shift = s_epi + grp * 192;                                   // [128] fp32
     uint32_t* s_alpha2 = reinterpret_cast<uint32_t*>(s_shift + kMid);     // [64] bf16x2
-    uint32_t acc_phase = 0;
     int it = 0;
+    int mine = 0;   // tiles this group has drained: accumulator grp + 2 * (mine & 1), barrier parity (mine >> 1) & 1
     float st1[8], st2[8];   // training statistics: this thread's 8 columns over its rows of every tile (fp32 partials)
 #pragma unroll
     for (int q = 0; q < 8; ++q) { st1[q] = 0.f; st2[q] = 0.f; }
@@ -385,7 +408,10 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
           s_alpha2[e] = *reinterpret_cast<const uint32_t*>(&a2);
         }
       }
-      if (lane == 0) ptx::mbar_wait(&tfull[grp], acc_phase);
+      const int acc = grp + 2 * (mine & 1);
+      const uint32_t acc_phase = (uint32_t)(mine >> 1) & 1u;
+      ++mine;
+      if (lane == 0) ptx::mbar_wait(&tfull[acc], acc_phase);
       __syncwarp();
       ptx::tc_fence_after();
       if (issuer) ptx::tma_store_wait_read();  // this group's previous store has drained the staging tile
@@ -393,8 +419,8 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
 #pragma unroll 1
       for (int c = 0; c < (p.ntile >> 5); c += 2) {
         uint32_t r0[32], r1[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(g * 32) << 16) + grp * kMid + c * 32, r0);
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(g * 32) << 16) + grp * kMid + c * 32 + 32, r1);
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(g * 32) << 16) + acc * kMid + c * 32, r0);
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(g * 32) << 16) + acc * kMid + c * 32 + 32, r1);
         ptx::tmem_ld_wait();
         uint8_t* orow = stg + (c >> 1) * kStageA + row * 128;
         const __nv_bfloat162 zero2 = __floats2bfloat162_rn(0.f, 0.f);
@@ -426,7 +452,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
         }
       }
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&tempty[grp]);
+      ptx::mbar_arrive(&tempty[acc]);
       ptx::fence_proxy_async_smem();
       ptx::named_bar_sync(1 + grp, 128);
       if (issuer) {
@@ -457,7 +483,6 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
           }
         }
       }
-      acc_phase ^= 1;
     }
     if (issuer) ptx::tma_store_wait_all();
     if (p.stats != nullptr) {
@@ -482,7 +507,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 0) ptx::tmem_dealloc(tmem_base, 256);
+  if (warp == 0) ptx::tmem_dealloc(tmem_base, kC1Acc * kMid);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -728,14 +753,30 @@ __global__ void __launch_bounds__(kC2Threads, 1) umma_conv2_kernel(const __grid_
 // ------------------------------------------------------------------------------------------------
 static inline const float* pf(const char* packed, size_t off) { return reinterpret_cast<const float*>(packed + off); }
 
+// dynamic shared memory of umma_gemm_kernel: 8 x 16 KB of operand slots (4 A + 4 W stages, or resident W + up to 8 A stages),
+// 64 KB of output staging, the shift-MMA operands, epilogue constants, barriers
+static size_t gemm_smem_bytes() {
+  return 1024 + kC1Stages * (kStageA + kStageW) + 4 * kStageA + kStageA + kStageW + 2 * 192 * 4 +
+         (3 * kC1StagesMax + 2 * kC1Acc + 4) * 8 + 16;
+}
+// weights-resident mode: K <= 256 and a single N tile; the A stages take the operand slots the weights leave free
+static void gemm_pipeline(GemmParams& g) {
+  static const bool on = [] { const char* v = getenv("TCVN_C1_WRES"); return !(v && v[0] == '0'); }();
+  g.wres = on && g.kchunks <= 4 && g.n_tiles_n == 1 ? 1 : 0;
+  g.stages = kC1Stages;
+  if (g.wres) {
+    const int slots = 2 * kC1Stages - g.kchunks;
+    g.stages = slots < kC1StagesMax ? slots : kC1StagesMax;
+  }
+}
+
 int launch_gemm(bool transform, const void* A, long long rows, int a_cols, int a_pitch, const void* W, int w_rows,
                        int kpad, int kphys, const float* a_scale, const float* a_shift, const float* a_alpha,
                        const float* o_shift, const float* o_alpha, void* out, int out_cols, int out_pitch, int n_tiles_n,
                        int Hp, int Wp, cudaStream_t st, double* stats, int* stat_slots) {
   if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one chunk");
   if (stats != nullptr && n_tiles_n != 1) return fail(TCVN_ERR_UNSUPPORTED, "epilogue statistics need a single N tile");
-  const size_t smem = 1024 + kC1Stages * (kStageA + kStageW) + 4 * kStageA + kStageA + kStageW + 2 * 192 * 4 +
-                      (3 * kC1Stages + 4) * 8 + 16;
+  const size_t smem = gemm_smem_bytes();
   bool& attr_done = device_flag(1);   // per device: the attribute belongs to the device's copy of the function
   if (!attr_done) {
     TCVN_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -757,6 +798,7 @@ int launch_gemm(bool transform, const void* A, long long rows, int a_cols, int a
   g.Hp = Hp; g.Wp = Wp;
   g.stats = stats;
   g.num_tiles = (int)ceil_div_ll(rows, kTileM) * n_tiles_n;
+  gemm_pipeline(g);
   const int grid = g.num_tiles < sm_count() ? g.num_tiles : sm_count();
   if (stat_slots) *stat_slots = 2 * grid;
   static const bool mma_shift_on = [] { const char* v = getenv("TCVN_MMA_SHIFT"); return !(v && v[0] == '0'); }();
@@ -779,8 +821,7 @@ int launch_gemm_shifted(const void* A, long long rows, int a_cols, int n_taps, c
   if (a_pitch <= 0) a_pitch = a_cols;
   if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one chunk");
   if (a_cols % 64 || x2_cols % 64 || n_taps < 1 || n_taps > 9) return fail(TCVN_ERR_ARG, "launch_gemm_shifted: bad shape");
-  const size_t smem = 1024 + kC1Stages * (kStageA + kStageW) + 4 * kStageA + kStageA + kStageW + 2 * 192 * 4 +
-                      (3 * kC1Stages + 4) * 8 + 16;
+  const size_t smem = gemm_smem_bytes();
   bool& attr_done = device_flag(1);
   if (!attr_done) {
     TCVN_CUDA(cudaFuncSetAttribute(umma_gemm_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -805,6 +846,7 @@ int launch_gemm_shifted(const void* A, long long rows, int a_cols, int n_taps, c
   g.a_scale = g.a_shift = g.a_alpha = nullptr; g.o_shift = bias; g.o_alpha = ones;
   g.Hp = Hp; g.Wp = Wp; g.stats = nullptr;
   g.num_tiles = (int)ceil_div_ll(rows, kTileM) * n_tiles_n;
+  gemm_pipeline(g);
   const int grid = g.num_tiles < sm_count() ? g.num_tiles : sm_count();
   if (n_tiles_n == 1) umma_gemm_kernel<false, true><<<grid, kC1Threads, smem, st>>>(tmA, tmW, tmO, tmX, g);
   else umma_gemm_kernel<false, false><<<grid, kC1Threads, smem, st>>>(tmA, tmW, tmO, tmX, g);
@@ -825,12 +867,12 @@ int umma_dense_layer_part(const CnnPlan& P, const BlockPlan& B, const LayerPlan&
                 P.mid, P.d.growth);
   if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one chunk");
   // ---- conv1 (BN2 scale is folded into the bf16 weights by pack.cu; the epilogue adds the folded shift)
-  if (which & 1) TCVN_TRY(launch_gemm(true, blk, rows, B.ctot, B.ctot, pk + L.p_w1, kMid, L.kpad, L.kphys, pf(pk, L.p_a_scale),
+  if (which & 1) TCVN_TRY(launch_gemm(true, blk, rows, B.ctot, B.ld, pk + L.p_w1, kMid, L.kpad, L.kphys, pf(pk, L.p_a_scale),
                        pf(pk, L.p_a_shift), pf(pk, L.p_a_alpha), pf(pk, L.p_o_shift), pf(pk, L.p_o_alpha), mid, kMid, kMid,
                        1, B.Hp, B.Wp, st));
   // ---- conv2
   if (!(which & 2)) return TCVN_OK;
-  return umma_conv2_fwd(mid, rows, pk + L.p_w2, pf(pk, L.p_b2), blk, B.ctot, L.kphys, B.Hp, B.Wp, B.W, st);
+  return umma_conv2_fwd(mid, rows, pk + L.p_w2, pf(pk, L.p_b2), blk, B.ld, L.kphys, B.Hp, B.Wp, B.W, st);
 }
 
 // out[:, col0 : col0+32] = conv3x3(mid) + bias over the ringed layout; mid bf16 [rows][128] activated with a zero ring,
@@ -883,7 +925,7 @@ int umma_conv2_fwd(const void* mid, long long rows, const void* w2, const float*
 int umma_transition(const CnnPlan& P, const BlockPlan& B, const BlockPlan& Nx, const char* pk, const void* pool,
                     void* next_blk, long long rows, cudaStream_t st) {
   return launch_gemm(false, pool, rows, B.ctot, B.ctot, pk + B.p_tw16, B.tn_tiles * kMid, B.tkpad, B.ctot, nullptr,
-                     nullptr, nullptr, pf(pk, B.p_tb16), pf(pk, B.p_ta16), next_blk, Nx.ctot, Nx.ctot, B.tn_tiles, Nx.Hp,
+                     nullptr, nullptr, pf(pk, B.p_tb16), pf(pk, B.p_ta16), next_blk, Nx.ctot, Nx.ld, B.tn_tiles, Nx.Hp,
                      Nx.Wp, st);
 }
 
