@@ -388,26 +388,29 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
 #pragma unroll
     for (int q = 0; q < 8; ++q) { st1[q] = 0.f; st2[q] = 0.f; }
     const int e_col = threadIdx.x - (10 + 4 * grp) * 32;
+    // epilogue constants of N tile nt -> shared memory (shift fp32, PReLU slopes as packed bf16 pairs).  With a single N
+    // tile (every conv1) they are loaded once; per tile, their L2 latency sat in front of every tile of an epilogue-bound
+    // group (the K = 64 layers).
+    auto load_consts = [&](int nt) {
+      if (!MMASHIFT) s_shift[e_col] = __ldg(p.o_shift + nt * p.ntile + e_col);
+      if (e_col < kMid / 2) {
+        const float2 a = __ldg(reinterpret_cast<const float2*>(p.o_alpha + nt * p.ntile) + e_col);
+        const __nv_bfloat162 a2 = __floats2bfloat162_rn(a.x, a.y);
+        s_alpha2[e_col] = *reinterpret_cast<const uint32_t*>(&a2);
+      }
+    };
+    if (p.n_tiles_n == 1) load_consts(0);   // visible to the group after the first named barrier below
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
       if ((it & 1) != grp) continue;
       const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
       const long long m = (long long)mt * kTileM + row;
       bool ring = false;
       {
-        const int rr = (int)(m % R);
-        const int y = rr / p.Wp, x = rr - y * p.Wp;
-        ring = y == 0 || y == p.Hp - 1 || x == 0 || x == p.Wp - 1;
+        const uint32_t rr = (uint32_t)m % (uint32_t)R;   // m < 2^31 (checked by the launcher): 32-bit division
+        const uint32_t y = rr / (uint32_t)p.Wp, x = rr - y * (uint32_t)p.Wp;
+        ring = y == 0 || y == (uint32_t)p.Hp - 1 || x == 0 || x == (uint32_t)p.Wp - 1;
       }
-      // this tile's epilogue constants -> shared memory (shift fp32, PReLU slopes as packed bf16 pairs)
-      {
-        const int e = threadIdx.x - (10 + 4 * grp) * 32;  // 0..127
-        if (!MMASHIFT) s_shift[e] = __ldg(p.o_shift + nt * p.ntile + e);
-        if (e < kMid / 2) {
-          const float2 a = __ldg(reinterpret_cast<const float2*>(p.o_alpha + nt * p.ntile) + e);
-          const __nv_bfloat162 a2 = __floats2bfloat162_rn(a.x, a.y);
-          s_alpha2[e] = *reinterpret_cast<const uint32_t*>(&a2);
-        }
-      }
+      if (p.n_tiles_n != 1) load_consts(nt);
       const int acc = grp + 2 * (mine & 1);
       const uint32_t acc_phase = (uint32_t)(mine >> 1) & 1u;
       ++mine;
