@@ -587,6 +587,7 @@ def run_ours(args):
         if launches_timed == 0:    # graph replay: the library's host-side counter does not tick; one replay = the captured launches
             launches_timed = net.graph_launches_per_replay * args.steps
         sampler.stop_flag.set()
+        sampler.join(timeout=6)   # an nvidia-smi query still in flight holds driver locks: it cost the host-driven e2e loop up to 25 % in one run out of four
         for _ in range(2):
             step_e2e()
         ms_e2e = timed(step_e2e, args.steps)

@@ -209,7 +209,7 @@ inline bool CnnPlan::build(const tcvn_cnn_desc& d, tcvn_precision prec, int n_im
   // 1536 MB 10.6k, 3072 MB 10.5k): 48 MB 5.3k, 80 MB 6.6k, 160 MB 7.7k, 320 MB 8.7k, 768 MB 9.3k, 1024 MB 9.3k events/s - the
   // layer kernels are issue/latency-bound, not HBM-bound, so keeping a chunk inside the 126 MB L2 buys nothing
   // yet and long persistent launches win; revisit when the kernels approach the memory roofline.
-  size_t l2_budget = (size_t)1536 << 20;
+  size_t l2_budget = (size_t)6144 << 20;   // re-measured after conv1 became bandwidth-bound: 768 MB 20.0-20.3 ms, 1536 MB 19.65-19.86, 3072 MB 19.6-19.9, 6144 MB 19.46-19.5 per 256-event step
   if (const char* e = getenv("TCVN_L2_BUDGET_MB")) { const int mb = atoi(e); if (mb > 0) l2_budget = (size_t)mb << 20; }
   // tiles of the two persistent kernels of a dense layer (128 / 126 rows) over `c` images: fraction of the
   // last wave of 148 CTAs that does useful work

@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;                                   // [stages][16 KB]
   uint8_t* sW = smem + p.stages * kStageA;              // [stages][16 KB], or [kchunks][16 KB] resident
-  uint8_t* sOut = sW + (p.wres ? p.kchunks : p.stages) * kStageW;   // [2 groups][2 halves][128 rows x 128 B], swizzled
+  uint8_t* sOut = sW + (p.wres ? p.kchunks * p.n_tiles_n : p.stages) * kStageW;   // [2 groups][2 halves][128 rows x 128 B], swizzled
   uint8_t* sXA = sOut + 4 * kStageA;                    // [128 rows x 128 B]: k0 = k1 = 1.0, rest 0   (MMASHIFT)
   uint8_t* sXB = sXA + kStageA;                         // [128 n x 128 B]: k0 = hi(shift[n]), k1 = lo(shift[n])
   float* s_epi = reinterpret_cast<float*>(sXB + kStageW);  // [2 groups][128 shift + 64 packed slopes]
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
   uint64_t* empty = bars + 2 * kC1StagesMax;   // MMA -> TMA
   uint64_t* tfull = bars + 3 * kC1StagesMax;   // MMA -> epilogue   [kC1Acc]
   uint64_t* tempty = tfull + kC1Acc;        // epilogue -> MMA   [kC1Acc]
-  uint64_t* wfull = tempty + kC1Acc;           // resident weight chunk kc has landed   [4]
+  uint64_t* wfull = tempty + kC1Acc;           // resident weight slot (nt, kc) has landed   [4]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -242,11 +242,13 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
   if (warp == 0) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      if (p.wres) {   // one barrier per chunk: the first tile's MMAs start as soon as THEIR chunk is there
-        for (int kc = 0; kc < p.kchunks; ++kc) {
-          ptx::mbar_arrive_expect_tx(&wfull[kc], p.ntile * 128);
-          ptx::tma_load_2d(sW + kc * kStageW, &tmW, &wfull[kc], kc * 64, 0);
-        }
+      if (p.wres) {   // one barrier per slot: the first tile's MMAs start as soon as THEIR chunk is there
+        for (int n = 0; n < p.n_tiles_n; ++n)
+          for (int kc = 0; kc < p.kchunks; ++kc) {
+            const int slot = n * p.kchunks + kc;
+            ptx::mbar_arrive_expect_tx(&wfull[slot], p.ntile * 128);
+            ptx::tma_load_2d(sW + slot * kStageW, &tmW, &wfull[slot], kc * 64, n * p.ntile);
+          }
       }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int mt = tile / p.n_tiles_n, nt = tile - mt * p.n_tiles_n;
@@ -271,7 +273,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
       const uint32_t idesc = ptx::umma_idesc_bf16(kTileM, p.ntile);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      bool w_pending = p.wres != 0;
+      uint32_t w_seen = p.wres ? 0u : 0xffu;   // resident weight slots this thread has already waited for
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
@@ -281,10 +283,11 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
                          ptx::umma_desc_join(ptx::kUmmaDescHiSw128, ptx::umma_desc_lo(ptx::smem_u32(sXB))), idesc, 0);
         for (int kc = 0; kc < p.kchunks; ++kc) {
           ptx::mbar_wait(TRANSFORM ? &ready[stage] : &full[stage], phase);
-          if (w_pending) ptx::mbar_wait(&wfull[kc], 0);
+          const int wslot = p.wres ? (tile % p.n_tiles_n) * p.kchunks + kc : stage;
+          if (!((w_seen >> wslot) & 1u)) { ptx::mbar_wait(&wfull[wslot], 0); w_seen |= 1u << wslot; }
           ptx::tc_fence_after();
           const uint32_t a_lo = ptx::umma_desc_lo(ptx::smem_u32(sA + stage * kStageA));
-          const uint32_t w_lo = ptx::umma_desc_lo(ptx::smem_u32(sW + (p.wres ? kc : stage) * kStageW));
+          const uint32_t w_lo = ptx::umma_desc_lo(ptx::smem_u32(sW + wslot * kStageW));
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             ptx::umma_bf16(d_tmem, ptx::umma_desc_join(ptx::kUmmaDescHiSw128, a_lo + 2 * k),
@@ -292,7 +295,6 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
           ptx::umma_commit(&empty[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        w_pending = false;
         ptx::umma_commit(&tfull[acc]);
         if (++acc == kC1Acc) { acc = 0; acc_phase ^= 1; }
       }
@@ -762,13 +764,13 @@ static size_t gemm_smem_bytes() {
   return 1024 + kC1Stages * (kStageA + kStageW) + 4 * kStageA + kStageA + kStageW + 2 * 192 * 4 +
          (3 * kC1StagesMax + 2 * kC1Acc + 4) * 8 + 16;
 }
-// weights-resident mode: K <= 256 and a single N tile; the A stages take the operand slots the weights leave free
+// weights-resident mode: at most four 16 KB weight slots (N tiles x K chunks); the A stages take the slots the weights leave free
 static void gemm_pipeline(GemmParams& g) {
   static const bool on = [] { const char* v = getenv("TCVN_C1_WRES"); return !(v && v[0] == '0'); }();
-  g.wres = on && g.kchunks <= 4 && g.n_tiles_n == 1 ? 1 : 0;
+  g.wres = on && g.kchunks * g.n_tiles_n <= 4 ? 1 : 0;
   g.stages = kC1Stages;
   if (g.wres) {
-    const int slots = 2 * kC1Stages - g.kchunks;
+    const int slots = 2 * kC1Stages - g.kchunks * g.n_tiles_n;
     g.stages = slots < kC1StagesMax ? slots : kC1StagesMax;
   }
 }
