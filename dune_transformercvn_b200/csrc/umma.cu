@@ -63,11 +63,16 @@ int make_map(const void* base, long long rows, int cols, int pitch, int box_cols
   cuuint64_t gstride[1] = {(cuuint64_t)pitch * sizeof(bf16)};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
+  // L2 promotion NONE: a 256-byte promotion fetches the neighbouring line of every 128-byte box row whose line is the lower
+  // half of a 256-byte block - for the block buffers, where a layer reads the first K channels of wider rows, that was 445 MB
+  // of DRAM reads for 356 MB needed (ncu).  For maps whose rows are whole blocks read half by half (mid and its gradients)
+  // promotion would be a free prefetch; measured (scripts/gpu_round2_promo3.sh): no difference, so one setting for all.
+  // TCVN_TMAP_PROMO = 128 / 256 forces another one (A/B).
   static const CUtensorMapL2promotion promo = [] {
     const char* v = getenv("TCVN_TMAP_PROMO");
     const int n = v ? atoi(v) : 0;
-    return n == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : n == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-         : n == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    return n == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : n == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+         : n == 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
   }();
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -465,7 +470,8 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
         if (p.ntile > 64) ptx::tma_store_2d(&tmO, stg + kStageA, nt * p.ntile + 64, mt * kTileM);
         ptx::tma_store_commit();
       }
-      if (p.stats != nullptr) {
+      if (MMASHIFT && p.stats != nullptr) {   // (statistics need the single-N-tile form, which is the MMASHIFT one: the other
+                                              // instantiations drop the accumulators - they spilled registers for nothing)
         // statistics of exactly the bf16 values being stored, read back from the staged tile 8 columns (16 bytes) at a
         // time: thread e owns column group e & 15 on rows (e >> 4) + 8 i.  (One column per thread cost 128 two-byte
         // loads per tile - as many LSU wavefronts as the operand transform - and made the train-mode kernel 35 % slower
@@ -490,7 +496,7 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
       }
     }
     if (issuer) ptx::tma_store_wait_all();
-    if (p.stats != nullptr) {
+    if (MMASHIFT && p.stats != nullptr) {
       // per-group reduction through the (now idle) staging tile in a fixed order, then one store per column into the slot
       ptx::named_bar_sync(1 + grp, 128);          // the issuer's stores have drained the staging tile
       float* red = reinterpret_cast<float*>(stg);  // [128 threads][16]
@@ -781,6 +787,8 @@ int launch_gemm(bool transform, const void* A, long long rows, int a_cols, int a
                        int Hp, int Wp, cudaStream_t st, double* stats, int* stat_slots) {
   if (rows >= (1ll << 31) - 4096) return fail(TCVN_ERR_UNSUPPORTED, "more than 2^31 rows in one chunk");
   if (stats != nullptr && n_tiles_n != 1) return fail(TCVN_ERR_UNSUPPORTED, "epilogue statistics need a single N tile");
+  if (stats != nullptr && getenv("TCVN_MMA_SHIFT") && getenv("TCVN_MMA_SHIFT")[0] == '0')
+    return fail(TCVN_ERR_UNSUPPORTED, "epilogue statistics live in the shift-MMA form of the kernel (unset TCVN_MMA_SHIFT=0)");
   const size_t smem = gemm_smem_bytes();
   bool& attr_done = device_flag(1);   // per device: the attribute belongs to the device's copy of the function
   if (!attr_done) {
