@@ -48,6 +48,39 @@ def test_host_side_size_queries_match_python_inventory():
     assert b"descriptor" in L.tcvn_last_error()
 
 
+def test_eval_workspace_uses_line_aligned_block_rows():
+    """The eval walk keeps every dense-block buffer on a row pitch of whole 128-byte lines (plan.h: BlockPlan::ld = channels
+    rounded up to 64; csrc/umma.cu: a 64-channel TMA box row is then exactly one line).  Host-only size query: the bf16
+    workspace for n images must hold, per image, the five block buffers at that pitch plus the 128-channel bottleneck map of
+    the largest block - and not much more."""
+    L = tl.load()
+    d = tl.CnnDesc()
+    d.in_channels, d.init_features, d.growth, d.bn_size, d.num_blocks = 3, 64, 32, 4, 5
+    layers = (3, 6, 12, 6, 3)
+    for i, n in enumerate(layers):
+        d.block_layers[i] = n
+    d.out_features, d.height, d.width, d.bn_eps = 256, 400, 280, 1e-5
+    n = 8
+    h, w = ((400 - 1) // 2 + 1 - 3) // 2 + 1, ((280 - 1) // 2 + 1 - 3) // 2 + 1   # stem conv s2, then AvgPool(3, 2): 99 x 69
+    c, need, padded_only = 64, 0, 0
+    rows0 = (h + 2) * (w + 2)
+    for b, nl in enumerate(layers):
+        c0p = (c + 7) // 8 * 8
+        ctot = c0p + nl * 32
+        ld = (ctot + 63) // 64 * 64
+        assert ld % 64 == 0 and ld >= ctot
+        rows = (h + 2) * (w + 2)
+        need += n * rows * ld * 2
+        padded_only += n * rows * (ld - ctot) * 2
+        c = (c + nl * 32) // 2
+        h, w = h // 2, w // 2
+    need += n * rows0 * 128 * 2                     # bottleneck map of block 1
+    got = L.tcvn_cnn_workspace_bytes(C.byref(d), tl.TCVN_BF16, n)
+    assert got >= need, (got, need)
+    assert got < need * 1.5, (got, need)             # pooled scratch, gap vector, hit offsets: small next to the maps
+    assert padded_only > 0                           # the tutorial network does have unaligned channel totals (160, 272, ...)
+
+
 def test_bad_arguments_are_reported_not_crashed():
     L = tl.load()
     rc = L.tcvn_densify(None, None, 0, 5, 3, 2, 400, 280, C.c_float(255.0), None, 0, None)
