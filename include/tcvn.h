@@ -117,7 +117,10 @@ size_t tcvn_cnn_packed_bytes(const tcvn_cnn_desc* d, tcvn_precision prec);
  * converts to bf16 for TCVN_BF16.  Runs on the stream; call again after the weights change. */
 int tcvn_cnn_pack(const tcvn_cnn_desc* d, tcvn_precision prec, const float* arena, void* packed,
                   size_t packed_bytes, tcvn_stream_t stream);
-/* workspace for a forward pass over n_images images */
+/* workspace for a forward pass over n_images images.  Layout (csrc/plan.h): one ringed NHWC buffer per dense block, rows
+ * padded to whole 128-byte lines (channel total rounded up to 64: a 64-channel TMA box row is then exactly one line; the
+ * pad channels are never written or read), the 128-channel bottleneck map, pooling scratch.  Images are walked in chunks
+ * sized by a working-set budget (6 GB by default, TCVN_L2_BUDGET_MB), so the size grows with n_images only up to the chunk. */
 size_t tcvn_cnn_workspace_bytes(const tcvn_cnn_desc* d, tcvn_precision prec, int n_images);
 /* eval-mode forward: pixels (n_images, in_channels, height, width) fp32 NCHW  ->
  * embedding (n_images, out_features) fp32.  The workspace must have been zero-filled once
