@@ -272,6 +272,10 @@ __global__ void __launch_bounds__(kC1Threads, 1) umma_gemm_kernel(const __grid_c
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
+      // a CTA does not visit every N tile (gridDim.x is a multiple of n_tiles_n more often than not), so the MMA thread may
+      // never wait for some resident weight slots: no bulk copy into this CTA's shared memory may be in flight when it exits
+      if (p.wres)
+        for (int slot = 0; slot < p.n_tiles_n * p.kchunks; ++slot) ptx::mbar_wait(&wfull[slot], 0);
     }
   } else if (warp == 1) {
     if (lane == 0) {
