@@ -634,7 +634,7 @@ def run_ours(args):
                     "frac": tflops / pk["bf16_sustained"], "traffic": None, "kernel": "whole DenseNet forward (fp32 path)"}
     cpu = None
     eager = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # the CPU baseline is reported at N = 1 only
         v, cms, cores, sample = time_cpu_reference(REFERENCE_SAMPLE_EVENTS, 3, 1, 1234)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
         if world == 1:
