@@ -136,7 +136,7 @@ namespace tcvn {
 //               bf16 -> swizzled staging tile -> TMA store
 // ------------------------------------------------------------------------------------------------
 constexpr int kC1Stages = 4;     // pipeline stages when the weights stream with the activations (one A + one W chunk per stage)
-constexpr int kC1StagesMax = 8;  // ... and when the weights are resident (K <= 256, one N tile): the 16 KB W slots become A stages
+constexpr int kC1StagesMax = 8;  // ... and when the weights are resident (at most four (N tile, K chunk) slots): the 16 KB W slots they leave free become A stages
 constexpr int kC1Acc = 4;       // TMEM accumulators (all 512 columns): the MMA warp runs up to two tiles ahead of each epilogue group
 constexpr int kC1Threads = 576;
 constexpr int kTileM = 128;
@@ -165,8 +165,9 @@ struct GemmParams {
   // the BatchNorm that follows (n_tiles_n == 1).  Every (CTA, epilogue group) stores its partial sums in its own slot,
   // stats[(2 * cta + group)][2][128]; the consumer adds the slots in a fixed order (no atomics: bit-reproducible).
   double* stats;
-  // weights-resident mode (kchunks <= 4, one N tile: every conv1 of dense blocks 1-2): the whole [128 x K] weight matrix is
-  // loaded once per CTA and the pipeline has `stages` A-only stages.  The clock-stamp trace of the streaming form showed a
+  // weights-resident mode (N tiles x K chunks <= 4: every conv1 of dense blocks 1-2, the first transition, the conv1
+  // input-gradient GEMMs up to K = 256): the whole weight matrix is loaded once per CTA, slot (nt, kc), and the pipeline has
+  // `stages` A-only stages.  The clock-stamp trace of the streaming form showed a
   // stage cycle of 3.2 us (1.2-2.2 us of it TMA latency under load) with 4 stages in flight: 0.8 us per chunk, below what
   // HBM delivers - the kernel was bound by bytes in flight, not by bandwidth, the epilogue or the tensor pipe.
   int wres, stages;
